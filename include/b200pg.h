@@ -1,0 +1,277 @@
+/*
+ * b200pg.h -- C-ABI boundary of the B200-native guided path tracer.
+ *
+ * This header is the drop-in boundary for the reference's integrator plugin
+ * interface (C++-ABI there):
+ *
+ *   reference                                              here
+ *   ---------------------------------------------------    --------------------------
+ *   MTS_EXPORT_PLUGIN / CreateInstance(const Properties&)  b200pg_integrator_create
+ *     include/mitsuba/core/cobject.h:99-107
+ *   Integrator::preprocess / render / postprocess          b200pg_render
+ *     include/mitsuba/render/integrator.h:61-107
+ *   Integrator::cancel (async)                             b200pg_cancel
+ *     include/mitsuba/render/integrator.h:86
+ *   Film::put / Film::develop / Film::getStorage           b200pg_film_read / _write
+ *     include/mitsuba/render/film.h:51, src/films/hdrfilm.cpp:391-546
+ *   SceneHandler (XML -> objects)                          b200pg_scene_load_xml
+ *     src/librender/scenehandler.cpp:197-760
+ *   Statistics (rays traced, avg. path length)             b200pg_stats
+ *     src/librender/skdtree.cpp:46-47, progressive_path.cpp:26
+ *   ProgressiveMonteCarloIntegrator pre/postprogression    b200pg_progression_* (training loop hooks)
+ *     include/mitsuba/render/progressiveintegrator.h:11-86
+ *
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ * All functions return 0 on success and a negative code on error unless noted;
+ * the message is available from b200pg_last_error() (thread-local).
+ */
+#ifndef B200PG_H
+#define B200PG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200PG_VERSION 100 /* 0.1.0 */
+
+/* ------------------------------------------------------------------ */
+/*  Scene description (flat POD). Field names follow the XML names of  */
+/*  the reference plugins wherever one exists.                         */
+/* ------------------------------------------------------------------ */
+
+enum B200pgShapeType { B200PG_SHAPE_RECTANGLE = 0, B200PG_SHAPE_TRIMESH = 1 };
+
+enum B200pgBsdfType {
+    B200PG_BSDF_DIFFUSE = 0,        /* src/bsdfs/diffuse.cpp        */
+    B200PG_BSDF_DIELECTRIC = 1,     /* src/bsdfs/dielectric.cpp     */
+    B200PG_BSDF_ROUGHCONDUCTOR = 2, /* src/bsdfs/roughconductor.cpp */
+    B200PG_BSDF_ROUGHPLASTIC = 3,   /* src/bsdfs/roughplastic.cpp   */
+    B200PG_BSDF_NULL = 4            /* src/bsdfs/null.cpp           */
+};
+
+enum B200pgDistribution { B200PG_DISTR_BECKMANN = 0, B200PG_DISTR_GGX = 1 };
+
+enum B200pgPhaseType { B200PG_PHASE_ISOTROPIC = 0, B200PG_PHASE_HG = 1 };
+
+enum B200pgMediumMethod { B200PG_MEDIUM_WOODCOCK = 0, B200PG_MEDIUM_SIMPSON = 1 };
+
+/* 4x4 row-major matrices everywhere (Matrix4x4 m[row][col], transform.h). */
+
+typedef struct B200pgShape {
+    int32_t type;            /* B200pgShapeType */
+    float to_world[16];      /* rectangle: objectToWorld incl. flipNormals (rectangle.cpp:79-84).
+                                trimesh: identity (vertices are already in world space). */
+    int32_t bsdf;            /* index into bsdfs, -1 = default per Shape::configure (shape.cpp:48-70) */
+    int32_t emitter;         /* index into emitters, -1 = none */
+    int32_t interior_medium; /* index into media, -1 = none */
+    int32_t exterior_medium;
+    uint32_t n_vertices, n_triangles; /* trimesh only */
+    const float *positions;           /* 3*n_vertices */
+    const float *normals;             /* 3*n_vertices or NULL (face normals) */
+    const float *texcoords;           /* 2*n_vertices or NULL */
+    const uint32_t *indices;          /* 3*n_triangles */
+} B200pgShape;
+
+typedef struct B200pgBsdf {
+    int32_t type;     /* B200pgBsdfType */
+    int32_t twosided; /* wrapped in a `twosided` adapter (twosided.cpp:117-195), same BRDF on both sides */
+    float reflectance[3];            /* diffuse `reflectance` / roughplastic `diffuseReflectance` */
+    float specular_reflectance[3];   /* `specularReflectance` */
+    float specular_transmittance[3]; /* `specularTransmittance` */
+    float int_ior, ext_ior;          /* dielectric / roughplastic */
+    float eta[3], k[3];              /* roughconductor (already divided by extEta) */
+    int32_t distribution;            /* B200pgDistribution */
+    float alpha_u, alpha_v;
+    int32_t sample_visible;          /* must be 1 (reference default, microfacet.h:138) */
+    int32_t nonlinear;               /* roughplastic */
+    /* roughplastic tabulated rough transmittance, reduced as rtrans.h:292-388 does
+       (filled by the scene loader; 100-entry 1-D table + scalars) */
+    float rt_ext_trans[100];
+    float rt_ext_diff;               /* external evalDiffuse (alpha, eta fixed) */
+    float rt_int_diff;               /* internal (1/eta) evalDiffuse(alpha) */
+} B200pgBsdf;
+
+typedef struct B200pgEmitter { /* `area`, src/emitters/area.cpp */
+    float radiance[3];
+    float sampling_weight;
+    int32_t shape; /* owning shape */
+} B200pgEmitter;
+
+typedef struct B200pgMedium { /* `heterogeneous` + `gridvolume`, src/medium/heterogeneous.cpp */
+    int32_t method;          /* B200pgMediumMethod */
+    float scale;             /* `scale` */
+    float albedo[3];         /* constvolume albedo */
+    int32_t phase_type;      /* B200pgPhaseType */
+    float phase_g;           /* hg `g` */
+    int32_t res[3];          /* grid resolution nx, ny, nz */
+    float aabb_min[3], aabb_max[3];
+    float to_world[16];      /* volume toWorld (identity supported) */
+    const float *density;    /* nx*ny*nz float32, x fastest (gridvolume.cpp:56-89) */
+    float step_size_multiplier; /* `stepSize` factor for simpson, 0 = auto */
+} B200pgMedium;
+
+typedef struct B200pgSensor { /* `perspective`, src/sensors/perspective.cpp */
+    float to_world[16];
+    float fov;          /* degrees */
+    int32_t fov_axis;   /* 0 = x, 1 = y, 2 = diagonal, 3 = smaller, 4 = larger */
+    float near_clip, far_clip;
+    int32_t medium;     /* index or -1: medium the camera sits in */
+} B200pgSensor;
+
+typedef struct B200pgFilm { /* `hdrfilm` + `gaussian` rfilter */
+    int32_t width, height;
+    float filter_stddev; /* gaussian stddev, radius = 4*stddev (gaussian.cpp:33-37) */
+} B200pgFilm;
+
+typedef struct B200pgSceneDesc {
+    int32_t n_shapes, n_bsdfs, n_emitters, n_media;
+    const B200pgShape *shapes;
+    const B200pgBsdf *bsdfs;
+    const B200pgEmitter *emitters;
+    const B200pgMedium *media;
+    B200pgSensor sensor;
+    B200pgFilm film;
+    int32_t sample_count; /* sampler `sampleCount` */
+    uint64_t seed;
+} B200pgSceneDesc;
+
+/* Integrator parameters. Names/defaults mirror the XML parameters of
+ * `progressivepath` / `progressivevolpath` (integrator.cpp:195-230,
+ * progressiveintegrator.cpp:296-300, progressive_path.cpp:117).
+ * Guiding parameters are this repo's own (the guided plugin is not in the
+ * reference snapshot). */
+typedef struct B200pgIntegratorParams {
+    int32_t max_depth;               /* maxDepth, -1 = infinite */
+    int32_t rr_depth;                /* rrDepth, default 5 */
+    int32_t strict_normals;          /* strictNormals */
+    int32_t hide_emitters;           /* hideEmitters */
+    int32_t samples_per_progression; /* samplesPerProgression, default 1 */
+    int32_t max_render_time;         /* maxRenderTime seconds, 0 = sample budget */
+    float max_component_value;       /* maxComponentValue, inf = no clamp */
+    int32_t use_nee;                 /* useNee */
+    int32_t volumetric;              /* 0 = progressivepath, 1 = progressivevolpath */
+    /* guiding */
+    int32_t guiding;                 /* 0 = off */
+    int32_t training_progressions;   /* number of progressions that train the field */
+    float guiding_probability;       /* one-sample MIS selection probability (default .5) */
+    int32_t guide_max_components;    /* K <= 32 */
+    int32_t guide_max_cell_samples;  /* spatial split threshold */
+    int32_t guide_train_discard_film;/* 1 = training progressions do not contribute to the film */
+    int32_t guided_distance;         /* guided free-flight sampling in media */
+    int32_t max_batch_paths;         /* wavefront batch size (0 = auto) */
+} B200pgIntegratorParams;
+
+typedef struct B200pgStats {
+    uint64_t paths;          /* camera samples completed */
+    uint64_t normal_rays;    /* closest-hit queries ("Normal rays traced", skdtree.cpp:46) */
+    uint64_t shadow_rays;    /* any-hit queries ("Shadow rays traced", skdtree.cpp:47) */
+    uint64_t path_length_sum;/* sum of rRec.depth at termination (progressive_path.cpp:310) */
+    uint64_t kernel_launches;
+    double seconds_total;
+    double seconds_trace;    /* CUDA-event time in trace kernels */
+    double seconds_shade;
+    double seconds_film;
+    double seconds_train;
+    uint64_t bvh_nodes_visited; /* only filled by the counting trace variant */
+    uint64_t prims_tested;
+    uint64_t train_samples;
+    uint32_t guide_cells;
+    uint32_t progressions_done;
+} B200pgStats;
+
+/* ------------------------------------------------------------------ */
+/*  Entry points                                                       */
+/* ------------------------------------------------------------------ */
+
+int b200pg_version(void);
+const char *b200pg_last_error(void);
+
+void b200pg_integrator_params_default(B200pgIntegratorParams *p);
+
+/* Scene: either parsed from Mitsuba 0.6 XML (subset, scenehandler.cpp semantics)
+ * or handed over as flat arrays. The loader copies everything it needs. */
+void *b200pg_scene_load_xml(const char *path, const char *const *defines /* "k=v", NULL-terminated, may be NULL */,
+                            char *err, size_t errlen);
+void *b200pg_scene_from_arrays(const B200pgSceneDesc *desc);
+/* Borrowed view of the flat description owned by the scene handle (valid until destroy). */
+const B200pgSceneDesc *b200pg_scene_desc(void *scene);
+/* Integrator parameters found in the XML (defaults if the scene came from arrays). */
+int b200pg_scene_integrator_params(void *scene, B200pgIntegratorParams *out);
+void b200pg_scene_destroy(void *scene);
+
+void *b200pg_integrator_create(void *scene, const B200pgIntegratorParams *params, int device);
+int b200pg_render(void *integ); /* blocking: all progressions on this handle's device */
+int b200pg_cancel(void *integ); /* async-safe */
+
+/* Progression-granular control (what ProgressiveMonteCarloIntegrator::renderSamples does,
+ * progressiveintegrator.cpp:65-114). `first_sample`/`n_samples` select the per-pixel sample
+ * indices rendered by this call so that sample batches can be split across GPUs;
+ * `row_begin`/`row_end` restrict to an image band (tile partition). */
+int b200pg_progression_render(void *integ, int first_sample, int n_samples, int row_begin, int row_end);
+/* Training between progressions: bin this progression's path-vertex samples per cell and
+ * accumulate per-cell sufficient statistics on the device... */
+int b200pg_train_accumulate(void *integ);
+/* ...expose the statistics buffer for an external sum over ranks (NCCL allreduce)... */
+int b200pg_train_stats_buffer(void *integ, void **dev_ptr, size_t *n_floats);
+/* ...then refit mixtures (M-step) and split spatial cells; identical on every rank. */
+int b200pg_train_update(void *integ);
+
+int b200pg_film_clear(void *integ);
+int b200pg_film_device_buffer(void *integ, void **dev_ptr, size_t *n_floats); /* H*W*4: R,G,B,weight */
+int b200pg_film_read(void *integ, float *rgbaw /* H*W*5: R,G,B,alpha,weight (imageblock.h:131-138) */);
+int b200pg_film_develop(void *integ, float *rgb /* H*W*3 = RGB/weight, fmtconv.cpp:978-1005 */);
+int b200pg_film_write(void *integ, const char *path /* .pfm */);
+int b200pg_stats(void *integ, B200pgStats *out);
+void b200pg_destroy(void *integ);
+
+/* ------------------------------------------------------------------ */
+/*  Per-kernel entry points (HOST buffers in/out; copies are done       */
+/*  inside). Used by the parity tests and by bench.py's e2e leg.        */
+/* ------------------------------------------------------------------ */
+
+/* rays: n * 8 floats (ox,oy,oz,mint, dx,dy,dz,maxt). hits: n * 4 words (t,u,v as float; prim as u32,
+ * 0xFFFFFFFF = miss). prim ids are "global primitive ids": shapes in order, rectangle = 1 prim,
+ * trimesh = n_triangles prims (same numbering as ShapeKDTree, skdtree.cpp:53-104). */
+int b200pg_k_trace(void *integ, const float *rays, size_t n, int shadow, float *hits_tuv, uint32_t *hits_prim);
+/* Same with device pointers, returns elapsed kernel ms in *ms (CUDA events). counts (may be NULL): 2 u64
+ * (bvh nodes visited, prims tested) filled by the counting variant. */
+int b200pg_k_trace_device(void *integ, const void *d_rays, size_t n, int shadow, void *d_hits, float *ms,
+                          uint64_t *counts);
+
+/* BSDF eval/pdf/sample in local coordinates. wi, wo: n*3. u: n*2.
+ * out_eval n*3, out_pdf n, out_wo n*3, out_weight n*3, out_spdf n, out_flags n (sampled type bits). */
+int b200pg_k_bsdf(void *integ, int bsdf_index, const float *wi, const float *wo, const float *u, size_t n,
+                  float *out_eval, float *out_pdf, float *out_wo, float *out_weight, float *out_spdf,
+                  uint32_t *out_flags);
+
+/* Radiance of n camera samples with explicit (pixel, sample index) pairs: out n*3. Uses the same
+ * counter-based RNG as a full render, so results are comparable sample by sample. */
+int b200pg_k_radiance(void *integ, const uint32_t *pixel, const uint32_t *sample_index, size_t n, float *out_rgb);
+
+/* Film splat of n samples (pos n*2, rgb n*3) into a cleared film; read back with b200pg_film_read. */
+int b200pg_k_film_splat(void *integ, const float *pos, const float *rgb, size_t n);
+
+/* Medium: trilinear density lookups (p n*3 -> out n), see gridvolume.cpp:337-388. */
+int b200pg_k_grid_lookup(void *integ, int medium, const float *p, size_t n, float *out);
+
+/* Guiding field kernels (vMF mixtures; this repo's own algorithm, oracle-pinned).
+ * Field snapshot layout is documented in DESIGN.md. */
+int b200pg_k_vmm_pdf_sample(void *integ, const float *pos, const float *dir, const float *u, size_t n,
+                            float *out_pdf, float *out_dir, float *out_spdf, uint32_t *out_cell);
+/* Bin n samples (pos n*3) by guiding cell: out_cell n, out_perm n (stable order), out_offsets n_cells+1. */
+int b200pg_k_bin_samples(void *integ, const float *pos, size_t n, uint32_t *out_cell, uint32_t *out_perm,
+                         uint32_t *out_offsets, uint32_t *n_cells);
+/* One weighted-EM step over externally supplied samples (pos n*3, dir n*3, weight n, pdf n, dist n). */
+int b200pg_k_em_step(void *integ, const float *pos, const float *dir, const float *weight, const float *pdf,
+                     const float *dist, size_t n);
+/* Field snapshot: header + cells + mixtures (flat floats). Pass NULL to query the size. */
+int b200pg_field_snapshot(void *integ, float *out, size_t *n_floats);
+int b200pg_field_load(void *integ, const float *in, size_t n_floats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PG_H */

@@ -1,0 +1,406 @@
+// TEST INFRASTRUCTURE ONLY -- see oracle_math.h header note.
+//
+// oracle_scene.h: scene containers, SAH kd-tree (gkdtree.h rules), Havran traversal
+// (sahkdtree3.h:178-308), TriAccel (triaccel.h:37-158), rectangle (rectangle.cpp:125-168)
+// and intersection records (skdtree.h:343-428).
+#pragma once
+#include <cstdio>
+#include <memory>
+#include <vector>
+
+#include "../include/b200pg.h"
+#include "oracle_math.h"
+
+namespace orc {
+
+struct Ray {
+    Vec3 o, d, dRcp;
+    Float mint, maxt;
+    Ray() : mint(Epsilon), maxt(std::numeric_limits<Float>::infinity()) {}
+    Ray(const Vec3 &o_, const Vec3 &d_, Float mint_ = Epsilon, Float maxt_ = std::numeric_limits<Float>::infinity())
+        : o(o_), d(d_), mint(mint_), maxt(maxt_) {
+        dRcp = Vec3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);  // ray.h:  setDirection
+    }
+    Vec3 operator()(Float t) const { return o + d * t; }
+};
+
+struct AABB {
+    Vec3 min, max;
+    AABB() { reset(); }
+    void reset() {
+        min = Vec3(std::numeric_limits<Float>::infinity());
+        max = Vec3(-std::numeric_limits<Float>::infinity());
+    }
+    void expandBy(const Vec3 &p) {
+        for (int i = 0; i < 3; ++i) {
+            min[i] = std::min(min[i], p[i]);
+            max[i] = std::max(max[i], p[i]);
+        }
+    }
+    void expandBy(const AABB &b) {
+        expandBy(b.min);
+        expandBy(b.max);
+    }
+    Float surfaceArea() const {
+        Vec3 d = max - min;
+        return 2.0f * (d.x * d.y + d.x * d.z + d.y * d.z);
+    }
+    // aabb.h:308-338
+    bool rayIntersect(const Ray &ray, Float &nearT, Float &farT) const {
+        nearT = -std::numeric_limits<Float>::infinity();
+        farT = std::numeric_limits<Float>::infinity();
+        for (int i = 0; i < 3; i++) {
+            const Float origin = ray.o[i];
+            const Float minVal = min[i], maxVal = max[i];
+            if (ray.d[i] == 0) {
+                if (origin < minVal || origin > maxVal) return false;
+            } else {
+                Float t1 = (minVal - origin) * ray.dRcp[i];
+                Float t2 = (maxVal - origin) * ray.dRcp[i];
+                if (t1 > t2) std::swap(t1, t2);
+                nearT = std::max(t1, nearT);
+                farT = std::min(t2, farT);
+                if (!(nearT <= farT)) return false;
+            }
+        }
+        return true;
+    }
+};
+
+static const uint32_t KNoTriangleFlag = 0xFFFFFFFFu;
+
+// triaccel.h:37-94
+struct TriAccel {
+    uint32_t k;
+    Float n_u, n_v, n_d;
+    Float a_u, a_v, b_nu, b_nv;
+    Float c_nu, c_nv;
+    uint32_t shapeIndex, primIndex;
+
+    int load(const Vec3 &A, const Vec3 &B, const Vec3 &C) {
+        static const int waldModulo[4] = {1, 2, 0, 1};
+        Vec3 b = C - A, c = B - A, N = cross(c, b);
+        k = 0;
+        for (int j = 0; j < 3; j++)
+            if (std::abs(N[j]) > std::abs(N[k])) k = j;
+        uint32_t u = waldModulo[k], v = waldModulo[k + 1];
+        const Float n_k = N[k], denom = b[u] * c[v] - b[v] * c[u];
+        if (denom == 0) {
+            k = 3;
+            return 1;
+        }
+        n_u = N[u] / n_k;
+        n_v = N[v] / n_k;
+        n_d = dot(A, N) / n_k;
+        b_nu = b[u] / denom;
+        b_nv = -b[v] / denom;
+        a_u = A[u];
+        a_v = A[v];
+        c_nu = c[v] / denom;
+        c_nv = -c[u] / denom;
+        return 0;
+    }
+
+    // triaccel.h:96-158
+    bool rayIntersect(const Ray &ray, Float mint, Float maxt, Float &u, Float &v, Float &t) const {
+        Float o_u, o_v, o_k, d_u, d_v, d_k;
+        switch (k) {
+            case 0: o_u = ray.o[1]; o_v = ray.o[2]; o_k = ray.o[0]; d_u = ray.d[1]; d_v = ray.d[2]; d_k = ray.d[0]; break;
+            case 1: o_u = ray.o[2]; o_v = ray.o[0]; o_k = ray.o[1]; d_u = ray.d[2]; d_v = ray.d[0]; d_k = ray.d[1]; break;
+            case 2: o_u = ray.o[0]; o_v = ray.o[1]; o_k = ray.o[2]; d_u = ray.d[0]; d_v = ray.d[1]; d_k = ray.d[2]; break;
+            default: return false;
+        }
+        t = (n_d - o_u * n_u - o_v * n_v - o_k) / (d_u * n_u + d_v * n_v + d_k);
+        if (t < mint || t > maxt) return false;
+        const Float hu = o_u + t * d_u - a_u;
+        const Float hv = o_v + t * d_v - a_v;
+        u = hv * b_nu + hu * b_nv;
+        v = hu * c_nu + hv * c_nv;
+        return u >= 0 && v >= 0 && u + v <= 1.0f;
+    }
+};
+
+struct Shape {
+    int type;
+    int bsdf, emitter, interiorMedium, exteriorMedium;
+    // rectangle
+    Mat4 objectToWorld, worldToObject;
+    Frame frame;
+    Vec3 dpdu, dpdv;
+    Float invSurfaceArea;
+    // trimesh
+    std::vector<Vec3> positions, normals;
+    std::vector<Vec2> texcoords;
+    std::vector<uint32_t> indices;
+    std::vector<Float> areaCdf;  // DiscreteDistribution m_cdf (pmf.h)
+    uint32_t primOffset;         // first global primitive id
+    bool isMediumTransition() const { return interiorMedium >= 0 || exteriorMedium >= 0; }
+};
+
+struct Intersection {
+    Float t;
+    Vec3 p;
+    Vec3 geoN;      // geoFrame.n
+    Frame shFrame;
+    Vec2 uv;
+    Vec3 wi;
+    Vec3 dpdu;
+    int shape;
+    uint32_t primIndex;
+    bool isValid() const { return t != std::numeric_limits<Float>::infinity(); }
+    Vec3 toWorld(const Vec3 &v) const { return shFrame.toWorld(v); }
+    Vec3 toLocal(const Vec3 &v) const { return shFrame.toLocal(v); }
+};
+
+// DiscreteDistribution::sample / sampleReuse (pmf.h:124-188) over a normalized cdf
+inline size_t cdfSample(const std::vector<Float> &cdf, Float sampleValue) {
+    auto entry = std::lower_bound(cdf.begin(), cdf.end(), sampleValue);
+    size_t index = std::min(cdf.size() - 2, (size_t)std::max((ptrdiff_t)0, (ptrdiff_t)(entry - cdf.begin()) - 1));
+    while ((cdf[index + 1] - cdf[index]) == 0 && index < cdf.size() - 1) ++index;
+    return index;
+}
+inline size_t cdfSampleReuse(const std::vector<Float> &cdf, Float &sampleValue, Float &pdf) {
+    size_t index = cdfSample(cdf, sampleValue);
+    pdf = cdf[index + 1] - cdf[index];
+    sampleValue = (sampleValue - cdf[index]) / (cdf[index + 1] - cdf[index]);
+    return index;
+}
+inline Float cdfNormalize(std::vector<Float> &cdf) {  // pmf.h:98-112
+    Float sum = cdf[cdf.size() - 1];
+    if (sum > 0) {
+        Float normalization = 1.0f / sum;
+        for (size_t i = 1; i < cdf.size(); ++i) cdf[i] *= normalization;
+        cdf[cdf.size() - 1] = 1.0f;
+    }
+    return sum;
+}
+
+// ---------------------------------------------------------------------------
+// kd-tree: 8-byte nodes (gkdtree.h:452-582): leaf = {start|0x80000000, end};
+// inner = {(leftOffset << 2) | axis, split}; children adjacent (right = left + 1).
+// ---------------------------------------------------------------------------
+struct KDNode {
+    uint32_t a;
+    union {
+        float split;
+        uint32_t end;
+    };
+    bool isLeaf() const { return a & 0x80000000u; }
+    uint32_t primStart() const { return a & 0x7FFFFFFFu; }
+    uint32_t primEnd() const { return end; }
+    int axis() const { return a & 3u; }
+    uint32_t leftOffset() const { return (a & 0x7FFFFFFFu) >> 2; }
+};
+
+struct TraversalCounters {
+    uint64_t nodes = 0, indices = 0, prims = 0;
+};
+
+class KDTree {
+public:
+    // build defaults, gkdtree.h:734-744
+    Float traversalCost = 15, queryCost = 20, emptySpaceBonus = 0.9f;
+    uint32_t stopPrims = 6, maxBadRefines = 3, exactPrimThreshold = 65536, minMaxBins = 128;
+    int maxDepth = 0;
+
+    std::vector<KDNode> nodes;
+    std::vector<uint32_t> indices;
+    AABB aabb, tightAABB;
+
+    void build(const std::vector<AABB> &primBoxes) {
+        boxes = &primBoxes;
+        uint32_t n = (uint32_t)primBoxes.size();
+        aabb.reset();
+        for (uint32_t i = 0; i < n; ++i) aabb.expandBy(primBoxes[i]);
+        tightAABB = aabb;
+        if (maxDepth == 0) {
+            int lg = 0;
+            for (uint32_t v = n; v > 1; v >>= 1) ++lg;          // math::log2i
+            maxDepth = (int)(8 + 1.3f * lg);                    // gkdtree.h:986
+        }
+        maxDepth = std::min(maxDepth, 48);                      // MTS_KD_MAXDEPTH
+        nodes.clear();
+        indices.clear();
+        nodes.push_back(KDNode());
+        std::vector<uint32_t> all(n);
+        for (uint32_t i = 0; i < n; ++i) all[i] = i;
+        buildNode(0, all, aabb, 0, 0);
+        // enlarge after the build (gkdtree.h:1214-1219)
+        const Float eps = 1e-3f;
+        aabb.min = aabb.min - ((aabb.max - aabb.min) * eps + Vec3(eps));
+        aabb.max = aabb.max + ((aabb.max - aabb.min) * eps + Vec3(eps));
+        boxes = nullptr;
+    }
+
+private:
+    const std::vector<AABB> *boxes = nullptr;
+
+    struct Event {
+        Float pos;
+        int type;  // 0 = end, 1 = planar, 2 = start (ordering of gkdtree.h:1331-1377)
+        bool operator<(const Event &o) const { return pos < o.pos || (pos == o.pos && type < o.type); }
+    };
+
+    void makeLeaf(uint32_t nodeIdx, const std::vector<uint32_t> &prims) {
+        KDNode &nd = nodes[nodeIdx];
+        nd.a = 0x80000000u | (uint32_t)indices.size();
+        indices.insert(indices.end(), prims.begin(), prims.end());
+        nd.end = (uint32_t)indices.size();
+    }
+
+    inline Float sahCost(const AABB &box, int axis, Float split, uint32_t nL, uint32_t nR) const {
+        // SurfaceAreaHeuristic3 (sahkdtree3.h:39-84): probabilities = SA(child)/SA(node)
+        Vec3 d = box.max - box.min;
+        int a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
+        Float invSA = 1.0f / (d[0] * d[1] + d[1] * d[2] + d[0] * d[2]);
+        Float cross = d[a1] * d[a2], perim = d[a1] + d[a2];
+        Float pL = (cross + (split - box.min[axis]) * perim) * invSA;
+        Float pR = (cross + (box.max[axis] - split) * perim) * invSA;
+        Float cost = traversalCost + queryCost * (pL * nL + pR * nR);
+        if (nL == 0 || nR == 0) cost *= emptySpaceBonus;  // gkdtree.h:2039-2041
+        return cost;
+    }
+
+    void buildNode(uint32_t nodeIdx, std::vector<uint32_t> &prims, const AABB &box, int depth, uint32_t badRefines) {
+        uint32_t n = (uint32_t)prims.size();
+        if (n <= stopPrims || depth >= maxDepth) {  // gkdtree.h:1797-1800
+            makeLeaf(nodeIdx, prims);
+            return;
+        }
+        Float bestCost = std::numeric_limits<Float>::infinity(), bestSplit = 0;
+        int bestAxis = -1;
+        bool bestPlanarLeft = true;
+
+        if (n > exactPrimThreshold) {
+            // min-max binning (gkdtree.h:1792-1925): bins over the tight bounds of the node
+            AABB tight;
+            for (uint32_t p : prims) {
+                const AABB &b = (*boxes)[p];
+                for (int i = 0; i < 3; ++i) {
+                    tight.min[i] = std::min(tight.min[i], std::max(b.min[i], box.min[i]));
+                    tight.max[i] = std::max(tight.max[i], std::min(b.max[i], box.max[i]));
+                }
+            }
+            std::vector<uint32_t> minBins(minMaxBins), maxBins(minMaxBins);
+            for (int axis = 0; axis < 3; ++axis) {
+                Float lo = tight.min[axis], hi = tight.max[axis];
+                if (!(hi > lo)) continue;
+                std::fill(minBins.begin(), minBins.end(), 0u);
+                std::fill(maxBins.begin(), maxBins.end(), 0u);
+                Float invBin = (Float)minMaxBins / (hi - lo);
+                for (uint32_t p : prims) {
+                    const AABB &b = (*boxes)[p];
+                    int i0 = std::min((int)minMaxBins - 1, std::max(0, (int)((std::max(b.min[axis], lo) - lo) * invBin)));
+                    int i1 = std::min((int)minMaxBins - 1, std::max(0, (int)((std::min(b.max[axis], hi) - lo) * invBin)));
+                    minBins[i0]++;
+                    maxBins[i1]++;
+                }
+                uint32_t nL = 0, nR = n;
+                for (uint32_t i = 0; i + 1 < minMaxBins; ++i) {
+                    nL += minBins[i];
+                    nR -= maxBins[i];
+                    Float split = lo + (Float)(i + 1) * (hi - lo) / (Float)minMaxBins;
+                    if (!(split > box.min[axis] && split < box.max[axis])) continue;
+                    Float c = sahCost(box, axis, split, nL, nR);
+                    if (c < bestCost) {
+                        bestCost = c;
+                        bestAxis = axis;
+                        bestSplit = split;
+                        bestPlanarLeft = true;
+                    }
+                }
+            }
+        } else {
+            // exact sweep over sorted edge events (gkdtree.h:1954-2405)
+            std::vector<Event> ev;
+            ev.reserve(2 * n);
+            for (int axis = 0; axis < 3; ++axis) {
+                ev.clear();
+                for (uint32_t p : prims) {
+                    const AABB &b = (*boxes)[p];
+                    Float lo = std::max(b.min[axis], box.min[axis]), hi = std::min(b.max[axis], box.max[axis]);
+                    if (lo == hi) {
+                        ev.push_back({lo, 1});
+                    } else {
+                        ev.push_back({lo, 2});
+                        ev.push_back({hi, 0});
+                    }
+                }
+                std::sort(ev.begin(), ev.end());
+                uint32_t nL = 0, nR = n;
+                size_t i = 0;
+                while (i < ev.size()) {
+                    Float pos = ev[i].pos;
+                    uint32_t pEnd = 0, pPlanar = 0, pStart = 0;
+                    while (i < ev.size() && ev[i].pos == pos && ev[i].type == 0) { ++pEnd; ++i; }
+                    while (i < ev.size() && ev[i].pos == pos && ev[i].type == 1) { ++pPlanar; ++i; }
+                    while (i < ev.size() && ev[i].pos == pos && ev[i].type == 2) { ++pStart; ++i; }
+                    nR -= pPlanar + pEnd;
+                    if (pos > box.min[axis] && pos < box.max[axis]) {
+                        Float cL = sahCost(box, axis, pos, nL + pPlanar, nR);
+                        Float cR = sahCost(box, axis, pos, nL, nR + pPlanar);
+                        if (cL < bestCost || cR < bestCost) {  // planar prims to the cheaper side (:2050-2078)
+                            bestPlanarLeft = cL <= cR;
+                            bestCost = std::min(cL, cR);
+                            bestAxis = axis;
+                            bestSplit = pos;
+                        }
+                    }
+                    nL += pStart + pPlanar;
+                }
+            }
+        }
+
+        Float leafCost = n * queryCost;
+        if (bestAxis < 0) {
+            makeLeaf(nodeIdx, prims);
+            return;
+        }
+        if (bestCost >= leafCost) {  // "bad refines", gkdtree.h:1835-1843 / 2105-2112
+            if ((bestCost > 4 * leafCost && n < 16) || badRefines >= maxBadRefines) {
+                makeLeaf(nodeIdx, prims);
+                return;
+            }
+            ++badRefines;
+        }
+
+        std::vector<uint32_t> left, right;
+        for (uint32_t p : prims) {
+            const AABB &b = (*boxes)[p];
+            Float lo = std::max(b.min[bestAxis], box.min[bestAxis]), hi = std::min(b.max[bestAxis], box.max[bestAxis]);
+            if (lo == hi && lo == bestSplit) {
+                (bestPlanarLeft ? left : right).push_back(p);
+            } else {
+                if (lo < bestSplit) left.push_back(p);
+                if (hi > bestSplit) right.push_back(p);
+                if (lo >= bestSplit && hi <= bestSplit && !(lo == hi && lo == bestSplit)) {
+                    // degenerate sliver exactly on the plane handled above; nothing else can land here
+                }
+            }
+        }
+        if (left.size() == n && right.size() == n) {  // no progress at all
+            makeLeaf(nodeIdx, prims);
+            return;
+        }
+        std::vector<uint32_t>().swap(prims);
+        uint32_t leftIdx = (uint32_t)nodes.size();
+        nodes.push_back(KDNode());
+        nodes.push_back(KDNode());
+        nodes[nodeIdx].a = ((leftIdx - nodeIdx) << 2) | (uint32_t)bestAxis;
+        nodes[nodeIdx].split = bestSplit;
+        AABB lb = box, rb = box;
+        lb.max[bestAxis] = bestSplit;
+        rb.min[bestAxis] = bestSplit;
+        buildNode(leftIdx, left, lb, depth + 1, badRefines);
+        buildNode(leftIdx + 1, right, rb, depth + 1, badRefines);
+    }
+};
+
+struct IntersectionCache {  // skdtree.h:237-241
+    uint32_t shapeIndex, primIndex;
+    Float u, v;
+};
+
+struct Scene;  // fwd
+
+}  // namespace orc

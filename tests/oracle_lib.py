@@ -1,0 +1,161 @@
+"""ctypes wrapper around oracle/_build/liboracle.so (TEST INFRASTRUCTURE: the CPU oracle)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+from conftest import ROOT, load_package
+
+b200pg = load_package()
+A = b200pg._abi
+
+fp = C.POINTER(C.c_float)
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+
+
+def _f(a):
+    return a.ctypes.data_as(fp)
+
+
+def _u(a):
+    return a.ctypes.data_as(u32p)
+
+
+class Oracle:
+    def __init__(self, so=None):
+        so = so or os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+        self.lib = L = C.CDLL(so)
+        L.orc_scene_create.restype = C.c_void_p
+        L.orc_scene_create.argtypes = [C.POINTER(A.SceneDesc)]
+        L.orc_scene_destroy.argtypes = [C.c_void_p]
+        L.orc_kd_info.argtypes = [C.c_void_p, u64p]
+        L.orc_trace.argtypes = [C.c_void_p, fp, C.c_size_t, C.c_int, fp, u32p, u64p, C.c_int]
+        L.orc_trace_bruteforce.argtypes = [C.c_void_p, fp, C.c_size_t, fp, u32p]
+        L.orc_camera_rays.argtypes = [C.c_void_p, fp, C.c_size_t, fp]
+        L.orc_bsdf.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_size_t, fp, fp, fp, fp, fp, u32p]
+        L.orc_radiance.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), u32p, u32p, C.c_size_t, fp]
+        L.orc_film_splat.argtypes = [C.c_void_p, fp, fp, C.c_size_t, fp]
+        L.orc_render.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), C.c_int, C.c_int, C.c_int, C.c_int, fp,
+                                 C.c_int, u64p, C.POINTER(C.c_double)]
+        L.orc_rtrans_reduce.argtypes = [fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                        C.c_float, C.c_float, fp, fp, fp]
+        L.orc_num_threads.restype = C.c_int
+
+    def num_threads(self):
+        return self.lib.orc_num_threads()
+
+    # ---- rough transmittance tables
+    def rtrans_reduce(self, table, eta, alpha):
+        """table: dict from b200pg.rtrans.load_packed / load_dat (raw floats in file order)."""
+        ext = np.zeros(table["thetaN"], np.float32)
+        ed = C.c_float()
+        idf = C.c_float()
+        raw = np.ascontiguousarray(table["raw"], np.float32)
+        self.lib.orc_rtrans_reduce(_f(raw), table["etaN"], table["alphaN"], table["thetaN"], table["etaMin"],
+                                   table["etaMax"], table["alphaMin"], table["alphaMax"], eta, alpha, _f(ext),
+                                   C.byref(ed), C.byref(idf))
+        return ext, ed.value, idf.value
+
+    def scene(self, builder):
+        return OracleScene(self, builder)
+
+
+class OracleScene:
+    def __init__(self, orc, builder):
+        self.orc = orc
+        self.L = orc.lib
+        from b200pg import rtrans
+
+        def red(distr, eta, alpha):
+            return orc.rtrans_reduce(rtrans.load_packed(distr), eta, alpha)
+
+        self.desc, self._keep = builder.desc(rtrans_reduce=red)
+        self.h = self.L.orc_scene_create(C.byref(self.desc))
+        if not self.h:
+            raise RuntimeError("orc_scene_create failed")
+        self.W, self.H = builder.width, builder.height
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.orc_scene_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def kd_info(self):
+        out = (C.c_uint64 * 3)()
+        self.L.orc_kd_info(self.h, out)
+        return dict(nodes=out[0], indices=out[1], prims=out[2])
+
+    def trace(self, rays, shadow=False, nthreads=0):
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = rays.shape[0]
+        tuv = np.zeros((n, 3), np.float32)
+        prim = np.zeros(n, np.uint32)
+        cnt = (C.c_uint64 * 3)()
+        self.L.orc_trace(self.h, _f(rays), n, int(shadow), _f(tuv), _u(prim), cnt, nthreads)
+        return tuv, prim, dict(nodes=cnt[0], indices=cnt[1], prims=cnt[2])
+
+    def trace_bruteforce(self, rays):
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = rays.shape[0]
+        tuv = np.zeros((n, 3), np.float32)
+        prim = np.zeros(n, np.uint32)
+        self.L.orc_trace_bruteforce(self.h, _f(rays), n, _f(tuv), _u(prim))
+        return tuv, prim
+
+    def camera_rays(self, pos):
+        pos = np.ascontiguousarray(pos, np.float32)
+        rays = np.zeros((pos.shape[0], 8), np.float32)
+        self.L.orc_camera_rays(self.h, _f(pos), pos.shape[0], _f(rays))
+        return rays
+
+    def bsdf(self, index, wi, wo, u):
+        wi = np.ascontiguousarray(wi, np.float32)
+        wo = np.ascontiguousarray(wo, np.float32)
+        u = np.ascontiguousarray(u, np.float32)
+        n = wi.shape[0]
+        ev = np.zeros((n, 3), np.float32)
+        pdf = np.zeros(n, np.float32)
+        swo = np.zeros((n, 3), np.float32)
+        w = np.zeros((n, 3), np.float32)
+        spdf = np.zeros(n, np.float32)
+        fl = np.zeros(n, np.uint32)
+        r = self.L.orc_bsdf(self.h, index, _f(wi), _f(wo), _f(u), n, _f(ev), _f(pdf), _f(swo), _f(w), _f(spdf), _u(fl))
+        assert r == 0
+        return dict(eval=ev, pdf=pdf, wo=swo, weight=w, spdf=spdf, flags=fl)
+
+    def radiance(self, params, pixel, sample):
+        pixel = np.ascontiguousarray(pixel, np.uint32)
+        sample = np.ascontiguousarray(sample, np.uint32)
+        out = np.zeros((pixel.shape[0], 3), np.float32)
+        self.L.orc_radiance(self.h, C.byref(params), _u(pixel), _u(sample), pixel.shape[0], _f(out))
+        return out
+
+    def film_splat(self, pos, rgb):
+        pos = np.ascontiguousarray(pos, np.float32)
+        rgb = np.ascontiguousarray(rgb, np.float32)
+        film = np.zeros((self.H, self.W, 5), np.float32)
+        self.L.orc_film_splat(self.h, _f(pos), _f(rgb), pos.shape[0], _f(film))
+        return film
+
+    def render(self, params, first_sample=0, n_samples=1, rows=None, film=None, nthreads=0):
+        if film is None:
+            film = np.zeros((self.H, self.W, 5), np.float32)
+        st = (C.c_uint64 * 7)()
+        sec = C.c_double()
+        r0, r1 = rows if rows else (0, self.H)
+        self.L.orc_render(self.h, C.byref(params), first_sample, n_samples, r0, r1, _f(film), nthreads, st,
+                          C.byref(sec))
+        stats = dict(paths=st[0], normal_rays=st[1], shadow_rays=st[2], path_length_sum=st[3], kd_nodes=st[4],
+                     kd_indices=st[5], prim_tests=st[6], seconds=sec.value)
+        return film, stats
+
+
+def develop(film):
+    """RGB / weight (fmtconv.cpp:978-1005)."""
+    w = film[..., 4:5]
+    return np.where(w > 0, film[..., :3] / np.maximum(w, 1e-30), 0.0).astype(np.float32)
