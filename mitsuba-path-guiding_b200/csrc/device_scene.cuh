@@ -1,0 +1,316 @@
+// device_scene.cuh -- device view of the compiled scene, BVH traversal, primitive tests,
+// intersection records and area-light sampling.
+//
+// What each routine has to agree with in the reference (paths relative to the reference root):
+//   traceRay         closest / any hit as ShapeKDTree::rayIntersect (src/librender/skdtree.cpp:112-142, 207-226):
+//                    adaptive ray epsilon, [mint, maxt] interval, TriAccel test (include/mitsuba/render/triaccel.h:96-158),
+//                    rectangle test (src/shapes/rectangle.cpp:125-148). The accelerator is this repo's own BVH2
+//                    (the north star allows a rebuilt BVH); hit results do not depend on it.
+//   fillIntersection ShapeKDTree::fillIntersectionRecord<true> (include/mitsuba/render/skdtree.h:343-428),
+//                    Rectangle::fillIntersectionRecord (rectangle.cpp:155-168), computeShadingFrame (util.cpp:605-610)
+//   sampleEmitter    Scene::sampleEmitterDirect (src/librender/scene.cpp:871-895), AreaLight::sampleDirect
+//                    (src/emitters/area.cpp:158-173), Shape::sampleDirect (src/librender/shape.cpp:102-116)
+#pragma once
+#include "device_bsdf.cuh"
+#include "pg_types.h"
+
+namespace pg {
+
+struct DeviceScene {
+    const float4 *nodes;
+    const float4 *prims;
+    const float4 *rects;
+    const ShapeRecord *shapes;
+    const MeshRecord *meshes;
+    const float *positions;
+    const float *normals;
+    const float *texcoords;
+    const uint32_t *indices;
+    const float *areaCdf;
+    const BsdfRecord *bsdfs;
+    const EmitterRecord *emitters;
+    const float *emitterCdf;
+    const MediumRecord *media;
+    const float *density;
+    const uint32_t *primGlobalId;
+    uint32_t nEmitters;
+    uint32_t nPrims;
+    CameraRecord camera;
+    FilmRecord film;
+    uint64_t seed;
+};
+
+struct Hit {
+    float t, u, v;
+    uint32_t prim;  // index into DeviceScene::prims (BVH order), kMiss = none
+};
+
+// Ray interval exactly as ShapeKDTree::rayIntersect sets it up (skdtree.cpp:119-133 / 212-222):
+// an epsilon of exactly `Epsilon` is scaled by the largest origin coordinate.
+PG_DEV float adaptiveMinT(float3 o, float mint, bool shadow) {
+    if (mint == kEpsilon) {
+        float m = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
+        if (!shadow) m = fmaxf(m, kEpsilon);
+        mint *= m;
+    }
+    return mint;
+}
+
+template <bool kAnyHit, bool kCount>
+PG_DEV bool traceRay(const DeviceScene &S, float3 o, float3 d, float mint, float maxt, Hit &hit, uint32_t *cntNodes,
+                     uint32_t *cntPrims) {
+    const float3 idir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    int stack[64];
+    int sp = 0;
+    int node = 0;
+    hit.prim = kMiss;
+    hit.t = maxt;
+    float tmax = maxt;
+    while (true) {
+        if (node >= 0) {
+            const float4 n0 = __ldg(S.nodes + 4 * node + 0);
+            const float4 n1 = __ldg(S.nodes + 4 * node + 1);
+            const float4 n2 = __ldg(S.nodes + 4 * node + 2);
+            const float4 n3 = __ldg(S.nodes + 4 * node + 3);
+            if (kCount) (*cntNodes)++;
+            // slabs; fminf/fmaxf drop NaNs from 0*inf
+            float c0lox = (n0.x - o.x) * idir.x, c0hix = (n0.y - o.x) * idir.x;
+            float c0loy = (n0.z - o.y) * idir.y, c0hiy = (n0.w - o.y) * idir.y;
+            float c0loz = (n2.x - o.z) * idir.z, c0hiz = (n2.y - o.z) * idir.z;
+            float c1lox = (n1.x - o.x) * idir.x, c1hix = (n1.y - o.x) * idir.x;
+            float c1loy = (n1.z - o.y) * idir.y, c1hiy = (n1.w - o.y) * idir.y;
+            float c1loz = (n2.z - o.z) * idir.z, c1hiz = (n2.w - o.z) * idir.z;
+            float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), mint));
+            float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tmax));
+            float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), mint));
+            float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tmax));
+            // conservative far bound (flat boxes, rounding): 1 + 2*gamma(3)
+            bool h0 = t0n <= t0f * 1.0000004f;
+            bool h1 = t1n <= t1f * 1.0000004f;
+            int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+            if (h0 && h1) {
+                if (t1n < t0n) {
+                    int tmp = c0; c0 = c1; c1 = tmp;
+                }
+                stack[sp++] = c1;
+                node = c0;
+            } else if (h0) {
+                node = c0;
+            } else if (h1) {
+                node = c1;
+            } else {
+                if (sp == 0) break;
+                node = stack[--sp];
+            }
+        } else {
+            const uint32_t code = (uint32_t)(~node);
+            const uint32_t first = code >> 4, count = code & 15u;
+            for (uint32_t i = 0; i < count; ++i) {
+                const float4 q0 = __ldg(S.prims + 3 * (first + i));
+                const uint32_t k = __float_as_uint(q0.x);
+                if (kCount) (*cntPrims)++;
+                float t, u, v;
+                bool ok = false;
+                if (k != kNoTriangle) {
+                    if (k > 2) continue;  // degenerate triangle (TriAccel::load failure, triaccel.h:80-83)
+                    const float4 q1 = __ldg(S.prims + 3 * (first + i) + 1);
+                    const float4 q2 = __ldg(S.prims + 3 * (first + i) + 2);
+                    // Wald's projected test, triaccel.h:96-158
+                    float o_u, o_v, o_k, d_u, d_v, d_k;
+                    if (k == 0) { o_u = o.y; o_v = o.z; o_k = o.x; d_u = d.y; d_v = d.z; d_k = d.x; }
+                    else if (k == 1) { o_u = o.z; o_v = o.x; o_k = o.y; d_u = d.z; d_v = d.x; d_k = d.y; }
+                    else { o_u = o.x; o_v = o.y; o_k = o.z; d_u = d.x; d_v = d.y; d_k = d.z; }
+                    t = (q0.w - o_u * q0.y - o_v * q0.z - o_k) / (d_u * q0.y + d_v * q0.z + d_k);
+                    if (!(t < mint || t > tmax)) {
+                        const float hu = o_u + t * d_u - q1.x;
+                        const float hv = o_v + t * d_v - q1.y;
+                        u = hv * q1.z + hu * q1.w;
+                        v = hu * q2.x + hv * q2.y;
+                        ok = u >= 0 && v >= 0 && u + v <= 1.0f;
+                    }
+                } else {
+                    // rectangle.cpp:125-148: transform to object space, plane z = 0, |x|,|y| <= 1
+                    const uint32_t ri = __float_as_uint(q0.y);
+                    const float4 r0 = __ldg(S.rects + 8 * ri), r1 = __ldg(S.rects + 8 * ri + 1), r2 = __ldg(S.rects + 8 * ri + 2);
+                    float3 lo = f3(r0.x * o.x + r0.y * o.y + r0.z * o.z + r0.w, r1.x * o.x + r1.y * o.y + r1.z * o.z + r1.w,
+                                   r2.x * o.x + r2.y * o.y + r2.z * o.z + r2.w);
+                    float3 ld = f3(r0.x * d.x + r0.y * d.y + r0.z * d.z, r1.x * d.x + r1.y * d.y + r1.z * d.z,
+                                   r2.x * d.x + r2.y * d.y + r2.z * d.z);
+                    t = -lo.z / ld.z;
+                    if (t >= mint && t <= tmax) {
+                        float lx = lo.x + ld.x * t, ly = lo.y + ld.y * t;
+                        if (fabsf(lx) <= 1 && fabsf(ly) <= 1) {
+                            ok = true;
+                            u = lx;
+                            v = ly;
+                        }
+                    }
+                }
+                if (ok) {
+                    if (kAnyHit) {
+                        hit.prim = first + i;
+                        return true;
+                    }
+                    tmax = t;
+                    hit.t = t;
+                    hit.u = u;
+                    hit.v = v;
+                    hit.prim = first + i;
+                }
+            }
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+    }
+    return hit.prim != kMiss;
+}
+
+struct Intersection {
+    float3 p, geoN;
+    Frame sh;
+    float3 wi;
+    float2 uv;
+    float t;
+    int shape, bsdf, emitter;
+    uint32_t primIndex;
+};
+
+PG_DEV void fillIntersection(const DeviceScene &S, float3 o, float3 d, const Hit &h, Intersection &its) {
+    const float4 q2 = __ldg(S.prims + 3 * h.prim + 2);
+    const uint32_t shapeIdx = __float_as_uint(q2.z), primIdx = __float_as_uint(q2.w);
+    const ShapeRecord sr = S.shapes[shapeIdx];
+    its.shape = (int)shapeIdx;
+    its.bsdf = sr.bsdf;
+    its.emitter = sr.emitter;
+    its.primIndex = primIdx;
+    its.t = h.t;
+    float3 dpdu, shN;
+    if (sr.type == B200PG_SHAPE_TRIMESH) {
+        const MeshRecord mr = S.meshes[sr.meshOffset];
+        const uint32_t *idx = S.indices + 3 * ((size_t)mr.indexOffset + primIdx);
+        const uint32_t i0 = idx[0] + mr.vertexOffset, i1 = idx[1] + mr.vertexOffset, i2 = idx[2] + mr.vertexOffset;
+        const float3 b = f3(1 - h.u - h.v, h.u, h.v);
+        const float3 p0 = ld3(S.positions + 3 * (size_t)i0), p1 = ld3(S.positions + 3 * (size_t)i1), p2 = ld3(S.positions + 3 * (size_t)i2);
+        its.p = p0 * b.x + p1 * b.y + p2 * b.z;
+        float3 side1 = p1 - p0, side2 = p2 - p0;
+        float3 faceNormal = cross(side1, side2);
+        float len = length(faceNormal);
+        if (!isZero(faceNormal)) faceNormal = faceNormal / len;
+        dpdu = side1;
+        if (mr.hasNormals) {
+            const float3 n0 = ld3(S.normals + 3 * (size_t)i0), n1 = ld3(S.normals + 3 * (size_t)i1), n2 = ld3(S.normals + 3 * (size_t)i2);
+            shN = normalize(n0 * b.x + n1 * b.y + n2 * b.z);
+            if (dot(faceNormal, shN) < 0) faceNormal = -faceNormal;
+        } else {
+            shN = faceNormal;
+        }
+        its.geoN = faceNormal;
+        its.uv = make_float2(b.y, b.z);
+    } else {
+        const float4 r3 = __ldg(S.rects + 8 * sr.meshOffset + 3), r4 = __ldg(S.rects + 8 * sr.meshOffset + 4);
+        shN = f3(r3.x, r3.y, r3.z);
+        its.geoN = shN;
+        dpdu = f3(r4.x, r4.y, r4.z);
+        its.uv = make_float2(0.5f * (h.u + 1), 0.5f * (h.v + 1));
+        its.p = o + d * h.t;
+    }
+    its.sh = shadingFrame(shN, dpdu);
+    its.wi = its.sh.toLocal(-d);
+}
+
+struct DirectSample {
+    float3 d, n;
+    float dist, pdf;
+    int emitter;
+};
+
+// Shape::samplePosition for rectangles (rectangle.cpp:210-216) and meshes (trimesh.cpp:412-423, triangle.cpp:24-59)
+PG_DEV void samplePosition(const DeviceScene &S, const ShapeRecord &sr, float2 sample, float3 &p, float3 &n, float &pdf) {
+    if (sr.type == B200PG_SHAPE_RECTANGLE) {
+        const float4 *r = S.rects + 8 * sr.meshOffset;
+        const float4 r3 = __ldg(r + 3), m0 = __ldg(r + 5), m1 = __ldg(r + 6), m2 = __ldg(r + 7);
+        float lx = sample.x * 2 - 1, ly = sample.y * 2 - 1;
+        p = f3(m0.x * lx + m0.y * ly + m0.w, m1.x * lx + m1.y * ly + m1.w, m2.x * lx + m2.y * ly + m2.w);
+        n = f3(r3.x, r3.y, r3.z);
+        pdf = r3.w;
+    } else {
+        const MeshRecord mr = S.meshes[sr.meshOffset];
+        const float *cdf = S.areaCdf + mr.cdfOffset;
+        uint32_t index = cdfSample(cdf, mr.nTriangles + 1, sample.y);
+        sample.y = (sample.y - cdf[index]) / (cdf[index + 1] - cdf[index]);  // sampleReuse, pmf.h:163-168
+        const uint32_t *idx = S.indices + 3 * ((size_t)mr.indexOffset + index);
+        const uint32_t i0 = idx[0] + mr.vertexOffset, i1 = idx[1] + mr.vertexOffset, i2 = idx[2] + mr.vertexOffset;
+        const float3 p0 = ld3(S.positions + 3 * (size_t)i0), p1 = ld3(S.positions + 3 * (size_t)i1), p2 = ld3(S.positions + 3 * (size_t)i2);
+        float2 bary = squareToUniformTriangle(sample);
+        float3 sideA = p1 - p0, sideB = p2 - p0;
+        p = p0 + (sideA * bary.x) + (sideB * bary.y);
+        if (mr.hasNormals) {
+            const float3 n0 = ld3(S.normals + 3 * (size_t)i0), n1 = ld3(S.normals + 3 * (size_t)i1), n2 = ld3(S.normals + 3 * (size_t)i2);
+            n = normalize(n0 * (1.0f - bary.x - bary.y) + n1 * bary.x + n2 * bary.y);
+        } else {
+            n = normalize(cross(sideA, sideB));
+        }
+        pdf = mr.invSurfaceArea;
+    }
+}
+
+// Emitter sampling without the visibility test (the shadow ray goes to the shadow queue).
+// Returns radiance / pdf (zero when rejected).
+PG_DEV float3 sampleEmitterDirect(const DeviceScene &S, float3 ref, float3 refN, float2 sample, DirectSample &dRec) {
+    uint32_t index = cdfSample(S.emitterCdf, S.nEmitters + 1, sample.x);
+    float emPdf = S.emitterCdf[index + 1] - S.emitterCdf[index];
+    sample.x = (sample.x - S.emitterCdf[index]) / (S.emitterCdf[index + 1] - S.emitterCdf[index]);
+    const EmitterRecord em = S.emitters[index];
+    const ShapeRecord sr = S.shapes[em.shape];
+    float3 p;
+    samplePosition(S, sr, sample, p, dRec.n, dRec.pdf);
+    dRec.d = p - ref;
+    float distSquared = dot(dRec.d, dRec.d);
+    dRec.dist = sqrtf(distSquared);
+    dRec.d = dRec.d / dRec.dist;
+    float dp = fabsf(dot(dRec.d, dRec.n));
+    dRec.pdf *= dp != 0 ? (distSquared / dp) : 0.0f;
+    dRec.emitter = (int)index;
+    if (dot(dRec.d, refN) >= 0 && dot(dRec.d, dRec.n) < 0 && dRec.pdf != 0) {
+        float3 value = ld3(em.radiance) / dRec.pdf;
+        dRec.pdf *= emPdf;
+        return value / emPdf;
+    }
+    dRec.pdf = 0.0f;
+    return f3(0.0f);
+}
+
+// Scene::pdfEmitterDirect after DirectSamplingRecord::setQuery (records.inl:170-178; scene.cpp:992-995;
+// area.cpp:175-183; shape.cpp:117-126). The refN test of AreaLight::pdfDirect always passes for a direction
+// that was just sampled from the BSDF on the same side as refN, so it is not carried along.
+PG_DEV float pdfEmitterDirect(const DeviceScene &S, int emitter, float3 d, float3 n, float dist) {
+    if (!(dot(d, n) < 0)) return 0.0f;
+    const EmitterRecord em = S.emitters[emitter];
+    const ShapeRecord sr = S.shapes[em.shape];
+    float invArea = sr.type == B200PG_SHAPE_RECTANGLE ? __ldg(S.rects + 8 * sr.meshOffset + 3).w
+                                                       : S.meshes[sr.meshOffset].invSurfaceArea;
+    float discrete = S.emitterCdf[emitter + 1] - S.emitterCdf[emitter];
+    return invArea * (dist * dist) / fabsf(dot(d, n)) * discrete;
+}
+
+// PerspectiveCameraImpl::sampleRayDifferential without differentials (perspective.cpp:271-298)
+PG_DEV void sampleCameraRay(const CameraRecord &C, float2 pixelSample, float3 &o, float3 &d, float &mint, float &maxt) {
+    const float *m = C.sampleToCamera;
+    float sx = pixelSample.x * C.invResX, sy = pixelSample.y * C.invResY;
+    float x = m[0] * sx + m[1] * sy + m[3];
+    float y = m[4] * sx + m[5] * sy + m[7];
+    float z = m[8] * sx + m[9] * sy + m[11];
+    float w = m[12] * sx + m[13] * sy + m[15];
+    float3 nearP = f3(x, y, z);
+    if (w != 1.0f) nearP = nearP / w;
+    float3 dl = normalize(nearP);
+    float invZ = 1.0f / dl.z;
+    mint = C.nearClip * invZ;
+    maxt = C.farClip * invZ;
+    const float *t = C.toWorld;
+    o = f3(t[3], t[7], t[11]);
+    d = f3(t[0] * dl.x + t[1] * dl.y + t[2] * dl.z, t[4] * dl.x + t[5] * dl.y + t[6] * dl.z,
+           t[8] * dl.x + t[9] * dl.y + t[10] * dl.z);
+}
+
+}  // namespace pg

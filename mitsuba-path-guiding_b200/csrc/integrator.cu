@@ -1,0 +1,650 @@
+// integrator.cu -- host side of the wavefront integrator and the C-ABI of include/b200pg.h.
+//
+// Mirrors, for this path, what the reference's plugin interface does:
+//   ProgressiveMonteCarloIntegrator::render / renderSamples (src/librender/progressiveintegrator.cpp:65-220):
+//     numPasses = spp / samplesPerProgression, pre/postprogression hooks around each pass
+//   BlockedRenderProcess + LocalWorker tiles (src/librender/renderproc.cpp, imageproc.cpp): replaced by
+//     wavefront batches over the whole image band on one GPU
+//   Film::put / develop (src/films/hdrfilm.cpp:391-546)
+// There is no CPU fallback: without a CUDA device every entry point fails loudly.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/b200pg.h"
+#include "guiding_host.h"
+#include "host_scene.h"
+#include "wavefront.cuh"
+
+namespace pg {
+
+// launch wrappers implemented in kernels.cu
+void launchGenerate(const DeviceScene &S, const BatchDesc &B, const PathState &P, Counters *C, cudaStream_t st);
+void launchTrace(const DeviceScene &S, const PathState &P, float4 *hits, const uint32_t *nPtr, uint32_t *work, Counters *C,
+                 bool count, cudaStream_t st);
+void launchShadow(const DeviceScene &S, const ShadowQueue &Q, float4 *rad, const uint32_t *nPtr, uint32_t *work, Counters *C,
+                  bool count, cudaStream_t st);
+void launchShade(const ShadeArgs &A, cudaStream_t st);
+void launchFlush(const ShadeArgs &A, cudaStream_t st);
+void launchTraceRays(const DeviceScene &S, const float4 *rays, uint32_t n, float4 *hits, uint32_t *work, Counters *C, bool shadow,
+                     bool count, cudaStream_t st);
+void launchFilmSplat(const FilmRecord &F, float4 *film, const float2 *pos, const float3 *rgb, uint32_t n, float maxComponentValue,
+                     cudaStream_t st);
+void launchBsdfTest(const DeviceScene &S, int bsdfIndex, const float *wi, const float *wo, const float *u, uint32_t n, float *outEval,
+                    float *outPdf, float *outWo, float *outWeight, float *outSpdf, uint32_t *outFlags, cudaStream_t st);
+
+static thread_local std::string g_lastError;
+static int fail(const std::string &msg, int code = -1) {
+    g_lastError = msg;
+    return code;
+}
+#define CUDA_OK(expr)                                                                                       \
+    do {                                                                                                    \
+        cudaError_t e_ = (expr);                                                                            \
+        if (e_ != cudaSuccess) throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void alloc(size_t count) {
+        if (count <= n) return;
+        release();
+        CUDA_OK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+        n = count;
+    }
+    void upload(const T *src, size_t count, cudaStream_t st = 0) {
+        alloc(count);
+        if (count) CUDA_OK(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
+    }
+    void upload(const std::vector<T> &v, cudaStream_t st = 0) { upload(v.data(), v.size(), st); }
+};
+
+struct PathBuffers {
+    DevBuf<float4> rayO, rayD, thr, rad, pos;
+    DevBuf<uint32_t> flags, slot;
+    DevBuf<int32_t> medium;
+    void alloc(size_t n) {
+        rayO.alloc(n); rayD.alloc(n); thr.alloc(n); rad.alloc(n); pos.alloc(n);
+        flags.alloc(n); slot.alloc(n); medium.alloc(n);
+    }
+    PathState view() {
+        PathState s;
+        s.rayO = rayO.p; s.rayD = rayD.p; s.thr = thr.p; s.rad = rad.p; s.pos = pos.p;
+        s.flags = flags.p; s.slot = slot.p; s.medium = medium.p;
+        return s;
+    }
+};
+
+struct Integrator {
+    HostScene *scene = nullptr;
+    B200pgIntegratorParams params;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::atomic<int> cancel{0};
+
+    // device scene
+    DevBuf<float4> dNodes, dPrims, dRects;
+    DevBuf<ShapeRecord> dShapes;
+    DevBuf<MeshRecord> dMeshes;
+    DevBuf<float> dPositions, dNormals, dTexcoords, dAreaCdf, dEmitterCdf, dDensity;
+    DevBuf<uint32_t> dIndices, dPrimGlobal;
+    DevBuf<BsdfRecord> dBsdfs;
+    DevBuf<EmitterRecord> dEmitters;
+    DevBuf<MediumRecord> dMedia;
+    DeviceScene S;
+
+    // wavefront state
+    PathBuffers bufA, bufB;
+    DevBuf<float4> dHits, dShO, dShD, dShC;
+    DevBuf<int32_t> dShMedium;
+    DevBuf<Counters> dCounters;
+    DevBuf<float4> dFilm;
+    size_t batchCapacity = 0;
+    bool countTraversal = false;
+
+    B200pgStats stats;
+    cudaEvent_t ev[8];
+    GuidingHost guide;
+
+    ~Integrator() {
+        if (stream) cudaStreamDestroy(stream);
+        for (auto &e : ev)
+            if (e) cudaEventDestroy(e);
+    }
+
+    void init() {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            throw std::runtime_error("no CUDA device available (this library has no CPU path)");
+        if (device < 0 || device >= count) throw std::runtime_error("invalid CUDA device index");
+        CUDA_OK(cudaSetDevice(device));
+        CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        for (auto &e2 : ev) {
+            e2 = nullptr;
+            CUDA_OK(cudaEventCreate(&e2));
+        }
+        std::memset(&stats, 0, sizeof(stats));
+        HostScene &H = *scene;
+        dNodes.upload(reinterpret_cast<const float4 *>(H.nodes.data()), H.nodes.size() * 4, stream);
+        dPrims.upload(reinterpret_cast<const float4 *>(H.prims.data()), H.prims.size() * 3, stream);
+        dRects.upload(reinterpret_cast<const float4 *>(H.rects.data()), H.rects.size() * 8, stream);
+        dShapes.upload(H.shapeRecs, stream);
+        dMeshes.upload(H.meshes, stream);
+        dPositions.upload(H.positions, stream);
+        dNormals.upload(H.normals, stream);
+        dTexcoords.upload(H.texcoords, stream);
+        dIndices.upload(H.indices, stream);
+        dAreaCdf.upload(H.areaCdf, stream);
+        dBsdfs.upload(H.bsdfRecs, stream);
+        dEmitters.upload(H.emitterRecs, stream);
+        dEmitterCdf.upload(H.emitterCdf, stream);
+        dMedia.upload(H.mediumRecs, stream);
+        dDensity.upload(H.densityPool, stream);
+        dPrimGlobal.upload(H.primGlobalId, stream);
+        S.nodes = dNodes.p; S.prims = dPrims.p; S.rects = dRects.p;
+        S.shapes = dShapes.p; S.meshes = dMeshes.p;
+        S.positions = dPositions.p; S.normals = dNormals.p; S.texcoords = dTexcoords.p;
+        S.indices = dIndices.p; S.areaCdf = dAreaCdf.p;
+        S.bsdfs = dBsdfs.p; S.emitters = dEmitters.p; S.emitterCdf = dEmitterCdf.p;
+        S.media = dMedia.p; S.density = dDensity.p; S.primGlobalId = dPrimGlobal.p;
+        S.nEmitters = (uint32_t)H.emitters.size();
+        S.nPrims = (uint32_t)H.prims.size();
+        S.camera = H.camera;
+        S.film = H.filmRec;
+        S.seed = H.seed;
+        dCounters.alloc(1);
+        CUDA_OK(cudaMemsetAsync(dCounters.p, 0, sizeof(Counters), stream));
+        dFilm.alloc((size_t)H.film.width * H.film.height);
+        CUDA_OK(cudaMemsetAsync(dFilm.p, 0, dFilm.n * sizeof(float4), stream));
+        if (params.use_nee && H.emitters.empty()) params.use_nee = 0;  // nothing to sample
+        guide.init(this->params, H, stream);
+        CUDA_OK(cudaStreamSynchronize(stream));
+    }
+
+    void ensureBatch(size_t n) {
+        if (n <= batchCapacity) return;
+        bufA.alloc(n); bufB.alloc(n);
+        dHits.alloc(n); dShO.alloc(n); dShD.alloc(n); dShC.alloc(n); dShMedium.alloc(n);
+        batchCapacity = n;
+    }
+
+    IntegratorConfig config() const {
+        IntegratorConfig c;
+        c.maxDepth = params.max_depth;
+        c.rrDepth = params.rr_depth;
+        c.strictNormals = params.strict_normals;
+        c.hideEmitters = params.hide_emitters;
+        c.useNee = params.use_nee;
+        c.volumetric = params.volumetric;
+        c.maxComponentValue = params.max_component_value;
+        c.guiding = 0;
+        c.guidingProbability = params.guiding_probability;
+        c.recordTraining = 0;
+        c.guidedDistance = params.guided_distance;
+        return c;
+    }
+
+    // Runs one wavefront batch to completion (all bounces). Everything is enqueued on `stream`
+    // without host synchronisation unless maxDepth is infinite.
+    void runBatch(const BatchDesc &B, float *radianceOut) {
+        ensureBatch(B.nPaths);
+        const size_t zeroBytes = offsetof(Counters, paths);
+        CUDA_OK(cudaMemsetAsync(dCounters.p, 0, zeroBytes, stream));
+        PathState cur = bufA.view(), next = bufB.view();
+        launchGenerate(S, B, cur, dCounters.p, stream);
+        stats.kernel_launches++;
+        ShadeArgs A;
+        A.S = S;
+        A.cfg = config();
+        guide.configure(A);
+        A.shadow.o = dShO.p; A.shadow.d = dShD.p; A.shadow.c = dShC.p; A.shadow.medium = dShMedium.p;
+        A.hits = dHits.p;
+        A.C = dCounters.p;
+        A.film = dFilm.p;
+        A.radianceOut = radianceOut;
+        const int maxBounces = params.max_depth > 0 ? std::min(params.max_depth + 1, 256) : 256;
+        Counters *C = dCounters.p;
+        int b = 0;
+        for (; b < maxBounces; ++b) {
+            if (cancel.load()) break;
+            launchTrace(S, cur, dHits.p, &C->queue[b], &C->traceWork[b], C, countTraversal, stream);
+            A.cur = cur;
+            A.next = next;
+            A.bounce = b;
+            launchShade(A, stream);
+            launchShadow(S, A.shadow, next.rad, &C->shadow[b], &C->shadowWork[b], C, countTraversal, stream);
+            stats.kernel_launches += 3;
+            std::swap(cur, next);
+            if (params.max_depth <= 0 && (b & 3) == 3) {  // infinite depth: poll the queue size
+                uint32_t nq = 0;
+                CUDA_OK(cudaMemcpyAsync(&nq, &C->queue[b + 1], sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+                CUDA_OK(cudaStreamSynchronize(stream));
+                if (nq == 0) {
+                    ++b;
+                    break;
+                }
+            }
+        }
+        A.cur = cur;
+        A.next = next;
+        A.bounce = std::min(b, maxBounces);
+        launchFlush(A, stream);
+        stats.kernel_launches++;
+    }
+
+    void pullCounters() {
+        Counters h;
+        CUDA_OK(cudaMemcpyAsync(&h, dCounters.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        stats.paths = h.paths;
+        stats.normal_rays = h.normalRays;
+        stats.shadow_rays = h.shadowRays;
+        stats.path_length_sum = h.pathLen;
+        stats.bvh_nodes_visited = h.nodesVisited;
+        stats.prims_tested = h.primsTested;
+        stats.train_samples = h.trainSamples;
+    }
+
+    // One progression over (rows, samples), split into batches of at most maxBatch paths.
+    void renderProgression(int firstSample, int nSamples, int rowBegin, int rowEnd) {
+        const int W = scene->film.width, H = scene->film.height;
+        if (rowEnd <= 0 || rowEnd > H) rowEnd = H;
+        if (rowBegin < 0) rowBegin = 0;
+        if (rowBegin >= rowEnd || nSamples <= 0) return;
+        size_t maxBatch = params.max_batch_paths > 0 ? (size_t)params.max_batch_paths : (size_t)4 << 20;
+        const size_t rowPaths = (size_t)W;
+        auto t0 = std::chrono::steady_clock::now();
+        // split: whole band x k samples if it fits, else row chunks per sample
+        const size_t bandPaths = rowPaths * (rowEnd - rowBegin);
+        if (bandPaths <= maxBatch) {
+            int spb = (int)std::max<size_t>(1, maxBatch / bandPaths);
+            for (int s = 0; s < nSamples && !cancel.load(); s += spb) {
+                BatchDesc B;
+                std::memset(&B, 0, sizeof(B));
+                B.rowBegin = rowBegin;
+                B.nRows = rowEnd - rowBegin;
+                B.firstSample = firstSample + s;
+                B.nSamples = std::min(spb, nSamples - s);
+                B.nPaths = (uint32_t)(bandPaths * B.nSamples);
+                runBatch(B, nullptr);
+            }
+        } else {
+            int rowsPer = (int)std::max<size_t>(1, maxBatch / rowPaths);
+            for (int s = 0; s < nSamples; ++s)
+                for (int r = rowBegin; r < rowEnd && !cancel.load(); r += rowsPer) {
+                    BatchDesc B;
+                    std::memset(&B, 0, sizeof(B));
+                    B.rowBegin = r;
+                    B.nRows = std::min(rowsPer, rowEnd - r);
+                    B.firstSample = firstSample + s;
+                    B.nSamples = 1;
+                    B.nPaths = (uint32_t)(rowPaths * B.nRows);
+                    runBatch(B, nullptr);
+                }
+        }
+        CUDA_OK(cudaStreamSynchronize(stream));
+        stats.seconds_total += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        stats.progressions_done++;
+    }
+};
+
+struct SceneHandle {
+    HostScene host;
+};
+
+}  // namespace pg
+
+using namespace pg;
+
+// =============================================================================================
+// C-ABI
+// =============================================================================================
+extern "C" {
+
+int b200pg_version(void) { return B200PG_VERSION; }
+const char *b200pg_last_error(void) { return g_lastError.c_str(); }
+
+void b200pg_integrator_params_default(B200pgIntegratorParams *p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->max_depth = -1;               // integrator.cpp:203
+    p->rr_depth = 5;                 // integrator.cpp:198
+    p->samples_per_progression = 1;  // progressiveintegrator.cpp:297
+    p->max_render_time = 0;
+    p->max_component_value = std::numeric_limits<float>::infinity();
+    p->use_nee = 1;                  // progressive_path.cpp:117
+    p->guiding_probability = 0.5f;
+    p->guide_max_components = 16;
+    p->guide_max_cell_samples = 32768;
+}
+
+void *b200pg_scene_from_arrays(const B200pgSceneDesc *desc) {
+    try {
+        std::unique_ptr<SceneHandle> h(new SceneHandle());
+        std::string err;
+        if (!h->host.copyFrom(desc, err) || !h->host.compile(err)) {
+            fail(err);
+            return nullptr;
+        }
+        return h.release();
+    } catch (const std::exception &e) {
+        fail(e.what());
+        return nullptr;
+    }
+}
+
+void *b200pg_scene_load_xml(const char *path, const char *const *defines, char *errOut, size_t errlen) {
+    try {
+        std::unique_ptr<SceneHandle> h(new SceneHandle());
+        std::string err;
+        if (!loadSceneXml(path, defines, h->host, err) || !h->host.compile(err)) {
+            fail(err);
+            if (errOut && errlen) std::snprintf(errOut, errlen, "%s", err.c_str());
+            return nullptr;
+        }
+        return h.release();
+    } catch (const std::exception &e) {
+        fail(e.what());
+        if (errOut && errlen) std::snprintf(errOut, errlen, "%s", e.what());
+        return nullptr;
+    }
+}
+
+const B200pgSceneDesc *b200pg_scene_desc(void *scene) {
+    if (!scene) return nullptr;
+    return &((SceneHandle *)scene)->host.view;
+}
+
+int b200pg_scene_integrator_params(void *scene, B200pgIntegratorParams *out) {
+    if (!scene || !out) return fail("null argument");
+    *out = ((SceneHandle *)scene)->host.xmlParams;
+    return 0;
+}
+
+void b200pg_scene_destroy(void *scene) { delete (SceneHandle *)scene; }
+
+void *b200pg_integrator_create(void *scene, const B200pgIntegratorParams *params, int device) {
+    if (!scene) {
+        fail("null scene");
+        return nullptr;
+    }
+    try {
+        std::unique_ptr<Integrator> I(new Integrator());
+        I->scene = &((SceneHandle *)scene)->host;
+        if (params)
+            I->params = *params;
+        else
+            I->params = I->scene->xmlParams;
+        // MonteCarloIntegrator ctor checks (integrator.cpp:225-229)
+        if (I->params.rr_depth <= 0) {
+            fail("'rrDepth' must be set to a value greater than zero!");
+            return nullptr;
+        }
+        if (I->params.max_depth <= 0 && I->params.max_depth != -1) {
+            fail("'maxDepth' must be set to -1 (infinite) or a value greater than zero!");
+            return nullptr;
+        }
+        if (I->params.max_depth > 250) {
+            fail("maxDepth above 250 is not supported by the wavefront queues");
+            return nullptr;
+        }
+        if (I->params.samples_per_progression <= 0) I->params.samples_per_progression = 1;
+        I->device = device;
+        I->init();
+        return I.release();
+    } catch (const std::exception &e) {
+        fail(e.what());
+        return nullptr;
+    }
+}
+
+#define PG_TRY(I) \
+    if (!(I)) return fail("null integrator"); \
+    Integrator *self = (Integrator *)(I); \
+    try { \
+        CUDA_OK(cudaSetDevice(self->device));
+#define PG_END \
+    } catch (const std::exception &e) { return fail(e.what()); } \
+    return 0;
+
+int b200pg_progression_render(void *integ, int first_sample, int n_samples, int row_begin, int row_end) {
+    PG_TRY(integ)
+    self->renderProgression(first_sample, n_samples, row_begin, row_end);
+    self->pullCounters();
+    PG_END
+}
+
+int b200pg_render(void *integ) {
+    PG_TRY(integ)
+    // ProgressiveMonteCarloIntegrator::renderSamples (progressiveintegrator.cpp:65-114) /
+    // renderTime (:117-168)
+    const int spp = self->scene->sampleCount;
+    const int perPass = self->params.samples_per_progression;
+    const int numPasses = std::max(1, spp / perPass);
+    auto t0 = std::chrono::steady_clock::now();
+    if (self->params.max_render_time > 0) {
+        int pass = 0;
+        while (!self->cancel.load()) {
+            self->guide.preprogression(pass);
+            self->renderProgression(pass * perPass, perPass, 0, 0);
+            self->guide.postprogression(pass, nullptr);
+            ++pass;
+            double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (el >= self->params.max_render_time) break;
+        }
+    } else {
+        for (int pass = 0; pass < numPasses && !self->cancel.load(); ++pass) {
+            self->guide.preprogression(pass);
+            self->renderProgression(pass * perPass, perPass, 0, 0);
+            self->guide.postprogression(pass, nullptr);
+        }
+    }
+    self->pullCounters();
+    PG_END
+}
+
+int b200pg_cancel(void *integ) {
+    if (!integ) return fail("null integrator");
+    ((Integrator *)integ)->cancel.store(1);
+    return 0;
+}
+
+int b200pg_film_clear(void *integ) {
+    PG_TRY(integ)
+    CUDA_OK(cudaMemsetAsync(self->dFilm.p, 0, self->dFilm.n * sizeof(float4), self->stream));
+    CUDA_OK(cudaStreamSynchronize(self->stream));
+    PG_END
+}
+
+int b200pg_film_device_buffer(void *integ, void **dev_ptr, size_t *n_floats) {
+    if (!integ) return fail("null integrator");
+    Integrator *self = (Integrator *)integ;
+    if (dev_ptr) *dev_ptr = self->dFilm.p;
+    if (n_floats) *n_floats = self->dFilm.n * 4;
+    return 0;
+}
+
+int b200pg_film_read(void *integ, float *rgbaw) {
+    PG_TRY(integ)
+    std::vector<float4> h(self->dFilm.n);
+    CUDA_OK(cudaMemcpyAsync(h.data(), self->dFilm.p, h.size() * sizeof(float4), cudaMemcpyDeviceToHost, self->stream));
+    CUDA_OK(cudaStreamSynchronize(self->stream));
+    for (size_t i = 0; i < h.size(); ++i) {
+        rgbaw[5 * i + 0] = h[i].x;
+        rgbaw[5 * i + 1] = h[i].y;
+        rgbaw[5 * i + 2] = h[i].z;
+        rgbaw[5 * i + 3] = h[i].w;  // alpha == weight on this path (rRec.alpha stays 1, integrator.h:218-225)
+        rgbaw[5 * i + 4] = h[i].w;
+    }
+    PG_END
+}
+
+int b200pg_film_develop(void *integ, float *rgb) {
+    PG_TRY(integ)
+    std::vector<float4> h(self->dFilm.n);
+    CUDA_OK(cudaMemcpyAsync(h.data(), self->dFilm.p, h.size() * sizeof(float4), cudaMemcpyDeviceToHost, self->stream));
+    CUDA_OK(cudaStreamSynchronize(self->stream));
+    for (size_t i = 0; i < h.size(); ++i) {  // weight normalisation, fmtconv.cpp:978-1005
+        float inv = h[i].w > 0 ? 1.0f / h[i].w : 0.0f;
+        rgb[3 * i + 0] = h[i].x * inv;
+        rgb[3 * i + 1] = h[i].y * inv;
+        rgb[3 * i + 2] = h[i].z * inv;
+    }
+    PG_END
+}
+
+int b200pg_film_write(void *integ, const char *path) {
+    if (!integ || !path) return fail("null argument");
+    Integrator *self = (Integrator *)integ;
+    const int W = self->scene->film.width, H = self->scene->film.height;
+    std::vector<float> rgb((size_t)W * H * 3);
+    int r = b200pg_film_develop(integ, rgb.data());
+    if (r) return r;
+    std::string p(path);
+    if (p.size() < 4 || p.substr(p.size() - 4) != ".pfm") return fail("only .pfm output is supported (hdrfilm fileFormat=pfm)");
+    FILE *f = std::fopen(path, "wb");
+    if (!f) return fail(std::string("cannot open ") + path);
+    std::fprintf(f, "PF\n%d %d\n-1.0\n", W, H);  // little endian, bottom-up scanlines (bitmap.cpp writePFM)
+    for (int y = H - 1; y >= 0; --y) std::fwrite(rgb.data() + (size_t)y * W * 3, sizeof(float), (size_t)W * 3, f);
+    std::fclose(f);
+    return 0;
+}
+
+int b200pg_stats(void *integ, B200pgStats *out) {
+    if (!integ || !out) return fail("null argument");
+    Integrator *self = (Integrator *)integ;
+    *out = self->stats;
+    out->guide_cells = self->guide.numCells();
+    return 0;
+}
+
+void b200pg_destroy(void *integ) { delete (Integrator *)integ; }
+
+// ---------------------------------------------------------------------------------------------
+// per-kernel entry points
+// ---------------------------------------------------------------------------------------------
+int b200pg_k_trace_device(void *integ, const void *d_rays, size_t n, int shadow, void *d_hits, float *ms, uint64_t *counts) {
+    PG_TRY(integ)
+    Counters *C = self->dCounters.p;
+    CUDA_OK(cudaMemsetAsync(&C->misc[0], 0, sizeof(uint32_t), self->stream));
+    if (counts) {
+        CUDA_OK(cudaMemsetAsync(&C->nodesVisited, 0, 2 * sizeof(unsigned long long), self->stream));
+    }
+    CUDA_OK(cudaEventRecord(self->ev[0], self->stream));
+    launchTraceRays(self->S, (const float4 *)d_rays, (uint32_t)n, (float4 *)d_hits, &C->misc[0], C, shadow != 0, counts != nullptr,
+                    self->stream);
+    CUDA_OK(cudaEventRecord(self->ev[1], self->stream));
+    CUDA_OK(cudaStreamSynchronize(self->stream));
+    CUDA_OK(cudaGetLastError());
+    if (ms) CUDA_OK(cudaEventElapsedTime(ms, self->ev[0], self->ev[1]));
+    if (counts) {
+        unsigned long long h[2];
+        CUDA_OK(cudaMemcpy(h, &C->nodesVisited, sizeof(h), cudaMemcpyDeviceToHost));
+        counts[0] = h[0];
+        counts[1] = h[1];
+    }
+    self->stats.kernel_launches++;
+    PG_END
+}
+
+int b200pg_k_trace(void *integ, const float *rays, size_t n, int shadow, float *hits_tuv, uint32_t *hits_prim) {
+    PG_TRY(integ)
+    DevBuf<float4> dR, dH;
+    dR.upload(reinterpret_cast<const float4 *>(rays), n * 2, self->stream);
+    dH.alloc(n);
+    int r = b200pg_k_trace_device(integ, dR.p, n, shadow, dH.p, nullptr, nullptr);
+    if (r) return r;
+    std::vector<float4> h(n);
+    CUDA_OK(cudaMemcpy(h.data(), dH.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) {
+        if (hits_tuv) {
+            hits_tuv[3 * i] = h[i].x;
+            hits_tuv[3 * i + 1] = h[i].y;
+            hits_tuv[3 * i + 2] = h[i].z;
+        }
+        uint32_t p;
+        std::memcpy(&p, &h[i].w, 4);
+        hits_prim[i] = p;
+    }
+    PG_END
+}
+
+int b200pg_k_bsdf(void *integ, int bsdf_index, const float *wi, const float *wo, const float *u, size_t n, float *out_eval,
+                  float *out_pdf, float *out_wo, float *out_weight, float *out_spdf, uint32_t *out_flags) {
+    PG_TRY(integ)
+    if (bsdf_index < 0 || bsdf_index >= (int)self->scene->bsdfRecs.size()) return fail("bsdf index out of range");
+    DevBuf<float> dWi, dWo, dU, dE, dP, dSo, dW, dSp;
+    DevBuf<uint32_t> dF;
+    dWi.upload(wi, 3 * n, self->stream);
+    dWo.upload(wo, 3 * n, self->stream);
+    dU.upload(u, 2 * n, self->stream);
+    dE.alloc(3 * n); dP.alloc(n); dSo.alloc(3 * n); dW.alloc(3 * n); dSp.alloc(n); dF.alloc(n);
+    launchBsdfTest(self->S, bsdf_index, dWi.p, dWo.p, dU.p, (uint32_t)n, dE.p, dP.p, dSo.p, dW.p, dSp.p, dF.p, self->stream);
+    CUDA_OK(cudaMemcpyAsync(out_eval, dE.p, 3 * n * 4, cudaMemcpyDeviceToHost, self->stream));
+    CUDA_OK(cudaMemcpyAsync(out_pdf, dP.p, n * 4, cudaMemcpyDeviceToHost, self->stream));
+    CUDA_OK(cudaMemcpyAsync(out_wo, dSo.p, 3 * n * 4, cudaMemcpyDeviceToHost, self->stream));
+    CUDA_OK(cudaMemcpyAsync(out_weight, dW.p, 3 * n * 4, cudaMemcpyDeviceToHost, self->stream));
+    CUDA_OK(cudaMemcpyAsync(out_spdf, dSp.p, n * 4, cudaMemcpyDeviceToHost, self->stream));
+    CUDA_OK(cudaMemcpyAsync(out_flags, dF.p, n * 4, cudaMemcpyDeviceToHost, self->stream));
+    CUDA_OK(cudaStreamSynchronize(self->stream));
+    CUDA_OK(cudaGetLastError());
+    self->stats.kernel_launches++;
+    PG_END
+}
+
+int b200pg_k_radiance(void *integ, const uint32_t *pixel, const uint32_t *sample_index, size_t n, float *out_rgb) {
+    PG_TRY(integ)
+    DevBuf<uint32_t> dPix, dSmp;
+    DevBuf<float> dOut;
+    dPix.upload(pixel, n, self->stream);
+    dSmp.upload(sample_index, n, self->stream);
+    dOut.alloc(3 * n);
+    CUDA_OK(cudaMemsetAsync(dOut.p, 0, 3 * n * 4, self->stream));
+    BatchDesc B;
+    std::memset(&B, 0, sizeof(B));
+    B.nPaths = (uint32_t)n;
+    B.pixelList = dPix.p;
+    B.sampleList = dSmp.p;
+    self->runBatch(B, dOut.p);
+    CUDA_OK(cudaMemcpyAsync(out_rgb, dOut.p, 3 * n * 4, cudaMemcpyDeviceToHost, self->stream));
+    CUDA_OK(cudaStreamSynchronize(self->stream));
+    CUDA_OK(cudaGetLastError());
+    self->pullCounters();
+    PG_END
+}
+
+int b200pg_k_film_splat(void *integ, const float *pos, const float *rgb, size_t n) {
+    PG_TRY(integ)
+    DevBuf<float> dPos, dRgb;
+    dPos.upload(pos, 2 * n, self->stream);
+    dRgb.upload(rgb, 3 * n, self->stream);
+    launchFilmSplat(self->S.film, self->dFilm.p, (const float2 *)dPos.p, (const float3 *)dRgb.p, (uint32_t)n,
+                    self->params.max_component_value, self->stream);
+    CUDA_OK(cudaStreamSynchronize(self->stream));
+    CUDA_OK(cudaGetLastError());
+    self->stats.kernel_launches++;
+    PG_END
+}
+
+}  // extern "C"

@@ -1,0 +1,530 @@
+// kernels.cu -- the wavefront stages as hand-written sm_100a CUDA kernels:
+//   k_generate   camera-ray generation        (progressiveintegrator.cpp:246-271, perspective.cpp:271-298)
+//   k_trace      closest-hit / any-hit BVH traversal over a compacted ray queue
+//   k_shade      intersection fill, emitted radiance + MIS, Russian roulette, NEE, BSDF sampling,
+//                queue compaction, film splat at termination (progressive_path.cpp:133-314)
+//   k_shadow     shadow-ray resolve: adds the NEE contribution to the (moved) path record
+//   k_film_splat standalone splat kernel (imageblock.h:151-197) used by the parity tests
+// All kernels are persistent (grid = k * #SMs) and read their work size from device counters so
+// that a whole batch (all bounces) is enqueued without a host round trip.
+#include <cooperative_groups.h>
+
+#include "guiding_device.cuh"
+#include "medium_device.cuh"
+#include "wavefront.cuh"
+
+namespace pg {
+
+namespace cg = cooperative_groups;
+
+PG_DEV uint32_t laneId() { return threadIdx.x & 31u; }
+
+// Warp-aggregated append: returns the destination index for lanes with `pred`, one atomic per warp.
+PG_DEV uint32_t warpAppend(uint32_t *counter, bool pred) {
+    const unsigned mask = __ballot_sync(0xffffffffu, pred);
+    uint32_t base = 0;
+    if (laneId() == 0 && mask) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    return base + __popc(mask & ((1u << laneId()) - 1u));
+}
+
+PG_DEV void warpAddU64(unsigned long long *counter, unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (laneId() == 0 && v) atomicAdd(counter, v);
+}
+
+// ------------------------------------------------------------------------------------------
+// Film: Gaussian-filtered splat (ImageBlock::put, include/mitsuba/render/imageblock.h:151-197).
+// The arithmetic replays the reference's 32x32 tile + border coordinates (imageproc.cpp:27-78,
+// rfilter.cpp:51) so that the discretised filter lookups land in the same table bins.
+// Film texel = float4 (R, G, B, weight); alpha == weight on this path.
+// ------------------------------------------------------------------------------------------
+PG_DEV void filmSplat(const FilmRecord &F, float4 *film, float2 pos, float3 spec, float maxComponentValue) {
+    float maxSpec = maxComp(spec);
+    if (maxSpec > maxComponentValue) spec = spec * (maxComponentValue / maxSpec);  // progressiveintegrator.cpp:274-277
+    // ImageBlock::put rejects NaN / negative samples (imageblock.h:154-158)
+    if (!(isfinite(spec.x) && isfinite(spec.y) && isfinite(spec.z)) || spec.x < 0 || spec.y < 0 || spec.z < 0) return;
+    const int border = (int)ceilf(F.radius - 0.5f);
+    const int pxI = min(max((int)pos.x, 0), F.width - 1), pyI = min(max((int)pos.y, 0), F.height - 1);
+    const int ox = (pxI >> 5) << 5, oy = (pyI >> 5) << 5;
+    const int bw = min(32, F.width - ox) + 2 * border, bh = min(32, F.height - oy) + 2 * border;
+    const float px = pos.x - 0.5f - (float)(ox - border), py = pos.y - 0.5f - (float)(oy - border);
+    const int minx = max((int)ceilf(px - F.radius), 0), miny = max((int)ceilf(py - F.radius), 0);
+    const int maxx = min((int)floorf(px + F.radius), bw - 1), maxy = min((int)floorf(py + F.radius), bh - 1);
+    float wx[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        int x = minx + i;
+        wx[i] = x <= maxx ? F.values[min((int)fabsf((x - px) * F.scaleFactor), 31)] : 0.0f;
+    }
+    for (int y = miny; y <= maxy; ++y) {
+        const float wy = F.values[min((int)fabsf((y - py) * F.scaleFactor), 31)];
+        const int fy = y + oy - border;
+        if (fy < 0 || fy >= F.height) continue;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int x = minx + i;
+            const int fx = x + ox - border;
+            if (x > maxx || fx < 0 || fx >= F.width) continue;
+            const float w = wx[i] * wy;
+            atomicAdd(film + (size_t)fy * F.width + fx, make_float4(w * spec.x, w * spec.y, w * spec.z, w));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_film_splat(FilmRecord F, float4 *film, const float2 *pos, const float3 *rgb,
+                                                    uint32_t n, float maxComponentValue) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float *c = reinterpret_cast<const float *>(rgb) + 3 * (size_t)i;
+        filmSplat(F, film, pos[i], f3(c[0], c[1], c[2]), maxComponentValue);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Camera rays
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_generate(DeviceScene S, BatchDesc B, PathState P, Counters *C) {
+    const uint32_t W = S.film.width;
+    const uint32_t nPix = B.nRows * W;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < B.nPaths; i += gridDim.x * blockDim.x) {
+        uint32_t pixel, sample;
+        if (B.pixelList) {
+            pixel = B.pixelList[i];
+            sample = B.sampleList[i];
+        } else {
+            sample = B.firstSample + i / nPix;
+            pixel = B.rowBegin * W + i % nPix;
+        }
+        Rng rng;
+        rng.init(S.seed, pixel, sample);
+        const float2 off = rng.next2D();
+        const float2 samplePos = make_float2((float)(pixel % W) + off.x, (float)(pixel / W) + off.y);
+        float3 o, d;
+        float mint, maxt;
+        sampleCameraRay(S.camera, samplePos, o, d, mint, maxt);
+        P.rayO[i] = make_float4(o.x, o.y, o.z, mint);
+        P.rayD[i] = make_float4(d.x, d.y, d.z, maxt);
+        P.thr[i] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+        P.rad[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        P.pos[i] = make_float4(samplePos.x, samplePos.y, __uint_as_float((uint32_t)rng.state),
+                               __uint_as_float((uint32_t)(rng.state >> 32)));
+        P.flags[i] = 1u | kFlagFirst;  // rRec.newQuery: depth = 1 (integrator.h:218-225)
+        P.slot[i] = i;
+        P.medium[i] = S.camera.medium;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) C->queue[0] = B.nPaths;
+}
+
+// ------------------------------------------------------------------------------------------
+// Traversal. One thread per ray, warps fetch 32 rays at a time from a device work counter
+// (dynamic load balancing: rays of one queue differ a lot in traversal length).
+// ------------------------------------------------------------------------------------------
+template <bool kCount>
+__global__ void __launch_bounds__(128) k_trace(DeviceScene S, const float4 *__restrict__ rayO, const float4 *__restrict__ rayD,
+                                               const uint32_t *__restrict__ flags, float4 *__restrict__ hits,
+                                               const uint32_t *nPtr, uint32_t *work, Counters *C) {
+    const uint32_t n = *nPtr;
+    unsigned long long rays = 0;
+    uint32_t cn = 0, cp = 0;
+    while (true) {
+        uint32_t base = 0;
+        if (laneId() == 0) base = atomicAdd(work, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + laneId();
+        if (i < n) {
+            Hit h;
+            h.prim = kMiss;
+            h.t = kInf;
+            h.u = h.v = 0;
+            if (!(flags[i] & (kFlagDead | kFlagNoTrace))) {
+                const float4 ro = rayO[i], rd = rayD[i];
+                const float3 o = f3(ro.x, ro.y, ro.z), d = f3(rd.x, rd.y, rd.z);
+                const float mint = adaptiveMinT(o, ro.w, false);
+                traceRay<false, kCount>(S, o, d, mint, rd.w, h, &cn, &cp);
+                if (h.prim == kMiss) h.t = kInf;
+                rays++;
+            }
+            hits[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+        }
+    }
+    warpAddU64(&C->normalRays, rays);
+    if (kCount) {
+        warpAddU64(&C->nodesVisited, cn);
+        warpAddU64(&C->primsTested, cp);
+    }
+}
+
+// Shadow rays: any-hit; an unoccluded ray adds its contribution to the path record it belongs to.
+template <bool kCount>
+__global__ void __launch_bounds__(128) k_shadow(DeviceScene S, ShadowQueue Q, float4 *__restrict__ rad, const uint32_t *nPtr,
+                                                uint32_t *work, Counters *C) {
+    const uint32_t n = *nPtr;
+    unsigned long long rays = 0;
+    uint32_t cn = 0, cp = 0;
+    while (true) {
+        uint32_t base = 0;
+        if (laneId() == 0) base = atomicAdd(work, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + laneId();
+        if (i < n) {
+            const float4 ro = Q.o[i], rd = Q.d[i];
+            const float3 o = f3(ro.x, ro.y, ro.z), d = f3(rd.x, rd.y, rd.z);
+            const float mint = adaptiveMinT(o, ro.w, true);
+            Hit h;
+            rays++;
+            bool occluded = rd.w > mint && traceRay<true, kCount>(S, o, d, mint, rd.w, h, &cn, &cp);
+            if (!occluded) {
+                const float4 c = Q.c[i];
+                const uint32_t dst = __float_as_uint(c.w);
+                float4 r = rad[dst];  // exactly one shadow ray per path and bounce: no race
+                r.x += c.x;
+                r.y += c.y;
+                r.z += c.z;
+                rad[dst] = r;
+            }
+        }
+    }
+    warpAddU64(&C->shadowRays, rays);
+    if (kCount) {
+        warpAddU64(&C->nodesVisited, cn);
+        warpAddU64(&C->primsTested, cp);
+    }
+}
+
+// Standalone ray queries for the parity tests / traversal benchmark (b200pg_k_trace*).
+template <bool kShadow, bool kCount>
+__global__ void __launch_bounds__(128) k_trace_rays(DeviceScene S, const float4 *__restrict__ rays, uint32_t n,
+                                                    float4 *__restrict__ hits, uint32_t *work, Counters *C) {
+    uint32_t cn = 0, cp = 0;
+    while (true) {
+        uint32_t base = 0;
+        if (laneId() == 0) base = atomicAdd(work, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + laneId();
+        if (i < n) {
+            const float4 ro = rays[2 * i], rd = rays[2 * i + 1];
+            const float3 o = f3(ro.x, ro.y, ro.z), d = f3(rd.x, rd.y, rd.z);
+            const float mint = adaptiveMinT(o, ro.w, kShadow);
+            Hit h;
+            h.prim = kMiss;
+            h.t = kInf;
+            h.u = h.v = 0;
+            if (rd.w > mint) traceRay<kShadow, kCount>(S, o, d, mint, rd.w, h, &cn, &cp);
+            if (h.prim == kMiss) { h.t = kInf; h.u = h.v = 0; }
+            const uint32_t gid = h.prim == kMiss ? kMiss : S.primGlobalId[h.prim];
+            hits[i] = make_float4(h.t, h.u, h.v, __uint_as_float(gid));
+        }
+    }
+    if (kCount) {
+        warpAddU64(&C->nodesVisited, cn);
+        warpAddU64(&C->primsTested, cp);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Shade stage (surface path tracer, ProgressiveMIPathTracer::Li)
+// ------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(128) k_shade(ShadeArgs A) {
+    const DeviceScene &S = A.S;
+    const IntegratorConfig &cfg = A.cfg;
+    const uint32_t n = A.C->queue[A.bounce];
+    uint32_t *nextCount = &A.C->queue[A.bounce + 1];
+    uint32_t *shadowCount = &A.C->shadow[A.bounce];
+    unsigned long long donePaths = 0, doneLen = 0;
+
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + laneId();
+        const bool valid = i < n;
+
+        bool alive = false;      // continues into the next queue
+        bool wantShadow = false;
+        bool terminate = false;
+        float4 ro, rd, thr4, rad4, pos4;
+        uint32_t fl = 0, slot = 0;
+        int medium = -1;
+        float3 L = f3(0.0f), thr = f3(1.0f);
+        float eta = 1.0f;
+        Rng rng;
+        rng.state = 0;
+        rng.inc = 1;
+        float3 newO = f3(0.0f), newD = f3(0.0f);
+        float newPdf = 0.0f;
+        float3 shO = f3(0.0f), shD = f3(0.0f), shC = f3(0.0f);
+        float shMaxT = 0.0f;
+        uint32_t depth = 0;
+
+        if (valid) {
+            ro = A.cur.rayO[i];
+            rd = A.cur.rayD[i];
+            thr4 = A.cur.thr[i];
+            rad4 = A.cur.rad[i];
+            pos4 = A.cur.pos[i];
+            fl = A.cur.flags[i];
+            slot = A.cur.slot[i];
+            medium = A.cur.medium[i];
+            const float4 h4 = A.hits[i];
+            L = f3(rad4.x, rad4.y, rad4.z);
+            thr = f3(thr4.x, thr4.y, thr4.z);
+            eta = thr4.w;
+            depth = fl & kDepthMask;
+            const float2 samplePos = make_float2(pos4.x, pos4.y);
+            const uint32_t pixel = (uint32_t)samplePos.y * (uint32_t)S.film.width + (uint32_t)samplePos.x;
+            rng.state = ((uint64_t)__float_as_uint(pos4.w) << 32) | (uint64_t)__float_as_uint(pos4.z);
+            rng.inc = ((uint64_t)pixel << 1) | 1ULL;
+            const float3 o = f3(ro.x, ro.y, ro.z), d = f3(rd.x, rd.y, rd.z);
+            Hit h;
+            h.t = h4.x;
+            h.u = h4.y;
+            h.v = h4.z;
+            h.prim = __float_as_uint(h4.w);
+
+            if (fl & kFlagDead) {
+                terminate = true;
+            } else if (h.prim == kMiss) {
+                terminate = true;  // no environment emitter on this path (progressive_path.cpp:150-159)
+            } else {
+                Intersection its;
+                fillIntersection(S, o, d, h, its);
+                const BsdfRecord &bsdf = S.bsdfs[its.bsdf];
+
+                // ---- emitted radiance: directly visible (first hit) or reached by BSDF sampling (MIS)
+                if (its.emitter >= 0) {
+                    const float3 Le = dot(its.sh.n, -d) <= 0 ? f3(0.0f) : ld3(S.emitters[its.emitter].radiance);  // area.cpp:104-109
+                    if (fl & kFlagFirst) {
+                        if (!cfg.hideEmitters) L += thr * Le;  // progressive_path.cpp:167-169
+                    } else {
+                        const float lumPdf = (cfg.useNee && !(fl & kFlagPrevDelta))
+                                                 ? pdfEmitterDirect(S, its.emitter, d, its.sh.n, its.t) : 0.0f;
+                        const float weight = cfg.useNee ? miWeight(rad4.w, lumPdf) : 1.0f;
+                        L += thr * Le * weight;  // progressive_path.cpp:276-284
+                    }
+                }
+                // ---- Russian roulette closes the previous loop iteration (progressive_path.cpp:296-306)
+                if (!(fl & kFlagFirst)) {
+                    if (depth++ >= (uint32_t)cfg.rrDepth) {
+                        const float q = fminf(maxComp(thr) * eta * eta, 0.95f);
+                        if (rng.next1D() >= q)
+                            terminate = true;
+                        else
+                            thr = thr / q;
+                    }
+                }
+                // ---- loop condition and depth / strict-normal stops (:149, :175-184)
+                if (!terminate && !((int)depth <= cfg.maxDepth || cfg.maxDepth < 0)) terminate = true;
+                if (!terminate && (((int)depth >= cfg.maxDepth && cfg.maxDepth > 0) ||
+                                   (cfg.strictNormals && dot(d, its.geoN) * its.wi.z >= 0)))
+                    terminate = true;
+
+                if (!terminate) {
+                    // ---- direct illumination sampling (:191-219)
+                    const uint32_t btype = bsdf.typeFlags;
+                    if (cfg.useNee && (btype & kSmooth)) {
+                        const float3 refN = (btype & (kTransmission | kBackSide)) == 0 ? its.sh.n : f3(0.0f);  // records.inl:160-164
+                        DirectSample dRec;
+                        const float2 u = rng.next2D();
+                        const float3 value = sampleEmitterDirect(S, its.p, refN, u, dRec);
+                        if (!isZero(value)) {
+                            const float3 woL = its.sh.toLocal(dRec.d);
+                            const float3 bsdfVal = bsdfEval(bsdf, its.wi, woL);
+                            if (!isZero(bsdfVal) && (!cfg.strictNormals || dot(its.geoN, dRec.d) * woL.z > 0)) {
+                                const float bPdf = bsdfPdf(bsdf, its.wi, woL);
+                                const float weight = miWeight(dRec.pdf, bPdf);
+                                shC = thr * value * bsdfVal * weight;
+                                shO = its.p;
+                                shD = dRec.d;
+                                shMaxT = dRec.dist * (1 - kShadowEpsilon);  // scene.cpp:883-884
+                                wantShadow = true;
+                            }
+                        }
+                    }
+                    // ---- BSDF sampling (:226-238)
+                    float bPdf, bEta;
+                    uint32_t sampledType;
+                    float3 woL;
+                    const float3 bsdfWeight = bsdfSample(bsdf, its.wi, rng.next2D(), woL, bPdf, bEta, sampledType);
+                    if (isZero(bsdfWeight)) {
+                        terminate = true;
+                    } else {
+                        const float3 wo = its.sh.toWorld(woL);
+                        if (cfg.strictNormals && dot(its.geoN, wo) * woL.z <= 0) {
+                            terminate = true;
+                        } else {
+                            thr *= bsdfWeight;  // (:271-272; a miss of the new ray terminates next bounce)
+                            eta *= bEta;
+                            newO = its.p;
+                            newD = wo;
+                            newPdf = bPdf;
+                            fl &= ~(kFlagFirst | kFlagPrevDelta);
+                            if (sampledType & kDelta) fl |= kFlagPrevDelta;
+                            if (sampledType != kNull) fl |= kFlagScattered;
+                            alive = true;
+                        }
+                    }
+                }
+            }
+            if (terminate && wantShadow) {
+                // park the record for one bounce so that the shadow ray has somewhere to land
+                alive = true;
+                fl |= kFlagDead;
+                terminate = false;
+            }
+        }
+
+        // ---- compaction into the next queue / shadow queue (one atomic per warp each)
+        const uint32_t j = warpAppend(nextCount, alive);
+        const uint32_t sidx = warpAppend(shadowCount, wantShadow);
+        if (alive) {
+            A.next.rayO[j] = make_float4(newO.x, newO.y, newO.z, kEpsilon);
+            A.next.rayD[j] = make_float4(newD.x, newD.y, newD.z, kInf);
+            A.next.thr[j] = make_float4(thr.x, thr.y, thr.z, eta);
+            A.next.rad[j] = make_float4(L.x, L.y, L.z, newPdf);
+            A.next.pos[j] = make_float4(pos4.x, pos4.y, __uint_as_float((uint32_t)rng.state),
+                                        __uint_as_float((uint32_t)(rng.state >> 32)));
+            A.next.flags[j] = (fl & ~kDepthMask) | (depth & kDepthMask);
+            A.next.slot[j] = slot;
+            A.next.medium[j] = medium;
+        }
+        if (wantShadow) {
+            A.shadow.o[sidx] = make_float4(shO.x, shO.y, shO.z, kEpsilon);
+            A.shadow.d[sidx] = make_float4(shD.x, shD.y, shD.z, shMaxT);
+            A.shadow.c[sidx] = make_float4(shC.x, shC.y, shC.z, __uint_as_float(j));
+        }
+        if (valid && terminate) {
+            donePaths++;
+            doneLen += depth;
+            if (A.radianceOut) {
+                A.radianceOut[3 * (size_t)slot + 0] = L.x;
+                A.radianceOut[3 * (size_t)slot + 1] = L.y;
+                A.radianceOut[3 * (size_t)slot + 2] = L.z;
+            } else {
+                filmSplat(S.film, A.film, make_float2(pos4.x, pos4.y), L, cfg.maxComponentValue);
+            }
+        }
+    }
+    warpAddU64(&A.C->paths, donePaths);
+    warpAddU64(&A.C->pathLen, doneLen);
+}
+
+// Flush whatever is still queued after the last bounce (only parked/dead records can remain).
+__global__ void __launch_bounds__(256) k_flush(ShadeArgs A) {
+    const uint32_t n = A.C->queue[A.bounce];
+    unsigned long long donePaths = 0, doneLen = 0;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + laneId();
+        if (i < n) {
+            const float4 rad4 = A.cur.rad[i], pos4 = A.cur.pos[i];
+            const uint32_t slot = A.cur.slot[i];
+            donePaths++;
+            doneLen += A.cur.flags[i] & kDepthMask;
+            if (A.radianceOut) {
+                A.radianceOut[3 * (size_t)slot + 0] = rad4.x;
+                A.radianceOut[3 * (size_t)slot + 1] = rad4.y;
+                A.radianceOut[3 * (size_t)slot + 2] = rad4.z;
+            } else {
+                filmSplat(A.S.film, A.film, make_float2(pos4.x, pos4.y), f3(rad4.x, rad4.y, rad4.z), A.cfg.maxComponentValue);
+            }
+        }
+    }
+    warpAddU64(&A.C->paths, donePaths);
+    warpAddU64(&A.C->pathLen, doneLen);
+}
+
+// ------------------------------------------------------------------------------------------
+// BSDF test kernel (b200pg_k_bsdf)
+// ------------------------------------------------------------------------------------------
+__global__ void k_bsdf_test(DeviceScene S, int bsdfIndex, const float *wi, const float *wo, const float *u, uint32_t n,
+                            float *outEval, float *outPdf, float *outWo, float *outWeight, float *outSpdf, uint32_t *outFlags) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const BsdfRecord &b = S.bsdfs[bsdfIndex];
+        const float3 vi = ld3(wi + 3 * (size_t)i), vo = ld3(wo + 3 * (size_t)i);
+        const float3 e = bsdfEval(b, vi, vo);
+        outEval[3 * (size_t)i] = e.x; outEval[3 * (size_t)i + 1] = e.y; outEval[3 * (size_t)i + 2] = e.z;
+        outPdf[i] = bsdfPdf(b, vi, vo);
+        float3 so;
+        float spdf, eta;
+        uint32_t st;
+        float3 w = bsdfSample(b, vi, make_float2(u[2 * (size_t)i], u[2 * (size_t)i + 1]), so, spdf, eta, st);
+        if (isZero(w)) { so = f3(0.0f); spdf = 0; }
+        outWo[3 * (size_t)i] = so.x; outWo[3 * (size_t)i + 1] = so.y; outWo[3 * (size_t)i + 2] = so.z;
+        outWeight[3 * (size_t)i] = w.x; outWeight[3 * (size_t)i + 1] = w.y; outWeight[3 * (size_t)i + 2] = w.z;
+        outSpdf[i] = spdf;
+        outFlags[i] = st;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launch wrappers (called from integrator.cpp, compiled by the host compiler)
+// ------------------------------------------------------------------------------------------
+static int g_numSMs = 0;
+static int numSMs() {
+    if (!g_numSMs) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_numSMs, cudaDevAttrMultiProcessorCount, dev);
+        if (g_numSMs <= 0) g_numSMs = 148;
+    }
+    return g_numSMs;
+}
+template <typename K>
+static int persistentGrid(K kernel, int block) {
+    int perSM = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, block, 0);
+    if (perSM <= 0) perSM = 1;
+    return numSMs() * perSM;  // grid = multiple of the SM count, one resident wave
+}
+
+void launchGenerate(const DeviceScene &S, const BatchDesc &B, const PathState &P, Counters *C, cudaStream_t st) {
+    static int grid = persistentGrid(k_generate, 256);
+    k_generate<<<grid, 256, 0, st>>>(S, B, P, C);
+}
+void launchTrace(const DeviceScene &S, const PathState &P, float4 *hits, const uint32_t *nPtr, uint32_t *work, Counters *C,
+                 bool count, cudaStream_t st) {
+    static int grid = persistentGrid(k_trace<false>, 128);
+    if (count)
+        k_trace<true><<<grid, 128, 0, st>>>(S, P.rayO, P.rayD, P.flags, hits, nPtr, work, C);
+    else
+        k_trace<false><<<grid, 128, 0, st>>>(S, P.rayO, P.rayD, P.flags, hits, nPtr, work, C);
+}
+void launchShadow(const DeviceScene &S, const ShadowQueue &Q, float4 *rad, const uint32_t *nPtr, uint32_t *work, Counters *C,
+                  bool count, cudaStream_t st) {
+    static int grid = persistentGrid(k_shadow<false>, 128);
+    if (count)
+        k_shadow<true><<<grid, 128, 0, st>>>(S, Q, rad, nPtr, work, C);
+    else
+        k_shadow<false><<<grid, 128, 0, st>>>(S, Q, rad, nPtr, work, C);
+}
+void launchShade(const ShadeArgs &A, cudaStream_t st) {
+    static int grid = persistentGrid(k_shade, 128);
+    k_shade<<<grid, 128, 0, st>>>(A);
+}
+void launchFlush(const ShadeArgs &A, cudaStream_t st) {
+    static int grid = persistentGrid(k_flush, 256);
+    k_flush<<<grid, 256, 0, st>>>(A);
+}
+void launchTraceRays(const DeviceScene &S, const float4 *rays, uint32_t n, float4 *hits, uint32_t *work, Counters *C, bool shadow,
+                     bool count, cudaStream_t st) {
+    static int grid = persistentGrid(k_trace_rays<false, false>, 128);
+    if (shadow) {
+        if (count) k_trace_rays<true, true><<<grid, 128, 0, st>>>(S, rays, n, hits, work, C);
+        else k_trace_rays<true, false><<<grid, 128, 0, st>>>(S, rays, n, hits, work, C);
+    } else {
+        if (count) k_trace_rays<false, true><<<grid, 128, 0, st>>>(S, rays, n, hits, work, C);
+        else k_trace_rays<false, false><<<grid, 128, 0, st>>>(S, rays, n, hits, work, C);
+    }
+}
+void launchFilmSplat(const FilmRecord &F, float4 *film, const float2 *pos, const float3 *rgb, uint32_t n, float maxComponentValue,
+                     cudaStream_t st) {
+    int grid = numSMs() * 4;
+    k_film_splat<<<grid, 256, 0, st>>>(F, film, pos, rgb, n, maxComponentValue);
+}
+void launchBsdfTest(const DeviceScene &S, int bsdfIndex, const float *wi, const float *wo, const float *u, uint32_t n, float *outEval,
+                    float *outPdf, float *outWo, float *outWeight, float *outSpdf, uint32_t *outFlags, cudaStream_t st) {
+    k_bsdf_test<<<numSMs(), 128, 0, st>>>(S, bsdfIndex, wi, wo, u, n, outEval, outPdf, outWo, outWeight, outSpdf, outFlags);
+}
+
+}  // namespace pg

@@ -1,0 +1,107 @@
+// pg_types.h -- POD records shared by the host scene compiler and the CUDA kernels.
+// Layouts are chosen for 16-byte vector loads (LDG.128): every record is a whole number of float4s.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/b200pg.h"
+
+namespace pg {
+
+static const uint32_t kNoTriangle = 0xFFFFFFFFu;  // rectangle marker, as KNoTriangleFlag in skdtree.h
+static const uint32_t kMiss = 0xFFFFFFFFu;
+
+// BVH2 node, 64 B = 4 x float4 (one 128-B line holds two nodes).
+//   q0 = c0.min.x c0.max.x c0.min.y c0.max.y
+//   q1 = c1.min.x c1.max.x c1.min.y c1.max.y
+//   q2 = c0.min.z c0.max.z c1.min.z c1.max.z
+//   q3 = child0, child1 (int bits), pad, pad.   child >= 0: inner node index;
+//        child < 0: leaf, ~child = (first_prim << 4) | count   (count <= 15)
+struct BvhNode {
+    float q[16];
+};
+
+// Primitive record, 48 B = 3 x float4, stored in BVH leaf order.
+// Triangle (Wald projection, same arithmetic as triaccel.h:37-158):
+//   q0 = k(bits) n_u n_v n_d | q1 = a_u a_v b_nu b_nv | q2 = c_nu c_nv shape(bits) prim(bits)
+// Rectangle: q0 = kNoTriangle, rectIndex(bits), 0, 0 | q1 = 0 | q2 = 0 0 shape(bits) kNoTriangle
+struct PrimRecord {
+    float q[12];
+};
+
+// Rectangle, 8 x float4: rows of worldToObject (3), then frame/dpdu data for shading.
+//   r0..r2 = worldToObject rows (x y z w)
+//   r3 = n.xyz, invSurfaceArea   r4 = dpdu.xyz, 0   r5 = objectToWorld row0   r6 = row1   r7 = row2
+struct RectRecord {
+    float q[32];
+};
+
+struct ShapeRecord {  // 32 B
+    int32_t type;      // B200pgShapeType
+    int32_t bsdf;
+    int32_t emitter;
+    int32_t interiorMedium, exteriorMedium;
+    uint32_t primOffset;   // first global primitive id
+    uint32_t meshOffset;   // trimesh: index into the mesh table; rectangle: rect index
+    uint32_t flags;        // bit0 = has vertex normals
+};
+
+struct MeshRecord {  // offsets into the concatenated vertex/index pools
+    uint32_t vertexOffset;  // in vertices
+    uint32_t indexOffset;   // in triangles
+    uint32_t cdfOffset;     // area cdf (n_triangles + 1 floats)
+    uint32_t nTriangles;
+    float invSurfaceArea;
+    uint32_t hasNormals;
+    uint32_t pad0, pad1;
+};
+
+struct BsdfRecord {  // mirrors B200pgBsdf + derived constants
+    int32_t type, twosided;
+    float reflectance[3];
+    float specRefl[3];
+    float specTrans[3];
+    float eta, invEta;          // intIOR / extIOR
+    float condEta[3], condK[3];
+    int32_t distribution;
+    float alphaU, alphaV;
+    int32_t nonlinear;
+    float specSamplingWeight;   // roughplastic.cpp:283-286
+    float invEta2;
+    float rtIntDiff;
+    uint32_t typeFlags;         // BSDF::getType() bits
+    float rtExt[100];           // reduced rough transmittance (rtrans.h:292-388)
+    float pad[3];
+};
+
+struct EmitterRecord {
+    float radiance[3];
+    int32_t shape;
+};
+
+struct CameraRecord {
+    float sampleToCamera[16];
+    float toWorld[12];  // 3x4 affine
+    float nearClip, farClip;
+    float invResX, invResY;
+    int32_t medium;
+};
+
+struct FilmRecord {
+    int32_t width, height;
+    float radius, scaleFactor;
+    float values[32];
+};
+
+struct MediumRecord {
+    int32_t method, phaseType;
+    float scale, invMaxDensity, maxDensity, g;
+    float albedo[3];
+    int32_t res[3];
+    float aabbMin[3], aabbMax[3];
+    float worldToGrid[12];  // 3x4 affine
+    uint64_t densityOffset; // into the density pool (floats)
+    float stepSize;
+    float pad;
+};
+
+}  // namespace pg

@@ -1,0 +1,85 @@
+// wavefront.cuh -- wavefront path state, queues and kernel launch wrappers.
+//
+// Data layout in HBM (see DESIGN.md "Data layout"): path state lives in two ping-pong SoA
+// buffers that are COMPACTED every bounce (a path's record moves to its new queue index), so
+// that every stage reads and writes its state with fully coalesced 16-byte accesses.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_scene.cuh"
+#include "guiding_device.cuh"
+
+namespace pg {
+
+// flags word: bits 0-7 depth (rRec.depth), then:
+enum : uint32_t {
+    kFlagDead = 1u << 8,       // terminated but parked one bounce so its shadow ray can land
+    kFlagPrevDelta = 1u << 9,  // last sampled lobe was a delta lobe (bRec.sampledType & EDelta)
+    kFlagFirst = 1u << 10,     // rRec.type still includes EEmittedRadiance
+    kFlagScattered = 1u << 11,
+    kFlagPrevMedium = 1u << 12,  // last event was a medium scattering event
+    kFlagNoTrace = 1u << 13,
+    kDepthMask = 0xFFu
+};
+
+struct PathState {
+    float4 *rayO;     // o.xyz, mint
+    float4 *rayD;     // d.xyz, maxt
+    float4 *thr;      // throughput rgb, eta
+    float4 *rad;      // accumulated radiance rgb, pdf of the last sampled direction
+    float4 *pos;      // samplePos.xy, rng state lo/hi (bits)
+    uint32_t *flags;
+    uint32_t *slot;   // index of the camera sample inside the batch
+    int32_t *medium;  // current medium (-1 = none)
+};
+
+struct ShadowQueue {
+    float4 *o;  // o.xyz, mint
+    float4 *d;  // d.xyz, maxt
+    float4 *c;  // contribution rgb, destination path index (bits)
+    int32_t *medium;
+};
+
+struct IntegratorConfig {
+    int maxDepth, rrDepth, strictNormals, hideEmitters, useNee, volumetric;
+    float maxComponentValue;
+    // guiding
+    int guiding;
+    float guidingProbability;
+    int recordTraining;
+    int guidedDistance;
+};
+
+// device counters: per bounce {paths in queue, shadow rays}, then global statistics
+struct Counters {
+    uint32_t queue[260];
+    uint32_t shadow[260];
+    uint32_t traceWork[260];   // dynamic work-fetch cursors, one per bounce
+    uint32_t shadowWork[260];
+    uint32_t misc[16];
+    unsigned long long paths, normalRays, shadowRays, pathLen, nodesVisited, primsTested, trainSamples;
+};
+
+struct BatchDesc {
+    uint32_t nPaths;
+    uint32_t rowBegin, nRows;  // image band
+    uint32_t firstSample, nSamples;
+    const uint32_t *pixelList;   // optional explicit (pixel, sample) pairs
+    const uint32_t *sampleList;
+};
+
+struct ShadeArgs {
+    DeviceScene S;
+    IntegratorConfig cfg;
+    PathState cur, next;
+    ShadowQueue shadow;
+    const float4 *hits;
+    Counters *C;
+    float4 *film;
+    float *radianceOut;  // optional: per-slot radiance instead of film splats (b200pg_k_radiance)
+    GuideDevice G;
+    int bounce;
+};
+
+}  // namespace pg
