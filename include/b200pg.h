@@ -227,6 +227,16 @@ int b200pg_film_write(void *integ, const char *path /* .pfm */);
 int b200pg_stats(void *integ, B200pgStats *out);
 void b200pg_destroy(void *integ);
 
+/* Measurement helpers (no reference counterpart; the reference only logs "Progression[i] took t s",
+ * progressiveintegrator.cpp:314-317).
+ *   options: "count_traversal" (0/1: counting variant of the trace kernels fills bvh_nodes_visited /
+ *            prims_tested), "timing" (0/1: per-stage CUDA events).
+ *   stage times: 5 doubles / 5 launch counts = trace(closest), shade, shadow(any-hit), film, train.
+ *   scene_upload: re-sends the compiled scene host->device (bench.py's end-to-end leg). */
+int b200pg_set_option(void *integ, const char *name, int value);
+int b200pg_stage_times(void *integ, double *seconds5, uint64_t *launches5);
+int b200pg_scene_upload(void *integ, size_t *bytes);
+
 /* ------------------------------------------------------------------ */
 /*  Per-kernel entry points (HOST buffers in/out; copies are done       */
 /*  inside). Used by the parity tests and by bench.py's e2e leg.        */

@@ -54,6 +54,9 @@ def lib():
     L.b200pg_film_write.argtypes = [C.c_void_p, C.c_char_p]
     L.b200pg_stats.argtypes = [C.c_void_p, C.POINTER(A.Stats)]
     L.b200pg_destroy.argtypes = [C.c_void_p]
+    L.b200pg_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    L.b200pg_stage_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    L.b200pg_scene_upload.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
     L.b200pg_k_trace.argtypes = [C.c_void_p, fp, C.c_size_t, C.c_int, fp, u32p]
     L.b200pg_k_trace_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, fp, C.POINTER(C.c_uint64)]
     L.b200pg_k_bsdf.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_size_t, fp, fp, fp, fp, fp, u32p]
@@ -197,6 +200,21 @@ class Integrator:
         s = A.Stats()
         _check(lib().b200pg_stats(self.h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in A.Stats._fields_}
+
+    def set_option(self, name, value):
+        _check(lib().b200pg_set_option(self.h, name.encode(), int(value)))
+
+    def stage_times(self):
+        sec = (C.c_double * 5)()
+        cnt = (C.c_uint64 * 5)()
+        _check(lib().b200pg_stage_times(self.h, sec, cnt))
+        names = ("trace", "shade", "shadow", "film", "train")
+        return {n: dict(seconds=sec[i], launches=cnt[i]) for i, n in enumerate(names)}
+
+    def scene_upload(self):
+        n = C.c_size_t()
+        _check(lib().b200pg_scene_upload(self.h, C.byref(n)))
+        return n.value
 
     # ---- training hooks
     def train_accumulate(self):

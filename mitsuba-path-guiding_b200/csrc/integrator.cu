@@ -126,10 +126,61 @@ struct Integrator {
     cudaEvent_t ev[8];
     GuidingHost guide;
 
+    // per-stage CUDA-event timing on the launching stream (drained after each progression)
+    enum { kTimeTrace = 0, kTimeShade = 1, kTimeShadow = 2, kTimeFilm = 3, kTimeTrain = 4, kTimeKinds = 5 };
+    struct Span { int kind; cudaEvent_t a, b; };
+    std::vector<cudaEvent_t> evPool;
+    std::vector<Span> spans;
+    double stageSeconds[kTimeKinds] = {0, 0, 0, 0, 0};
+    uint64_t stageLaunches[kTimeKinds] = {0, 0, 0, 0, 0};
+    bool timing = true;
+    cudaEvent_t getEvent() {
+        if (evPool.empty()) {
+            cudaEvent_t e;
+            CUDA_OK(cudaEventCreate(&e));
+            return e;
+        }
+        cudaEvent_t e = evPool.back();
+        evPool.pop_back();
+        return e;
+    }
+    cudaEvent_t spanBegin() {
+        if (!timing) return nullptr;
+        cudaEvent_t a = getEvent();
+        CUDA_OK(cudaEventRecord(a, stream));
+        return a;
+    }
+    void spanEnd(int kind, cudaEvent_t a) {
+        if (!timing) return;
+        cudaEvent_t b = getEvent();
+        CUDA_OK(cudaEventRecord(b, stream));
+        spans.push_back(Span{kind, a, b});
+    }
+    void drainSpans() {  // requires a synchronised stream
+        for (auto &sp : spans) {
+            float ms = 0;
+            CUDA_OK(cudaEventElapsedTime(&ms, sp.a, sp.b));
+            stageSeconds[sp.kind] += ms * 1e-3;
+            stageLaunches[sp.kind]++;
+            evPool.push_back(sp.a);
+            evPool.push_back(sp.b);
+        }
+        spans.clear();
+        stats.seconds_trace = stageSeconds[kTimeTrace] + stageSeconds[kTimeShadow];
+        stats.seconds_shade = stageSeconds[kTimeShade];
+        stats.seconds_film = stageSeconds[kTimeFilm];
+        stats.seconds_train = stageSeconds[kTimeTrain];
+    }
+
     ~Integrator() {
         if (stream) cudaStreamDestroy(stream);
         for (auto &e : ev)
             if (e) cudaEventDestroy(e);
+        for (auto &sp : spans) {
+            cudaEventDestroy(sp.a);
+            cudaEventDestroy(sp.b);
+        }
+        for (auto &e : evPool) cudaEventDestroy(e);
     }
 
     void init() {
@@ -228,12 +279,18 @@ struct Integrator {
         int b = 0;
         for (; b < maxBounces; ++b) {
             if (cancel.load()) break;
+            cudaEvent_t t = spanBegin();
             launchTrace(S, cur, dHits.p, &C->queue[b], &C->traceWork[b], C, countTraversal, stream);
+            spanEnd(kTimeTrace, t);
             A.cur = cur;
             A.next = next;
             A.bounce = b;
+            t = spanBegin();
             launchShade(A, stream);
+            spanEnd(kTimeShade, t);
+            t = spanBegin();
             launchShadow(S, A.shadow, next.rad, &C->shadow[b], &C->shadowWork[b], C, countTraversal, stream);
+            spanEnd(kTimeShadow, t);
             stats.kernel_launches += 3;
             std::swap(cur, next);
             if (params.max_depth <= 0 && (b & 3) == 3) {  // infinite depth: poll the queue size
@@ -274,7 +331,8 @@ struct Integrator {
         if (rowBegin >= rowEnd || nSamples <= 0) return;
         size_t maxBatch = params.max_batch_paths > 0 ? (size_t)params.max_batch_paths : (size_t)4 << 20;
         const size_t rowPaths = (size_t)W;
-        auto t0 = std::chrono::steady_clock::now();
+        // device time of the whole progression: CUDA events on the launching stream
+        CUDA_OK(cudaEventRecord(ev[2], stream));
         // split: whole band x k samples if it fits, else row chunks per sample
         const size_t bandPaths = rowPaths * (rowEnd - rowBegin);
         if (bandPaths <= maxBatch) {
@@ -303,8 +361,13 @@ struct Integrator {
                     runBatch(B, nullptr);
                 }
         }
+        CUDA_OK(cudaEventRecord(ev[3], stream));
         CUDA_OK(cudaStreamSynchronize(stream));
-        stats.seconds_total += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        CUDA_OK(cudaGetLastError());
+        drainSpans();
+        float msTotal = 0;
+        CUDA_OK(cudaEventElapsedTime(&msTotal, ev[2], ev[3]));
+        stats.seconds_total += msTotal * 1e-3;
         stats.progressions_done++;
     }
 };
@@ -541,6 +604,54 @@ int b200pg_stats(void *integ, B200pgStats *out) {
 
 void b200pg_destroy(void *integ) { delete (Integrator *)integ; }
 
+int b200pg_set_option(void *integ, const char *name, int value) {
+    if (!integ || !name) return fail("null argument");
+    Integrator *self = (Integrator *)integ;
+    std::string n(name);
+    if (n == "count_traversal") self->countTraversal = value != 0;
+    else if (n == "timing") self->timing = value != 0;
+    else return fail("unknown option " + n);
+    return 0;
+}
+
+int b200pg_stage_times(void *integ, double *seconds5, uint64_t *launches5) {
+    if (!integ) return fail("null integrator");
+    Integrator *self = (Integrator *)integ;
+    for (int i = 0; i < Integrator::kTimeKinds; ++i) {
+        if (seconds5) seconds5[i] = self->stageSeconds[i];
+        if (launches5) launches5[i] = self->stageLaunches[i];
+    }
+    return 0;
+}
+
+int b200pg_scene_upload(void *integ, size_t *bytes) {
+    PG_TRY(integ)
+    HostScene &H = *self->scene;
+    size_t total = 0;
+    auto up = [&](auto &dst, const auto &src) {
+        dst.upload(src, self->stream);
+        total += src.size() * sizeof(src[0]);
+    };
+    self->dNodes.upload(reinterpret_cast<const float4 *>(H.nodes.data()), H.nodes.size() * 4, self->stream);
+    self->dPrims.upload(reinterpret_cast<const float4 *>(H.prims.data()), H.prims.size() * 3, self->stream);
+    self->dRects.upload(reinterpret_cast<const float4 *>(H.rects.data()), H.rects.size() * 8, self->stream);
+    total += H.nodes.size() * 64 + H.prims.size() * 48 + H.rects.size() * 128;
+    up(self->dShapes, H.shapeRecs);
+    up(self->dMeshes, H.meshes);
+    up(self->dPositions, H.positions);
+    up(self->dNormals, H.normals);
+    up(self->dIndices, H.indices);
+    up(self->dAreaCdf, H.areaCdf);
+    up(self->dBsdfs, H.bsdfRecs);
+    up(self->dEmitters, H.emitterRecs);
+    up(self->dEmitterCdf, H.emitterCdf);
+    up(self->dMedia, H.mediumRecs);
+    up(self->dDensity, H.densityPool);
+    CUDA_OK(cudaStreamSynchronize(self->stream));
+    if (bytes) *bytes = total;
+    PG_END
+}
+
 // ---------------------------------------------------------------------------------------------
 // per-kernel entry points
 // ---------------------------------------------------------------------------------------------
@@ -630,6 +741,7 @@ int b200pg_k_radiance(void *integ, const uint32_t *pixel, const uint32_t *sample
     CUDA_OK(cudaMemcpyAsync(out_rgb, dOut.p, 3 * n * 4, cudaMemcpyDeviceToHost, self->stream));
     CUDA_OK(cudaStreamSynchronize(self->stream));
     CUDA_OK(cudaGetLastError());
+    self->drainSpans();
     self->pullCounters();
     PG_END
 }

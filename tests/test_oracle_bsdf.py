@@ -1,0 +1,139 @@
+"""Pins the oracle's BSDF restatement the way the reference's own test does (src/tests/test_chisquare.cpp:393-620,
+src/libcore/chisquare.cpp): (i) sample().weight * pdf == eval within ERROR_REQ = 1e-2 (test_chisquare.cpp:34-38),
+(ii) chi^2 test of sample() against numerically integrated pdf() on a 10x20 (theta, phi) grid with
+thetaBins*phiBins*1000 samples (chisquare.cpp:48-58) at significance 0.0025 with Sidak correction."""
+import numpy as np
+import pytest
+from scipy import stats
+
+from bsdf_cases import bsdf_scene, random_dirs
+
+SMOOTH = ["diffuse", "twosided_diffuse", "roughconductor_beckmann_0.3", "roughconductor_ggx_0.15",
+          "roughplastic_beckmann_0.7", "roughplastic_ggx_0.2_twosided"]
+SIGNIFICANCE = 0.0025
+N_WI = 6  # the reference uses 20 incident directions; 6 keeps the CPU suite short
+
+
+@pytest.fixture(scope="module")
+def scene(oracle):
+    sb, idx = bsdf_scene()
+    return oracle.scene(sb), idx
+
+
+@pytest.mark.parametrize("name", SMOOTH)
+def test_weight_times_pdf_equals_eval(scene, name):
+    sc, idx = scene
+    rng = np.random.RandomState(11)
+    n = 20000
+    wi = random_dirs(rng, n, upper=not name.count("twosided"))
+    u = rng.rand(n, 2).astype(np.float32)
+    s = sc.bsdf(idx[name], wi, wi, u)
+    ok = s["spdf"] > 0
+    assert ok.mean() > 0.5
+    e = sc.bsdf(idx[name], wi[ok], s["wo"][ok], u[ok])
+    lhs = s["weight"][ok] * s["spdf"][ok, None]
+    rhs = e["eval"]
+    # test_chisquare.cpp:530-560 compares per channel, relative for large values
+    err = np.abs(lhs - rhs) / np.maximum(np.abs(rhs), 1.0)
+    assert err.max() < 1e-2
+    # the pdf returned by sample() and by pdf() must agree as well
+    perr = np.abs(s["spdf"][ok] - e["pdf"]) / np.maximum(e["pdf"], 1.0)
+    assert perr.max() < 1e-2
+
+
+def _chi2(sc, index, wi, rng, theta_bins=10, phi_bins=20, sub=24):
+    n = theta_bins * phi_bins * 1000
+    u = rng.rand(n, 2).astype(np.float32)
+    wis = np.repeat(wi[None], n, 0).astype(np.float32)
+    s = sc.bsdf(index, wis, wis, u)
+    ok = s["spdf"] > 0
+    wo = s["wo"][ok]
+    theta = np.arccos(np.clip(wo[:, 2], -1, 1))
+    phi = np.arctan2(wo[:, 1], wo[:, 0])
+    phi[phi < 0] += 2 * np.pi
+    ti = np.minimum((theta / np.pi * theta_bins).astype(int), theta_bins - 1)
+    pi_ = np.minimum((phi / (2 * np.pi) * phi_bins).astype(int), phi_bins - 1)
+    obs = np.bincount(ti * phi_bins + pi_, minlength=theta_bins * phi_bins).astype(np.float64)
+    # expected frequencies: midpoint quadrature of pdf * sin(theta) over each bin
+    tt = (np.arange(theta_bins * sub) + 0.5) * (np.pi / (theta_bins * sub))
+    pp = (np.arange(phi_bins * sub) + 0.5) * (2 * np.pi / (phi_bins * sub))
+    T, P = np.meshgrid(tt, pp, indexing="ij")
+    d = np.stack([np.sin(T) * np.cos(P), np.sin(T) * np.sin(P), np.cos(T)], -1).reshape(-1, 3).astype(np.float32)
+    pdf = sc.bsdf(index, np.repeat(wi[None], d.shape[0], 0).astype(np.float32), d, np.zeros((d.shape[0], 2), np.float32))["pdf"]
+    w = (pdf.reshape(T.shape) * np.sin(T)) * (np.pi / (theta_bins * sub)) * (2 * np.pi / (phi_bins * sub))
+    exp = w.reshape(theta_bins, sub, phi_bins, sub).sum((1, 3)).ravel() * n
+    # pool low-frequency cells (chisquare.cpp: minExpFrequency = 5)
+    order = np.argsort(exp)
+    pooled_o = pooled_e = 0.0
+    chsq, dof = 0.0, 0
+    for i in order:
+        if exp[i] == 0:
+            if obs[i] > n * 1e-5:
+                return 0.0  # samples in a region of zero density
+            continue
+        if exp[i] < 5:
+            pooled_o += obs[i]
+            pooled_e += exp[i]
+            continue
+        chsq += (obs[i] - exp[i]) ** 2 / exp[i]
+        dof += 1
+    if pooled_e > 0:
+        chsq += (pooled_o - pooled_e) ** 2 / pooled_e
+        dof += 1
+    return float(stats.chi2.sf(chsq, max(dof - 1, 1)))
+
+
+@pytest.mark.parametrize("name", SMOOTH)
+def test_chi_square_sampling_vs_pdf(scene, name):
+    sc, idx = scene
+    rng = np.random.RandomState(5)
+    alpha = 1 - (1 - SIGNIFICANCE) ** (1.0 / N_WI)  # Sidak, test_chisquare.cpp
+    for k in range(N_WI):
+        wi = random_dirs(rng, 1, upper=True)[0]
+        wi[2] = max(wi[2], 0.05)
+        wi /= np.linalg.norm(wi)
+        p = _chi2(sc, idx[name], wi, rng)
+        assert p > alpha, "chi^2 rejected %s at wi=%s (p=%g)" % (name, wi, p)
+
+
+def test_dielectric_delta_lobes(scene):
+    """dielectric.cpp:289-340: reflection with probability F, refraction otherwise; weights 1 and eta^-2-type factors."""
+    sc, idx = scene
+    rng = np.random.RandomState(3)
+    n = 50000
+    wi = random_dirs(rng, n)
+    u = rng.rand(n, 2).astype(np.float32)
+    s = sc.bsdf(idx["dielectric_water_air"], wi, wi, u)
+    refl = (s["flags"] & 0x20) != 0
+    trans = (s["flags"] & 0x40) != 0
+    assert (refl ^ trans).all()
+    # reflection mirrors wi about the normal, weight = specularReflectance = 1
+    np.testing.assert_allclose(s["wo"][refl], wi[refl] * np.array([-1, -1, 1], np.float32), atol=1e-6)
+    np.testing.assert_allclose(s["weight"][refl], 1.0, atol=1e-6)
+    # refraction: Snell's law and the radiance scaling factor (eta_i/eta_t)^2
+    eta = np.float32(1.3330) / np.float32(1.000277)
+    sin_i = np.sqrt(1 - wi[trans, 2] ** 2)
+    sin_t = np.sqrt(1 - s["wo"][trans, 2] ** 2)
+    ratio = np.where(wi[trans, 2] > 0, 1 / eta, eta)
+    np.testing.assert_allclose(sin_t, sin_i * ratio, atol=2e-5)
+    np.testing.assert_allclose(s["weight"][trans, 0], ratio ** 2, rtol=1e-5)
+    assert (np.sign(s["wo"][trans, 2]) == -np.sign(wi[trans, 2])).all()
+    # probability of reflection equals the Fresnel term: check against the empirical frequency at normal incidence
+    wi0 = np.repeat(np.array([[0, 0, 1]], np.float32), n, 0)
+    s0 = sc.bsdf(idx["dielectric_water_air"], wi0, wi0, u)
+    F = ((eta - 1) / (eta + 1)) ** 2
+    assert abs(((s0["flags"] & 0x20) != 0).mean() - F) < 3 * np.sqrt(F / n) + 1e-4
+    # eval/pdf w.r.t. solid angle are zero for delta lobes
+    e = sc.bsdf(idx["dielectric_water_air"], wi, s["wo"], u)
+    assert (e["eval"] == 0).all() and (e["pdf"] == 0).all()
+
+
+def test_energy_conservation(scene):
+    """E[weight] <= 1 for every model with unit specular reflectance (albedo of a BRDF cannot exceed one)."""
+    sc, idx = scene
+    rng = np.random.RandomState(9)
+    n = 200000
+    for name in SMOOTH:
+        wi = np.repeat(np.array([[0.3, 0.1, 0.9486833]], np.float32), n, 0)
+        s = sc.bsdf(idx[name], wi, wi, rng.rand(n, 2).astype(np.float32))
+        assert s["weight"].mean(0).max() <= 1.0 + 5e-3, name

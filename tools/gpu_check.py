@@ -50,3 +50,8 @@ ig, io = film_g[..., :3] / np.maximum(film_g[..., 4:5], 1e-20), develop(film_o)
 rel = np.abs(ig - io).mean() / io.mean()
 print("image rel L1", float(rel), "weight max diff", float(np.abs(film_g[..., 4] - film_o[..., 4]).max()))
 print("GPU Mpaths/s", st["paths"] / t_g / 1e6, "CPU Mpaths/s", st_o["paths"] / st_o["seconds"] / 1e6)
+mm = np.where(prim_o2 != prim_g2)[0]
+om = prim_o2[mm] == 0xFFFFFFFF; gm = prim_g2[mm] == 0xFFFFFFFF
+print("trace2 mismatch: oracle miss", int(om.sum()), "gpu miss", int(gm.sum()), "both hit", int((~om & ~gm).sum()))
+for i in mm[:8]:
+    print(r2[i], tuv_o2[i], prim_o2[i], tuv_g2[i], prim_g2[i], "src prim", prim_o[m][i])
