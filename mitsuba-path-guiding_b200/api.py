@@ -177,8 +177,11 @@ class Integrator:
     def film_clear(self):
         _check(lib().b200pg_film_clear(self.h))
 
-    def film(self):
-        out = np.zeros((self.H, self.W, 5), np.float32)
+    def film(self, out=None):
+        """Raw accumulators (H, W, 5) = R, G, B, alpha, weight. Pass a pinned ``out`` array for a fast copy."""
+        if out is None:
+            out = np.empty((self.H, self.W, 5), np.float32)
+        assert out.dtype == np.float32 and out.size == self.H * self.W * 5 and out.flags["C_CONTIGUOUS"]
         _check(lib().b200pg_film_read(self.h, _f(out)))
         return out
 

@@ -33,6 +33,7 @@ struct DeviceScene {
     const MediumRecord *media;
     const float *density;
     const uint32_t *primGlobalId;
+    const PrimInfo *primInfo;
     uint32_t nEmitters;
     uint32_t nPrims;
     CameraRecord camera;
@@ -59,107 +60,86 @@ PG_DEV float adaptiveMinT(float3 o, float mint, bool shadow) {
 template <bool kAnyHit, bool kCount>
 PG_DEV bool traceRay(const DeviceScene &S, float3 o, float3 d, float mint, float maxt, Hit &hit, uint32_t *cntNodes,
                      uint32_t *cntPrims) {
+    // "while-while" traversal: every lane first descends to its next leaf, then the warp processes
+    // leaves together, so that the (uniform, branch-free) primitive test runs with many lanes active.
     const float3 idir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    int stack[64];
+    const int kDone = (int)0x80000000;  // ~kDone is not a valid leaf code
+    int stack[48];
     int sp = 0;
     int node = 0;
     hit.prim = kMiss;
     hit.t = maxt;
     float tmax = maxt;
     while (true) {
-        if (node >= 0) {
+        while (node >= 0) {
             const float4 n0 = __ldg(S.nodes + 4 * node + 0);
             const float4 n1 = __ldg(S.nodes + 4 * node + 1);
             const float4 n2 = __ldg(S.nodes + 4 * node + 2);
             const float4 n3 = __ldg(S.nodes + 4 * node + 3);
             if (kCount) (*cntNodes)++;
             // slabs; fminf/fmaxf drop NaNs from 0*inf
-            float c0lox = (n0.x - o.x) * idir.x, c0hix = (n0.y - o.x) * idir.x;
-            float c0loy = (n0.z - o.y) * idir.y, c0hiy = (n0.w - o.y) * idir.y;
-            float c0loz = (n2.x - o.z) * idir.z, c0hiz = (n2.y - o.z) * idir.z;
-            float c1lox = (n1.x - o.x) * idir.x, c1hix = (n1.y - o.x) * idir.x;
-            float c1loy = (n1.z - o.y) * idir.y, c1hiy = (n1.w - o.y) * idir.y;
-            float c1loz = (n2.z - o.z) * idir.z, c1hiz = (n2.w - o.z) * idir.z;
-            float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), mint));
-            float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tmax));
-            float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), mint));
-            float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tmax));
+            const float c0lox = (n0.x - o.x) * idir.x, c0hix = (n0.y - o.x) * idir.x;
+            const float c0loy = (n0.z - o.y) * idir.y, c0hiy = (n0.w - o.y) * idir.y;
+            const float c0loz = (n2.x - o.z) * idir.z, c0hiz = (n2.y - o.z) * idir.z;
+            const float c1lox = (n1.x - o.x) * idir.x, c1hix = (n1.y - o.x) * idir.x;
+            const float c1loy = (n1.z - o.y) * idir.y, c1hiy = (n1.w - o.y) * idir.y;
+            const float c1loz = (n2.z - o.z) * idir.z, c1hiz = (n2.w - o.z) * idir.z;
+            const float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), mint));
+            const float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tmax));
+            const float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), mint));
+            const float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tmax));
             // conservative far bound (flat boxes, rounding): 1 + 2*gamma(3)
-            bool h0 = t0n <= t0f * 1.0000004f;
-            bool h1 = t1n <= t1f * 1.0000004f;
+            const bool h0 = t0n <= t0f * 1.0000004f;
+            const bool h1 = t1n <= t1f * 1.0000004f;
             int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
             if (h0 && h1) {
                 if (t1n < t0n) {
-                    int tmp = c0; c0 = c1; c1 = tmp;
+                    const int tmp = c0; c0 = c1; c1 = tmp;
                 }
                 stack[sp++] = c1;
                 node = c0;
-            } else if (h0) {
-                node = c0;
-            } else if (h1) {
-                node = c1;
+            } else if (h0 | h1) {
+                node = h0 ? c0 : c1;
             } else {
-                if (sp == 0) break;
-                node = stack[--sp];
+                node = sp ? stack[--sp] : kDone;
             }
-        } else {
+        }
+        if (node == kDone) break;
+        {
             const uint32_t code = (uint32_t)(~node);
-            const uint32_t first = code >> 4, count = code & 15u;
+            const uint32_t first = code >> kLeafShift, count = code & 7u, rectMask = (code >> 3) & 15u;
             for (uint32_t i = 0; i < count; ++i) {
-                const float4 q0 = __ldg(S.prims + 3 * (first + i));
-                const uint32_t k = __float_as_uint(q0.x);
+                const float4 r0 = __ldg(S.prims + 3 * (first + i));
+                const float4 r1 = __ldg(S.prims + 3 * (first + i) + 1);
+                const float4 r2 = __ldg(S.prims + 3 * (first + i) + 2);
                 if (kCount) (*cntPrims)++;
-                float t, u, v;
-                bool ok = false;
-                if (k != kNoTriangle) {
-                    if (k > 2) continue;  // degenerate triangle (TriAccel::load failure, triaccel.h:80-83)
-                    const float4 q1 = __ldg(S.prims + 3 * (first + i) + 1);
-                    const float4 q2 = __ldg(S.prims + 3 * (first + i) + 2);
-                    // Wald's projected test, triaccel.h:96-158
-                    float o_u, o_v, o_k, d_u, d_v, d_k;
-                    if (k == 0) { o_u = o.y; o_v = o.z; o_k = o.x; d_u = d.y; d_v = d.z; d_k = d.x; }
-                    else if (k == 1) { o_u = o.z; o_v = o.x; o_k = o.y; d_u = d.z; d_v = d.x; d_k = d.y; }
-                    else { o_u = o.x; o_v = o.y; o_k = o.z; d_u = d.x; d_v = d.y; d_k = d.z; }
-                    t = (q0.w - o_u * q0.y - o_v * q0.z - o_k) / (d_u * q0.y + d_v * q0.z + d_k);
-                    if (!(t < mint || t > tmax)) {
-                        const float hu = o_u + t * d_u - q1.x;
-                        const float hv = o_v + t * d_v - q1.y;
-                        u = hv * q1.z + hu * q1.w;
-                        v = hu * q2.x + hv * q2.y;
-                        ok = u >= 0 && v >= 0 && u + v <= 1.0f;
-                    }
-                } else {
-                    // rectangle.cpp:125-148: transform to object space, plane z = 0, |x|,|y| <= 1
-                    const uint32_t ri = __float_as_uint(q0.y);
-                    const float4 r0 = __ldg(S.rects + 8 * ri), r1 = __ldg(S.rects + 8 * ri + 1), r2 = __ldg(S.rects + 8 * ri + 2);
-                    float3 lo = f3(r0.x * o.x + r0.y * o.y + r0.z * o.z + r0.w, r1.x * o.x + r1.y * o.y + r1.z * o.z + r1.w,
-                                   r2.x * o.x + r2.y * o.y + r2.z * o.z + r2.w);
-                    float3 ld = f3(r0.x * d.x + r0.y * d.y + r0.z * d.z, r1.x * d.x + r1.y * d.y + r1.z * d.z,
-                                   r2.x * d.x + r2.y * d.y + r2.z * d.z);
-                    t = -lo.z / ld.z;
-                    if (t >= mint && t <= tmax) {
-                        float lx = lo.x + ld.x * t, ly = lo.y + ld.y * t;
-                        if (fabsf(lx) <= 1 && fabsf(ly) <= 1) {
-                            ok = true;
-                            u = lx;
-                            v = ly;
+                // local = M o + w, local direction = M d (rectangle.cpp:125-133 for rectangles)
+                const float loz = r2.x * o.x + r2.y * o.y + r2.z * o.z + r2.w;
+                const float ldz = r2.x * d.x + r2.y * d.y + r2.z * d.z;
+                const float t = -loz / ldz;
+                if (t >= mint && t <= tmax) {
+                    const float lox = r0.x * o.x + r0.y * o.y + r0.z * o.z + r0.w;
+                    const float loy = r1.x * o.x + r1.y * o.y + r1.z * o.z + r1.w;
+                    const float ldx = r0.x * d.x + r0.y * d.y + r0.z * d.z;
+                    const float ldy = r1.x * d.x + r1.y * d.y + r1.z * d.z;
+                    const float u = lox + ldx * t, v = loy + ldy * t;
+                    const bool isRect = (rectMask >> i) & 1u;
+                    const bool ok = isRect ? (fabsf(u) <= 1 && fabsf(v) <= 1) : (u >= 0 && v >= 0 && u + v <= 1.0f);
+                    if (ok) {
+                        if (kAnyHit) {
+                            hit.prim = first + i;
+                            return true;
                         }
-                    }
-                }
-                if (ok) {
-                    if (kAnyHit) {
+                        tmax = t;
+                        hit.t = t;
+                        hit.u = u;
+                        hit.v = v;
                         hit.prim = first + i;
-                        return true;
                     }
-                    tmax = t;
-                    hit.t = t;
-                    hit.u = u;
-                    hit.v = v;
-                    hit.prim = first + i;
                 }
             }
-            if (sp == 0) break;
-            node = stack[--sp];
+            node = sp ? stack[--sp] : kDone;
+            if (node == kDone) break;
         }
     }
     return hit.prim != kMiss;
@@ -176,8 +156,8 @@ struct Intersection {
 };
 
 PG_DEV void fillIntersection(const DeviceScene &S, float3 o, float3 d, const Hit &h, Intersection &its) {
-    const float4 q2 = __ldg(S.prims + 3 * h.prim + 2);
-    const uint32_t shapeIdx = __float_as_uint(q2.z), primIdx = __float_as_uint(q2.w);
+    const PrimInfo pi = S.primInfo[h.prim];
+    const uint32_t shapeIdx = pi.shape, primIdx = pi.prim;
     const ShapeRecord sr = S.shapes[shapeIdx];
     its.shape = (int)shapeIdx;
     its.bsdf = sr.bsdf;

@@ -587,6 +587,7 @@ bool HostScene::compile(std::string &err) {
     // ---- shapes, primitives (global ids numbered as in skdtree.cpp:53-104)
     std::vector<BPrim> bprims;
     std::vector<PrimRecord> flat;  // global-id order
+    std::vector<PrimInfo> flatInfo;
     shapeRecs.clear();
     rects.clear();
     meshes.clear();
@@ -628,12 +629,9 @@ bool HostScene::compile(std::string &err) {
             sr.meshOffset = (uint32_t)rects.size();
             rects.push_back(rr);
             PrimRecord pr;
-            std::memset(&pr, 0, sizeof(pr));
-            pr.q[0] = u2f(kNoTriangle);
-            pr.q[1] = u2f(sr.meshOffset);
-            pr.q[10] = u2f((uint32_t)si);
-            pr.q[11] = u2f(kNoTriangle);
+            for (int i = 0; i < 12; ++i) pr.q[i] = inv[i];  // rows of worldToObject
             flat.push_back(pr);
+            flatInfo.push_back(PrimInfo{(uint32_t)si, kNoTriangle});
             BPrim bp;
             Box bx;
             bx.reset();
@@ -672,37 +670,45 @@ bool HostScene::compile(std::string &err) {
             sr.flags = mr.hasNormals;
             size_t cdf0 = areaCdf.size();
             areaCdf.push_back(0.0f);
-            static const int waldModulo[4] = {1, 2, 0, 1};
             for (uint32_t t = 0; t < s.n_triangles; ++t) {
                 const float *pa = s.positions + 3 * (size_t)s.indices[3 * t], *pb = s.positions + 3 * (size_t)s.indices[3 * t + 1],
                             *pc = s.positions + 3 * (size_t)s.indices[3 * t + 2];
                 V3 A = v3(pa[0], pa[1], pa[2]), B = v3(pb[0], pb[1], pb[2]), C = v3(pc[0], pc[1], pc[2]);
-                // Wald's projected triangle constants (triaccel.h:68-94)
-                V3 b = sub(C, A), c = sub(B, A), N = cross(c, b);
-                uint32_t k = 0;
-                for (int j = 0; j < 3; ++j)
-                    if (std::fabs(N[j]) > std::fabs(N[k])) k = j;
-                uint32_t u = waldModulo[k], v = waldModulo[k + 1];
-                float n_k = N[k], denom = b[u] * c[v] - b[v] * c[u];
+                // Plane form of the triangle test: with e1 = B-A, e2 = C-A, N = e1 x e2,
+                //   t = (N.A - N.o) / (N.d),  u = Nu.(P-A),  v = Nv.(P-A),  Nu = (e2 x N)/(e1.(e2 x N)),
+                //   Nv = (N x e1)/(e2.(N x e1)) -- the same (t, u, v) TriAccel::rayIntersect returns
+                // (triaccel.h:96-158; u weights vertex 1, v vertex 2). Constants are derived in double.
                 PrimRecord pr;
                 std::memset(&pr, 0, sizeof(pr));
-                if (denom == 0) {
-                    pr.q[0] = u2f(3u);  // degenerate: never hit
-                } else {
-                    pr.q[0] = u2f(k);
-                    pr.q[1] = N[u] / n_k;
-                    pr.q[2] = N[v] / n_k;
-                    pr.q[3] = dot(A, N) / n_k;
-                    pr.q[4] = A[u];
-                    pr.q[5] = A[v];
-                    pr.q[6] = b[u] / denom;
-                    pr.q[7] = -b[v] / denom;
-                    pr.q[8] = c[v] / denom;
-                    pr.q[9] = -c[u] / denom;
+                {
+                    double a[3] = {A.x, A.y, A.z}, e1[3] = {(double)B.x - A.x, (double)B.y - A.y, (double)B.z - A.z},
+                           e2[3] = {(double)C.x - A.x, (double)C.y - A.y, (double)C.z - A.z};
+                    auto crs = [](const double *p, const double *q, double *r) {
+                        r[0] = p[1] * q[2] - p[2] * q[1];
+                        r[1] = p[2] * q[0] - p[0] * q[2];
+                        r[2] = p[0] * q[1] - p[1] * q[0];
+                    };
+                    auto dt = [](const double *p, const double *q) { return p[0] * q[0] + p[1] * q[1] + p[2] * q[2]; };
+                    double N[3], nu[3], nv[3];
+                    crs(e1, e2, N);
+                    crs(e2, N, nu);
+                    crs(N, e1, nv);
+                    double du = dt(e1, nu), dv = dt(e2, nv), nn = std::sqrt(dt(N, N));
+                    if (nn == 0 || du == 0 || dv == 0) {
+                        pr.q[11] = 1.0f;  // degenerate (TriAccel::load failure, triaccel.h:80-83): t = -1/0, never hit
+                    } else {
+                        for (int j = 0; j < 3; ++j) {
+                            pr.q[j] = (float)(nu[j] / du);
+                            pr.q[4 + j] = (float)(nv[j] / dv);
+                            pr.q[8 + j] = (float)(N[j] / nn);
+                        }
+                        pr.q[3] = (float)(-dt(nu, a) / du);
+                        pr.q[7] = (float)(-dt(nv, a) / dv);
+                        pr.q[11] = (float)(-dt(N, a) / nn);
+                    }
                 }
-                pr.q[10] = u2f((uint32_t)si);
-                pr.q[11] = u2f(t);
                 flat.push_back(pr);
+                flatInfo.push_back(PrimInfo{(uint32_t)si, t});
                 BPrim bp;
                 for (int a = 0; a < 3; ++a) {
                     bp.bmin[a] = std::min(A[a], std::min(B[a], C[a]));
@@ -807,16 +813,30 @@ bool HostScene::compile(std::string &err) {
             o.q[0] = b0.mn[0]; o.q[1] = b0.mx[0]; o.q[2] = b0.mn[1]; o.q[3] = b0.mx[1];
             o.q[4] = b1.mn[0]; o.q[5] = b1.mx[0]; o.q[6] = b1.mn[1]; o.q[7] = b1.mx[1];
             o.q[8] = b0.mn[2]; o.q[9] = b0.mx[2]; o.q[10] = b1.mn[2]; o.q[11] = b1.mx[2];
-            int32_t c0 = t.child[0] >= 0 ? remap[t.child[0]] : t.child[0];
-            int32_t c1 = t.child[1] >= 0 ? remap[t.child[1]] : t.child[1];
+            // leaves: re-encode as (first << 7) | (rectMask << 3) | count
+            auto leaf = [&](int32_t c) {
+                uint32_t code = (uint32_t)(~c);
+                uint32_t first = code >> 4, count = code & 15u, mask = 0;
+                for (uint32_t k = 0; k < count; ++k)
+                    if (flatInfo[bprims[first + k].id].prim == kNoTriangle) mask |= 1u << k;
+                return ~(int32_t)((first << kLeafShift) | (mask << 3) | count);
+            };
+            int32_t c0 = t.child[0] >= 0 ? remap[t.child[0]] : leaf(t.child[0]);
+            int32_t c1 = t.child[1] >= 0 ? remap[t.child[1]] : leaf(t.child[1]);
             o.q[12] = u2f((uint32_t)c0);
             o.q[13] = u2f((uint32_t)c1);
             o.q[14] = o.q[15] = 0;
         }
         prims.resize(bprims.size());
         primGlobalId.resize(bprims.size());
+        primInfo.resize(bprims.size());
+        if (bprims.size() >= (1u << 24)) {
+            err = "more than 16M primitives are not supported by the leaf encoding";
+            return false;
+        }
         for (size_t i = 0; i < bprims.size(); ++i) {
             prims[i] = flat[bprims[i].id];
+            primInfo[i] = flatInfo[bprims[i].id];
             primGlobalId[i] = bprims[i].id;
         }
     }

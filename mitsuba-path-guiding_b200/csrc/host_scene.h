@@ -30,6 +30,7 @@ struct HostScene {
     std::vector<BvhNode> nodes;
     std::vector<PrimRecord> prims;       // BVH leaf order
     std::vector<uint32_t> primGlobalId;  // BVH order -> global primitive id
+    std::vector<PrimInfo> primInfo;      // BVH order -> (shape, primitive index)
     std::vector<RectRecord> rects;
     std::vector<ShapeRecord> shapeRecs;
     std::vector<MeshRecord> meshes;

@@ -35,6 +35,9 @@ void launchShadow(const DeviceScene &S, const ShadowQueue &Q, float4 *rad, const
                   bool count, cudaStream_t st);
 void launchShade(const ShadeArgs &A, cudaStream_t st);
 void launchFlush(const ShadeArgs &A, cudaStream_t st);
+void launchFilmExport(const float4 *film, float *out, uint32_t n, int develop, cudaStream_t st);
+void launchSplat(const FilmRecord &F, float4 *film, const float4 *splatA, const float *splatB, uint32_t n, float maxComponentValue,
+                 cudaStream_t st);
 void launchTraceRays(const DeviceScene &S, const float4 *rays, uint32_t n, float4 *hits, uint32_t *work, Counters *C, bool shadow,
                      bool count, cudaStream_t st);
 void launchFilmSplat(const FilmRecord &F, float4 *film, const float2 *pos, const float3 *rgb, uint32_t n, float maxComponentValue,
@@ -108,6 +111,7 @@ struct Integrator {
     DevBuf<MeshRecord> dMeshes;
     DevBuf<float> dPositions, dNormals, dTexcoords, dAreaCdf, dEmitterCdf, dDensity;
     DevBuf<uint32_t> dIndices, dPrimGlobal;
+    DevBuf<PrimInfo> dPrimInfo;
     DevBuf<BsdfRecord> dBsdfs;
     DevBuf<EmitterRecord> dEmitters;
     DevBuf<MediumRecord> dMedia;
@@ -117,8 +121,11 @@ struct Integrator {
     PathBuffers bufA, bufB;
     DevBuf<float4> dHits, dShO, dShD, dShC;
     DevBuf<int32_t> dShMedium;
+    DevBuf<float4> dSplatA;
+    DevBuf<float> dSplatB;
     DevBuf<Counters> dCounters;
     DevBuf<float4> dFilm;
+    DevBuf<float> dFilmOut;
     size_t batchCapacity = 0;
     bool countTraversal = false;
 
@@ -213,12 +220,14 @@ struct Integrator {
         dMedia.upload(H.mediumRecs, stream);
         dDensity.upload(H.densityPool, stream);
         dPrimGlobal.upload(H.primGlobalId, stream);
+        dPrimInfo.upload(H.primInfo, stream);
         S.nodes = dNodes.p; S.prims = dPrims.p; S.rects = dRects.p;
         S.shapes = dShapes.p; S.meshes = dMeshes.p;
         S.positions = dPositions.p; S.normals = dNormals.p; S.texcoords = dTexcoords.p;
         S.indices = dIndices.p; S.areaCdf = dAreaCdf.p;
         S.bsdfs = dBsdfs.p; S.emitters = dEmitters.p; S.emitterCdf = dEmitterCdf.p;
         S.media = dMedia.p; S.density = dDensity.p; S.primGlobalId = dPrimGlobal.p;
+        S.primInfo = dPrimInfo.p;
         S.nEmitters = (uint32_t)H.emitters.size();
         S.nPrims = (uint32_t)H.prims.size();
         S.camera = H.camera;
@@ -237,6 +246,7 @@ struct Integrator {
         if (n <= batchCapacity) return;
         bufA.alloc(n); bufB.alloc(n);
         dHits.alloc(n); dShO.alloc(n); dShD.alloc(n); dShC.alloc(n); dShMedium.alloc(n);
+        dSplatA.alloc(n); dSplatB.alloc(n);
         batchCapacity = n;
     }
 
@@ -274,6 +284,8 @@ struct Integrator {
         A.C = dCounters.p;
         A.film = dFilm.p;
         A.radianceOut = radianceOut;
+        A.splatA = dSplatA.p;
+        A.splatB = dSplatB.p;
         const int maxBounces = params.max_depth > 0 ? std::min(params.max_depth + 1, 256) : 256;
         Counters *C = dCounters.p;
         int b = 0;
@@ -308,6 +320,12 @@ struct Integrator {
         A.bounce = std::min(b, maxBounces);
         launchFlush(A, stream);
         stats.kernel_launches++;
+        if (!radianceOut && !cancel.load()) {  // every path of the batch has ended exactly once: rasterise them
+            cudaEvent_t t = spanBegin();
+            launchSplat(S.film, dFilm.p, dSplatA.p, dSplatB.p, B.nPaths, params.max_component_value, stream);
+            spanEnd(kTimeFilm, t);
+            stats.kernel_launches++;
+        }
     }
 
     void pullCounters() {
@@ -550,30 +568,24 @@ int b200pg_film_device_buffer(void *integ, void **dev_ptr, size_t *n_floats) {
 
 int b200pg_film_read(void *integ, float *rgbaw) {
     PG_TRY(integ)
-    std::vector<float4> h(self->dFilm.n);
-    CUDA_OK(cudaMemcpyAsync(h.data(), self->dFilm.p, h.size() * sizeof(float4), cudaMemcpyDeviceToHost, self->stream));
+    // expand (R,G,B,weight) -> (R,G,B,alpha,weight) on the device, then ONE device->host copy straight into the
+    // caller's buffer (fast when that buffer is pinned). alpha == weight here: rRec.alpha stays 1 (integrator.h:218-225).
+    self->dFilmOut.alloc(self->dFilm.n * 5);
+    launchFilmExport(self->dFilm.p, self->dFilmOut.p, (uint32_t)self->dFilm.n, 0, self->stream);
+    CUDA_OK(cudaMemcpyAsync(rgbaw, self->dFilmOut.p, self->dFilm.n * 5 * sizeof(float), cudaMemcpyDeviceToHost, self->stream));
     CUDA_OK(cudaStreamSynchronize(self->stream));
-    for (size_t i = 0; i < h.size(); ++i) {
-        rgbaw[5 * i + 0] = h[i].x;
-        rgbaw[5 * i + 1] = h[i].y;
-        rgbaw[5 * i + 2] = h[i].z;
-        rgbaw[5 * i + 3] = h[i].w;  // alpha == weight on this path (rRec.alpha stays 1, integrator.h:218-225)
-        rgbaw[5 * i + 4] = h[i].w;
-    }
+    self->stats.kernel_launches++;
     PG_END
 }
 
 int b200pg_film_develop(void *integ, float *rgb) {
     PG_TRY(integ)
-    std::vector<float4> h(self->dFilm.n);
-    CUDA_OK(cudaMemcpyAsync(h.data(), self->dFilm.p, h.size() * sizeof(float4), cudaMemcpyDeviceToHost, self->stream));
+    // weight normalisation RGB / weight (fmtconv.cpp:978-1005) on the device
+    self->dFilmOut.alloc(self->dFilm.n * 5);
+    launchFilmExport(self->dFilm.p, self->dFilmOut.p, (uint32_t)self->dFilm.n, 1, self->stream);
+    CUDA_OK(cudaMemcpyAsync(rgb, self->dFilmOut.p, self->dFilm.n * 3 * sizeof(float), cudaMemcpyDeviceToHost, self->stream));
     CUDA_OK(cudaStreamSynchronize(self->stream));
-    for (size_t i = 0; i < h.size(); ++i) {  // weight normalisation, fmtconv.cpp:978-1005
-        float inv = h[i].w > 0 ? 1.0f / h[i].w : 0.0f;
-        rgb[3 * i + 0] = h[i].x * inv;
-        rgb[3 * i + 1] = h[i].y * inv;
-        rgb[3 * i + 2] = h[i].z * inv;
-    }
+    self->stats.kernel_launches++;
     PG_END
 }
 
@@ -637,6 +649,7 @@ int b200pg_scene_upload(void *integ, size_t *bytes) {
     self->dRects.upload(reinterpret_cast<const float4 *>(H.rects.data()), H.rects.size() * 8, self->stream);
     total += H.nodes.size() * 64 + H.prims.size() * 48 + H.rects.size() * 128;
     up(self->dShapes, H.shapeRecs);
+    up(self->dPrimInfo, H.primInfo);
     up(self->dMeshes, H.meshes);
     up(self->dPositions, H.positions);
     up(self->dNormals, H.normals);

@@ -28,6 +28,36 @@ PG_DEV uint32_t warpAppend(uint32_t *counter, bool pred) {
     return base + __popc(mask & ((1u << laneId()) - 1u));
 }
 
+// Block-aggregated append for two queues at once: ONE global atomic per block and queue instead of
+// one per warp (the per-warp version serialised ~130k same-address atomics per bounce at L2 and was
+// 35% of k_shade's stall samples, profiles/r01_v1_summary.txt). Must be called by all threads of the
+// block; `smem` holds 2*(warps+1) words.
+PG_DEV void blockAppend2(uint32_t *counterA, bool predA, uint32_t *counterB, bool predB, uint32_t *smem, uint32_t &idxA,
+                         uint32_t &idxB) {
+    const uint32_t warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
+    const unsigned maskA = __ballot_sync(0xffffffffu, predA), maskB = __ballot_sync(0xffffffffu, predB);
+    uint32_t *cntA = smem, *cntB = smem + nWarps + 1;
+    if (laneId() == 0) {
+        cntA[warp] = __popc(maskA);
+        cntB[warp] = __popc(maskB);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        uint32_t *cnt = threadIdx.x ? cntB : cntA;
+        uint32_t total = 0;
+        for (uint32_t w = 0; w < nWarps; ++w) {
+            const uint32_t c = cnt[w];
+            cnt[w] = total;  // exclusive prefix
+            total += c;
+        }
+        cnt[nWarps] = total ? atomicAdd(threadIdx.x ? counterB : counterA, total) : 0u;
+    }
+    __syncthreads();
+    idxA = cntA[nWarps] + cntA[warp] + __popc(maskA & ((1u << laneId()) - 1u));
+    idxB = cntB[nWarps] + cntB[warp] + __popc(maskB & ((1u << laneId()) - 1u));
+    __syncthreads();  // smem is reused by the next loop iteration
+}
+
 PG_DEV void warpAddU64(unsigned long long *counter, unsigned long long v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -78,6 +108,25 @@ __global__ void __launch_bounds__(256) k_film_splat(FilmRecord F, float4 *film, 
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float *c = reinterpret_cast<const float *>(rgb) + 3 * (size_t)i;
         filmSplat(F, film, pos[i], f3(c[0], c[1], c[2]), maxComponentValue);
+    }
+}
+
+// Film export: develop = 0 -> (R,G,B,alpha,weight) per pixel; develop = 1 -> RGB / weight (fmtconv.cpp:978-1005)
+__global__ void __launch_bounds__(256) k_film_export(const float4 *__restrict__ film, float *__restrict__ out, uint32_t n, int develop) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 f = film[i];
+        if (develop) {
+            const float inv = f.w > 0 ? 1.0f / f.w : 0.0f;
+            out[3 * (size_t)i + 0] = f.x * inv;
+            out[3 * (size_t)i + 1] = f.y * inv;
+            out[3 * (size_t)i + 2] = f.z * inv;
+        } else {
+            out[5 * (size_t)i + 0] = f.x;
+            out[5 * (size_t)i + 1] = f.y;
+            out[5 * (size_t)i + 2] = f.z;
+            out[5 * (size_t)i + 3] = f.w;
+            out[5 * (size_t)i + 4] = f.w;
+        }
     }
 }
 
@@ -229,16 +278,30 @@ __global__ void __launch_bounds__(128) k_trace_rays(DeviceScene S, const float4 
 // Shade stage (surface path tracer, ProgressiveMIPathTracer::Li)
 // ------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(128) k_shade(ShadeArgs A) {
+// A terminated path leaves its final sample value in the splat buffer (indexed by the path's slot, i.e.
+// in pixel order); k_splat rasterises the whole batch afterwards with all lanes busy.
+PG_DEV void finishPath(const ShadeArgs &A, uint32_t slot, float4 pos4, float3 L) {
+    if (A.radianceOut) {
+        A.radianceOut[3 * (size_t)slot + 0] = L.x;
+        A.radianceOut[3 * (size_t)slot + 1] = L.y;
+        A.radianceOut[3 * (size_t)slot + 2] = L.z;
+    } else {
+        A.splatA[slot] = make_float4(pos4.x, pos4.y, L.x, L.y);
+        A.splatB[slot] = L.z;
+    }
+}
+
+__global__ void __launch_bounds__(kShadeThreads) k_shade(ShadeArgs A) {
     const DeviceScene &S = A.S;
     const IntegratorConfig &cfg = A.cfg;
     const uint32_t n = A.C->queue[A.bounce];
     uint32_t *nextCount = &A.C->queue[A.bounce + 1];
     uint32_t *shadowCount = &A.C->shadow[A.bounce];
     unsigned long long donePaths = 0, doneLen = 0;
+    __shared__ uint32_t sAppend[2 * (kShadeThreads / 32 + 1)];
 
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += gridDim.x * blockDim.x) {
-        const uint32_t i = base + laneId();
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
         const bool valid = i < n;
 
         bool alive = false;      // continues into the next queue
@@ -375,9 +438,9 @@ __global__ void __launch_bounds__(128) k_shade(ShadeArgs A) {
             }
         }
 
-        // ---- compaction into the next queue / shadow queue (one atomic per warp each)
-        const uint32_t j = warpAppend(nextCount, alive);
-        const uint32_t sidx = warpAppend(shadowCount, wantShadow);
+        // ---- compaction into the next queue / shadow queue (one atomic per block each)
+        uint32_t j, sidx;
+        blockAppend2(nextCount, alive, shadowCount, wantShadow, sAppend, j, sidx);
         if (alive) {
             A.next.rayO[j] = make_float4(newO.x, newO.y, newO.z, kEpsilon);
             A.next.rayD[j] = make_float4(newD.x, newD.y, newD.z, kInf);
@@ -397,17 +460,21 @@ __global__ void __launch_bounds__(128) k_shade(ShadeArgs A) {
         if (valid && terminate) {
             donePaths++;
             doneLen += depth;
-            if (A.radianceOut) {
-                A.radianceOut[3 * (size_t)slot + 0] = L.x;
-                A.radianceOut[3 * (size_t)slot + 1] = L.y;
-                A.radianceOut[3 * (size_t)slot + 2] = L.z;
-            } else {
-                filmSplat(S.film, A.film, make_float2(pos4.x, pos4.y), L, cfg.maxComponentValue);
-            }
+            finishPath(A, slot, pos4, L);
         }
     }
     warpAddU64(&A.C->paths, donePaths);
     warpAddU64(&A.C->pathLen, doneLen);
+}
+
+// Film accumulation for a finished batch: one thread per camera sample, in slot (= pixel) order, so the
+// 32 float4 atomics of a warp instruction fall on neighbouring texels.
+__global__ void __launch_bounds__(256) k_splat(FilmRecord F, float4 *film, const float4 *__restrict__ splatA,
+                                               const float *__restrict__ splatB, uint32_t n, float maxComponentValue) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 a = splatA[i];
+        filmSplat(F, film, make_float2(a.x, a.y), f3(a.z, a.w, splatB[i]), maxComponentValue);
+    }
 }
 
 // Flush whatever is still queued after the last bounce (only parked/dead records can remain).
@@ -421,13 +488,7 @@ __global__ void __launch_bounds__(256) k_flush(ShadeArgs A) {
             const uint32_t slot = A.cur.slot[i];
             donePaths++;
             doneLen += A.cur.flags[i] & kDepthMask;
-            if (A.radianceOut) {
-                A.radianceOut[3 * (size_t)slot + 0] = rad4.x;
-                A.radianceOut[3 * (size_t)slot + 1] = rad4.y;
-                A.radianceOut[3 * (size_t)slot + 2] = rad4.z;
-            } else {
-                filmSplat(A.S.film, A.film, make_float2(pos4.x, pos4.y), f3(rad4.x, rad4.y, rad4.z), A.cfg.maxComponentValue);
-            }
+            finishPath(A, slot, pos4, f3(rad4.x, rad4.y, rad4.z));
         }
     }
     warpAddU64(&A.C->paths, donePaths);
@@ -499,8 +560,16 @@ void launchShadow(const DeviceScene &S, const ShadowQueue &Q, float4 *rad, const
         k_shadow<false><<<grid, 128, 0, st>>>(S, Q, rad, nPtr, work, C);
 }
 void launchShade(const ShadeArgs &A, cudaStream_t st) {
-    static int grid = persistentGrid(k_shade, 128);
-    k_shade<<<grid, 128, 0, st>>>(A);
+    static int grid = persistentGrid(k_shade, kShadeThreads);
+    k_shade<<<grid, kShadeThreads, 0, st>>>(A);
+}
+void launchSplat(const FilmRecord &F, float4 *film, const float4 *splatA, const float *splatB, uint32_t n, float maxComponentValue,
+                 cudaStream_t st) {
+    static int grid = persistentGrid(k_splat, 256);
+    k_splat<<<grid, 256, 0, st>>>(F, film, splatA, splatB, n, maxComponentValue);
+}
+void launchFilmExport(const float4 *film, float *out, uint32_t n, int develop, cudaStream_t st) {
+    k_film_export<<<numSMs() * 4, 256, 0, st>>>(film, out, n, develop);
 }
 void launchFlush(const ShadeArgs &A, cudaStream_t st) {
     static int grid = persistentGrid(k_flush, 256);

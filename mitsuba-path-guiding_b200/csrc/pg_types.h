@@ -15,17 +15,26 @@ static const uint32_t kMiss = 0xFFFFFFFFu;
 //   q1 = c1.min.x c1.max.x c1.min.y c1.max.y
 //   q2 = c0.min.z c0.max.z c1.min.z c1.max.z
 //   q3 = child0, child1 (int bits), pad, pad.   child >= 0: inner node index;
-//        child < 0: leaf, ~child = (first_prim << 4) | count   (count <= 15)
+//        child < 0: leaf, ~child = (first_prim << 7) | (rectMask << 3) | count   (count <= 4;
+//        bit i of rectMask: primitive first_prim + i is a rectangle)
 struct BvhNode {
     float q[16];
 };
+static const int kLeafShift = 7;
 
-// Primitive record, 48 B = 3 x float4, stored in BVH leaf order.
-// Triangle (Wald projection, same arithmetic as triaccel.h:37-158):
-//   q0 = k(bits) n_u n_v n_d | q1 = a_u a_v b_nu b_nv | q2 = c_nu c_nv shape(bits) prim(bits)
-// Rectangle: q0 = kNoTriangle, rectIndex(bits), 0, 0 | q1 = 0 | q2 = 0 0 shape(bits) kNoTriangle
+// Primitive record, 48 B = 3 x float4 (rows of a 3x4 affine map), stored in BVH leaf order.
+// One branch-free test serves both primitive kinds: with l(x) = M x + w,
+//     t = -l(o).z / (M d).z,   (u, v) = (l(o) + t M d).xy
+//   rectangle: M, w = worldToObject (the arithmetic of rectangle.cpp:125-148); accept |u|,|v| <= 1
+//   triangle:  row2 = geometric plane, rows 0/1 = barycentric planes of vertices 1 and 2;
+//              accept u, v >= 0, u + v <= 1 (same (t,u,v) as TriAccel::rayIntersect, triaccel.h:96-158,
+//              up to rounding)
 struct PrimRecord {
     float q[12];
+};
+
+struct PrimInfo {  // read by the shade stage only
+    uint32_t shape, prim;  // prim == kNoTriangle for rectangles
 };
 
 // Rectangle, 8 x float4: rows of worldToObject (3), then frame/dpdu data for shading.

@@ -23,6 +23,8 @@ enum : uint32_t {
     kDepthMask = 0xFFu
 };
 
+static constexpr int kShadeThreads = 256;
+
 struct PathState {
     float4 *rayO;     // o.xyz, mint
     float4 *rayD;     // d.xyz, maxt
@@ -77,6 +79,8 @@ struct ShadeArgs {
     const float4 *hits;
     Counters *C;
     float4 *film;
+    float4 *splatA;      // per slot: samplePos.xy, L.r, L.g   (written once, when the path ends)
+    float *splatB;       // per slot: L.b
     float *radianceOut;  // optional: per-slot radiance instead of film splats (b200pg_k_radiance)
     GuideDevice G;
     int bounce;

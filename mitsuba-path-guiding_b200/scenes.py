@@ -409,8 +409,10 @@ def _cornell_walls(sb, with_boxes=True):
         sb.rectangle(rect(xo, b), bsdf=b, xml_ops=xo)
     boxw = sb.diffuse((0.725, 0.71, 0.68))
     if with_boxes:
-        tall = [_op("scale", 0.3, 0.6, 0.3), _op("rotate", Y, 17.0), _op("translate", -0.33, 0.6, -0.3)]
-        short = [_op("scale", 0.3, 0.3, 0.3), _op("rotate", Y, -17.0), _op("translate", 0.35, 0.3, 0.35)]
+        # boxes float 1 mm above the floor: no coplanar faces, hence no equal-t ties whose winner would
+        # depend on the traversal order of the accelerator (kd-tree in the reference, BVH here)
+        tall = [_op("scale", 0.3, 0.6, 0.3), _op("rotate", Y, 17.0), _op("translate", -0.33, 0.601, -0.3)]
+        short = [_op("scale", 0.3, 0.3, 0.3), _op("rotate", Y, -17.0), _op("translate", 0.35, 0.301, 0.35)]
         sb.cube(rect(tall, boxw), bsdf=boxw, xml_ops=tall)
         sb.cube(rect(short, boxw), bsdf=boxw, xml_ops=short)
     return rect, white, boxw
@@ -440,9 +442,10 @@ def cornell_caustic(width=1024, height=1024, spp=64, seed=1337, max_depth=8):
     shield = [_op("scale", 0.15, 0.15, 1.0), _op("rotate", X, 90.0), _op("translate", 0.0, 1.55, 0.0)]
     sb.rectangle(rect(shield, white), bsdf=white, xml_ops=shield)
     glass = sb.dielectric(int_ior=1.5, ext_ior=1.0)
-    gl = [_op("scale", 0.3, 0.3, 0.3), _op("rotate", Y, 25.0), _op("translate", 0.3, 0.3, 0.2)]
+    # lifted 2 mm off the floor: coplanar glass/floor faces would make the closest hit ambiguous (equal t)
+    gl = [_op("scale", 0.3, 0.3, 0.3), _op("rotate", Y, 25.0), _op("translate", 0.3, 0.302, 0.2)]
     sb.cube(rect(gl, glass), bsdf=glass, xml_ops=gl)
-    tall = [_op("scale", 0.25, 0.55, 0.25), _op("rotate", Y, 17.0), _op("translate", -0.4, 0.55, -0.35)]
+    tall = [_op("scale", 0.25, 0.55, 0.25), _op("rotate", Y, 17.0), _op("translate", -0.4, 0.551, -0.35)]
     sb.cube(rect(tall, boxw), bsdf=boxw, xml_ops=tall)
     sb.set_camera((0.0, 1.0, 3.9), (0.0, 1.0, 0.0), (0.0, 1.0, 0.0), 39.3)
     sb.integrator = dict(type="progressivepath", maxDepth=max_depth)

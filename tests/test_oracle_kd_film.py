@@ -1,0 +1,125 @@
+"""Oracle self-checks that do not need a GPU: SAH kd-tree + Havran traversal against brute force (the pattern of the
+reference's kd-tree tests, src/tests/test_kd.cpp:86-217), film splatting against a direct numpy restatement of
+ImageBlock::put (include/mitsuba/render/imageblock.h:151-197) and the filter table (rfilter.cpp:38-56)."""
+import numpy as np
+import pytest
+
+from bsdf_cases import random_dirs
+
+
+def _chords(rng, n, center, radius):
+    """Uniformly random chords through a sphere (test_kd.cpp:98-113)."""
+    a = random_dirs(rng, n) * radius + center
+    b = random_dirs(rng, n) * radius + center
+    d = b - a
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return np.concatenate([a, np.full((n, 1), 1e-4), d, np.full((n, 1), np.inf)], 1).astype(np.float32)
+
+
+@pytest.mark.parametrize("scene_name", ["cornell_box", "cornell_caustic"])
+def test_kdtree_matches_bruteforce(pkg, oracle, scene_name):
+    sb = getattr(pkg.scenes, scene_name)(64, 64)
+    sc = oracle.scene(sb)
+    rng = np.random.RandomState(0)
+    rays = np.concatenate([_chords(rng, 40000, np.array([0, 1, 0], np.float32), 1.6),
+                           sc.camera_rays((rng.rand(20000, 2) * 64).astype(np.float32))])
+    tuv, prim, cnt = sc.trace(rays)
+    tuv_b, prim_b = sc.trace_bruteforce(rays)
+    assert np.array_equal(prim, prim_b)
+    hit = prim != 0xFFFFFFFF
+    assert hit.mean() > 0.5
+    assert np.array_equal(tuv[hit], tuv_b[hit])  # same arithmetic, same primitive: bit-identical
+    assert cnt["prims"] < 0.5 * len(rays) * sc.kd_info()["prims"]  # the tree actually culls
+
+
+def test_kdtree_on_mesh(pkg, oracle):
+    """A 2 x 80k-triangle heightfield exercises the min-max binning path (> exactPrimThreshold, gkdtree.h:1792-1925)."""
+    S = pkg.scenes
+    sb = S.SceneBuilder(32, 32)
+    P, N, T = S.heightfield_mesh(n=201, seed=3)
+    sb.trimesh(P, T, N=N, bsdf=sb.diffuse((0.5, 0.5, 0.5)))
+    sb.rectangle([S.scale(0.2, 0.2, 1), S.rotate((1, 0, 0), 90), S.translate(0, 1, 0)], radiance=(5, 5, 5))
+    sb.set_camera((0, 1.5, 2.5), (0, 0, 0), (0, 1, 0), 45.0)
+    sc = oracle.scene(sb)
+    info = sc.kd_info()
+    assert info["prims"] == 2 * 200 * 200 + 1
+    rng = np.random.RandomState(1)
+    rays = _chords(rng, 3000, np.array([0, 0, 0], np.float32), 1.2)
+    tuv, prim, _ = sc.trace(rays)
+    tuv_b, prim_b = sc.trace_bruteforce(rays)
+    assert np.array_equal(prim, prim_b)
+    m = prim != 0xFFFFFFFF
+    assert np.array_equal(tuv[m], tuv_b[m])
+    # any-hit agrees with closest-hit on hit/miss
+    _, occ, _ = sc.trace(rays, shadow=True)
+    assert np.array_equal(occ != 0xFFFFFFFF, m)
+
+
+def test_single_primitive_and_misses(pkg, oracle):
+    S = pkg.scenes
+    sb = S.SceneBuilder(8, 8)
+    sb.rectangle([S.scale(1, 1, 1)], bsdf=sb.diffuse((0.5, 0.5, 0.5)), radiance=(1, 1, 1))
+    sb.set_camera((0, 0, 4), (0, 0, 0), (0, 1, 0), 40.0)
+    sc = oracle.scene(sb)
+    rays = np.array([[0, 0, 4, 1e-4, 0, 0, -1, np.inf], [3, 0, 4, 1e-4, 0, 0, -1, np.inf],
+                     [0, 0, 4, 1e-4, 0, 0, 1, np.inf], [0.5, 0.5, 4, 1e-4, 0, 0, -1, 3.0]], np.float32)
+    tuv, prim, _ = sc.trace(rays)
+    assert prim.tolist() == [0, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF]
+    assert tuv[0, 0] == 4.0 and tuv[0, 1] == 0.0 and tuv[0, 2] == 0.0  # rectangle returns local x, y
+
+
+def _numpy_film(W, H, pos, rgb, stddev=0.5):
+    """Direct restatement of ImageBlock::put on a single full-image block with border (no tiling)."""
+    radius = 4 * stddev
+    alpha = np.float32(-1.0 / (2 * stddev * stddev))
+    xs = (np.float32(radius) * np.arange(31, dtype=np.float32)) / np.float32(31)
+    vals = np.maximum(np.float32(0), np.exp(alpha * xs * xs) - np.exp(alpha * np.float32(radius) ** 2)).astype(np.float32)
+    s = np.float32(0)
+    for v in vals:
+        s += v
+    s *= np.float32(2 * radius / 31)
+    vals = np.concatenate([vals * (np.float32(1) / s), [np.float32(0)]]).astype(np.float32)
+    scale = np.float32(31 / radius)
+    border = int(np.ceil(radius - 0.5))
+    film = np.zeros((H, W, 5), np.float64)
+    for (x, y), c in zip(pos, rgb):
+        px, py = np.float32(x) - np.float32(0.5) + border, np.float32(y) - np.float32(0.5) + border
+        x0, x1 = max(int(np.ceil(px - radius)), 0), min(int(np.floor(px + radius)), W + 2 * border - 1)
+        y0, y1 = max(int(np.ceil(py - radius)), 0), min(int(np.floor(py + radius)), H + 2 * border - 1)
+        for yy in range(y0, y1 + 1):
+            wy = vals[min(int(abs((np.float32(yy) - py) * scale)), 31)]
+            for xx in range(x0, x1 + 1):
+                wx = vals[min(int(abs((np.float32(xx) - px) * scale)), 31)]
+                fx, fy = xx - border, yy - border
+                if 0 <= fx < W and 0 <= fy < H:
+                    film[fy, fx] += np.float32(wx * wy) * np.array([c[0], c[1], c[2], 1, 1])
+    return film, vals
+
+
+def test_film_splat_against_numpy(pkg, oracle):
+    sb = pkg.scenes.cornell_box(16, 12)  # smaller than one 32x32 tile: tiling does not enter
+    sc = oracle.scene(sb)
+    rng = np.random.RandomState(2)
+    pos = (rng.rand(300, 2) * [16, 12]).astype(np.float32)
+    rgb = rng.rand(300, 3).astype(np.float32)
+    got = sc.film_splat(pos, rgb)
+    want, vals = _numpy_film(16, 12, pos, rgb)
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)
+    # filter table: normalised so that its Riemann sum is 1 (rfilter.cpp:49-55)
+    assert abs(vals[:31].sum() * 2 * 2.0 / 31 - 1.0) < 1e-6
+
+
+def test_render_is_deterministic_and_partitionable(pkg, oracle):
+    sb = pkg.scenes.cornell_box(64, 64)
+    sc = oracle.scene(sb)
+    p = pkg._abi.default_params()
+    p.max_depth = 5
+    a, sa = sc.render(p, 0, 2, nthreads=1)
+    b, sb_ = sc.render(p, 0, 2, nthreads=4)
+    for k in ("paths", "normal_rays", "shadow_rays", "path_length_sum"):
+        assert sa[k] == sb_[k]
+    np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-5)  # only the merge order differs
+    c, _ = sc.render(p, 0, 1)
+    c, _ = sc.render(p, 1, 1, film=c)
+    np.testing.assert_allclose(a, c, rtol=1e-5, atol=1e-5)
+    assert sa["paths"] == 64 * 64 * 2 and 1.0 <= sa["path_length_sum"] / sa["paths"] <= 5.0

@@ -55,3 +55,8 @@ om = prim_o2[mm] == 0xFFFFFFFF; gm = prim_g2[mm] == 0xFFFFFFFF
 print("trace2 mismatch: oracle miss", int(om.sum()), "gpu miss", int(gm.sum()), "both hit", int((~om & ~gm).sum()))
 for i in mm[:8]:
     print(r2[i], tuv_o2[i], prim_o2[i], tuv_g2[i], prim_g2[i], "src prim", prim_o[m][i])
+m2 = (prim_o2 != 0xFFFFFFFF) & (prim_o2 == prim_g2)
+dt = np.abs(tuv_o2[m2, 0] - tuv_g2[m2, 0]); rel = dt / (1 + tuv_o2[m2, 0])
+print("secondary dt: max abs", dt.max(), "q99.9 rel(1+t)", np.quantile(rel, 0.999), "q99.99", np.quantile(rel, 0.9999), "max rel", rel.max())
+duv = np.abs(tuv_o2[m2, 1:] - tuv_g2[m2, 1:]).max(1)
+print("secondary duv: max", duv.max(), "q99.9", np.quantile(duv, 0.999))
