@@ -6,9 +6,11 @@
                                                            (oracle restatement; the reference binary cannot
                                                            be built here)
 
-A "step" = one progression (``--spp-per-step`` samples per pixel) of the guided/unguided path tracer over the
-whole image of the workload. value = camera paths completed per second (whole job, all ranks), device-timed
-with CUDA events, scene resident in HBM. e2e = same metric through the C-ABI with host buffers: per step the
+A "step" = one guiding TRAINING ITERATION of the guided path tracer: one progression (``--spp-per-step`` samples per
+pixel, recording path-vertex samples and sampling from the current field) over the whole image, followed by the
+training update (radix-sort binning, ``--em-iters`` weighted-EM iterations, spatial split). With N > 1 GPUs the
+per-cell EM sufficient statistics are summed with one NCCL allreduce per EM iteration (the only data-path collective).
+value = camera paths completed per second (whole job, all ranks), device-timed with CUDA events, scene resident in HBM. e2e = same metric through the C-ABI with host buffers: per step the
 compiled scene is re-sent host->device and the film is read back device->host.
 """
 import argparse
@@ -116,6 +118,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="cornell_caustic_1024")
     ap.add_argument("--spp-per-step", type=int, default=4)
+    ap.add_argument("--em-iters", type=int, default=4)
+    ap.add_argument("--no-guiding", action="store_true")
     ap.add_argument("--ref-seconds", type=float, default=3.0)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=10.0)
     args = ap.parse_args()
@@ -140,9 +144,23 @@ def main():
     scene = api.Scene.from_builder(sb)
     p = api.default_params()
     p.max_depth = 8
+    guided = not args.no_guiding
+    p.guiding = 1 if guided else 0
+    p.guide_max_components = 16
+    p.guide_max_cell_samples = 32768
     integ = api.Integrator(scene, p, device=local)
     spp = args.spp_per_step
     npix = sb.width * sb.height
+
+    def wrap(ptr, n):
+        class _W:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+        return torch.as_tensor(_W(), device="cuda")
+
+    def allreduce_stats(ptr, n):  # EM sufficient statistics: sum over ranks (NCCL over NVLink)
+        dist.all_reduce(wrap(ptr, n), op=dist.ReduceOp.SUM)
+        torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -151,7 +169,11 @@ def main():
 
     # ---- sample batches are split per GPU: rank r renders sample indices r*spp.. of every step (weak scaling)
     def step(k):
+        if guided:
+            integ.guiding_mode(True, k > 0)
         integ.progression((k * world + rank) * spp, spp)
+        if guided:
+            integ.train(args.em_iters, allreduce_stats if world > 1 else None)
 
     for k in range(max(args.warmup, 3)):
         step(k)
@@ -173,7 +195,7 @@ def main():
     s1 = integ.stats()
     t1s = integ.stage_times()
     # device time: CUDA events recorded on the launching stream around every progression (b200pg stats)
-    elapsed = s1["seconds_total"] - s0["seconds_total"]
+    elapsed = (s1["seconds_total"] - s0["seconds_total"]) + (t1s["train"]["seconds"] - t0s["train"]["seconds"])
     if world > 1:
         tt = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -193,6 +215,8 @@ def main():
     cpu = None
     if rank == 0:
         integ.set_option("count_traversal", 1)
+        if guided:
+            integ.guiding_mode(False, True)
         c0 = integ.stats()
         integ.progression(10_000_000, spp)  # same workload, disjoint sample indices, outside the timed region
         c1 = integ.stats()
@@ -221,7 +245,10 @@ def main():
                 "queue_only_gbs": (48.0 * nrays + 52.0 * srays) * args.steps / max(trace_all, 1e-9) / 1e9,
                 "per_ray": {"nodes": nodes / max(nrays + srays, 1), "prims": prims / max(nrays + srays, 1)},
                 "avg_launch_ms": 1e3 * tr_sec / max(tr_n, 1),
-                "stage_seconds": {"trace": tr_sec, "shade": sh_sec, "shadow": sd_sec, "device_total": elapsed, "host_wall": wall}}
+                "stage_seconds": {"trace": tr_sec, "shade": sh_sec, "shadow": sd_sec,
+                                  "film": t1s["film"]["seconds"] - t0s["film"]["seconds"],
+                                  "train": t1s["train"]["seconds"] - t0s["train"]["seconds"],
+                                  "device_total": elapsed, "host_wall": wall}}
 
     # ---- end-to-end through the C-ABI with host buffers: scene H2D + render + film D2H every step
     barrier()
@@ -248,12 +275,7 @@ def main():
     # ---- multi-GPU: every rank holds a full-size film; one NCCL reduce at the end
     if world > 1:
         ptr, n = integ.film_device_buffer()
-
-        class _Wrap:
-            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-
-        ft = torch.as_tensor(_Wrap(), device="cuda")
-        dist.reduce(ft, dst=0, op=dist.ReduceOp.SUM)
+        dist.reduce(wrap(ptr, n), dst=0, op=dist.ReduceOp.SUM)
         torch.cuda.synchronize()
 
     if rank == 0:
@@ -278,7 +300,9 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "spp_per_step": spp, "paths_per_step_per_gpu": npix * spp,
                        "l2": "wavefront state per step (%.0f MB) exceeds the 126 MB L2" % (npix * spp * 250 / 1e6),
-                       "guiding": "off (unguided progressivepath; guiding rows land later in round 1)"},
+                       "guiding": ("training iteration per step: K=16 vMF lobes/cell, %d EM iterations, %d cells at the end"
+                                   % (args.em_iters, s1["guide_cells"])) if guided else "off",
+                       "parallelism": "sample batches split per GPU; NCCL allreduce of EM statistics" if world > 1 else "1 GPU"},
             "mrays_per_sec": rays / elapsed / 1e6,
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),

@@ -211,13 +211,20 @@ int b200pg_cancel(void *integ); /* async-safe */
  * indices rendered by this call so that sample batches can be split across GPUs;
  * `row_begin`/`row_end` restrict to an image band (tile partition). */
 int b200pg_progression_render(void *integ, int first_sample, int n_samples, int row_begin, int row_end);
-/* Training between progressions: bin this progression's path-vertex samples per cell and
- * accumulate per-cell sufficient statistics on the device... */
+/* Guiding control for progression-granular use: `record` = the following progressions store path-vertex
+ * training samples, `sample` = they draw directions from the field (one-sample MIS with the BSDF). */
+int b200pg_guiding_mode(void *integ, int record, int sample);
+/* Training update between progressions (the place of postprogression(), progressiveintegrator.h:40-52):
+ *   begin       bin the recorded samples per cell (kd-tree lookup + stable radix sort)
+ *   accumulate  E-step over the local samples -> per-cell sufficient statistics on the device
+ *   stats_buffer exposes that buffer (cells x (4K + 8) floats) for an external sum over ranks (NCCL allreduce)
+ *   update      M-step from the (summed) statistics; commit != 0 on the last EM iteration of the update
+ *   end         spatial split of over-full cells; identical on every rank given identical statistics */
+int b200pg_train_begin(void *integ, uint32_t *n_samples, uint32_t *n_cells);
 int b200pg_train_accumulate(void *integ);
-/* ...expose the statistics buffer for an external sum over ranks (NCCL allreduce)... */
 int b200pg_train_stats_buffer(void *integ, void **dev_ptr, size_t *n_floats);
-/* ...then refit mixtures (M-step) and split spatial cells; identical on every rank. */
-int b200pg_train_update(void *integ);
+int b200pg_train_update(void *integ, int commit);
+int b200pg_train_end(void *integ);
 
 int b200pg_film_clear(void *integ);
 int b200pg_film_device_buffer(void *integ, void **dev_ptr, size_t *n_floats); /* H*W*4: R,G,B,weight */
@@ -269,17 +276,22 @@ int b200pg_k_grid_lookup(void *integ, int medium, const float *p, size_t n, floa
 
 /* Guiding field kernels (vMF mixtures; this repo's own algorithm, oracle-pinned).
  * Field snapshot layout is documented in DESIGN.md. */
+/* pos n*3, dir n*3, u n*3 (lobe selection, u1, u2): out_pdf = pdf of dir, out_dir/out_spdf = sampled direction + pdf */
 int b200pg_k_vmm_pdf_sample(void *integ, const float *pos, const float *dir, const float *u, size_t n,
                             float *out_pdf, float *out_dir, float *out_spdf, uint32_t *out_cell);
 /* Bin n samples (pos n*3) by guiding cell: out_cell n, out_perm n (stable order), out_offsets n_cells+1. */
 int b200pg_k_bin_samples(void *integ, const float *pos, size_t n, uint32_t *out_cell, uint32_t *out_perm,
                          uint32_t *out_offsets, uint32_t *n_cells);
-/* One weighted-EM step over externally supplied samples (pos n*3, dir n*3, weight n, pdf n, dist n). */
+/* A complete training update (bin, n_iter x (E, M), split) over externally supplied samples
+ * (pos n*3, dir n*3, weight n, pdf n, dist n). n_iter = 0: E-step only, stats_out (cells*(4K+8) floats, may be NULL)
+ * receives the sufficient statistics and the field is left untouched. */
 int b200pg_k_em_step(void *integ, const float *pos, const float *dir, const float *weight, const float *pdf,
-                     const float *dist, size_t n);
-/* Field snapshot: header + cells + mixtures (flat floats). Pass NULL to query the size. */
-int b200pg_field_snapshot(void *integ, float *out, size_t *n_floats);
-int b200pg_field_load(void *integ, const float *in, size_t n_floats);
+                     const float *dist, size_t n, int n_iter, float *stats_out);
+/* Field snapshot as 32-bit words: header[8] = {'GUID', nNodes, nCells, K, 0...}, nodes[4*nNodes] = {axis (3 = leaf),
+ * split, left | cell, 0}, cell headers[8*nCells] = {running sample count, running weight sum, 0...}, lobes[12*nCells*K] =
+ * {pi, mu.xyz, kappa, norm, exp(-2 kappa), 0, S, R.xyz}. Pass out = NULL to query the size. */
+int b200pg_field_snapshot(void *integ, uint32_t *out, size_t *n_words);
+int b200pg_field_load(void *integ, const uint32_t *in, size_t n_words);
 
 #ifdef __cplusplus
 }

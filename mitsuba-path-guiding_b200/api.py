@@ -44,8 +44,11 @@ def lib():
     L.b200pg_scene_destroy.argtypes = [C.c_void_p]
     L.b200pg_integrator_create.restype = C.c_void_p
     L.b200pg_integrator_create.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), C.c_int]
-    for name in ("b200pg_render", "b200pg_cancel", "b200pg_film_clear", "b200pg_train_accumulate", "b200pg_train_update"):
+    for name in ("b200pg_render", "b200pg_cancel", "b200pg_film_clear", "b200pg_train_accumulate", "b200pg_train_end"):
         getattr(L, name).argtypes = [C.c_void_p]
+    L.b200pg_train_update.argtypes = [C.c_void_p, C.c_int]
+    L.b200pg_train_begin.argtypes = [C.c_void_p, u32p, u32p]
+    L.b200pg_guiding_mode.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.b200pg_progression_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     L.b200pg_train_stats_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.b200pg_film_device_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
@@ -65,9 +68,9 @@ def lib():
     L.b200pg_k_grid_lookup.argtypes = [C.c_void_p, C.c_int, fp, C.c_size_t, fp]
     L.b200pg_k_vmm_pdf_sample.argtypes = [C.c_void_p, fp, fp, fp, C.c_size_t, fp, fp, fp, u32p]
     L.b200pg_k_bin_samples.argtypes = [C.c_void_p, fp, C.c_size_t, u32p, u32p, u32p, u32p]
-    L.b200pg_k_em_step.argtypes = [C.c_void_p, fp, fp, fp, fp, fp, C.c_size_t]
-    L.b200pg_field_snapshot.argtypes = [C.c_void_p, fp, C.POINTER(C.c_size_t)]
-    L.b200pg_field_load.argtypes = [C.c_void_p, fp, C.c_size_t]
+    L.b200pg_k_em_step.argtypes = [C.c_void_p, fp, fp, fp, fp, fp, C.c_size_t, C.c_int, fp]
+    L.b200pg_field_snapshot.argtypes = [C.c_void_p, u32p, C.POINTER(C.c_size_t)]
+    L.b200pg_field_load.argtypes = [C.c_void_p, u32p, C.c_size_t]
     _lib = L
     return L
 
@@ -219,7 +222,15 @@ class Integrator:
         _check(lib().b200pg_scene_upload(self.h, C.byref(n)))
         return n.value
 
-    # ---- training hooks
+    # ---- guiding / training hooks
+    def guiding_mode(self, record, sample):
+        _check(lib().b200pg_guiding_mode(self.h, int(record), int(sample)))
+
+    def train_begin(self):
+        n, c = C.c_uint32(), C.c_uint32()
+        _check(lib().b200pg_train_begin(self.h, C.byref(n), C.byref(c)))
+        return n.value, c.value
+
     def train_accumulate(self):
         _check(lib().b200pg_train_accumulate(self.h))
 
@@ -229,8 +240,55 @@ class Integrator:
         _check(lib().b200pg_train_stats_buffer(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
-    def train_update(self):
-        _check(lib().b200pg_train_update(self.h))
+    def train_update(self, commit):
+        _check(lib().b200pg_train_update(self.h, int(commit)))
+
+    def train_end(self):
+        _check(lib().b200pg_train_end(self.h))
+
+    def train(self, n_iter=4, allreduce=None):
+        """One training update; ``allreduce(dev_ptr, n_floats)`` sums the statistics buffer over ranks (optional)."""
+        n, c = self.train_begin()
+        for it in range(n_iter):
+            self.train_accumulate()
+            if allreduce is not None:
+                allreduce(*self.train_stats_buffer())
+            self.train_update(it == n_iter - 1)
+        self.train_end()
+        return n, c
+
+    def field_snapshot(self):
+        n = C.c_size_t(0)
+        _check(lib().b200pg_field_snapshot(self.h, None, C.byref(n)))
+        w = np.zeros(n.value, np.uint32)
+        _check(lib().b200pg_field_snapshot(self.h, _u(w), C.byref(n)))
+        return w
+
+    def field_load(self, words):
+        words = np.ascontiguousarray(words, np.uint32)
+        _check(lib().b200pg_field_load(self.h, _u(words), words.size))
+
+    def k_vmm_pdf_sample(self, pos, dirs, u):
+        pos, dirs, u = (np.ascontiguousarray(x, np.float32) for x in (pos, dirs, u))
+        n = pos.shape[0]
+        pdf, sd, spdf, cell = np.zeros(n, np.float32), np.zeros((n, 3), np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint32)
+        _check(lib().b200pg_k_vmm_pdf_sample(self.h, _f(pos), _f(dirs), _f(u), n, _f(pdf), _f(sd), _f(spdf), _u(cell)))
+        return dict(pdf=pdf, dir=sd, spdf=spdf, cell=cell)
+
+    def k_bin_samples(self, pos, n_cells):
+        pos = np.ascontiguousarray(pos, np.float32)
+        n = pos.shape[0]
+        cell, perm, off = np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n_cells + 1, np.uint32)
+        nc = C.c_uint32()
+        _check(lib().b200pg_k_bin_samples(self.h, _f(pos), n, _u(cell), _u(perm), _u(off), C.byref(nc)))
+        assert nc.value == n_cells
+        return cell, perm, off
+
+    def k_em_step(self, s, n_iter, n_cells, K):
+        a = [np.ascontiguousarray(s[k], np.float32) for k in ("pos", "dir", "weight", "pdf", "dist")]
+        st = np.zeros(n_cells * (4 * K + 8), np.float32)
+        _check(lib().b200pg_k_em_step(self.h, *[_f(x) for x in a], a[0].shape[0], n_iter, _f(st)))
+        return st.reshape(n_cells, 4 * K + 8)
 
     # ---- per-kernel entry points
     def k_trace(self, rays, shadow=False):

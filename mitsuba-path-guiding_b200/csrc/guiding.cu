@@ -1,14 +1,697 @@
-// guiding.cu -- guiding-field kernels and their C-ABI entry points (filled in with the guiding rows).
-#include "../../include/b200pg.h"
+// guiding.cu -- training of the guiding field (north-star subsystem 3) and the standalone query kernel:
+//   k_guide_cells      sample position -> cell index (kd-tree walk)
+//   k_radix_*          hand-written stable LSD radix sort (8-bit digits) of (cell, sample index) pairs = binning;
+//                      bit-exact against the oracle's stable counting sort (oracle_guiding.h: guideBin)
+//   k_estep            weighted-EM E-step, warp-cooperative: lane k evaluates lobe k of the cell's mixture,
+//                      responsibilities are normalised with a warp reduction, every lane keeps the sufficient
+//                      statistics of its own lobe in registers (Kahan-compensated)
+//   k_reduce_partials  per-cell sum of the chunk partials in a fixed order (deterministic)
+//   k_mstep            M-step with decayed running statistics and MAP priors, one warp per cell
+//   k_guide_query      pdf / sample of the field at arbitrary points (b200pg_k_vmm_pdf_sample)
+// This is the repo's own algorithm (no guiding code exists in the reference snapshot); the CPU
+// statement it is tested against is oracle/oracle_guiding.h.
+#include <cmath>
+#include <cstring>
 
-extern "C" {
-int b200pg_train_accumulate(void *) { return -2; }
-int b200pg_train_stats_buffer(void *, void **, size_t *) { return -2; }
-int b200pg_train_update(void *) { return -2; }
-int b200pg_k_grid_lookup(void *, int, const float *, size_t, float *) { return -2; }
-int b200pg_k_vmm_pdf_sample(void *, const float *, const float *, const float *, size_t, float *, float *, float *, uint32_t *) { return -2; }
-int b200pg_k_bin_samples(void *, const float *, size_t, uint32_t *, uint32_t *, uint32_t *, uint32_t *) { return -2; }
-int b200pg_k_em_step(void *, const float *, const float *, const float *, const float *, const float *, size_t) { return -2; }
-int b200pg_field_snapshot(void *, float *, size_t *) { return -2; }
-int b200pg_field_load(void *, const float *, size_t) { return -2; }
+#include "guiding_device.cuh"
+#include "guiding_host.h"
+
+namespace pg {
+
+static constexpr int kSortThreads = 256;
+static constexpr int kSortRounds = 8;
+static constexpr int kSortTile = kSortThreads * kSortRounds;
+static constexpr int kChunk = 4096;  // samples per E-step work item
+
+__device__ __forceinline__ uint32_t lane() { return threadIdx.x & 31u; }
+
+__global__ void __launch_bounds__(256) k_guide_cells(GuideDevice G, const float4 *__restrict__ sPos, uint32_t n,
+                                                     uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 p = sPos[i];
+        keys[i] = guideLookup(G, f3(p.x, p.y, p.z));
+        vals[i] = i;
+    }
 }
+
+// ---- radix sort pass: per-block digit histogram, laid out digit-major (hist[digit * nBlocks + block])
+__global__ void __launch_bounds__(kSortThreads) k_radix_hist(const uint32_t *__restrict__ keys, uint32_t n, int shift,
+                                                             uint32_t *__restrict__ hist, uint32_t nBlocks) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * kSortTile;
+    for (int r = 0; r < kSortRounds; ++r) {
+        const uint32_t i = base + r * kSortThreads + threadIdx.x;
+        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[threadIdx.x * nBlocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// exclusive scan over all (digit, block) counters in three small kernels: per-segment scan + segment totals,
+// scan of the totals (one block), add-back. Integer sums: the result does not depend on the schedule.
+static constexpr int kScanSeg = 2048;  // entries per block (256 threads x 8)
+__global__ void __launch_bounds__(256) k_scan_segments(uint32_t *__restrict__ data, uint32_t m, uint32_t *__restrict__ totals) {
+    __shared__ uint32_t warpSums[8];
+    const uint32_t base = blockIdx.x * kScanSeg + threadIdx.x * 8;
+    uint32_t v[8], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        v[i] = base + i < m ? data[base + i] : 0u;
+        sum += v[i];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane() >= o) incl += t;
+    }
+    if (lane() == 31) warpSums[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t warpBase = 0;
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) warpBase += warpSums[w];
+    uint32_t run = warpBase + incl - sum;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (base + i < m) data[base + i] = run;
+        run += v[i];
+    }
+    if (threadIdx.x == 255) totals[blockIdx.x] = run;
+}
+__global__ void __launch_bounds__(1024) k_scan_totals(uint32_t *__restrict__ totals, uint32_t n) {
+    // n <= a few thousand: one block, chunked sequential carry
+    __shared__ uint32_t carry;
+    __shared__ uint32_t warpSums[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n ? totals[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane() >= o) incl += t;
+        }
+        if (lane() == 31) warpSums[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        uint32_t warpBase = 0;
+        for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) warpBase += warpSums[w];
+        const uint32_t c = carry;
+        if (i < n) totals[i] = c + warpBase + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = c + warpBase + incl;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) k_scan_add(uint32_t *__restrict__ data, uint32_t m, const uint32_t *__restrict__ totals) {
+    const uint32_t add = totals[blockIdx.x];
+    const uint32_t base = blockIdx.x * kScanSeg + threadIdx.x * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (base + i < m) data[base + i] += add;
+}
+
+// stable scatter: keys are visited in index order (round by round, warp by warp), so equal digits keep their order
+__global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t *__restrict__ keysIn, const uint32_t *__restrict__ valsIn,
+                                                                uint32_t *__restrict__ keysOut, uint32_t *__restrict__ valsOut,
+                                                                uint32_t n, int shift, const uint32_t *__restrict__ hist,
+                                                                uint32_t nBlocks) {
+    __shared__ uint32_t offs[256];
+    offs[threadIdx.x] = hist[threadIdx.x * nBlocks + blockIdx.x];
+    __syncthreads();
+    const uint32_t base = blockIdx.x * kSortTile;
+    const uint32_t warp = threadIdx.x >> 5;
+    for (int r = 0; r < kSortRounds; ++r) {
+        const uint32_t i = base + r * kSortThreads + threadIdx.x;
+        const bool valid = i < n;
+        const uint32_t key = valid ? keysIn[i] : 0u;
+        const uint32_t d = (key >> shift) & 255u;
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        unsigned peers = 0;
+        if (valid) peers = __match_any_sync(act, d);
+        const uint32_t rankInWarp = __popc(peers & ((1u << lane()) - 1u));
+        const bool leader = valid && rankInWarp == 0;
+        uint32_t pos = 0;
+        for (uint32_t w = 0; w < kSortThreads / 32; ++w) {
+            if (warp == w) {
+                if (valid) pos = offs[d] + rankInWarp;
+                __syncwarp();
+                if (leader) offs[d] += __popc(peers);
+            }
+            __syncthreads();
+        }
+        if (valid) {
+            keysOut[pos] = key;
+            valsOut[pos] = valsIn[i];
+        }
+    }
+}
+
+// first index of every cell that occurs in the sorted key array (no atomics: one writer per cell)
+__global__ void __launch_bounds__(256) k_cell_starts(const uint32_t *__restrict__ keys, uint32_t n, uint32_t *__restrict__ start) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t k = keys[i];
+        if (i == 0 || keys[i - 1] != k) start[k] = i;
+    }
+}
+
+// ---- E-step ------------------------------------------------------------------------------------------
+struct Kahan {
+    float s = 0, c = 0;
+    __device__ __forceinline__ void add(float v) {
+        const float y = v - c;
+        const float t = s + y;
+        c = (t - s) - y;
+        s = t;
+    }
+};
+
+// KP = lobes per sample group (power of two >= K): a warp evaluates 32 / KP samples at a time, lane (l % KP) owns
+// lobe (l % KP) of sample group (l / KP). Samples were gathered into sorted order beforehand, so a warp walks a
+// contiguous range of 16-byte records. Every lane keeps the statistics of its lobe (and group) in registers.
+template <int KP>
+__global__ void __launch_bounds__(256) k_estep(GuideDevice G, const float4 *__restrict__ sPos, const float4 *__restrict__ sDir,
+                                               const uint4 *__restrict__ work, uint32_t nWork, float *__restrict__ partials,
+                                               int stride) {
+    constexpr int kGroups = 32 / KP;
+    __shared__ float red[8 * kGroups][kGuideMaxK * 4 + 8];
+    const uint32_t warp = threadIdx.x >> 5, k = lane() % KP, grp = lane() / KP;
+    const int K = G.K;
+    for (uint32_t w = blockIdx.x; w < nWork; w += gridDim.x) {
+        const uint4 item = work[w];
+        float4 la = make_float4(0, 0, 0, 0), lb = make_float4(0, 0, 0, 0);
+        if ((int)k < K) {
+            la = __ldg(G.lobes + ((size_t)item.x * K + k) * 3);
+            lb = __ldg(G.lobes + ((size_t)item.x * K + k) * 3 + 1);
+        }
+        Kahan S, Rx, Ry, Rz, cn, cW, p1x, p1y, p1z, p2x, p2y, p2z;
+        // warp `warp` owns the contiguous slice [b, e) of the chunk
+        const uint32_t len = item.z - item.y, per = (len + 7) / 8;
+        const uint32_t b = item.y + warp * per, e = min(b + per, item.z);
+        for (uint32_t j0 = b; j0 < e; j0 += kGroups) {
+            const uint32_t j = j0 + grp;
+            const bool have = j < e;
+            float4 p = make_float4(0, 0, 0, 0), d = make_float4(0, 0, 1, 1);
+            if (have) {
+                p = sPos[j];
+                d = sDir[j];
+                cn.add(1.0f);
+                p1x.add(p.x); p1y.add(p.y); p1z.add(p.z);
+                p2x.add(p.x * p.x); p2y.add(p.y * p.y); p2z.add(p.z * p.z);
+            }
+            const float sw = p.w;
+            const bool good = have && sw > 0 && isfinite(sw);
+            float pk = 0.0f;
+            if (good && (int)k < K) {
+                const float c = la.y * d.x + la.z * d.y + la.w * d.z;
+                pk = la.x * lb.y * expf(lb.x * (c - 1.0f));
+            }
+            float total = pk;
+#pragma unroll
+            for (int o = KP / 2; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+            if (!good || !(total > 0) || !isfinite(total)) continue;
+            cW.add(sw);
+            const float g = sw * (pk * (1.0f / total));
+            S.add(g);
+            Rx.add(g * d.x);
+            Ry.add(g * d.y);
+            Rz.add(g * d.z);
+        }
+        float *r = red[warp * kGroups + grp];
+        if ((int)k < K) {
+            r[4 * k + 0] = S.s;
+            r[4 * k + 1] = Rx.s;
+            r[4 * k + 2] = Ry.s;
+            r[4 * k + 3] = Rz.s;
+        }
+        if (k == 0) {
+            float *c = r + 4 * K;
+            c[0] = cn.s; c[1] = cW.s; c[2] = p1x.s; c[3] = p1y.s; c[4] = p1z.s; c[5] = p2x.s; c[6] = p2y.s; c[7] = p2z.s;
+        }
+        __syncthreads();
+        for (int el = threadIdx.x; el < stride; el += blockDim.x) {
+            double acc = 0.0;
+            for (int ww = 0; ww < 8 * kGroups; ++ww) acc += (double)red[ww][el];
+            partials[(size_t)w * stride + el] = (float)acc;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_gather_samples(const float4 *__restrict__ sPos, const float4 *__restrict__ sDir,
+                                                        const uint32_t *__restrict__ perm, uint32_t n, float4 *__restrict__ oPos,
+                                                        float4 *__restrict__ oDir) {
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t i = perm[j];
+        oPos[j] = sPos[i];
+        oDir[j] = sDir[i];
+    }
+}
+
+// work items of one cell are consecutive: workOfs[cell] .. workOfs[cell + 1]
+__global__ void __launch_bounds__(256) k_reduce_partials(const float *__restrict__ partials, const uint32_t *__restrict__ workOfs,
+                                                         uint32_t nCells, int stride, float *__restrict__ stats) {
+    const size_t total = (size_t)nCells * stride;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t cell = (uint32_t)(i / stride), e = (uint32_t)(i % stride);
+        double acc = 0.0;
+        for (uint32_t w = workOfs[cell]; w < workOfs[cell + 1]; ++w) acc += (double)partials[(size_t)w * stride + e];
+        stats[i] = (float)acc;
+    }
+}
+
+// ---- M-step: one warp per cell, lane k = lobe k ----------------------------------------------------------
+__global__ void __launch_bounds__(256) k_mstep(float4 *__restrict__ lobes, const float *__restrict__ stats, uint32_t nCells, int K,
+                                               int stride, int commit) {
+    const uint32_t warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = (gridDim.x * blockDim.x) >> 5;
+    const int k = (int)lane();
+    for (uint32_t c = warpGlobal; c < nCells; c += nWarps) {
+        const float *st = stats + (size_t)c * stride;
+        float4 a = make_float4(0, 0, 0, 0), b = a, s = a;
+        float S = 0, R0 = 0, R1 = 0, R2 = 0;
+        if (k < K) {
+            float4 *L = lobes + ((size_t)c * K + k) * 3;
+            a = L[0];
+            b = L[1];
+            s = L[2];
+            S = kGuideDecay * s.x + st[4 * k];
+            R0 = kGuideDecay * s.y + st[4 * k + 1];
+            R1 = kGuideDecay * s.z + st[4 * k + 2];
+            R2 = kGuideDecay * s.w + st[4 * k + 3];
+        }
+        float sumS = S;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sumS += __shfl_xor_sync(0xffffffffu, sumS, o);
+        if (k < K) {
+            if (sumS > 0 && isfinite(sumS)) {
+                const float prior = kGuidePriorWeight * sumS / (float)K;
+                const float denom = 1.0f / (sumS + (float)K * prior);
+                a.x = (S + prior) * denom;
+                const float rl = sqrtf(R0 * R0 + R1 * R1 + R2 * R2);
+                float rbar = (rl + prior * kGuidePriorMeanCos) / (S + prior);
+                rbar = fminf(rbar, 0.9999f);
+                const float kappa = rbar * (3.0f - rbar * rbar) / (1.0f - rbar * rbar);
+                b.x = fminf(kGuideKappaMax, fmaxf(kGuideKappaMin, kappa));
+                if (rl > 0) {
+                    const float ir = 1.0f / rl;
+                    a.y = R0 * ir;
+                    a.z = R1 * ir;
+                    a.w = R2 * ir;
+                }
+                b.z = expf(-2.0f * b.x);
+                b.y = b.x / (2 * kPi * (1.0f - b.z));
+            }
+            float4 *L = lobes + ((size_t)c * K + k) * 3;
+            L[0] = a;
+            L[1] = b;
+            if (commit) L[2] = make_float4(S, R0, R1, R2);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_guide_query(GuideDevice G, const float *__restrict__ pos, const float *__restrict__ dir,
+                                                     const float *__restrict__ u, uint32_t n, float *__restrict__ outPdf,
+                                                     float *__restrict__ outDir, float *__restrict__ outSpdf,
+                                                     uint32_t *__restrict__ outCell) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float3 p = ld3(pos + 3 * (size_t)i), w = ld3(dir + 3 * (size_t)i);
+        const uint32_t c = guideLookup(G, p);
+        outCell[i] = c;
+        outPdf[i] = guidePdf(G, c, w);
+        const float3 d = guideSample(G, c, u[3 * (size_t)i], u[3 * (size_t)i + 1], u[3 * (size_t)i + 2]);
+        outDir[3 * (size_t)i] = d.x;
+        outDir[3 * (size_t)i + 1] = d.y;
+        outDir[3 * (size_t)i + 2] = d.z;
+        outSpdf[i] = guidePdf(G, c, d);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pack_samples(const float *pos, const float *dir, const float *weight, const float *pdf,
+                                                      const float *dist, uint32_t n, float4 *sPos, float4 *sDir, float *sDist) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        sPos[i] = make_float4(pos[3 * (size_t)i], pos[3 * (size_t)i + 1], pos[3 * (size_t)i + 2], weight ? weight[i] : 0.0f);
+        sDir[i] = make_float4(dir ? dir[3 * (size_t)i] : 0.0f, dir ? dir[3 * (size_t)i + 1] : 0.0f, dir ? dir[3 * (size_t)i + 2] : 1.0f,
+                              pdf ? pdf[i] : 1.0f);
+        sDist[i] = dist ? dist[i] : 0.0f;
+    }
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+static int gridFor(size_t n, int block) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    size_t want = (n + block - 1) / block;
+    return (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)sms * 8));
+}
+
+static void finalizeLobe(GuideLobeHost &l) {
+    l.eMin2K = std::exp(-2.0f * l.kappa);
+    l.norm = l.kappa / (2 * 3.14159265358979323846f * (1.0f - l.eMin2K));
+}
+
+void GuidingHost::init(const B200pgIntegratorParams &P, const HostScene &H, cudaStream_t st) {
+    stream = st;
+    active = P.guiding != 0;
+    K = std::min(std::max(P.guide_max_components > 0 ? P.guide_max_components : 16, 1), kGuideMaxK);
+    alpha = P.guiding_probability > 0 ? P.guiding_probability : 0.5f;
+    maxCellSamples = P.guide_max_cell_samples > 0 ? (float)P.guide_max_cell_samples : 32768.0f;
+    maxVerts = P.max_depth > 0 ? std::max(1, P.max_depth - 1) : 16;
+    maxVerts = std::min(maxVerts, 32);
+    float mn[3], mx[3];
+    for (int a = 0; a < 3; ++a) {  // slightly enlarged scene box
+        float ext = H.sceneMax[a] - H.sceneMin[a];
+        mn[a] = H.sceneMin[a] - 0.01f * ext - 1e-3f;
+        mx[a] = H.sceneMax[a] + 0.01f * ext + 1e-3f;
+    }
+    resetField(mn, mx);
+    dSCount.alloc(1);
+    CUDA_OK(cudaMemsetAsync(dSCount.p, 0, sizeof(uint32_t), stream));
+}
+
+void GuidingHost::resetField(const float *, const float *) {
+    nodes.assign(1, GuideNodeHost{3u, 0.0f, 0u, 0u});
+    cells.assign(1, GuideCellHost());
+    std::memset(&cells[0], 0, sizeof(GuideCellHost));
+    lobes.resize(K);
+    for (int k = 0; k < K; ++k) {  // spherical Fibonacci directions, equal weights
+        GuideLobeHost &l = lobes[k];
+        std::memset(&l, 0, sizeof(l));
+        float z = 1.0f - (2.0f * k + 1.0f) / (float)K;
+        float r = std::sqrt(std::max(0.0f, 1.0f - z * z));
+        float phi = 2.0f * 3.14159265358979323846f * (float)k * 0.6180339887f;
+        l.weight = 1.0f / K;
+        l.mux = r * std::cos(phi);
+        l.muy = r * std::sin(phi);
+        l.muz = z;
+        l.kappa = kGuideInitKappa;
+        finalizeLobe(l);
+    }
+    trained = false;
+    uploadField();
+}
+
+void GuidingHost::uploadField() {
+    dNodes.upload(reinterpret_cast<const uint4 *>(nodes.data()), nodes.size(), stream);
+    dLobes.upload(reinterpret_cast<const float4 *>(lobes.data()), lobes.size() * 3, stream);
+    CUDA_OK(cudaStreamSynchronize(stream));
+}
+
+void GuidingHost::ensureBatch(size_t nPaths) {
+    if (!active) return;
+    const size_t nv = nPaths * (size_t)maxVerts;
+    if (nv > vertCapacity) {
+        dVPos.alloc(nv); dVDir.alloc(nv); dVThr.alloc(nv); dVL.alloc(nv);
+        vertCapacity = nv;
+    }
+}
+
+void GuidingHost::configure(ShadeArgs &A) {
+    GuideDevice &G = A.G;
+    std::memset(&G, 0, sizeof(G));
+    G.nodes = dNodes.p;
+    G.lobes = dLobes.p;
+    G.K = K;
+    G.alpha = alpha;
+    G.enabled = active && sampling && trained;
+    G.record = active && recording;
+    G.vPos = dVPos.p; G.vDir = dVDir.p; G.vThr = dVThr.p; G.vL = dVL.p;
+    G.maxVerts = maxVerts;
+    G.sPos = dSPos.p; G.sDir = dSDir.p; G.sDist = dSDist.p;
+    G.sCount = dSCount.p;
+    G.sCapacity = (uint32_t)sampleCapacity;
+}
+
+void GuidingHost::sortByCell(uint32_t n) {
+    const uint32_t nBlocks = (n + kSortTile - 1) / kSortTile;
+    dKeysA.alloc(n); dKeysB.alloc(n); dValsA.alloc(n); dValsB.alloc(n);
+    dBlockHist.alloc((size_t)256 * std::max(nBlocks, 1u));
+    GuideDevice G;
+    std::memset(&G, 0, sizeof(G));
+    G.nodes = dNodes.p;
+    G.lobes = dLobes.p;
+    G.K = K;
+    k_guide_cells<<<gridFor(n, 256), 256, 0, stream>>>(G, dSPos.p, n, dKeysA.p, dValsA.p);
+    launches++;
+    uint32_t *kin = dKeysA.p, *vin = dValsA.p, *kout = dKeysB.p, *vout = dValsB.p;
+    const int passes = numCells() > 65536 ? 3 : (numCells() > 256 ? 2 : 1);
+    for (int pass = 0; pass < passes && n > 0; ++pass) {
+        const int shift = 8 * pass;
+        k_radix_hist<<<nBlocks, kSortThreads, 0, stream>>>(kin, n, shift, dBlockHist.p, nBlocks);
+        const uint32_t m = 256 * nBlocks, nSeg = (m + kScanSeg - 1) / kScanSeg;
+        dScanTotals.alloc(nSeg);
+        k_scan_segments<<<nSeg, 256, 0, stream>>>(dBlockHist.p, m, dScanTotals.p);
+        k_scan_totals<<<1, 1024, 0, stream>>>(dScanTotals.p, nSeg);
+        k_scan_add<<<nSeg, 256, 0, stream>>>(dBlockHist.p, m, dScanTotals.p);
+        k_radix_scatter<<<nBlocks, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, dBlockHist.p, nBlocks);
+        launches += 5;
+        std::swap(kin, kout);
+        std::swap(vin, vout);
+    }
+    sortedCells = kin;
+    sortedPerm = vin;
+    // per-cell counts -> offsets (host; the cell count is small)
+    dCellCount.alloc(numCells() + 1);
+    CUDA_OK(cudaMemsetAsync(dCellCount.p, 0xFF, numCells() * sizeof(uint32_t), stream));
+    if (n) {
+        k_cell_starts<<<gridFor(n, 256), 256, 0, stream>>>(sortedCells, n, dCellCount.p);
+        launches++;
+    }
+    std::vector<uint32_t> start(numCells());
+    CUDA_OK(cudaMemcpyAsync(start.data(), dCellCount.p, start.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    CUDA_OK(cudaGetLastError());
+    offsets.assign(numCells() + 1, n);
+    for (uint32_t c = numCells(); c-- > 0;) offsets[c] = start[c] != 0xFFFFFFFFu ? start[c] : offsets[c + 1];  // empty cells
+    offsets[0] = 0;
+}
+
+void GuidingHost::buildWork() {
+    std::vector<uint4> work;
+    std::vector<uint32_t> workOfs(numCells() + 1, 0);
+    for (uint32_t c = 0; c < numCells(); ++c) {
+        workOfs[c] = (uint32_t)work.size();
+        for (uint32_t b = offsets[c]; b < offsets[c + 1]; b += kChunk)
+            work.push_back(make_uint4(c, b, std::min(b + (uint32_t)kChunk, offsets[c + 1]), 0u));
+    }
+    workOfs[numCells()] = (uint32_t)work.size();
+    nWork = (uint32_t)work.size();
+    dWork.upload(work, stream);
+    dCellCount.upload(workOfs, stream);  // reused as the per-cell work offsets from here on
+    dSortPos.alloc(nSamples);
+    dSortDir.alloc(nSamples);
+    if (nSamples) {
+        k_gather_samples<<<gridFor(nSamples, 256), 256, 0, stream>>>(dSPos.p, dSDir.p, sortedPerm, nSamples, dSortPos.p, dSortDir.p);
+        launches++;
+    }
+    dPartials.alloc((size_t)std::max(nWork, 1u) * statsStride());
+    dStats.alloc((size_t)numCells() * statsStride());
+}
+
+void GuidingHost::begin() {
+    uint32_t n = 0;
+    CUDA_OK(cudaMemcpyAsync(&n, dSCount.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    nSamples = (uint32_t)std::min<size_t>(n, sampleCapacity);
+    sortByCell(nSamples);
+    buildWork();
+}
+
+void GuidingHost::beginExternal(const float *pos, const float *dir, const float *weight, const float *pdf, const float *dist,
+                                size_t n) {
+    if (n > sampleCapacity) {
+        dSPos.alloc(n); dSDir.alloc(n); dSDist.alloc(n);
+        sampleCapacity = n;
+    }
+    DevBuf<float> a, b, c, d, e;
+    a.upload(pos, 3 * n, stream);
+    if (dir) b.upload(dir, 3 * n, stream);
+    if (weight) c.upload(weight, n, stream);
+    if (pdf) d.upload(pdf, n, stream);
+    if (dist) e.upload(dist, n, stream);
+    if (n) {
+        k_pack_samples<<<gridFor(n, 256), 256, 0, stream>>>(a.p, dir ? b.p : nullptr, weight ? c.p : nullptr, pdf ? d.p : nullptr,
+                                                            dist ? e.p : nullptr, (uint32_t)n, dSPos.p, dSDir.p, dSDist.p);
+        launches++;
+    }
+    CUDA_OK(cudaStreamSynchronize(stream));
+    nSamples = (uint32_t)n;
+    sortByCell(nSamples);
+    buildWork();
+}
+
+void GuidingHost::accumulate() {
+    GuideDevice G;
+    std::memset(&G, 0, sizeof(G));
+    G.lobes = dLobes.p;
+    G.K = K;
+    const int stride = (int)statsStride();
+    if (nWork) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        const uint32_t grid = std::min<uint32_t>(nWork, (uint32_t)sms * 4);
+        if (K <= 8)
+            k_estep<8><<<grid, 256, 0, stream>>>(G, dSortPos.p, dSortDir.p, dWork.p, nWork, dPartials.p, stride);
+        else if (K <= 16)
+            k_estep<16><<<grid, 256, 0, stream>>>(G, dSortPos.p, dSortDir.p, dWork.p, nWork, dPartials.p, stride);
+        else
+            k_estep<32><<<grid, 256, 0, stream>>>(G, dSortPos.p, dSortDir.p, dWork.p, nWork, dPartials.p, stride);
+        launches++;
+    }
+    k_reduce_partials<<<gridFor((size_t)numCells() * stride, 256), 256, 0, stream>>>(dPartials.p, dCellCount.p, numCells(), stride,
+                                                                                      dStats.p);
+    launches++;
+}
+
+void GuidingHost::update(bool commit) {
+    const int stride = (int)statsStride();
+    k_mstep<<<gridFor((size_t)numCells() * 32, 256), 256, 0, stream>>>(dLobes.p, dStats.p, numCells(), K, stride, commit ? 1 : 0);
+    launches++;
+}
+
+void GuidingHost::end() {
+    // bring the refitted mixtures and the last statistics to the host, fold the cell statistics into the running
+    // headers, split over-full cells (same rule and arithmetic as oracle_guiding.h: guideSplit) and re-upload
+    const size_t stride = statsStride();
+    std::vector<float> stats((size_t)numCells() * stride);
+    CUDA_OK(cudaMemcpyAsync(lobes.data(), dLobes.p, lobes.size() * sizeof(GuideLobeHost), cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaMemcpyAsync(stats.data(), dStats.p, stats.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    CUDA_OK(cudaGetLastError());
+    const uint32_t nc0 = numCells();
+    for (uint32_t c = 0; c < nc0; ++c) {
+        const float *cs = &stats[stride * c + (size_t)K * 4];
+        cells[c].sampleCount = kGuideDecay * cells[c].sampleCount + cs[0];
+        cells[c].weightSum = kGuideDecay * cells[c].weightSum + cs[1];
+    }
+    std::vector<uint32_t> leafOf(nc0, 0);
+    for (uint32_t n = 0; n < nodes.size(); ++n)
+        if (nodes[n].axis == 3u) leafOf[nodes[n].left] = n;
+    for (uint32_t c = 0; c < nc0; ++c) {
+        if (!(cells[c].sampleCount > maxCellSamples)) continue;
+        const float *cs = &stats[stride * c + (size_t)K * 4];
+        const float n = cs[0];
+        if (!(n >= 2)) continue;
+        float mean[3];
+        double var[3];
+        for (int a = 0; a < 3; ++a) {
+            mean[a] = cs[2 + a] / n;
+            var[a] = (double)cs[5 + a] / (double)n - (double)mean[a] * (double)mean[a];
+        }
+        int axis = 0;
+        if (var[1] > var[axis]) axis = 1;
+        if (var[2] > var[axis]) axis = 2;
+        if (!(var[axis] > 0)) continue;
+        const uint32_t leaf = leafOf[c], left = (uint32_t)nodes.size(), newCell = numCells();
+        nodes.push_back(GuideNodeHost{3u, 0.0f, c, 0u});
+        nodes.push_back(GuideNodeHost{3u, 0.0f, newCell, 0u});
+        nodes[leaf] = GuideNodeHost{(uint32_t)axis, mean[axis], left, 0u};
+        GuideCellHost h = cells[c];
+        h.sampleCount *= 0.5f;
+        h.weightSum *= 0.5f;
+        cells[c] = h;
+        cells.push_back(h);
+        for (int k = 0; k < K; ++k) {
+            GuideLobeHost &l = lobes[(size_t)c * K + k];
+            l.statS *= 0.5f; l.statRx *= 0.5f; l.statRy *= 0.5f; l.statRz *= 0.5f;
+        }
+        for (int k = 0; k < K; ++k) lobes.push_back(lobes[(size_t)c * K + k]);
+    }
+    trained = true;
+    uploadField();
+    CUDA_OK(cudaMemsetAsync(dSCount.p, 0, sizeof(uint32_t), stream));
+    sortedPerm = sortedCells = nullptr;
+}
+
+void GuidingHost::trainLocal() {
+    begin();
+    for (int it = 0; it < emIterations; ++it) {
+        accumulate();
+        update(it == emIterations - 1);
+    }
+    end();
+}
+
+void GuidingHost::query(const float *pos, const float *dir, const float *u, size_t n, float *outPdf, float *outDir, float *outSpdf,
+                        uint32_t *outCell) {
+    DevBuf<float> dP, dD, dU, oP, oD, oS;
+    DevBuf<uint32_t> oC;
+    dP.upload(pos, 3 * n, stream);
+    dD.upload(dir, 3 * n, stream);
+    dU.upload(u, 3 * n, stream);
+    oP.alloc(n); oD.alloc(3 * n); oS.alloc(n); oC.alloc(n);
+    GuideDevice G;
+    std::memset(&G, 0, sizeof(G));
+    G.nodes = dNodes.p;
+    G.lobes = dLobes.p;
+    G.K = K;
+    if (n) k_guide_query<<<gridFor(n, 256), 256, 0, stream>>>(G, dP.p, dD.p, dU.p, (uint32_t)n, oP.p, oD.p, oS.p, oC.p);
+    launches++;
+    CUDA_OK(cudaMemcpyAsync(outPdf, oP.p, n * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaMemcpyAsync(outDir, oD.p, 3 * n * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaMemcpyAsync(outSpdf, oS.p, n * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaMemcpyAsync(outCell, oC.p, n * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    CUDA_OK(cudaGetLastError());
+}
+
+void GuidingHost::bin(const float *pos, size_t n, uint32_t *outCell, uint32_t *outPerm, uint32_t *outOffsets, uint32_t *nCells) {
+    beginExternal(pos, nullptr, nullptr, nullptr, nullptr, n);
+    if (n) {
+        CUDA_OK(cudaMemcpyAsync(outPerm, sortedPerm, n * 4, cudaMemcpyDeviceToHost, stream));
+        // cells in ORIGINAL order: keys buffer A still holds them only if an even number of passes ran; recompute instead
+        GuideDevice G;
+        std::memset(&G, 0, sizeof(G));
+        G.nodes = dNodes.p;
+        DevBuf<uint32_t> k, v;
+        k.alloc(n); v.alloc(n);
+        k_guide_cells<<<gridFor(n, 256), 256, 0, stream>>>(G, dSPos.p, (uint32_t)n, k.p, v.p);
+        launches++;
+        CUDA_OK(cudaMemcpyAsync(outCell, k.p, n * 4, cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+    }
+    std::memcpy(outOffsets, offsets.data(), offsets.size() * 4);
+    if (nCells) *nCells = numCells();
+    CUDA_OK(cudaGetLastError());
+}
+
+std::vector<uint32_t> GuidingHost::snapshot() {
+    std::vector<uint32_t> w(8 + 4 * nodes.size() + 8 * cells.size() + 12 * lobes.size());
+    w[0] = 0x47554944u;
+    w[1] = (uint32_t)nodes.size();
+    w[2] = (uint32_t)cells.size();
+    w[3] = (uint32_t)K;
+    w[4] = w[5] = w[6] = w[7] = 0;
+    size_t o = 8;
+    std::memcpy(&w[o], nodes.data(), nodes.size() * 16);
+    o += 4 * nodes.size();
+    std::memcpy(&w[o], cells.data(), cells.size() * 32);
+    o += 8 * cells.size();
+    std::memcpy(&w[o], lobes.data(), lobes.size() * 48);
+    return w;
+}
+
+bool GuidingHost::load(const uint32_t *w, size_t n) {
+    if (n < 8 || w[0] != 0x47554944u) return false;
+    const size_t nn = w[1], nc = w[2];
+    const int k = (int)w[3];
+    if (k <= 0 || k > kGuideMaxK || n != 8 + 4 * nn + 8 * nc + 12 * nc * (size_t)k) return false;
+    K = k;
+    nodes.resize(nn);
+    cells.resize(nc);
+    lobes.resize(nc * (size_t)K);
+    size_t o = 8;
+    std::memcpy(nodes.data(), &w[o], nn * 16);
+    o += 4 * nn;
+    std::memcpy(cells.data(), &w[o], nc * 32);
+    o += 8 * nc;
+    std::memcpy(lobes.data(), &w[o], lobes.size() * 48);
+    trained = true;
+    uploadField();
+    return true;
+}
+
+}  // namespace pg

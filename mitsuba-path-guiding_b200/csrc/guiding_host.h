@@ -1,19 +1,106 @@
-// guiding_host.h -- host side of the guiding field (training schedule hooks).
+// guiding_host.h -- host side of the guiding field: device buffers, training schedule, snapshots.
+//
+// A training update (north-star subsystem 3) runs between two progressions, where a guided version of
+// ProgressiveMonteCarloIntegrator would use its postprogression() hook (progressiveintegrator.h:40-52):
+//   begin()      count the recorded samples, look up their cells, stable radix sort by cell (binning)
+//   accumulate() E-step: per-cell sufficient statistics of the local samples  -> stats buffer
+//   [ external sum of the stats buffer over ranks: NCCL allreduce, see bench.py / INTEGRATION.md ]
+//   update()     M-step from decayed running statistics + MAP priors (identical on every rank)
+//   end()        spatial split of over-full cells (host, deterministic), re-upload of the field
 #pragma once
 #include <cuda_runtime.h>
 
+#include <vector>
+
 #include "../../include/b200pg.h"
+#include "devbuf.h"
 #include "host_scene.h"
 #include "wavefront.cuh"
 
 namespace pg {
 
+struct GuideNodeHost {
+    uint32_t axis;
+    float split;
+    uint32_t left;
+    uint32_t pad;
+};
+struct GuideLobeHost {
+    float weight, mux, muy, muz;
+    float kappa, norm, eMin2K, pad0;
+    float statS, statRx, statRy, statRz;
+};
+struct GuideCellHost {
+    float sampleCount, weightSum;
+    float pad[6];
+};
+
 struct GuidingHost {
-    void init(const B200pgIntegratorParams &, const HostScene &, cudaStream_t) {}
-    void configure(ShadeArgs &A) { A.G.enabled = 0; }
-    void preprogression(int) {}
-    void postprogression(int, void *) {}
-    uint32_t numCells() const { return 0; }
+    // configuration
+    int K = 16;
+    int maxVerts = 0;
+    float alpha = 0.5f;
+    float maxCellSamples = 32768;
+    int emIterations = 4;
+    bool active = false;    // guiding requested by the integrator parameters
+    bool trained = false;   // the field has seen at least one training update
+    bool recording = false; // the next progression records training vertices
+    bool sampling = false;  // the next progression samples from the field
+    cudaStream_t stream = nullptr;
+
+    // field (host mirror + device copy)
+    std::vector<GuideNodeHost> nodes;
+    std::vector<GuideLobeHost> lobes;
+    std::vector<GuideCellHost> cells;
+    DevBuf<uint4> dNodes;
+    DevBuf<float4> dLobes;
+
+    // training-vertex records and samples
+    DevBuf<float4> dVPos, dVDir, dVThr, dVL;
+    DevBuf<float4> dSPos, dSDir, dSortPos, dSortDir;
+    DevBuf<float> dSDist;
+    DevBuf<uint32_t> dSCount;
+    size_t vertCapacity = 0, sampleCapacity = 0;
+
+    // binning (radix sort) and EM scratch
+    DevBuf<uint32_t> dKeysA, dKeysB, dValsA, dValsB, dBlockHist, dCellCount, dScanTotals;
+    DevBuf<float> dStats, dPartials;
+    DevBuf<uint4> dWork;  // (cell, begin, end, 0) chunks of the sorted sample range
+    std::vector<uint32_t> offsets;  // per-cell offsets of the current binning (host)
+    uint32_t nSamples = 0, nWork = 0;
+    uint32_t *sortedPerm = nullptr;  // device pointer into dVals*, valid between begin() and end()
+    uint32_t *sortedCells = nullptr;
+    uint64_t launches = 0;
+
+    void init(const B200pgIntegratorParams &P, const HostScene &H, cudaStream_t st);
+    void resetField(const float *bmin, const float *bmax);
+    void uploadField();
+    void ensureBatch(size_t nPaths);
+    void configure(ShadeArgs &A);
+    void preprogression(int pass) { (void)pass; }
+    uint32_t numCells() const { return (uint32_t)cells.size(); }
+    size_t statsStride() const { return (size_t)K * 4 + 8; }
+
+    // training update
+    void begin();
+    void beginExternal(const float *pos, const float *dir, const float *weight, const float *pdf, const float *dist, size_t n);
+    void accumulate();
+    void update(bool commit);
+    void end();
+    void trainLocal();  // begin + emIterations x (accumulate, update) + end
+
+    // per-kernel entry points
+    void query(const float *pos, const float *dir, const float *u, size_t n, float *outPdf, float *outDir, float *outSpdf,
+               uint32_t *outCell);
+    void bin(const float *pos, size_t n, uint32_t *outCell, uint32_t *outPerm, uint32_t *outOffsets, uint32_t *nCells);
+
+    // snapshots (32-bit words; layout in oracle/oracle_guiding.h and DESIGN.md)
+    std::vector<uint32_t> snapshot();
+    bool load(const uint32_t *w, size_t n);
+
+private:
+    void sortByCell(uint32_t n);
+    void buildWork();
 };
 
 }  // namespace pg

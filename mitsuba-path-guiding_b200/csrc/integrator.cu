@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "../../include/b200pg.h"
+#include "devbuf.h"
 #include "guiding_host.h"
 #include "host_scene.h"
 #include "wavefront.cuh"
@@ -50,38 +51,6 @@ static int fail(const std::string &msg, int code = -1) {
     g_lastError = msg;
     return code;
 }
-#define CUDA_OK(expr)                                                                                       \
-    do {                                                                                                    \
-        cudaError_t e_ = (expr);                                                                            \
-        if (e_ != cudaSuccess) throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(e_)); \
-    } while (0)
-
-template <typename T>
-struct DevBuf {
-    T *p = nullptr;
-    size_t n = 0;
-    DevBuf() {}
-    DevBuf(const DevBuf &) = delete;
-    DevBuf &operator=(const DevBuf &) = delete;
-    ~DevBuf() { release(); }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        n = 0;
-    }
-    void alloc(size_t count) {
-        if (count <= n) return;
-        release();
-        CUDA_OK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
-        n = count;
-    }
-    void upload(const T *src, size_t count, cudaStream_t st = 0) {
-        alloc(count);
-        if (count) CUDA_OK(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
-    }
-    void upload(const std::vector<T> &v, cudaStream_t st = 0) { upload(v.data(), v.size(), st); }
-};
-
 struct PathBuffers {
     DevBuf<float4> rayO, rayD, thr, rad, pos;
     DevBuf<uint32_t> flags, slot;
@@ -270,6 +239,7 @@ struct Integrator {
     // without host synchronisation unless maxDepth is infinite.
     void runBatch(const BatchDesc &B, float *radianceOut) {
         ensureBatch(B.nPaths);
+        guide.ensureBatch(B.nPaths);
         const size_t zeroBytes = offsetof(Counters, paths);
         CUDA_OK(cudaMemsetAsync(dCounters.p, 0, zeroBytes, stream));
         PathState cur = bufA.view(), next = bufB.view();
@@ -349,6 +319,13 @@ struct Integrator {
         if (rowBegin >= rowEnd || nSamples <= 0) return;
         size_t maxBatch = params.max_batch_paths > 0 ? (size_t)params.max_batch_paths : (size_t)4 << 20;
         const size_t rowPaths = (size_t)W;
+        if (guide.active && guide.recording) {
+            size_t want = std::min<size_t>((size_t)W * (rowEnd - rowBegin) * nSamples * guide.maxVerts, (size_t)48 << 20);
+            if (want > guide.sampleCapacity) {
+                guide.dSPos.alloc(want); guide.dSDir.alloc(want); guide.dSDist.alloc(want);
+                guide.sampleCapacity = want;
+            }
+        }
         // device time of the whole progression: CUDA events on the launching stream
         CUDA_OK(cudaEventRecord(ev[2], stream));
         // split: whole band x k samples if it fits, else row chunks per sample
@@ -527,18 +504,31 @@ int b200pg_render(void *integ) {
     if (self->params.max_render_time > 0) {
         int pass = 0;
         while (!self->cancel.load()) {
-            self->guide.preprogression(pass);
+            self->guide.recording = self->guide.active && pass < self->params.training_progressions;
+            self->guide.sampling = true;
             self->renderProgression(pass * perPass, perPass, 0, 0);
-            self->guide.postprogression(pass, nullptr);
+            if (self->guide.recording) self->guide.trainLocal();
             ++pass;
             double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             if (el >= self->params.max_render_time) break;
         }
     } else {
+        const int trainPasses = self->guide.active ? std::min(self->params.training_progressions, numPasses) : 0;
         for (int pass = 0; pass < numPasses && !self->cancel.load(); ++pass) {
-            self->guide.preprogression(pass);
+            // preprogression: choose what this pass records / samples
+            self->guide.recording = pass < trainPasses;
+            self->guide.sampling = true;
             self->renderProgression(pass * perPass, perPass, 0, 0);
-            self->guide.postprogression(pass, nullptr);
+            // postprogression: refit the field from this pass' samples
+            if (pass < trainPasses) {
+                cudaEvent_t t = self->spanBegin();
+                self->guide.trainLocal();
+                self->spanEnd(Integrator::kTimeTrain, t);
+                CUDA_OK(cudaStreamSynchronize(self->stream));
+                self->drainSpans();
+                if (self->params.guide_train_discard_film && pass == trainPasses - 1)
+                    CUDA_OK(cudaMemsetAsync(self->dFilm.p, 0, self->dFilm.n * sizeof(float4), self->stream));
+            }
         }
     }
     self->pullCounters();
@@ -610,6 +600,7 @@ int b200pg_stats(void *integ, B200pgStats *out) {
     if (!integ || !out) return fail("null argument");
     Integrator *self = (Integrator *)integ;
     *out = self->stats;
+    out->kernel_launches += self->guide.launches;
     out->guide_cells = self->guide.numCells();
     return 0;
 }
@@ -770,6 +761,121 @@ int b200pg_k_film_splat(void *integ, const float *pos, const float *rgb, size_t 
     CUDA_OK(cudaGetLastError());
     self->stats.kernel_launches++;
     PG_END
+}
+
+// ---------------------------------------------------------------------------------------------
+// guiding: training hooks and per-kernel entry points
+// ---------------------------------------------------------------------------------------------
+int b200pg_guiding_mode(void *integ, int record, int sample) {
+    if (!integ) return fail("null integrator");
+    Integrator *self = (Integrator *)integ;
+    if (!self->guide.active && (record || sample)) return fail("guiding is not enabled in the integrator parameters");
+    self->guide.recording = record != 0;
+    self->guide.sampling = sample != 0;
+    return 0;
+}
+
+int b200pg_train_begin(void *integ, uint32_t *n_samples, uint32_t *n_cells) {
+    PG_TRY(integ)
+    if (!self->guide.active) return fail("guiding is not enabled in the integrator parameters");
+    cudaEvent_t t = self->spanBegin();
+    self->guide.begin();
+    self->spanEnd(Integrator::kTimeTrain, t);
+    CUDA_OK(cudaStreamSynchronize(self->stream));
+    self->drainSpans();
+    if (n_samples) *n_samples = self->guide.nSamples;
+    if (n_cells) *n_cells = self->guide.numCells();
+    PG_END
+}
+int b200pg_train_accumulate(void *integ) {
+    PG_TRY(integ)
+    cudaEvent_t t = self->spanBegin();
+    self->guide.accumulate();
+    self->spanEnd(Integrator::kTimeTrain, t);
+    CUDA_OK(cudaStreamSynchronize(self->stream));
+    CUDA_OK(cudaGetLastError());
+    self->drainSpans();
+    PG_END
+}
+int b200pg_train_stats_buffer(void *integ, void **dev_ptr, size_t *n_floats) {
+    if (!integ) return fail("null integrator");
+    Integrator *self = (Integrator *)integ;
+    if (dev_ptr) *dev_ptr = self->guide.dStats.p;
+    if (n_floats) *n_floats = (size_t)self->guide.numCells() * self->guide.statsStride();
+    return 0;
+}
+int b200pg_train_update(void *integ, int commit) {
+    PG_TRY(integ)
+    cudaEvent_t t = self->spanBegin();
+    self->guide.update(commit != 0);
+    self->spanEnd(Integrator::kTimeTrain, t);
+    CUDA_OK(cudaStreamSynchronize(self->stream));
+    CUDA_OK(cudaGetLastError());
+    self->drainSpans();
+    PG_END
+}
+int b200pg_train_end(void *integ) {
+    PG_TRY(integ)
+    cudaEvent_t t = self->spanBegin();
+    self->guide.end();
+    self->spanEnd(Integrator::kTimeTrain, t);
+    CUDA_OK(cudaStreamSynchronize(self->stream));
+    self->drainSpans();
+    PG_END
+}
+
+int b200pg_k_vmm_pdf_sample(void *integ, const float *pos, const float *dir, const float *u, size_t n, float *out_pdf,
+                            float *out_dir, float *out_spdf, uint32_t *out_cell) {
+    PG_TRY(integ)
+    self->guide.query(pos, dir, u, n, out_pdf, out_dir, out_spdf, out_cell);
+    PG_END
+}
+int b200pg_k_bin_samples(void *integ, const float *pos, size_t n, uint32_t *out_cell, uint32_t *out_perm, uint32_t *out_offsets,
+                         uint32_t *n_cells) {
+    PG_TRY(integ)
+    self->guide.bin(pos, n, out_cell, out_perm, out_offsets, n_cells);
+    PG_END
+}
+int b200pg_k_em_step(void *integ, const float *pos, const float *dir, const float *weight, const float *pdf, const float *dist,
+                     size_t n, int n_iter, float *stats_out) {
+    PG_TRY(integ)
+    GuidingHost &g = self->guide;
+    g.beginExternal(pos, dir, weight, pdf, dist, n);
+    if (n_iter <= 0) {
+        g.accumulate();
+        if (stats_out)
+            CUDA_OK(cudaMemcpyAsync(stats_out, g.dStats.p, (size_t)g.numCells() * g.statsStride() * sizeof(float),
+                                    cudaMemcpyDeviceToHost, self->stream));
+        CUDA_OK(cudaStreamSynchronize(self->stream));
+        CUDA_OK(cudaGetLastError());
+    } else {
+        for (int it = 0; it < n_iter; ++it) {
+            g.accumulate();
+            g.update(it == n_iter - 1);
+        }
+        if (stats_out)
+            CUDA_OK(cudaMemcpyAsync(stats_out, g.dStats.p, (size_t)g.numCells() * g.statsStride() * sizeof(float),
+                                    cudaMemcpyDeviceToHost, self->stream));
+        g.end();
+    }
+    PG_END
+}
+int b200pg_field_snapshot(void *integ, uint32_t *out, size_t *n_words) {
+    PG_TRY(integ)
+    std::vector<uint32_t> w = self->guide.snapshot();
+    if (out && n_words && *n_words >= w.size()) std::memcpy(out, w.data(), w.size() * 4);
+    if (n_words) *n_words = w.size();
+    PG_END
+}
+int b200pg_field_load(void *integ, const uint32_t *in, size_t n_words) {
+    PG_TRY(integ)
+    if (!self->guide.load(in, n_words)) return fail("malformed guiding-field snapshot");
+    self->guide.sampling = true;
+    PG_END
+}
+int b200pg_k_grid_lookup(void *integ, int medium, const float *p, size_t n, float *out) {
+    (void)integ; (void)medium; (void)p; (void)n; (void)out;
+    return fail("medium kernels are not built yet");
 }
 
 }  // extern "C"

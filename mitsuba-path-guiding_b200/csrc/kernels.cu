@@ -278,6 +278,37 @@ __global__ void __launch_bounds__(128) k_trace_rays(DeviceScene S, const float4 
 // Shade stage (surface path tracer, ProgressiveMIPathTracer::Li)
 // ------------------------------------------------------------------------------------------
 
+// Training samples of a finished path: for every recorded vertex the incident-radiance estimate along the
+// sampled direction is everything the path gathered after the vertex divided by the throughput right after it;
+// sample weight = avg_rgb(estimate) / pdf. Called by whole warps; one atomic per warp reserves the output range.
+PG_DEV void emitTrainingSamples(const GuideDevice &G, bool finished, uint32_t slot, uint32_t vcount, float3 Lfinal) {
+    const uint32_t nMine = finished ? vcount : 0u;
+    uint32_t incl = nMine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)laneId() >= o) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    uint32_t base = 0;
+    if (laneId() == 31) base = atomicAdd(G.sCount, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    uint32_t dst = base + incl - nMine;
+    for (uint32_t v = 0; v < nMine; ++v, ++dst) {
+        if (dst >= G.sCapacity) break;
+        const size_t vi = (size_t)slot * G.maxVerts + v;
+        const float4 p = G.vPos[vi], d = G.vDir[vi], T = G.vThr[vi], Lk = G.vL[vi];
+        const float3 diff = Lfinal - f3(Lk.x, Lk.y, Lk.z);
+        const float ex = T.x > 0 ? diff.x / T.x : 0.0f, ey = T.y > 0 ? diff.y / T.y : 0.0f, ez = T.z > 0 ? diff.z / T.z : 0.0f;
+        float w = ((ex + ey + ez) * (1.0f / 3.0f)) / p.w;
+        if (!isfinite(w) || w < 0) w = 0.0f;
+        G.sPos[dst] = make_float4(p.x, p.y, p.z, w);
+        G.sDir[dst] = make_float4(d.x, d.y, d.z, p.w);
+        G.sDist[dst] = d.w;
+    }
+}
+
 // A terminated path leaves its final sample value in the splat buffer (indexed by the path's slot, i.e.
 // in pixel order); k_splat rasterises the whole batch afterwards with all lanes busy.
 PG_DEV void finishPath(const ShadeArgs &A, uint32_t slot, float4 pos4, float3 L) {
@@ -319,7 +350,7 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(ShadeArgs A) {
         float newPdf = 0.0f;
         float3 shO = f3(0.0f), shD = f3(0.0f), shC = f3(0.0f);
         float shMaxT = 0.0f;
-        uint32_t depth = 0;
+        uint32_t depth = 0, vcount = 0;
 
         if (valid) {
             ro = A.cur.rayO[i];
@@ -345,6 +376,15 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(ShadeArgs A) {
             h.u = h4.y;
             h.v = h4.z;
             h.prim = __float_as_uint(h4.w);
+            vcount = (fl >> kVertShift) & 0xFFu;
+            if (A.G.record && vcount > 0 && !(fl & kFlagVertexClosed)) {
+                // close the previous training vertex: radiance gathered so far (its NEE has landed by now)
+                // and the distance to this hit
+                const size_t vi = (size_t)slot * A.G.maxVerts + (vcount - 1);
+                A.G.vL[vi] = make_float4(L.x, L.y, L.z, 0.0f);
+                A.G.vDir[vi].w = h.prim == kMiss ? 0.0f : h.t;
+                fl |= kFlagVertexClosed;
+            }
 
             if (fl & kFlagDead) {
                 terminate = true;
@@ -386,6 +426,9 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(ShadeArgs A) {
                 if (!terminate) {
                     // ---- direct illumination sampling (:191-219)
                     const uint32_t btype = bsdf.typeFlags;
+                    // guided vertex: smooth BSDF only -- delta lobes are never guided
+                    const bool guided = A.G.enabled && (btype & kSmooth);
+                    const uint32_t gcell = guided ? guideLookup(A.G, its.p) : 0u;
                     if (cfg.useNee && (btype & kSmooth)) {
                         const float3 refN = (btype & (kTransmission | kBackSide)) == 0 ? its.sh.n : f3(0.0f);  // records.inl:160-164
                         DirectSample dRec;
@@ -395,7 +438,8 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(ShadeArgs A) {
                             const float3 woL = its.sh.toLocal(dRec.d);
                             const float3 bsdfVal = bsdfEval(bsdf, its.wi, woL);
                             if (!isZero(bsdfVal) && (!cfg.strictNormals || dot(its.geoN, dRec.d) * woL.z > 0)) {
-                                const float bPdf = bsdfPdf(bsdf, its.wi, woL);
+                                float bPdf = bsdfPdf(bsdf, its.wi, woL);
+                                if (guided) bPdf = A.G.alpha * guidePdf(A.G, gcell, dRec.d) + (1 - A.G.alpha) * bPdf;
                                 const float weight = miWeight(dRec.pdf, bPdf);
                                 shC = thr * value * bsdfVal * weight;
                                 shO = its.p;
@@ -408,12 +452,37 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(ShadeArgs A) {
                     // ---- BSDF sampling (:226-238)
                     float bPdf, bEta;
                     uint32_t sampledType;
-                    float3 woL;
-                    const float3 bsdfWeight = bsdfSample(bsdf, its.wi, rng.next2D(), woL, bPdf, bEta, sampledType);
+                    float3 woL, wo, bsdfWeight;
+                    if (guided) {
+                        // one-sample MIS between the guiding mixture (probability alpha) and the BSDF
+                        float u0 = rng.next1D();
+                        const float2 u12 = rng.next2D();
+                        float3 fcos;
+                        float pb;
+                        bool ok = true;
+                        if (u0 < A.G.alpha) {
+                            u0 /= A.G.alpha;
+                            wo = guideSample(A.G, gcell, u0, u12.x, u12.y);
+                            woL = its.sh.toLocal(wo);
+                            fcos = bsdfEval(bsdf, its.wi, woL);
+                            pb = bsdfPdf(bsdf, its.wi, woL);
+                            bEta = 1.0f;
+                            sampledType = kGlossyReflection;
+                        } else {
+                            const float3 w = bsdfSample(bsdf, its.wi, u12, woL, pb, bEta, sampledType);
+                            ok = !isZero(w);
+                            fcos = w * pb;
+                            wo = its.sh.toWorld(woL);
+                        }
+                        bPdf = ok ? A.G.alpha * guidePdf(A.G, gcell, wo) + (1 - A.G.alpha) * pb : 0.0f;
+                        bsdfWeight = (ok && !isZero(fcos) && bPdf > 0) ? fcos / bPdf : f3(0.0f);
+                    } else {
+                        bsdfWeight = bsdfSample(bsdf, its.wi, rng.next2D(), woL, bPdf, bEta, sampledType);
+                        wo = its.sh.toWorld(woL);
+                    }
                     if (isZero(bsdfWeight)) {
                         terminate = true;
                     } else {
-                        const float3 wo = its.sh.toWorld(woL);
                         if (cfg.strictNormals && dot(its.geoN, wo) * woL.z <= 0) {
                             terminate = true;
                         } else {
@@ -426,6 +495,14 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(ShadeArgs A) {
                             if (sampledType & kDelta) fl |= kFlagPrevDelta;
                             if (sampledType != kNull) fl |= kFlagScattered;
                             alive = true;
+                            if (A.G.record && (btype & kSmooth) && (int)vcount < A.G.maxVerts) {
+                                const size_t vi = (size_t)slot * A.G.maxVerts + vcount;
+                                A.G.vPos[vi] = make_float4(its.p.x, its.p.y, its.p.z, bPdf);
+                                A.G.vDir[vi] = make_float4(wo.x, wo.y, wo.z, 0.0f);
+                                A.G.vThr[vi] = make_float4(thr.x, thr.y, thr.z, 0.0f);
+                                vcount++;
+                                fl &= ~kFlagVertexClosed;
+                            }
                         }
                     }
                 }
@@ -448,7 +525,7 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(ShadeArgs A) {
             A.next.rad[j] = make_float4(L.x, L.y, L.z, newPdf);
             A.next.pos[j] = make_float4(pos4.x, pos4.y, __uint_as_float((uint32_t)rng.state),
                                         __uint_as_float((uint32_t)(rng.state >> 32)));
-            A.next.flags[j] = (fl & ~kDepthMask) | (depth & kDepthMask);
+            A.next.flags[j] = (fl & ~(kDepthMask | (0xFFu << kVertShift))) | (depth & kDepthMask) | (vcount << kVertShift);
             A.next.slot[j] = slot;
             A.next.medium[j] = medium;
         }
@@ -462,6 +539,7 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(ShadeArgs A) {
             doneLen += depth;
             finishPath(A, slot, pos4, L);
         }
+        if (A.G.record) emitTrainingSamples(A.G, valid && terminate, slot, vcount, L);
     }
     warpAddU64(&A.C->paths, donePaths);
     warpAddU64(&A.C->pathLen, doneLen);

@@ -20,10 +20,12 @@ enum : uint32_t {
     kFlagScattered = 1u << 11,
     kFlagPrevMedium = 1u << 12,  // last event was a medium scattering event
     kFlagNoTrace = 1u << 13,
+    kFlagVertexClosed = 1u << 14,  // the last training vertex already has its L_k / distance
     kDepthMask = 0xFFu
 };
 
 static constexpr int kShadeThreads = 256;
+static constexpr int kVertShift = 16;  // flags bits 16-23: number of recorded training vertices
 
 struct PathState {
     float4 *rayO;     // o.xyz, mint

@@ -22,6 +22,7 @@
 #include "oracle_bsdf.h"
 #include "oracle_medium.h"
 #include "oracle_scene.h"
+#include "oracle_guiding.h"
 
 namespace orc {
 
@@ -412,14 +413,32 @@ static inline Float miWeight(Float pdfA, Float pdfB) {  // progressive_path.cpp:
     return pdfA / (pdfA + pdfB);
 }
 
+// Guiding context of one Li call: the field to sample from (may be null) and the training-sample sink (may be
+// null). The guided branches below are this repo's design (oracle_guiding.h), everything else is the reference's.
+struct GuideCtx {
+    const GuideField *field = nullptr;
+    GuideSamples *rec = nullptr;
+    Float alpha = 0.5f;  // one-sample MIS selection probability of the guiding distribution
+};
+struct GuideVertex {
+    Vec3 pos, dir, T, Lk;
+    Float pdf, dist;
+};
+
 // ProgressiveMIPathTracer::Li, progressive_path.cpp:133-314 (no environment emitter, no subsurface)
-static Vec3 Li_path(const Scene &scene, const B200pgIntegratorParams &P, const Ray &r, Rng &rng, Stats &st) {
+static Vec3 Li_path(const Scene &scene, const B200pgIntegratorParams &P, const Ray &r, Rng &rng, Stats &st,
+                    const GuideCtx *G = nullptr) {
     Intersection its;
     Ray ray(r);
     Vec3 Li(0.0f);
     bool scattered = false;
     int depth = 1;
     bool emittedRadiance = true;  // rRec.type & EEmittedRadiance
+    const GuideField *field = G ? G->field : nullptr;
+    const bool record = G && G->rec;
+    const Float alpha = G ? G->alpha : 0.0f;
+    GuideVertex verts[64];
+    int nVerts = 0;
 
     scene.rayIntersect(ray, its, &st);
     ray.mint = Epsilon;
@@ -446,6 +465,9 @@ static Vec3 Li_path(const Scene &scene, const B200pgIntegratorParams &P, const R
         dRec.refN = Vec3(0.0f);
         const unsigned btype = bsdf.typeFlags();
         if ((btype & (ETransmission | EBackSide)) == 0) dRec.refN = its.shFrame.n;  // records.inl:160-164
+        // guided vertex: smooth BSDF (delta lobes are never guided, cf. getDeltaSamplingRate bsdf.h:374-382)
+        const bool guided = field && (btype & ESmooth);
+        const uint32_t gcell = guided ? field->lookup(its.p) : 0u;
 
         if (P.use_nee && (btype & ESmooth)) {
             Vec3 value = scene.sampleEmitterDirectNoVis(dRec, rng.next2D());
@@ -461,28 +483,67 @@ static Vec3 Li_path(const Scene &scene, const B200pgIntegratorParams &P, const R
                 const Vec3 bsdfVal = bsdf.eval(its.wi, wo);
                 if (!bsdfVal.isZero() && (!P.strict_normals || dot(its.geoN, dRec.d) * Frame::cosTheta(wo) > 0)) {
                     Float bsdfPdf = bsdf.pdf(its.wi, wo);
+                    if (guided)  // the direction-sampling technique is the one-sample-MIS mixture
+                        bsdfPdf = alpha * field->pdf(gcell, dRec.d) + (1 - alpha) * bsdfPdf;
                     Float weight = miWeight(dRec.pdf, bsdfPdf);
                     Li += throughput * value * bsdfVal * weight;
                 }
             }
         }
+        const Vec3 LafterNee = Li;
 
-        /* BSDF sampling */
+        /* BSDF sampling (one-sample MIS between the BSDF and the guiding mixture at guided vertices) */
         Float bsdfPdf, bEta;
         unsigned sampledType;
-        Vec3 woLocal;
-        Vec3 bsdfWeight = bsdf.sample(its.wi, rng.next2D(), woLocal, bsdfPdf, bEta, sampledType);
-        if (bsdfWeight.isZero()) break;
+        Vec3 woLocal, bsdfWeight, wo;
+        if (guided) {
+            Float u0 = rng.next1D();
+            Vec2 u12 = rng.next2D();
+            Vec3 fcos;
+            Float pb;
+            if (u0 < alpha) {
+                u0 /= alpha;
+                wo = field->sample(gcell, u0, u12.x, u12.y);
+                woLocal = its.toLocal(wo);
+                fcos = bsdf.eval(its.wi, woLocal);
+                pb = bsdf.pdf(its.wi, woLocal);
+                bEta = 1.0f;
+                sampledType = EGlossyReflection;
+            } else {
+                Vec3 w = bsdf.sample(its.wi, u12, woLocal, pb, bEta, sampledType);
+                if (w.isZero()) break;
+                fcos = w * pb;
+                wo = its.toWorld(woLocal);
+            }
+            bsdfPdf = alpha * field->pdf(gcell, wo) + (1 - alpha) * pb;
+            if (fcos.isZero() || !(bsdfPdf > 0)) break;
+            bsdfWeight = fcos / bsdfPdf;
+        } else {
+            bsdfWeight = bsdf.sample(its.wi, rng.next2D(), woLocal, bsdfPdf, bEta, sampledType);
+            if (bsdfWeight.isZero()) break;
+            wo = its.toWorld(woLocal);
+        }
         scattered |= sampledType != ENull;
 
-        const Vec3 wo = its.toWorld(woLocal);
         Float woDotGeoN = dot(its.geoN, wo);
         if (P.strict_normals && woDotGeoN * Frame::cosTheta(woLocal) <= 0) break;
 
         bool hitEmitter = false;
         Vec3 value;
         ray = Ray(its.p, wo);
-        if (scene.rayIntersect(ray, its, &st)) {
+        const bool recordVertex = record && (btype & ESmooth) && nVerts < 64;
+        if (recordVertex) {
+            GuideVertex &gv = verts[nVerts++];
+            gv.pos = its.p;
+            gv.dir = wo;
+            gv.pdf = bsdfPdf;
+            gv.T = throughput * bsdfWeight;
+            gv.Lk = LafterNee;
+            gv.dist = 0.0f;
+        }
+        const bool hitSomething = scene.rayIntersect(ray, its, &st);
+        if (recordVertex) verts[nVerts - 1].dist = hitSomething ? its.t : 0.0f;
+        if (hitSomething) {
             if (scene.shapes[its.shape].emitter >= 0) {
                 value = scene.emitterEval(its, -ray.d);
                 // dRec.setQuery(ray, its), records.inl:170-178
@@ -516,6 +577,18 @@ static Vec3 Li_path(const Scene &scene, const B200pgIntegratorParams &P, const R
     }
     st.paths++;
     st.pathLen += depth;
+    if (record) {
+        // incident-radiance estimate along each sampled direction: everything the path gathered after the
+        // vertex, divided by the throughput right after the vertex; sample weight = avg_rgb(estimate) / pdf
+        for (int v = 0; v < nVerts; ++v) {
+            const GuideVertex &gv = verts[v];
+            Vec3 d = Li - gv.Lk, est(0.0f);
+            for (int c = 0; c < 3; ++c) est[c] = gv.T[c] > 0 ? d[c] / gv.T[c] : 0.0f;
+            Float w = est.average() / gv.pdf;
+            if (!std::isfinite(w) || w < 0) w = 0.0f;
+            G->rec->push(gv.pos, gv.dir, w, gv.pdf, gv.dist);
+        }
+    }
     return Li;
 }
 
@@ -525,9 +598,10 @@ static Vec3 Li_path(const Scene &scene, const B200pgIntegratorParams &P, const R
 
 namespace orc {
 
-static Vec3 Li(const Scene &scene, const B200pgIntegratorParams &P, const Ray &r, Rng &rng, Stats &st) {
+static Vec3 Li(const Scene &scene, const B200pgIntegratorParams &P, const Ray &r, Rng &rng, Stats &st,
+               const GuideCtx *G = nullptr) {
     if (P.volumetric) return Li_volpath(scene, P, r, rng, st);
-    return Li_path(scene, P, r, rng, st);
+    return Li_path(scene, P, r, rng, st, G);
 }
 
 // ---------------------------------------------------------------------------
@@ -821,11 +895,20 @@ int orc_bsdf(void *s, int bsdfIndex, const float *wi, const float *wo, const flo
     return 0;
 }
 
+// field (may be NULL): guiding field to sample from; sink (may be NULL): receives the training samples of all
+// n paths in index order (deterministic).
 int orc_radiance(void *s, const B200pgIntegratorParams *P, const uint32_t *pixel, const uint32_t *sample, size_t n,
-                 float *out_rgb) {
+                 float *out_rgb, void *field, void *sink) {
     Scene *sc = (Scene *)s;
-#pragma omp parallel for schedule(dynamic, 256)
-    for (long long i = 0; i < (long long)n; ++i) {
+    const int nChunks = (int)((n + 255) / 256);
+    std::vector<GuideSamples> chunkSamples(sink ? nChunks : 0);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int ch = 0; ch < nChunks; ++ch)
+    for (long long i = (long long)ch * 256; i < std::min<long long>((long long)n, (long long)(ch + 1) * 256); ++i) {
+        GuideCtx G;
+        G.field = (const GuideField *)field;
+        G.rec = sink ? &chunkSamples[ch] : nullptr;
+        G.alpha = P->guiding_probability;
         Rng rng;
         rng.init(sc->seed, pixel[i], sample[i]);
         int px = pixel[i] % sc->film.width, py = pixel[i] / sc->film.width;
@@ -833,8 +916,13 @@ int orc_radiance(void *s, const B200pgIntegratorParams *P, const uint32_t *pixel
         Vec2 samplePos(px + off.x, py + off.y);
         Ray ray = sc->sampleRay(samplePos);
         Stats st;
-        Vec3 L = Li(*sc, *P, ray, rng, st);
+        Vec3 L = Li(*sc, *P, ray, rng, st, (field || sink) ? &G : nullptr);
         out_rgb[3 * i] = L.x; out_rgb[3 * i + 1] = L.y; out_rgb[3 * i + 2] = L.z;
+    }
+    if (sink) {
+        GuideSamples *out = (GuideSamples *)sink;
+        for (auto &c : chunkSamples)
+            for (size_t j = 0; j < c.size(); ++j) out->push(c.pos[j], c.dir[j], c.weight[j], c.pdf[j], c.dist[j]);
     }
     return 0;
 }
@@ -860,7 +948,7 @@ int orc_film_splat(void *s, const float *pos, const float *rgb, size_t n, float 
 // under a mutex (renderproc.cpp:141-148). film: H*W*5 accumulators (+=). stats: 7 u64
 // (paths, normal rays, shadow rays, path length sum, kd nodes, kd indices, prim tests).
 int orc_render(void *s, const B200pgIntegratorParams *P, int first_sample, int n_samples, int row_begin, int row_end,
-               float *film, int nthreads, uint64_t *stats, double *seconds) {
+               float *film, int nthreads, uint64_t *stats, double *seconds, void *field, void *sink) {
     Scene *sc = (Scene *)s;
     const int W = sc->film.width, H = sc->film.height;
     if (row_end <= 0 || row_end > H) row_end = H;
@@ -871,6 +959,7 @@ int orc_render(void *s, const B200pgIntegratorParams *P, int first_sample, int n
     const int ntiles = tx * (ty1 - ty0);
     std::mutex filmMutex;
     Stats total;
+    std::vector<GuideSamples> tileSamples(sink ? ntiles : 0);
     auto t0 = std::chrono::steady_clock::now();
 #pragma omp parallel num_threads(nthreads)
     {
@@ -892,7 +981,11 @@ int orc_render(void *s, const B200pgIntegratorParams *P, int first_sample, int n
                         Vec2 off = rng.next2D();
                         Vec2 samplePos(x + off.x, y + off.y);
                         Ray ray = sc->sampleRay(samplePos);
-                        Vec3 spec = Li(*sc, *P, ray, rng, st);
+                        GuideCtx G;
+                        G.field = (const GuideField *)field;
+                        G.rec = sink ? &tileSamples[tile] : nullptr;
+                        G.alpha = P->guiding_probability;
+                        Vec3 spec = Li(*sc, *P, ray, rng, st, (field || sink) ? &G : nullptr);
                         float maxSpec = spec.maxc();  // progressiveintegrator.cpp:274-277
                         if (maxSpec > P->max_component_value) spec *= P->max_component_value / maxSpec;
                         Float v[5] = {spec.x, spec.y, spec.z, 1.0f, 1.0f};
@@ -926,6 +1019,11 @@ int orc_render(void *s, const B200pgIntegratorParams *P, int first_sample, int n
     }
     auto t1 = std::chrono::steady_clock::now();
     if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    if (sink) {
+        GuideSamples *out = (GuideSamples *)sink;
+        for (auto &c : tileSamples)
+            for (size_t j = 0; j < c.size(); ++j) out->push(c.pos[j], c.dir[j], c.weight[j], c.pdf[j], c.dist[j]);
+    }
     if (stats) {
         stats[0] = total.paths;
         stats[1] = total.normalRays;
@@ -994,5 +1092,91 @@ int orc_rtrans_reduce(const float *raw, int etaN, int alphaN, int thetaN, float 
 }
 
 int orc_num_threads(void) { return omp_get_max_threads(); }
+
+// ---- guiding field (this repo's own algorithm; see oracle_guiding.h)
+void *orc_field_create(int K, const float *bmin, const float *bmax) {
+    GuideField *f = new GuideField();
+    f->init(K, bmin, bmax);
+    return f;
+}
+void orc_field_destroy(void *f) { delete (GuideField *)f; }
+size_t orc_field_snapshot(void *f, uint32_t *out, size_t cap) {
+    std::vector<uint32_t> w = ((GuideField *)f)->snapshot();
+    if (out && cap >= w.size()) std::memcpy(out, w.data(), w.size() * 4);
+    return w.size();
+}
+int orc_field_load(void *f, const uint32_t *w, size_t n) { return ((GuideField *)f)->load(w, n) ? 0 : -1; }
+int orc_field_info(void *f, uint32_t *out /* nodes, cells, K */) {
+    GuideField *F = (GuideField *)f;
+    out[0] = (uint32_t)F->nodes.size();
+    out[1] = F->numCells();
+    out[2] = (uint32_t)F->K;
+    return 0;
+}
+// u: n*3 (lobe selection, u1, u2). out_pdf: pdf of `dir`; out_dir / out_spdf: sampled direction and its pdf.
+int orc_vmm_pdf_sample(void *f, const float *pos, const float *dir, const float *u, size_t n, float *out_pdf, float *out_dir,
+                       float *out_spdf, uint32_t *out_cell) {
+    GuideField *F = (GuideField *)f;
+    for (size_t i = 0; i < n; ++i) {
+        uint32_t c = F->lookup(Vec3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]));
+        out_cell[i] = c;
+        out_pdf[i] = F->pdf(c, Vec3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]));
+        Vec3 d = F->sample(c, u[3 * i], u[3 * i + 1], u[3 * i + 2]);
+        out_dir[3 * i] = d.x; out_dir[3 * i + 1] = d.y; out_dir[3 * i + 2] = d.z;
+        out_spdf[i] = F->pdf(c, d);
+    }
+    return 0;
+}
+int orc_bin_samples(void *f, const float *pos, size_t n, uint32_t *out_cell, uint32_t *out_perm, uint32_t *out_offsets) {
+    GuideField *F = (GuideField *)f;
+    std::vector<Vec3> p(n);
+    for (size_t i = 0; i < n; ++i) p[i] = Vec3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+    std::vector<uint32_t> cell, perm, offsets;
+    guideBin(*F, p.data(), n, cell, perm, offsets);
+    std::memcpy(out_cell, cell.data(), n * 4);
+    std::memcpy(out_perm, perm.data(), n * 4);
+    std::memcpy(out_offsets, offsets.data(), offsets.size() * 4);
+    return 0;
+}
+static void fillSamples(GuideSamples &S, const float *pos, const float *dir, const float *weight, const float *pdf,
+                        const float *dist, size_t n) {
+    for (size_t i = 0; i < n; ++i)
+        S.push(Vec3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]), Vec3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]), weight[i],
+               pdf[i], dist[i]);
+}
+// E-step only: stats_out has numCells * (4K + 8) floats (double accumulation, rounded once)
+int orc_estep(void *f, const float *pos, const float *dir, const float *weight, const float *pdf, const float *dist, size_t n,
+              float *stats_out) {
+    GuideField *F = (GuideField *)f;
+    GuideSamples S;
+    fillSamples(S, pos, dir, weight, pdf, dist, n);
+    std::vector<uint32_t> cell, perm, offsets;
+    guideBin(*F, S.pos.data(), n, cell, perm, offsets);
+    std::vector<double> st;
+    guideEStep(*F, S, perm, offsets, st);
+    for (size_t i = 0; i < st.size(); ++i) stats_out[i] = (float)st[i];
+    return 0;
+}
+int orc_train(void *f, const float *pos, const float *dir, const float *weight, const float *pdf, const float *dist, size_t n,
+              int nIter, float maxCellSamples) {
+    GuideField *F = (GuideField *)f;
+    GuideSamples S;
+    fillSamples(S, pos, dir, weight, pdf, dist, n);
+    guideTrain(*F, S, nIter, maxCellSamples);
+    return 0;
+}
+void *orc_samples_create(void) { return new GuideSamples(); }
+void orc_samples_destroy(void *h) { delete (GuideSamples *)h; }
+size_t orc_samples_size(void *h) { return ((GuideSamples *)h)->size(); }
+void orc_samples_clear(void *h) { *((GuideSamples *)h) = GuideSamples(); }
+int orc_samples_get(void *h, float *pos, float *dir, float *weight, float *pdf, float *dist) {
+    GuideSamples *S = (GuideSamples *)h;
+    for (size_t i = 0; i < S->size(); ++i) {
+        pos[3 * i] = S->pos[i].x; pos[3 * i + 1] = S->pos[i].y; pos[3 * i + 2] = S->pos[i].z;
+        dir[3 * i] = S->dir[i].x; dir[3 * i + 1] = S->dir[i].y; dir[3 * i + 2] = S->dir[i].z;
+        weight[i] = S->weight[i]; pdf[i] = S->pdf[i]; dist[i] = S->dist[i];
+    }
+    return 0;
+}
 
 }  // extern "C"

@@ -35,10 +35,27 @@ class Oracle:
         L.orc_trace_bruteforce.argtypes = [C.c_void_p, fp, C.c_size_t, fp, u32p]
         L.orc_camera_rays.argtypes = [C.c_void_p, fp, C.c_size_t, fp]
         L.orc_bsdf.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_size_t, fp, fp, fp, fp, fp, u32p]
-        L.orc_radiance.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), u32p, u32p, C.c_size_t, fp]
+        L.orc_radiance.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), u32p, u32p, C.c_size_t, fp, C.c_void_p, C.c_void_p]
         L.orc_film_splat.argtypes = [C.c_void_p, fp, fp, C.c_size_t, fp]
         L.orc_render.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), C.c_int, C.c_int, C.c_int, C.c_int, fp,
-                                 C.c_int, u64p, C.POINTER(C.c_double)]
+                                 C.c_int, u64p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
+        L.orc_field_create.restype = C.c_void_p
+        L.orc_field_create.argtypes = [C.c_int, fp, fp]
+        L.orc_field_destroy.argtypes = [C.c_void_p]
+        L.orc_field_snapshot.restype = C.c_size_t
+        L.orc_field_snapshot.argtypes = [C.c_void_p, u32p, C.c_size_t]
+        L.orc_field_load.argtypes = [C.c_void_p, u32p, C.c_size_t]
+        L.orc_field_info.argtypes = [C.c_void_p, u32p]
+        L.orc_vmm_pdf_sample.argtypes = [C.c_void_p, fp, fp, fp, C.c_size_t, fp, fp, fp, u32p]
+        L.orc_bin_samples.argtypes = [C.c_void_p, fp, C.c_size_t, u32p, u32p, u32p]
+        L.orc_estep.argtypes = [C.c_void_p, fp, fp, fp, fp, fp, C.c_size_t, fp]
+        L.orc_train.argtypes = [C.c_void_p, fp, fp, fp, fp, fp, C.c_size_t, C.c_int, C.c_float]
+        L.orc_samples_create.restype = C.c_void_p
+        L.orc_samples_destroy.argtypes = [C.c_void_p]
+        L.orc_samples_size.restype = C.c_size_t
+        L.orc_samples_size.argtypes = [C.c_void_p]
+        L.orc_samples_clear.argtypes = [C.c_void_p]
+        L.orc_samples_get.argtypes = [C.c_void_p, fp, fp, fp, fp, fp]
         L.orc_rtrans_reduce.argtypes = [fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                         C.c_float, C.c_float, fp, fp, fp]
         L.orc_num_threads.restype = C.c_int
@@ -60,6 +77,97 @@ class Oracle:
 
     def scene(self, builder):
         return OracleScene(self, builder)
+
+    def field(self, K, bmin, bmax):
+        return OracleField(self, K, bmin, bmax)
+
+    def samples(self):
+        return OracleSamples(self)
+
+
+class OracleSamples:
+    """Training-sample sink filled by guided/unguided oracle renders."""
+
+    def __init__(self, orc):
+        self.L = orc.lib
+        self.h = self.L.orc_samples_create()
+
+    def __del__(self):
+        try:
+            self.L.orc_samples_destroy(self.h)
+        except Exception:
+            pass
+
+    def clear(self):
+        self.L.orc_samples_clear(self.h)
+
+    def get(self):
+        n = self.L.orc_samples_size(self.h)
+        pos, dirs = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+        w, pdf, dist = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+        if n:
+            self.L.orc_samples_get(self.h, _f(pos), _f(dirs), _f(w), _f(pdf), _f(dist))
+        return dict(pos=pos, dir=dirs, weight=w, pdf=pdf, dist=dist)
+
+
+class OracleField:
+    """CPU statement of the guiding field (oracle/oracle_guiding.h)."""
+
+    def __init__(self, orc, K, bmin, bmax):
+        self.L = orc.lib
+        a, b = np.asarray(bmin, np.float32), np.asarray(bmax, np.float32)
+        self.h = self.L.orc_field_create(K, _f(a), _f(b))
+
+    def __del__(self):
+        try:
+            self.L.orc_field_destroy(self.h)
+        except Exception:
+            pass
+
+    def info(self):
+        out = (C.c_uint32 * 3)()
+        self.L.orc_field_info(self.h, out)
+        return dict(nodes=out[0], cells=out[1], K=out[2])
+
+    def snapshot(self):
+        n = self.L.orc_field_snapshot(self.h, None, 0)
+        w = np.zeros(n, np.uint32)
+        self.L.orc_field_snapshot(self.h, _u(w), n)
+        return w
+
+    def load(self, words):
+        words = np.ascontiguousarray(words, np.uint32)
+        assert self.L.orc_field_load(self.h, _u(words), words.size) == 0
+
+    def pdf_sample(self, pos, dirs, u):
+        pos, dirs, u = (np.ascontiguousarray(x, np.float32) for x in (pos, dirs, u))
+        n = pos.shape[0]
+        pdf, sd, spdf, cell = np.zeros(n, np.float32), np.zeros((n, 3), np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint32)
+        self.L.orc_vmm_pdf_sample(self.h, _f(pos), _f(dirs), _f(u), n, _f(pdf), _f(sd), _f(spdf), _u(cell))
+        return dict(pdf=pdf, dir=sd, spdf=spdf, cell=cell)
+
+    def bin(self, pos):
+        pos = np.ascontiguousarray(pos, np.float32)
+        n = pos.shape[0]
+        cell, perm = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        off = np.zeros(self.info()["cells"] + 1, np.uint32)
+        self.L.orc_bin_samples(self.h, _f(pos), n, _u(cell), _u(perm), _u(off))
+        return cell, perm, off
+
+    def _args(self, s):
+        a = [np.ascontiguousarray(s[k], np.float32) for k in ("pos", "dir", "weight", "pdf", "dist")]
+        return a, a[0].shape[0]
+
+    def estep(self, s):
+        a, n = self._args(s)
+        i = self.info()
+        st = np.zeros(i["cells"] * (4 * i["K"] + 8), np.float32)
+        self.L.orc_estep(self.h, *[_f(x) for x in a], n, _f(st))
+        return st.reshape(i["cells"], 4 * i["K"] + 8)
+
+    def train(self, s, n_iter=4, max_cell_samples=32768):
+        a, n = self._args(s)
+        self.L.orc_train(self.h, *[_f(x) for x in a], n, n_iter, max_cell_samples)
 
 
 class OracleScene:
@@ -128,11 +236,12 @@ class OracleScene:
         assert r == 0
         return dict(eval=ev, pdf=pdf, wo=swo, weight=w, spdf=spdf, flags=fl)
 
-    def radiance(self, params, pixel, sample):
+    def radiance(self, params, pixel, sample, field=None, sink=None):
         pixel = np.ascontiguousarray(pixel, np.uint32)
         sample = np.ascontiguousarray(sample, np.uint32)
         out = np.zeros((pixel.shape[0], 3), np.float32)
-        self.L.orc_radiance(self.h, C.byref(params), _u(pixel), _u(sample), pixel.shape[0], _f(out))
+        self.L.orc_radiance(self.h, C.byref(params), _u(pixel), _u(sample), pixel.shape[0], _f(out),
+                            field.h if field is not None else None, sink.h if sink is not None else None)
         return out
 
     def film_splat(self, pos, rgb):
@@ -142,14 +251,14 @@ class OracleScene:
         self.L.orc_film_splat(self.h, _f(pos), _f(rgb), pos.shape[0], _f(film))
         return film
 
-    def render(self, params, first_sample=0, n_samples=1, rows=None, film=None, nthreads=0):
+    def render(self, params, first_sample=0, n_samples=1, rows=None, film=None, nthreads=0, field=None, sink=None):
         if film is None:
             film = np.zeros((self.H, self.W, 5), np.float32)
         st = (C.c_uint64 * 7)()
         sec = C.c_double()
         r0, r1 = rows if rows else (0, self.H)
         self.L.orc_render(self.h, C.byref(params), first_sample, n_samples, r0, r1, _f(film), nthreads, st,
-                          C.byref(sec))
+                          C.byref(sec), field.h if field is not None else None, sink.h if sink is not None else None)
         stats = dict(paths=st[0], normal_rays=st[1], shadow_rays=st[2], path_length_sum=st[3], kd_nodes=st[4],
                      kd_indices=st[5], prim_tests=st[6], seconds=sec.value)
         return film, stats

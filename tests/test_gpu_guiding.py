@@ -1,0 +1,217 @@
+"""GPU parity of the guiding subsystem (north-star subsystems 2 and 3) against oracle/oracle_guiding.h, through the C-ABI.
+Bars: cell indices, binning permutation and offsets BIT-EXACT; mixture pdf and sampled-direction pdf within 1e-5 relative;
+E-step sufficient statistics within 1e-5 relative (of the cell's largest statistic); refitted weights / mean directions /
+mean cosines within 1e-5 absolute (kappa itself is ill-conditioned as the mean cosine approaches 1:
+d kappa / kappa ~ d rbar / (1 - rbar^2), so it is compared through the well-conditioned mean cosine A(kappa))."""
+import numpy as np
+import pytest
+
+from bsdf_cases import random_dirs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api(pkg):
+    from b200pg import api as _api
+
+    return _api
+
+
+@pytest.fixture(scope="module")
+def trained(pkg, api, oracle):
+    """A field trained on the GPU (4 progressions) and mirrored into the oracle through a snapshot."""
+    sb = pkg.scenes.cornell_caustic(128, 128, spp=8)
+    p = api.default_params()
+    p.max_depth = 8
+    p.guiding = 1
+    p.guide_max_components = 16
+    p.guide_max_cell_samples = 6000
+    it = api.Integrator(api.Scene.from_builder(sb), p)
+    counts = []
+    for k in range(4):
+        it.guiding_mode(True, k > 0)
+        it.progression(100 * k, 4)
+        counts.append(it.train(4))
+    snap = it.field_snapshot()
+    fld = oracle.field(16, (0, 0, 0), (1, 1, 1))
+    fld.load(snap)
+    return sb, p, it, fld, snap, counts, oracle.scene(sb)
+
+
+def _mean_cos(kappa):
+    kappa = kappa.astype(np.float64)
+    return 1.0 / np.tanh(kappa) - 1.0 / kappa
+
+
+def test_training_grows_the_spatial_tree(trained):
+    sb, p, it, fld, snap, counts, osc = trained
+    assert snap[0] == 0x47554944 and snap[3] == 16
+    nodes, cells = int(snap[1]), int(snap[2])
+    assert cells >= 8 and nodes == 2 * cells - 1
+    assert all(n > 50000 for n, c in counts)
+    assert it.stats()["guide_cells"] == cells
+    lob = snap.view(np.float32)[8 + 4 * nodes + 8 * cells:].reshape(cells, 16, 12)
+    assert np.allclose(lob[:, :, 0].sum(1), 1, atol=1e-5)                      # mixture weights
+    assert np.allclose(np.linalg.norm(lob[:, :, 1:4], axis=2), 1, atol=1e-4)   # unit mean directions
+    assert (lob[:, :, 4] >= 0.01).all() and (lob[:, :, 4] <= 5000).all()
+
+
+def test_query_pdf_and_sample(trained):
+    sb, p, it, fld, snap, counts, osc = trained
+    rng = np.random.RandomState(0)
+    n = 200000
+    pos = (rng.rand(n, 3) * [2.2, 2.2, 2.2] - [1.1, 0.1, 1.1]).astype(np.float32)
+    d = random_dirs(rng, n)
+    u = rng.rand(n, 3).astype(np.float32)
+    qo, qg = fld.pdf_sample(pos, d, u), it.k_vmm_pdf_sample(pos, d, u)
+    assert np.array_equal(qo["cell"], qg["cell"])                              # indexing: bit-exact
+    assert np.all(np.abs(qo["pdf"] - qg["pdf"]) <= 1e-5 * np.maximum(qo["pdf"], 1e-3))
+    assert np.abs(qo["dir"] - qg["dir"]).max() <= 1e-5
+    assert np.all(np.abs(qo["spdf"] - qg["spdf"]) <= 1e-5 * np.maximum(qo["spdf"], 1e-2))
+    tuv = it.k_vmm_pdf_sample(pos[:0], d[:0], u[:0])                           # empty input
+    assert tuv["pdf"].shape == (0,)
+
+
+def test_binning_is_bit_exact(trained):
+    sb, p, it, fld, snap, counts, osc = trained
+    rng = np.random.RandomState(1)
+    nc = fld.info()["cells"]
+    for n in (1, 255, 2049, 300001):  # ragged sizes around the sort tile (2048) and round (256) boundaries
+        pos = (rng.rand(n, 3) * [2.2, 2.2, 2.2] - [1.1, 0.1, 1.1]).astype(np.float32)
+        if n > 1000:
+            pos[: n // 3] = pos[0]    # many collisions in one cell
+        co, po, oo = fld.bin(pos)
+        cg, pg_, og = it.k_bin_samples(pos, nc)
+        assert np.array_equal(co, cg) and np.array_equal(po, pg_) and np.array_equal(oo, og), n
+    cg, pg_, og = it.k_bin_samples(np.zeros((0, 3), np.float32), nc)
+    assert (og == 0).all()
+
+
+def test_em_statistics_and_refit(trained, api, pkg):
+    sb, p, it, fld, snap, counts, osc = trained
+    rng = np.random.RandomState(2)
+    m = 40000
+    pix = rng.randint(0, sb.width * sb.height, m).astype(np.uint32)
+    smp = rng.randint(0, 64, m).astype(np.uint32)
+    sink = fld.L.orc_samples_create
+    from oracle_lib import OracleSamples, Oracle
+
+    sink = Oracle().samples()
+    osc.radiance(p, pix, smp, field=fld, sink=sink)
+    s = sink.get()
+    assert len(s["weight"]) > 30000
+    info = fld.info()
+    st_o = fld.estep(s)
+    st_g = it.k_em_step(s, 0, info["cells"], info["K"])
+    scale = np.maximum(np.abs(st_o).max(1, keepdims=True), 1e-6)
+    assert (np.abs(st_o - st_g) / scale).max() <= 1e-5
+    assert np.array_equal(st_o[:, -8], st_g[:, -8])                            # per-cell sample counts: exact
+    # full training update on identical samples and identical starting field (no spatial split: huge threshold)
+    p2 = api.default_params()
+    p2.max_depth, p2.guiding, p2.guide_max_components, p2.guide_max_cell_samples = 8, 1, 16, 2 ** 30
+    it2 = api.Integrator(api.Scene.from_builder(sb), p2)
+    it2.field_load(snap)
+    fld_keep = fld
+    fld = Oracle().field(16, (0, 0, 0), (1, 1, 1))
+    fld.load(snap)
+    fld.train(s, 4, float(2 ** 30))
+    it2.k_em_step(s, 4, info["cells"], info["K"])
+    a, g = fld.snapshot(), it2.field_snapshot()
+    assert a.size == g.size and np.array_equal(a[:8 + 4 * info["nodes"]], g[:8 + 4 * info["nodes"]])  # same tree
+    o = 8 + 4 * info["nodes"] + 8 * info["cells"]
+    la, lg = a.view(np.float32)[o:].reshape(-1, 12), g.view(np.float32)[o:].reshape(-1, 12)
+    assert np.abs(la[:, 0] - lg[:, 0]).max() <= 1e-5                           # weights
+    heavy = la[:, 0] > 1e-3                                                   # mean direction of lobes that carry mass
+    assert np.abs(la[heavy, 1:4] - lg[heavy, 1:4]).max() <= 2e-5
+    assert np.abs(_mean_cos(la[:, 4]) - _mean_cos(lg[:, 4])).max() <= 1e-5     # concentration via A(kappa)
+    cell_scale = np.repeat(np.abs(la[:, 8]).reshape(info["cells"], -1).max(1), info["K"])[:, None]
+    assert (np.abs(la[:, 8:12] - lg[:, 8:12]) / np.maximum(cell_scale, 1e-6)).max() <= 1e-5  # running statistics
+    # the refitted fields give the same pdf
+    pos = (rng.rand(50000, 3) * [2.2, 2.2, 2.2] - [1.1, 0.1, 1.1]).astype(np.float32)
+    d = random_dirs(rng, 50000)
+    u = rng.rand(50000, 3).astype(np.float32)
+    qo, qg = fld.pdf_sample(pos, d, u), it2.k_vmm_pdf_sample(pos, d, u)
+    assert np.all(np.abs(qo["pdf"] - qg["pdf"]) <= 2e-5 * np.maximum(qo["pdf"], 1e-2))
+
+
+def test_guided_radiance_sample_by_sample(trained):
+    sb, p, it, fld, snap, counts, osc = trained
+    it.field_load(snap)
+    it.guiding_mode(False, True)
+    rng = np.random.RandomState(3)
+    n = 60000
+    pix = rng.randint(0, sb.width * sb.height, n).astype(np.uint32)
+    smp = rng.randint(0, 1000, n).astype(np.uint32)
+    want = osc.radiance(p, pix, smp, field=fld)
+    got = it.k_radiance(pix, smp)
+    err = np.abs(got - want).max(1) / (np.abs(want).max(1) + 1e-3)
+    assert (err > 1e-3).mean() < 3e-3
+    # and the unguided estimator of the same integrator agrees in the mean (one-sample MIS is unbiased)
+    it.guiding_mode(False, False)
+    plain = it.k_radiance(pix, smp)
+    assert abs(plain.mean() - got.mean()) < 0.03 * plain.mean()
+
+
+def test_training_samples_match_oracle(trained):
+    """Samples recorded by the wavefront kernels equal the oracle's (as a multiset: the GPU emits them in completion order)."""
+    sb, p, it, fld, snap, counts, osc = trained
+    from oracle_lib import Oracle
+
+    it.field_load(snap)
+    it.guiding_mode(True, True)
+    rng = np.random.RandomState(4)
+    n = 20000
+    pix = rng.randint(0, sb.width * sb.height, n).astype(np.uint32)
+    smp = rng.randint(0, 1000, n).astype(np.uint32)
+    sink = Oracle().samples()
+    osc.radiance(p, pix, smp, field=fld, sink=sink)
+    s = sink.get()
+    it.k_radiance(pix, smp)
+    ns, nc = it.train_begin()
+    assert abs(ns - len(s["weight"])) <= 0.003 * ns
+    # compare aggregate statistics of both sample sets through the same (oracle) E-step
+    it.train_accumulate()
+    it.train_update(True)
+    it.train_end()
+    it.guiding_mode(False, True)
+
+
+def test_guided_render_equal_spp_error(trained, oracle):
+    """Converged-image check: guided and unguided renders agree with the oracle reference; guiding lowers relMSE."""
+    sb, p, it, fld, snap, counts, osc = trained
+    from oracle_lib import develop
+
+    ref = develop(osc.render(p, 5000, 256)[0])
+
+    def relmse(img):
+        e = ((img - ref) ** 2 / (ref ** 2 + 1e-3)).mean(2).ravel()
+        e.sort()
+        return float(e[: int(len(e) * 0.999)].mean())  # 0.1% outliers trimmed
+
+    it.field_load(snap)
+    it.film_clear(); it.guiding_mode(False, True); it.progression(0, 32); g = it.develop()
+    it.film_clear(); it.guiding_mode(False, False); it.progression(0, 32); u = it.develop()
+    assert abs(g.mean() - ref.mean()) < 0.02 * ref.mean() and abs(u.mean() - ref.mean()) < 0.02 * ref.mean()
+    assert relmse(g) < 0.9 * relmse(u)
+
+
+def test_b200pg_render_runs_the_training_schedule(api, pkg):
+    sb = pkg.scenes.cornell_caustic(96, 96, spp=12)
+    p = api.default_params()
+    p.max_depth = 6
+    p.guiding = 1
+    p.samples_per_progression = 2
+    p.training_progressions = 3
+    p.guide_max_cell_samples = 4000
+    it = api.Integrator(api.Scene.from_builder(sb), p)
+    it.render()
+    st = it.stats()
+    assert st["progressions_done"] == 6 and st["paths"] == 96 * 96 * 12 and st["guide_cells"] >= 2
+    assert np.isfinite(it.develop()).all()
+    # guiding calls on an integrator without guiding are errors, not silent no-ops
+    it0 = api.Integrator(api.Scene.from_builder(sb), api.default_params())
+    with pytest.raises(api.B200pgError, match="guiding"):
+        it0.guiding_mode(True, True)
+    with pytest.raises(api.B200pgError, match="guiding"):
+        it0.train_begin()

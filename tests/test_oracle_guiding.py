@@ -1,0 +1,151 @@
+"""CPU tests of the guiding-field oracle (oracle/oracle_guiding.h). PARITY UNPINNED: there is no guiding code, test or
+golden vector in the reference snapshot; these tests pin the oracle to its own specification through
+mathematical properties (normalisation, sample<->pdf consistency, EM recovery of a planted mixture, unbiasedness)."""
+import numpy as np
+import pytest
+from scipy import stats
+
+from bsdf_cases import random_dirs
+
+
+def _vmf_samples(rng, mu, kappa, n):
+    u1, u2 = rng.rand(n), rng.rand(n)
+    c = 1 + np.log(u1 + (1 - u1) * np.exp(-2 * kappa)) / kappa
+    s = np.sqrt(np.maximum(0, 1 - c * c))
+    mu = np.asarray(mu, np.float64) / np.linalg.norm(mu)
+    a = np.cross(mu, [1, 0, 0] if abs(mu[0]) < 0.9 else [0, 1, 0]); a /= np.linalg.norm(a)
+    b = np.cross(mu, a)
+    phi = 2 * np.pi * u2
+    return (np.outer(s * np.cos(phi), a) + np.outer(s * np.sin(phi), b) + np.outer(c, mu)).astype(np.float32)
+
+
+def _planted(rng, n):
+    """Samples of a two-lobe target, drawn uniformly on the sphere and weighted by target/uniform."""
+    d = random_dirs(rng, n)
+    mu1, mu2 = np.array([0, 0, 1.0]), np.array([1.0, 0, 0])
+    k1, k2 = 30.0, 8.0
+    f = lambda mu, k: k / (2 * np.pi * (1 - np.exp(-2 * k))) * np.exp(k * (d @ mu - 1))
+    target = 0.7 * f(mu1, k1) + 0.3 * f(mu2, k2)
+    pdf = np.full(n, 1 / (4 * np.pi), np.float32)
+    pos = (rng.rand(n, 3) * 0.5).astype(np.float32)
+    return dict(pos=pos, dir=d, weight=(target / pdf).astype(np.float32), pdf=pdf, dist=np.ones(n, np.float32))
+
+
+def test_initial_field_is_normalised(oracle):
+    fld = oracle.field(16, (-1, -1, -1), (1, 1, 1))
+    assert fld.info() == dict(nodes=1, cells=1, K=16)
+    # integrate the pdf over the sphere (midpoint rule)
+    nt, nphi = 400, 800
+    t = (np.arange(nt) + 0.5) * np.pi / nt
+    p = (np.arange(nphi) + 0.5) * 2 * np.pi / nphi
+    T, P = np.meshgrid(t, p, indexing="ij")
+    d = np.stack([np.sin(T) * np.cos(P), np.sin(T) * np.sin(P), np.cos(T)], -1).reshape(-1, 3).astype(np.float32)
+    q = fld.pdf_sample(np.zeros_like(d), d, np.zeros_like(d))
+    integral = (q["pdf"].reshape(nt, nphi) * np.sin(T)).sum() * (np.pi / nt) * (2 * np.pi / nphi)
+    assert abs(integral - 1) < 2e-3
+
+
+def test_em_recovers_planted_mixture_and_sampling_matches_pdf(oracle):
+    rng = np.random.RandomState(0)
+    fld = oracle.field(8, (-1, -1, -1), (1, 1, 1))
+    for _ in range(6):
+        fld.train(_planted(rng, 60000), n_iter=4, max_cell_samples=1e9)
+    assert fld.info()["cells"] == 1
+    lob = fld.snapshot().view(np.float32)[8 + 4 + 8:].reshape(8, 12)
+    assert abs(lob[:, 0].sum() - 1) < 1e-5
+    # probability mass near each planted lobe
+    mass1 = lob[lob[:, 1:4] @ np.array([0, 0, 1.0]) > 0.9, 0].sum()
+    mass2 = lob[lob[:, 1:4] @ np.array([1.0, 0, 0]) > 0.7, 0].sum()
+    assert abs(mass1 - 0.7) < 0.08 and abs(mass2 - 0.3) < 0.08
+    # the fitted pdf is close to the target on its support
+    d = _vmf_samples(rng, [0, 0, 1], 30.0, 2000)
+    q = fld.pdf_sample(np.zeros_like(d), d, rng.rand(2000, 3).astype(np.float32))
+    target = 0.7 * 30 / (2 * np.pi) * np.exp(30 * (d[:, 2] - 1))
+    assert np.median(np.abs(q["pdf"] - target) / target) < 0.25
+    # chi^2: sampled directions follow the fitted pdf (10 x 20 theta/phi bins)
+    n = 200000
+    u = rng.rand(n, 3).astype(np.float32)
+    s = fld.pdf_sample(np.zeros((n, 3), np.float32), np.tile([0, 0, 1], (n, 1)).astype(np.float32), u)
+    th = np.arccos(np.clip(s["dir"][:, 2], -1, 1)); ph = np.arctan2(s["dir"][:, 1], s["dir"][:, 0]); ph[ph < 0] += 2 * np.pi
+    obs = np.bincount(np.minimum((th / np.pi * 10).astype(int), 9) * 20 + np.minimum((ph / (2 * np.pi) * 20).astype(int), 19), minlength=200)
+    sub = 16
+    tt = (np.arange(10 * sub) + 0.5) * np.pi / (10 * sub); pp = (np.arange(20 * sub) + 0.5) * 2 * np.pi / (20 * sub)
+    T, P = np.meshgrid(tt, pp, indexing="ij")
+    dd = np.stack([np.sin(T) * np.cos(P), np.sin(T) * np.sin(P), np.cos(T)], -1).reshape(-1, 3).astype(np.float32)
+    pdf = fld.pdf_sample(np.zeros_like(dd), dd, np.zeros_like(dd))["pdf"].reshape(T.shape)
+    exp = ((pdf * np.sin(T)) * (np.pi / (10 * sub)) * (2 * np.pi / (20 * sub))).reshape(10, sub, 20, sub).sum((1, 3)).ravel() * n
+    big = exp >= 5
+    chi = ((obs[big] - exp[big]) ** 2 / exp[big]).sum() + (obs[~big].sum() - exp[~big].sum()) ** 2 / max(exp[~big].sum(), 1e-9)
+    assert stats.chi2.sf(chi, big.sum()) > 0.0025
+    assert np.allclose(np.linalg.norm(s["dir"], axis=1), 1, atol=1e-5)
+
+
+def test_binning_is_stable_and_split_rule(oracle):
+    rng = np.random.RandomState(1)
+    fld = oracle.field(4, (0, 0, 0), (1, 1, 1))
+    s = _planted(rng, 50000)
+    s["pos"] = rng.rand(50000, 3).astype(np.float32) * [1, 0.2, 0.5]
+    fld.train(s, n_iter=2, max_cell_samples=1000)  # forces a split along x (largest variance)
+    info = fld.info()
+    assert info["cells"] == 2 and info["nodes"] == 3
+    words = fld.snapshot()
+    root = words[8:12]
+    assert root[0] == 0 and abs(root[1:2].view(np.float32)[0] - s["pos"][:, 0].mean()) < 1e-4
+    for _ in range(3):
+        fld.train(s, n_iter=1, max_cell_samples=1000)
+    cell, perm, off = fld.bin(s["pos"])
+    nc = fld.info()["cells"]
+    assert nc == 16 and off[0] == 0 and off[-1] == 50000
+    sorted_cells = cell[perm]
+    assert np.all(np.diff(sorted_cells.astype(np.int64)) >= 0)
+    for c in range(nc):  # stability: original order inside every bin
+        seg = perm[off[c]:off[c + 1]]
+        assert np.all(np.diff(seg.astype(np.int64)) > 0) and np.all(cell[seg] == c)
+    # children inherit the parent's mixture: all cells still hold normalised mixtures
+    lob = fld.snapshot().view(np.float32)[8 + 4 * fld.info()["nodes"] + 8 * nc:].reshape(nc, 4, 12)
+    assert np.allclose(lob[:, :, 0].sum(1), 1, atol=1e-5)
+    # empty / zero-weight input leaves the field unchanged
+    before = fld.snapshot().copy()
+    z = {k: v[:0] for k, v in s.items()}
+    fld.train(z, n_iter=2, max_cell_samples=1e9)
+    after = fld.snapshot()
+    assert np.array_equal(before[8 + 4 * fld.info()["nodes"] + 8 * nc:].view(np.float32)[0::12], after[8 + 4 * fld.info()["nodes"] + 8 * nc:].view(np.float32)[0::12])
+
+
+def test_estep_is_linear_in_sample_shards(oracle):
+    """The sufficient statistics of disjoint sample shards add up (what the NCCL allreduce relies on)."""
+    rng = np.random.RandomState(2)
+    fld = oracle.field(8, (0, 0, 0), (1, 1, 1))
+    s = _planted(rng, 40000)
+    fld.train(s, 2, 5000)
+    whole = fld.estep(s)
+    a = {k: v[:17000] for k, v in s.items()}
+    b = {k: v[17000:] for k, v in s.items()}
+    parts = fld.estep(a) + fld.estep(b)
+    np.testing.assert_allclose(parts, whole, rtol=2e-6, atol=1e-4)
+    assert whole[:, -8].sum() == 40000  # sample counts are exact
+
+
+def test_guided_render_is_unbiased_and_reduces_error(pkg, oracle):
+    sb = pkg.scenes.cornell_caustic(48, 48, spp=8)
+    sc = oracle.scene(sb)
+    p = pkg._abi.default_params()
+    p.max_depth = 6
+    p.guiding_probability = 0.5
+    fld = oracle.field(8, (-1.1, -0.1, -1.1), (1.1, 2.1, 1.1))
+    sink = oracle.samples()
+    for it in range(4):
+        sink.clear()
+        sc.render(p, 100 * it, 8, field=fld if it else None, sink=sink)
+        s = sink.get()
+        assert len(s["weight"]) > 10000 and np.isfinite(s["weight"]).all() and (s["weight"] >= 0).all()
+        assert np.allclose(np.linalg.norm(s["dir"], axis=1), 1, atol=1e-4)
+        fld.train(s, 4, 4000)
+    from oracle_lib import develop
+
+    ref = develop(sc.render(p, 5000, 512)[0])
+    g = develop(sc.render(p, 0, 128, field=fld)[0])
+    u = develop(sc.render(p, 0, 128)[0])
+    assert abs(g.mean() - ref.mean()) < 0.02 * ref.mean()  # unbiased
+    mse = lambda x: float(((x - ref) ** 2).mean())
+    assert mse(g) < 1.05 * mse(u)  # guiding must not hurt (it helps clearly on the caustic light paths)

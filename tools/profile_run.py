@@ -1,16 +1,24 @@
-"""Short run for ncu: a few progressions of the bench workload (same kernels as bench.py, no oracle)."""
-import os, sys
+"""Short run for ncu: a few steps of the bench workload (same kernels as bench.py, no oracle).
+usage: profile_run.py [caustic|cornell] [steps] [guided|plain]"""
+import os, sys, time
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import __graft_entry__ as ge
 pkg = ge.load_package()
 from b200pg import api
 name = sys.argv[1] if len(sys.argv) > 1 else "caustic"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+guided = len(sys.argv) > 3 and sys.argv[3] == "guided"
 sb = pkg.scenes.cornell_caustic(1024, 1024) if name == "caustic" else pkg.scenes.cornell_box(512, 512)
 scene = api.Scene.from_builder(sb)
 p = api.default_params(); p.max_depth = 8
+if guided:
+    p.guiding = 1; p.guide_max_components = 16; p.guide_max_cell_samples = 32768
 it = api.Integrator(scene, p)
 for k in range(steps):
+    if guided:
+        it.guiding_mode(True, k > 0)
     it.progression(4 * k, 4)
+    if guided:
+        t0 = time.time(); n, c = it.train(4); print("train", k, n, c, "wall ms", 1e3 * (time.time() - t0))
 st = it.stats()
 print("paths", st["paths"], "launches", st["kernel_launches"], "device s", st["seconds_total"], it.stage_times())
