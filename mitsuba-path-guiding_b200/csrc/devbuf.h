@@ -28,8 +28,17 @@ struct DevBuf {
         p = nullptr;
         n = 0;
     }
+    // grows geometrically: buffers that creep up by a few elements per call (sample counts, work lists) must not
+    // pay a synchronising cudaFree + cudaMalloc every time
     void alloc(size_t count) {
         if (count <= n) return;
+        release();
+        const size_t want = std::max<size_t>(count + count / 2, 64);
+        CUDA_OK(cudaMalloc(&p, want * sizeof(T)));
+        n = want;
+    }
+    void allocExact(size_t count) {  // capacity == count (buffers whose .n is used as the logical size)
+        if (count == n) return;
         release();
         CUDA_OK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
         n = count;

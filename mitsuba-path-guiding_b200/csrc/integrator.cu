@@ -204,7 +204,7 @@ struct Integrator {
         S.seed = H.seed;
         dCounters.alloc(1);
         CUDA_OK(cudaMemsetAsync(dCounters.p, 0, sizeof(Counters), stream));
-        dFilm.alloc((size_t)H.film.width * H.film.height);
+        dFilm.allocExact((size_t)H.film.width * H.film.height);
         CUDA_OK(cudaMemsetAsync(dFilm.p, 0, dFilm.n * sizeof(float4), stream));
         if (params.use_nee && H.emitters.empty()) params.use_nee = 0;  // nothing to sample
         guide.init(this->params, H, stream);
