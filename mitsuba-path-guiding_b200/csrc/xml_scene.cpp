@@ -1,9 +1,1009 @@
-// xml_scene.cpp -- Mitsuba 0.6 XML subset reader (scenehandler.cpp semantics).
+// xml_scene.cpp -- Mitsuba 0.6 scene XML subset reader for the hot path.
+//
+// Follows the semantics of the reference's SAX handler (src/librender/scenehandler.cpp):
+//   * property tags (float/integer/boolean/string/rgb/spectrum/point/vector/transform) write into the PARENT object
+//     (:271-700); object tags carry `type` and optionally `id`; <ref id=... name=...> re-uses a named object (:744-760)
+//   * transform ops compose as `op * current` (:348-440); <rotate> is in degrees; <lookat> falls back to an arbitrary
+//     up vector (:391-396)
+//   * `$name` in attribute values is substituted from -D key=value and <default> (:208-221, 684-688)
+//   * <rgb value="r, g, b"> / single value broadcast (:461-505); <spectrum value="x"> = constant spectrum (:588-593)
+// Objects on the hot path only; anything else is an error with a message naming the plugin (no silent ignore).
+#include <zlib.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <sstream>
+
 #include "host_scene.h"
 
 namespace pg {
-bool loadSceneXml(const char *, const char *const *, HostScene &, std::string &err) {
-    err = "XML loader not built yet";
-    return false;
+namespace {
+
+struct XmlNode {
+    std::string tag;
+    std::map<std::string, std::string> attr;
+    std::vector<std::unique_ptr<XmlNode>> children;
+    bool has(const char *k) const { return attr.count(k) != 0; }
+    std::string get(const char *k, const std::string &def = "") const {
+        auto it = attr.find(k);
+        return it == attr.end() ? def : it->second;
+    }
+};
+
+struct XmlError {
+    std::string msg;
+};
+
+class XmlParser {
+public:
+    explicit XmlParser(const std::string &s) : src(s) {}
+    std::unique_ptr<XmlNode> parse() {
+        skipMisc();
+        auto root = element();
+        return root;
+    }
+
+private:
+    const std::string &src;
+    size_t pos = 0;
+    [[noreturn]] void fail(const std::string &m) {
+        size_t line = 1;
+        for (size_t i = 0; i < pos && i < src.size(); ++i)
+            if (src[i] == '\n') ++line;
+        throw XmlError{"XML parse error (line " + std::to_string(line) + "): " + m};
+    }
+    void skipWs() {
+        while (pos < src.size() && std::isspace((unsigned char)src[pos])) ++pos;
+    }
+    bool starts(const char *s) const { return src.compare(pos, std::strlen(s), s) == 0; }
+    void skipMisc() {
+        while (true) {
+            skipWs();
+            if (starts("<?")) {
+                size_t e = src.find("?>", pos);
+                if (e == std::string::npos) fail("unterminated declaration");
+                pos = e + 2;
+            } else if (starts("<!--")) {
+                size_t e = src.find("-->", pos);
+                if (e == std::string::npos) fail("unterminated comment");
+                pos = e + 3;
+            } else if (starts("<!")) {
+                size_t e = src.find('>', pos);
+                if (e == std::string::npos) fail("unterminated doctype");
+                pos = e + 1;
+            } else {
+                return;
+            }
+        }
+    }
+    static std::string unescape(const std::string &v) {
+        std::string o;
+        for (size_t i = 0; i < v.size(); ++i) {
+            if (v[i] == '&') {
+                if (v.compare(i, 4, "&lt;") == 0) { o += '<'; i += 3; }
+                else if (v.compare(i, 4, "&gt;") == 0) { o += '>'; i += 3; }
+                else if (v.compare(i, 5, "&amp;") == 0) { o += '&'; i += 4; }
+                else if (v.compare(i, 6, "&quot;") == 0) { o += '"'; i += 5; }
+                else if (v.compare(i, 6, "&apos;") == 0) { o += '\''; i += 5; }
+                else o += v[i];
+            } else {
+                o += v[i];
+            }
+        }
+        return o;
+    }
+    std::string name() {
+        size_t b = pos;
+        while (pos < src.size() && (std::isalnum((unsigned char)src[pos]) || src[pos] == '_' || src[pos] == '-' || src[pos] == ':' || src[pos] == '.')) ++pos;
+        if (b == pos) fail("expected a name");
+        return src.substr(b, pos - b);
+    }
+    std::unique_ptr<XmlNode> element() {
+        if (pos >= src.size() || src[pos] != '<') fail("expected '<'");
+        ++pos;
+        std::unique_ptr<XmlNode> n(new XmlNode());
+        n->tag = name();
+        while (true) {
+            skipWs();
+            if (pos >= src.size()) fail("unterminated tag <" + n->tag + ">");
+            if (src[pos] == '/') {
+                if (!starts("/>")) fail("malformed tag end");
+                pos += 2;
+                return n;
+            }
+            if (src[pos] == '>') {
+                ++pos;
+                break;
+            }
+            std::string k = name();
+            skipWs();
+            if (pos >= src.size() || src[pos] != '=') fail("expected '=' after attribute " + k);
+            ++pos;
+            skipWs();
+            char q = pos < src.size() ? src[pos] : 0;
+            if (q != '"' && q != '\'') fail("expected a quoted attribute value");
+            size_t e = src.find(q, pos + 1);
+            if (e == std::string::npos) fail("unterminated attribute value");
+            n->attr[k] = unescape(src.substr(pos + 1, e - pos - 1));
+            pos = e + 1;
+        }
+        while (true) {  // children
+            skipMisc();
+            if (pos >= src.size()) fail("missing </" + n->tag + ">");
+            if (starts("</")) {
+                pos += 2;
+                std::string c = name();
+                if (c != n->tag) fail("mismatched </" + c + "> for <" + n->tag + ">");
+                skipWs();
+                if (pos >= src.size() || src[pos] != '>') fail("malformed closing tag");
+                ++pos;
+                return n;
+            }
+            if (src[pos] == '<') {
+                n->children.push_back(element());
+            } else {
+                ++pos;  // character data is not used by the scene format
+            }
+        }
+    }
+};
+
+// ---- small matrix helpers (row-major 4x4), mirroring src/libcore/transform.cpp
+struct M4 {
+    float m[16];
+};
+M4 identity() {
+    M4 r;
+    std::memset(r.m, 0, sizeof(r.m));
+    r.m[0] = r.m[5] = r.m[10] = r.m[15] = 1;
+    return r;
 }
+M4 mul(const M4 &a, const M4 &b) {
+    M4 r;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            float s = 0;
+            for (int k = 0; k < 4; ++k) s += a.m[i * 4 + k] * b.m[k * 4 + j];
+            r.m[i * 4 + j] = s;
+        }
+    return r;
+}
+M4 translate(float x, float y, float z) {
+    M4 r = identity();
+    r.m[3] = x; r.m[7] = y; r.m[11] = z;
+    return r;
+}
+M4 scale(float x, float y, float z) {
+    M4 r = identity();
+    r.m[0] = x; r.m[5] = y; r.m[10] = z;
+    return r;
+}
+M4 rotate(float ax, float ay, float az, float angle) {  // transform.cpp:65-98
+    float len = std::sqrt(ax * ax + ay * ay + az * az);
+    float inv = 1.0f / len;
+    float x = ax * inv, y = ay * inv, z = az * inv;
+    float rad = angle * (3.14159265358979323846f / 180.0f);
+    float s = std::sin(rad), c = std::cos(rad);
+    M4 r = identity();
+    r.m[0] = x * x + (1.0f - x * x) * c; r.m[1] = x * y * (1.0f - c) - z * s; r.m[2] = x * z * (1.0f - c) + y * s;
+    r.m[4] = x * y * (1.0f - c) + z * s; r.m[5] = y * y + (1.0f - y * y) * c; r.m[6] = y * z * (1.0f - c) - x * s;
+    r.m[8] = x * z * (1.0f - c) - y * s; r.m[9] = y * z * (1.0f - c) + x * s; r.m[10] = z * z + (1.0f - z * z) * c;
+    return r;
+}
+void cross3(const float *a, const float *b, float *o) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+bool normalize3(float *v) {
+    float l = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (l == 0) return false;
+    float inv = 1.0f / l;
+    v[0] *= inv; v[1] *= inv; v[2] *= inv;
+    return true;
+}
+bool lookAt(const float *p, const float *t, const float *up, M4 &out, std::string &err) {  // transform.cpp:191-214
+    float dir[3] = {t[0] - p[0], t[1] - p[1], t[2] - p[2]}, left[3], newUp[3];
+    if (!normalize3(dir)) {
+        err = "lookAt(): 'origin' and 'target' coincide!";
+        return false;
+    }
+    cross3(up, dir, left);
+    if (!normalize3(left)) {
+        err = "lookAt(): the forward and upward direction must be linearly independent!";
+        return false;
+    }
+    cross3(dir, left, newUp);
+    out = identity();
+    for (int i = 0; i < 3; ++i) {
+        out.m[i * 4 + 0] = left[i];
+        out.m[i * 4 + 1] = newUp[i];
+        out.m[i * 4 + 2] = dir[i];
+        out.m[i * 4 + 3] = p[i];
+    }
+    return true;
+}
+
+std::vector<std::string> tokenize(const std::string &s, const char *delims) {
+    std::vector<std::string> out;
+    size_t i = 0;
+    while (i < s.size()) {
+        size_t b = s.find_first_not_of(delims, i);
+        if (b == std::string::npos) break;
+        size_t e = s.find_first_of(delims, b);
+        out.push_back(s.substr(b, e == std::string::npos ? std::string::npos : e - b));
+        if (e == std::string::npos) break;
+        i = e;
+    }
+    return out;
+}
+
+struct Loader {
+    HostScene &H;
+    std::string baseDir;
+    std::map<std::string, std::string> params;    // -D key=value and <default>
+    std::map<std::string, int> bsdfIds, mediumIds;  // id -> index
+    Loader(HostScene &h) : H(h) {}
+
+    [[noreturn]] void fail(const std::string &m) { throw XmlError{m}; }
+
+    std::string subst(const std::string &v) {  // scenehandler.cpp:208-221
+        if (v.find('$') == std::string::npos) return v;
+        std::string out = v;
+        // longest names first so that $foobar is not clobbered by $foo
+        std::vector<std::pair<std::string, std::string>> ps(params.begin(), params.end());
+        std::sort(ps.begin(), ps.end(), [](auto &a, auto &b) { return a.first.size() > b.first.size(); });
+        for (auto &kv : ps) {
+            std::string key = "$" + kv.first;
+            size_t p = 0;
+            while ((p = out.find(key, p)) != std::string::npos) {
+                out.replace(p, key.size(), kv.second);
+                p += kv.second.size();
+            }
+        }
+        if (out.find('$') != std::string::npos) fail("The scene references an undefined parameter: \"" + out + "\"");
+        return out;
+    }
+    void substAll(XmlNode &n) {
+        if (n.tag == "default") {  // scenehandler.cpp:684-688
+            std::string name = n.get("name");
+            if (!params.count(name)) params[name] = subst(n.get("value"));
+            return;
+        }
+        for (auto &kv : n.attr) kv.second = subst(kv.second);
+        for (auto &c : n.children) substAll(*c);
+    }
+
+    float toFloat(const XmlNode &n, const std::string &v) {
+        char *end = nullptr;
+        float f = std::strtof(v.c_str(), &end);
+        if (end == v.c_str() || *end != '\0') fail("<" + n.tag + ">: could not parse floating point value \"" + v + "\"");
+        return f;
+    }
+    const XmlNode *prop(const XmlNode &obj, const char *name) {
+        for (auto &c : obj.children)
+            if (c->get("name") == name && !c->has("type") && c->tag != "ref") return c.get();
+        return nullptr;
+    }
+    float getFloat(const XmlNode &obj, const char *name, float def) {
+        const XmlNode *p = prop(obj, name);
+        if (!p) return def;
+        if (p->tag != "float" && p->tag != "integer") fail(std::string("property \"") + name + "\" has the wrong type");
+        return toFloat(*p, p->get("value"));
+    }
+    int getInt(const XmlNode &obj, const char *name, int def) {
+        const XmlNode *p = prop(obj, name);
+        if (!p) return def;
+        if (p->tag != "integer") fail(std::string("property \"") + name + "\" must be an <integer>");
+        return (int)std::strtol(p->get("value").c_str(), nullptr, 10);
+    }
+    bool getBool(const XmlNode &obj, const char *name, bool def) {
+        const XmlNode *p = prop(obj, name);
+        if (!p) return def;
+        if (p->tag != "boolean") fail(std::string("property \"") + name + "\" must be a <boolean>");
+        std::string v = p->get("value");
+        for (auto &c : v) c = (char)std::tolower(c);
+        if (v == "true") return true;
+        if (v == "false") return false;
+        fail("Could not parse boolean value \"" + v + "\" -- must be \"true\" or \"false\"");
+    }
+    std::string getString(const XmlNode &obj, const char *name, const std::string &def) {
+        const XmlNode *p = prop(obj, name);
+        if (!p) return def;
+        if (p->tag != "string") fail(std::string("property \"") + name + "\" must be a <string>");
+        return p->get("value");
+    }
+    // rgb / spectrum (scenehandler.cpp:461-633): "r, g, b" or one value broadcast; spectral power data are not supported
+    bool getSpectrum(const XmlNode &obj, const char *name, float out[3]) {
+        const XmlNode *p = prop(obj, name);
+        if (!p) return false;
+        if (p->tag != "rgb" && p->tag != "spectrum" && p->tag != "srgb")
+            fail(std::string("property \"") + name + "\" must be <rgb> or <spectrum>");
+        if (p->tag == "srgb") fail("<srgb> values are not supported, use linear <rgb>");
+        if (p->has("filename")) fail("<spectrum filename=...> is not supported");
+        std::string v = p->get("value");
+        if (v.find(':') != std::string::npos) fail("wavelength:value spectra are not supported in RGB mode here");
+        auto tok = tokenize(v, ", ");
+        if (tok.size() == 1) {
+            out[0] = out[1] = out[2] = toFloat(*p, tok[0]);
+        } else if (tok.size() == 3) {
+            for (int i = 0; i < 3; ++i) out[i] = toFloat(*p, tok[i]);
+        } else {
+            fail(std::string("<") + p->tag + ">: invalid value \"" + v + "\" (need 1 or 3 components)");
+        }
+        return true;
+    }
+    float iorByName(const std::string &nameIn) {  // src/bsdfs/ior.h:39-64
+        static const struct { const char *n; float v; } table[] = {
+            {"vacuum", 1.0f}, {"helium", 1.000036f}, {"hydrogen", 1.000132f}, {"air", 1.000277f}, {"carbon dioxide", 1.00045f},
+            {"water", 1.3330f}, {"acetone", 1.36f}, {"ethanol", 1.361f}, {"carbon tetrachloride", 1.461f}, {"glycerol", 1.4729f},
+            {"benzene", 1.501f}, {"silicone oil", 1.52045f}, {"bromine", 1.661f}, {"water ice", 1.31f}, {"fused quartz", 1.458f},
+            {"pyrex", 1.470f}, {"acrylic glass", 1.49f}, {"polypropylene", 1.49f}, {"bk7", 1.5046f}, {"sodium chloride", 1.544f},
+            {"amber", 1.55f}, {"pet", 1.5750f}, {"diamond", 2.419f}};
+        std::string n = nameIn;
+        for (auto &c : n) c = (char)std::tolower(c);
+        for (auto &e : table)
+            if (n == e.n) return e.v;
+        fail("Unable to find an IOR value for \"" + n + "\"!");
+    }
+    float getIOR(const XmlNode &obj, const char *name, const char *def) {  // lookupIOR, ior.h:94-113
+        const XmlNode *p = prop(obj, name);
+        if (!p) return iorByName(def);
+        if (p->tag == "float") return toFloat(*p, p->get("value"));
+        if (p->tag == "string") return iorByName(p->get("value"));
+        fail(std::string("property \"") + name + "\" must be a <float> or a material name");
+    }
+    M4 getTransform(const XmlNode &obj, const char *name) {
+        M4 cur = identity();
+        for (auto &c : obj.children) {
+            if (c->tag != "transform" || c->get("name") != name) continue;
+            for (auto &op : c->children) {
+                auto f = [&](const char *k, float def) { return op->has(k) && !op->get(k).empty() ? toFloat(*op, op->get(k)) : def; };
+                if (op->tag == "translate") {
+                    cur = mul(translate(f("x", 0), f("y", 0), f("z", 0)), cur);
+                } else if (op->tag == "rotate") {
+                    if (!op->has("angle")) fail("<rotate>: missing 'angle'");
+                    cur = mul(rotate(f("x", 0), f("y", 0), f("z", 0), toFloat(*op, op->get("angle"))), cur);
+                } else if (op->tag == "scale") {
+                    bool hasXYZ = op->has("x") || op->has("y") || op->has("z"), hasValue = op->has("value");
+                    if (hasXYZ && hasValue) fail("<scale>: provided both xyz and value arguments!");
+                    if (hasValue) {
+                        float v = toFloat(*op, op->get("value"));
+                        cur = mul(scale(v, v, v), cur);
+                    } else if (hasXYZ) {
+                        cur = mul(scale(f("x", 1), f("y", 1), f("z", 1)), cur);
+                    } else {
+                        fail("<scale>: provided neither xyz nor value arguments!");
+                    }
+                } else if (op->tag == "lookat") {
+                    auto o = tokenize(op->get("origin"), ", "), t = tokenize(op->get("target"), ", "), u = tokenize(op->get("up"), ", ");
+                    if (o.size() != 3) fail("<lookat>: invalid 'origin' argument");
+                    if (t.size() != 3) fail("<lookat>: invalid 'target' argument");
+                    float po[3], pt[3], up[3] = {0, 0, 0};
+                    for (int i = 0; i < 3; ++i) {
+                        po[i] = toFloat(*op, o[i]);
+                        pt[i] = toFloat(*op, t[i]);
+                    }
+                    if (u.size() == 3)
+                        for (int i = 0; i < 3; ++i) up[i] = toFloat(*op, u[i]);
+                    else if (!u.empty())
+                        fail("<lookat>: invalid 'up' argument");
+                    if (up[0] * up[0] + up[1] * up[1] + up[2] * up[2] == 0) {  // arbitrary up axis (:391-396)
+                        float d[3] = {pt[0] - po[0], pt[1] - po[1], pt[2] - po[2]};
+                        normalize3(d);
+                        float c[3];
+                        if (std::fabs(d[0]) > std::fabs(d[1])) {
+                            float il = 1.0f / std::sqrt(d[0] * d[0] + d[2] * d[2]);
+                            c[0] = d[2] * il; c[1] = 0; c[2] = -d[0] * il;
+                        } else {
+                            float il = 1.0f / std::sqrt(d[1] * d[1] + d[2] * d[2]);
+                            c[0] = 0; c[1] = d[2] * il; c[2] = -d[1] * il;
+                        }
+                        cross3(c, d, up);
+                    }
+                    M4 la;
+                    std::string err;
+                    if (!lookAt(po, pt, up, la, err)) fail(err);
+                    cur = mul(la, cur);
+                } else if (op->tag == "matrix") {
+                    auto tok = tokenize(op->get("value"), ", ");
+                    if (tok.size() != 16) fail("Invalid matrix specified");
+                    M4 m;
+                    for (int i = 0; i < 16; ++i) m.m[i] = toFloat(*op, tok[i]);
+                    cur = mul(m, cur);
+                } else {
+                    fail("unsupported transform operation <" + op->tag + ">");
+                }
+            }
+        }
+        return cur;
+    }
+
+    // -------------------------------------------------------------------------------- objects
+    int parseBsdf(const XmlNode &n) {
+        std::string type = n.get("type");
+        B200pgBsdf b;
+        std::memset(&b, 0, sizeof(b));
+        for (int c = 0; c < 3; ++c) b.specular_reflectance[c] = b.specular_transmittance[c] = 1.0f;
+        b.sample_visible = 1;
+        b.alpha_u = b.alpha_v = 0.1f;
+        b.int_ior = 1.5046f;
+        b.ext_ior = 1.000277f;
+        const XmlNode *src = &n;
+        if (type == "twosided") {  // twosided.cpp: one nested BRDF (same on both sides)
+            const XmlNode *inner = nullptr;
+            int count = 0;
+            for (auto &c : n.children)
+                if (c->tag == "bsdf") {
+                    inner = c.get();
+                    ++count;
+                }
+            if (count != 1) fail("twosided: exactly one nested BSDF is supported");
+            b.twosided = 1;
+            src = inner;
+            type = inner->get("type");
+        }
+        auto microfacet = [&]() {  // MicrofacetDistribution(props), microfacet.h:99-146
+            std::string d = getString(*src, "distribution", "beckmann");
+            for (auto &c : d) c = (char)std::tolower(c);
+            if (d == "beckmann") b.distribution = B200PG_DISTR_BECKMANN;
+            else if (d == "ggx") b.distribution = B200PG_DISTR_GGX;
+            else if (d == "phong" || d == "as") fail("the phong/as microfacet distribution is not supported");
+            else fail("Specified an invalid distribution \"" + d + "\", must be \"beckmann\", \"ggx\", or \"phong\"/\"as\"!");
+            bool hasA = prop(*src, "alpha"), hasU = prop(*src, "alphaU"), hasV = prop(*src, "alphaV");
+            if (hasA) {
+                if (hasU || hasV) fail("Microfacet model: please specify either 'alpha' or 'alphaU'/'alphaV'.");
+                b.alpha_u = b.alpha_v = getFloat(*src, "alpha", 0.1f);
+            } else if (hasU || hasV) {
+                if (!hasU || !hasV) fail("Microfacet model: both 'alphaU' and 'alphaV' must be specified.");
+                b.alpha_u = getFloat(*src, "alphaU", 0.1f);
+                b.alpha_v = getFloat(*src, "alphaV", 0.1f);
+            }
+            b.sample_visible = getBool(*src, "sampleVisible", true) ? 1 : 0;
+        };
+        if (type == "diffuse") {
+            b.type = B200PG_BSDF_DIFFUSE;
+            float r[3] = {0.5f, 0.5f, 0.5f};  // diffuse.cpp:81-83
+            if (!getSpectrum(*src, "reflectance", r)) getSpectrum(*src, "diffuseReflectance", r);
+            std::memcpy(b.reflectance, r, sizeof(r));
+        } else if (type == "dielectric") {
+            b.type = B200PG_BSDF_DIELECTRIC;
+            b.int_ior = getIOR(*src, "intIOR", "bk7");
+            b.ext_ior = getIOR(*src, "extIOR", "air");
+            getSpectrum(*src, "specularReflectance", b.specular_reflectance);
+            getSpectrum(*src, "specularTransmittance", b.specular_transmittance);
+        } else if (type == "roughconductor") {
+            b.type = B200PG_BSDF_ROUGHCONDUCTOR;
+            microfacet();
+            std::string mat = getString(*src, "material", "Cu");
+            std::string lower = mat;
+            for (auto &c : lower) c = (char)std::tolower(c);
+            float eta[3], k[3];
+            bool haveEta = getSpectrum(*src, "eta", eta), haveK = getSpectrum(*src, "k", k);
+            if (lower == "none") {
+                if (!haveEta) eta[0] = eta[1] = eta[2] = 0.0f;
+                if (!haveK) k[0] = k[1] = k[2] = 1.0f;
+            } else if (!haveEta || !haveK) {
+                // the reference integrates data/ior/<material>.{eta,k}.spd against the CIE curves
+                // (roughconductor.cpp:174-186); that spectral pipeline is out of scope: require explicit RGB values
+                fail("roughconductor: material \"" + mat + "\" needs explicit <rgb name=\"eta\"> and <rgb name=\"k\"> values "
+                     "(SPD -> RGB conversion is not part of this path)");
+            }
+            float extEta = getIOR(*src, "extEta", "air");
+            for (int c = 0; c < 3; ++c) {
+                b.eta[c] = eta[c] / extEta;
+                b.k[c] = k[c] / extEta;
+            }
+            b.ext_ior = extEta;
+            getSpectrum(*src, "specularReflectance", b.specular_reflectance);
+        } else if (type == "roughplastic") {
+            b.type = B200PG_BSDF_ROUGHPLASTIC;
+            microfacet();
+            b.int_ior = getIOR(*src, "intIOR", "polypropylene");
+            b.ext_ior = getIOR(*src, "extIOR", "air");
+            float r[3] = {0.5f, 0.5f, 0.5f};
+            getSpectrum(*src, "diffuseReflectance", r);
+            std::memcpy(b.reflectance, r, sizeof(r));
+            getSpectrum(*src, "specularReflectance", b.specular_reflectance);
+            b.nonlinear = getBool(*src, "nonlinear", false) ? 1 : 0;
+        } else if (type == "null") {
+            b.type = B200PG_BSDF_NULL;
+        } else {
+            fail("BSDF plugin \"" + type + "\" is not on the accelerated path (supported: diffuse, dielectric, roughconductor, "
+                 "roughplastic, twosided, null)");
+        }
+        H.bsdfs.push_back(b);
+        int idx = (int)H.bsdfs.size() - 1;
+        if (n.has("id")) bsdfIds[n.get("id")] = idx;
+        return idx;
+    }
+
+    void readVol(const std::string &path, B200pgMedium &m) {  // gridvolume.cpp:224-286
+        std::ifstream f(path, std::ios::binary);
+        if (!f) fail("gridvolume: cannot open \"" + path + "\"");
+        char hdr[4];
+        f.read(hdr, 4);
+        if (!f || hdr[0] != 'V' || hdr[1] != 'O' || hdr[2] != 'L') fail("Encountered an invalid volume data file (incorrect header identifier)");
+        if (hdr[3] != 3) fail("Encountered an invalid volume data file (incorrect file version)");
+        int32_t meta[5];
+        f.read((char *)meta, sizeof(meta));
+        float box[6];
+        f.read((char *)box, sizeof(box));
+        if (!f) fail("gridvolume: truncated header");
+        if (meta[0] != 1) fail("gridvolume: only float32 volumes (type 1) are supported");
+        if (meta[4] != 1) fail("gridvolume: the density volume must have one channel");
+        for (int c = 0; c < 3; ++c) {
+            m.res[c] = meta[1 + c];
+            m.aabb_min[c] = box[c];
+            m.aabb_max[c] = box[3 + c];
+        }
+        size_t n = (size_t)meta[1] * meta[2] * meta[3];
+        H.ownedF.emplace_back(n);
+        f.read((char *)H.ownedF.back().data(), n * sizeof(float));
+        if (!f) fail("gridvolume: truncated data");
+        m.density = H.ownedF.back().data();
+    }
+
+    int parseMedium(const XmlNode &n) {
+        if (n.get("type") != "heterogeneous") fail("medium plugin \"" + n.get("type") + "\" is not on the accelerated path (supported: heterogeneous)");
+        B200pgMedium m;
+        std::memset(&m, 0, sizeof(m));
+        std::string method = getString(n, "method", "woodcock");  // heterogeneous.cpp:195-202
+        for (auto &c : method) c = (char)std::tolower(c);
+        if (method == "woodcock") m.method = B200PG_MEDIUM_WOODCOCK;
+        else if (method == "simpson") m.method = B200PG_MEDIUM_SIMPSON;
+        else fail("Unsupported integration method \"" + method + "\"!");
+        if (prop(n, "sigmaS") || prop(n, "sigmaA")) fail("The 'sigmaS' and 'sigmaA' properties are only supported by homogeneous media.");
+        m.scale = getFloat(n, "scale", 1.0f);
+        m.step_size_multiplier = getFloat(n, "stepSize", 0.0f);
+        m.albedo[0] = m.albedo[1] = m.albedo[2] = 0.0f;
+        bool haveDensity = false, haveAlbedo = false;
+        m.phase_type = B200PG_PHASE_ISOTROPIC;
+        for (int i = 0; i < 16; ++i) m.to_world[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+        for (auto &c : n.children) {
+            if (c->tag == "volume") {
+                std::string role = c->get("name"), vt = c->get("type");
+                if (role == "density") {
+                    if (vt != "gridvolume") fail("density volume plugin \"" + vt + "\" is not supported (need gridvolume)");
+                    std::string fn = getString(*c, "filename", "");
+                    if (fn.empty()) fail("gridvolume: missing filename");
+                    if (fn[0] != '/') fn = baseDir + "/" + fn;
+                    readVol(fn, m);
+                    haveDensity = true;
+                } else if (role == "albedo") {
+                    if (vt != "constvolume") fail("albedo volume plugin \"" + vt + "\" is not supported (need constvolume)");
+                    if (!getSpectrum(*c, "value", m.albedo)) fail("constvolume: missing value");
+                    haveAlbedo = true;
+                } else {
+                    fail("heterogeneous: unsupported volume \"" + role + "\"");
+                }
+            } else if (c->tag == "phase") {
+                std::string pt = c->get("type");
+                if (pt == "isotropic") m.phase_type = B200PG_PHASE_ISOTROPIC;
+                else if (pt == "hg") {
+                    m.phase_type = B200PG_PHASE_HG;
+                    m.phase_g = getFloat(*c, "g", 0.8f);  // hg.cpp:54
+                    if (m.phase_g >= 1 || m.phase_g <= -1) fail("The asymmetry parameter must lie in the interval (-1, 1)!");
+                } else fail("phase function plugin \"" + pt + "\" is not supported (isotropic, hg)");
+            }
+        }
+        if (!haveDensity) fail("No density specified!");  // heterogeneous.cpp:230-233
+        if (!haveAlbedo) fail("No albedo specified!");
+        H.media.push_back(m);
+        int idx = (int)H.media.size() - 1;
+        if (n.has("id")) mediumIds[n.get("id")] = idx;
+        return idx;
+    }
+
+    void loadSerialized(const std::string &path, int shapeIndex, const M4 &toWorld, bool flipNormals, B200pgShape &s) {
+        // trimesh.cpp:175-270: header 0x041C, version 3|4, zlib stream: flags, [name], counts, positions, normals, uvs, colors, indices
+        std::ifstream f(path, std::ios::binary | std::ios::ate);
+        if (!f) fail("serialized: cannot open \"" + path + "\"");
+        size_t size = (size_t)f.tellg();
+        std::vector<unsigned char> buf(size);
+        f.seekg(0);
+        f.read((char *)buf.data(), size);
+        if (size < 8) fail("Encountered an invalid file format!");
+        auto rd16 = [&](size_t o) { return (uint16_t)(buf[o] | (buf[o + 1] << 8)); };
+        if (rd16(0) != 0x041C) fail("Encountered an invalid file format!");
+        int version = rd16(2);
+        if (version != 3 && version != 4) fail("Encountered an incompatible file version!");
+        size_t offset = 0;
+        if (shapeIndex != 0) {
+            uint32_t count;
+            std::memcpy(&count, &buf[size - 4], 4);
+            if (shapeIndex < 0 || shapeIndex > (int)count) fail("Unable to unserialize mesh, shape index is out of range!");
+            if (version == 4) {
+                uint64_t o;
+                std::memcpy(&o, &buf[size - 8 * (count - shapeIndex) - 4], 8);
+                offset = (size_t)o;
+            } else {
+                uint32_t o;
+                std::memcpy(&o, &buf[size - 4 * (count - shapeIndex + 1)], 4);
+                offset = o;
+            }
+        }
+        offset += 4;  // skip the (per-shape) header
+        z_stream zs;
+        std::memset(&zs, 0, sizeof(zs));
+        if (inflateInit(&zs) != Z_OK) fail("zlib: inflateInit failed");
+        zs.next_in = buf.data() + offset;
+        zs.avail_in = (uInt)std::min<size_t>(size - offset, 0xFFFFFFFFu);
+        std::vector<unsigned char> out;
+        std::vector<unsigned char> chunk(1 << 20);
+        int rc;
+        do {
+            zs.next_out = chunk.data();
+            zs.avail_out = (uInt)chunk.size();
+            rc = inflate(&zs, Z_NO_FLUSH);
+            if (rc != Z_OK && rc != Z_STREAM_END) {
+                inflateEnd(&zs);
+                fail("zlib: inflate failed while reading \"" + path + "\"");
+            }
+            out.insert(out.end(), chunk.data(), chunk.data() + (chunk.size() - zs.avail_out));
+        } while (rc != Z_STREAM_END);
+        inflateEnd(&zs);
+        size_t p = 0;
+        auto need = [&](size_t n) { if (p + n > out.size()) fail("serialized: truncated stream"); };
+        uint32_t flags;
+        need(4); std::memcpy(&flags, &out[p], 4); p += 4;
+        if (version == 4) {
+            while (p < out.size() && out[p] != 0) ++p;
+            ++p;
+        }
+        uint64_t nv, nt;
+        need(16); std::memcpy(&nv, &out[p], 8); std::memcpy(&nt, &out[p + 8], 8); p += 16;
+        const bool dbl = flags & 0x2000;
+        auto readArr = [&](size_t count, std::vector<float> &dst) {
+            dst.resize(count);
+            if (dbl) {
+                need(count * 8);
+                for (size_t i = 0; i < count; ++i) {
+                    double d;
+                    std::memcpy(&d, &out[p + 8 * i], 8);
+                    dst[i] = (float)d;
+                }
+                p += count * 8;
+            } else {
+                need(count * 4);
+                std::memcpy(dst.data(), &out[p], count * 4);
+                p += count * 4;
+            }
+        };
+        std::vector<float> pos, nrm, uv, col;
+        readArr(nv * 3, pos);
+        if (flags & 0x0001) readArr(nv * 3, nrm);
+        if (flags & 0x0002) readArr(nv * 2, uv);
+        if (flags & 0x0008) readArr(nv * 3, col);
+        std::vector<uint32_t> idx(nt * 3);
+        need(nt * 12);
+        std::memcpy(idx.data(), &out[p], nt * 12);
+        finishMesh(pos, nrm, uv, idx, toWorld, flipNormals, (flags & 0x0010) != 0, s);
+    }
+
+    void loadObj(const std::string &path, const M4 &toWorld, bool flipNormals, bool faceNormals, B200pgShape &s) {
+        std::ifstream f(path);
+        if (!f) fail("obj: cannot open \"" + path + "\"");
+        std::vector<float> P, N, T;
+        std::vector<float> pos, nrm, uv;
+        std::vector<uint32_t> idx;
+        std::map<std::string, uint32_t> remap;
+        std::string line;
+        bool anyN = false;
+        while (std::getline(f, line)) {
+            std::istringstream is(line);
+            std::string t;
+            is >> t;
+            if (t == "v") { float a, b, c; is >> a >> b >> c; P.insert(P.end(), {a, b, c}); }
+            else if (t == "vn") { float a, b, c; is >> a >> b >> c; N.insert(N.end(), {a, b, c}); }
+            else if (t == "vt") { float a, b; is >> a >> b; T.insert(T.end(), {a, b}); }
+            else if (t == "f") {
+                std::vector<uint32_t> poly;
+                std::string v;
+                while (is >> v) {
+                    auto it = remap.find(v);
+                    if (it == remap.end()) {
+                        int pi = 0, ti = 0, ni = 0;
+                        if (std::sscanf(v.c_str(), "%d/%d/%d", &pi, &ti, &ni) != 3 && std::sscanf(v.c_str(), "%d//%d", &pi, &ni) != 2 &&
+                            std::sscanf(v.c_str(), "%d/%d", &pi, &ti) != 2)
+                            std::sscanf(v.c_str(), "%d", &pi);
+                        if (pi < 0) pi = (int)(P.size() / 3) + pi + 1;
+                        if (ni < 0) ni = (int)(N.size() / 3) + ni + 1;
+                        if (ti < 0) ti = (int)(T.size() / 2) + ti + 1;
+                        if (pi <= 0 || (size_t)pi * 3 > P.size()) fail("obj: vertex index out of range");
+                        uint32_t id = (uint32_t)(pos.size() / 3);
+                        pos.insert(pos.end(), &P[3 * (pi - 1)], &P[3 * (pi - 1)] + 3);
+                        if (ni > 0 && (size_t)ni * 3 <= N.size()) { nrm.insert(nrm.end(), &N[3 * (ni - 1)], &N[3 * (ni - 1)] + 3); anyN = true; }
+                        else nrm.insert(nrm.end(), {0.0f, 0.0f, 0.0f});
+                        if (ti > 0 && (size_t)ti * 2 <= T.size()) uv.insert(uv.end(), &T[2 * (ti - 1)], &T[2 * (ti - 1)] + 2);
+                        else uv.insert(uv.end(), {0.0f, 0.0f});
+                        it = remap.emplace(v, id).first;
+                    }
+                    poly.push_back(it->second);
+                }
+                for (size_t k = 2; k < poly.size(); ++k) idx.insert(idx.end(), {poly[0], poly[k - 1], poly[k]});
+            }
+        }
+        if (idx.empty()) fail("obj: no faces in \"" + path + "\"");
+        if (!anyN) nrm.clear();
+        finishMesh(pos, nrm, uv, idx, toWorld, flipNormals, faceNormals, s);
+    }
+
+    void finishMesh(std::vector<float> &pos, std::vector<float> &nrm, std::vector<float> &uv, std::vector<uint32_t> &idx,
+                    const M4 &toWorld, bool flipNormals, bool faceNormals, B200pgShape &s) {
+        // apply toWorld (serialized.cpp / obj.cpp transform vertices on load); normals with the inverse transpose
+        double a[9] = {toWorld.m[0], toWorld.m[1], toWorld.m[2], toWorld.m[4], toWorld.m[5], toWorld.m[6], toWorld.m[8], toWorld.m[9], toWorld.m[10]};
+        double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+        if (det == 0) fail("mesh: singular toWorld");
+        double inv[9] = {(a[4] * a[8] - a[5] * a[7]) / det, (a[2] * a[7] - a[1] * a[8]) / det, (a[1] * a[5] - a[2] * a[4]) / det,
+                         (a[5] * a[6] - a[3] * a[8]) / det, (a[0] * a[8] - a[2] * a[6]) / det, (a[2] * a[3] - a[0] * a[5]) / det,
+                         (a[3] * a[7] - a[4] * a[6]) / det, (a[1] * a[6] - a[0] * a[7]) / det, (a[0] * a[4] - a[1] * a[3]) / det};
+        for (size_t v = 0; v < pos.size() / 3; ++v) {
+            float x = pos[3 * v], y = pos[3 * v + 1], z = pos[3 * v + 2];
+            pos[3 * v] = toWorld.m[0] * x + toWorld.m[1] * y + toWorld.m[2] * z + toWorld.m[3];
+            pos[3 * v + 1] = toWorld.m[4] * x + toWorld.m[5] * y + toWorld.m[6] * z + toWorld.m[7];
+            pos[3 * v + 2] = toWorld.m[8] * x + toWorld.m[9] * y + toWorld.m[10] * z + toWorld.m[11];
+        }
+        if (faceNormals) nrm.clear();
+        for (size_t v = 0; v < nrm.size() / 3; ++v) {
+            double x = nrm[3 * v], y = nrm[3 * v + 1], z = nrm[3 * v + 2];
+            double nx = inv[0] * x + inv[3] * y + inv[6] * z, ny = inv[1] * x + inv[4] * y + inv[7] * z, nz = inv[2] * x + inv[5] * y + inv[8] * z;
+            double l = std::sqrt(nx * nx + ny * ny + nz * nz);
+            if (l > 0) { nx /= l; ny /= l; nz /= l; }
+            if (flipNormals) { nx = -nx; ny = -ny; nz = -nz; }
+            nrm[3 * v] = (float)nx; nrm[3 * v + 1] = (float)ny; nrm[3 * v + 2] = (float)nz;
+        }
+        s.type = B200PG_SHAPE_TRIMESH;
+        s.n_vertices = (uint32_t)(pos.size() / 3);
+        s.n_triangles = (uint32_t)(idx.size() / 3);
+        H.ownedF.push_back(std::move(pos));
+        s.positions = H.ownedF.back().data();
+        if (!nrm.empty()) {
+            H.ownedF.push_back(std::move(nrm));
+            s.normals = H.ownedF.back().data();
+        }
+        if (!uv.empty()) {
+            H.ownedF.push_back(std::move(uv));
+            s.texcoords = H.ownedF.back().data();
+        }
+        H.ownedU.push_back(std::move(idx));
+        s.indices = H.ownedU.back().data();
+        for (int i = 0; i < 16; ++i) s.to_world[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+    }
+
+    void parseShape(const XmlNode &n) {
+        std::string type = n.get("type");
+        B200pgShape s;
+        std::memset(&s, 0, sizeof(s));
+        s.bsdf = s.emitter = s.interior_medium = s.exterior_medium = -1;
+        M4 toWorld = getTransform(n, "toWorld");
+        bool flip = getBool(n, "flipNormals", false);
+        if (type == "rectangle") {
+            s.type = B200PG_SHAPE_RECTANGLE;
+            M4 m = flip ? mul(toWorld, scale(1, 1, -1)) : toWorld;  // rectangle.cpp:79-84
+            std::memcpy(s.to_world, m.m, sizeof(m.m));
+        } else if (type == "cube") {  // cube.cpp:24-104
+            static const float P[24][3] = {{1, -1, -1}, {1, -1, 1}, {-1, -1, 1}, {-1, -1, -1}, {1, 1, -1}, {-1, 1, -1}, {-1, 1, 1}, {1, 1, 1},
+                                           {1, -1, -1}, {1, 1, -1}, {1, 1, 1}, {1, -1, 1}, {1, -1, 1}, {1, 1, 1}, {-1, 1, 1}, {-1, -1, 1},
+                                           {-1, -1, 1}, {-1, 1, 1}, {-1, 1, -1}, {-1, -1, -1}, {1, 1, -1}, {1, -1, -1}, {-1, -1, -1}, {-1, 1, -1}};
+            static const float N[6][3] = {{0, -1, 0}, {0, 1, 0}, {1, 0, 0}, {0, 0, 1}, {-1, 0, 0}, {0, 0, -1}};
+            static const float UV[4][2] = {{0, 1}, {1, 1}, {1, 0}, {0, 0}};
+            static const uint32_t T[12][3] = {{0, 1, 2}, {3, 0, 2}, {4, 5, 6}, {7, 4, 6}, {8, 9, 10}, {11, 8, 10}, {12, 13, 14}, {15, 12, 14},
+                                              {16, 17, 18}, {19, 16, 18}, {20, 21, 22}, {23, 20, 22}};
+            std::vector<float> pos, nrm, uv;
+            std::vector<uint32_t> idx;
+            for (int i = 0; i < 24; ++i) {
+                pos.insert(pos.end(), P[i], P[i] + 3);
+                nrm.insert(nrm.end(), N[i / 4], N[i / 4] + 3);
+                uv.insert(uv.end(), UV[i % 4], UV[i % 4] + 2);
+            }
+            for (auto &t : T) idx.insert(idx.end(), t, t + 3);
+            finishMesh(pos, nrm, uv, idx, toWorld, flip, false, s);
+        } else if (type == "serialized") {
+            std::string fn = getString(n, "filename", "");
+            if (fn.empty()) fail("serialized: missing filename");
+            if (fn[0] != '/') fn = baseDir + "/" + fn;
+            loadSerialized(fn, getInt(n, "shapeIndex", 0), toWorld, flip, s);
+            if (getBool(n, "faceNormals", false)) s.normals = nullptr;
+        } else if (type == "obj") {
+            std::string fn = getString(n, "filename", "");
+            if (fn.empty()) fail("obj: missing filename");
+            if (fn[0] != '/') fn = baseDir + "/" + fn;
+            loadObj(fn, toWorld, flip, getBool(n, "faceNormals", false), s);
+        } else {
+            fail("shape plugin \"" + type + "\" is not on the accelerated path (supported: rectangle, cube, serialized, obj)");
+        }
+        for (auto &c : n.children) {
+            if (c->tag == "bsdf") {
+                s.bsdf = parseBsdf(*c);
+            } else if (c->tag == "ref") {
+                std::string id = c->get("id"), role = c->get("name");
+                if (bsdfIds.count(id)) s.bsdf = bsdfIds[id];
+                else if (mediumIds.count(id)) {
+                    if (role == "interior") s.interior_medium = mediumIds[id];
+                    else if (role == "exterior") s.exterior_medium = mediumIds[id];
+                    else fail("Shape: Invalid medium child (must be named 'interior' or 'exterior')!");  // shape.cpp:160-178
+                } else fail("Referenced object \"" + id + "\" has not been defined (only bsdf and medium references are supported)");
+            } else if (c->tag == "medium") {
+                int m = parseMedium(*c);
+                std::string role = c->get("name");
+                if (role == "interior") s.interior_medium = m;
+                else if (role == "exterior") s.exterior_medium = m;
+                else fail("Shape: Invalid medium child (must be named 'interior' or 'exterior')!");
+            } else if (c->tag == "emitter") {
+                if (c->get("type") != "area") fail("emitter plugin \"" + c->get("type") + "\" cannot be attached to a shape (need area)");
+                B200pgEmitter e;
+                e.radiance[0] = e.radiance[1] = e.radiance[2] = 1.0f;  // area.cpp: default radiance = D65 -> 1 in RGB mode
+                getSpectrum(*c, "radiance", e.radiance);
+                e.sampling_weight = getFloat(*c, "samplingWeight", 1.0f);
+                e.shape = (int)H.shapes.size();
+                H.emitters.push_back(e);
+                s.emitter = (int)H.emitters.size() - 1;
+            } else if (c->tag == "subsurface" || c->tag == "sensor") {
+                fail("<" + c->tag + "> children of shapes are not supported");
+            }
+        }
+        H.shapes.push_back(s);
+    }
+
+    void parseIntegrator(const XmlNode &n) {
+        std::string type = n.get("type");
+        B200pgIntegratorParams &P = H.xmlParams;
+        bool vol = false, guided = false;
+        if (type == "progressivepath" || type == "path") vol = false;
+        else if (type == "progressivevolpath" || type == "volpath" || type == "volpath_simple") vol = true;
+        else if (type == "guidedpath" || type == "b200guidedpath") guided = true;
+        else if (type == "guidedvolpath" || type == "b200guidedvolpath") { guided = true; vol = true; }
+        else fail("integrator plugin \"" + type + "\" is not on the accelerated path (supported: progressivepath, progressivevolpath, "
+                  "path, volpath, guidedpath, guidedvolpath)");
+        P.volumetric = vol ? 1 : 0;
+        P.max_depth = getInt(n, "maxDepth", -1);                       // integrator.cpp:197-223
+        P.rr_depth = getInt(n, "rrDepth", 5);
+        P.strict_normals = getBool(n, "strictNormals", false) ? 1 : 0;
+        P.hide_emitters = getBool(n, "hideEmitters", false) ? 1 : 0;
+        P.samples_per_progression = getInt(n, "samplesPerProgression", 1);  // progressiveintegrator.cpp:296-300
+        P.max_render_time = getInt(n, "maxRenderTime", 0);
+        P.max_component_value = getFloat(n, "maxComponentValue", std::numeric_limits<float>::infinity());
+        P.use_nee = getBool(n, "useNee", true) ? 1 : 0;                // progressive_path.cpp:117
+        P.guiding = getBool(n, "guiding", guided) ? 1 : 0;
+        P.training_progressions = getInt(n, "trainingProgressions", guided ? 8 : 0);
+        P.guiding_probability = getFloat(n, "guidingProbability", 0.5f);
+        P.guide_max_components = getInt(n, "maxComponents", 16);
+        P.guide_max_cell_samples = getInt(n, "maxSamplesPerCell", 32768);
+        P.guide_train_discard_film = getBool(n, "discardTrainingSamples", false) ? 1 : 0;
+        P.guided_distance = getBool(n, "guidedDistanceSampling", false) ? 1 : 0;
+        if (P.rr_depth <= 0) fail("'rrDepth' must be set to a value greater than zero!");
+        if (P.max_depth <= 0 && P.max_depth != -1) fail("'maxDepth' must be set to -1 (infinite) or a value greater than zero!");
+    }
+
+    void parseSensor(const XmlNode &n) {
+        if (n.get("type") != "perspective") fail("sensor plugin \"" + n.get("type") + "\" is not on the accelerated path (supported: perspective)");
+        B200pgSensor &S = H.sensor;
+        M4 tw = getTransform(n, "toWorld");
+        std::memcpy(S.to_world, tw.m, sizeof(tw.m));
+        if (prop(n, "focalLength") && prop(n, "fov")) fail("Please specify either a focal length ('focalLength') or a field of view ('fov')!");
+        if (prop(n, "fov")) {
+            S.fov = getFloat(n, "fov", 0);
+        } else {  // sensor.cpp:260-272: 36x24mm film, diagonal fov from the focal length
+            std::string fl = getString(n, "focalLength", "50mm");
+            if (fl.size() > 2 && fl.substr(fl.size() - 2) == "mm") fl = fl.substr(0, fl.size() - 2);
+            float value = std::strtof(fl.c_str(), nullptr);
+            S.fov = 2 * 180 / 3.14159265358979323846f * std::atan(std::sqrt((float)(36 * 36 + 24 * 24)) / (2 * value));
+        }
+        std::string axis = prop(n, "fov") ? getString(n, "fovAxis", "x") : std::string("diagonal");
+        for (auto &c : axis) c = (char)std::tolower(c);
+        if (axis == "x") S.fov_axis = 0;
+        else if (axis == "y") S.fov_axis = 1;
+        else if (axis == "diagonal") S.fov_axis = 2;
+        else if (axis == "smaller") S.fov_axis = 3;
+        else if (axis == "larger") S.fov_axis = 4;
+        else fail("The 'fovAxis' parameter must be set to one of 'smaller', 'larger', 'diagonal', 'x', or 'y'!");
+        S.near_clip = getFloat(n, "nearClip", 1e-2f);  // sensor.cpp:158-160
+        S.far_clip = getFloat(n, "farClip", 1e4f);
+        S.medium = -1;
+        H.film.width = 768;  // film.cpp:29-32
+        H.film.height = 576;
+        H.film.filter_stddev = 0.5f;
+        H.sampleCount = 4;  // independent.cpp:57
+        for (auto &c : n.children) {
+            if (c->tag == "sampler") {
+                std::string st = c->get("type");
+                if (st != "independent" && st != "deterministic")
+                    fail("sampler plugin \"" + st + "\" is not supported (progressive rendering needs independent or deterministic, "
+                         "progressiveintegrator.cpp:31-35)");
+                H.sampleCount = getInt(*c, "sampleCount", 4);
+                H.seed = (uint64_t)getInt(*c, "seed", 1337);
+            } else if (c->tag == "film") {
+                if (c->get("type") != "hdrfilm") fail("film plugin \"" + c->get("type") + "\" is not supported (need hdrfilm)");
+                H.film.width = getInt(*c, "width", 768);
+                H.film.height = getInt(*c, "height", 576);
+                if (prop(*c, "cropWidth") || prop(*c, "cropOffsetX")) fail("hdrfilm: crop windows are not supported");
+                for (auto &f : c->children)
+                    if (f->tag == "rfilter") {
+                        if (f->get("type") != "gaussian") fail("rfilter plugin \"" + f->get("type") + "\" is not supported (need gaussian)");
+                        H.film.filter_stddev = getFloat(*f, "stddev", 0.5f);
+                    }
+            } else if (c->tag == "medium") {
+                S.medium = parseMedium(*c);
+            } else if (c->tag == "ref") {
+                std::string id = c->get("id");
+                if (!mediumIds.count(id)) fail("sensor: referenced object \"" + id + "\" is not a medium");
+                S.medium = mediumIds[id];
+            }
+        }
+    }
+
+    void parseScene(const XmlNode &root) {
+        if (root.tag != "scene") fail("the root element must be <scene>");
+        if (!root.has("version")) fail("The scene is missing a version attribute!");  // scenehandler.cpp:228-233
+        b200pg_integrator_params_default(&H.xmlParams);
+        bool haveSensor = false;
+        for (auto &c : root.children) {
+            if (c->tag == "default") continue;
+            if (c->tag == "integrator") parseIntegrator(*c);
+            else if (c->tag == "sensor") { parseSensor(*c); haveSensor = true; }
+            else if (c->tag == "bsdf") parseBsdf(*c);
+            else if (c->tag == "medium") parseMedium(*c);
+            else if (c->tag == "shape") parseShape(*c);
+            else if (c->tag == "emitter") fail("emitter plugin \"" + c->get("type") + "\" is not on the accelerated path (area lights attached to shapes only)");
+            else if (c->tag == "include") fail("<include> is not supported");
+            else if (c->tag == "texture" || c->tag == "subsurface" || c->tag == "phase" || c->tag == "volume")
+                fail("top-level <" + c->tag + "> objects are not supported");
+            else fail("unexpected tag <" + c->tag + ">");
+        }
+        if (!haveSensor) fail("the scene needs a perspective <sensor> (the reference's default sensor fallback, scene.cpp:272-312, is not replicated)");
+    }
+};
+
+}  // namespace
+
+bool loadSceneXml(const char *path, const char *const *defines, HostScene &out, std::string &err) {
+    try {
+        std::ifstream f(path);
+        if (!f) {
+            err = std::string("cannot open scene file \"") + (path ? path : "") + "\"";
+            return false;
+        }
+        std::stringstream ss;
+        ss << f.rdbuf();
+        std::string text = ss.str();
+        XmlParser parser(text);
+        std::unique_ptr<XmlNode> root = parser.parse();
+        Loader L(out);
+        std::string p(path);
+        size_t slash = p.find_last_of('/');
+        L.baseDir = slash == std::string::npos ? "." : p.substr(0, slash);
+        if (defines)
+            for (const char *const *d = defines; *d; ++d) {
+                std::string kv(*d);
+                size_t eq = kv.find('=');
+                if (eq == std::string::npos) {
+                    err = "define \"" + kv + "\" must have the form key=value";
+                    return false;
+                }
+                L.params[kv.substr(0, eq)] = kv.substr(eq + 1);
+            }
+        L.substAll(*root);
+        L.parseScene(*root);
+        if (out.shapes.empty()) {
+            err = "scene has no shapes";
+            return false;
+        }
+        out.refreshView();
+        return true;
+    } catch (const XmlError &e) {
+        err = e.msg;
+        return false;
+    } catch (const std::exception &e) {
+        err = e.what();
+        return false;
+    }
+}
+
 }  // namespace pg

@@ -553,6 +553,45 @@ def mesh_scene(width=2048, height=2048, spp=16, seed=1337, n=3163, max_depth=8):
     return sb
 
 
+def write_serialized(path, P, T, N=None, UV=None, name="mesh"):
+    """Mitsuba .serialized v4 file (trimesh.cpp:175-270): 0x041C, version, zlib{flags, name, counts, arrays}, offset dictionary."""
+    import struct
+    import zlib
+
+    flags = 0x1000  # single precision
+    if N is not None:
+        flags |= 0x0001
+    if UV is not None:
+        flags |= 0x0002
+    body = struct.pack("<I", flags) + name.encode() + b"\0" + struct.pack("<QQ", P.shape[0], T.shape[0])
+    body += np.ascontiguousarray(P, "<f4").tobytes()
+    if N is not None:
+        body += np.ascontiguousarray(N, "<f4").tobytes()
+    if UV is not None:
+        body += np.ascontiguousarray(UV, "<f4").tobytes()
+    body += np.ascontiguousarray(T, "<u4").tobytes()
+    with open(path, "wb") as f:
+        f.write(struct.pack("<HH", 0x041C, 4))
+        f.write(zlib.compress(body, 1))
+        f.write(struct.pack("<QI", 0, 1))
+
+
+def save_scene(sb, directory, name="scene.xml"):
+    """Writes the XML plus the mesh / volume files it references; returns the XML path."""
+    import os
+
+    os.makedirs(directory, exist_ok=True)
+    for i, s in enumerate(sb.shapes):
+        if s["xml"] == "serialized":
+            write_serialized(os.path.join(directory, (s.get("name") or "mesh%d" % i) + ".serialized"), s["P"], s["T"], s.get("N"), s.get("UV"))
+    for i, m in enumerate(sb.media):
+        write_vol(os.path.join(directory, m["vol_path"] or ("medium%d.vol" % i)), m["density"], m["aabb_min"], m["aabb_max"])
+    path = os.path.join(directory, name)
+    with open(path, "w") as f:
+        f.write(sb.to_xml())
+    return path
+
+
 def write_vol(path, density, aabb_min, aabb_max):
     """Mitsuba VOL v3 file (gridvolume.cpp:56-89, 224-286): 'VOL',3, type=1 (f32), nx,ny,nz, channels, 6xf32 AABB."""
     nz, ny, nx = density.shape

@@ -1,0 +1,141 @@
+"""Scene XML subset reader (csrc/xml_scene.cpp) against the same scenes built as flat arrays: the XML text is ordinary
+Mitsuba 0.6 XML (scenes.SceneBuilder.to_xml), so this is the "same scene XML" promise of the drop-in boundary.
+Semantics under test follow src/librender/scenehandler.cpp (transform composition :348-440, $param substitution
+:208-221, <default> :684-688, rgb/spectrum parsing :461-633, ref/id :744-760). No GPU needed: parsing is host code."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def api(pkg):
+    from b200pg import api as _api
+
+    return _api
+
+
+def _arr(ptr, n):
+    return np.ctypeslib.as_array(ptr, shape=(n,)).copy() if n else np.zeros(0)
+
+
+def _compare_desc(a, b, A):
+    assert (a.n_shapes, a.n_emitters, a.n_media) == (b.n_shapes, b.n_emitters, b.n_media)
+    assert (a.film.width, a.film.height, a.sample_count, a.seed) == (b.film.width, b.film.height, b.sample_count, b.seed)
+    np.testing.assert_allclose(a.sensor.to_world[:], b.sensor.to_world[:], atol=1e-6)
+    assert abs(a.sensor.fov - b.sensor.fov) < 1e-6 and a.sensor.fov_axis == b.sensor.fov_axis and a.sensor.medium == b.sensor.medium
+    for i in range(a.n_shapes):
+        sa, sb = a.shapes[i], b.shapes[i]
+        assert sa.type == sb.type and sa.emitter == sb.emitter, i
+        assert (sa.interior_medium, sa.exterior_medium) == (sb.interior_medium, sb.exterior_medium)
+        ba, bb = a.bsdfs[sa.bsdf], b.bsdfs[sb.bsdf]
+        assert (ba.type, ba.twosided, ba.distribution) == (bb.type, bb.twosided, bb.distribution), i
+        fields = {A.BSDF_DIFFUSE: ("reflectance",), A.BSDF_DIELECTRIC: ("specular_reflectance", "specular_transmittance"),
+                  A.BSDF_ROUGHCONDUCTOR: ("specular_reflectance", "eta", "k"),
+                  A.BSDF_ROUGHPLASTIC: ("reflectance", "specular_reflectance"), A.BSDF_NULL: ()}[ba.type]
+        for f in fields:
+            np.testing.assert_allclose(getattr(ba, f)[:], getattr(bb, f)[:], rtol=1e-6, atol=1e-7)
+        assert abs(ba.int_ior - bb.int_ior) < 1e-6 and abs(ba.alpha_u - bb.alpha_u) < 1e-7
+        if ba.type == A.BSDF_ROUGHPLASTIC:
+            np.testing.assert_allclose(ba.rt_ext_trans[:], bb.rt_ext_trans[:], rtol=1e-6)
+        if sa.type == A.SHAPE_RECTANGLE:
+            np.testing.assert_allclose(sa.to_world[:], sb.to_world[:], atol=2e-6)
+        else:
+            assert (sa.n_vertices, sa.n_triangles) == (sb.n_vertices, sb.n_triangles)
+            np.testing.assert_allclose(_arr(sa.positions, 3 * sa.n_vertices), _arr(sb.positions, 3 * sb.n_vertices), atol=2e-6)
+            assert np.array_equal(_arr(sa.indices, 3 * sa.n_triangles), _arr(sb.indices, 3 * sb.n_triangles))
+            assert bool(sa.normals) == bool(sb.normals)
+            if sa.normals:
+                np.testing.assert_allclose(_arr(sa.normals, 3 * sa.n_vertices), _arr(sb.normals, 3 * sb.n_vertices), atol=2e-6)
+    for i in range(a.n_emitters):
+        np.testing.assert_allclose(a.emitters[i].radiance[:], b.emitters[i].radiance[:], rtol=1e-6)
+        assert a.emitters[i].shape == b.emitters[i].shape
+    for i in range(a.n_media):
+        ma, mb = a.media[i], b.media[i]
+        assert (ma.method, ma.phase_type, list(ma.res)) == (mb.method, mb.phase_type, list(mb.res))
+        assert abs(ma.scale - mb.scale) < 1e-6 and abs(ma.phase_g - mb.phase_g) < 1e-7
+        n = ma.res[0] * ma.res[1] * ma.res[2]
+        assert np.array_equal(_arr(ma.density, n), _arr(mb.density, n))
+        np.testing.assert_allclose(list(ma.aabb_min) + list(ma.aabb_max), list(mb.aabb_min) + list(mb.aabb_max), atol=1e-7)
+
+
+@pytest.mark.parametrize("name,kw", [("cornell_box", dict(width=64, height=48)), ("cornell_caustic", dict(width=32, height=32)),
+                                     ("cornell_medium", dict(width=32, height=32, res=12)), ("mesh_scene", dict(width=32, height=32, n=17))])
+def test_xml_roundtrip_equals_flat_arrays(api, pkg, tmp_path, name, kw):
+    S = pkg.scenes
+    sb = getattr(S, name)(**kw)
+    xml = S.save_scene(sb, str(tmp_path))
+    from_xml = api.Scene.load_xml(xml)
+    from_arrays = api.Scene.from_builder(sb)
+    _compare_desc(from_xml.desc, from_arrays.desc, pkg._abi)
+    p = from_xml.integrator_params()
+    assert p.max_depth == 8 and p.rr_depth == 5 and p.use_nee == 1
+    assert p.volumetric == (1 if name == "cornell_medium" else 0)
+
+
+def _scene(body, integrator='<integrator type="progressivepath"/>'):
+    return ('<?xml version="1.0"?>\n<!-- comment -->\n<scene version="0.6.0">\n' + integrator + '''
+    <sensor type="perspective"><float name="fov" value="40"/>
+      <transform name="toWorld"><lookat origin="0, 0, 4" target="0, 0, 0"/></transform>
+      <sampler type="independent"><integer name="sampleCount" value="$spp"/></sampler>
+      <film type="hdrfilm"><integer name="width" value="32"/><integer name="height" value="16"/></film>
+    </sensor>''' + body + "\n</scene>\n")
+
+
+def test_defaults_params_and_transform_order(api, tmp_path):
+    body = '''<default name="spp" value="9"/><default name="r" value="0.25"/>
+    <shape type="rectangle">
+      <transform name="toWorld"><scale x="2" y="3"/><rotate z="1" angle="90"/><translate x="1" y="0" z="-1"/></transform>
+      <bsdf type="diffuse"><rgb name="reflectance" value="$r"/></bsdf>
+      <emitter type="area"><spectrum name="radiance" value="3"/></emitter>
+    </shape>'''
+    path = tmp_path / "a.xml"
+    path.write_text(_scene(body).replace("<scene version", "<scene version", 1).replace('<sensor', '<default name="unused" value="1"/>\n<sensor', 1).replace('<!-- comment -->\n<scene version="0.6.0">', '<!-- comment -->\n<scene version="0.6.0">\n<default name="spp" value="9"/>'))
+    sc = api.Scene.load_xml(str(path))
+    d = sc.desc
+    assert d.sample_count == 9 and d.film.width == 32 and d.film.height == 16
+    assert list(d.bsdfs[d.shapes[0].bsdf].reflectance) == [0.25, 0.25, 0.25]       # single value broadcasts
+    assert list(d.emitters[0].radiance) == [3.0, 3.0, 3.0]                        # <spectrum value="3"/> on an emitter
+    # translate * rotate * scale applied to (1,1,0): scale -> (2,3,0), rotate z 90 -> (-3,2,0), translate -> (-2,2,-1)
+    m = np.array(d.shapes[0].to_world[:]).reshape(4, 4)
+    np.testing.assert_allclose(m @ [1, 1, 0, 1], [-2, 2, -1, 1], atol=1e-5)
+    # -D overrides <default> (scenehandler.cpp:208-221)
+    sc2 = api.Scene.load_xml(str(path), {"spp": "21", "r": "0.5"})
+    assert sc2.desc.sample_count == 21 and sc2.desc.bsdfs[sc2.desc.shapes[0].bsdf].reflectance[0] == 0.5
+    # lookat without 'up' picks an arbitrary but valid frame (scenehandler.cpp:391-396)
+    cam = np.array(d.sensor.to_world[:]).reshape(4, 4)
+    np.testing.assert_allclose(cam[:3, 2], [0, 0, -1], atol=1e-6)
+    np.testing.assert_allclose(cam[:3, :3].T @ cam[:3, :3], np.eye(3), atol=1e-5)
+    # defaults of the reference objects
+    p = sc.integrator_params()
+    assert (p.max_depth, p.rr_depth, p.samples_per_progression) == (-1, 5, 1) and p.max_component_value == float("inf")
+
+
+@pytest.mark.parametrize("body,integrator,match", [
+    ('<shape type="sphere"/>', None, "sphere"),
+    ('<shape type="rectangle"><bsdf type="plastic"/></shape>', None, "plastic"),
+    ('<shape type="rectangle"><bsdf type="roughconductor"/></shape>', None, "eta"),
+    ('<shape type="rectangle"><bsdf type="diffuse"><rgb name="reflectance" value="1 2"/></bsdf></shape>', None, "1 or 3"),
+    ('<shape type="rectangle"/>', '<integrator type="bdpt"/>', "bdpt"),
+    ('<shape type="rectangle"/>', '<integrator type="path"><integer name="rrDepth" value="0"/></integrator>', "rrDepth"),
+    ('<shape type="rectangle"/><emitter type="envmap"/>', None, "envmap"),
+    ('<shape type="rectangle"><ref id="nope"/></shape>', None, "nope"),
+    ('<shape type="rectangle"><float name="x" value="$undefined"/></shape>', None, "undefined"),
+    ('<shape type="rectangle">', None, "XML parse error"),
+])
+def test_unsupported_or_malformed_input_is_an_error(api, tmp_path, body, integrator, match):
+    path = tmp_path / "bad.xml"
+    text = _scene(body, integrator) if integrator else _scene(body)
+    path.write_text(text.replace("$spp", "4"))
+    with pytest.raises(api.B200pgError, match=match):
+        api.Scene.load_xml(str(path))
+
+
+def test_missing_file_and_version(api, tmp_path):
+    with pytest.raises(api.B200pgError, match="cannot open"):
+        api.Scene.load_xml(str(tmp_path / "missing.xml"))
+    path = tmp_path / "nov.xml"
+    path.write_text(_scene('<shape type="rectangle"/>').replace(' version="0.6.0"', "").replace("$spp", "4"))
+    with pytest.raises(api.B200pgError, match="version"):
+        api.Scene.load_xml(str(path))
