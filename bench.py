@@ -83,16 +83,16 @@ def run_reference(args):
     sc = orc.scene(sb)
     p = pkg._abi.default_params()
     p.max_depth = 8
-    cores = orc.num_threads()
+    cores = len(os.sched_getaffinity(0))
     # bounded sample: a band of rows sized so that one step takes a few seconds
-    film, st = sc.render(p, 0, 1, rows=(0, 32))
+    film, st = sc.render(p, 0, 1, rows=(0, 32), nthreads=cores)
     rate = st["paths"] / max(st["seconds"], 1e-6)
     rows = int(min(sb.height, max(32, (rate * args.ref_seconds / sb.width) // 32 * 32)))
     for _ in range(args.warmup):
-        sc.render(p, 0, 1, rows=(0, rows))
+        sc.render(p, 0, 1, rows=(0, rows), nthreads=cores)
     t = paths = rays = 0.0
     for k in range(args.steps):
-        film, st = sc.render(p, k, 1, rows=(0, rows))
+        film, st = sc.render(p, k, 1, rows=(0, rows), nthreads=cores)
         t += st["seconds"]
         paths += st["paths"]
         rays += st["normal_rays"] + st["shadow_rays"]
@@ -258,10 +258,15 @@ def main():
     h2d = d2h = 0
     te = time.perf_counter()
     for k in range(args.steps):
+        _t0 = time.perf_counter()
         h2d = integ.scene_upload()
+        _t1 = time.perf_counter()
         step(args.warmup + args.steps + k)
+        _t2 = time.perf_counter()
         integ.film(out=host_film)
         d2h = host_film.nbytes
+        if os.environ.get("B200PG_BENCH_DEBUG"):
+            print("e2e step", k, "upload %.2f step %.2f film %.2f ms" % (1e3 * (_t1 - _t0), 1e3 * (_t2 - _t1), 1e3 * (time.perf_counter() - _t2)), file=sys.stderr)
     barrier()
     e_elapsed = time.perf_counter() - te
     if world > 1:
@@ -285,11 +290,12 @@ def main():
 
             orc = Oracle()
             osc = orc.scene(sb)
-            f, st = osc.render(p, 0, 1, rows=(0, 32))
+            ncores = len(os.sched_getaffinity(0))  # torchrun sets OMP_NUM_THREADS=1: ask for all host cores explicitly
+            f, st = osc.render(p, 0, 1, rows=(0, 32), nthreads=ncores)
             rate = st["paths"] / max(st["seconds"], 1e-6)
             rows = int(min(sb.height, max(32, (rate * args.cpu_baseline_seconds / sb.width) // 32 * 32)))
-            f, st = osc.render(p, 0, 1, rows=(0, rows))
-            cpu = {"value": st["paths"] / st["seconds"] / 1e6, "unit": "Mpaths/s", "cores": orc.num_threads(), "kind": "port",
+            f, st = osc.render(p, 0, 1, rows=(0, rows), nthreads=ncores)
+            cpu = {"value": st["paths"] / st["seconds"] / 1e6, "unit": "Mpaths/s", "cores": ncores, "kind": "port",
                    "sample": "rows 0..%d of the %dx%d image, 1 spp (%.1f s)" % (rows, sb.width, sb.height, st["seconds"]),
                    "mrays_per_sec": (st["normal_rays"] + st["shadow_rays"]) / st["seconds"] / 1e6}
         except Exception as ex:  # the oracle is test infrastructure; its absence must not break the product arm

@@ -498,7 +498,7 @@ def cornell_medium(width=1024, height=1024, spp=64, seed=1337, max_depth=8, res=
     return sb
 
 
-def heightfield_mesh(n=3163, seed=1337, amp=0.05):
+def heightfield_mesh(n=2237, seed=1337, amp=0.05):
     """(n-1)^2*2 triangles over [-1,1]^2 in xz, y = amp * sum of seeded sines, with vertex normals."""
     rng = np.random.RandomState(seed)
     x = np.linspace(-1, 1, n, dtype=np.float64)
@@ -526,8 +526,8 @@ def heightfield_mesh(n=3163, seed=1337, amp=0.05):
     return P, N.astype(f32), T.astype(np.uint32)
 
 
-def mesh_scene(width=2048, height=2048, spp=16, seed=1337, n=3163, max_depth=8):
-    """Config C4: ~10M-triangle procedural mesh in 4 shapes with roughconductor/roughplastic, 2 area lights."""
+def mesh_scene(width=2048, height=2048, spp=16, seed=1337, n=2237, max_depth=8):
+    """Config C4 (n = 2237 -> 2 * 2236^2 = 10.0 M triangles): ~10M-triangle procedural mesh in 4 shapes with roughconductor/roughplastic, 2 area lights."""
     sb = SceneBuilder(width, height, spp, seed)
     cond = sb.roughconductor(eta=(0.2004, 0.9240, 1.1022), k=(3.9129, 2.4528, 2.1421), alpha=0.15, distribution="ggx")
     plast = sb.roughplastic(diffuse=(0.4, 0.25, 0.1), alpha=0.2, distribution="beckmann")

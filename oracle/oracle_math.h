@@ -211,6 +211,16 @@ struct Rng {
         return (xorshifted >> rot) | (xorshifted << ((32u - rot) & 31u));
     }
     Float next1D() { return (Float)(nextU32() >> 8) * (1.0f / 16777216.0f); }
+    // independent child stream (transmittance estimates draw from a fork so that the main stream's consumption
+    // does not depend on how many medium interactions a connection crosses); consumes two words of the parent
+    Rng fork() {
+        Rng r;
+        uint64_t a = nextU32();
+        uint64_t b = nextU32();
+        r.inc = inc;
+        r.state = mix64((a << 32) | b);
+        return r;
+    }
     Vec2 next2D() {
         Float a = next1D();
         Float b = next1D();

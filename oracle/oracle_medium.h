@@ -1,8 +1,10 @@
 // TEST INFRASTRUCTURE ONLY -- see oracle_math.h header note.
 //
 // oracle_medium.h: heterogeneous medium over a dense grid volume, restated from
-//   src/medium/heterogeneous.cpp:546-663 (Woodcock tracking), src/volume/gridvolume.cpp:188-215, 337-388,
+//   src/medium/heterogeneous.cpp:228-262 (configure), :546-587 (evalTransmittance), :589-663 (sampleDistance, Woodcock),
+//   src/volume/gridvolume.cpp:188-198 (worldToGrid, step size), :337-388 (trilinear lookupFloat),
 //   src/phase/hg.cpp:74-110, src/phase/isotropic.cpp:62-78.
+// Only the default method (Woodcock / delta tracking, heterogeneous.cpp:195-197) is restated.
 #pragma once
 #include <vector>
 
@@ -11,16 +13,155 @@
 
 namespace orc {
 
+struct MediumSample {  // MediumSamplingRecord fields used on this path
+    Float t;
+    Vec3 p;
+    Vec3 sigmaS, transmittance;
+    Float pdfSuccess, pdfFailure;
+};
+
 struct Medium {
     B200pgMedium d;
     std::vector<Float> density;
+    Float maxDensity, invMaxDensity;
+    Float gridScale[3], gridOffset[3];  // worldToGrid = scale((res-1)/extent) * translate(-min)
+    Vec3 bmin, bmax;
+
     static Medium fromDesc(const B200pgMedium &m) {
         Medium r;
         r.d = m;
         size_t n = (size_t)m.res[0] * m.res[1] * m.res[2];
         if (m.density) r.density.assign(m.density, m.density + n);
         r.d.density = nullptr;
+        r.maxDensity = m.scale * 1.0f;  // getMaximumFloatValue() == 1 (gridvolume.cpp:583-585)
+        r.invMaxDensity = 1.0f / r.maxDensity;
+        for (int c = 0; c < 3; ++c) {
+            Float ext = m.aabb_max[c] - m.aabb_min[c];
+            r.gridScale[c] = (m.res[c] - 1) / ext;
+            r.gridOffset[c] = r.gridScale[c] * -m.aabb_min[c];
+        }
+        r.bmin = Vec3(m.aabb_min[0], m.aabb_min[1], m.aabb_min[2]);
+        r.bmax = Vec3(m.aabb_max[0], m.aabb_max[1], m.aabb_max[2]);
         return r;
+    }
+
+    // GridDataSource::lookupFloat, gridvolume.cpp:337-388 (float32 data, zero outside)
+    Float lookup(const Vec3 &_p) const {
+        const Float px = gridScale[0] * _p.x + gridOffset[0], py = gridScale[1] * _p.y + gridOffset[1],
+                    pz = gridScale[2] * _p.z + gridOffset[2];
+        const int x1 = (int)std::floor(px), y1 = (int)std::floor(py), z1 = (int)std::floor(pz), x2 = x1 + 1, y2 = y1 + 1, z2 = z1 + 1;
+        const int rx = d.res[0], ry = d.res[1], rz = d.res[2];
+        if (x1 < 0 || y1 < 0 || z1 < 0 || x2 >= rx || y2 >= ry || z2 >= rz) return 0;
+        const Float fx = px - x1, fy = py - y1, fz = pz - z1, _fx = 1.0f - fx, _fy = 1.0f - fy, _fz = 1.0f - fz;
+        const Float *f = density.data();
+        const Float d000 = f[((size_t)z1 * ry + y1) * rx + x1], d001 = f[((size_t)z1 * ry + y1) * rx + x2],
+                    d010 = f[((size_t)z1 * ry + y2) * rx + x1], d011 = f[((size_t)z1 * ry + y2) * rx + x2],
+                    d100 = f[((size_t)z2 * ry + y1) * rx + x1], d101 = f[((size_t)z2 * ry + y1) * rx + x2],
+                    d110 = f[((size_t)z2 * ry + y2) * rx + x1], d111 = f[((size_t)z2 * ry + y2) * rx + x2];
+        return ((d000 * _fx + d001 * fx) * _fy + (d010 * _fx + d011 * fx) * fy) * _fz +
+               ((d100 * _fx + d101 * fx) * _fy + (d110 * _fx + d111 * fx) * fy) * fz;
+    }
+
+    // AABB::rayIntersect of the density box (aabb.h:308-338)
+    bool clip(const Vec3 &o, const Vec3 &dir, Float &nearT, Float &farT) const {
+        nearT = -std::numeric_limits<Float>::infinity();
+        farT = std::numeric_limits<Float>::infinity();
+        for (int i = 0; i < 3; i++) {
+            const Float origin = o[i], minVal = bmin[i], maxVal = bmax[i];
+            if (dir[i] == 0) {
+                if (origin < minVal || origin > maxVal) return false;
+            } else {
+                const Float rcp = 1.0f / dir[i];
+                Float t1 = (minVal - origin) * rcp, t2 = (maxVal - origin) * rcp;
+                if (t1 > t2) std::swap(t1, t2);
+                nearT = std::max(t1, nearT);
+                farT = std::min(t2, farT);
+                if (!(nearT <= farT)) return false;
+            }
+        }
+        return true;
+    }
+
+    // heterogeneous.cpp:589-663, Woodcock branch. Ray interval [rmint, rmaxt].
+    bool sampleDistance(const Vec3 &o, const Vec3 &dir, Float rmint, Float rmaxt, MediumSample &mRec, Rng &rng) const {
+        mRec.pdfFailure = 1.0f;
+        mRec.pdfSuccess = 1.0f;
+        mRec.transmittance = Vec3(1.0f);
+        Float mint, maxt;
+        if (!clip(o, dir, mint, maxt)) return false;
+        mint = std::max(mint, rmint);
+        maxt = std::min(maxt, rmaxt);
+        Float t = mint, densityAtT = 0;
+        while (true) {
+            t -= std::log(1 - rng.next1D()) * invMaxDensity;
+            if (t >= maxt) break;
+            Vec3 p = o + dir * t;
+            densityAtT = lookup(p) * d.scale;
+            if (densityAtT * invMaxDensity > rng.next1D()) {
+                mRec.t = t;
+                mRec.p = p;
+                Vec3 albedo(d.albedo[0], d.albedo[1], d.albedo[2]);
+                mRec.sigmaS = albedo * densityAtT;
+                Float tr = densityAtT != 0.0f ? 1.0f / densityAtT : 0;
+                if (!std::isfinite(tr)) tr = 0;
+                mRec.transmittance = Vec3(tr);
+                return true;  // pdfSuccess == 1 > 0
+            }
+        }
+        return false;
+    }
+
+    // heterogeneous.cpp:546-587, Woodcock branch: 2 ratio-free tracking trials
+    Float evalTransmittance(const Vec3 &o, const Vec3 &dir, Float rmint, Float rmaxt, Rng &rng) const {
+        Float mint, maxt;
+        if (!clip(o, dir, mint, maxt)) return 1.0f;
+        mint = std::max(mint, rmint);
+        maxt = std::min(maxt, rmaxt);
+        const int nSamples = 2;
+        Float result = 0;
+        for (int i = 0; i < nSamples; ++i) {
+            Float t = mint;
+            while (true) {
+                t -= std::log(1 - rng.next1D()) * invMaxDensity;
+                if (t >= maxt) {
+                    result += 1;
+                    break;
+                }
+                Float dens = lookup(o + dir * t) * d.scale;
+                if (dens * invMaxDensity > rng.next1D()) break;
+            }
+        }
+        return result / nSamples;
+    }
+
+    // phase functions: wi = direction the light comes from (= -ray.d), wo = scattered direction
+    Float phaseEval(const Vec3 &wi, const Vec3 &wo) const {
+        if (d.phase_type == B200PG_PHASE_HG) {  // hg.cpp:103-106
+            const Float g = d.phase_g;
+            Float temp = 1.0f + g * g + 2.0f * g * dot(wi, wo);
+            return INV_FOURPI * (1 - g * g) / (temp * std::sqrt(temp));
+        }
+        return INV_FOURPI;  // isotropic.cpp:76-78
+    }
+    Vec3 phaseSample(const Vec3 &wi, const Vec2 &sample, Float &pdf) const {
+        Vec3 wo;
+        if (d.phase_type == B200PG_PHASE_HG) {  // hg.cpp:74-95
+            const Float g = d.phase_g;
+            Float cosTheta;
+            if (std::abs(g) < Epsilon) {
+                cosTheta = 1 - 2 * sample.x;
+            } else {
+                Float sqrTerm = (1 - g * g) / (1 - g + 2 * g * sample.x);
+                cosTheta = (1 + g * g - sqrTerm * sqrTerm) / (2 * g);
+            }
+            Float sinTheta = safe_sqrt(1.0f - cosTheta * cosTheta);
+            Float phi = 2 * PI_F * sample.y;
+            wo = Frame(-wi).toWorld(Vec3(sinTheta * std::cos(phi), sinTheta * std::sin(phi), cosTheta));
+        } else {
+            wo = squareToUniformSphere(sample);
+        }
+        pdf = phaseEval(wi, wo);
+        return wo;
     }
 };
 
