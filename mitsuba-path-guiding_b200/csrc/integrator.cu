@@ -36,6 +36,11 @@ void launchShadow(const DeviceScene &S, const ShadowQueue &Q, float4 *rad, const
                   bool count, cudaStream_t st);
 void launchShade(const ShadeArgs &A, cudaStream_t st);
 void launchFlush(const ShadeArgs &A, cudaStream_t st);
+// volpath.cu
+void launchShadeVol(const ShadeArgs &A, cudaStream_t st);
+void launchShadowVol(const DeviceScene &S, const ShadowQueue &Q, float4 *rad, const uint32_t *nPtr, uint32_t *work, Counters *C,
+                     cudaStream_t st);
+void launchGridLookup(const DeviceScene &S, int medium, const float *p, uint32_t n, float *out, cudaStream_t st);
 void launchFilmExport(const float4 *film, float *out, uint32_t n, int develop, cudaStream_t st);
 void launchSplat(const FilmRecord &F, float4 *film, const float4 *splatA, const float *splatB, uint32_t n, float maxComponentValue,
                  cudaStream_t st);
@@ -90,6 +95,7 @@ struct Integrator {
     PathBuffers bufA, bufB;
     DevBuf<float4> dHits, dShO, dShD, dShC;
     DevBuf<int32_t> dShMedium;
+    DevBuf<uint4> dShAux;
     DevBuf<float4> dSplatA;
     DevBuf<float> dSplatB;
     DevBuf<Counters> dCounters;
@@ -215,6 +221,7 @@ struct Integrator {
         if (n <= batchCapacity) return;
         bufA.alloc(n); bufB.alloc(n);
         dHits.alloc(n); dShO.alloc(n); dShD.alloc(n); dShC.alloc(n); dShMedium.alloc(n);
+        if (params.volumetric) dShAux.alloc(n);
         dSplatA.alloc(n); dSplatB.alloc(n);
         batchCapacity = n;
     }
@@ -249,7 +256,7 @@ struct Integrator {
         A.S = S;
         A.cfg = config();
         guide.configure(A);
-        A.shadow.o = dShO.p; A.shadow.d = dShD.p; A.shadow.c = dShC.p; A.shadow.medium = dShMedium.p;
+        A.shadow.o = dShO.p; A.shadow.d = dShD.p; A.shadow.c = dShC.p; A.shadow.medium = dShMedium.p; A.shadow.aux = dShAux.p;
         A.hits = dHits.p;
         A.C = dCounters.p;
         A.film = dFilm.p;
@@ -268,10 +275,13 @@ struct Integrator {
             A.next = next;
             A.bounce = b;
             t = spanBegin();
-            launchShade(A, stream);
+            if (params.volumetric) launchShadeVol(A, stream); else launchShade(A, stream);
             spanEnd(kTimeShade, t);
             t = spanBegin();
-            launchShadow(S, A.shadow, next.rad, &C->shadow[b], &C->shadowWork[b], C, countTraversal, stream);
+            if (params.volumetric)
+                launchShadowVol(S, A.shadow, next.rad, &C->shadow[b], &C->shadowWork[b], C, stream);
+            else
+                launchShadow(S, A.shadow, next.rad, &C->shadow[b], &C->shadowWork[b], C, countTraversal, stream);
             spanEnd(kTimeShadow, t);
             stats.kernel_launches += 3;
             std::swap(cur, next);
@@ -874,8 +884,17 @@ int b200pg_field_load(void *integ, const uint32_t *in, size_t n_words) {
     PG_END
 }
 int b200pg_k_grid_lookup(void *integ, int medium, const float *p, size_t n, float *out) {
-    (void)integ; (void)medium; (void)p; (void)n; (void)out;
-    return fail("medium kernels are not built yet");
+    PG_TRY(integ)
+    if (medium < 0 || medium >= (int)self->scene->media.size()) return fail("medium index out of range");
+    DevBuf<float> dP, dO;
+    dP.upload(p, 3 * n, self->stream);
+    dO.alloc(n);
+    launchGridLookup(self->S, medium, dP.p, (uint32_t)n, dO.p, self->stream);
+    CUDA_OK(cudaMemcpyAsync(out, dO.p, n * sizeof(float), cudaMemcpyDeviceToHost, self->stream));
+    CUDA_OK(cudaStreamSynchronize(self->stream));
+    CUDA_OK(cudaGetLastError());
+    self->stats.kernel_launches++;
+    PG_END
 }
 
 }  // extern "C"

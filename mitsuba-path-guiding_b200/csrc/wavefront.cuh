@@ -21,6 +21,7 @@ enum : uint32_t {
     kFlagPrevMedium = 1u << 12,  // last event was a medium scattering event
     kFlagNoTrace = 1u << 13,
     kFlagVertexClosed = 1u << 14,  // the last training vertex already has its L_k / distance
+    kFlagLook = 1u << 15,          // volumetric: the emitter look-up along the sampled ray is still pending
     kDepthMask = 0xFFu
 };
 
@@ -43,6 +44,7 @@ struct ShadowQueue {
     float4 *d;  // d.xyz, maxt
     float4 *c;  // contribution rgb, destination path index (bits)
     int32_t *medium;
+    uint4 *aux;  // volumetric: forked rng state lo/hi, pixel, interactions left
 };
 
 struct IntegratorConfig {

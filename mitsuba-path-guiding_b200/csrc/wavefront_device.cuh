@@ -1,0 +1,100 @@
+// wavefront_device.cuh -- device helpers shared by the shade kernels (kernels.cu, volpath.cu):
+// queue appends, counter reductions, path termination and training-sample emission.
+#pragma once
+#include "guiding_device.cuh"
+#include "wavefront.cuh"
+
+namespace pg {
+
+PG_DEV uint32_t laneId() { return threadIdx.x & 31u; }
+
+// Warp-aggregated append: returns the destination index for lanes with `pred`, one atomic per warp.
+PG_DEV uint32_t warpAppend(uint32_t *counter, bool pred) {
+    const unsigned mask = __ballot_sync(0xffffffffu, pred);
+    uint32_t base = 0;
+    if (laneId() == 0 && mask) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    return base + __popc(mask & ((1u << laneId()) - 1u));
+}
+
+// Block-aggregated append for two queues at once: ONE global atomic per block and queue instead of
+// one per warp (the per-warp version serialised ~130k same-address atomics per bounce at L2 and was
+// 35% of k_shade's stall samples, profiles/r01_v1_summary.txt). Must be called by all threads of the
+// block; `smem` holds 2*(warps+1) words.
+PG_DEV void blockAppend2(uint32_t *counterA, bool predA, uint32_t *counterB, bool predB, uint32_t *smem, uint32_t &idxA,
+                         uint32_t &idxB) {
+    const uint32_t warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
+    const unsigned maskA = __ballot_sync(0xffffffffu, predA), maskB = __ballot_sync(0xffffffffu, predB);
+    uint32_t *cntA = smem, *cntB = smem + nWarps + 1;
+    if (laneId() == 0) {
+        cntA[warp] = __popc(maskA);
+        cntB[warp] = __popc(maskB);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        uint32_t *cnt = threadIdx.x ? cntB : cntA;
+        uint32_t total = 0;
+        for (uint32_t w = 0; w < nWarps; ++w) {
+            const uint32_t c = cnt[w];
+            cnt[w] = total;  // exclusive prefix
+            total += c;
+        }
+        cnt[nWarps] = total ? atomicAdd(threadIdx.x ? counterB : counterA, total) : 0u;
+    }
+    __syncthreads();
+    idxA = cntA[nWarps] + cntA[warp] + __popc(maskA & ((1u << laneId()) - 1u));
+    idxB = cntB[nWarps] + cntB[warp] + __popc(maskB & ((1u << laneId()) - 1u));
+    __syncthreads();  // smem is reused by the next loop iteration
+}
+
+PG_DEV void warpAddU64(unsigned long long *counter, unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (laneId() == 0 && v) atomicAdd(counter, v);
+}
+
+// Training samples of a finished path: for every recorded vertex the incident-radiance estimate along the
+// sampled direction is everything the path gathered after the vertex divided by the throughput right after it;
+// sample weight = avg_rgb(estimate) / pdf. Called by whole warps; one atomic per warp reserves the output range.
+PG_DEV void emitTrainingSamples(const GuideDevice &G, bool finished, uint32_t slot, uint32_t vcount, float3 Lfinal) {
+    const uint32_t nMine = finished ? vcount : 0u;
+    uint32_t incl = nMine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)laneId() >= o) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    uint32_t base = 0;
+    if (laneId() == 31) base = atomicAdd(G.sCount, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    uint32_t dst = base + incl - nMine;
+    for (uint32_t v = 0; v < nMine; ++v, ++dst) {
+        if (dst >= G.sCapacity) break;
+        const size_t vi = (size_t)slot * G.maxVerts + v;
+        const float4 p = G.vPos[vi], d = G.vDir[vi], T = G.vThr[vi], Lk = G.vL[vi];
+        const float3 diff = Lfinal - f3(Lk.x, Lk.y, Lk.z);
+        const float ex = T.x > 0 ? diff.x / T.x : 0.0f, ey = T.y > 0 ? diff.y / T.y : 0.0f, ez = T.z > 0 ? diff.z / T.z : 0.0f;
+        float w = ((ex + ey + ez) * (1.0f / 3.0f)) / p.w;
+        if (!isfinite(w) || w < 0) w = 0.0f;
+        G.sPos[dst] = make_float4(p.x, p.y, p.z, w);
+        G.sDir[dst] = make_float4(d.x, d.y, d.z, p.w);
+        G.sDist[dst] = d.w;
+    }
+}
+
+// A terminated path leaves its final sample value in the splat buffer (indexed by the path's slot, i.e.
+// in pixel order); k_splat rasterises the whole batch afterwards with all lanes busy.
+PG_DEV void finishPath(const ShadeArgs &A, uint32_t slot, float4 pos4, float3 L) {
+    if (A.radianceOut) {
+        A.radianceOut[3 * (size_t)slot + 0] = L.x;
+        A.radianceOut[3 * (size_t)slot + 1] = L.y;
+        A.radianceOut[3 * (size_t)slot + 2] = L.z;
+    } else {
+        A.splatA[slot] = make_float4(pos4.x, pos4.y, L.x, L.y);
+        A.splatB[slot] = L.z;
+    }
+}
+
+}  // namespace pg

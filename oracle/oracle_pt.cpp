@@ -927,6 +927,14 @@ int orc_radiance(void *s, const B200pgIntegratorParams *P, const uint32_t *pixel
     return 0;
 }
 
+// GridDataSource::lookupFloat on a batch of points (gridvolume.cpp:337-388)
+int orc_grid_lookup(void *s, int medium, const float *p, size_t n, float *out) {
+    Scene *sc = (Scene *)s;
+    if (medium < 0 || medium >= (int)sc->media.size()) return -1;
+    for (size_t i = 0; i < n; ++i) out[i] = sc->media[medium].lookup(Vec3(p[3 * i], p[3 * i + 1], p[3 * i + 2]));
+    return 0;
+}
+
 int orc_film_splat(void *s, const float *pos, const float *rgb, size_t n, float *film /* H*W*5 */) {
     Scene *sc = (Scene *)s;
     ImageBlock blk;

@@ -37,6 +37,7 @@ class Oracle:
         L.orc_bsdf.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_size_t, fp, fp, fp, fp, fp, u32p]
         L.orc_radiance.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), u32p, u32p, C.c_size_t, fp, C.c_void_p, C.c_void_p]
         L.orc_film_splat.argtypes = [C.c_void_p, fp, fp, C.c_size_t, fp]
+        L.orc_grid_lookup.argtypes = [C.c_void_p, C.c_int, fp, C.c_size_t, fp]
         L.orc_render.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), C.c_int, C.c_int, C.c_int, C.c_int, fp,
                                  C.c_int, u64p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
         L.orc_field_create.restype = C.c_void_p
@@ -242,6 +243,12 @@ class OracleScene:
         out = np.zeros((pixel.shape[0], 3), np.float32)
         self.L.orc_radiance(self.h, C.byref(params), _u(pixel), _u(sample), pixel.shape[0], _f(out),
                             field.h if field is not None else None, sink.h if sink is not None else None)
+        return out
+
+    def grid_lookup(self, medium, p):
+        p = np.ascontiguousarray(p, np.float32)
+        out = np.zeros(p.shape[0], np.float32)
+        assert self.L.orc_grid_lookup(self.h, medium, _f(p), p.shape[0], _f(out)) == 0
         return out
 
     def film_splat(self, pos, rgb):
