@@ -274,6 +274,15 @@ int b200pg_k_film_splat(void *integ, const float *pos, const float *rgb, size_t 
 /* Medium: trilinear density lookups (p n*3 -> out n), see gridvolume.cpp:337-388. */
 int b200pg_k_grid_lookup(void *integ, int medium, const float *p, size_t n, float *out);
 
+/* Medium: free-flight sampling and transmittance along n rays (rays n*8 = o.xyz, mint, d.xyz, maxt), replacing
+ * HeterogeneousMedium::sampleDistance / evalTransmittance (heterogeneous.cpp:589-663, 546-587; Woodcock branch) and
+ * PhaseFunction::sample (hg.cpp:74-95, isotropic.cpp:62-74). Ray i draws from the stream (seed, pixel = i, sample = 0):
+ * first the distance, then the transmittance estimate, then one phase-function sample with wi = -d.
+ * out_t[i] = sampled distance (inf: left the medium), out_tr[i] = transmittance estimate (0, 0.5 or 1),
+ * out_wo (n*3) / out_pdf = sampled scattering direction and its pdf. */
+int b200pg_k_medium_sample(void *integ, int medium, const float *rays, size_t n, float *out_t, float *out_tr,
+                           float *out_wo, float *out_pdf);
+
 /* Guiding field kernels (vMF mixtures; this repo's own algorithm, oracle-pinned).
  * Field snapshot layout is documented in DESIGN.md. */
 /* pos n*3, dir n*3, u n*3 (lobe selection, u1, u2): out_pdf = pdf of dir, out_dir/out_spdf = sampled direction + pdf */

@@ -66,6 +66,7 @@ def lib():
     L.b200pg_k_radiance.argtypes = [C.c_void_p, u32p, u32p, C.c_size_t, fp]
     L.b200pg_k_film_splat.argtypes = [C.c_void_p, fp, fp, C.c_size_t]
     L.b200pg_k_grid_lookup.argtypes = [C.c_void_p, C.c_int, fp, C.c_size_t, fp]
+    L.b200pg_k_medium_sample.argtypes = [C.c_void_p, C.c_int, fp, C.c_size_t, fp, fp, fp, fp]
     L.b200pg_k_vmm_pdf_sample.argtypes = [C.c_void_p, fp, fp, fp, C.c_size_t, fp, fp, fp, u32p]
     L.b200pg_k_bin_samples.argtypes = [C.c_void_p, fp, C.c_size_t, u32p, u32p, u32p, u32p]
     L.b200pg_k_em_step.argtypes = [C.c_void_p, fp, fp, fp, fp, fp, C.c_size_t, C.c_int, fp]
@@ -336,3 +337,10 @@ class Integrator:
         out = np.zeros(p.shape[0], np.float32)
         _check(lib().b200pg_k_grid_lookup(self.h, medium, _f(p), p.shape[0], _f(out)))
         return out
+
+    def k_medium_sample(self, medium, rays):
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = rays.shape[0]
+        t, tr, wo, pdf = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros((n, 3), np.float32), np.zeros(n, np.float32)
+        _check(lib().b200pg_k_medium_sample(self.h, medium, _f(rays), n, _f(t), _f(tr), _f(wo), _f(pdf)))
+        return t, tr, wo, pdf

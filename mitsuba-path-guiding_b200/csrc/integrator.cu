@@ -41,6 +41,8 @@ void launchShadeVol(const ShadeArgs &A, cudaStream_t st);
 void launchShadowVol(const DeviceScene &S, const ShadowQueue &Q, float4 *rad, const uint32_t *nPtr, uint32_t *work, Counters *C,
                      cudaStream_t st);
 void launchGridLookup(const DeviceScene &S, int medium, const float *p, uint32_t n, float *out, cudaStream_t st);
+void launchMediumTest(const DeviceScene &S, int medium, const float4 *rays, uint32_t n, float *outT, float *outTr, float *outWo,
+                      float *outPdf, cudaStream_t st);
 void launchFilmExport(const float4 *film, float *out, uint32_t n, int develop, cudaStream_t st);
 void launchSplat(const FilmRecord &F, float4 *film, const float4 *splatA, const float *splatB, uint32_t n, float maxComponentValue,
                  cudaStream_t st);
@@ -891,6 +893,25 @@ int b200pg_k_grid_lookup(void *integ, int medium, const float *p, size_t n, floa
     dO.alloc(n);
     launchGridLookup(self->S, medium, dP.p, (uint32_t)n, dO.p, self->stream);
     CUDA_OK(cudaMemcpyAsync(out, dO.p, n * sizeof(float), cudaMemcpyDeviceToHost, self->stream));
+    CUDA_OK(cudaStreamSynchronize(self->stream));
+    CUDA_OK(cudaGetLastError());
+    self->stats.kernel_launches++;
+    PG_END
+}
+
+int b200pg_k_medium_sample(void *integ, int medium, const float *rays, size_t n, float *out_t, float *out_tr, float *out_wo,
+                           float *out_pdf) {
+    PG_TRY(integ)
+    if (medium < 0 || medium >= (int)self->scene->media.size()) return fail("medium index out of range");
+    DevBuf<float4> dR;
+    DevBuf<float> dT, dTr, dWo, dPdf;
+    dR.upload(reinterpret_cast<const float4 *>(rays), 2 * n, self->stream);
+    dT.alloc(n); dTr.alloc(n); dWo.alloc(3 * n); dPdf.alloc(n);
+    launchMediumTest(self->S, medium, dR.p, (uint32_t)n, dT.p, dTr.p, dWo.p, dPdf.p, self->stream);
+    CUDA_OK(cudaMemcpyAsync(out_t, dT.p, n * 4, cudaMemcpyDeviceToHost, self->stream));
+    CUDA_OK(cudaMemcpyAsync(out_tr, dTr.p, n * 4, cudaMemcpyDeviceToHost, self->stream));
+    CUDA_OK(cudaMemcpyAsync(out_wo, dWo.p, 3 * n * 4, cudaMemcpyDeviceToHost, self->stream));
+    CUDA_OK(cudaMemcpyAsync(out_pdf, dPdf.p, n * 4, cudaMemcpyDeviceToHost, self->stream));
     CUDA_OK(cudaStreamSynchronize(self->stream));
     CUDA_OK(cudaGetLastError());
     self->stats.kernel_launches++;

@@ -406,6 +406,29 @@ __global__ void __launch_bounds__(256) k_grid_lookup(DeviceScene S, int medium, 
         out[i] = gridLookup(S.media[medium], S.density, ld3(p + 3 * (size_t)i));
 }
 
+// b200pg_k_medium_sample: sampleDistance, evalTransmittance and one phase-function sample per ray
+__global__ void __launch_bounds__(128) k_medium_test(DeviceScene S, int medium, const float4 *__restrict__ rays, uint32_t n,
+                                                     float *__restrict__ outT, float *__restrict__ outTr, float *__restrict__ outWo,
+                                                     float *__restrict__ outPdf) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 ro = rays[2 * i], rd = rays[2 * i + 1];
+        const float3 o = f3(ro.x, ro.y, ro.z), d = f3(rd.x, rd.y, rd.z);
+        const MediumRecord &M = S.media[medium];
+        Rng rng;
+        rng.init(S.seed, i, 0);
+        MediumSample mRec;
+        const bool ok = mediumSampleDistance(M, S.density, o, d, ro.w, rd.w, mRec, rng);
+        outT[i] = ok ? mRec.t : kInf;
+        outTr[i] = mediumTransmittance(M, S.density, o, d, ro.w, rd.w, rng);
+        float pdf;
+        const float3 wo = phaseSample(M, -d, rng.next2D(), pdf);
+        outWo[3 * (size_t)i] = wo.x;
+        outWo[3 * (size_t)i + 1] = wo.y;
+        outWo[3 * (size_t)i + 2] = wo.z;
+        outPdf[i] = pdf;
+    }
+}
+
 template <typename K>
 static int volGrid(K kernel, int block) {
     int dev = 0, sms = 0, perSM = 0;
@@ -429,6 +452,12 @@ void launchShadowVol(const DeviceScene &S, const ShadowQueue &Q, float4 *rad, co
 void launchGridLookup(const DeviceScene &S, int medium, const float *p, uint32_t n, float *out, cudaStream_t st) {
     static int grid = volGrid(k_grid_lookup, 256);
     k_grid_lookup<<<grid, 256, 0, st>>>(S, medium, p, n, out);
+}
+
+void launchMediumTest(const DeviceScene &S, int medium, const float4 *rays, uint32_t n, float *outT, float *outTr, float *outWo,
+                      float *outPdf, cudaStream_t st) {
+    static int grid = volGrid(k_medium_test, 128);
+    k_medium_test<<<grid, 128, 0, st>>>(S, medium, rays, n, outT, outTr, outWo, outPdf);
 }
 
 }  // namespace pg

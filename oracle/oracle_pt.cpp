@@ -935,6 +935,46 @@ int orc_grid_lookup(void *s, int medium, const float *p, size_t n, float *out) {
     return 0;
 }
 
+// sampleDistance, evalTransmittance and one phase sample per ray; ray i draws from the stream (seed, pixel = i, sample = 0)
+int orc_medium_sample(void *s, int medium, const float *rays, size_t n, float *out_t, float *out_tr, float *out_wo, float *out_pdf) {
+    Scene *sc = (Scene *)s;
+    if (medium < 0 || medium >= (int)sc->media.size()) return -1;
+    const Medium &M = sc->media[medium];
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)n; ++i) {
+        const float *r = rays + 8 * i;
+        Vec3 o(r[0], r[1], r[2]), d(r[4], r[5], r[6]);
+        Rng rng;
+        rng.init(sc->seed, (uint32_t)i, 0);
+        MediumSample mRec;
+        bool ok = M.sampleDistance(o, d, r[3], r[7], mRec, rng);
+        out_t[i] = ok ? mRec.t : std::numeric_limits<Float>::infinity();
+        out_tr[i] = M.evalTransmittance(o, d, r[3], r[7], rng);
+        Float pdf;
+        Vec3 wo = M.phaseSample(-d, rng.next2D(), pdf);
+        out_wo[3 * i] = wo.x; out_wo[3 * i + 1] = wo.y; out_wo[3 * i + 2] = wo.z;
+        out_pdf[i] = pdf;
+    }
+    return 0;
+}
+
+// phase function eval for (wi, wo) pairs and sample for (wi, u) (hg.cpp:74-110, isotropic.cpp:62-78)
+int orc_phase(void *s, int medium, const float *wi, const float *wo, const float *u, size_t n, float *out_eval, float *out_wo,
+              float *out_pdf) {
+    Scene *sc = (Scene *)s;
+    if (medium < 0 || medium >= (int)sc->media.size()) return -1;
+    const Medium &M = sc->media[medium];
+    for (size_t i = 0; i < n; ++i) {
+        Vec3 vi(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), vo(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
+        out_eval[i] = M.phaseEval(vi, vo);
+        Float pdf;
+        Vec3 w = M.phaseSample(vi, Vec2(u[2 * i], u[2 * i + 1]), pdf);
+        out_wo[3 * i] = w.x; out_wo[3 * i + 1] = w.y; out_wo[3 * i + 2] = w.z;
+        out_pdf[i] = pdf;
+    }
+    return 0;
+}
+
 int orc_film_splat(void *s, const float *pos, const float *rgb, size_t n, float *film /* H*W*5 */) {
     Scene *sc = (Scene *)s;
     ImageBlock blk;

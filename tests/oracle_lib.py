@@ -38,6 +38,8 @@ class Oracle:
         L.orc_radiance.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), u32p, u32p, C.c_size_t, fp, C.c_void_p, C.c_void_p]
         L.orc_film_splat.argtypes = [C.c_void_p, fp, fp, C.c_size_t, fp]
         L.orc_grid_lookup.argtypes = [C.c_void_p, C.c_int, fp, C.c_size_t, fp]
+        L.orc_medium_sample.argtypes = [C.c_void_p, C.c_int, fp, C.c_size_t, fp, fp, fp, fp]
+        L.orc_phase.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_size_t, fp, fp, fp]
         L.orc_render.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), C.c_int, C.c_int, C.c_int, C.c_int, fp,
                                  C.c_int, u64p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
         L.orc_field_create.restype = C.c_void_p
@@ -250,6 +252,20 @@ class OracleScene:
         out = np.zeros(p.shape[0], np.float32)
         assert self.L.orc_grid_lookup(self.h, medium, _f(p), p.shape[0], _f(out)) == 0
         return out
+
+    def medium_sample(self, medium, rays):
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = rays.shape[0]
+        t, tr, wo, pdf = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros((n, 3), np.float32), np.zeros(n, np.float32)
+        assert self.L.orc_medium_sample(self.h, medium, _f(rays), n, _f(t), _f(tr), _f(wo), _f(pdf)) == 0
+        return t, tr, wo, pdf
+
+    def phase(self, medium, wi, wo, u):
+        wi, wo, u = (np.ascontiguousarray(a, np.float32) for a in (wi, wo, u))
+        n = wi.shape[0]
+        ev, swo, pdf = np.zeros(n, np.float32), np.zeros((n, 3), np.float32), np.zeros(n, np.float32)
+        assert self.L.orc_phase(self.h, medium, _f(wi), _f(wo), _f(u), n, _f(ev), _f(swo), _f(pdf)) == 0
+        return ev, swo, pdf
 
     def film_splat(self, pos, rgb):
         pos = np.ascontiguousarray(pos, np.float32)

@@ -138,7 +138,10 @@ def test_bsdf_eval_pdf_sample(pkg, api, oracle):
         if not loose:  # the bulk agrees to a few ulp; the tail is acos/atan2/tan conditioning near grazing wi
             assert np.quantile(dwo, 0.99) <= 1e-5 and np.quantile(dwo, 0.999) <= 5e-5, (name, "dwo q99.9", float(np.quantile(dwo, 0.999)))
         werr = (np.abs(o["weight"][ok] - g["weight"][ok]) / np.maximum(np.abs(o["weight"][ok]), 1e-2)).max(1)
-        assert np.quantile(werr, 0.999) <= rtol and werr.max() <= 100 * rtol, (name, "werr q99.9/max", float(np.quantile(werr, 0.999)), float(werr.max()))
+        # grazing outgoing directions: the weight carries cos(theta_o), whose relative error is |d wo.z| / |wo.z|
+        # (wo itself agrees to dtol); that conditioning term is added to the cap on the tail
+        cond = 2 * np.abs(o["wo"][ok][:, 2] - g["wo"][ok][:, 2]) / np.maximum(np.abs(o["wo"][ok][:, 2]), 1e-6)
+        assert np.quantile(werr, 0.999) <= rtol and (werr <= 100 * rtol + cond).all(), (name, "werr q99.9/max", float(np.quantile(werr, 0.999)), float(werr.max()))
         frac_bad = (np.abs(o["spdf"][ok] - g["spdf"][ok]) > 10 * rtol * np.maximum(np.abs(o["spdf"][ok]), 1e-2)).mean()
         assert frac_bad < 1e-3, (name, frac_bad)
 
