@@ -2,9 +2,9 @@
 //   k_guide_cells      sample position -> cell index (kd-tree walk)
 //   k_radix_*          hand-written stable LSD radix sort (8-bit digits) of (cell, sample index) pairs = binning;
 //                      bit-exact against the oracle's stable counting sort (oracle_guiding.h: guideBin)
-//   k_estep            weighted-EM E-step, warp-cooperative: lane k evaluates lobe k of the cell's mixture,
-//                      responsibilities are normalised with a warp reduction, every lane keeps the sufficient
-//                      statistics of its own lobe in registers (Kahan-compensated)
+//   k_estep            weighted-EM E-step, one warp per chunk of one cell's samples: lobes staged in shared memory,
+//                      lane = sample, per-lane sufficient statistics in registers, butterfly reduction per chunk
+//   k_cell_moments     per-chunk position moments (split statistics), once per training update
 //   k_reduce_partials  per-cell sum of the chunk partials in a fixed order (deterministic)
 //   k_mstep            M-step with decayed running statistics and MAP priors, one warp per cell
 //   k_guide_query      pdf / sample of the field at arbitrary points (b200pg_k_vmm_pdf_sample)
@@ -21,7 +21,7 @@ namespace pg {
 static constexpr int kSortThreads = 256;
 static constexpr int kSortRounds = 8;
 static constexpr int kSortTile = kSortThreads * kSortRounds;
-static constexpr int kChunk = 4096;  // samples per E-step work item
+static constexpr int kChunk = 2048;  // samples per E-step work item (one warp)
 
 __device__ __forceinline__ uint32_t lane() { return threadIdx.x & 31u; }
 
@@ -158,85 +158,108 @@ __global__ void __launch_bounds__(256) k_cell_starts(const uint32_t *__restrict_
 }
 
 // ---- E-step ------------------------------------------------------------------------------------------
-struct Kahan {
-    float s = 0, c = 0;
-    __device__ __forceinline__ void add(float v) {
-        const float y = v - c;
-        const float t = s + y;
-        c = (t - s) - y;
-        s = t;
-    }
-};
-
-// KP = lobes per sample group (power of two >= K): a warp evaluates 32 / KP samples at a time, lane (l % KP) owns
-// lobe (l % KP) of sample group (l / KP). Samples were gathered into sorted order beforehand, so a warp walks a
-// contiguous range of 16-byte records. Every lane keeps the statistics of its lobe (and group) in registers.
-template <int KP>
-__global__ void __launch_bounds__(256) k_estep(GuideDevice G, const float4 *__restrict__ sPos, const float4 *__restrict__ sDir,
+// One warp per work item (a chunk of <= kChunk consecutive samples of ONE cell, gathered into sorted order
+// beforehand); lane = sample. The cell's K lobes sit in shared memory (broadcast reads), every lane evaluates all K
+// lobes for its sample (same summation order as the oracle: total += p_k, k ascending) and keeps the 4 K
+// sufficient statistics of its samples in registers; one butterfly reduction per work item at the end.
+// ~9 issued instructions per sample and lobe-free shuffles in the inner loop, against ~35 for the earlier
+// lane-per-lobe formulation (profiles/r01_v3_summary.txt).
+template <int KMAX>
+__global__ void __launch_bounds__(128) k_estep(GuideDevice G, const float4 *__restrict__ sPos, const float4 *__restrict__ sDir,
                                                const uint4 *__restrict__ work, uint32_t nWork, float *__restrict__ partials,
                                                int stride) {
-    constexpr int kGroups = 32 / KP;
-    __shared__ float red[8 * kGroups][kGuideMaxK * 4 + 8];
-    const uint32_t warp = threadIdx.x >> 5, k = lane() % KP, grp = lane() / KP;
+    __shared__ float4 sLobe[4][KMAX * 2];
+    const uint32_t warp = threadIdx.x >> 5, ln = lane();
     const int K = G.K;
-    for (uint32_t w = blockIdx.x; w < nWork; w += gridDim.x) {
+    float4 *myLobes = sLobe[warp];
+    for (uint32_t w = blockIdx.x * 4 + warp; w < nWork; w += gridDim.x * 4) {
         const uint4 item = work[w];
-        float4 la = make_float4(0, 0, 0, 0), lb = make_float4(0, 0, 0, 0);
-        if ((int)k < K) {
-            la = __ldg(G.lobes + ((size_t)item.x * K + k) * 3);
-            lb = __ldg(G.lobes + ((size_t)item.x * K + k) * 3 + 1);
-        }
-        Kahan S, Rx, Ry, Rz, cn, cW, p1x, p1y, p1z, p2x, p2y, p2z;
-        // warp `warp` owns the contiguous slice [b, e) of the chunk
-        const uint32_t len = item.z - item.y, per = (len + 7) / 8;
-        const uint32_t b = item.y + warp * per, e = min(b + per, item.z);
-        for (uint32_t j0 = b; j0 < e; j0 += kGroups) {
-            const uint32_t j = j0 + grp;
-            const bool have = j < e;
-            float4 p = make_float4(0, 0, 0, 0), d = make_float4(0, 0, 1, 1);
-            if (have) {
-                p = sPos[j];
-                d = sDir[j];
-                cn.add(1.0f);
-                p1x.add(p.x); p1y.add(p.y); p1z.add(p.z);
-                p2x.add(p.x * p.x); p2y.add(p.y * p.y); p2z.add(p.z * p.z);
-            }
-            const float sw = p.w;
-            const bool good = have && sw > 0 && isfinite(sw);
-            float pk = 0.0f;
-            if (good && (int)k < K) {
-                const float c = la.y * d.x + la.z * d.y + la.w * d.z;
-                pk = la.x * lb.y * expf(lb.x * (c - 1.0f));
-            }
-            float total = pk;
+        __syncwarp();
+        for (int k = (int)ln; k < 2 * K; k += 32) myLobes[k] = __ldg(G.lobes + (size_t)item.x * K * 2 + k);
+        __syncwarp();
+        float S[KMAX], Rx[KMAX], Ry[KMAX], Rz[KMAX];
 #pragma unroll
-            for (int o = KP / 2; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-            if (!good || !(total > 0) || !isfinite(total)) continue;
-            cW.add(sw);
-            const float g = sw * (pk * (1.0f / total));
-            S.add(g);
-            Rx.add(g * d.x);
-            Ry.add(g * d.y);
-            Rz.add(g * d.z);
+        for (int k = 0; k < KMAX; ++k) S[k] = Rx[k] = Ry[k] = Rz[k] = 0.0f;
+        float cW = 0.0f;
+        for (uint32_t j = item.y + ln; j < item.z; j += 32) {
+            const float4 p = sPos[j], d = sDir[j];
+            const float sw = p.w;
+            if (!(sw > 0) || !isfinite(sw)) continue;
+            float pk[KMAX];
+            float total = 0.0f;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                pk[k] = 0.0f;
+                if (k < K) {
+                    const float4 la = myLobes[2 * k], lb = myLobes[2 * k + 1];
+                    const float c = la.y * d.x + la.z * d.y + la.w * d.z;
+                    pk[k] = la.x * lb.y * expf(lb.x * (c - 1.0f));
+                    total += pk[k];
+                }
+            }
+            if (!(total > 0) || !isfinite(total)) continue;
+            cW += sw;
+            const float inv = 1.0f / total;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                if (k < K) {
+                    const float g = sw * (pk[k] * inv);
+                    S[k] += g;
+                    Rx[k] += g * d.x;
+                    Ry[k] += g * d.y;
+                    Rz[k] += g * d.z;
+                }
+            }
         }
-        float *r = red[warp * kGroups + grp];
-        if ((int)k < K) {
-            r[4 * k + 0] = S.s;
-            r[4 * k + 1] = Rx.s;
-            r[4 * k + 2] = Ry.s;
-            r[4 * k + 3] = Rz.s;
+        // butterfly reduction over the 32 lanes (fixed order -> deterministic); lane 0 holds the sums
+        float *out = partials + (size_t)w * stride;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            if (k < K) {
+                float a = S[k], b = Rx[k], c = Ry[k], e = Rz[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    a += __shfl_xor_sync(0xffffffffu, a, o);
+                    b += __shfl_xor_sync(0xffffffffu, b, o);
+                    c += __shfl_xor_sync(0xffffffffu, c, o);
+                    e += __shfl_xor_sync(0xffffffffu, e, o);
+                }
+                if (ln == 0) *reinterpret_cast<float4 *>(out + 4 * k) = make_float4(a, b, c, e);
+            }
         }
-        if (k == 0) {
-            float *c = r + 4 * K;
-            c[0] = cn.s; c[1] = cW.s; c[2] = p1x.s; c[3] = p1y.s; c[4] = p1z.s; c[5] = p2x.s; c[6] = p2y.s; c[7] = p2z.s;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cW += __shfl_xor_sync(0xffffffffu, cW, o);
+        if (ln == 0) out[4 * K + 1] = cW;
+    }
+}
+
+// Per-chunk position moments (count, sum x, sum x^2) -- independent of the mixtures, so computed once per training
+// update, not once per EM iteration. Written into the cell-statistics slots of the partials buffer that k_estep
+// leaves alone (slot 1, the weight sum, is k_estep's).
+__global__ void __launch_bounds__(128) k_cell_moments(const float4 *__restrict__ sPos, const uint4 *__restrict__ work, uint32_t nWork,
+                                                      float *__restrict__ partials, int stride, int K) {
+    const uint32_t warp = threadIdx.x >> 5, ln = lane();
+    for (uint32_t w = blockIdx.x * 4 + warp; w < nWork; w += gridDim.x * 4) {
+        const uint4 item = work[w];
+        float m[6] = {0, 0, 0, 0, 0, 0};
+        for (uint32_t j = item.y + ln; j < item.z; j += 32) {
+            const float4 p = sPos[j];
+            m[0] += p.x; m[1] += p.y; m[2] += p.z;
+            m[3] += p.x * p.x; m[4] += p.y * p.y; m[5] += p.z * p.z;
         }
-        __syncthreads();
-        for (int el = threadIdx.x; el < stride; el += blockDim.x) {
-            double acc = 0.0;
-            for (int ww = 0; ww < 8 * kGroups; ++ww) acc += (double)red[ww][el];
-            partials[(size_t)w * stride + el] = (float)acc;
+        double acc[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            acc[i] = (double)m[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
         }
-        __syncthreads();
+        if (ln == 0) {
+            float *c = partials + (size_t)w * stride + 4 * K;
+            c[0] = (float)(item.z - item.y);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) c[2 + i] = (float)acc[i];
+        }
     }
 }
 
@@ -263,8 +286,8 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const float *__restrict
 }
 
 // ---- M-step: one warp per cell, lane k = lobe k ----------------------------------------------------------
-__global__ void __launch_bounds__(256) k_mstep(float4 *__restrict__ lobes, const float *__restrict__ stats, uint32_t nCells, int K,
-                                               int stride, int commit) {
+__global__ void __launch_bounds__(256) k_mstep(float4 *__restrict__ lobes, float4 *__restrict__ lobeStats, const float *__restrict__ stats,
+                                               uint32_t nCells, int K, int stride, int commit) {
     const uint32_t warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = (gridDim.x * blockDim.x) >> 5;
     const int k = (int)lane();
     for (uint32_t c = warpGlobal; c < nCells; c += nWarps) {
@@ -272,10 +295,10 @@ __global__ void __launch_bounds__(256) k_mstep(float4 *__restrict__ lobes, const
         float4 a = make_float4(0, 0, 0, 0), b = a, s = a;
         float S = 0, R0 = 0, R1 = 0, R2 = 0;
         if (k < K) {
-            float4 *L = lobes + ((size_t)c * K + k) * 3;
+            const float4 *L = lobes + ((size_t)c * K + k) * 2;
             a = L[0];
             b = L[1];
-            s = L[2];
+            s = lobeStats[(size_t)c * K + k];
             S = kGuideDecay * s.x + st[4 * k];
             R0 = kGuideDecay * s.y + st[4 * k + 1];
             R1 = kGuideDecay * s.z + st[4 * k + 2];
@@ -303,10 +326,10 @@ __global__ void __launch_bounds__(256) k_mstep(float4 *__restrict__ lobes, const
                 b.z = expf(-2.0f * b.x);
                 b.y = b.x / (2 * kPi * (1.0f - b.z));
             }
-            float4 *L = lobes + ((size_t)c * K + k) * 3;
+            float4 *L = lobes + ((size_t)c * K + k) * 2;
             L[0] = a;
             L[1] = b;
-            if (commit) L[2] = make_float4(S, R0, R1, R2);
+            if (commit) lobeStats[(size_t)c * K + k] = make_float4(S, R0, R1, R2);
         }
     }
 }
@@ -396,7 +419,15 @@ void GuidingHost::resetField(const float *, const float *) {
 
 void GuidingHost::uploadField() {
     dNodes.upload(reinterpret_cast<const uint4 *>(nodes.data()), nodes.size(), stream);
-    dLobes.upload(reinterpret_cast<const float4 *>(lobes.data()), lobes.size() * 3, stream);
+    // device layout: query data (2 x float4 per lobe) and running statistics (1 x float4 per lobe) in separate arrays
+    stageQuery.resize(lobes.size() * 8);
+    stageStats.resize(lobes.size() * 4);
+    for (size_t i = 0; i < lobes.size(); ++i) {
+        std::memcpy(&stageQuery[8 * i], &lobes[i].weight, 32);
+        std::memcpy(&stageStats[4 * i], &lobes[i].statS, 16);
+    }
+    dLobes.upload(reinterpret_cast<const float4 *>(stageQuery.data()), lobes.size() * 2, stream);
+    dLobeStats.upload(reinterpret_cast<const float4 *>(stageStats.data()), lobes.size(), stream);
     CUDA_OK(cudaStreamSynchronize(stream));
 }
 
@@ -414,6 +445,7 @@ void GuidingHost::configure(ShadeArgs &A) {
     std::memset(&G, 0, sizeof(G));
     G.nodes = dNodes.p;
     G.lobes = dLobes.p;
+    G.lobeStats = dLobeStats.p;
     G.K = K;
     G.alpha = alpha;
     G.enabled = active && sampling && trained;
@@ -433,6 +465,7 @@ void GuidingHost::sortByCell(uint32_t n) {
     std::memset(&G, 0, sizeof(G));
     G.nodes = dNodes.p;
     G.lobes = dLobes.p;
+    G.lobeStats = dLobeStats.p;
     G.K = K;
     k_guide_cells<<<gridFor(n, 256), 256, 0, stream>>>(G, dSPos.p, n, dKeysA.p, dValsA.p);
     launches++;
@@ -489,6 +522,13 @@ void GuidingHost::buildWork() {
     }
     dPartials.alloc((size_t)std::max(nWork, 1u) * statsStride());
     dStats.alloc((size_t)numCells() * statsStride());
+    if (nWork) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        k_cell_moments<<<std::min<uint32_t>((nWork + 3) / 4, (uint32_t)sms * 16), 128, 0, stream>>>(dSortPos.p, dWork.p, nWork, dPartials.p,
+                                                                                                   (int)statsStride(), K);
+        launches++;
+    }
 }
 
 void GuidingHost::begin() {
@@ -527,18 +567,19 @@ void GuidingHost::accumulate() {
     GuideDevice G;
     std::memset(&G, 0, sizeof(G));
     G.lobes = dLobes.p;
+    G.lobeStats = dLobeStats.p;
     G.K = K;
     const int stride = (int)statsStride();
     if (nWork) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-        const uint32_t grid = std::min<uint32_t>(nWork, (uint32_t)sms * 4);
+        const uint32_t grid = std::min<uint32_t>((nWork + 3) / 4, (uint32_t)sms * 8);
         if (K <= 8)
-            k_estep<8><<<grid, 256, 0, stream>>>(G, dSortPos.p, dSortDir.p, dWork.p, nWork, dPartials.p, stride);
+            k_estep<8><<<grid, 128, 0, stream>>>(G, dSortPos.p, dSortDir.p, dWork.p, nWork, dPartials.p, stride);
         else if (K <= 16)
-            k_estep<16><<<grid, 256, 0, stream>>>(G, dSortPos.p, dSortDir.p, dWork.p, nWork, dPartials.p, stride);
+            k_estep<16><<<grid, 128, 0, stream>>>(G, dSortPos.p, dSortDir.p, dWork.p, nWork, dPartials.p, stride);
         else
-            k_estep<32><<<grid, 256, 0, stream>>>(G, dSortPos.p, dSortDir.p, dWork.p, nWork, dPartials.p, stride);
+            k_estep<32><<<grid, 128, 0, stream>>>(G, dSortPos.p, dSortDir.p, dWork.p, nWork, dPartials.p, stride);
         launches++;
     }
     k_reduce_partials<<<gridFor((size_t)numCells() * stride, 256), 256, 0, stream>>>(dPartials.p, dCellCount.p, numCells(), stride,
@@ -548,7 +589,7 @@ void GuidingHost::accumulate() {
 
 void GuidingHost::update(bool commit) {
     const int stride = (int)statsStride();
-    k_mstep<<<gridFor((size_t)numCells() * 32, 256), 256, 0, stream>>>(dLobes.p, dStats.p, numCells(), K, stride, commit ? 1 : 0);
+    k_mstep<<<gridFor((size_t)numCells() * 32, 256), 256, 0, stream>>>(dLobes.p, dLobeStats.p, dStats.p, numCells(), K, stride, commit ? 1 : 0);
     launches++;
 }
 
@@ -557,10 +598,17 @@ void GuidingHost::end() {
     // headers, split over-full cells (same rule and arithmetic as oracle_guiding.h: guideSplit) and re-upload
     const size_t stride = statsStride();
     std::vector<float> stats((size_t)numCells() * stride);
-    CUDA_OK(cudaMemcpyAsync(lobes.data(), dLobes.p, lobes.size() * sizeof(GuideLobeHost), cudaMemcpyDeviceToHost, stream));
+    stageQuery.resize(lobes.size() * 8);
+    stageStats.resize(lobes.size() * 4);
+    CUDA_OK(cudaMemcpyAsync(stageQuery.data(), dLobes.p, lobes.size() * 32, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaMemcpyAsync(stageStats.data(), dLobeStats.p, lobes.size() * 16, cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaMemcpyAsync(stats.data(), dStats.p, stats.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
     CUDA_OK(cudaGetLastError());
+    for (size_t i = 0; i < lobes.size(); ++i) {
+        std::memcpy(&lobes[i].weight, &stageQuery[8 * i], 32);
+        std::memcpy(&lobes[i].statS, &stageStats[4 * i], 16);
+    }
     const uint32_t nc0 = numCells();
     for (uint32_t c = 0; c < nc0; ++c) {
         const float *cs = &stats[stride * c + (size_t)K * 4];
@@ -627,6 +675,7 @@ void GuidingHost::query(const float *pos, const float *dir, const float *u, size
     std::memset(&G, 0, sizeof(G));
     G.nodes = dNodes.p;
     G.lobes = dLobes.p;
+    G.lobeStats = dLobeStats.p;
     G.K = K;
     if (n) k_guide_query<<<gridFor(n, 256), 256, 0, stream>>>(G, dP.p, dD.p, dU.p, (uint32_t)n, oP.p, oD.p, oS.p, oC.p);
     launches++;

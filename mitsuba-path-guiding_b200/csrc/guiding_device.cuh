@@ -5,7 +5,8 @@
 // and stated a second time on the CPU in oracle/oracle_guiding.h, which the parity tests compare against.
 //
 //   field   = spatial kd-tree over the scene box; leaves ("cells") hold a mixture of K von Mises-Fisher lobes
-//   query   = tree walk (16-byte nodes) -> cell; pdf / sample over the cell's K lobes (3 x float4 each)
+//   query   = tree walk (16-byte nodes) -> cell; pdf / sample over the cell's K lobes (2 x float4 each, 32 B;
+//             the running EM statistics live in a separate array so that queries do not drag them through L1/L2)
 //   use     = one-sample MIS between the BSDF and the mixture at every vertex with a smooth BSDF
 #pragma once
 #include "device_math.cuh"
@@ -21,7 +22,8 @@ static constexpr float kGuideInitKappa = 5.0f;
 
 struct GuideDevice {
     const uint4 *nodes;    // {axis (3 = leaf), split bits, left | cell, 0}
-    const float4 *lobes;   // cells * K * 3: {pi, mu.xyz} {kappa, norm, exp(-2 kappa), 0} {S, R.xyz}
+    const float4 *lobes;   // cells * K * 2: {pi, mu.xyz} {kappa, norm, exp(-2 kappa), 0}
+    const float4 *lobeStats;  // cells * K: running statistics {S, R.xyz} (training only)
     int K;
     int enabled;           // sample from the field in the shade stage
     int record;            // record training vertices
@@ -49,27 +51,47 @@ PG_DEV uint32_t guideLookup(const GuideDevice &G, float3 p) {
     }
 }
 
+PG_DEV float guideLobeTerm(float4 a, float4 b, float3 w) {
+    const float c = a.y * w.x + a.z * w.y + a.w * w.z;
+    return a.x * b.y * expf(b.x * (c - 1.0f));
+}
+
 PG_DEV float guidePdf(const GuideDevice &G, uint32_t cell, float3 w) {
-    const float4 *L = G.lobes + (size_t)cell * G.K * 3;
+    const float4 *L = G.lobes + (size_t)cell * G.K * 2;
     float s = 0;
+#pragma unroll 4
     for (int k = 0; k < G.K; ++k) {
-        const float4 a = __ldg(L + 3 * k), b = __ldg(L + 3 * k + 1);
-        const float c = a.y * w.x + a.z * w.y + a.w * w.z;
-        s += a.x * b.y * expf(b.x * (c - 1.0f));
+        const float4 a = __ldg(L + 2 * k), b = __ldg(L + 2 * k + 1);
+        s += guideLobeTerm(a, b, w);
     }
     return s;
 }
 
+// pdf of two directions in one pass over the cell's lobes (the NEE direction and the sampled direction of a
+// guided vertex): every lobe is fetched once. Same summation order as guidePdf.
+PG_DEV void guidePdf2(const GuideDevice &G, uint32_t cell, float3 w1, float3 w2, float &p1, float &p2) {
+    const float4 *L = G.lobes + (size_t)cell * G.K * 2;
+    float s1 = 0, s2 = 0;
+#pragma unroll 4
+    for (int k = 0; k < G.K; ++k) {
+        const float4 a = __ldg(L + 2 * k), b = __ldg(L + 2 * k + 1);
+        s1 += guideLobeTerm(a, b, w1);
+        s2 += guideLobeTerm(a, b, w2);
+    }
+    p1 = s1;
+    p2 = s2;
+}
+
 PG_DEV float3 guideSample(const GuideDevice &G, uint32_t cell, float u0, float u1, float u2) {
-    const float4 *L = G.lobes + (size_t)cell * G.K * 3;
+    const float4 *L = G.lobes + (size_t)cell * G.K * 2;
     int k = 0;
     float4 a = __ldg(L);
     while (k < G.K - 1 && u0 >= a.x) {
         u0 -= a.x;
         ++k;
-        a = __ldg(L + 3 * k);
+        a = __ldg(L + 2 * k);
     }
-    const float4 b = __ldg(L + 3 * k + 1);
+    const float4 b = __ldg(L + 2 * k + 1);
     float cosT = 1.0f + logf(u1 + (1.0f - u1) * b.z) / b.x;
     cosT = fminf(1.0f, fmaxf(-1.0f, cosT));
     const float sinT = safeSqrt(1.0f - cosT * cosT);

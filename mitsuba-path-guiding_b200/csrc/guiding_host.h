@@ -53,7 +53,8 @@ struct GuidingHost {
     std::vector<GuideLobeHost> lobes;
     std::vector<GuideCellHost> cells;
     DevBuf<uint4> dNodes;
-    DevBuf<float4> dLobes;
+    DevBuf<float4> dLobes, dLobeStats;
+    std::vector<float> stageQuery, stageStats;  // host staging of the two device lobe arrays
 
     // training-vertex records and samples
     DevBuf<float4> dVPos, dVDir, dVThr, dVL;

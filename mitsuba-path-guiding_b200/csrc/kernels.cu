@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(128) k_trace_rays(DeviceScene S, const float4 
 // Shade stage (surface path tracer, ProgressiveMIPathTracer::Li)
 // ------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(kShadeThreads) k_shade(ShadeArgs A) {
+__global__ void __launch_bounds__(kShadeThreads, 5) k_shade(ShadeArgs A) {
     const DeviceScene &S = A.S;
     const IntegratorConfig &cfg = A.cfg;
     const uint32_t n = A.C->queue[A.bounce];
@@ -339,6 +339,11 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(ShadeArgs A) {
                     // guided vertex: smooth BSDF only -- delta lobes are never guided
                     const bool guided = A.G.enabled && (btype & kSmooth);
                     const uint32_t gcell = guided ? guideLookup(A.G, its.p) : 0u;
+                    // NEE (:191-219). At a guided vertex the MIS weight needs the mixture pdf of the light direction; it is
+                    // evaluated together with the pdf of the sampled direction in ONE pass over the cell's lobes below.
+                    bool neePending = false;
+                    float neeBsdfPdf = 0.0f, neeLightPdf = 0.0f;
+                    float3 neeContrib = f3(0.0f);
                     if (cfg.useNee && (btype & kSmooth)) {
                         const float3 refN = (btype & (kTransmission | kBackSide)) == 0 ? its.sh.n : f3(0.0f);  // records.inl:160-164
                         DirectSample dRec;
@@ -348,14 +353,13 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(ShadeArgs A) {
                             const float3 woL = its.sh.toLocal(dRec.d);
                             const float3 bsdfVal = bsdfEval(bsdf, its.wi, woL);
                             if (!isZero(bsdfVal) && (!cfg.strictNormals || dot(its.geoN, dRec.d) * woL.z > 0)) {
-                                float bPdf = bsdfPdf(bsdf, its.wi, woL);
-                                if (guided) bPdf = A.G.alpha * guidePdf(A.G, gcell, dRec.d) + (1 - A.G.alpha) * bPdf;
-                                const float weight = miWeight(dRec.pdf, bPdf);
-                                shC = thr * value * bsdfVal * weight;
+                                neeBsdfPdf = bsdfPdf(bsdf, its.wi, woL);
+                                neeLightPdf = dRec.pdf;
+                                neeContrib = thr * value * bsdfVal;
                                 shO = its.p;
                                 shD = dRec.d;
                                 shMaxT = dRec.dist * (1 - kShadowEpsilon);  // scene.cpp:883-884
-                                wantShadow = true;
+                                neePending = true;
                             }
                         }
                     }
@@ -384,11 +388,23 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(ShadeArgs A) {
                             fcos = w * pb;
                             wo = its.sh.toWorld(woL);
                         }
-                        bPdf = ok ? A.G.alpha * guidePdf(A.G, gcell, wo) + (1 - A.G.alpha) * pb : 0.0f;
+                        float gNee = 0.0f, gWo = 0.0f;
+                        if (neePending && ok)
+                            guidePdf2(A.G, gcell, shD, wo, gNee, gWo);
+                        else if (neePending)
+                            gNee = guidePdf(A.G, gcell, shD);
+                        else if (ok)
+                            gWo = guidePdf(A.G, gcell, wo);
+                        if (neePending) neeBsdfPdf = A.G.alpha * gNee + (1 - A.G.alpha) * neeBsdfPdf;
+                        bPdf = ok ? A.G.alpha * gWo + (1 - A.G.alpha) * pb : 0.0f;
                         bsdfWeight = (ok && !isZero(fcos) && bPdf > 0) ? fcos / bPdf : f3(0.0f);
                     } else {
                         bsdfWeight = bsdfSample(bsdf, its.wi, rng.next2D(), woL, bPdf, bEta, sampledType);
                         wo = its.sh.toWorld(woL);
+                    }
+                    if (neePending) {
+                        shC = neeContrib * miWeight(neeLightPdf, neeBsdfPdf);
+                        wantShadow = true;
                     }
                     if (isZero(bsdfWeight)) {
                         terminate = true;

@@ -25,7 +25,7 @@ enum : uint32_t {
     kDepthMask = 0xFFu
 };
 
-static constexpr int kShadeThreads = 256;
+static constexpr int kShadeThreads = 128;
 static constexpr int kVertShift = 16;  // flags bits 16-23: number of recorded training vertices
 
 struct PathState {
