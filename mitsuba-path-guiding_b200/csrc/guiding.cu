@@ -4,6 +4,7 @@
 //                      bit-exact against the oracle's stable counting sort (oracle_guiding.h: guideBin)
 //   k_estep            weighted-EM E-step, one warp per chunk of one cell's samples: lobes staged in shared memory,
 //                      lane = sample, per-lane sufficient statistics in registers, butterfly reduction per chunk
+//   k_gather_partition gather into sorted order + per-chunk partition (usable weights first)
 //   k_cell_moments     per-chunk position moments (split statistics), once per training update
 //   k_reduce_partials  per-cell sum of the chunk partials in a fixed order (deterministic)
 //   k_mstep            M-step with decayed running statistics and MAP priors, one warp per cell
@@ -181,10 +182,21 @@ __global__ void __launch_bounds__(128) k_estep(GuideDevice G, const float4 *__re
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) S[k] = Rx[k] = Ry[k] = Rz[k] = 0.0f;
         float cW = 0.0f;
-        for (uint32_t j = item.y + ln; j < item.z; j += 32) {
-            const float4 p = sPos[j], d = sDir[j];
+        // samples with a usable weight were moved to the front of the chunk by k_gather_partition (item.w of them)
+        const uint32_t endGood = item.y + item.w;
+        uint32_t j = item.y + ln;
+        float4 pn = make_float4(0, 0, 0, 0), dn = pn;
+        if (j < endGood) {
+            pn = sPos[j];
+            dn = sDir[j];
+        }
+        for (; j < endGood; j += 32) {
+            const float4 p = pn, d = dn;
+            if (j + 32 < endGood) {  // prefetch the next sample while this one is evaluated
+                pn = sPos[j + 32];
+                dn = sDir[j + 32];
+            }
             const float sw = p.w;
-            if (!(sw > 0) || !isfinite(sw)) continue;
             float pk[KMAX];
             float total = 0.0f;
 #pragma unroll
@@ -192,8 +204,7 @@ __global__ void __launch_bounds__(128) k_estep(GuideDevice G, const float4 *__re
                 pk[k] = 0.0f;
                 if (k < K) {
                     const float4 la = myLobes[2 * k], lb = myLobes[2 * k + 1];
-                    const float c = la.y * d.x + la.z * d.y + la.w * d.z;
-                    pk[k] = la.x * lb.y * expf(lb.x * (c - 1.0f));
+                    pk[k] = guideLobeTerm(la, lb, f3(d.x, d.y, d.z));
                     total += pk[k];
                 }
             }
@@ -263,13 +274,38 @@ __global__ void __launch_bounds__(128) k_cell_moments(const float4 *__restrict__
     }
 }
 
-__global__ void __launch_bounds__(256) k_gather_samples(const float4 *__restrict__ sPos, const float4 *__restrict__ sDir,
-                                                        const uint32_t *__restrict__ perm, uint32_t n, float4 *__restrict__ oPos,
-                                                        float4 *__restrict__ oDir) {
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-        const uint32_t i = perm[j];
-        oPos[j] = sPos[i];
-        oDir[j] = sDir[i];
+// Gather into sorted order, one warp per work chunk, with a stable partition inside the chunk: samples whose weight
+// is positive and finite go to the front (count -> work[w].w), the others to the back in reverse order. Zero-weight
+// samples (paths that found no light) only matter for the cell's sample count and position moments, so the E-step
+// iterates over the dense front part with all lanes busy.
+__global__ void __launch_bounds__(128) k_gather_partition(const float4 *__restrict__ sPos, const float4 *__restrict__ sDir,
+                                                          const uint32_t *__restrict__ perm, uint4 *__restrict__ work, uint32_t nWork,
+                                                          float4 *__restrict__ oPos, float4 *__restrict__ oDir) {
+    const uint32_t warp = threadIdx.x >> 5, ln = lane();
+    for (uint32_t w = blockIdx.x * 4 + warp; w < nWork; w += gridDim.x * 4) {
+        const uint4 item = work[w];
+        uint32_t nGood = 0, nBad = 0;
+        for (uint32_t j0 = item.y; j0 < item.z; j0 += 32) {
+            const uint32_t j = j0 + ln;
+            const bool valid = j < item.z;
+            float4 p = make_float4(0, 0, 0, 0), d = p;
+            if (valid) {
+                const uint32_t i = perm[j];
+                p = sPos[i];
+                d = sDir[i];
+            }
+            const bool good = valid && p.w > 0 && isfinite(p.w);
+            const unsigned gm = __ballot_sync(0xffffffffu, good), bm = __ballot_sync(0xffffffffu, valid && !good);
+            const unsigned lt = (1u << ln) - 1u;
+            if (valid) {
+                const uint32_t dst = good ? item.y + nGood + __popc(gm & lt) : item.z - 1 - (nBad + __popc(bm & lt));
+                oPos[dst] = p;
+                oDir[dst] = d;
+            }
+            nGood += __popc(gm);
+            nBad += __popc(bm);
+        }
+        if (ln == 0) work[w].w = nGood;
     }
 }
 
@@ -517,7 +553,10 @@ void GuidingHost::buildWork() {
     dSortPos.alloc(nSamples);
     dSortDir.alloc(nSamples);
     if (nSamples) {
-        k_gather_samples<<<gridFor(nSamples, 256), 256, 0, stream>>>(dSPos.p, dSDir.p, sortedPerm, nSamples, dSortPos.p, dSortDir.p);
+        int smCount = 148;
+        cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, 0);
+        k_gather_partition<<<std::min<uint32_t>((nWork + 3) / 4, (uint32_t)smCount * 16), 128, 0, stream>>>(dSPos.p, dSDir.p, sortedPerm, dWork.p,
+                                                                                                     nWork, dSortPos.p, dSortDir.p);
         launches++;
     }
     dPartials.alloc((size_t)std::max(nWork, 1u) * statsStride());

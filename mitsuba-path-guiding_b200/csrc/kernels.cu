@@ -388,13 +388,10 @@ __global__ void __launch_bounds__(kShadeThreads, 5) k_shade(ShadeArgs A) {
                             fcos = w * pb;
                             wo = its.sh.toWorld(woL);
                         }
+                        // one pass over the cell's lobes for both directions (a single code path keeps the warp converged;
+                        // an unused direction is evaluated on a dummy and discarded)
                         float gNee = 0.0f, gWo = 0.0f;
-                        if (neePending && ok)
-                            guidePdf2(A.G, gcell, shD, wo, gNee, gWo);
-                        else if (neePending)
-                            gNee = guidePdf(A.G, gcell, shD);
-                        else if (ok)
-                            gWo = guidePdf(A.G, gcell, wo);
+                        if (neePending || ok) guidePdf2(A.G, gcell, neePending ? shD : wo, ok ? wo : shD, gNee, gWo);
                         if (neePending) neeBsdfPdf = A.G.alpha * gNee + (1 - A.G.alpha) * neeBsdfPdf;
                         bPdf = ok ? A.G.alpha * gWo + (1 - A.G.alpha) * pb : 0.0f;
                         bsdfWeight = (ok && !isZero(fcos) && bPdf > 0) ? fcos / bPdf : f3(0.0f);

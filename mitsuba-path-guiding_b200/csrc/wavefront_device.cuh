@@ -69,12 +69,28 @@ PG_DEV void emitTrainingSamples(const GuideDevice &G, bool finished, uint32_t sl
     uint32_t base = 0;
     if (laneId() == 31) base = atomicAdd(G.sCount, total);
     base = __shfl_sync(0xffffffffu, base, 31);
-    uint32_t dst = base + incl - nMine;
-    for (uint32_t v = 0; v < nMine; ++v, ++dst) {
-        if (dst >= G.sCapacity) break;
-        const size_t vi = (size_t)slot * G.maxVerts + v;
+    // The warp emits its `total` samples cooperatively, 32 at a time: item t belongs to the first lane whose inclusive
+    // prefix exceeds t (binary search over the prefix with shuffles), so the vertex loads/stores run with all lanes
+    // busy instead of a serial per-path loop with a handful of finished lanes.
+    for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+        const uint32_t t = t0 + laneId();
+        uint32_t owner = 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint32_t v = __shfl_sync(0xffffffffu, incl, (owner + o - 1) & 31);
+            if (v <= t) owner += o;
+        }
+        owner &= 31u;
+        const uint32_t oIncl = __shfl_sync(0xffffffffu, incl, owner), oN = __shfl_sync(0xffffffffu, nMine, owner);
+        const uint32_t oSlot = __shfl_sync(0xffffffffu, slot, owner);
+        const float Lx = __shfl_sync(0xffffffffu, Lfinal.x, owner), Ly = __shfl_sync(0xffffffffu, Lfinal.y, owner),
+                    Lz = __shfl_sync(0xffffffffu, Lfinal.z, owner);
+        const uint32_t dst = base + t;
+        if (t >= total || dst >= G.sCapacity) continue;
+        const uint32_t v = t - (oIncl - oN);
+        const size_t vi = (size_t)oSlot * G.maxVerts + v;
         const float4 p = G.vPos[vi], d = G.vDir[vi], T = G.vThr[vi], Lk = G.vL[vi];
-        const float3 diff = Lfinal - f3(Lk.x, Lk.y, Lk.z);
+        const float3 diff = f3(Lx, Ly, Lz) - f3(Lk.x, Lk.y, Lk.z);
         const float ex = T.x > 0 ? diff.x / T.x : 0.0f, ey = T.y > 0 ? diff.y / T.y : 0.0f, ez = T.z > 0 ? diff.z / T.z : 0.0f;
         float w = ((ex + ey + ez) * (1.0f / 3.0f)) / p.w;
         if (!isfinite(w) || w < 0) w = 0.0f;
