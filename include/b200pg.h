@@ -226,6 +226,21 @@ int b200pg_train_stats_buffer(void *integ, void **dev_ptr, size_t *n_floats);
 int b200pg_train_update(void *integ, int commit);
 int b200pg_train_end(void *integ);
 
+/* The whole training update in one call (begin, n_iter x (E-step, [cross-GPU sum,] M-step), end) without host round
+ * trips between the EM iterations; n_iter <= 0 uses the integrator's emIterations. With peers connected (below) the
+ * per-cell sufficient statistics are summed over all ranks inside the M-step kernel. */
+int b200pg_train(void *integ, int n_iter, uint32_t *n_samples, uint32_t *n_cells);
+
+/* Multi-GPU statistics exchange over NVLink peer memory (one process per GPU, replicated scene and field):
+ *   b200pg_comm_local_handle  writes the 64-byte CUDA IPC handle of this rank's exchange block
+ *   b200pg_comm_connect       maps the blocks of all `world` ranks (`handles` = world x 64 bytes, gathered by the host
+ *                             with whatever transport it has: torch.distributed all_gather, MPI, Mitsuba's own
+ *                             StreamBackend sched_remote.cpp:33-119)
+ * Afterwards b200pg_train sums the statistics of all ranks in rank order (bit-identical on every rank), so the
+ * replicated fields stay identical without a broadcast. All ranks must call b200pg_train the same number of times. */
+int b200pg_comm_local_handle(void *integ, void *handle64);
+int b200pg_comm_connect(void *integ, int rank, int world, const void *handles);
+
 int b200pg_film_clear(void *integ);
 int b200pg_film_device_buffer(void *integ, void **dev_ptr, size_t *n_floats); /* H*W*4: R,G,B,weight */
 int b200pg_film_read(void *integ, float *rgbaw /* H*W*5: R,G,B,alpha,weight (imageblock.h:131-138) */);

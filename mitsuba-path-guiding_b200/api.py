@@ -70,6 +70,9 @@ def lib():
     L.b200pg_k_vmm_pdf_sample.argtypes = [C.c_void_p, fp, fp, fp, C.c_size_t, fp, fp, fp, u32p]
     L.b200pg_k_bin_samples.argtypes = [C.c_void_p, fp, C.c_size_t, u32p, u32p, u32p, u32p]
     L.b200pg_k_em_step.argtypes = [C.c_void_p, fp, fp, fp, fp, fp, C.c_size_t, C.c_int, fp]
+    L.b200pg_train.argtypes = [C.c_void_p, C.c_int, u32p, u32p]
+    L.b200pg_comm_local_handle.argtypes = [C.c_void_p, C.c_void_p]
+    L.b200pg_comm_connect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.b200pg_field_snapshot.argtypes = [C.c_void_p, u32p, C.POINTER(C.c_size_t)]
     L.b200pg_field_load.argtypes = [C.c_void_p, u32p, C.c_size_t]
     _lib = L
@@ -257,6 +260,22 @@ class Integrator:
             self.train_update(it == n_iter - 1)
         self.train_end()
         return n, c
+
+    def train_fused(self, n_iter=4):
+        """One training update in a single library call; sums statistics over the connected ranks (comm_connect)."""
+        n, c = C.c_uint32(0), C.c_uint32(0)
+        _check(lib().b200pg_train(self.h, n_iter, C.byref(n), C.byref(c)))
+        return n.value, c.value
+
+    def comm_local_handle(self):
+        buf = (C.c_ubyte * 64)()
+        _check(lib().b200pg_comm_local_handle(self.h, buf))
+        return bytes(buf)
+
+    def comm_connect(self, rank, world, handles):
+        assert len(handles) == 64 * world
+        buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+        _check(lib().b200pg_comm_connect(self.h, rank, world, buf))
 
     def field_snapshot(self):
         n = C.c_size_t(0)

@@ -13,6 +13,7 @@
 // statement it is tested against is oracle/oracle_guiding.h.
 #include <cmath>
 #include <cstring>
+#include <stdexcept>
 
 #include "guiding_device.cuh"
 #include "guiding_host.h"
@@ -370,6 +371,108 @@ __global__ void __launch_bounds__(256) k_mstep(float4 *__restrict__ lobes, float
     }
 }
 
+// ---- fused cross-GPU sum + M-step over NVLink peer memory ---------------------------------------------------
+// One kernel per EM iteration does: (1) arrival signal into every peer's flag row, (2) wait for every peer's signal,
+// (3) per cell: statistics = sum over ranks r = 0..world-1 (fixed order -> bit-identical on every rank) of the
+// peers' E-step results, read straight from their HBM over NVLink, (4) M-step. The statistics buffers are
+// double-buffered by iteration parity, so no second barrier is needed: a rank can overwrite buffer b only after
+// passing the barrier of the next iteration, which every peer reaches only after it finished reading buffer b.
+struct CommView {
+    float *const *peers;   // world pointers to the ranks' exchange blocks
+    int rank, world;
+    uint32_t epoch;        // arrival value of this iteration (monotonic)
+    size_t bufFloats;      // floats per statistics buffer
+    int buf;               // which of the two buffers this iteration uses
+    uint32_t *error;       // set when the wait timed out (a peer never arrived)
+};
+__device__ __forceinline__ uint32_t *commFlags(float *block, size_t bufFloats) {
+    return reinterpret_cast<uint32_t *>(block + 2 * bufFloats);
+}
+__device__ __forceinline__ float ldPeer(const float *p) {  // system-scope load that bypasses the (non-coherent) L1
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_mstep_allreduce(CommView cv, float4 *__restrict__ lobes, float4 *__restrict__ lobeStats,
+                                                         float *__restrict__ stats, uint32_t nCells, int K, int stride, int commit) {
+    // ---- barrier: every block signals/waits on its own (the flag rows are written once per rank and iteration by
+    // block 0; all blocks poll the same local row)
+    if (blockIdx.x == 0 && (int)threadIdx.x < cv.world) {
+        __threadfence_system();
+        uint32_t *peerRow = commFlags(cv.peers[threadIdx.x], cv.bufFloats) + cv.rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peerRow), "r"(cv.epoch) : "memory");
+    }
+    if ((int)threadIdx.x < cv.world) {
+        const uint32_t *mine = commFlags(cv.peers[cv.rank], cv.bufFloats) + threadIdx.x;
+        const long long t0 = clock64();
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if ((int)(v - cv.epoch) >= 0) break;
+            if (clock64() - t0 > 4000000000LL) {  // ~2 s: a peer never arrived; fail loudly instead of hanging the GPU
+                atomicExch(cv.error, 1u);
+                break;
+            }
+        } while (true);
+    }
+    __syncthreads();
+
+    const uint32_t warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = (gridDim.x * blockDim.x) >> 5;
+    const int k = (int)lane();
+    const size_t bufOfs = (size_t)cv.buf * cv.bufFloats;
+    for (uint32_t c = warpGlobal; c < nCells; c += nWarps) {
+        // sum over ranks, element e = lane, lane + 32, ... of the cell's `stride` statistics
+        float *own = stats + (size_t)c * stride;
+        for (int e = k; e < stride; e += 32) {
+            float acc = 0.0f;
+            for (int r = 0; r < cv.world; ++r) acc += ldPeer(cv.peers[r] + bufOfs + (size_t)c * stride + e);
+            own[e] = acc;
+        }
+        __syncwarp();
+        const float *st = own;
+        float4 a = make_float4(0, 0, 0, 0), b = a, s = a;
+        float S = 0, R0 = 0, R1 = 0, R2 = 0;
+        if (k < K) {
+            const float4 *L = lobes + ((size_t)c * K + k) * 2;
+            a = L[0];
+            b = L[1];
+            s = lobeStats[(size_t)c * K + k];
+            S = kGuideDecay * s.x + st[4 * k];
+            R0 = kGuideDecay * s.y + st[4 * k + 1];
+            R1 = kGuideDecay * s.z + st[4 * k + 2];
+            R2 = kGuideDecay * s.w + st[4 * k + 3];
+        }
+        float sumS = S;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sumS += __shfl_xor_sync(0xffffffffu, sumS, o);
+        if (k < K) {
+            if (sumS > 0 && isfinite(sumS)) {
+                const float prior = kGuidePriorWeight * sumS / (float)K;
+                const float denom = 1.0f / (sumS + (float)K * prior);
+                a.x = (S + prior) * denom;
+                const float rl = sqrtf(R0 * R0 + R1 * R1 + R2 * R2);
+                float rbar = (rl + prior * kGuidePriorMeanCos) / (S + prior);
+                rbar = fminf(rbar, 0.9999f);
+                const float kappa = rbar * (3.0f - rbar * rbar) / (1.0f - rbar * rbar);
+                b.x = fminf(kGuideKappaMax, fmaxf(kGuideKappaMin, kappa));
+                if (rl > 0) {
+                    const float ir = 1.0f / rl;
+                    a.y = R0 * ir;
+                    a.z = R1 * ir;
+                    a.w = R2 * ir;
+                }
+                b.z = expf(-2.0f * b.x);
+                b.y = b.x / (2 * kPi * (1.0f - b.z));
+            }
+            float4 *L = lobes + ((size_t)c * K + k) * 2;
+            L[0] = a;
+            L[1] = b;
+            if (commit) lobeStats[(size_t)c * K + k] = make_float4(S, R0, R1, R2);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_guide_query(GuideDevice G, const float *__restrict__ pos, const float *__restrict__ dir,
                                                      const float *__restrict__ u, uint32_t n, float *__restrict__ outPdf,
                                                      float *__restrict__ outDir, float *__restrict__ outSpdf,
@@ -602,7 +705,9 @@ void GuidingHost::beginExternal(const float *pos, const float *dir, const float 
     buildWork();
 }
 
-void GuidingHost::accumulate() {
+void GuidingHost::accumulate() { accumulateInto(dStats.p); }
+
+void GuidingHost::accumulateInto(float *statsOut) {
     GuideDevice G;
     std::memset(&G, 0, sizeof(G));
     G.lobes = dLobes.p;
@@ -622,7 +727,7 @@ void GuidingHost::accumulate() {
         launches++;
     }
     k_reduce_partials<<<gridFor((size_t)numCells() * stride, 256), 256, 0, stream>>>(dPartials.p, dCellCount.p, numCells(), stride,
-                                                                                      dStats.p);
+                                                                                      statsOut);
     launches++;
 }
 
@@ -693,13 +798,91 @@ void GuidingHost::end() {
     sortedPerm = sortedCells = nullptr;
 }
 
-void GuidingHost::trainLocal() {
+void GuidingHost::trainLocal() { train(emIterations); }
+
+// One complete training update without host round trips between the EM iterations. With connected peers the
+// E-step result of iteration `it` goes into exchange buffer it % 2 and k_mstep_allreduce sums it over the ranks.
+void GuidingHost::train(int nIter) {
     begin();
-    for (int it = 0; it < emIterations; ++it) {
-        accumulate();
-        update(it == emIterations - 1);
+    const int stride = (int)statsStride();
+    if (commWorld > 1 && (size_t)numCells() * stride > commFloats)
+        throw std::runtime_error("guiding field has more cells than the multi-GPU exchange buffer holds");
+    for (int it = 0; it < nIter; ++it) {
+        const bool commit = it == nIter - 1;
+        if (commWorld > 1) {
+            const int buf = (int)(commEpoch & 1u);
+            accumulateInto(commBlock + (size_t)buf * commFloats);
+            CommView cv;
+            cv.peers = dCommPeers.p;
+            cv.rank = commRank;
+            cv.world = commWorld;
+            cv.epoch = ++commEpoch;
+            cv.bufFloats = commFloats;
+            cv.buf = buf;
+            cv.error = dCommError.p;
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+            // every block of the grid must be resident while it waits for the peers: at most one block per SM
+            const int grid = (int)std::max<size_t>(1, std::min<size_t>(((size_t)numCells() * 32 + 255) / 256, (size_t)sms));
+            k_mstep_allreduce<<<grid, 256, 0, stream>>>(cv, dLobes.p, dLobeStats.p, dStats.p, numCells(), K, stride, commit ? 1 : 0);
+            launches++;
+        } else {
+            accumulate();
+            update(commit);
+        }
+    }
+    if (commWorld > 1) {
+        uint32_t err = 0;
+        CUDA_OK(cudaMemcpyAsync(&err, dCommError.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        if (err) throw std::runtime_error("multi-GPU statistics exchange timed out: a peer rank never arrived");
     }
     end();
+}
+
+void GuidingHost::commLocalHandle(void *out64) {
+    if (!commBlock) {
+        commFloats = kCommMaxCells * statsStride();
+        const size_t bytes = 2 * commFloats * sizeof(float) + 64 * sizeof(uint32_t);
+        CUDA_OK(cudaMalloc(&commBlock, bytes));
+        CUDA_OK(cudaMemset(commBlock, 0, bytes));
+    }
+    cudaIpcMemHandle_t h;
+    CUDA_OK(cudaIpcGetMemHandle(&h, commBlock));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(out64, &h, 64);
+}
+
+void GuidingHost::commConnect(int rank, int world, const void *handles) {
+    if (world < 1 || world > 16 || rank < 0 || rank >= world) throw std::runtime_error("invalid rank / world size");
+    if (!commBlock) throw std::runtime_error("b200pg_comm_local_handle must be called first");
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            commPeers[r] = commBlock;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, (const char *)handles + 64 * (size_t)r, 64);
+        void *ptr = nullptr;
+        CUDA_OK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        commPeers[r] = (float *)ptr;
+    }
+    commRank = rank;
+    commWorld = world;
+    commEpoch = 0;
+    dCommPeers.upload(commPeers, (size_t)world, stream);
+    dCommError.alloc(1);
+    CUDA_OK(cudaMemsetAsync(dCommError.p, 0, sizeof(uint32_t), stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+}
+
+void GuidingHost::commClose() {
+    for (int r = 0; r < commWorld; ++r)
+        if (r != commRank && commPeers[r]) cudaIpcCloseMemHandle(commPeers[r]);
+    if (commBlock) cudaFree(commBlock);
+    commBlock = nullptr;
+    commWorld = 1;
+    for (auto &q : commPeers) q = nullptr;
 }
 
 void GuidingHost::query(const float *pos, const float *dir, const float *u, size_t n, float *outPdf, float *outDir, float *outSpdf,

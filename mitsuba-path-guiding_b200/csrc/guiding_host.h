@@ -86,9 +86,29 @@ struct GuidingHost {
     void begin();
     void beginExternal(const float *pos, const float *dir, const float *weight, const float *pdf, const float *dist, size_t n);
     void accumulate();
+    void accumulateInto(float *statsOut);
     void update(bool commit);
     void end();
     void trainLocal();  // begin + emIterations x (accumulate, update) + end
+    void train(int nIter);  // same with an explicit iteration count; sums the statistics over the connected ranks
+
+    // ---- multi-GPU: peer-memory exchange of the per-cell EM statistics (no NCCL call on the data path) -----------
+    // Every rank owns one cudaMalloc'ed exchange block {2 x kCommCapacity floats of statistics (double-buffered by EM
+    // iteration parity), 64 arrival flags} that its peers map through CUDA IPC. k_mstep_allreduce signals arrival
+    // in every peer's flag row, waits for all peers, then sums the cell's statistics over the ranks in rank order
+    // (identical result on every rank) and runs the M-step in the same kernel.
+    static constexpr size_t kCommMaxCells = 16384;
+    int commRank = 0, commWorld = 1;
+    uint32_t commEpoch = 0;
+    float *commBlock = nullptr;            // own exchange block (device)
+    size_t commFloats = 0;                 // floats per statistics buffer
+    float *commPeers[16] = {nullptr};      // mapped blocks of all ranks (own included)
+    DevBuf<float *> dCommPeers;
+    DevBuf<uint32_t> dCommError;
+    void commLocalHandle(void *out64);
+    void commConnect(int rank, int world, const void *handles);
+    void commClose();
+    ~GuidingHost() { commClose(); }
 
     // per-kernel entry points
     void query(const float *pos, const float *dir, const float *u, size_t n, float *outPdf, float *outDir, float *outSpdf,

@@ -826,6 +826,31 @@ int b200pg_train_update(void *integ, int commit) {
     self->drainSpans();
     PG_END
 }
+int b200pg_train(void *integ, int n_iter, uint32_t *n_samples, uint32_t *n_cells) {
+    PG_TRY(integ)
+    if (!self->guide.active) return fail("guiding is not enabled in the integrator parameters");
+    cudaEvent_t t = self->spanBegin();
+    self->guide.train(n_iter > 0 ? n_iter : self->guide.emIterations);
+    self->spanEnd(Integrator::kTimeTrain, t);
+    CUDA_OK(cudaStreamSynchronize(self->stream));
+    CUDA_OK(cudaGetLastError());
+    self->drainSpans();
+    if (n_samples) *n_samples = self->guide.nSamples;
+    if (n_cells) *n_cells = self->guide.numCells();
+    PG_END
+}
+int b200pg_comm_local_handle(void *integ, void *handle64) {
+    PG_TRY(integ)
+    if (!handle64) return fail("null argument");
+    self->guide.commLocalHandle(handle64);
+    PG_END
+}
+int b200pg_comm_connect(void *integ, int rank, int world, const void *handles) {
+    PG_TRY(integ)
+    if (!handles) return fail("null argument");
+    self->guide.commConnect(rank, world, handles);
+    PG_END
+}
 int b200pg_train_end(void *integ) {
     PG_TRY(integ)
     cudaEvent_t t = self->spanBegin();

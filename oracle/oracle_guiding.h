@@ -181,10 +181,9 @@ inline void guideBin(const GuideField &F, const Vec3 *pos, size_t n, std::vector
     const uint32_t nc = F.numCells();
     cell.resize(n);
     offsets.assign(nc + 1, 0);
-    for (size_t i = 0; i < n; ++i) {
-        cell[i] = F.lookup(pos[i]);
-        offsets[cell[i] + 1]++;
-    }
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)n; ++i) cell[i] = F.lookup(pos[i]);
+    for (size_t i = 0; i < n; ++i) offsets[cell[i] + 1]++;
     for (uint32_t c = 0; c < nc; ++c) offsets[c + 1] += offsets[c];
     perm.resize(n);
     std::vector<uint32_t> cur(offsets.begin(), offsets.end() - 1);
@@ -201,7 +200,10 @@ inline void guideEStep(const GuideField &F, const GuideSamples &smp, const std::
     const int K = F.K;
     const size_t stride = (size_t)K * 4 + 8;
     stats.assign(stride * F.numCells(), 0.0);
-    for (uint32_t c = 0; c < F.numCells(); ++c) {
+    // cells are independent: parallel over cells (the CPU baseline uses every host core); the sums inside a cell stay
+    // sequential in sorted order, so the result does not depend on the thread count
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long long c = 0; c < (long long)F.numCells(); ++c) {
         double *st = &stats[stride * c];
         const GuideLobe *L = &F.lobes[(size_t)c * K];
         for (uint32_t j = offsets[c]; j < offsets[c + 1]; ++j) {

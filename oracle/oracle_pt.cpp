@@ -1068,9 +1068,22 @@ int orc_render(void *s, const B200pgIntegratorParams *P, int first_sample, int n
     auto t1 = std::chrono::steady_clock::now();
     if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
     if (sink) {
+        // concatenate the per-tile sample lists in tile order (deterministic); parallel copy so that the merge does
+        // not serialise the CPU baseline
         GuideSamples *out = (GuideSamples *)sink;
-        for (auto &c : tileSamples)
-            for (size_t j = 0; j < c.size(); ++j) out->push(c.pos[j], c.dir[j], c.weight[j], c.pdf[j], c.dist[j]);
+        std::vector<size_t> ofs(tileSamples.size() + 1, out->size());
+        for (size_t t = 0; t < tileSamples.size(); ++t) ofs[t + 1] = ofs[t] + tileSamples[t].size();
+        const size_t tot = ofs.back();
+        out->pos.resize(tot); out->dir.resize(tot); out->weight.resize(tot); out->pdf.resize(tot); out->dist.resize(tot);
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
+        for (long long t = 0; t < (long long)tileSamples.size(); ++t) {
+            const GuideSamples &c = tileSamples[t];
+            std::copy(c.pos.begin(), c.pos.end(), out->pos.begin() + ofs[t]);
+            std::copy(c.dir.begin(), c.dir.end(), out->dir.begin() + ofs[t]);
+            std::copy(c.weight.begin(), c.weight.end(), out->weight.begin() + ofs[t]);
+            std::copy(c.pdf.begin(), c.pdf.end(), out->pdf.begin() + ofs[t]);
+            std::copy(c.dist.begin(), c.dist.end(), out->dist.begin() + ofs[t]);
+        }
     }
     if (stats) {
         stats[0] = total.paths;
@@ -1211,6 +1224,11 @@ int orc_train(void *f, const float *pos, const float *dir, const float *weight, 
     GuideSamples S;
     fillSamples(S, pos, dir, weight, pdf, dist, n);
     guideTrain(*F, S, nIter, maxCellSamples);
+    return 0;
+}
+// training update straight from a sample sink (no copies through the caller): what the CPU baseline times
+int orc_train_sink(void *f, void *sink, int nIter, float maxCellSamples) {
+    guideTrain(*(GuideField *)f, *(GuideSamples *)sink, nIter, maxCellSamples);
     return 0;
 }
 void *orc_samples_create(void) { return new GuideSamples(); }

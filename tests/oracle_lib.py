@@ -53,6 +53,7 @@ class Oracle:
         L.orc_bin_samples.argtypes = [C.c_void_p, fp, C.c_size_t, u32p, u32p, u32p]
         L.orc_estep.argtypes = [C.c_void_p, fp, fp, fp, fp, fp, C.c_size_t, fp]
         L.orc_train.argtypes = [C.c_void_p, fp, fp, fp, fp, fp, C.c_size_t, C.c_int, C.c_float]
+        L.orc_train_sink.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float]
         L.orc_samples_create.restype = C.c_void_p
         L.orc_samples_destroy.argtypes = [C.c_void_p]
         L.orc_samples_size.restype = C.c_size_t
@@ -167,6 +168,9 @@ class OracleField:
         st = np.zeros(i["cells"] * (4 * i["K"] + 8), np.float32)
         self.L.orc_estep(self.h, *[_f(x) for x in a], n, _f(st))
         return st.reshape(i["cells"], 4 * i["K"] + 8)
+
+    def train_sink(self, sink, n_iter=4, max_cell_samples=32768):
+        self.L.orc_train_sink(self.h, sink.h, n_iter, max_cell_samples)
 
     def train(self, s, n_iter=4, max_cell_samples=32768):
         a, n = self._args(s)
