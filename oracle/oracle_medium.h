@@ -111,6 +111,48 @@ struct Medium {
         return false;
     }
 
+    // Guided free-flight sampling (this repo's design, DESIGN.md "Guiding in media"; no counterpart in the reference
+    // snapshot): Woodcock tracking whose real-vs-null decision at every tentative collision is steered by the guiding
+    // field and compensated by weights ("weighted delta tracking"). With a = sigma_t(x) / sigma_max the analog
+    // probability of a real collision, and g = 4 pi * (mixture pdf of the cell at x in the ray direction) the ratio of
+    // the radiance arriving along the ray to the mean incident radiance,
+    //     P_guided = a * albedo / (a * albedo + (1 - a) * g),     P_real = (1 - beta) * a + beta * P_guided,
+    // real collision: weight *= albedo * a / P_real; null collision: weight *= (1 - a) / (1 - P_real).
+    // beta = 1/2 bounds both factors by 2 (and by 2 * albedo). `pdfDir(p)` returns the mixture pdf at p in direction dir.
+    template <typename PdfDir>
+    bool sampleDistanceGuided(const Vec3 &o, const Vec3 &dir, Float rmint, Float rmaxt, MediumSample &mRec, Vec3 &weight, Rng &rng,
+                              const PdfDir &pdfDir) const {
+        weight = Vec3(1.0f);
+        Float mint, maxt;
+        if (!clip(o, dir, mint, maxt)) return false;
+        mint = std::max(mint, rmint);
+        maxt = std::min(maxt, rmaxt);
+        const Vec3 albedo(d.albedo[0], d.albedo[1], d.albedo[2]);
+        const Float albedoAvg = (albedo.x + albedo.y + albedo.z) * (1.0f / 3.0f);
+        const Float beta = 0.5f;
+        Float t = mint;
+        while (true) {
+            t -= std::log(1 - rng.next1D()) * invMaxDensity;
+            if (t >= maxt) break;
+            const Vec3 p = o + dir * t;
+            const Float a = std::min(lookup(p) * d.scale * invMaxDensity, 1.0f);
+            const Float u = rng.next1D();
+            if (!(a > 0)) continue;  // empty space: a null collision with probability one
+            const Float g = 4 * PI_F * pdfDir(p);
+            const Float num = a * albedoAvg, den = num + (1 - a) * g;
+            const Float pGuided = den > 0 ? num / den : a;
+            const Float pReal = (1 - beta) * a + beta * pGuided;
+            if (u < pReal) {
+                weight *= albedo * (a / pReal);
+                mRec.t = t;
+                mRec.p = p;
+                return true;
+            }
+            weight *= (1 - a) / (1 - pReal);
+        }
+        return false;
+    }
+
     // heterogeneous.cpp:546-587, Woodcock branch: 2 ratio-free tracking trials
     Float evalTransmittance(const Vec3 &o, const Vec3 &dir, Float rmint, Float rmaxt, Rng &rng) const {
         Float mint, maxt;

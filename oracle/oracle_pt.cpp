@@ -600,7 +600,7 @@ namespace orc {
 
 static Vec3 Li(const Scene &scene, const B200pgIntegratorParams &P, const Ray &r, Rng &rng, Stats &st,
                const GuideCtx *G = nullptr) {
-    if (P.volumetric) return Li_volpath(scene, P, r, rng, st);
+    if (P.volumetric) return Li_volpath(scene, P, r, rng, st, G);
     return Li_path(scene, P, r, rng, st, G);
 }
 

@@ -114,7 +114,18 @@ static void rayIntersectAndLookForEmitter(const Scene &scene, Rng &rng, int medi
     }
 }
 
-static Vec3 Li_volpath(const Scene &scene, const B200pgIntegratorParams &P, const Ray &r, Rng &rng, Stats &st) {
+// Guided variant (G != nullptr): this repo's design on top of the reference loop --
+//   * direction sampling at medium vertices and at surface vertices with a smooth BSDF: one-sample MIS between the phase
+//     function / BSDF and the cell's vMF mixture (probability alpha for the mixture), exactly as in Li_path;
+//   * P.guided_distance: guided collision probabilities in the free-flight sampling (Medium::sampleDistanceGuided);
+//   * every such vertex is recorded as a training sample.
+static Vec3 Li_volpath(const Scene &scene, const B200pgIntegratorParams &P, const Ray &r, Rng &rng, Stats &st,
+                       const GuideCtx *G = nullptr) {
+    const GuideField *field = G ? G->field : nullptr;
+    const bool record = G && G->rec;
+    const Float alpha = G ? G->alpha : 0.0f;
+    GuideVertex verts[64];
+    int nVerts = 0;
     Intersection its;
     MediumSample mRec;
     Ray ray(r);
@@ -131,11 +142,24 @@ static Vec3 Li_volpath(const Scene &scene, const B200pgIntegratorParams &P, cons
 
     while (depth <= maxDepth || maxDepth < 0) {
         bool mediumEvent = false;
-        if (medium >= 0) mediumEvent = scene.media[medium].sampleDistance(ray.o, ray.d, 0, its.t, mRec, rng);
+        const bool guidedDist = field && P.guided_distance && medium >= 0;
+        Vec3 distWeight(1.0f);
+        if (guidedDist) {
+            const Vec3 rd = ray.d;
+            mediumEvent = scene.media[medium].sampleDistanceGuided(ray.o, ray.d, 0, its.t, mRec, distWeight, rng,
+                                                                   [&](const Vec3 &p) { return field->pdf(field->lookup(p), rd); });
+        } else if (medium >= 0) {
+            mediumEvent = scene.media[medium].sampleDistance(ray.o, ray.d, 0, its.t, mRec, rng);
+        }
         if (mediumEvent) {
             const Medium &med = scene.media[medium];
             if (depth >= maxDepth && maxDepth != -1) break;
-            throughput *= mRec.sigmaS * mRec.transmittance / mRec.pdfSuccess;
+            if (guidedDist)
+                throughput *= distWeight;
+            else
+                throughput *= mRec.sigmaS * mRec.transmittance / mRec.pdfSuccess;
+            const bool guided = field != nullptr;
+            const uint32_t gcell = guided ? field->lookup(mRec.p) : 0u;
 
             Scene::DirectSample dRec;
             dRec.ref = mRec.p;
@@ -153,18 +177,45 @@ static Vec3 Li_volpath(const Scene &scene, const B200pgIntegratorParams &P, cons
                     Float phaseVal = med.phaseEval(-ray.d, dRec.d);
                     if (phaseVal != 0) {
                         Float phasePdf = phaseVal;  // phase->pdf == eval for hg / isotropic
+                        if (guided) phasePdf = alpha * field->pdf(gcell, dRec.d) + (1 - alpha) * phasePdf;
                         const Float weight = miWeight(dRec.pdf, phasePdf);
                         Li += throughput * value * phaseVal * weight;
                     }
                 }
             }
+            const Vec3 LafterNee = Li;
             Float phasePdf;
-            Vec3 wo = med.phaseSample(-ray.d, rng.next2D(), phasePdf);
-            // phaseWeight == 1
+            Vec3 wo;
+            if (guided) {  // one-sample MIS between the mixture and the phase function
+                Float u0 = rng.next1D();
+                Vec2 u12 = rng.next2D();
+                Float pp;
+                if (u0 < alpha) {
+                    wo = field->sample(gcell, u0 / alpha, u12.x, u12.y);
+                    pp = med.phaseEval(-ray.d, wo);
+                } else {
+                    wo = med.phaseSample(-ray.d, u12, pp);
+                }
+                phasePdf = alpha * field->pdf(gcell, wo) + (1 - alpha) * pp;
+                if (!(pp > 0) || !(phasePdf > 0)) break;
+                throughput *= pp / phasePdf;
+            } else {
+                wo = med.phaseSample(-ray.d, rng.next2D(), phasePdf);  // phaseWeight == 1
+            }
+            if (record && nVerts < 64) {
+                GuideVertex &gv = verts[nVerts++];
+                gv.pos = mRec.p;
+                gv.dir = wo;
+                gv.pdf = phasePdf;
+                gv.T = throughput;
+                gv.Lk = LafterNee;
+                gv.dist = 0.0f;
+            }
             ray = Ray(mRec.p, wo, 0.0f);
             Vec3 value(0.0f);
             Rng fr = rng.fork();
             rayIntersectAndLookForEmitter(scene, fr, medium, maxDepth - depth - 1, ray, its, dRec, value, st);
+            if (record && nVerts > 0 && verts[nVerts - 1].dist == 0.0f && its.isValid()) verts[nVerts - 1].dist = its.t;
             if (!value.isZero() && std::min(value.x, std::min(value.y, value.z)) > 0.f) {
                 const Float emitterPdf = P.use_nee ? scene.pdfEmitterDirect(dRec) : 0.0f;
                 const Float weight = P.use_nee ? miWeight(phasePdf, emitterPdf) : 1.0f;
@@ -172,7 +223,10 @@ static Vec3 Li_volpath(const Scene &scene, const B200pgIntegratorParams &P, cons
             }
             emittedRadiance = false;
         } else {
-            if (medium >= 0) throughput *= mRec.transmittance / mRec.pdfFailure;
+            if (guidedDist)
+                throughput *= distWeight;
+            else if (medium >= 0)
+                throughput *= mRec.transmittance / mRec.pdfFailure;
             if (!its.isValid()) break;
             const Shape &shape = scene.shapes[its.shape];
             const Bsdf &bsdf = scene.bsdfOf(shape);
@@ -186,6 +240,8 @@ static Vec3 Li_volpath(const Scene &scene, const B200pgIntegratorParams &P, cons
             dRec.refN = Vec3(0.0f);
             const unsigned btype = bsdf.typeFlags();
             if ((btype & (ETransmission | EBackSide)) == 0) dRec.refN = its.shFrame.n;
+            const bool guided = field && (btype & ESmooth);
+            const uint32_t gcell = guided ? field->lookup(its.p) : 0u;
             if (P.use_nee && (btype & ESmooth)) {
                 int interactions = maxDepth - depth - 1;
                 Vec3 value = scene.sampleEmitterDirectNoVis(dRec, rng.next2D());
@@ -203,22 +259,56 @@ static Vec3 Li_volpath(const Scene &scene, const B200pgIntegratorParams &P, cons
                     Float woDotGeoN = dot(its.geoN, dRec.d);
                     if (!bsdfVal.isZero() && (!P.strict_normals || woDotGeoN * Frame::cosTheta(woL) > 0)) {
                         Float bsdfPdf = bsdf.pdf(its.wi, woL);
+                        if (guided) bsdfPdf = alpha * field->pdf(gcell, dRec.d) + (1 - alpha) * bsdfPdf;
                         const Float weight = miWeight(dRec.pdf, bsdfPdf);
                         Li += throughput * (value * bsdfVal * weight);
                     }
                 }
             }
+            const Vec3 LafterNee = Li;
             Float bsdfPdf, bEta;
             unsigned sampledType;
-            Vec3 woLocal;
-            Vec3 bsdfWeight = bsdf.sample(its.wi, rng.next2D(), woLocal, bsdfPdf, bEta, sampledType);
-            if (bsdfWeight.isZero()) break;
-            const Vec3 wo = its.toWorld(woLocal);
+            Vec3 woLocal, bsdfWeight, wo;
+            if (guided) {
+                Float u0 = rng.next1D();
+                Vec2 u12 = rng.next2D();
+                Vec3 fcos;
+                Float pb;
+                if (u0 < alpha) {
+                    wo = field->sample(gcell, u0 / alpha, u12.x, u12.y);
+                    woLocal = its.toLocal(wo);
+                    fcos = bsdf.eval(its.wi, woLocal);
+                    pb = bsdf.pdf(its.wi, woLocal);
+                    bEta = 1.0f;
+                    sampledType = EGlossyReflection;
+                } else {
+                    Vec3 w = bsdf.sample(its.wi, u12, woLocal, pb, bEta, sampledType);
+                    if (w.isZero()) break;
+                    fcos = w * pb;
+                    wo = its.toWorld(woLocal);
+                }
+                bsdfPdf = alpha * field->pdf(gcell, wo) + (1 - alpha) * pb;
+                if (fcos.isZero() || !(bsdfPdf > 0)) break;
+                bsdfWeight = fcos / bsdfPdf;
+            } else {
+                bsdfWeight = bsdf.sample(its.wi, rng.next2D(), woLocal, bsdfPdf, bEta, sampledType);
+                if (bsdfWeight.isZero()) break;
+                wo = its.toWorld(woLocal);
+            }
             Float woDotGeoN = dot(its.geoN, wo);
             if (woDotGeoN * Frame::cosTheta(woLocal) <= 0 && P.strict_normals) break;
             ray = Ray(its.p, wo);
             throughput *= bsdfWeight;
             eta *= bEta;
+            if (record && (btype & ESmooth) && nVerts < 64) {
+                GuideVertex &gv = verts[nVerts++];
+                gv.pos = its.p;
+                gv.dir = wo;
+                gv.pdf = bsdfPdf;
+                gv.T = throughput;
+                gv.Lk = LafterNee;
+                gv.dist = 0.0f;
+            }
             if (shape.isMediumTransition()) medium = targetMedium(shape, its.geoN, ray.d);
             if (sampledType == ENull) {  // index-matched boundary (:318-328)
                 emittedRadiance = !scattered;
@@ -229,6 +319,7 @@ static Vec3 Li_volpath(const Scene &scene, const B200pgIntegratorParams &P, cons
             Vec3 value(0.0f);
             Rng fr = rng.fork();
             rayIntersectAndLookForEmitter(scene, fr, medium, maxDepth - depth - 1, ray, its, dRec, value, st);
+            if (record && (btype & ESmooth) && nVerts > 0 && its.isValid()) verts[nVerts - 1].dist = its.t;
             if (!value.isZero()) {
                 const Float emitterPdf = (P.use_nee && !(sampledType & EDelta)) ? scene.pdfEmitterDirect(dRec) : 0;
                 const Float weight = P.use_nee ? miWeight(bsdfPdf, emitterPdf) : 1.0f;
@@ -245,6 +336,16 @@ static Vec3 Li_volpath(const Scene &scene, const B200pgIntegratorParams &P, cons
     }
     st.paths++;
     st.pathLen += depth;
+    if (record) {  // same training-sample definition as Li_path
+        for (int v = 0; v < nVerts; ++v) {
+            const GuideVertex &gv = verts[v];
+            Vec3 dL = Li - gv.Lk, est(0.0f);
+            for (int c = 0; c < 3; ++c) est[c] = gv.T[c] > 0 ? dL[c] / gv.T[c] : 0.0f;
+            Float w = est.average() / gv.pdf;
+            if (!std::isfinite(w) || w < 0) w = 0.0f;
+            G->rec->push(gv.pos, gv.dir, w, gv.pdf, gv.dist);
+        }
+    }
     return Li;
 }
 

@@ -148,3 +148,41 @@ def test_volumetric_render_is_energy_consistent(pkg, oracle):
     T = np.exp(-1.3 * 1.0)
     assert set(np.unique(L[:, 0])).issubset({0.0, 1.0})  # the camera ray either reaches the emitter or is absorbed
     assert abs(L[:, 0].mean() - T) < 4 * np.sqrt(T * (1 - T) / n)
+
+
+def test_guided_volumetric_path_is_unbiased(pkg, oracle):
+    """Guided direction sampling at medium / surface vertices and guided collision probabilities (weighted delta
+    tracking) change the sampling, not the expectation: the guided mean image matches the unguided one."""
+    from b200pg import api
+    from oracle_lib import develop
+
+    sb = pkg.scenes.cornell_medium(40, 40, spp=8, res=24, scale_=12.0)
+    sc = oracle.scene(sb)
+    p = api.default_params()
+    p.max_depth = 6
+    p.volumetric = 1
+    p.guiding_probability = 0.5
+    fld = oracle.field(8, (-1.1, -0.1, -1.1), (1.1, 2.1, 1.1))
+    sink = oracle.samples()
+    for it in range(4):
+        sink.clear()
+        sc.render(p, 100 * it, 8, field=fld if it else None, sink=sink)
+        s = sink.get()
+        assert len(s["weight"]) > 10000 and np.isfinite(s["weight"]).all() and (s["weight"] >= 0).all()
+        assert np.allclose(np.linalg.norm(s["dir"], axis=1), 1, atol=1e-4)
+        # medium vertices are recorded too: positions strictly inside the medium box, away from every wall
+        inside = (np.abs(s["pos"][:, 0]) < 0.59) & (np.abs(s["pos"][:, 2]) < 0.59) & (s["pos"][:, 1] > 0.21) & (s["pos"][:, 1] < 1.39)
+        assert inside.mean() > 0.05
+        fld.train(s, 4, 4000)
+    assert fld.info()["cells"] > 1
+    ref = develop(sc.render(p, 5000, 768)[0])
+    tol = 0.02 * ref.mean()
+    g_dir = develop(sc.render(p, 0, 384, field=fld)[0])
+    assert abs(g_dir.mean() - ref.mean()) < tol
+    p.guided_distance = 1
+    g_dist = develop(sc.render(p, 0, 384, field=fld)[0])
+    assert abs(g_dist.mean() - ref.mean()) < tol
+    # region-wise too (the medium cube covers the image centre): guards against compensating errors
+    c = slice(12, 28)
+    assert abs(g_dist[c, c].mean() - ref[c, c].mean()) < 0.03 * ref[c, c].mean()
+    assert abs(g_dir[c, c].mean() - ref[c, c].mean()) < 0.03 * ref[c, c].mean()
