@@ -249,6 +249,14 @@ struct Integrator {
     void runBatch(const BatchDesc &B, float *radianceOut) {
         ensureBatch(B.nPaths);
         guide.ensureBatch(B.nPaths);
+        if (guide.active && guide.recording) {  // room for this batch's training samples (renderProgression sizes it for a
+            // whole progression beforehand; this covers stand-alone batches such as b200pg_k_radiance)
+            const size_t want = std::min<size_t>((size_t)B.nPaths * guide.maxVerts, (size_t)48 << 20);
+            if (want > guide.sampleCapacity) {
+                guide.dSPos.alloc(want); guide.dSDir.alloc(want); guide.dSDist.alloc(want);
+                guide.sampleCapacity = want;
+            }
+        }
         const size_t zeroBytes = offsetof(Counters, paths);
         CUDA_OK(cudaMemsetAsync(dCounters.p, 0, zeroBytes, stream));
         PathState cur = bufA.view(), next = bufB.view();

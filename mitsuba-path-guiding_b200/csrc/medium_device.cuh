@@ -6,6 +6,7 @@
 //   phaseEval / phaseSample   src/phase/hg.cpp:74-110, src/phase/isotropic.cpp:62-78
 #pragma once
 #include "device_scene.cuh"
+#include "guiding_device.cuh"
 
 namespace pg {
 
@@ -75,6 +76,41 @@ PG_DEV bool mediumSampleDistance(const MediumRecord &M, const float *density, fl
             mRec.transmittance = tr;
             return true;
         }
+    }
+    return false;
+}
+
+// Guided free-flight sampling: weighted delta tracking with field-steered collision probabilities (this repo's design;
+// CPU statement and derivation: oracle/oracle_medium.h sampleDistanceGuided, DESIGN.md "Guiding in media").
+PG_DEV bool mediumSampleDistanceGuided(const MediumRecord &M, const float *density, const GuideDevice &G, float3 o, float3 d,
+                                       float rmint, float rmaxt, MediumSample &mRec, float3 &weight, Rng &rng) {
+    weight = f3(1.0f);
+    float mint, maxt;
+    if (!mediumClip(M, o, d, mint, maxt)) return false;
+    mint = fmaxf(mint, rmint);
+    maxt = fminf(maxt, rmaxt);
+    const float3 albedo = ld3(M.albedo);
+    const float albedoAvg = (albedo.x + albedo.y + albedo.z) * (1.0f / 3.0f);
+    const float beta = 0.5f;
+    float t = mint;
+    while (true) {
+        t -= logf(1 - rng.next1D()) * M.invMaxDensity;
+        if (t >= maxt) break;
+        const float3 p = o + d * t;
+        const float a = fminf(gridLookup(M, density, p) * M.scale * M.invMaxDensity, 1.0f);
+        const float u = rng.next1D();
+        if (!(a > 0)) continue;
+        const float g = 4 * kPi * guidePdf(G, guideLookup(G, p), d);
+        const float num = a * albedoAvg, den = num + (1 - a) * g;
+        const float pGuided = den > 0 ? num / den : a;
+        const float pReal = (1 - beta) * a + beta * pGuided;
+        if (u < pReal) {
+            weight = weight * (albedo * (a / pReal));
+            mRec.t = t;
+            mRec.p = p;
+            return true;
+        }
+        weight = weight * ((1 - a) / (1 - pReal));
     }
     return false;
 }

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_vol(ShadeArgs A) {
         int shMedium = -1, shInteractions = 0;
         uint32_t shOnSurface = 0;
         uint64_t shRng = 0;
-        uint32_t depth = 0;
+        uint32_t depth = 0, vcount = 0;
 
         if (valid) {
             const float4 ro = A.cur.rayO[i], rd = A.cur.rayD[i], thr4 = A.cur.thr[i], rad4 = A.cur.rad[i];
@@ -134,6 +134,15 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_vol(ShadeArgs A) {
             h.u = h4.y;
             h.v = h4.z;
             h.prim = __float_as_uint(h4.w);
+            vcount = (fl >> kVertShift) & 0xFFu;
+            if (A.G.record && vcount > 0 && !(fl & kFlagVertexClosed)) {
+                // close the previous training vertex: radiance gathered so far (its NEE has landed by now) and the
+                // distance to the first surface along the sampled ray
+                const size_t vi = (size_t)slot * A.G.maxVerts + (vcount - 1);
+                A.G.vL[vi] = make_float4(L.x, L.y, L.z, 0.0f);
+                A.G.vDir[vi].w = h.prim == kMiss ? 0.0f : h.t;
+                fl |= kFlagVertexClosed;
+            }
 
             if (fl & kFlagDead) {
                 terminate = true;
@@ -175,14 +184,22 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_vol(ShadeArgs A) {
                     // ---- free-flight distance in the current medium (:118-121)
                     MediumSample mRec;
                     bool mediumEvent = false;
-                    if (medium >= 0)
+                    const bool guidedDist = A.G.enabled && cfg.guidedDistance && medium >= 0;
+                    float3 distWeight = f3(1.0f);
+                    if (guidedDist)
+                        mediumEvent = mediumSampleDistanceGuided(S.media[medium], S.density, A.G, o, d, 0.0f, hitValid ? h.t : kInf, mRec,
+                                                                 distWeight, rng);
+                    else if (medium >= 0)
                         mediumEvent = mediumSampleDistance(S.media[medium], S.density, o, d, 0.0f, hitValid ? h.t : kInf, mRec, rng);
+                    if (guidedDist) thr *= distWeight;  // real-collision and null-collision weights alike
                     if (mediumEvent) {
                         const MediumRecord &M = S.media[medium];
                         if ((int)depth >= maxDepth && maxDepth != -1) {
                             terminate = true;  // (:128-129)
                         } else {
-                            thr *= mRec.sigmaS * mRec.transmittance;  // pdfSuccess == 1 for Woodcock tracking
+                            if (!guidedDist) thr *= mRec.sigmaS * mRec.transmittance;  // pdfSuccess == 1 for Woodcock tracking
+                            const bool guided = A.G.enabled != 0;
+                            const uint32_t gcell = guided ? guideLookup(A.G, mRec.p) : 0u;
                             if (cfg.useNee) {  // (:137-168)
                                 DirectSample dRec;
                                 const float2 u = rng.next2D();
@@ -191,7 +208,9 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_vol(ShadeArgs A) {
                                 if (!isZero(value)) {
                                     const float phaseVal = phaseEval(M, -d, dRec.d);
                                     if (phaseVal != 0) {
-                                        const float weight = miWeight(dRec.pdf, phaseVal);  // phase pdf == phase value
+                                        float dirPdf = phaseVal;  // phase pdf == phase value
+                                        if (guided) dirPdf = A.G.alpha * guidePdf(A.G, gcell, dRec.d) + (1 - A.G.alpha) * phaseVal;
+                                        const float weight = miWeight(dRec.pdf, dirPdf);
                                         shC = thr * value * phaseVal * weight;
                                         shO = mRec.p;
                                         shD = dRec.d;
@@ -205,7 +224,35 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_vol(ShadeArgs A) {
                                 }
                             }
                             float phasePdf;
-                            const float3 wo = phaseSample(M, -d, rng.next2D(), phasePdf);  // phase weight == 1
+                            float3 wo;
+                            bool dirOk = true;
+                            if (guided) {  // one-sample MIS between the mixture and the phase function
+                                const float u0 = rng.next1D();
+                                const float2 u12 = rng.next2D();
+                                float pp;
+                                if (u0 < A.G.alpha) {
+                                    wo = guideSample(A.G, gcell, u0 / A.G.alpha, u12.x, u12.y);
+                                    pp = phaseEval(M, -d, wo);
+                                } else {
+                                    wo = phaseSample(M, -d, u12, pp);
+                                }
+                                phasePdf = A.G.alpha * guidePdf(A.G, gcell, wo) + (1 - A.G.alpha) * pp;
+                                dirOk = pp > 0 && phasePdf > 0;
+                                if (dirOk) thr = thr * (pp / phasePdf);
+                            } else {
+                                wo = phaseSample(M, -d, rng.next2D(), phasePdf);  // phase weight == 1
+                            }
+                            if (!dirOk) {
+                                terminate = true;
+                            } else {
+                            if (A.G.record && (int)vcount < A.G.maxVerts) {
+                                const size_t vi = (size_t)slot * A.G.maxVerts + vcount;
+                                A.G.vPos[vi] = make_float4(mRec.p.x, mRec.p.y, mRec.p.z, phasePdf);
+                                A.G.vDir[vi] = make_float4(wo.x, wo.y, wo.z, 0.0f);
+                                A.G.vThr[vi] = make_float4(thr.x, thr.y, thr.z, 0.0f);
+                                vcount++;
+                                fl &= ~kFlagVertexClosed;
+                            }
                             newO = mRec.p;
                             newD = wo;
                             newMint = 0.0f;
@@ -213,6 +260,7 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_vol(ShadeArgs A) {
                             fl &= ~kFlagPrevDelta;
                             fl |= kFlagPrevMedium | kFlagLook;
                             alive = true;
+                            }
                         }
                     } else if (!hitValid) {
                         terminate = true;  // no environment emitter on this path (:183-195)
@@ -229,6 +277,8 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_vol(ShadeArgs A) {
                             terminate = true;  // (:207-216)
                         } else {
                             const uint32_t btype = bsdf.typeFlags;
+                            const bool guided = A.G.enabled && (btype & kSmooth);
+                            const uint32_t gcell = guided ? guideLookup(A.G, its.p) : 0u;
                             if (cfg.useNee && (btype & kSmooth)) {  // (:226-262)
                                 const float3 refN = (btype & (kTransmission | kBackSide)) == 0 ? its.sh.n : f3(0.0f);
                                 DirectSample dRec;
@@ -239,7 +289,8 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_vol(ShadeArgs A) {
                                     const float3 woL = its.sh.toLocal(dRec.d);
                                     const float3 bsdfVal = bsdfEval(bsdf, its.wi, woL);
                                     if (!isZero(bsdfVal) && (!cfg.strictNormals || dot(its.geoN, dRec.d) * woL.z > 0)) {
-                                        const float bPdf = bsdfPdf(bsdf, its.wi, woL);
+                                        float bPdf = bsdfPdf(bsdf, its.wi, woL);
+                                        if (guided) bPdf = A.G.alpha * guidePdf(A.G, gcell, dRec.d) + (1 - A.G.alpha) * bPdf;
                                         const float weight = miWeight(dRec.pdf, bPdf);
                                         shC = thr * value * bsdfVal * weight;
                                         shO = its.p;
@@ -256,9 +307,32 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_vol(ShadeArgs A) {
                             // ---- BSDF sampling (:268-283)
                             float bPdf, bEta;
                             uint32_t sampledType;
-                            float3 woL;
-                            const float3 bsdfWeight = bsdfSample(bsdf, its.wi, rng.next2D(), woL, bPdf, bEta, sampledType);
-                            const float3 wo = its.sh.toWorld(woL);
+                            float3 woL, wo, bsdfWeight;
+                            if (guided) {
+                                const float u0 = rng.next1D();
+                                const float2 u12 = rng.next2D();
+                                float3 fcos;
+                                float pb;
+                                bool ok = true;
+                                if (u0 < A.G.alpha) {
+                                    wo = guideSample(A.G, gcell, u0 / A.G.alpha, u12.x, u12.y);
+                                    woL = its.sh.toLocal(wo);
+                                    fcos = bsdfEval(bsdf, its.wi, woL);
+                                    pb = bsdfPdf(bsdf, its.wi, woL);
+                                    bEta = 1.0f;
+                                    sampledType = kGlossyReflection;
+                                } else {
+                                    const float3 w = bsdfSample(bsdf, its.wi, u12, woL, pb, bEta, sampledType);
+                                    ok = !isZero(w);
+                                    fcos = w * pb;
+                                    wo = its.sh.toWorld(woL);
+                                }
+                                bPdf = ok ? A.G.alpha * guidePdf(A.G, gcell, wo) + (1 - A.G.alpha) * pb : 0.0f;
+                                bsdfWeight = (ok && !isZero(fcos) && bPdf > 0) ? fcos / bPdf : f3(0.0f);
+                            } else {
+                                bsdfWeight = bsdfSample(bsdf, its.wi, rng.next2D(), woL, bPdf, bEta, sampledType);
+                                wo = its.sh.toWorld(woL);
+                            }
                             if (isZero(bsdfWeight) || (cfg.strictNormals && dot(its.geoN, wo) * woL.z <= 0)) {
                                 terminate = true;
                             } else {
@@ -268,6 +342,14 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_vol(ShadeArgs A) {
                                 newD = wo;
                                 newMint = kEpsilon;
                                 newPdf = bPdf;
+                                if (A.G.record && (btype & kSmooth) && (int)vcount < A.G.maxVerts) {
+                                    const size_t vi = (size_t)slot * A.G.maxVerts + vcount;
+                                    A.G.vPos[vi] = make_float4(its.p.x, its.p.y, its.p.z, bPdf);
+                                    A.G.vDir[vi] = make_float4(wo.x, wo.y, wo.z, 0.0f);
+                                    A.G.vThr[vi] = make_float4(thr.x, thr.y, thr.z, 0.0f);
+                                    vcount++;
+                                    fl &= ~kFlagVertexClosed;
+                                }
                                 if (transition) medium = dot(wo, its.geoN) > 0 ? sr.exteriorMedium : sr.interiorMedium;  // (:314-315)
                                 fl &= ~(kFlagPrevDelta | kFlagPrevMedium);
                                 if (sampledType == kNull) {
@@ -299,7 +381,7 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_vol(ShadeArgs A) {
             A.next.thr[j] = make_float4(thr.x, thr.y, thr.z, eta);
             A.next.rad[j] = make_float4(L.x, L.y, L.z, newPdf);
             A.next.pos[j] = make_float4(pos4.x, pos4.y, __uint_as_float((uint32_t)rng.state), __uint_as_float((uint32_t)(rng.state >> 32)));
-            A.next.flags[j] = (fl & ~kDepthMask) | (depth & kDepthMask);
+            A.next.flags[j] = (fl & ~(kDepthMask | (0xFFu << kVertShift))) | (depth & kDepthMask) | (vcount << kVertShift);
             A.next.slot[j] = slot;
             A.next.medium[j] = medium;
         }
@@ -315,6 +397,7 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_vol(ShadeArgs A) {
             doneLen += depth;
             finishPath(A, slot, pos4, L);
         }
+        if (A.G.record) emitTrainingSamples(A.G, valid && terminate, slot, vcount, L);
     }
     warpAddU64(&A.C->paths, donePaths);
     warpAddU64(&A.C->pathLen, doneLen);

@@ -147,3 +147,80 @@ def test_full_size_c3_properties(api, pkg):
     it.progression(0, 2)
     np.testing.assert_allclose(it.film(), 2 * f, rtol=1e-4, atol=1e-4)
     assert 1.0 <= st["path_length_sum"] / st["paths"] <= 8.0
+
+
+# ---- guided volumetric path (direction guiding at medium / surface vertices, guided free-flight sampling) -------------
+@pytest.fixture(scope="module")
+def trained_medium(pkg, api, oracle):
+    """A field trained on the GPU by the volumetric integrator (4 progressions), mirrored into the oracle."""
+    sb = pkg.scenes.cornell_medium(96, 96, spp=8, res=32, scale_=12.0)
+    p = _params(api, guiding=1, guide_max_components=16, guide_max_cell_samples=6000)
+    it = api.Integrator(api.Scene.from_builder(sb), p)
+    counts = []
+    for k in range(4):
+        it.guiding_mode(True, k > 0)
+        it.progression(100 * k, 4)
+        counts.append(it.train_fused(4))
+    snap = it.field_snapshot()
+    fld = oracle.field(16, (0, 0, 0), (1, 1, 1))
+    fld.load(snap)
+    return sb, p, it, fld, snap, counts, oracle.scene(sb)
+
+
+def test_volumetric_training_records_medium_vertices(trained_medium):
+    sb, p, it, fld, snap, counts, osc = trained_medium
+    assert all(n > 20000 for n, c in counts)
+    assert counts[-1][1] > counts[0][1] >= 1  # the spatial tree grew
+    assert fld.info()["cells"] == counts[-1][1] or fld.info()["cells"] >= counts[-1][1]
+
+
+@pytest.mark.parametrize("guided_distance", [0, 1])
+def test_guided_vol_radiance_sample_by_sample(api, trained_medium, guided_distance):
+    sb, p, it0, fld, snap, counts, osc = trained_medium
+    p2 = _params(api, guiding=1, guide_max_components=16, guide_max_cell_samples=6000, guided_distance=guided_distance)
+    it = api.Integrator(api.Scene.from_builder(sb), p2)
+    it.field_load(snap)
+    it.guiding_mode(False, True)
+    rng = np.random.RandomState(3)
+    n = 40000
+    pix = rng.randint(0, sb.width * sb.height, n).astype(np.uint32)
+    smp = rng.randint(0, 1000, n).astype(np.uint32)
+    want = osc.radiance(p2, pix, smp, field=fld)
+    got = it.k_radiance(pix, smp)
+    err = np.abs(got - want).max(1) / (np.abs(want).max(1) + 1e-3)
+    # guided tracking makes a field query per tentative collision: more decisions that can flip on rounding
+    assert (err > 1e-3).mean() < (1e-2 if guided_distance else 5e-3), float((err > 1e-3).mean())
+    assert abs(got.mean() - want.mean()) < 5e-3 * want.mean()
+    # unbiased: the unguided estimator of the same integrator agrees in the mean
+    it.guiding_mode(False, False)
+    plain = it.k_radiance(pix, smp)
+    assert abs(plain.mean() - got.mean()) < 0.04 * plain.mean()
+
+
+def test_guided_vol_training_samples_match_oracle(api, trained_medium):
+    sb, p, it0, fld, snap, counts, osc = trained_medium
+    from oracle_lib import Oracle
+
+    it = api.Integrator(api.Scene.from_builder(sb), p)
+    it.field_load(snap)
+    it.guiding_mode(True, True)
+    rng = np.random.RandomState(4)
+    n = 20000
+    pix = rng.randint(0, sb.width * sb.height, n).astype(np.uint32)
+    smp = rng.randint(0, 1000, n).astype(np.uint32)
+    sink = Oracle().samples()
+    osc.radiance(p, pix, smp, field=fld, sink=sink)
+    s = sink.get()
+    it.k_radiance(pix, smp)
+    ns, nc = it.train_begin()
+    assert abs(ns - len(s["weight"])) <= 0.005 * ns
+    it.train_accumulate()
+    it.train_update(True)
+    it.train_end()
+    # the oracle's samples through the GPU E-step give the oracle's statistics
+    st_o = fld.estep(s)
+    it2 = api.Integrator(api.Scene.from_builder(sb), p)
+    it2.field_load(snap)
+    st_g = it2.k_em_step(s, 0, fld.info()["cells"], fld.info()["K"])
+    scale = np.maximum(np.abs(st_o).max(1, keepdims=True), 1e-6)
+    assert (np.abs(st_o - st_g) / scale).max() <= 2e-5
