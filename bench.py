@@ -121,8 +121,7 @@ def guided_params(pkg, args):
     p.guide_max_components = 16
     p.guide_max_cell_samples = 32768
     p.volumetric = 1 if args.workload == "medium_1024" else 0
-    if p.volumetric:
-        p.guiding = 0  # guided volumetric paths: see DESIGN.md (surface guiding only in this round)
+    p.guided_distance = 1 if (p.volumetric and p.guiding and args.guided_distance) else 0
     return p
 
 
@@ -177,9 +176,11 @@ def main():
     ap.add_argument("--em-iters", type=int, default=4)
     ap.add_argument("--pretrain", type=int, default=12, help="untimed training iterations before warm-up (steady-state field)")
     ap.add_argument("--no-guiding", action="store_true")
+    ap.add_argument("--guided-distance", action="store_true", help="medium workloads: guided free-flight sampling")
     ap.add_argument("--nccl-allreduce", action="store_true", help="sum EM statistics with torch.distributed/NCCL instead of the fused peer-memory kernel")
     ap.add_argument("--ref-seconds", type=float, default=3.0)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -395,6 +396,8 @@ def main():
         try:
             if world > 1:
                 raise RuntimeError("reported at N=1 only")
+            if args.no_cpu_baseline:
+                raise RuntimeError("skipped (--no-cpu-baseline)")
             ncores = len(os.sched_getaffinity(0))  # torchrun sets OMP_NUM_THREADS=1: ask for all host cores explicitly
             cb = CpuGuidedStep(pkg, sb, p, guided, args.em_iters, ncores)
             if guided:

@@ -574,7 +574,7 @@ void GuidingHost::ensureBatch(size_t nPaths) {
     if (!active) return;
     const size_t nv = nPaths * (size_t)maxVerts;
     if (nv > vertCapacity) {
-        dVPos.alloc(nv); dVDir.alloc(nv); dVThr.alloc(nv); dVL.alloc(nv);
+        dVRec.alloc(4 * nv);
         vertCapacity = nv;
     }
 }
@@ -589,7 +589,7 @@ void GuidingHost::configure(ShadeArgs &A) {
     G.alpha = alpha;
     G.enabled = active && sampling && trained;
     G.record = active && recording;
-    G.vPos = dVPos.p; G.vDir = dVDir.p; G.vThr = dVThr.p; G.vL = dVL.p;
+    G.vRec = dVRec.p;
     G.maxVerts = maxVerts;
     G.sPos = dSPos.p; G.sDir = dSDir.p; G.sDist = dSDist.p;
     G.sCount = dSCount.p;

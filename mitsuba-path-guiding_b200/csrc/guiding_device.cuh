@@ -28,11 +28,12 @@ struct GuideDevice {
     int enabled;           // sample from the field in the shade stage
     int record;            // record training vertices
     float alpha;           // selection probability of the guiding distribution
-    // training-vertex records, indexed [slot * maxVerts + v]
-    float4 *vPos;          // position, pdf of the sampled direction
-    float4 *vDir;          // sampled direction, distance to the next vertex
-    float4 *vThr;          // throughput right after the vertex
-    float4 *vL;            // radiance gathered up to and including the vertex' NEE
+    // training-vertex records, 64 B = 4 x float4 at [(slot * maxVerts + v) * 4]: two whole 32-byte sectors, each written
+    // by ONE shade invocation (HBM3e is ECC-protected: a partially written sector costs a read-modify-write):
+    //   sector A (when the vertex is sampled): {position, pdf of the sampled direction} {sampled direction, 0}
+    //   sector B (one bounce later, "closing"): {throughput right after the vertex, distance to the next hit}
+    //                                           {radiance gathered up to and including the vertex' NEE, 0}
+    float4 *vRec;
     int maxVerts;
     // training samples (output of finished paths)
     float4 *sPos;          // position, weight

@@ -57,7 +57,7 @@ struct GuidingHost {
     std::vector<float> stageQuery, stageStats;  // host staging of the two device lobe arrays
 
     // training-vertex records and samples
-    DevBuf<float4> dVPos, dVDir, dVThr, dVL;
+    DevBuf<float4> dVRec;  // 4 x float4 per training vertex
     DevBuf<float4> dSPos, dSDir, dSortPos, dSortDir;
     DevBuf<float> dSDist;
     DevBuf<uint32_t> dSCount;

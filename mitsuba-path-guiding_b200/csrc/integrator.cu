@@ -44,8 +44,7 @@ void launchGridLookup(const DeviceScene &S, int medium, const float *p, uint32_t
 void launchMediumTest(const DeviceScene &S, int medium, const float4 *rays, uint32_t n, float *outT, float *outTr, float *outWo,
                       float *outPdf, cudaStream_t st);
 void launchFilmExport(const float4 *film, float *out, uint32_t n, int develop, cudaStream_t st);
-void launchSplat(const FilmRecord &F, float4 *film, const float4 *splatA, const float *splatB, uint32_t n, float maxComponentValue,
-                 cudaStream_t st);
+void launchSplat(const FilmRecord &F, float4 *film, const float4 *splat, uint32_t n, float maxComponentValue, cudaStream_t st);
 void launchTraceRays(const DeviceScene &S, const float4 *rays, uint32_t n, float4 *hits, uint32_t *work, Counters *C, bool shadow,
                      bool count, cudaStream_t st);
 void launchFilmSplat(const FilmRecord &F, float4 *film, const float2 *pos, const float3 *rgb, uint32_t n, float maxComponentValue,
@@ -98,8 +97,7 @@ struct Integrator {
     DevBuf<float4> dHits, dShO, dShD, dShC;
     DevBuf<int32_t> dShMedium;
     DevBuf<uint4> dShAux;
-    DevBuf<float4> dSplatA;
-    DevBuf<float> dSplatB;
+    DevBuf<float4> dSplat;
     DevBuf<Counters> dCounters;
     DevBuf<float4> dFilm;
     DevBuf<float> dFilmOut;
@@ -224,7 +222,7 @@ struct Integrator {
         bufA.alloc(n); bufB.alloc(n);
         dHits.alloc(n); dShO.alloc(n); dShD.alloc(n); dShC.alloc(n); dShMedium.alloc(n);
         if (params.volumetric) dShAux.alloc(n);
-        dSplatA.alloc(n); dSplatB.alloc(n);
+        dSplat.alloc(2 * n);
         batchCapacity = n;
     }
 
@@ -271,8 +269,7 @@ struct Integrator {
         A.C = dCounters.p;
         A.film = dFilm.p;
         A.radianceOut = radianceOut;
-        A.splatA = dSplatA.p;
-        A.splatB = dSplatB.p;
+        A.splat = dSplat.p;
         const int maxBounces = params.max_depth > 0 ? std::min(params.max_depth + 1, 256) : 256;
         Counters *C = dCounters.p;
         int b = 0;
@@ -312,7 +309,7 @@ struct Integrator {
         stats.kernel_launches++;
         if (!radianceOut && !cancel.load()) {  // every path of the batch has ended exactly once: rasterise them
             cudaEvent_t t = spanBegin();
-            launchSplat(S.film, dFilm.p, dSplatA.p, dSplatB.p, B.nPaths, params.max_component_value, stream);
+            launchSplat(S.film, dFilm.p, dSplat.p, B.nPaths, params.max_component_value, stream);
             spanEnd(kTimeFilm, t);
             stats.kernel_launches++;
         }

@@ -290,9 +290,7 @@ __global__ void __launch_bounds__(kShadeThreads, 5) k_shade(ShadeArgs A) {
             if (A.G.record && vcount > 0 && !(fl & kFlagVertexClosed)) {
                 // close the previous training vertex: radiance gathered so far (its NEE has landed by now)
                 // and the distance to this hit
-                const size_t vi = (size_t)slot * A.G.maxVerts + (vcount - 1);
-                A.G.vL[vi] = make_float4(L.x, L.y, L.z, 0.0f);
-                A.G.vDir[vi].w = h.prim == kMiss ? 0.0f : h.t;
+                guideVertexClose(A.G, slot, vcount - 1, thr, h.prim == kMiss ? 0.0f : h.t, L);
                 fl |= kFlagVertexClosed;
             }
 
@@ -419,10 +417,7 @@ __global__ void __launch_bounds__(kShadeThreads, 5) k_shade(ShadeArgs A) {
                             if (sampledType != kNull) fl |= kFlagScattered;
                             alive = true;
                             if (A.G.record && (btype & kSmooth) && (int)vcount < A.G.maxVerts) {
-                                const size_t vi = (size_t)slot * A.G.maxVerts + vcount;
-                                A.G.vPos[vi] = make_float4(its.p.x, its.p.y, its.p.z, bPdf);
-                                A.G.vDir[vi] = make_float4(wo.x, wo.y, wo.z, 0.0f);
-                                A.G.vThr[vi] = make_float4(thr.x, thr.y, thr.z, 0.0f);
+                                guideVertexOpen(A.G, slot, vcount, its.p, bPdf, wo);
                                 vcount++;
                                 fl &= ~kFlagVertexClosed;
                             }
@@ -470,11 +465,11 @@ __global__ void __launch_bounds__(kShadeThreads, 5) k_shade(ShadeArgs A) {
 
 // Film accumulation for a finished batch: one thread per camera sample, in slot (= pixel) order, so the
 // 32 float4 atomics of a warp instruction fall on neighbouring texels.
-__global__ void __launch_bounds__(256) k_splat(FilmRecord F, float4 *film, const float4 *__restrict__ splatA,
-                                               const float *__restrict__ splatB, uint32_t n, float maxComponentValue) {
+__global__ void __launch_bounds__(256) k_splat(FilmRecord F, float4 *film, const float4 *__restrict__ splat, uint32_t n,
+                                               float maxComponentValue) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 a = splatA[i];
-        filmSplat(F, film, make_float2(a.x, a.y), f3(a.z, a.w, splatB[i]), maxComponentValue);
+        const float4 a = splat[2 * (size_t)i], b = splat[2 * (size_t)i + 1];
+        filmSplat(F, film, make_float2(a.x, a.y), f3(a.z, a.w, b.x), maxComponentValue);
     }
 }
 
@@ -564,10 +559,9 @@ void launchShade(const ShadeArgs &A, cudaStream_t st) {
     static int grid = persistentGrid(k_shade, kShadeThreads);
     k_shade<<<grid, kShadeThreads, 0, st>>>(A);
 }
-void launchSplat(const FilmRecord &F, float4 *film, const float4 *splatA, const float *splatB, uint32_t n, float maxComponentValue,
-                 cudaStream_t st) {
+void launchSplat(const FilmRecord &F, float4 *film, const float4 *splat, uint32_t n, float maxComponentValue, cudaStream_t st) {
     static int grid = persistentGrid(k_splat, 256);
-    k_splat<<<grid, 256, 0, st>>>(F, film, splatA, splatB, n, maxComponentValue);
+    k_splat<<<grid, 256, 0, st>>>(F, film, splat, n, maxComponentValue);
 }
 void launchFilmExport(const float4 *film, float *out, uint32_t n, int develop, cudaStream_t st) {
     k_film_export<<<numSMs() * 4, 256, 0, st>>>(film, out, n, develop);

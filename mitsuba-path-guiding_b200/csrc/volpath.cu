@@ -138,9 +138,7 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_vol(ShadeArgs A) {
             if (A.G.record && vcount > 0 && !(fl & kFlagVertexClosed)) {
                 // close the previous training vertex: radiance gathered so far (its NEE has landed by now) and the
                 // distance to the first surface along the sampled ray
-                const size_t vi = (size_t)slot * A.G.maxVerts + (vcount - 1);
-                A.G.vL[vi] = make_float4(L.x, L.y, L.z, 0.0f);
-                A.G.vDir[vi].w = h.prim == kMiss ? 0.0f : h.t;
+                guideVertexClose(A.G, slot, vcount - 1, thr, h.prim == kMiss ? 0.0f : h.t, L);
                 fl |= kFlagVertexClosed;
             }
 
@@ -246,10 +244,7 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_vol(ShadeArgs A) {
                                 terminate = true;
                             } else {
                             if (A.G.record && (int)vcount < A.G.maxVerts) {
-                                const size_t vi = (size_t)slot * A.G.maxVerts + vcount;
-                                A.G.vPos[vi] = make_float4(mRec.p.x, mRec.p.y, mRec.p.z, phasePdf);
-                                A.G.vDir[vi] = make_float4(wo.x, wo.y, wo.z, 0.0f);
-                                A.G.vThr[vi] = make_float4(thr.x, thr.y, thr.z, 0.0f);
+                                guideVertexOpen(A.G, slot, vcount, mRec.p, phasePdf, wo);
                                 vcount++;
                                 fl &= ~kFlagVertexClosed;
                             }
@@ -343,10 +338,7 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_vol(ShadeArgs A) {
                                 newMint = kEpsilon;
                                 newPdf = bPdf;
                                 if (A.G.record && (btype & kSmooth) && (int)vcount < A.G.maxVerts) {
-                                    const size_t vi = (size_t)slot * A.G.maxVerts + vcount;
-                                    A.G.vPos[vi] = make_float4(its.p.x, its.p.y, its.p.z, bPdf);
-                                    A.G.vDir[vi] = make_float4(wo.x, wo.y, wo.z, 0.0f);
-                                    A.G.vThr[vi] = make_float4(thr.x, thr.y, thr.z, 0.0f);
+                                    guideVertexOpen(A.G, slot, vcount, its.p, bPdf, wo);
                                     vcount++;
                                     fl &= ~kFlagVertexClosed;
                                 }

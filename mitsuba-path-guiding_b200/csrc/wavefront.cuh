@@ -83,8 +83,7 @@ struct ShadeArgs {
     const float4 *hits;
     Counters *C;
     float4 *film;
-    float4 *splatA;      // per slot: samplePos.xy, L.r, L.g   (written once, when the path ends)
-    float *splatB;       // per slot: L.b
+    float4 *splat;       // per slot, 2 x float4 = one 32-byte sector: {samplePos.xy, L.r, L.g} {L.b, 0, 0, 0} (written once)
     float *radianceOut;  // optional: per-slot radiance instead of film splats (b200pg_k_radiance)
     GuideDevice G;
     int bounce;
