@@ -159,6 +159,177 @@ __global__ void __launch_bounds__(256) k_cell_starts(const uint32_t *__restrict_
     }
 }
 
+// ---- block-wide helpers for the single-block bookkeeping kernels (1024 threads) ---------------------------------
+__device__ __forceinline__ uint32_t blockExclusiveScan1024(uint32_t v, uint32_t *smem33, uint32_t &total) {
+    // smem33: 33 words. Returns the exclusive prefix of v over the block's 1024 threads; total = block sum.
+    const uint32_t ln = lane(), wp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)ln >= o) incl += t;
+    }
+    __syncthreads();
+    if (ln == 31) smem33[wp] = incl;
+    __syncthreads();
+    if (wp == 0) {
+        uint32_t w = smem33[ln], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if ((int)ln >= o) wi += t;
+        }
+        smem33[ln] = wi - w;
+        if (ln == 31) smem33[32] = wi;
+    }
+    __syncthreads();
+    total = smem33[32];
+    return smem33[wp] + incl - v;
+}
+
+// Work list of one training update, built on the device (no host round trip between binning and the EM iterations):
+//   offsets[c]  = first sorted sample of cell c (suffix minimum of the cell starts; empty cells inherit the next start)
+//   workOfs[c]  = first work item of cell c, items = chunks of <= kChunk consecutive samples of ONE cell
+//   counts[2]   = number of work items
+// One block of 1024 threads; nCells <= 16 * 1024.
+__global__ void __launch_bounds__(1024) k_build_work(const uint32_t *__restrict__ cellStart, uint32_t nCells, uint32_t n, uint32_t chunk,
+                                                     uint32_t *__restrict__ offsets, uint32_t *__restrict__ workOfs,
+                                                     uint32_t *__restrict__ counts) {
+    __shared__ uint32_t sm[33];
+    __shared__ uint32_t carry;
+    const uint32_t per = (nCells + 1023) / 1024;  // consecutive cells per thread
+    const uint32_t c0 = threadIdx.x * per, c1 = min(c0 + per, nCells);
+    // ---- suffix minimum: thread-local, then across threads (reverse inclusive scan with min)
+    uint32_t local = 0xFFFFFFFFu;
+    for (uint32_t c = c1; c-- > c0;) local = min(local, cellStart[c]);
+    // reverse exclusive "min-scan" over threads via shared memory (1024 values): simple log-step
+    __shared__ uint32_t mins[1024];
+    mins[threadIdx.x] = local;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        uint32_t v = mins[threadIdx.x];
+        if (threadIdx.x + o < 1024) v = min(v, mins[threadIdx.x + o]);
+        __syncthreads();
+        mins[threadIdx.x] = v;
+        __syncthreads();
+    }
+    uint32_t after = threadIdx.x + 1 < 1024 ? mins[threadIdx.x + 1] : 0xFFFFFFFFu;  // min over all later threads
+    after = min(after, n);
+    for (uint32_t c = c1; c-- > c0;) {
+        after = min(after, cellStart[c]);
+        offsets[c] = after;
+    }
+    if (threadIdx.x == 0) {
+        offsets[nCells] = n;
+        carry = 0;
+    }
+    __syncthreads();
+    // ---- chunks per cell -> exclusive scan
+    uint32_t mine = 0;
+    for (uint32_t c = c0; c < c1; ++c) mine += (offsets[c + 1] - offsets[c] + chunk - 1) / chunk;
+    uint32_t total;
+    uint32_t run = blockExclusiveScan1024(mine, sm, total);
+    for (uint32_t c = c0; c < c1; ++c) {
+        workOfs[c] = run;
+        run += (offsets[c + 1] - offsets[c] + chunk - 1) / chunk;
+    }
+    if (threadIdx.x == 0) {
+        workOfs[nCells] = total;
+        counts[2] = total;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fill_work(const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ workOfs, uint32_t nCells,
+                                                   uint32_t chunk, const uint32_t *__restrict__ counts, uint4 *__restrict__ work) {
+    const uint32_t nWork = counts[2];
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < nWork; w += gridDim.x * blockDim.x) {
+        uint32_t lo = 0, hi = nCells;  // last cell with workOfs[c] <= w
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (workOfs[mid] <= w) lo = mid; else hi = mid;
+        }
+        const uint32_t b = offsets[lo] + (w - workOfs[lo]) * chunk;
+        work[w] = make_uint4(lo, b, min(b + chunk, offsets[lo + 1]), 0u);
+    }
+}
+
+// Spatial refinement on the device (same rule and arithmetic as oracle_guiding.h guideSplit / the former host code):
+// fold this update's cell statistics into the running headers, split every cell whose running sample count exceeds the
+// threshold at the mean sample position along the axis of largest variance; cells are visited in index order, the
+// left child keeps the parent's index, the right child gets index nCells0 + (number of splitting cells before it).
+// One block of 1024 threads. counts = {nCells, nNodes, nWork, -}.
+__global__ void __launch_bounds__(1024) k_split(uint4 *__restrict__ nodes, float4 *__restrict__ lobes, float4 *__restrict__ lobeStats,
+                                                float2 *__restrict__ cells, uint32_t *__restrict__ cellLeaf, const float *__restrict__ stats,
+                                                uint32_t *__restrict__ counts, int K, int stride, float maxCellSamples, uint32_t maxCells) {
+    __shared__ uint32_t sm[33];
+    const uint32_t nc0 = counts[0], nn0 = counts[1];
+    const uint32_t per = (nc0 + 1023) / 1024;
+    const uint32_t c0 = threadIdx.x * per, c1 = min(c0 + per, nc0);
+    uint32_t mine = 0;
+    for (uint32_t c = c0; c < c1; ++c) {
+        const float *cs = stats + (size_t)stride * c + (size_t)K * 4;
+        float2 h = cells[c];
+        h.x = kGuideDecay * h.x + cs[0];
+        h.y = kGuideDecay * h.y + cs[1];
+        cells[c] = h;
+        bool split = false;
+        if (h.x > maxCellSamples && cs[0] >= 2) {
+            double best = 0.0;
+            for (int a = 0; a < 3; ++a) {
+                const float mean = cs[2 + a] / cs[0];
+                const double var = (double)cs[5 + a] / (double)cs[0] - (double)mean * (double)mean;
+                if (a == 0 || var > best) best = var;
+            }
+            split = best > 0;
+        }
+        mine += split ? 1u : 0u;
+    }
+    uint32_t total;
+    uint32_t rank = blockExclusiveScan1024(mine, sm, total);
+    const uint32_t room = maxCells > nc0 ? maxCells - nc0 : 0u;
+    for (uint32_t c = c0; c < c1; ++c) {
+        const float *cs = stats + (size_t)stride * c + (size_t)K * 4;
+        const float2 h = cells[c];
+        if (!(h.x > maxCellSamples && cs[0] >= 2)) continue;
+        const float n = cs[0];
+        float mean[3];
+        double var[3];
+        for (int a = 0; a < 3; ++a) {
+            mean[a] = cs[2 + a] / n;
+            var[a] = (double)cs[5 + a] / (double)n - (double)mean[a] * (double)mean[a];
+        }
+        int axis = 0;
+        if (var[1] > var[axis]) axis = 1;
+        if (var[2] > var[axis]) axis = 2;
+        if (!(var[axis] > 0)) continue;
+        const uint32_t r = rank++;
+        if (r >= room) continue;  // field is at capacity
+        const uint32_t leaf = cellLeaf[c], left = nn0 + 2 * r, newCell = nc0 + r;
+        nodes[left] = make_uint4(3u, 0u, c, 0u);
+        nodes[left + 1] = make_uint4(3u, 0u, newCell, 0u);
+        nodes[leaf] = make_uint4((uint32_t)axis, __float_as_uint(mean[axis]), left, 0u);
+        cellLeaf[c] = left;
+        cellLeaf[newCell] = left + 1;
+        const float2 hh = make_float2(h.x * 0.5f, h.y * 0.5f);
+        cells[c] = hh;
+        cells[newCell] = hh;
+        for (int k = 0; k < K; ++k) {
+            float4 st = lobeStats[(size_t)c * K + k];
+            st.x *= 0.5f; st.y *= 0.5f; st.z *= 0.5f; st.w *= 0.5f;
+            lobeStats[(size_t)c * K + k] = st;
+            lobeStats[(size_t)newCell * K + k] = st;
+            lobes[((size_t)newCell * K + k) * 2] = lobes[((size_t)c * K + k) * 2];
+            lobes[((size_t)newCell * K + k) * 2 + 1] = lobes[((size_t)c * K + k) * 2 + 1];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t done = min(total, room);
+        counts[0] = nc0 + done;
+        counts[1] = nn0 + 2 * done;
+    }
+}
+
 // ---- E-step ------------------------------------------------------------------------------------------
 // One warp per work item (a chunk of <= kChunk consecutive samples of ONE cell, gathered into sorted order
 // beforehand); lane = sample. The cell's K lobes sit in shared memory (broadcast reads), every lane evaluates all K
@@ -168,9 +339,10 @@ __global__ void __launch_bounds__(256) k_cell_starts(const uint32_t *__restrict_
 // lane-per-lobe formulation (profiles/r01_v3_summary.txt).
 template <int KMAX>
 __global__ void __launch_bounds__(128) k_estep(GuideDevice G, const float4 *__restrict__ sPos, const float4 *__restrict__ sDir,
-                                               const uint4 *__restrict__ work, uint32_t nWork, float *__restrict__ partials,
-                                               int stride) {
+                                               const uint4 *__restrict__ work, const uint32_t *__restrict__ counts,
+                                               float *__restrict__ partials, int stride) {
     __shared__ float4 sLobe[4][KMAX * 2];
+    const uint32_t nWork = counts[2];
     const uint32_t warp = threadIdx.x >> 5, ln = lane();
     const int K = G.K;
     float4 *myLobes = sLobe[warp];
@@ -248,9 +420,10 @@ __global__ void __launch_bounds__(128) k_estep(GuideDevice G, const float4 *__re
 // Per-chunk position moments (count, sum x, sum x^2) -- independent of the mixtures, so computed once per training
 // update, not once per EM iteration. Written into the cell-statistics slots of the partials buffer that k_estep
 // leaves alone (slot 1, the weight sum, is k_estep's).
-__global__ void __launch_bounds__(128) k_cell_moments(const float4 *__restrict__ sPos, const uint4 *__restrict__ work, uint32_t nWork,
-                                                      float *__restrict__ partials, int stride, int K) {
+__global__ void __launch_bounds__(128) k_cell_moments(const float4 *__restrict__ sPos, const uint4 *__restrict__ work,
+                                                      const uint32_t *__restrict__ counts, float *__restrict__ partials, int stride, int K) {
     const uint32_t warp = threadIdx.x >> 5, ln = lane();
+    const uint32_t nWork = counts[2];
     for (uint32_t w = blockIdx.x * 4 + warp; w < nWork; w += gridDim.x * 4) {
         const uint4 item = work[w];
         float m[6] = {0, 0, 0, 0, 0, 0};
@@ -280,9 +453,11 @@ __global__ void __launch_bounds__(128) k_cell_moments(const float4 *__restrict__
 // samples (paths that found no light) only matter for the cell's sample count and position moments, so the E-step
 // iterates over the dense front part with all lanes busy.
 __global__ void __launch_bounds__(128) k_gather_partition(const float4 *__restrict__ sPos, const float4 *__restrict__ sDir,
-                                                          const uint32_t *__restrict__ perm, uint4 *__restrict__ work, uint32_t nWork,
-                                                          float4 *__restrict__ oPos, float4 *__restrict__ oDir) {
+                                                          const uint32_t *__restrict__ perm, uint4 *__restrict__ work,
+                                                          const uint32_t *__restrict__ counts, float4 *__restrict__ oPos,
+                                                          float4 *__restrict__ oDir) {
     const uint32_t warp = threadIdx.x >> 5, ln = lane();
+    const uint32_t nWork = counts[2];
     for (uint32_t w = blockIdx.x * 4 + warp; w < nWork; w += gridDim.x * 4) {
         const uint4 item = work[w];
         uint32_t nGood = 0, nBad = 0;
@@ -529,6 +704,14 @@ void GuidingHost::init(const B200pgIntegratorParams &P, const HostScene &H, cuda
         mn[a] = H.sceneMin[a] - 0.01f * ext - 1e-3f;
         mx[a] = H.sceneMax[a] + 0.01f * ext + 1e-3f;
     }
+    if (active) {  // the field lives on the device at a fixed capacity; the host keeps a lazily refreshed mirror
+        dNodes.allocExact(2 * kCommMaxCells);
+        dLobes.allocExact(kCommMaxCells * (size_t)K * 2);
+        dLobeStats.allocExact(kCommMaxCells * (size_t)K);
+        dCells.allocExact(kCommMaxCells);
+        dCellLeaf.allocExact(kCommMaxCells);
+        dCounts.allocExact(4);
+    }
     resetField(mn, mx);
     dSCount.alloc(1);
     CUDA_OK(cudaMemsetAsync(dSCount.p, 0, sizeof(uint32_t), stream));
@@ -556,18 +739,76 @@ void GuidingHost::resetField(const float *, const float *) {
     uploadField();
 }
 
+// host mirror -> device (initial field, loaded snapshots)
 void GuidingHost::uploadField() {
-    dNodes.upload(reinterpret_cast<const uint4 *>(nodes.data()), nodes.size(), stream);
-    // device layout: query data (2 x float4 per lobe) and running statistics (1 x float4 per lobe) in separate arrays
+    nCells = (uint32_t)cells.size();
+    nNodes = (uint32_t)nodes.size();
+    mirrorValid = true;
+    if (!active && dNodes.n == 0) {  // query-only use (tests): size the buffers to the field
+        dNodes.allocExact(std::max<size_t>(nodes.size(), 1));
+        dLobes.allocExact(std::max<size_t>(lobes.size() * 2, 1));
+        dLobeStats.allocExact(std::max<size_t>(lobes.size(), 1));
+        dCells.allocExact(std::max<size_t>(cells.size(), 1));
+        dCellLeaf.allocExact(std::max<size_t>(cells.size(), 1));
+        dCounts.allocExact(4);
+    }
+    if (nodes.size() > dNodes.n || lobes.size() * 2 > dLobes.n || cells.size() > dCells.n) {
+        // a snapshot larger than the current capacity: grow everything (keeps query-only integrators small)
+        dNodes.release(); dLobes.release(); dLobeStats.release(); dCells.release(); dCellLeaf.release();
+        dNodes.allocExact(std::max<size_t>(nodes.size(), 2 * kCommMaxCells));
+        dLobes.allocExact(std::max<size_t>(lobes.size() * 2, kCommMaxCells * (size_t)K * 2));
+        dLobeStats.allocExact(std::max<size_t>(lobes.size(), kCommMaxCells * (size_t)K));
+        dCells.allocExact(std::max<size_t>(cells.size(), kCommMaxCells));
+        dCellLeaf.allocExact(std::max<size_t>(cells.size(), kCommMaxCells));
+    }
     stageQuery.resize(lobes.size() * 8);
     stageStats.resize(lobes.size() * 4);
     for (size_t i = 0; i < lobes.size(); ++i) {
         std::memcpy(&stageQuery[8 * i], &lobes[i].weight, 32);
         std::memcpy(&stageStats[4 * i], &lobes[i].statS, 16);
     }
-    dLobes.upload(reinterpret_cast<const float4 *>(stageQuery.data()), lobes.size() * 2, stream);
-    dLobeStats.upload(reinterpret_cast<const float4 *>(stageStats.data()), lobes.size(), stream);
+    std::vector<float> hdr(cells.size() * 2);
+    std::vector<uint32_t> leaf(cells.size(), 0);
+    for (size_t c = 0; c < cells.size(); ++c) {
+        hdr[2 * c] = cells[c].sampleCount;
+        hdr[2 * c + 1] = cells[c].weightSum;
+    }
+    for (uint32_t n = 0; n < nodes.size(); ++n)
+        if (nodes[n].axis == 3u) leaf[nodes[n].left] = n;
+    const uint32_t counts[4] = {nCells, nNodes, 0u, 0u};
+    CUDA_OK(cudaMemcpyAsync(dNodes.p, nodes.data(), nodes.size() * 16, cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaMemcpyAsync(dLobes.p, stageQuery.data(), lobes.size() * 32, cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaMemcpyAsync(dLobeStats.p, stageStats.data(), lobes.size() * 16, cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaMemcpyAsync(dCells.p, hdr.data(), hdr.size() * 4, cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaMemcpyAsync(dCellLeaf.p, leaf.data(), leaf.size() * 4, cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaMemcpyAsync(dCounts.p, counts, sizeof(counts), cudaMemcpyHostToDevice, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
+}
+
+// device -> host mirror (snapshots); the device copy is the source of truth after a training update
+void GuidingHost::syncMirror() {
+    if (mirrorValid) return;
+    nodes.resize(nNodes);
+    cells.resize(nCells);
+    lobes.resize((size_t)nCells * K);
+    stageQuery.resize(lobes.size() * 8);
+    stageStats.resize(lobes.size() * 4);
+    std::vector<float> hdr((size_t)nCells * 2);
+    CUDA_OK(cudaMemcpyAsync(nodes.data(), dNodes.p, nodes.size() * 16, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaMemcpyAsync(stageQuery.data(), dLobes.p, lobes.size() * 32, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaMemcpyAsync(stageStats.data(), dLobeStats.p, lobes.size() * 16, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaMemcpyAsync(hdr.data(), dCells.p, hdr.size() * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    for (size_t i = 0; i < lobes.size(); ++i) {
+        std::memcpy(&lobes[i].weight, &stageQuery[8 * i], 32);
+        std::memcpy(&lobes[i].statS, &stageStats[4 * i], 16);
+    }
+    for (size_t c = 0; c < cells.size(); ++c) {
+        std::memset(&cells[c], 0, sizeof(GuideCellHost));
+        cells[c].sampleCount = hdr[2 * c];
+        cells[c].weightSum = hdr[2 * c + 1];
+    }
+    mirrorValid = true;
 }
 
 void GuidingHost::ensureBatch(size_t nPaths) {
@@ -606,8 +847,10 @@ void GuidingHost::sortByCell(uint32_t n) {
     G.lobes = dLobes.p;
     G.lobeStats = dLobeStats.p;
     G.K = K;
-    k_guide_cells<<<gridFor(n, 256), 256, 0, stream>>>(G, dSPos.p, n, dKeysA.p, dValsA.p);
-    launches++;
+    if (n) {
+        k_guide_cells<<<gridFor(n, 256), 256, 0, stream>>>(G, dSPos.p, n, dKeysA.p, dValsA.p);
+        launches++;
+    }
     uint32_t *kin = dKeysA.p, *vin = dValsA.p, *kout = dKeysB.p, *vout = dValsB.p;
     const int passes = numCells() > 65536 ? 3 : (numCells() > 256 ? 2 : 1);
     for (int pass = 0; pass < passes && n > 0; ++pass) {
@@ -625,59 +868,48 @@ void GuidingHost::sortByCell(uint32_t n) {
     }
     sortedCells = kin;
     sortedPerm = vin;
-    // per-cell counts -> offsets (host; the cell count is small)
-    dCellCount.alloc(numCells() + 1);
-    CUDA_OK(cudaMemsetAsync(dCellCount.p, 0xFF, numCells() * sizeof(uint32_t), stream));
+    // first sorted index of every cell that occurs (0xFFFFFFFF = empty cell)
+    dCellStart.alloc(numCells() + 1);
+    CUDA_OK(cudaMemsetAsync(dCellStart.p, 0xFF, numCells() * sizeof(uint32_t), stream));
     if (n) {
-        k_cell_starts<<<gridFor(n, 256), 256, 0, stream>>>(sortedCells, n, dCellCount.p);
+        k_cell_starts<<<gridFor(n, 256), 256, 0, stream>>>(sortedCells, n, dCellStart.p);
         launches++;
     }
-    std::vector<uint32_t> start(numCells());
-    CUDA_OK(cudaMemcpyAsync(start.data(), dCellCount.p, start.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    CUDA_OK(cudaStreamSynchronize(stream));
-    CUDA_OK(cudaGetLastError());
-    offsets.assign(numCells() + 1, n);
-    for (uint32_t c = numCells(); c-- > 0;) offsets[c] = start[c] != 0xFFFFFFFFu ? start[c] : offsets[c + 1];  // empty cells
-    offsets[0] = 0;
 }
 
+// Work items, gather + partition, position moments: all enqueued without a host round trip; kernels read the number
+// of work items from dCounts[2] and run on persistent grids.
 void GuidingHost::buildWork() {
-    std::vector<uint4> work;
-    std::vector<uint32_t> workOfs(numCells() + 1, 0);
-    for (uint32_t c = 0; c < numCells(); ++c) {
-        workOfs[c] = (uint32_t)work.size();
-        for (uint32_t b = offsets[c]; b < offsets[c + 1]; b += kChunk)
-            work.push_back(make_uint4(c, b, std::min(b + (uint32_t)kChunk, offsets[c + 1]), 0u));
-    }
-    workOfs[numCells()] = (uint32_t)work.size();
-    nWork = (uint32_t)work.size();
-    dWork.upload(work, stream);
-    dCellCount.upload(workOfs, stream);  // reused as the per-cell work offsets from here on
+    if (numCells() > 16 * 1024) throw std::runtime_error("guiding field exceeds 16384 cells");
+    const uint32_t nc = numCells();
+    workBound = nSamples / kChunk + nc + 1;
+    dOffsets.alloc(nc + 1);
+    dWorkOfs.alloc(nc + 1);
+    dWork.alloc(workBound);
+    k_build_work<<<1, 1024, 0, stream>>>(dCellStart.p, nc, nSamples, (uint32_t)kChunk, dOffsets.p, dWorkOfs.p, dCounts.p);
+    k_fill_work<<<gridFor(workBound, 256), 256, 0, stream>>>(dOffsets.p, dWorkOfs.p, nc, (uint32_t)kChunk, dCounts.p, dWork.p);
+    launches += 2;
     dSortPos.alloc(nSamples);
     dSortDir.alloc(nSamples);
-    if (nSamples) {
-        int smCount = 148;
-        cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, 0);
-        k_gather_partition<<<std::min<uint32_t>((nWork + 3) / 4, (uint32_t)smCount * 16), 128, 0, stream>>>(dSPos.p, dSDir.p, sortedPerm, dWork.p,
-                                                                                                     nWork, dSortPos.p, dSortDir.p);
-        launches++;
-    }
-    dPartials.alloc((size_t)std::max(nWork, 1u) * statsStride());
-    dStats.alloc((size_t)numCells() * statsStride());
-    if (nWork) {
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-        k_cell_moments<<<std::min<uint32_t>((nWork + 3) / 4, (uint32_t)sms * 16), 128, 0, stream>>>(dSortPos.p, dWork.p, nWork, dPartials.p,
-                                                                                                   (int)statsStride(), K);
-        launches++;
-    }
+    dPartials.alloc((size_t)workBound * statsStride());
+    dStats.alloc((size_t)nc * statsStride());
+    int smCount = 148;
+    cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, 0);
+    const uint32_t grid = std::max(1u, std::min<uint32_t>((workBound + 3) / 4, (uint32_t)smCount * 16));
+    k_gather_partition<<<grid, 128, 0, stream>>>(dSPos.p, dSDir.p, sortedPerm, dWork.p, dCounts.p, dSortPos.p, dSortDir.p);
+    k_cell_moments<<<grid, 128, 0, stream>>>(dSortPos.p, dWork.p, dCounts.p, dPartials.p, (int)statsStride(), K);
+    launches += 2;
 }
 
 void GuidingHost::begin() {
-    uint32_t n = 0;
-    CUDA_OK(cudaMemcpyAsync(&n, dSCount.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    CUDA_OK(cudaStreamSynchronize(stream));
-    nSamples = (uint32_t)std::min<size_t>(n, sampleCapacity);
+    if (pendingCount == 0xFFFFFFFFu) {  // not told by the integrator: ask the device
+        uint32_t n = 0;
+        CUDA_OK(cudaMemcpyAsync(&n, dSCount.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        pendingCount = n;
+    }
+    nSamples = (uint32_t)std::min<size_t>(pendingCount, sampleCapacity);
+    pendingCount = 0xFFFFFFFFu;
     sortByCell(nSamples);
     buildWork();
 }
@@ -711,24 +943,19 @@ void GuidingHost::accumulateInto(float *statsOut) {
     GuideDevice G;
     std::memset(&G, 0, sizeof(G));
     G.lobes = dLobes.p;
-    G.lobeStats = dLobeStats.p;
     G.K = K;
     const int stride = (int)statsStride();
-    if (nWork) {
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-        const uint32_t grid = std::min<uint32_t>((nWork + 3) / 4, (uint32_t)sms * 8);
-        if (K <= 8)
-            k_estep<8><<<grid, 128, 0, stream>>>(G, dSortPos.p, dSortDir.p, dWork.p, nWork, dPartials.p, stride);
-        else if (K <= 16)
-            k_estep<16><<<grid, 128, 0, stream>>>(G, dSortPos.p, dSortDir.p, dWork.p, nWork, dPartials.p, stride);
-        else
-            k_estep<32><<<grid, 128, 0, stream>>>(G, dSortPos.p, dSortDir.p, dWork.p, nWork, dPartials.p, stride);
-        launches++;
-    }
-    k_reduce_partials<<<gridFor((size_t)numCells() * stride, 256), 256, 0, stream>>>(dPartials.p, dCellCount.p, numCells(), stride,
-                                                                                      statsOut);
-    launches++;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const uint32_t grid = std::max(1u, std::min<uint32_t>((workBound + 3) / 4, (uint32_t)sms * 8));
+    if (K <= 8)
+        k_estep<8><<<grid, 128, 0, stream>>>(G, dSortPos.p, dSortDir.p, dWork.p, dCounts.p, dPartials.p, stride);
+    else if (K <= 16)
+        k_estep<16><<<grid, 128, 0, stream>>>(G, dSortPos.p, dSortDir.p, dWork.p, dCounts.p, dPartials.p, stride);
+    else
+        k_estep<32><<<grid, 128, 0, stream>>>(G, dSortPos.p, dSortDir.p, dWork.p, dCounts.p, dPartials.p, stride);
+    k_reduce_partials<<<gridFor((size_t)numCells() * stride, 256), 256, 0, stream>>>(dPartials.p, dWorkOfs.p, numCells(), stride, statsOut);
+    launches += 2;
 }
 
 void GuidingHost::update(bool commit) {
@@ -737,64 +964,21 @@ void GuidingHost::update(bool commit) {
     launches++;
 }
 
+// Fold the update's cell statistics into the running headers and split over-full cells -- on the device; the host
+// only learns the new cell / node counts (8 bytes).
 void GuidingHost::end() {
-    // bring the refitted mixtures and the last statistics to the host, fold the cell statistics into the running
-    // headers, split over-full cells (same rule and arithmetic as oracle_guiding.h: guideSplit) and re-upload
-    const size_t stride = statsStride();
-    std::vector<float> stats((size_t)numCells() * stride);
-    stageQuery.resize(lobes.size() * 8);
-    stageStats.resize(lobes.size() * 4);
-    CUDA_OK(cudaMemcpyAsync(stageQuery.data(), dLobes.p, lobes.size() * 32, cudaMemcpyDeviceToHost, stream));
-    CUDA_OK(cudaMemcpyAsync(stageStats.data(), dLobeStats.p, lobes.size() * 16, cudaMemcpyDeviceToHost, stream));
-    CUDA_OK(cudaMemcpyAsync(stats.data(), dStats.p, stats.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    k_split<<<1, 1024, 0, stream>>>(dNodes.p, dLobes.p, dLobeStats.p, dCells.p, dCellLeaf.p, dStats.p, dCounts.p,
+                                   K, (int)statsStride(), maxCellSamples, (uint32_t)std::min<size_t>(dCells.n, 16 * 1024));
+    launches++;
+    uint32_t counts[2] = {0, 0};
+    CUDA_OK(cudaMemcpyAsync(counts, dCounts.p, sizeof(counts), cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaMemsetAsync(dSCount.p, 0, sizeof(uint32_t), stream));
     CUDA_OK(cudaStreamSynchronize(stream));
     CUDA_OK(cudaGetLastError());
-    for (size_t i = 0; i < lobes.size(); ++i) {
-        std::memcpy(&lobes[i].weight, &stageQuery[8 * i], 32);
-        std::memcpy(&lobes[i].statS, &stageStats[4 * i], 16);
-    }
-    const uint32_t nc0 = numCells();
-    for (uint32_t c = 0; c < nc0; ++c) {
-        const float *cs = &stats[stride * c + (size_t)K * 4];
-        cells[c].sampleCount = kGuideDecay * cells[c].sampleCount + cs[0];
-        cells[c].weightSum = kGuideDecay * cells[c].weightSum + cs[1];
-    }
-    std::vector<uint32_t> leafOf(nc0, 0);
-    for (uint32_t n = 0; n < nodes.size(); ++n)
-        if (nodes[n].axis == 3u) leafOf[nodes[n].left] = n;
-    for (uint32_t c = 0; c < nc0; ++c) {
-        if (!(cells[c].sampleCount > maxCellSamples)) continue;
-        const float *cs = &stats[stride * c + (size_t)K * 4];
-        const float n = cs[0];
-        if (!(n >= 2)) continue;
-        float mean[3];
-        double var[3];
-        for (int a = 0; a < 3; ++a) {
-            mean[a] = cs[2 + a] / n;
-            var[a] = (double)cs[5 + a] / (double)n - (double)mean[a] * (double)mean[a];
-        }
-        int axis = 0;
-        if (var[1] > var[axis]) axis = 1;
-        if (var[2] > var[axis]) axis = 2;
-        if (!(var[axis] > 0)) continue;
-        const uint32_t leaf = leafOf[c], left = (uint32_t)nodes.size(), newCell = numCells();
-        nodes.push_back(GuideNodeHost{3u, 0.0f, c, 0u});
-        nodes.push_back(GuideNodeHost{3u, 0.0f, newCell, 0u});
-        nodes[leaf] = GuideNodeHost{(uint32_t)axis, mean[axis], left, 0u};
-        GuideCellHost h = cells[c];
-        h.sampleCount *= 0.5f;
-        h.weightSum *= 0.5f;
-        cells[c] = h;
-        cells.push_back(h);
-        for (int k = 0; k < K; ++k) {
-            GuideLobeHost &l = lobes[(size_t)c * K + k];
-            l.statS *= 0.5f; l.statRx *= 0.5f; l.statRy *= 0.5f; l.statRz *= 0.5f;
-        }
-        for (int k = 0; k < K; ++k) lobes.push_back(lobes[(size_t)c * K + k]);
-    }
+    nCells = counts[0];
+    nNodes = counts[1];
+    mirrorValid = false;
     trained = true;
-    uploadField();
-    CUDA_OK(cudaMemsetAsync(dSCount.p, 0, sizeof(uint32_t), stream));
     sortedPerm = sortedCells = nullptr;
 }
 
@@ -924,12 +1108,14 @@ void GuidingHost::bin(const float *pos, size_t n, uint32_t *outCell, uint32_t *o
         CUDA_OK(cudaMemcpyAsync(outCell, k.p, n * 4, cudaMemcpyDeviceToHost, stream));
         CUDA_OK(cudaStreamSynchronize(stream));
     }
-    std::memcpy(outOffsets, offsets.data(), offsets.size() * 4);
+    CUDA_OK(cudaMemcpyAsync(outOffsets, dOffsets.p, ((size_t)numCells() + 1) * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
     if (nCells) *nCells = numCells();
     CUDA_OK(cudaGetLastError());
 }
 
 std::vector<uint32_t> GuidingHost::snapshot() {
+    syncMirror();
     std::vector<uint32_t> w(8 + 4 * nodes.size() + 8 * cells.size() + 12 * lobes.size());
     w[0] = 0x47554944u;
     w[1] = (uint32_t)nodes.size();

@@ -53,6 +53,13 @@ struct GuidingHost {
     std::vector<GuideLobeHost> lobes;
     std::vector<GuideCellHost> cells;
     DevBuf<uint4> dNodes;
+    DevBuf<float2> dCells;       // running per-cell headers {sample count, weight sum}
+    DevBuf<uint32_t> dCellLeaf;  // leaf node of every cell
+    DevBuf<uint32_t> dCounts;    // {nCells, nNodes, nWork, -}
+    uint32_t nCells = 1, nNodes = 1; // host copy of the counts (refreshed at the end of every update)
+    bool mirrorValid = true;     // nodes / lobes / cells below mirror the device copy
+    uint32_t pendingCount = 0xFFFFFFFFu;  // recorded-sample count handed over by the integrator (saves a sync)
+    uint32_t workBound = 1;      // upper bound of the number of work items (grid / buffer sizing)
     DevBuf<float4> dLobes, dLobeStats;
     std::vector<float> stageQuery, stageStats;  // host staging of the two device lobe arrays
 
@@ -64,10 +71,9 @@ struct GuidingHost {
     size_t vertCapacity = 0, sampleCapacity = 0;
 
     // binning (radix sort) and EM scratch
-    DevBuf<uint32_t> dKeysA, dKeysB, dValsA, dValsB, dBlockHist, dCellCount, dScanTotals;
+    DevBuf<uint32_t> dKeysA, dKeysB, dValsA, dValsB, dBlockHist, dCellStart, dOffsets, dWorkOfs, dScanTotals;
     DevBuf<float> dStats, dPartials;
     DevBuf<uint4> dWork;  // (cell, begin, end, 0) chunks of the sorted sample range
-    std::vector<uint32_t> offsets;  // per-cell offsets of the current binning (host)
     uint32_t nSamples = 0, nWork = 0;
     uint32_t *sortedPerm = nullptr;  // device pointer into dVals*, valid between begin() and end()
     uint32_t *sortedCells = nullptr;
@@ -79,7 +85,8 @@ struct GuidingHost {
     void ensureBatch(size_t nPaths);
     void configure(ShadeArgs &A);
     void preprogression(int pass) { (void)pass; }
-    uint32_t numCells() const { return (uint32_t)cells.size(); }
+    uint32_t numCells() const { return nCells; }
+    void syncMirror();
     size_t statsStride() const { return (size_t)K * 4 + 8; }
 
     // training update

@@ -374,8 +374,12 @@ struct Integrator {
                 }
         }
         CUDA_OK(cudaEventRecord(ev[3], stream));
+        uint32_t recorded = 0xFFFFFFFFu;
+        if (guide.active && guide.recording)  // the training update needs the sample count: fetch it with this sync
+            CUDA_OK(cudaMemcpyAsync(&recorded, guide.dSCount.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         CUDA_OK(cudaStreamSynchronize(stream));
         CUDA_OK(cudaGetLastError());
+        guide.pendingCount = recorded;
         drainSpans();
         float msTotal = 0;
         CUDA_OK(cudaEventElapsedTime(&msTotal, ev[2], ev[3]));
@@ -759,6 +763,7 @@ int b200pg_k_radiance(void *integ, const uint32_t *pixel, const uint32_t *sample
     B.pixelList = dPix.p;
     B.sampleList = dSmp.p;
     self->runBatch(B, dOut.p);
+    self->guide.pendingCount = 0xFFFFFFFFu;  // a stand-alone batch may have recorded samples: the next update asks the device
     CUDA_OK(cudaMemcpyAsync(out_rgb, dOut.p, 3 * n * 4, cudaMemcpyDeviceToHost, self->stream));
     CUDA_OK(cudaStreamSynchronize(self->stream));
     CUDA_OK(cudaGetLastError());
