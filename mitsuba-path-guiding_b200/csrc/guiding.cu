@@ -910,6 +910,7 @@ void GuidingHost::begin() {
     }
     nSamples = (uint32_t)std::min<size_t>(pendingCount, sampleCapacity);
     pendingCount = 0xFFFFFFFFu;
+    samplesTrained += nSamples;
     sortByCell(nSamples);
     buildWork();
 }

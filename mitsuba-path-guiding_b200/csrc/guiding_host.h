@@ -59,6 +59,7 @@ struct GuidingHost {
     uint32_t nCells = 1, nNodes = 1; // host copy of the counts (refreshed at the end of every update)
     bool mirrorValid = true;     // nodes / lobes / cells below mirror the device copy
     uint32_t pendingCount = 0xFFFFFFFFu;  // recorded-sample count handed over by the integrator (saves a sync)
+    uint64_t samplesTrained = 0; // cumulative number of samples that went through a training update
     uint32_t workBound = 1;      // upper bound of the number of work items (grid / buffer sizing)
     DevBuf<float4> dLobes, dLobeStats;
     std::vector<float> stageQuery, stageStats;  // host staging of the two device lobe arrays

@@ -325,7 +325,7 @@ struct Integrator {
         stats.path_length_sum = h.pathLen;
         stats.bvh_nodes_visited = h.nodesVisited;
         stats.prims_tested = h.primsTested;
-        stats.train_samples = h.trainSamples;
+        stats.train_samples = guide.samplesTrained;
     }
 
     // One progression over (rows, samples), split into batches of at most maxBatch paths.

@@ -232,14 +232,15 @@ __global__ void __launch_bounds__(128) k_trace_rays(DeviceScene S, const float4 
 // Shade stage (surface path tracer, ProgressiveMIPathTracer::Li)
 // ------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(kShadeThreads, 5) k_shade(ShadeArgs A) {
+__global__ void __launch_bounds__(kShadeThreads, 8) k_shade(ShadeArgs A) {
     const DeviceScene &S = A.S;
     const IntegratorConfig &cfg = A.cfg;
     const uint32_t n = A.C->queue[A.bounce];
     uint32_t *nextCount = &A.C->queue[A.bounce + 1];
     uint32_t *shadowCount = &A.C->shadow[A.bounce];
     unsigned long long donePaths = 0, doneLen = 0;
-    __shared__ uint32_t sAppend[2 * (kShadeThreads / 32 + 1)];
+    __shared__ uint32_t sAppend[2 * 3 * (kShadeThreads / 32 + 1)];
+    uint32_t appendParity = 0;
 
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t i = base + threadIdx.x;
@@ -434,8 +435,10 @@ __global__ void __launch_bounds__(kShadeThreads, 5) k_shade(ShadeArgs A) {
         }
 
         // ---- compaction into the next queue / shadow queue (one atomic per block each)
-        uint32_t j, sidx;
-        blockAppend2(nextCount, alive, shadowCount, wantShadow, sAppend, j, sidx);
+        const AppendResult ap = blockAppend3(nextCount, alive, shadowCount, wantShadow, A.G.record ? A.G.sCount : nullptr,
+                                             (A.G.record && valid && terminate) ? vcount : 0u, sAppend, appendParity);
+        appendParity ^= 1u;
+        const uint32_t j = ap.idxA, sidx = ap.idxB;
         if (alive) {
             A.next.rayO[j] = make_float4(newO.x, newO.y, newO.z, kEpsilon);
             A.next.rayD[j] = make_float4(newD.x, newD.y, newD.z, kInf);
@@ -457,7 +460,7 @@ __global__ void __launch_bounds__(kShadeThreads, 5) k_shade(ShadeArgs A) {
             doneLen += depth;
             finishPath(A, slot, pos4, L);
         }
-        if (A.G.record) emitTrainingSamples(A.G, valid && terminate, slot, vcount, L);
+        if (A.G.record) emitTrainingSamples(A.G, (valid && terminate) ? vcount : 0u, ap.inclC, ap.warpTotalC, ap.baseC, slot, L);
     }
     warpAddU64(&A.C->paths, donePaths);
     warpAddU64(&A.C->pathLen, doneLen);

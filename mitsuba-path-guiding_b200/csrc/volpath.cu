@@ -90,7 +90,8 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_vol(ShadeArgs A) {
     uint32_t *nextCount = &A.C->queue[A.bounce + 1];
     uint32_t *shadowCount = &A.C->shadow[A.bounce];
     unsigned long long donePaths = 0, doneLen = 0, extraRays = 0;
-    __shared__ uint32_t sAppend[2 * (kShadeThreads / 32 + 1)];
+    __shared__ uint32_t sAppend[2 * 3 * (kShadeThreads / 32 + 1)];
+    uint32_t appendParity = 0;
 
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t i = base + threadIdx.x;
@@ -365,8 +366,10 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_vol(ShadeArgs A) {
             }
         }
 
-        uint32_t j, sidx;
-        blockAppend2(nextCount, alive, shadowCount, wantShadow, sAppend, j, sidx);
+        const AppendResult ap = blockAppend3(nextCount, alive, shadowCount, wantShadow, A.G.record ? A.G.sCount : nullptr,
+                                             (A.G.record && valid && terminate) ? vcount : 0u, sAppend, appendParity);
+        appendParity ^= 1u;
+        const uint32_t j = ap.idxA, sidx = ap.idxB;
         if (alive) {
             A.next.rayO[j] = make_float4(newO.x, newO.y, newO.z, newMint);
             A.next.rayD[j] = make_float4(newD.x, newD.y, newD.z, kInf);
@@ -389,7 +392,7 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_vol(ShadeArgs A) {
             doneLen += depth;
             finishPath(A, slot, pos4, L);
         }
-        if (A.G.record) emitTrainingSamples(A.G, valid && terminate, slot, vcount, L);
+        if (A.G.record) emitTrainingSamples(A.G, (valid && terminate) ? vcount : 0u, ap.inclC, ap.warpTotalC, ap.baseC, slot, L);
     }
     warpAddU64(&A.C->paths, donePaths);
     warpAddU64(&A.C->pathLen, doneLen);

@@ -17,34 +17,54 @@ PG_DEV uint32_t warpAppend(uint32_t *counter, bool pred) {
     return base + __popc(mask & ((1u << laneId()) - 1u));
 }
 
-// Block-aggregated append for two queues at once: ONE global atomic per block and queue instead of
-// one per warp (the per-warp version serialised ~130k same-address atomics per bounce at L2 and was
-// 35% of k_shade's stall samples, profiles/r01_v1_summary.txt). Must be called by all threads of the
-// block; `smem` holds 2*(warps+1) words.
-PG_DEV void blockAppend2(uint32_t *counterA, bool predA, uint32_t *counterB, bool predB, uint32_t *smem, uint32_t &idxA,
-                         uint32_t &idxB) {
+// Block-aggregated append for the two queues and the training-sample buffer at once: ONE global atomic per block
+// and counter instead of one per warp (the per-warp version serialised ~130k same-address atomics per bounce at L2
+// and was 35% of k_shade's stall samples, profiles/r01_v1_summary.txt). Must be called by all threads of the block.
+// `smem` holds 2 * 3 * (warps + 1) words and is double-buffered by `parity` (toggled by the caller every loop
+// iteration), which saves the trailing barrier. countC = number of items this thread appends to counter C;
+// inclC = inclusive prefix of countC inside the warp, warpTotalC = the warp's sum, baseC = index of the warp's first item.
+struct AppendResult {
+    uint32_t idxA, idxB, baseC, inclC, warpTotalC;
+};
+PG_DEV AppendResult blockAppend3(uint32_t *counterA, bool predA, uint32_t *counterB, bool predB, uint32_t *counterC, uint32_t countC,
+                                 uint32_t *smem, uint32_t parity) {
     const uint32_t warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
     const unsigned maskA = __ballot_sync(0xffffffffu, predA), maskB = __ballot_sync(0xffffffffu, predB);
-    uint32_t *cntA = smem, *cntB = smem + nWarps + 1;
+    uint32_t incl = countC;
+    if (counterC) {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)laneId() >= o) incl += v;
+        }
+    }
+    const uint32_t warpTotal = counterC ? __shfl_sync(0xffffffffu, incl, 31) : 0u;
+    uint32_t *cntA = smem + parity * 3 * (nWarps + 1), *cntB = cntA + nWarps + 1, *cntC = cntB + nWarps + 1;
     if (laneId() == 0) {
         cntA[warp] = __popc(maskA);
         cntB[warp] = __popc(maskB);
+        cntC[warp] = warpTotal;
     }
     __syncthreads();
-    if (threadIdx.x < 2) {
-        uint32_t *cnt = threadIdx.x ? cntB : cntA;
+    if (threadIdx.x < 3) {
+        uint32_t *cnt = threadIdx.x == 0 ? cntA : (threadIdx.x == 1 ? cntB : cntC);
+        uint32_t *counter = threadIdx.x == 0 ? counterA : (threadIdx.x == 1 ? counterB : counterC);
         uint32_t total = 0;
         for (uint32_t w = 0; w < nWarps; ++w) {
             const uint32_t c = cnt[w];
             cnt[w] = total;  // exclusive prefix
             total += c;
         }
-        cnt[nWarps] = total ? atomicAdd(threadIdx.x ? counterB : counterA, total) : 0u;
+        cnt[nWarps] = (total && counter) ? atomicAdd(counter, total) : 0u;
     }
     __syncthreads();
-    idxA = cntA[nWarps] + cntA[warp] + __popc(maskA & ((1u << laneId()) - 1u));
-    idxB = cntB[nWarps] + cntB[warp] + __popc(maskB & ((1u << laneId()) - 1u));
-    __syncthreads();  // smem is reused by the next loop iteration
+    AppendResult r;
+    r.idxA = cntA[nWarps] + cntA[warp] + __popc(maskA & ((1u << laneId()) - 1u));
+    r.idxB = cntB[nWarps] + cntB[warp] + __popc(maskB & ((1u << laneId()) - 1u));
+    r.baseC = cntC[nWarps] + cntC[warp];
+    r.inclC = incl;
+    r.warpTotalC = warpTotal;
+    return r;
 }
 
 PG_DEV void warpAddU64(unsigned long long *counter, unsigned long long v) {
@@ -55,20 +75,11 @@ PG_DEV void warpAddU64(unsigned long long *counter, unsigned long long v) {
 
 // Training samples of a finished path: for every recorded vertex the incident-radiance estimate along the
 // sampled direction is everything the path gathered after the vertex divided by the throughput right after it;
-// sample weight = avg_rgb(estimate) / pdf. Called by whole warps; one atomic per warp reserves the output range.
-PG_DEV void emitTrainingSamples(const GuideDevice &G, bool finished, uint32_t slot, uint32_t vcount, float3 Lfinal) {
-    const uint32_t nMine = finished ? vcount : 0u;
-    uint32_t incl = nMine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((int)laneId() >= o) incl += v;
-    }
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+// sample weight = avg_rgb(estimate) / pdf. Called by whole warps; the output range [base, base + total) of the warp was
+// reserved by blockAppend3 (nMine = this lane's vertex count if its path just finished, incl = its inclusive prefix).
+PG_DEV void emitTrainingSamples(const GuideDevice &G, uint32_t nMine, uint32_t incl, uint32_t total, uint32_t base, uint32_t slot,
+                                    float3 Lfinal) {
     if (total == 0) return;
-    uint32_t base = 0;
-    if (laneId() == 31) base = atomicAdd(G.sCount, total);
-    base = __shfl_sync(0xffffffffu, base, 31);
     // The warp emits its `total` samples cooperatively, 32 at a time: item t belongs to the first lane whose inclusive
     // prefix exceeds t (binary search over the prefix with shuffles), so the vertex loads/stores run with all lanes
     // busy instead of a serial per-path loop with a handful of finished lanes.
