@@ -68,7 +68,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.1)
 
     def summary(self, t0, t1):
         inside = [v for (t, v) in self.samples if t0 <= t <= t1]
@@ -242,7 +242,8 @@ def main():
                 integ.train_fused(args.em_iters)
 
     clocks = ClockSampler(local)
-    clocks.start()
+    if rank == 0:  # one sampler per job: nvidia-smi takes a driver-wide lock, 8 pollers would perturb the run
+        clocks.start()
     # untimed setup: bring the guiding field to its steady state (the spatial tree stops growing after ~10 updates), so
     # that the timed steps -- and the e2e steps after them -- all cost the same; the reference arm does the same
     base = 0

@@ -57,13 +57,82 @@ PG_DEV float adaptiveMinT(float3 o, float mint, bool shadow) {
     return mint;
 }
 
+// One inner-node step of the BVH2 descent: tests both child boxes (4 x LDG.128), continues with the nearer hit
+// child and pushes the farther one. kDoneNode when the stack runs empty.
+static constexpr int kDoneNode = (int)0x80000000;  // ~kDoneNode is not a valid leaf code
+PG_DEV int bvhNodeStep(const DeviceScene &S, int node, float3 o, float3 idir, float mint, float tmax, int *stack, int &sp) {
+    const float4 n0 = __ldg(S.nodes + 4 * node + 0);
+    const float4 n1 = __ldg(S.nodes + 4 * node + 1);
+    const float4 n2 = __ldg(S.nodes + 4 * node + 2);
+    const float4 n3 = __ldg(S.nodes + 4 * node + 3);
+    // slabs; fminf/fmaxf drop NaNs from 0*inf
+    const float c0lox = (n0.x - o.x) * idir.x, c0hix = (n0.y - o.x) * idir.x;
+    const float c0loy = (n0.z - o.y) * idir.y, c0hiy = (n0.w - o.y) * idir.y;
+    const float c0loz = (n2.x - o.z) * idir.z, c0hiz = (n2.y - o.z) * idir.z;
+    const float c1lox = (n1.x - o.x) * idir.x, c1hix = (n1.y - o.x) * idir.x;
+    const float c1loy = (n1.z - o.y) * idir.y, c1hiy = (n1.w - o.y) * idir.y;
+    const float c1loz = (n2.z - o.z) * idir.z, c1hiz = (n2.w - o.z) * idir.z;
+    const float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), mint));
+    const float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tmax));
+    const float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), mint));
+    const float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tmax));
+    // conservative far bound (flat boxes, rounding): 1 + 2*gamma(3)
+    const bool h0 = t0n <= t0f * 1.0000004f;
+    const bool h1 = t1n <= t1f * 1.0000004f;
+    int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+    if (h0 && h1) {
+        if (t1n < t0n) {
+            const int tmp = c0; c0 = c1; c1 = tmp;
+        }
+        stack[sp++] = c1;
+        return c0;
+    }
+    if (h0 | h1) return h0 ? c0 : c1;
+    return sp ? stack[--sp] : kDoneNode;
+}
+
+// All primitives of one leaf (<= 4): the branch-free affine test that serves rectangles and triangles alike.
+// Returns true on the first accepted hit in any-hit mode.
+template <bool kAnyHit, bool kCount>
+PG_DEV bool bvhLeafStep(const DeviceScene &S, int node, float3 o, float3 d, float mint, float &tmax, Hit &hit, uint32_t *cntPrims) {
+    const uint32_t code = (uint32_t)(~node);
+    const uint32_t first = code >> kLeafShift, count = code & 7u, rectMask = (code >> 3) & 15u;
+    for (uint32_t i = 0; i < count; ++i) {
+        const float4 r0 = __ldg(S.prims + 3 * (first + i));
+        const float4 r1 = __ldg(S.prims + 3 * (first + i) + 1);
+        const float4 r2 = __ldg(S.prims + 3 * (first + i) + 2);
+        if (kCount) (*cntPrims)++;
+        // local = M o + w, local direction = M d (rectangle.cpp:125-133 for rectangles)
+        const float loz = r2.x * o.x + r2.y * o.y + r2.z * o.z + r2.w;
+        const float ldz = r2.x * d.x + r2.y * d.y + r2.z * d.z;
+        const float t = -loz / ldz;
+        if (t >= mint && t <= tmax) {
+            const float lox = r0.x * o.x + r0.y * o.y + r0.z * o.z + r0.w;
+            const float loy = r1.x * o.x + r1.y * o.y + r1.z * o.z + r1.w;
+            const float ldx = r0.x * d.x + r0.y * d.y + r0.z * d.z;
+            const float ldy = r1.x * d.x + r1.y * d.y + r1.z * d.z;
+            const float u = lox + ldx * t, v = loy + ldy * t;
+            const bool isRect = (rectMask >> i) & 1u;
+            const bool ok = isRect ? (fabsf(u) <= 1 && fabsf(v) <= 1) : (u >= 0 && v >= 0 && u + v <= 1.0f);
+            if (ok) {
+                hit.prim = first + i;
+                if (kAnyHit) return true;
+                tmax = t;
+                hit.t = t;
+                hit.u = u;
+                hit.v = v;
+            }
+        }
+    }
+    return false;
+}
+
 template <bool kAnyHit, bool kCount>
 PG_DEV bool traceRay(const DeviceScene &S, float3 o, float3 d, float mint, float maxt, Hit &hit, uint32_t *cntNodes,
                      uint32_t *cntPrims) {
     // "while-while" traversal: every lane first descends to its next leaf, then the warp processes
     // leaves together, so that the (uniform, branch-free) primitive test runs with many lanes active.
     const float3 idir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    const int kDone = (int)0x80000000;  // ~kDone is not a valid leaf code
     int stack[48];
     int sp = 0;
     int node = 0;
@@ -72,75 +141,13 @@ PG_DEV bool traceRay(const DeviceScene &S, float3 o, float3 d, float mint, float
     float tmax = maxt;
     while (true) {
         while (node >= 0) {
-            const float4 n0 = __ldg(S.nodes + 4 * node + 0);
-            const float4 n1 = __ldg(S.nodes + 4 * node + 1);
-            const float4 n2 = __ldg(S.nodes + 4 * node + 2);
-            const float4 n3 = __ldg(S.nodes + 4 * node + 3);
             if (kCount) (*cntNodes)++;
-            // slabs; fminf/fmaxf drop NaNs from 0*inf
-            const float c0lox = (n0.x - o.x) * idir.x, c0hix = (n0.y - o.x) * idir.x;
-            const float c0loy = (n0.z - o.y) * idir.y, c0hiy = (n0.w - o.y) * idir.y;
-            const float c0loz = (n2.x - o.z) * idir.z, c0hiz = (n2.y - o.z) * idir.z;
-            const float c1lox = (n1.x - o.x) * idir.x, c1hix = (n1.y - o.x) * idir.x;
-            const float c1loy = (n1.z - o.y) * idir.y, c1hiy = (n1.w - o.y) * idir.y;
-            const float c1loz = (n2.z - o.z) * idir.z, c1hiz = (n2.w - o.z) * idir.z;
-            const float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), mint));
-            const float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tmax));
-            const float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), mint));
-            const float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tmax));
-            // conservative far bound (flat boxes, rounding): 1 + 2*gamma(3)
-            const bool h0 = t0n <= t0f * 1.0000004f;
-            const bool h1 = t1n <= t1f * 1.0000004f;
-            int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-            if (h0 && h1) {
-                if (t1n < t0n) {
-                    const int tmp = c0; c0 = c1; c1 = tmp;
-                }
-                stack[sp++] = c1;
-                node = c0;
-            } else if (h0 | h1) {
-                node = h0 ? c0 : c1;
-            } else {
-                node = sp ? stack[--sp] : kDone;
-            }
+            node = bvhNodeStep(S, node, o, idir, mint, tmax, stack, sp);
         }
-        if (node == kDone) break;
-        {
-            const uint32_t code = (uint32_t)(~node);
-            const uint32_t first = code >> kLeafShift, count = code & 7u, rectMask = (code >> 3) & 15u;
-            for (uint32_t i = 0; i < count; ++i) {
-                const float4 r0 = __ldg(S.prims + 3 * (first + i));
-                const float4 r1 = __ldg(S.prims + 3 * (first + i) + 1);
-                const float4 r2 = __ldg(S.prims + 3 * (first + i) + 2);
-                if (kCount) (*cntPrims)++;
-                // local = M o + w, local direction = M d (rectangle.cpp:125-133 for rectangles)
-                const float loz = r2.x * o.x + r2.y * o.y + r2.z * o.z + r2.w;
-                const float ldz = r2.x * d.x + r2.y * d.y + r2.z * d.z;
-                const float t = -loz / ldz;
-                if (t >= mint && t <= tmax) {
-                    const float lox = r0.x * o.x + r0.y * o.y + r0.z * o.z + r0.w;
-                    const float loy = r1.x * o.x + r1.y * o.y + r1.z * o.z + r1.w;
-                    const float ldx = r0.x * d.x + r0.y * d.y + r0.z * d.z;
-                    const float ldy = r1.x * d.x + r1.y * d.y + r1.z * d.z;
-                    const float u = lox + ldx * t, v = loy + ldy * t;
-                    const bool isRect = (rectMask >> i) & 1u;
-                    const bool ok = isRect ? (fabsf(u) <= 1 && fabsf(v) <= 1) : (u >= 0 && v >= 0 && u + v <= 1.0f);
-                    if (ok) {
-                        if (kAnyHit) {
-                            hit.prim = first + i;
-                            return true;
-                        }
-                        tmax = t;
-                        hit.t = t;
-                        hit.u = u;
-                        hit.v = v;
-                        hit.prim = first + i;
-                    }
-                }
-            }
-            node = sp ? stack[--sp] : kDone;
-            if (node == kDone) break;
-        }
+        if (node == kDoneNode) break;
+        if (bvhLeafStep<kAnyHit, kCount>(S, node, o, d, mint, tmax, hit, cntPrims)) return true;
+        node = sp ? stack[--sp] : kDoneNode;
+        if (node == kDoneNode) break;
     }
     return hit.prim != kMiss;
 }
