@@ -97,6 +97,7 @@ struct Integrator {
     DevBuf<float4> dHits, dShO, dShD, dShC;
     DevBuf<int32_t> dShMedium;
     DevBuf<uint4> dShAux;
+    DevBuf<float4> dTrkA, dTrkB, dLookL;
     DevBuf<float4> dSplat;
     DevBuf<Counters> dCounters;
     DevBuf<float4> dFilm;
@@ -221,7 +222,9 @@ struct Integrator {
         if (n <= batchCapacity) return;
         bufA.alloc(n); bufB.alloc(n);
         dHits.alloc(n); dShO.alloc(n); dShD.alloc(n); dShC.alloc(n); dShMedium.alloc(n);
-        if (params.volumetric) dShAux.alloc(n);
+        if (params.volumetric) {
+            dShAux.alloc(n); dTrkA.alloc(n); dTrkB.alloc(n); dLookL.alloc(n);
+        }
         dSplat.alloc(2 * n);
         batchCapacity = n;
     }
@@ -270,6 +273,7 @@ struct Integrator {
         A.film = dFilm.p;
         A.radianceOut = radianceOut;
         A.splat = dSplat.p;
+        A.trkA = dTrkA.p; A.trkB = dTrkB.p; A.lookL = dLookL.p;
         const int maxBounces = params.max_depth > 0 ? std::min(params.max_depth + 1, 256) : 256;
         Counters *C = dCounters.p;
         int b = 0;

@@ -8,8 +8,15 @@
 //   k_shadow_vol  attenuated emitter connections: Scene::evalTransmittance (src/librender/scene.cpp:662-722)
 //                 through any number of index-matched boundaries, Woodcock-tracking transmittance
 //                 (heterogeneous.cpp:546-587)
+//   k_look_vol    the emitter look-up along the ray sampled one iteration earlier (:401-460), as its own stage
+//   k_track_vol   Russian roulette + free-flight distance sampling of every queued path, as its own stage
+// The Woodcock loops run a geometrically distributed number of steps per path, and only for paths inside a medium:
+// inside the shade kernel they ran with 4.7 of 32 lanes (profiles/r01_v3_vol_summary.txt). The three tracking stages
+// (k_look_vol, k_track_vol, k_shadow_vol) are therefore persistent warps with PER-LANE refill: every lane owns one
+// job, advances it by one tracking step per iteration, and fetches the next job from the device cursor as soon as its
+// own is finished, so the step body always runs with (nearly) all lanes. k_shade_vol only handles the events.
 // The closest-hit query of every newly sampled ray is k_trace's (kernels.cu); follow-up segments behind
-// index-matched boundaries are traced inline, by the thread that owns the path.
+// index-matched boundaries are traced inline, by the lane that owns the job.
 //
 // RNG: transmittance estimates of one connection draw from a stream forked off the path's stream
 // (Rng::fork) so that the main stream advances by a fixed amount per connection (DESIGN.md "RNG").
@@ -48,22 +55,171 @@ PG_DEV BoundaryHit boundaryOf(const DeviceScene &S, const Hit &h, const Intersec
     return b;
 }
 
-// rayIntersectAndLookForEmitter (progressive_volpath.cpp:401-460). `first` is the closest hit of (o, d)
-// found by k_trace. Returns the attenuated emitted radiance and the direct-sampling record fields that
-// pdfEmitterDirect needs.
-PG_DEV float3 lookForEmitter(const DeviceScene &S, Rng &fr, int medium, int maxInteractions, float3 o, float3 d, BoundaryHit cur,
-                             int &emitter, float3 &emN, float &emDist, unsigned long long &rays) {
-    float transmittance = 1.0f;
-    int interactions = 0;
-    emitter = -1;
+// ---- persistent warps with per-lane refill -----------------------------------------------------------------------
+// Job interface: bool fetch(uint32_t i)  -> set up job i; false when it completed right away (output already written)
+//                bool tracking           -> the job's next unit of work is a tracking step
+//                void trackStep()        -> one tentative collision (cheap, uniform); clears `tracking` when the walk is over
+//                bool logicStep()        -> everything between two walks (boundary logic, inline traversal: expensive,
+//                                           divergent); true when the job is finished
+//                void finish()           -> write the job's output
+// Schedule: tracking steps run in bursts while at least kMinTrack lanes are walking; lanes whose walk is over wait for
+// the burst to end, then all of them run their logic step together, finished lanes are refilled, and the next burst
+// starts. The expensive divergent code is thus executed once per burst instead of once per tracking step.
+static constexpr int kMinTrack = 12;
+template <typename Job>
+PG_DEV void runWithRefill(Job &job, uint32_t n, uint32_t *work) {
+    const unsigned ltMask = (1u << laneId()) - 1u;
+    bool active = false, exhausted = false;
     while (true) {
-        if (medium >= 0) transmittance *= mediumTransmittance(S.media[medium], S.density, o, d, 0.0f, cur.t, fr);
-        if (cur.valid && (interactions == maxInteractions || !cur.isNull || cur.emitter >= 0)) break;
-        if (!cur.valid) break;
-        if (transmittance == 0) return f3(0.0f);
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (idle && !exhausted) {
+            const int leader = __ffs(idle) - 1, cnt = __popc(idle);
+            uint32_t base = 0;
+            if ((int)laneId() == leader) base = atomicAdd(work, (uint32_t)cnt);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (!active) {
+                const uint32_t i = base + __popc(idle & ltMask);
+                if (i < n) active = job.fetch(i);
+            }
+            exhausted = base + (uint32_t)cnt >= n;  // warp-uniform
+        }
+        if (!__any_sync(0xffffffffu, active)) {
+            if (exhausted) break;
+            continue;
+        }
+        while (true) {  // tracking burst
+            const bool walking = active && job.tracking;
+            const int nWalk = __popc(__ballot_sync(0xffffffffu, walking));
+            if (nWalk == 0) break;
+            if (nWalk < kMinTrack) {
+                const int nWait = __popc(__ballot_sync(0xffffffffu, active && !job.tracking));
+                const int nIdle = __popc(__ballot_sync(0xffffffffu, !active));
+                if (nWait > 0 || (nIdle > 0 && !exhausted)) break;
+            }
+            if (walking) job.trackStep();
+        }
+        if (active && !job.tracking && job.logicStep()) {
+            job.finish();
+            active = false;
+        }
+    }
+}
+
+// The two ratio-free tracking trials of HeterogeneousMedium::evalTransmittance (heterogeneous.cpp:546-587), one
+// tentative collision per step() so that it can be interleaved with other lanes' work.
+struct TrialTracker {
+    float t, mint, maxt, result;
+    int trial;
+    // false: the segment misses the density box (transmittance 1, no random numbers consumed)
+    PG_DEV bool begin(const MediumRecord &M, float3 o, float3 d, float rmint, float rmaxt) {
+        float a, b;
+        if (!mediumClip(M, o, d, a, b)) return false;
+        mint = fmaxf(a, rmint);
+        maxt = fminf(b, rmaxt);
+        t = mint;
+        result = 0.0f;
+        trial = 0;
+        return true;
+    }
+    // true when both trials are over
+    PG_DEV bool step(const MediumRecord &M, const float *density, float3 o, float3 d, Rng &rng) {
+        bool over;
+        t -= logf(1 - rng.next1D()) * M.invMaxDensity;
+        if (t >= maxt) {
+            result += 1;
+            over = true;
+        } else {
+            const float dens = gridLookup(M, density, o + d * t) * M.scale;
+            over = dens * M.invMaxDensity > rng.next1D();
+        }
+        if (over) {
+            t = mint;
+            return ++trial == 2;
+        }
+        return false;
+    }
+    PG_DEV float value() const { return result * 0.5f; }
+};
+
+PG_DEV Rng loadRng(float4 pos4, uint32_t width, uint32_t &pixel) {
+    Rng rng;
+    pixel = (uint32_t)pos4.y * width + (uint32_t)pos4.x;
+    rng.state = ((uint64_t)__float_as_uint(pos4.w) << 32) | (uint64_t)__float_as_uint(pos4.z);
+    rng.inc = ((uint64_t)pixel << 1) | 1ULL;
+    return rng;
+}
+
+// ---- k_look_vol: rayIntersectAndLookForEmitter (progressive_volpath.cpp:401-460) + the MIS weight of its result
+struct LookJob {
+    const ShadeArgs &A;
+    unsigned long long rays = 0;
+    uint32_t idx;
+    float3 o, d, thr;
+    float prevPdf, transmittance;
+    uint32_t fl;
+    int medium, interactions, maxInteractions;
+    BoundaryHit cur;
+    Rng fr;
+    TrialTracker trk;
+    bool tracking, zero;
+    PG_DEV LookJob(const ShadeArgs &a) : A(a) {}
+
+    PG_DEV void beginSegment() {
+        tracking = medium >= 0 && trk.begin(A.S.media[medium], o, d, 0.0f, cur.t);
+    }
+    PG_DEV bool fetch(uint32_t i) {
+        idx = i;
+        fl = A.cur.flags[i];
+        if ((fl & kFlagDead) || !(fl & kFlagLook)) {
+            A.lookL[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            return false;
+        }
+        const float4 ro = A.cur.rayO[i], rd = A.cur.rayD[i], thr4 = A.cur.thr[i], h4 = A.hits[i];
+        o = f3(ro.x, ro.y, ro.z);
+        d = f3(rd.x, rd.y, rd.z);
+        thr = f3(thr4.x, thr4.y, thr4.z);
+        prevPdf = A.cur.rad[i].w;
+        medium = A.cur.medium[i];
+        uint32_t pixel;
+        Rng rng = loadRng(A.cur.pos[i], (uint32_t)A.S.film.width, pixel);
+        fr = rng.fork();
+        Hit h;
+        h.t = h4.x;
+        h.u = h4.y;
+        h.v = h4.z;
+        h.prim = __float_as_uint(h4.w);
+        Intersection its;
+        if (h.prim != kMiss) fillIntersection(A.S, o, d, h, its);
+        cur = boundaryOf(A.S, h, its);
+        // the look-up ran with maxDepth - depth - 1, depth = the value before the loop's depth++
+        maxInteractions = A.cfg.maxDepth - (int)(fl & kDepthMask) - 1;
+        interactions = 0;
+        transmittance = 1.0f;
+        zero = false;
+        beginSegment();
+        return true;
+    }
+    PG_DEV void trackStep() {
+        if (trk.step(A.S.media[medium], A.S.density, o, d, fr)) {
+            transmittance *= trk.value();
+            tracking = false;
+        }
+    }
+    PG_DEV bool logicStep() {
+        const DeviceScene &S = A.S;
+        // the segment's transmittance is in: boundary logic of the reference loop
+        if (cur.valid && (interactions == maxInteractions || !cur.isNull || cur.emitter >= 0)) return true;
+        if (!cur.valid) return true;
+        if (transmittance == 0) {
+            zero = true;
+            return true;
+        }
         if (cur.transition) medium = dot(d, cur.geoN) > 0 ? cur.exterior : cur.interior;
         o = o + d * cur.t;
-        if (++interactions > 100) return f3(0.0f);
+        if (++interactions > 100) {
+            zero = true;
+            return true;
+        }
         Hit h;
         const float mint = adaptiveMinT(o, kEpsilon, false);
         uint32_t cn = 0, cp = 0;
@@ -72,15 +228,141 @@ PG_DEV float3 lookForEmitter(const DeviceScene &S, Rng &fr, int medium, int maxI
         Intersection its;
         if (h.prim != kMiss) fillIntersection(S, o, d, h, its);
         cur = boundaryOf(S, h, its);
+        beginSegment();
+        return false;
     }
-    if (cur.valid && cur.emitter >= 0) {
-        emitter = cur.emitter;
-        emN = cur.shN;
-        emDist = cur.t;
-        const float3 Le = dot(cur.shN, -d) <= 0 ? f3(0.0f) : ld3(S.emitters[cur.emitter].radiance);  // area.cpp:104-109
-        return Le * transmittance;
+    PG_DEV void finish() {
+        const DeviceScene &S = A.S;
+        float3 contrib = f3(0.0f);
+        if (!zero && cur.valid && cur.emitter >= 0) {
+            const float3 Le = dot(cur.shN, -d) <= 0 ? f3(0.0f) : ld3(S.emitters[cur.emitter].radiance);  // area.cpp:104-109
+            const float3 value = Le * transmittance;
+            const bool prevMedium = (fl & kFlagPrevMedium) != 0;
+            if (!isZero(value) && (!prevMedium || fminf(value.x, fminf(value.y, value.z)) > 0.0f)) {  // (:288-303, :330-345)
+                const float emitterPdf = (A.cfg.useNee && !(fl & kFlagPrevDelta)) ? pdfEmitterDirect(S, cur.emitter, d, cur.shN, cur.t) : 0.0f;
+                const float weight = A.cfg.useNee ? miWeight(prevPdf, emitterPdf) : 1.0f;
+                contrib = thr * value * weight;
+            }
+        }
+        A.lookL[idx] = make_float4(contrib.x, contrib.y, contrib.z, 0.0f);
     }
-    return f3(0.0f);
+};
+
+__global__ void __launch_bounds__(128) k_look_vol(ShadeArgs A) {
+    LookJob job(A);
+    runWithRefill(job, A.C->queue[A.bounce], &A.C->lookWork[A.bounce]);
+    warpAddU64(&A.C->normalRays, job.rays);
+}
+
+// ---- k_track_vol: the part of the loop between the emitter look-up and the event: Russian roulette of the previous
+// iteration (:350-360), loop condition, free-flight distance (:118-121). Output per queued path:
+//   trkA = {distance of the medium event (inf: none), rng state lo, hi (bits), flags: 1 = path ends here}
+//   trkB = {throughput after roulette and (guided) tracking weights, density at the event}
+struct TrackJob {
+    const ShadeArgs &A;
+    uint32_t idx;
+    float3 o, d, thr, albedo;
+    float t, maxt, dens, albedoAvg;
+    int medium;
+    bool guidedDist, event, tracking;
+    Rng rng;
+    PG_DEV TrackJob(const ShadeArgs &a) : A(a) {}
+
+    PG_DEV void write(float tEvent, uint32_t bits) {
+        A.trkA[idx] = make_float4(tEvent, __uint_as_float((uint32_t)rng.state), __uint_as_float((uint32_t)(rng.state >> 32)),
+                                  __uint_as_float(bits));
+        A.trkB[idx] = make_float4(thr.x, thr.y, thr.z, dens);
+    }
+    PG_DEV bool fetch(uint32_t i) {
+        idx = i;
+        const uint32_t fl = A.cur.flags[i];
+        const float4 thr4 = A.cur.thr[i];
+        thr = f3(thr4.x, thr4.y, thr4.z);
+        dens = 0.0f;
+        uint32_t pixel;
+        rng = loadRng(A.cur.pos[i], (uint32_t)A.S.film.width, pixel);
+        if (fl & kFlagDead) {
+            write(kInf, 1u);
+            return false;
+        }
+        uint32_t depth = fl & kDepthMask;
+        bool terminate = false;
+        if (fl & kFlagLook) {
+            rng.nextU32();  // the look-up's stream was forked off here (Rng::fork consumes two words)
+            rng.nextU32();
+            if (depth++ >= (uint32_t)A.cfg.rrDepth) {
+                const float q = fminf(maxComp(thr) * thr4.w * thr4.w, 0.95f);
+                if (rng.next1D() >= q)
+                    terminate = true;
+                else
+                    thr = thr / q;
+            }
+        }
+        if (!terminate && !((int)depth <= A.cfg.maxDepth || A.cfg.maxDepth < 0)) terminate = true;
+        if (terminate) {
+            write(kInf, 1u);
+            return false;
+        }
+        medium = A.cur.medium[i];
+        if (medium < 0) {
+            write(kInf, 0u);
+            return false;
+        }
+        const float4 ro = A.cur.rayO[i], rd = A.cur.rayD[i], h4 = A.hits[i];
+        o = f3(ro.x, ro.y, ro.z);
+        d = f3(rd.x, rd.y, rd.z);
+        const MediumRecord &M = A.S.media[medium];
+        float a, b;
+        if (!mediumClip(M, o, d, a, b)) {
+            write(kInf, 0u);
+            return false;
+        }
+        t = fmaxf(a, 0.0f);
+        maxt = fminf(b, __float_as_uint(h4.w) != kMiss ? h4.x : kInf);
+        guidedDist = A.G.enabled && A.cfg.guidedDistance;
+        albedo = ld3(M.albedo);
+        albedoAvg = (albedo.x + albedo.y + albedo.z) * (1.0f / 3.0f);
+        event = false;
+        tracking = true;
+        return true;
+    }
+    PG_DEV void trackStep() { tracking = !walk(); }
+    PG_DEV bool logicStep() { return true; }
+    // one tentative collision: heterogeneous.cpp:589-663 (Woodcock), or its guided variant (medium_device.cuh)
+    PG_DEV bool walk() {
+        const MediumRecord &M = A.S.media[medium];
+        t -= logf(1 - rng.next1D()) * M.invMaxDensity;
+        if (t >= maxt) return true;
+        const float3 p = o + d * t;
+        if (!guidedDist) {
+            dens = gridLookup(M, A.S.density, p) * M.scale;
+            if (dens * M.invMaxDensity > rng.next1D()) {
+                event = true;
+                return true;
+            }
+            return false;
+        }
+        const float a = fminf(gridLookup(M, A.S.density, p) * M.scale * M.invMaxDensity, 1.0f);
+        const float u = rng.next1D();
+        if (!(a > 0)) return false;
+        const float g = 4 * kPi * guidePdf(A.G, guideLookup(A.G, p), d);
+        const float num = a * albedoAvg, den = num + (1 - a) * g;
+        const float pGuided = den > 0 ? num / den : a;
+        const float pReal = 0.5f * a + 0.5f * pGuided;
+        if (u < pReal) {
+            thr = thr * (albedo * (a / pReal));
+            event = true;
+            return true;
+        }
+        thr = thr * ((1 - a) / (1 - pReal));
+        return false;
+    }
+    PG_DEV void finish() { write(event ? t : kInf, 0u); }
+};
+
+__global__ void __launch_bounds__(128) k_track_vol(ShadeArgs A) {
+    TrackJob job(A);
+    runWithRefill(job, A.C->queue[A.bounce], &A.C->trackWork[A.bounce]);
 }
 
 __global__ void __launch_bounds__(kShadeThreads) k_shade_vol(ShadeArgs A) {
@@ -89,7 +371,7 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_vol(ShadeArgs A) {
     const uint32_t n = A.C->queue[A.bounce];
     uint32_t *nextCount = &A.C->queue[A.bounce + 1];
     uint32_t *shadowCount = &A.C->shadow[A.bounce];
-    unsigned long long donePaths = 0, doneLen = 0, extraRays = 0;
+    unsigned long long donePaths = 0, doneLen = 0;
     __shared__ uint32_t sAppend[2 * 3 * (kShadeThreads / 32 + 1)];
     uint32_t appendParity = 0;
 
@@ -151,46 +433,33 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_vol(ShadeArgs A) {
                 if (hitValid) fillIntersection(S, o, d, h, its);
                 const int maxDepth = cfg.maxDepth;
 
-                // ---- second half of the previous loop iteration: emitter look-up along the sampled ray with
-                // MIS (:288-303 phase, :330-345 BSDF), then Russian roulette (:350-360)
+                // ---- results of the two tracking stages for this path: attenuated emitter radiance found along the ray
+                // (k_look_vol, already MIS-weighted), Russian roulette / loop condition / free-flight distance (k_track_vol)
+                const float4 tA = A.trkA[i], tB = A.trkB[i];
                 if (fl & kFlagLook) {
-                    Rng fr = rng.fork();
-                    int emitter;
-                    float3 emN = f3(0.0f);
-                    float emDist = 0.0f;
-                    // depth here is the value before the loop's depth++ (the look-up ran with maxDepth - depth - 1)
-                    const float3 value = lookForEmitter(S, fr, medium, maxDepth - (int)depth - 1, o, d, boundaryOf(S, h, its), emitter,
-                                                        emN, emDist, extraRays);
-                    const bool prevMedium = (fl & kFlagPrevMedium) != 0;
-                    if (!isZero(value) && (!prevMedium || fminf(value.x, fminf(value.y, value.z)) > 0.0f)) {
-                        const float emitterPdf = (cfg.useNee && !(fl & kFlagPrevDelta)) ? pdfEmitterDirect(S, emitter, d, emN, emDist) : 0.0f;
-                        const float weight = cfg.useNee ? miWeight(rad4.w, emitterPdf) : 1.0f;
-                        L += thr * value * weight;
-                    }
+                    const float4 lk = A.lookL[i];
+                    L += f3(lk.x, lk.y, lk.z);
                     fl &= ~(kFlagFirst | kFlagLook);  // rRec.type &= ~EEmittedRadiance
-                    if (depth++ >= (uint32_t)cfg.rrDepth) {
-                        const float q = fminf(maxComp(thr) * eta * eta, 0.95f);
-                        if (rng.next1D() >= q)
-                            terminate = true;
-                        else
-                            thr = thr / q;
-                    }
+                    depth++;
                     fl |= kFlagScattered;
                 }
-                if (!terminate && !((int)depth <= maxDepth || maxDepth < 0)) terminate = true;
+                if (__float_as_uint(tA.w) & 1u) terminate = true;  // Russian roulette or the loop condition ended the path
+                thr = f3(tB.x, tB.y, tB.z);
+                rng.state = ((uint64_t)__float_as_uint(tA.z) << 32) | (uint64_t)__float_as_uint(tA.y);
 
                 if (!terminate) {
-                    // ---- free-flight distance in the current medium (:118-121)
                     MediumSample mRec;
-                    bool mediumEvent = false;
+                    const bool mediumEvent = tA.x < kInf;
                     const bool guidedDist = A.G.enabled && cfg.guidedDistance && medium >= 0;
-                    float3 distWeight = f3(1.0f);
-                    if (guidedDist)
-                        mediumEvent = mediumSampleDistanceGuided(S.media[medium], S.density, A.G, o, d, 0.0f, hitValid ? h.t : kInf, mRec,
-                                                                 distWeight, rng);
-                    else if (medium >= 0)
-                        mediumEvent = mediumSampleDistance(S.media[medium], S.density, o, d, 0.0f, hitValid ? h.t : kInf, mRec, rng);
-                    if (guidedDist) thr *= distWeight;  // real-collision and null-collision weights alike
+                    if (mediumEvent) {
+                        mRec.t = tA.x;
+                        mRec.p = o + d * tA.x;
+                        const float densityAtT = tB.w;
+                        mRec.sigmaS = ld3(S.media[medium].albedo) * densityAtT;
+                        float tr = densityAtT != 0.0f ? 1.0f / densityAtT : 0.0f;
+                        if (!isfinite(tr)) tr = 0.0f;
+                        mRec.transmittance = tr;
+                    }
                     if (mediumEvent) {
                         const MediumRecord &M = S.media[medium];
                         if ((int)depth >= maxDepth && maxDepth != -1) {
@@ -396,76 +665,100 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_vol(ShadeArgs A) {
     }
     warpAddU64(&A.C->paths, donePaths);
     warpAddU64(&A.C->pathLen, doneLen);
-    warpAddU64(&A.C->normalRays, extraRays);
 }
 
 // Scene::evalTransmittance (scene.cpp:662-722) for the queued emitter connections; an unoccluded
 // connection adds contribution * transmittance to the path record it belongs to.
-__global__ void __launch_bounds__(128) k_shadow_vol(DeviceScene S, ShadowQueue Q, float4 *__restrict__ rad, const uint32_t *nPtr,
-                                                    uint32_t *work, Counters *C) {
-    const uint32_t n = *nPtr;
+struct ShadowJob {
+    const DeviceScene &S;
+    const ShadowQueue &Q;
+    float4 *rad;
     unsigned long long rays = 0;
-    while (true) {
-        uint32_t base = 0;
-        if (laneId() == 0) base = atomicAdd(work, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint32_t i = base + laneId();
-        if (i >= n) continue;
+    uint32_t idx;
+    float3 o, d;
+    float remaining, maxt, mintRaw, transmittance, segT;
+    int medium, interactions, maxInteractions;
+    bool surface, tracking;
+    ShapeRecord sr;
+    uint32_t primSlot, primIdx;
+    Rng rng;
+    TrialTracker trk;
+    PG_DEV ShadowJob(const DeviceScene &s, const ShadowQueue &q, float4 *r) : S(s), Q(q), rad(r) {}
+
+    // one segment: closest hit with the shadow-style epsilon (ShapeKDTree::rayIntersect(ray, t, shape, n, uv),
+    // skdtree.cpp:144-205), occluder test, then the segment's transmittance trials. true = connection decided.
+    PG_DEV bool beginSegment() {
+        if (!(remaining > 0)) return true;
+        Hit h;
+        h.prim = kMiss;
+        const float mint = adaptiveMinT(o, mintRaw, true);
+        uint32_t cn = 0, cp = 0;
+        rays++;
+        surface = false;
+        if (maxt > mint) surface = traceRay<false, false>(S, o, d, mint, maxt, h, &cn, &cp);
+        segT = surface ? h.t : kInf;
+        if (surface) {
+            const PrimInfo pi = S.primInfo[h.prim];
+            sr = S.shapes[pi.shape];
+            primSlot = h.prim;
+            primIdx = pi.prim;
+            if (interactions == maxInteractions || !(S.bsdfs[sr.bsdf].typeFlags & kNull)) {
+                transmittance = 0.0f;  // occluder
+                return true;
+            }
+        }
+        tracking = medium >= 0 && trk.begin(S.media[medium], o, d, 0.0f, fminf(segT, remaining));
+        return false;
+    }
+    PG_DEV bool fetch(uint32_t i) {
+        idx = i;
         const float4 ro = Q.o[i], rd = Q.d[i];
         const uint4 aux = Q.aux[i];
-        float3 o = f3(ro.x, ro.y, ro.z);
-        const float3 d = f3(rd.x, rd.y, rd.z);
-        int medium = Q.medium[i];
-        const int maxInteractions = (int)aux.w;
-        Rng rng;
+        o = f3(ro.x, ro.y, ro.z);
+        d = f3(rd.x, rd.y, rd.z);
+        medium = Q.medium[i];
+        maxInteractions = (int)aux.w;
         rng.state = ((uint64_t)aux.y << 32) | (uint64_t)aux.x;
         rng.inc = ((uint64_t)aux.z << 1) | 1ULL;
-        float remaining = rd.w;
-        const float lengthFactor = 1.0f - kShadowEpsilon;  // the far end lies on the emitter's surface
-        float mintRaw = ro.w, maxt = remaining * lengthFactor;
-        float transmittance = 1.0f;
-        int interactions = 0;
-        while (remaining > 0) {
-            // ShapeKDTree::rayIntersect(ray, t, shape, n, uv) (skdtree.cpp:144-205): closest hit, shadow-style epsilon
-            Hit h;
-            h.prim = kMiss;
-            const float mint = adaptiveMinT(o, mintRaw, true);
-            uint32_t cn = 0, cp = 0;
-            rays++;
-            bool surface = false;
-            if (maxt > mint) surface = traceRay<false, false>(S, o, d, mint, maxt, h, &cn, &cp);
-            const float t = surface ? h.t : kInf;
-            ShapeRecord sr;
-            uint32_t primIdx = 0;
-            if (surface) {
-                const PrimInfo pi = S.primInfo[h.prim];
-                sr = S.shapes[pi.shape];
-                primIdx = pi.prim;
-                if (interactions == maxInteractions || !(S.bsdfs[sr.bsdf].typeFlags & kNull)) {
-                    transmittance = 0.0f;  // occluder
-                    break;
-                }
-            }
-            if (medium >= 0) transmittance *= mediumTransmittance(S.media[medium], S.density, o, d, 0.0f, fminf(t, remaining), rng);
-            if (!surface || transmittance == 0) break;
-            if (sr.interiorMedium >= 0 || sr.exteriorMedium >= 0) {
-                const float3 nrm = windingNormal(S, h.prim, sr, primIdx);
-                const int expected = dot(-d, nrm) > 0 ? sr.exteriorMedium : sr.interiorMedium;
-                if (medium != expected) {  // medium inconsistency (scene.cpp:703-707)
-                    transmittance = 0.0f;
-                    break;
-                }
-                medium = dot(d, nrm) > 0 ? sr.exteriorMedium : sr.interiorMedium;
-            }
-            if (++interactions > 100) break;
-            o = o + d * t;
-            remaining -= t;
-            maxt = remaining * lengthFactor;
-            mintRaw = kEpsilon;
+        remaining = rd.w;
+        mintRaw = ro.w;
+        maxt = remaining * (1.0f - kShadowEpsilon);  // the far end lies on the emitter's surface
+        transmittance = 1.0f;
+        interactions = 0;
+        tracking = false;
+        if (beginSegment()) {
+            finish();
+            return false;
         }
+        return true;
+    }
+    PG_DEV void trackStep() {
+        if (trk.step(S.media[medium], S.density, o, d, rng)) {
+            transmittance *= trk.value();
+            tracking = false;
+        }
+    }
+    PG_DEV bool logicStep() {
+        if (!surface || transmittance == 0) return true;
+        if (sr.interiorMedium >= 0 || sr.exteriorMedium >= 0) {
+            const float3 nrm = windingNormal(S, primSlot, sr, primIdx);
+            const int expected = dot(-d, nrm) > 0 ? sr.exteriorMedium : sr.interiorMedium;
+            if (medium != expected) {  // medium inconsistency (scene.cpp:703-707)
+                transmittance = 0.0f;
+                return true;
+            }
+            medium = dot(d, nrm) > 0 ? sr.exteriorMedium : sr.interiorMedium;
+        }
+        if (++interactions > 100) return true;
+        o = o + d * segT;
+        remaining -= segT;
+        maxt = remaining * (1.0f - kShadowEpsilon);
+        mintRaw = kEpsilon;
+        return beginSegment();
+    }
+    PG_DEV void finish() {
         if (transmittance != 0) {
-            const float4 c = Q.c[i];
+            const float4 c = Q.c[idx];
             const uint32_t dst = __float_as_uint(c.w);
             float4 r = rad[dst];  // at most one connection per path and bounce: no race
             r.x += c.x * transmittance;
@@ -474,7 +767,13 @@ __global__ void __launch_bounds__(128) k_shadow_vol(DeviceScene S, ShadowQueue Q
             rad[dst] = r;
         }
     }
-    warpAddU64(&C->shadowRays, rays);
+};
+
+__global__ void __launch_bounds__(128) k_shadow_vol(DeviceScene S, ShadowQueue Q, float4 *__restrict__ rad, const uint32_t *nPtr,
+                                                    uint32_t *work, Counters *C) {
+    ShadowJob job(S, Q, rad);
+    runWithRefill(job, *nPtr, work);
+    warpAddU64(&C->shadowRays, job.rays);
 }
 
 // b200pg_k_grid_lookup: GridDataSource::lookupFloat on a batch of points
@@ -519,7 +818,9 @@ static int volGrid(K kernel, int block) {
 }
 
 void launchShadeVol(const ShadeArgs &A, cudaStream_t st) {
-    static int grid = volGrid(k_shade_vol, kShadeThreads);
+    static int gridLook = volGrid(k_look_vol, 128), gridTrack = volGrid(k_track_vol, 128), grid = volGrid(k_shade_vol, kShadeThreads);
+    k_look_vol<<<gridLook, 128, 0, st>>>(A);
+    k_track_vol<<<gridTrack, 128, 0, st>>>(A);
     k_shade_vol<<<grid, kShadeThreads, 0, st>>>(A);
 }
 void launchShadowVol(const DeviceScene &S, const ShadowQueue &Q, float4 *rad, const uint32_t *nPtr, uint32_t *work, Counters *C,

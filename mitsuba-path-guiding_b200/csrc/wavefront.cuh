@@ -63,6 +63,8 @@ struct Counters {
     uint32_t shadow[260];
     uint32_t traceWork[260];   // dynamic work-fetch cursors, one per bounce
     uint32_t shadowWork[260];
+    uint32_t lookWork[260];    // volumetric tracking stages (volpath.cu)
+    uint32_t trackWork[260];
     uint32_t misc[16];
     unsigned long long paths, normalRays, shadowRays, pathLen, nodesVisited, primsTested, trainSamples;
 };
@@ -85,6 +87,8 @@ struct ShadeArgs {
     float4 *film;
     float4 *splat;       // per slot, 2 x float4 = one 32-byte sector: {samplePos.xy, L.r, L.g} {L.b, 0, 0, 0} (written once)
     float *radianceOut;  // optional: per-slot radiance instead of film splats (b200pg_k_radiance)
+    float4 *trkA, *trkB; // volumetric: per queued path, output of k_track_vol (volpath.cu)
+    float4 *lookL;       // volumetric: per queued path, MIS-weighted emitter radiance found by k_look_vol
     GuideDevice G;
     int bounce;
 };
