@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(128) k_track_vol(ShadeArgs A) {
     runWithRefill(job, A.C->queue[A.bounce], &A.C->trackWork[A.bounce]);
 }
 
-__global__ void __launch_bounds__(kShadeThreads) k_shade_vol(ShadeArgs A) {
+__global__ void __launch_bounds__(kShadeThreads, 6) k_shade_vol(ShadeArgs A) {
     const DeviceScene &S = A.S;
     const IntegratorConfig &cfg = A.cfg;
     const uint32_t n = A.C->queue[A.bounce];
