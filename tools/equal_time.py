@@ -25,10 +25,10 @@ def relmse(img, ref):
     return float(e[: int(len(e) * 0.999)].mean())  # 0.1% outliers trimmed
 
 
-# converged reference: unguided, disjoint sample indices
+# converged reference: unguided path tracer, disjoint sample indices (REF_SPP samples per pixel)
 it = api.Integrator(scene, params(False))
 t0 = time.perf_counter()
-ref_spp = 8192 if size <= 512 else 4096
+ref_spp = int(os.environ.get("REF_SPP", "16384"))
 for k in range(ref_spp // 64):
     it.progression(1_000_000 + 64 * k, 64)
 ref = it.develop()
