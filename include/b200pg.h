@@ -308,7 +308,9 @@ int b200pg_k_bin_samples(void *integ, const float *pos, size_t n, uint32_t *out_
                          uint32_t *out_offsets, uint32_t *n_cells);
 /* A complete training update (bin, n_iter x (E, M), split) over externally supplied samples
  * (pos n*3, dir n*3, weight n, pdf n, dist n). n_iter = 0: E-step only, stats_out (cells*(4K+8) floats, may be NULL)
- * receives the sufficient statistics and the field is left untouched. */
+ * receives the sufficient statistics and the field is left untouched. With n_iter > 0 stats_out (if not NULL) receives
+ * the statistics of the LAST iteration, cells = the cell count BEFORE this update's split: size it for
+ * b200pg_stats().guide_cells * (4K+8) floats (pass NULL when they are not needed). */
 int b200pg_k_em_step(void *integ, const float *pos, const float *dir, const float *weight, const float *pdf,
                      const float *dist, size_t n, int n_iter, float *stats_out);
 /* Field snapshot as 32-bit words: header[8] = {'GUID', nNodes, nCells, K, 0...}, nodes[4*nNodes] = {axis (3 = leaf),

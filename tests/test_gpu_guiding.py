@@ -215,3 +215,72 @@ def test_b200pg_render_runs_the_training_schedule(api, pkg):
         it0.guiding_mode(True, True)
     with pytest.raises(api.B200pgError, match="guiding"):
         it0.train_begin()
+
+
+@pytest.mark.parametrize("K", [1, 5, 8, 24, 32])
+def test_em_other_component_counts(api, pkg, oracle, K):
+    """The E-step is compiled for K <= 8, <= 16 and <= 32 lobes: statistics, refit and split for K off the default."""
+    sb = pkg.scenes.cornell_box(32, 32, spp=1)
+    p = api.default_params()
+    p.max_depth, p.guiding, p.guide_max_components, p.guide_max_cell_samples = 4, 1, K, 3000
+    it = api.Integrator(api.Scene.from_builder(sb), p)
+    snap0 = it.field_snapshot()
+    assert snap0[3] == K and snap0[2] == 1
+    fld = oracle.field(K, (0, 0, 0), (1, 1, 1))
+    fld.load(snap0)
+    rng = np.random.RandomState(10 + K)
+    n = 20011  # not a multiple of the chunk (2048) or the warp
+    # samples from two planted lobes + a uniform background, 30% zero-weight, a few invalid weights
+    d = random_dirs(rng, n)
+    m1, m2 = np.array([0, 0, 1.0], np.float32), np.array([0.6, 0.8, 0], np.float32)
+    d[: n // 3] = (m1 + 0.15 * rng.randn(n // 3, 3)).astype(np.float32)
+    d[n // 3: n // 2] = (m2 + 0.3 * rng.randn(n // 2 - n // 3, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    w = (rng.rand(n) * 3).astype(np.float32)
+    w[rng.rand(n) < 0.3] = 0
+    w[5], w[6] = np.inf, -1.0
+    s = dict(pos=(rng.rand(n, 3) * [2, 2, 2] - [1, 0, 1]).astype(np.float32), dir=d.astype(np.float32), weight=w,
+             pdf=np.ones(n, np.float32), dist=np.ones(n, np.float32))
+    st_o = fld.estep(s)
+    st_g = it.k_em_step(s, 0, 1, K)
+    scale = np.maximum(np.abs(st_o).max(1, keepdims=True), 1e-6)
+    assert (np.abs(st_o - st_g) / scale).max() <= 1e-5
+    assert st_o[0, -8] == st_g[0, -8] == n
+    # two full updates (the first splits the root cell: 20011 samples > 3000)
+    for _ in range(2):
+        fld.train(s, 3, 3000.0)
+        it.k_em_step(s, 3, 64, K)  # statistics buffer sized for up to 64 cells (2 splits -> at most 4)
+    a, g = fld.snapshot(), it.field_snapshot()
+    nn, nc = int(a[1]), int(a[2])
+    assert nc >= 3 and a.size == g.size and np.array_equal(a[:8], g[:8])
+    # same tree after two splits: identical topology; the split planes are means of float position sums, which the GPU
+    # accumulates in a different order (1e-6 relative)
+    na, ng = a[8:8 + 4 * nn].reshape(nn, 4), g[8:8 + 4 * nn].reshape(nn, 4)
+    assert np.array_equal(na[:, [0, 2, 3]], ng[:, [0, 2, 3]])
+    np.testing.assert_allclose(ng[:, 1].view(np.float32), na[:, 1].view(np.float32), rtol=2e-6, atol=1e-6)
+    o = 8 + 4 * nn + 8 * nc
+    la, lg = a.view(np.float32)[o:].reshape(-1, 12), g.view(np.float32)[o:].reshape(-1, 12)
+    assert np.abs(la[:, 0] - lg[:, 0]).max() <= 2e-5
+    heavy = la[:, 0] > 1e-2
+    assert np.abs(la[heavy, 1:4] - lg[heavy, 1:4]).max() <= 5e-5
+    assert np.abs(_mean_cos(la[:, 4]) - _mean_cos(lg[:, 4])).max() <= 2e-5
+    hdr_a, hdr_g = a.view(np.float32)[8 + 4 * nn:o].reshape(nc, 8), g.view(np.float32)[8 + 4 * nn:o].reshape(nc, 8)
+    np.testing.assert_allclose(hdr_g[:, :2], hdr_a[:, :2], rtol=1e-5)  # running sample counts / weight sums
+
+
+def test_training_update_without_samples(api, pkg):
+    """An update over zero recorded samples is a no-op, not a crash (e.g. a progression whose paths all escaped)."""
+    sb = pkg.scenes.cornell_box(16, 16, spp=1)
+    p = api.default_params()
+    p.max_depth, p.guiding = 4, 1
+    it = api.Integrator(api.Scene.from_builder(sb), p)
+    before = it.field_snapshot()
+    n, c = it.train_fused(4)
+    assert (n, c) == (0, 1)
+    after = it.field_snapshot()
+    assert after[1] == before[1] and after[2] == before[2]
+    # and the field still answers queries with a normalised density
+    rng = np.random.RandomState(0)
+    d = random_dirs(rng, 20000)
+    q = it.k_vmm_pdf_sample(np.zeros((20000, 3), np.float32) + [0, 1, 0], d, rng.rand(20000, 3).astype(np.float32))
+    assert np.isfinite(q["pdf"]).all() and abs(q["pdf"].mean() * 4 * np.pi - 1) < 0.03
