@@ -2,8 +2,9 @@
 //   k_guide_cells      sample position -> cell index (kd-tree walk)
 //   k_radix_*          hand-written stable LSD radix sort (8-bit digits) of (cell, sample index) pairs = binning;
 //                      bit-exact against the oracle's stable counting sort (oracle_guiding.h: guideBin)
-//   k_estep            weighted-EM E-step, one warp per chunk of one cell's samples: lobes staged in shared memory,
-//                      lane = sample, per-lane sufficient statistics in registers, butterfly reduction per chunk
+//   k_estep            weighted-EM E-step, one warp per chunk of one cell's samples: samples streamed through shared memory
+//                      by bulk async copies (cp.async.bulk + mbarrier ring), lobes in shared memory, lane = sample,
+//                      per-lane sufficient statistics in registers, butterfly reduction per chunk
 //   k_gather_partition gather into sorted order + per-chunk partition (usable weights first)
 //   k_cell_moments     per-chunk position moments (split statistics), once per training update
 //   k_reduce_partials  per-cell sum of the chunk partials in a fixed order (deterministic)
@@ -337,63 +338,111 @@ __global__ void __launch_bounds__(1024) k_split(uint4 *__restrict__ nodes, float
 // sufficient statistics of its samples in registers; one butterfly reduction per work item at the end.
 // ~9 issued instructions per sample and lobe-free shuffles in the inner loop, against ~35 for the earlier
 // lane-per-lobe formulation (profiles/r01_v3_summary.txt).
+// ---- TMA-style bulk copies (cp.async.bulk, 1-D) + mbarrier, the Blackwell way to stream a contiguous array through
+// shared memory without staging registers
+__device__ __forceinline__ uint32_t smemAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulkLoad(void *dstSmem, const void *srcGlobal, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dstSmem)),
+                 "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(smemAddr(bar)), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+
+static constexpr int kEStages = 4;    // ring depth per warp
+static constexpr int kETile = 64;     // samples per stage (1 KB of positions + 1 KB of directions)
+
+// E-step. One warp per work item (<= kChunk consecutive samples of ONE cell, usable weights first); lane = sample.
+// The warp streams its samples through a private ring of kEStages shared-memory tiles filled by 1-D bulk async copies
+// (one elected lane arms the stage's mbarrier with the byte count and issues the two copies; all lanes wait on the
+// barrier's phase), so 16 KB per warp are in flight ahead of the arithmetic instead of one sample per lane in registers.
 template <int KMAX>
 __global__ void __launch_bounds__(128) k_estep(GuideDevice G, const float4 *__restrict__ sPos, const float4 *__restrict__ sDir,
                                                const uint4 *__restrict__ work, const uint32_t *__restrict__ counts,
                                                float *__restrict__ partials, int stride) {
     __shared__ float4 sLobe[4][KMAX * 2];
+    __shared__ __align__(128) float4 sTile[4][kEStages][2][kETile];
+    __shared__ __align__(8) uint64_t sBar[4][kEStages];
     const uint32_t nWork = counts[2];
     const uint32_t warp = threadIdx.x >> 5, ln = lane();
     const int K = G.K;
     float4 *myLobes = sLobe[warp];
+    if (ln == 0) {
+        for (int s = 0; s < kEStages; ++s) mbarInit(&sBar[warp][s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t parity = 0;  // bit s = phase the next wait on stage s expects
     for (uint32_t w = blockIdx.x * 4 + warp; w < nWork; w += gridDim.x * 4) {
         const uint4 item = work[w];
         __syncwarp();
         for (int k = (int)ln; k < 2 * K; k += 32) myLobes[k] = __ldg(G.lobes + (size_t)item.x * K * 2 + k);
-        __syncwarp();
         float S[KMAX], Rx[KMAX], Ry[KMAX], Rz[KMAX];
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) S[k] = Rx[k] = Ry[k] = Rz[k] = 0.0f;
         float cW = 0.0f;
         // samples with a usable weight were moved to the front of the chunk by k_gather_partition (item.w of them)
-        const uint32_t endGood = item.y + item.w;
-        uint32_t j = item.y + ln;
-        float4 pn = make_float4(0, 0, 0, 0), dn = pn;
-        if (j < endGood) {
-            pn = sPos[j];
-            dn = sDir[j];
-        }
-        for (; j < endGood; j += 32) {
-            const float4 p = pn, d = dn;
-            if (j + 32 < endGood) {  // prefetch the next sample while this one is evaluated
-                pn = sPos[j + 32];
-                dn = sDir[j + 32];
-            }
-            const float sw = p.w;
-            float pk[KMAX];
-            float total = 0.0f;
+        const uint32_t nGood = item.w, nTiles = (nGood + kETile - 1) / kETile;
+        auto issue = [&](uint32_t t) {  // lane 0 only
+            const int st = (int)(t % kEStages);
+            const uint32_t cnt = min((uint32_t)kETile, nGood - t * kETile), bytes = cnt * (uint32_t)sizeof(float4);
+            mbarExpectTx(&sBar[warp][st], 2 * bytes);
+            bulkLoad(&sTile[warp][st][0][0], sPos + item.y + (size_t)t * kETile, bytes, &sBar[warp][st]);
+            bulkLoad(&sTile[warp][st][1][0], sDir + item.y + (size_t)t * kETile, bytes, &sBar[warp][st]);
+        };
+        if (ln == 0)
+            for (uint32_t t = 0; t < min(nTiles, (uint32_t)kEStages); ++t) issue(t);
+        __syncwarp();
+        for (uint32_t t = 0; t < nTiles; ++t) {
+            const int st = (int)(t % kEStages);
+            mbarWait(&sBar[warp][st], (parity >> st) & 1u);
+            parity ^= 1u << st;
 #pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-                pk[k] = 0.0f;
-                if (k < K) {
-                    const float4 la = myLobes[2 * k], lb = myLobes[2 * k + 1];
-                    pk[k] = guideLobeTerm(la, lb, f3(d.x, d.y, d.z));
-                    total += pk[k];
+            for (int r = 0; r < kETile / 32; ++r) {
+                const uint32_t local = r * 32 + ln;
+                if (t * kETile + local >= nGood) break;
+                const float4 p = sTile[warp][st][0][local], d = sTile[warp][st][1][local];
+                const float sw = p.w;
+                float pk[KMAX];
+                float total = 0.0f;
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) {
+                    pk[k] = 0.0f;
+                    if (k < K) {
+                        const float4 la = myLobes[2 * k], lb = myLobes[2 * k + 1];
+                        pk[k] = guideLobeTerm(la, lb, f3(d.x, d.y, d.z));
+                        total += pk[k];
+                    }
+                }
+                if (!(total > 0) || !isfinite(total)) continue;
+                cW += sw;
+                const float inv = 1.0f / total;
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) {
+                    if (k < K) {
+                        const float g = sw * (pk[k] * inv);
+                        S[k] += g;
+                        Rx[k] += g * d.x;
+                        Ry[k] += g * d.y;
+                        Rz[k] += g * d.z;
+                    }
                 }
             }
-            if (!(total > 0) || !isfinite(total)) continue;
-            cW += sw;
-            const float inv = 1.0f / total;
-#pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-                if (k < K) {
-                    const float g = sw * (pk[k] * inv);
-                    S[k] += g;
-                    Rx[k] += g * d.x;
-                    Ry[k] += g * d.y;
-                    Rz[k] += g * d.z;
-                }
-            }
+            __syncwarp();  // every lane has read the stage: it can be refilled
+            if (ln == 0 && t + kEStages < nTiles) issue(t + kEStages);
         }
         // butterfly reduction over the 32 lanes (fixed order -> deterministic); lane 0 holds the sums
         float *out = partials + (size_t)w * stride;
