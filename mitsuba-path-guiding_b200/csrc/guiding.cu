@@ -5,8 +5,8 @@
 //   k_estep            weighted-EM E-step, one warp per chunk of one cell's samples: samples streamed through shared memory
 //                      by bulk async copies (cp.async.bulk + mbarrier ring), lobes in shared memory, lane = sample,
 //                      per-lane sufficient statistics in registers, butterfly reduction per chunk
-//   k_gather_partition gather into sorted order + per-chunk partition (usable weights first)
-//   k_cell_moments     per-chunk position moments (split statistics), once per training update
+//   k_gather_partition gather into sorted order + per-chunk partition (usable weights first) + per-chunk position
+//                      moments (split statistics), once per training update
 //   k_reduce_partials  per-cell sum of the chunk partials in a fixed order (deterministic)
 //   k_mstep            M-step with decayed running statistics and MAP priors, one warp per cell
 //   k_guide_query      pdf / sample of the field at arbitrary points (b200pg_k_vmm_pdf_sample)
@@ -466,21 +466,46 @@ __global__ void __launch_bounds__(128) k_estep(GuideDevice G, const float4 *__re
     }
 }
 
-// Per-chunk position moments (count, sum x, sum x^2) -- independent of the mixtures, so computed once per training
-// update, not once per EM iteration. Written into the cell-statistics slots of the partials buffer that k_estep
-// leaves alone (slot 1, the weight sum, is k_estep's).
-__global__ void __launch_bounds__(128) k_cell_moments(const float4 *__restrict__ sPos, const uint4 *__restrict__ work,
-                                                      const uint32_t *__restrict__ counts, float *__restrict__ partials, int stride, int K) {
+
+// Gather into sorted order, one warp per work chunk, with a stable partition inside the chunk: samples whose weight
+// is positive and finite go to the front (count -> work[w].w), the others to the back in reverse order. Zero-weight
+// samples (paths that found no light) only matter for the cell's sample count and position moments, so the E-step
+// iterates over the dense front part with all lanes busy.
+__global__ void __launch_bounds__(128) k_gather_partition(const float4 *__restrict__ sPos, const float4 *__restrict__ sDir,
+                                                          const uint32_t *__restrict__ perm, uint4 *__restrict__ work,
+                                                          const uint32_t *__restrict__ counts, float4 *__restrict__ oPos,
+                                                          float4 *__restrict__ oDir, float *__restrict__ partials, int stride, int K) {
     const uint32_t warp = threadIdx.x >> 5, ln = lane();
     const uint32_t nWork = counts[2];
     for (uint32_t w = blockIdx.x * 4 + warp; w < nWork; w += gridDim.x * 4) {
         const uint4 item = work[w];
-        float m[6] = {0, 0, 0, 0, 0, 0};
-        for (uint32_t j = item.y + ln; j < item.z; j += 32) {
-            const float4 p = sPos[j];
-            m[0] += p.x; m[1] += p.y; m[2] += p.z;
-            m[3] += p.x * p.x; m[4] += p.y * p.y; m[5] += p.z * p.z;
+        uint32_t nGood = 0, nBad = 0;
+        float m[6] = {0, 0, 0, 0, 0, 0};  // position moments of the chunk (split rule), all samples
+        for (uint32_t j0 = item.y; j0 < item.z; j0 += 32) {
+            const uint32_t j = j0 + ln;
+            const bool valid = j < item.z;
+            float4 p = make_float4(0, 0, 0, 0), d = p;
+            if (valid) {
+                const uint32_t i = perm[j];
+                p = sPos[i];
+                d = sDir[i];
+                m[0] += p.x; m[1] += p.y; m[2] += p.z;
+                m[3] += p.x * p.x; m[4] += p.y * p.y; m[5] += p.z * p.z;
+            }
+            const bool good = valid && p.w > 0 && isfinite(p.w);
+            const unsigned gm = __ballot_sync(0xffffffffu, good), bm = __ballot_sync(0xffffffffu, valid && !good);
+            const unsigned lt = (1u << ln) - 1u;
+            if (valid) {
+                const uint32_t dst = good ? item.y + nGood + __popc(gm & lt) : item.z - 1 - (nBad + __popc(bm & lt));
+                oPos[dst] = p;
+                oDir[dst] = d;
+            }
+            nGood += __popc(gm);
+            nBad += __popc(bm);
         }
+        if (ln == 0) work[w].w = nGood;
+        // moments: per-lane float partial sums (<= 64 samples each), combined across the lanes in double; written into the
+        // cell-statistics slots of the partials buffer that k_estep leaves alone (slot 1, the weight sum, is k_estep's)
         double acc[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
@@ -497,43 +522,6 @@ __global__ void __launch_bounds__(128) k_cell_moments(const float4 *__restrict__
     }
 }
 
-// Gather into sorted order, one warp per work chunk, with a stable partition inside the chunk: samples whose weight
-// is positive and finite go to the front (count -> work[w].w), the others to the back in reverse order. Zero-weight
-// samples (paths that found no light) only matter for the cell's sample count and position moments, so the E-step
-// iterates over the dense front part with all lanes busy.
-__global__ void __launch_bounds__(128) k_gather_partition(const float4 *__restrict__ sPos, const float4 *__restrict__ sDir,
-                                                          const uint32_t *__restrict__ perm, uint4 *__restrict__ work,
-                                                          const uint32_t *__restrict__ counts, float4 *__restrict__ oPos,
-                                                          float4 *__restrict__ oDir) {
-    const uint32_t warp = threadIdx.x >> 5, ln = lane();
-    const uint32_t nWork = counts[2];
-    for (uint32_t w = blockIdx.x * 4 + warp; w < nWork; w += gridDim.x * 4) {
-        const uint4 item = work[w];
-        uint32_t nGood = 0, nBad = 0;
-        for (uint32_t j0 = item.y; j0 < item.z; j0 += 32) {
-            const uint32_t j = j0 + ln;
-            const bool valid = j < item.z;
-            float4 p = make_float4(0, 0, 0, 0), d = p;
-            if (valid) {
-                const uint32_t i = perm[j];
-                p = sPos[i];
-                d = sDir[i];
-            }
-            const bool good = valid && p.w > 0 && isfinite(p.w);
-            const unsigned gm = __ballot_sync(0xffffffffu, good), bm = __ballot_sync(0xffffffffu, valid && !good);
-            const unsigned lt = (1u << ln) - 1u;
-            if (valid) {
-                const uint32_t dst = good ? item.y + nGood + __popc(gm & lt) : item.z - 1 - (nBad + __popc(bm & lt));
-                oPos[dst] = p;
-                oDir[dst] = d;
-            }
-            nGood += __popc(gm);
-            nBad += __popc(bm);
-        }
-        if (ln == 0) work[w].w = nGood;
-    }
-}
-
 // work items of one cell are consecutive: workOfs[cell] .. workOfs[cell + 1]
 __global__ void __launch_bounds__(256) k_reduce_partials(const float *__restrict__ partials, const uint32_t *__restrict__ workOfs,
                                                          uint32_t nCells, int stride, float *__restrict__ stats) {
@@ -547,11 +535,24 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const float *__restrict
 }
 
 // ---- M-step: one warp per cell, lane k = lobe k ----------------------------------------------------------
-__global__ void __launch_bounds__(256) k_mstep(float4 *__restrict__ lobes, float4 *__restrict__ lobeStats, const float *__restrict__ stats,
-                                               uint32_t nCells, int K, int stride, int commit) {
+// With `partials` != nullptr the per-cell sum of the chunk partials (k_reduce_partials' job: fixed order, double
+// accumulation) is done here by the cell's warp first -- one launch and one round trip of the statistics less per EM
+// iteration on the single-GPU path.
+__global__ void __launch_bounds__(256) k_mstep(float4 *__restrict__ lobes, float4 *__restrict__ lobeStats, float *__restrict__ stats,
+                                               uint32_t nCells, int K, int stride, int commit, const float *__restrict__ partials,
+                                               const uint32_t *__restrict__ workOfs) {
     const uint32_t warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = (gridDim.x * blockDim.x) >> 5;
     const int k = (int)lane();
     for (uint32_t c = warpGlobal; c < nCells; c += nWarps) {
+        if (partials) {
+            const uint32_t w0 = workOfs[c], w1 = workOfs[c + 1];
+            for (int e = k; e < stride; e += 32) {
+                double acc = 0.0;
+                for (uint32_t w = w0; w < w1; ++w) acc += (double)partials[(size_t)w * stride + e];
+                stats[(size_t)c * stride + e] = (float)acc;
+            }
+            __syncwarp();
+        }
         const float *st = stats + (size_t)c * stride;
         float4 a = make_float4(0, 0, 0, 0), b = a, s = a;
         float S = 0, R0 = 0, R1 = 0, R2 = 0;
@@ -945,9 +946,9 @@ void GuidingHost::buildWork() {
     int smCount = 148;
     cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, 0);
     const uint32_t grid = std::max(1u, std::min<uint32_t>((workBound + 3) / 4, (uint32_t)smCount * 16));
-    k_gather_partition<<<grid, 128, 0, stream>>>(dSPos.p, dSDir.p, sortedPerm, dWork.p, dCounts.p, dSortPos.p, dSortDir.p);
-    k_cell_moments<<<grid, 128, 0, stream>>>(dSortPos.p, dWork.p, dCounts.p, dPartials.p, (int)statsStride(), K);
-    launches += 2;
+    k_gather_partition<<<grid, 128, 0, stream>>>(dSPos.p, dSDir.p, sortedPerm, dWork.p, dCounts.p, dSortPos.p, dSortDir.p, dPartials.p,
+                                                 (int)statsStride(), K);
+    launches++;
 }
 
 void GuidingHost::begin() {
@@ -990,6 +991,13 @@ void GuidingHost::beginExternal(const float *pos, const float *dir, const float 
 void GuidingHost::accumulate() { accumulateInto(dStats.p); }
 
 void GuidingHost::accumulateInto(float *statsOut) {
+    estepOnly();
+    const int stride = (int)statsStride();
+    k_reduce_partials<<<gridFor((size_t)numCells() * stride, 256), 256, 0, stream>>>(dPartials.p, dWorkOfs.p, numCells(), stride, statsOut);
+    launches++;
+}
+
+void GuidingHost::estepOnly() {
     GuideDevice G;
     std::memset(&G, 0, sizeof(G));
     G.lobes = dLobes.p;
@@ -1004,13 +1012,13 @@ void GuidingHost::accumulateInto(float *statsOut) {
         k_estep<16><<<grid, 128, 0, stream>>>(G, dSortPos.p, dSortDir.p, dWork.p, dCounts.p, dPartials.p, stride);
     else
         k_estep<32><<<grid, 128, 0, stream>>>(G, dSortPos.p, dSortDir.p, dWork.p, dCounts.p, dPartials.p, stride);
-    k_reduce_partials<<<gridFor((size_t)numCells() * stride, 256), 256, 0, stream>>>(dPartials.p, dWorkOfs.p, numCells(), stride, statsOut);
-    launches += 2;
+    launches++;
 }
 
 void GuidingHost::update(bool commit) {
     const int stride = (int)statsStride();
-    k_mstep<<<gridFor((size_t)numCells() * 32, 256), 256, 0, stream>>>(dLobes.p, dLobeStats.p, dStats.p, numCells(), K, stride, commit ? 1 : 0);
+    k_mstep<<<gridFor((size_t)numCells() * 32, 256), 256, 0, stream>>>(dLobes.p, dLobeStats.p, dStats.p, numCells(), K, stride, commit ? 1 : 0,
+                                                                       nullptr, nullptr);
     launches++;
 }
 
@@ -1060,9 +1068,11 @@ void GuidingHost::train(int nIter) {
             const int grid = (int)std::max<size_t>(1, std::min<size_t>(((size_t)numCells() * 32 + 255) / 256, (size_t)sms));
             k_mstep_allreduce<<<grid, 256, 0, stream>>>(cv, dLobes.p, dLobeStats.p, dStats.p, numCells(), K, stride, commit ? 1 : 0);
             launches++;
-        } else {
-            accumulate();
-            update(commit);
+        } else {  // single GPU: the per-cell sum of the partials is folded into the M-step kernel
+            estepOnly();
+            k_mstep<<<gridFor((size_t)numCells() * 32, 256), 256, 0, stream>>>(dLobes.p, dLobeStats.p, dStats.p, numCells(), K, stride,
+                                                                               commit ? 1 : 0, dPartials.p, dWorkOfs.p);
+            launches++;
         }
     }
     if (commWorld > 1) {

@@ -95,6 +95,7 @@ struct GuidingHost {
     void beginExternal(const float *pos, const float *dir, const float *weight, const float *pdf, const float *dist, size_t n);
     void accumulate();
     void accumulateInto(float *statsOut);
+    void estepOnly();
     void update(bool commit);
     void end();
     void trainLocal();  // begin + emIterations x (accumulate, update) + end
