@@ -284,3 +284,42 @@ def test_training_update_without_samples(api, pkg):
     d = random_dirs(rng, 20000)
     q = it.k_vmm_pdf_sample(np.zeros((20000, 3), np.float32) + [0, 1, 0], d, rng.rand(20000, 3).astype(np.float32))
     assert np.isfinite(q["pdf"]).all() and abs(q["pdf"].mean() * 4 * np.pi - 1) < 0.03
+
+
+def test_render_time_budget_cancel_and_discarded_training_film(api, pkg):
+    """ProgressiveMonteCarloIntegrator::renderTime (progressiveintegrator.cpp:117-168): progressions until `maxRenderTime`
+    seconds have passed; Integrator::cancel() from another thread ends a render early (integrator.h:86);
+    discardTrainingSamples: the film only holds the progressions after training."""
+    import threading
+    import time
+
+    sb = pkg.scenes.cornell_caustic(128, 128, spp=4)
+    sc = api.Scene.from_builder(sb)
+    p = api.default_params()
+    p.max_depth, p.guiding, p.training_progressions, p.guide_max_cell_samples = 6, 1, 2, 4000
+    p.max_render_time = 1  # seconds
+    it = api.Integrator(sc, p)
+    t0 = time.perf_counter()
+    it.render()
+    el = time.perf_counter() - t0
+    st = it.stats()
+    assert 0.9 <= el < 3.0 and st["progressions_done"] > 4 and st["paths"] == st["progressions_done"] * 128 * 128
+    # cancel from another thread
+    p2 = api.default_params()
+    p2.max_depth, p2.max_render_time = 6, 30
+    it2 = api.Integrator(sc, p2)
+    timer = threading.Timer(0.3, it2.cancel)
+    timer.start()
+    t0 = time.perf_counter()
+    it2.render()
+    assert time.perf_counter() - t0 < 5.0
+    timer.join()
+    # discarded training film: 6 progressions of 1 spp, the first 3 train and are thrown away
+    sb3 = pkg.scenes.cornell_caustic(64, 64, spp=6)
+    p3 = api.default_params()
+    p3.max_depth, p3.guiding, p3.training_progressions, p3.guide_max_cell_samples, p3.guide_train_discard_film = 6, 1, 3, 4000, 1
+    it3 = api.Integrator(api.Scene.from_builder(sb3), p3)
+    it3.render()
+    f = it3.film()
+    assert it3.stats()["paths"] == 64 * 64 * 6
+    assert abs(f[..., 4].sum() / (64 * 64 * 3) - 1.0) < 0.03  # filter weight of 3 spp, not 6
