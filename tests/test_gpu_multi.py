@@ -71,7 +71,12 @@ def test_two_gpu_fused_statistics_sum(tmp_path, pkg):
     nn = int(one[1])
     assert nn >= 3  # the first update split the root cell
     two_first = _first_update_two_rank(tmp_path)
-    assert np.array_equal(one[:8 + 4 * nn], two_first[:8 + 4 * nn])  # same tree
+    # same tree: identical topology; the split planes are means of float position sums that the two ranks accumulate in a
+    # different order than one GPU does (1e-6 relative)
+    assert np.array_equal(one[:8], two_first[:8])
+    na, nb = one[8:8 + 4 * nn].reshape(nn, 4), two_first[8:8 + 4 * nn].reshape(nn, 4)
+    assert np.array_equal(na[:, [0, 2, 3]], nb[:, [0, 2, 3]])
+    np.testing.assert_allclose(nb[:, 1].view(np.float32), na[:, 1].view(np.float32), rtol=2e-6, atol=1e-6)
     o = 8 + 4 * nn + 8 * int(one[2])
     la, lb = one.view(np.float32)[o:].reshape(-1, 12), two_first.view(np.float32)[o:].reshape(-1, 12)
     assert np.abs(la[:, 0] - lb[:, 0]).max() <= 1e-5
