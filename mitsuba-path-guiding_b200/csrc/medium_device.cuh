@@ -3,6 +3,9 @@
 //   mediumSampleDistance / mediumTransmittance
 //                      HeterogeneousMedium::sampleDistance / evalTransmittance, Woodcock branch
 //                      (src/medium/heterogeneous.cpp:589-663, 546-587; sigma_max = scale * 1, gridvolume.cpp:583-585)
+//   mediumIntegrateDensity / mediumInvertDensityIntegral
+//                      method = simpson: composite Simpson quadrature and its Newton-bisection inversion
+//                      (heterogeneous.cpp:301-376, 420-544; HETVOL_EARLY_EXIT on, :31)
 //   phaseEval / phaseSample   src/phase/hg.cpp:74-110, src/phase/isotropic.cpp:62-78
 #pragma once
 #include "device_scene.cuh"
@@ -49,14 +52,119 @@ PG_DEV bool mediumClip(const MediumRecord &M, float3 o, float3 d, float &nearT, 
     return true;
 }
 
+// heterogeneous.cpp:301-376
+PG_DEV float mediumIntegrateDensity(const MediumRecord &M, const float *density, float3 o, float3 d, float rmint, float rmaxt) {
+    float mint, maxt;
+    if (!mediumClip(M, o, d, mint, maxt)) return 0.0f;
+    mint = fmaxf(mint, rmint);
+    maxt = fminf(maxt, rmaxt);
+    const float length = maxt - mint;
+    float3 p = o + d * mint;
+    const float3 pLast = o + d * maxt;
+    const float maxComp = fmaxf(fmaxf(fmaxf(fabsf(p.x), fabsf(pLast.x)), fmaxf(fabsf(p.y), fabsf(pLast.y))), fmaxf(fabsf(p.z), fabsf(pLast.z)));
+    if (length < 1e-6f * maxComp) return 0.0f;
+    uint32_t nSteps = (uint32_t)ceilf(length / M.stepSize);
+    nSteps += nSteps % 2;
+    const float step = length / nSteps;
+    const float3 increment = d * step;
+    float integrated = gridLookup(M, density, p) + gridLookup(M, density, pLast);
+    const float stopValue = -logf(kEpsilon) * 3.0f / (step * M.scale);
+    p = p + increment;
+    float m = 4;
+    for (uint32_t i = 1; i < nSteps; ++i) {
+        integrated += m * gridLookup(M, density, p);
+        m = 6 - m;
+        if (integrated > stopValue) return kInf;
+        const float3 next = p + increment;
+        if (p.x == next.x && p.y == next.y && p.z == next.z) break;
+        p = next;
+    }
+    return integrated * M.scale * step * (1.0f / 3.0f);
+}
+
+// heterogeneous.cpp:420-544
+PG_DEV bool mediumInvertDensityIntegral(const MediumRecord &M, const float *density, float3 o, float3 d, float rmint, float rmaxt,
+                                        float desiredDensity, float &integratedDensity, float &t, float &densityAtT) {
+    integratedDensity = densityAtT = 0.0f;
+    float mint, maxt;
+    if (!mediumClip(M, o, d, mint, maxt)) return false;
+    mint = fmaxf(mint, rmint);
+    maxt = fminf(maxt, rmaxt);
+    const float length = maxt - mint;
+    float3 p = o + d * mint;
+    const float3 pLast = o + d * maxt;
+    const float maxComp = fmaxf(fmaxf(fmaxf(fabsf(p.x), fabsf(pLast.x)), fmaxf(fabsf(p.y), fabsf(pLast.y))), fmaxf(fabsf(p.z), fabsf(pLast.z)));
+    if (length < 1e-6f * maxComp) return false;
+    const uint32_t nSteps = (uint32_t)ceilf(length / (2 * M.stepSize));
+    const float step = length / nSteps, multiplier = (1.0f / 6.0f) * step * M.scale;
+    const float3 fullStep = d * step, halfStep = fullStep * 0.5f;
+    float node1 = gridLookup(M, density, p);
+    for (uint32_t i = 0; i < nSteps; ++i) {
+        const float node2 = gridLookup(M, density, p + halfStep), node3 = gridLookup(M, density, p + fullStep);
+        const float newDensity = integratedDensity + multiplier * (node1 + node2 * 4 + node3);
+        if (newDensity >= desiredDensity) {
+            float a = 0, b = step, x = a, fx = integratedDensity - desiredDensity;
+            const float stepSqr = step * step, temp = M.scale / stepSqr;
+            int it = 1;
+            while (true) {
+                const float dfx = temp * (node1 * stepSqr - (3 * node1 - 4 * node2 + node3) * step * x + 2 * (node1 - 2 * node2 + node3) * x * x);
+                x -= fx / dfx;
+                if (x <= a || x >= b || dfx == 0) x = 0.5f * (b + a);
+                const float intval = integratedDensity + temp * (1.0f / 6.0f) *
+                                     (x * (6 * node1 * stepSqr - 3 * (3 * node1 - 4 * node2 + node3) * step * x +
+                                           4 * (node1 - 2 * node2 + node3) * x * x));
+                fx = intval - desiredDensity;
+                if (fabsf(fx) < 1e-6f) {
+                    t = mint + step * i + x;
+                    integratedDensity = intval;
+                    densityAtT = temp * (node1 * stepSqr - (3 * node1 - 4 * node2 + node3) * step * x +
+                                         2 * (node1 - 2 * node2 + node3) * x * x);
+                    return true;
+                } else if (++it > 30) {
+                    return false;
+                }
+                if (fx > 0) b = x; else a = x;
+            }
+        }
+        const float3 next = p + fullStep;
+        if (p.x == next.x && p.y == next.y && p.z == next.z) break;
+        integratedDensity = newDensity;
+        node1 = node3;
+        p = next;
+    }
+    return false;
+}
+
 struct MediumSample {
     float t;
     float3 p, sigmaS;
     float transmittance;
+    float pdfSuccess, pdfFailure;  // 1 for Woodcock tracking (heterogeneous.cpp:616-618)
 };
+
+// method = simpson branch of sampleDistance (heterogeneous.cpp:594-611)
+PG_DEV bool mediumSampleDistanceSimpson(const MediumRecord &M, const float *density, float3 o, float3 d, float rmint, float rmaxt,
+                                        MediumSample &mRec, Rng &rng) {
+    float integratedDensity, densityAtT;
+    bool success = false;
+    const float desiredDensity = -logf(1 - rng.next1D());
+    if (mediumInvertDensityIntegral(M, density, o, d, rmint, rmaxt, desiredDensity, integratedDensity, mRec.t, densityAtT)) {
+        mRec.p = o + d * mRec.t;
+        success = true;
+        mRec.sigmaS = ld3(M.albedo) * densityAtT;
+    }
+    const float expVal = expf(-integratedDensity);
+    mRec.pdfFailure = expVal;
+    mRec.pdfSuccess = expVal * densityAtT;
+    mRec.transmittance = expVal;
+    return success && mRec.pdfSuccess > 0;
+}
 
 PG_DEV bool mediumSampleDistance(const MediumRecord &M, const float *density, float3 o, float3 d, float rmint, float rmaxt,
                                  MediumSample &mRec, Rng &rng) {
+    if (M.method == B200PG_MEDIUM_SIMPSON) return mediumSampleDistanceSimpson(M, density, o, d, rmint, rmaxt, mRec, rng);
+    mRec.pdfSuccess = mRec.pdfFailure = 1.0f;
+    mRec.transmittance = 1.0f;
     float mint, maxt;
     if (!mediumClip(M, o, d, mint, maxt)) return false;
     mint = fmaxf(mint, rmint);
@@ -116,6 +224,7 @@ PG_DEV bool mediumSampleDistanceGuided(const MediumRecord &M, const float *densi
 }
 
 PG_DEV float mediumTransmittance(const MediumRecord &M, const float *density, float3 o, float3 d, float rmint, float rmaxt, Rng &rng) {
+    if (M.method == B200PG_MEDIUM_SIMPSON) return expf(-mediumIntegrateDensity(M, density, o, d, rmint, rmaxt));  // (:547-548)
     float mint, maxt;
     if (!mediumClip(M, o, d, mint, maxt)) return 1.0f;
     mint = fmaxf(mint, rmint);

@@ -110,8 +110,14 @@ PG_DEV void runWithRefill(Job &job, uint32_t n, uint32_t *work) {
 struct TrialTracker {
     float t, mint, maxt, result;
     int trial;
-    // false: the segment misses the density box (transmittance 1, no random numbers consumed)
-    PG_DEV bool begin(const MediumRecord &M, float3 o, float3 d, float rmint, float rmaxt) {
+    // false: no walk needed -- the segment misses the density box (transmittance 1, no random numbers consumed), or the
+    // medium integrates deterministically (method = simpson: the whole quadrature runs here, value() holds the result)
+    PG_DEV bool begin(const MediumRecord &M, const float *density, float3 o, float3 d, float rmint, float rmaxt) {
+        result = 2.0f;  // value() == 1
+        if (M.method == B200PG_MEDIUM_SIMPSON) {
+            result = 2.0f * expf(-mediumIntegrateDensity(M, density, o, d, rmint, rmaxt));
+            return false;
+        }
         float a, b;
         if (!mediumClip(M, o, d, a, b)) return false;
         mint = fmaxf(a, rmint);
@@ -165,7 +171,11 @@ struct LookJob {
     PG_DEV LookJob(const ShadeArgs &a) : A(a) {}
 
     PG_DEV void beginSegment() {
-        tracking = medium >= 0 && trk.begin(A.S.media[medium], o, d, 0.0f, cur.t);
+        tracking = false;
+        if (medium >= 0) {
+            tracking = trk.begin(A.S.media[medium], A.S.density, o, d, 0.0f, cur.t);
+            if (!tracking) transmittance *= trk.value();
+        }
     }
     PG_DEV bool fetch(uint32_t i) {
         idx = i;
@@ -312,6 +322,18 @@ struct TrackJob {
         o = f3(ro.x, ro.y, ro.z);
         d = f3(rd.x, rd.y, rd.z);
         const MediumRecord &M = A.S.media[medium];
+        if (M.method == B200PG_MEDIUM_SIMPSON) {  // deterministic quadrature: one unit of work, done right here
+            MediumSample mRec;
+            const bool ev = mediumSampleDistanceSimpson(M, A.S.density, o, d, 0.0f, __float_as_uint(h4.w) != kMiss ? h4.x : kInf, mRec, rng);
+            // the throughput factor is applied here (k_shade_vol skips it for this method, bit 2):
+            // event: sigma_s * transmittance / pdfSuccess, no event: transmittance / pdfFailure  (:125-126, :231-232)
+            if (ev)
+                thr = thr * ((mRec.sigmaS * mRec.transmittance) / mRec.pdfSuccess);
+            else
+                thr = thr * (mRec.transmittance / mRec.pdfFailure);
+            write(ev ? mRec.t : kInf, 2u);
+            return false;
+        }
         float a, b;
         if (!mediumClip(M, o, d, a, b)) {
             write(kInf, 0u);
@@ -319,7 +341,7 @@ struct TrackJob {
         }
         t = fmaxf(a, 0.0f);
         maxt = fminf(b, __float_as_uint(h4.w) != kMiss ? h4.x : kInf);
-        guidedDist = A.G.enabled && A.cfg.guidedDistance;
+        guidedDist = A.G.enabled && A.cfg.guidedDistance;  // (Woodcock only)
         albedo = ld3(M.albedo);
         albedoAvg = (albedo.x + albedo.y + albedo.z) * (1.0f / 3.0f);
         event = false;
@@ -450,7 +472,8 @@ __global__ void __launch_bounds__(kShadeThreads, 6) k_shade_vol(ShadeArgs A) {
                 if (!terminate) {
                     MediumSample mRec;
                     const bool mediumEvent = tA.x < kInf;
-                    const bool guidedDist = A.G.enabled && cfg.guidedDistance && medium >= 0;
+                    const bool thrDone = (__float_as_uint(tA.w) & 2u) != 0;  // simpson: k_track_vol applied the medium factor
+                    const bool guidedDist = (A.G.enabled && cfg.guidedDistance && medium >= 0) || thrDone;
                     if (mediumEvent) {
                         mRec.t = tA.x;
                         mRec.p = o + d * tA.x;
@@ -707,7 +730,11 @@ struct ShadowJob {
                 return true;
             }
         }
-        tracking = medium >= 0 && trk.begin(S.media[medium], o, d, 0.0f, fminf(segT, remaining));
+        tracking = false;
+        if (medium >= 0) {
+            tracking = trk.begin(S.media[medium], S.density, o, d, 0.0f, fminf(segT, remaining));
+            if (!tracking) transmittance *= trk.value();
+        }
         return false;
     }
     PG_DEV bool fetch(uint32_t i) {

@@ -4,7 +4,9 @@
 //   src/medium/heterogeneous.cpp:228-262 (configure), :546-587 (evalTransmittance), :589-663 (sampleDistance, Woodcock),
 //   src/volume/gridvolume.cpp:188-198 (worldToGrid, step size), :337-388 (trilinear lookupFloat),
 //   src/phase/hg.cpp:74-110, src/phase/isotropic.cpp:62-78.
-// Only the default method (Woodcock / delta tracking, heterogeneous.cpp:195-197) is restated.
+// Both integration methods are restated: Woodcock / delta tracking (the default, heterogeneous.cpp:195-197) and composite
+// Simpson quadrature with Newton-bisection inversion (:301-376 integrateDensity, :420-544 invertDensityIntegral; the
+// HETVOL_EARLY_EXIT shortcut of :336-355 is on by default, :31, and is restated too).
 #pragma once
 #include <vector>
 
@@ -23,7 +25,7 @@ struct MediumSample {  // MediumSamplingRecord fields used on this path
 struct Medium {
     B200pgMedium d;
     std::vector<Float> density;
-    Float maxDensity, invMaxDensity;
+    Float maxDensity, invMaxDensity, stepSize;
     Float gridScale[3], gridOffset[3];  // worldToGrid = scale((res-1)/extent) * translate(-min)
     Vec3 bmin, bmax;
 
@@ -39,6 +41,12 @@ struct Medium {
             Float ext = m.aabb_max[c] - m.aabb_min[c];
             r.gridScale[c] = (m.res[c] - 1) / ext;
             r.gridOffset[c] = r.gridScale[c] * -m.aabb_min[c];
+        }
+        // heterogeneous.cpp:244-256: stepSize property, else the density volume's (gridvolume.cpp:196-198; constvolume: inf)
+        r.stepSize = m.step_size_multiplier;
+        if (r.stepSize == 0) {
+            r.stepSize = std::numeric_limits<Float>::infinity();
+            for (int c = 0; c < 3; ++c) r.stepSize = std::min(r.stepSize, 0.5f * (m.aabb_max[c] - m.aabb_min[c]) / (Float)(m.res[c] - 1));
         }
         r.bmin = Vec3(m.aabb_min[0], m.aabb_min[1], m.aabb_min[2]);
         r.bmax = Vec3(m.aabb_max[0], m.aabb_max[1], m.aabb_max[2]);
@@ -82,8 +90,105 @@ struct Medium {
         return true;
     }
 
-    // heterogeneous.cpp:589-663, Woodcock branch. Ray interval [rmint, rmaxt].
+    // heterogeneous.cpp:301-376: composite Simpson quadrature of the density along [rmint, rmaxt]
+    Float integrateDensity(const Vec3 &o, const Vec3 &dir, Float rmint, Float rmaxt) const {
+        Float mint, maxt;
+        if (!clip(o, dir, mint, maxt)) return 0.0f;
+        mint = std::max(mint, rmint);
+        maxt = std::min(maxt, rmaxt);
+        Float length = maxt - mint, maxComp = 0;
+        Vec3 p = o + dir * mint, pLast = o + dir * maxt;
+        for (int i = 0; i < 3; ++i) maxComp = std::max(std::max(maxComp, std::abs(p[i])), std::abs(pLast[i]));
+        if (length < 1e-6f * maxComp) return 0.0f;
+        uint32_t nSteps = (uint32_t)std::ceil(length / stepSize);
+        nSteps += nSteps % 2;
+        const Float step = length / nSteps;
+        const Vec3 increment = dir * step;
+        Float integrated = lookup(p) + lookup(pLast);
+        const Float stopAfterDensity = -std::log(Epsilon);
+        const Float stopValue = stopAfterDensity * 3.0f / (step * d.scale);
+        p += increment;
+        Float m = 4;
+        for (uint32_t i = 1; i < nSteps; ++i) {
+            integrated += m * lookup(p);
+            m = 6 - m;
+            if (integrated > stopValue) return std::numeric_limits<Float>::infinity();  // HETVOL_EARLY_EXIT
+            Vec3 next = p + increment;
+            if (p.x == next.x && p.y == next.y && p.z == next.z) break;
+            p = next;
+        }
+        return integrated * d.scale * step * (1.0f / 3.0f);
+    }
+
+    // heterogeneous.cpp:420-544: solve int_{mint}^t density = desiredDensity (Simpson segments + Newton-bisection)
+    bool invertDensityIntegral(const Vec3 &o, const Vec3 &dir, Float rmint, Float rmaxt, Float desiredDensity, Float &integratedDensity,
+                               Float &t, Float &densityAtMinT, Float &densityAtT) const {
+        integratedDensity = densityAtMinT = densityAtT = 0.0f;
+        Float mint, maxt;
+        if (!clip(o, dir, mint, maxt)) return false;
+        mint = std::max(mint, rmint);
+        maxt = std::min(maxt, rmaxt);
+        Float length = maxt - mint, maxComp = 0;
+        Vec3 p = o + dir * mint, pLast = o + dir * maxt;
+        for (int i = 0; i < 3; ++i) maxComp = std::max(std::max(maxComp, std::abs(p[i])), std::abs(pLast[i]));
+        if (length < 1e-6f * maxComp) return false;
+        uint32_t nSteps = (uint32_t)std::ceil(length / (2 * stepSize));
+        Float step = length / nSteps, multiplier = (1.0f / 6.0f) * step * d.scale;
+        Vec3 fullStep = dir * step, halfStep = fullStep * 0.5f;
+        Float node1 = lookup(p);
+        densityAtMinT = rmint == mint ? node1 * d.scale : 0.0f;
+        for (uint32_t i = 0; i < nSteps; ++i) {
+            Float node2 = lookup(p + halfStep), node3 = lookup(p + fullStep);
+            Float newDensity = integratedDensity + multiplier * (node1 + node2 * 4 + node3);
+            if (newDensity >= desiredDensity) {
+                Float a = 0, b = step, x = a, fx = integratedDensity - desiredDensity, stepSqr = step * step, temp = d.scale / stepSqr;
+                int it = 1;
+                while (true) {
+                    Float dfx = temp * (node1 * stepSqr - (3 * node1 - 4 * node2 + node3) * step * x + 2 * (node1 - 2 * node2 + node3) * x * x);
+                    x -= fx / dfx;
+                    if (x <= a || x >= b || dfx == 0) x = 0.5f * (b + a);
+                    Float intval = integratedDensity + temp * (1.0f / 6.0f) *
+                                   (x * (6 * node1 * stepSqr - 3 * (3 * node1 - 4 * node2 + node3) * step * x +
+                                         4 * (node1 - 2 * node2 + node3) * x * x));
+                    fx = intval - desiredDensity;
+                    if (std::abs(fx) < 1e-6f) {
+                        t = mint + step * i + x;
+                        integratedDensity = intval;
+                        densityAtT = temp * (node1 * stepSqr - (3 * node1 - 4 * node2 + node3) * step * x +
+                                             2 * (node1 - 2 * node2 + node3) * x * x);
+                        return true;
+                    } else if (++it > 30) {
+                        return false;
+                    }
+                    if (fx > 0) b = x; else a = x;
+                }
+            }
+            Vec3 next = p + fullStep;
+            if (p.x == next.x && p.y == next.y && p.z == next.z) break;
+            integratedDensity = newDensity;
+            node1 = node3;
+            p = next;
+        }
+        return false;
+    }
+
+    // heterogeneous.cpp:589-663. Ray interval [rmint, rmaxt].
     bool sampleDistance(const Vec3 &o, const Vec3 &dir, Float rmint, Float rmaxt, MediumSample &mRec, Rng &rng) const {
+        if (d.method == B200PG_MEDIUM_SIMPSON) {  // (:594-611)
+            Float integratedDensity, densityAtMinT, densityAtT;
+            bool success = false;
+            const Float desiredDensity = -std::log(1 - rng.next1D());
+            if (invertDensityIntegral(o, dir, rmint, rmaxt, desiredDensity, integratedDensity, mRec.t, densityAtMinT, densityAtT)) {
+                mRec.p = o + dir * mRec.t;
+                success = true;
+                mRec.sigmaS = Vec3(d.albedo[0], d.albedo[1], d.albedo[2]) * densityAtT;
+            }
+            const Float expVal = std::exp(-integratedDensity);
+            mRec.pdfFailure = expVal;
+            mRec.pdfSuccess = expVal * densityAtT;
+            mRec.transmittance = Vec3(expVal);
+            return success && mRec.pdfSuccess > 0;  // (:662)
+        }
         mRec.pdfFailure = 1.0f;
         mRec.pdfSuccess = 1.0f;
         mRec.transmittance = Vec3(1.0f);
@@ -155,6 +260,7 @@ struct Medium {
 
     // heterogeneous.cpp:546-587, Woodcock branch: 2 ratio-free tracking trials
     Float evalTransmittance(const Vec3 &o, const Vec3 &dir, Float rmint, Float rmaxt, Rng &rng) const {
+        if (d.method == B200PG_MEDIUM_SIMPSON) return std::exp(-integrateDensity(o, dir, rmint, rmaxt));  // (:547-548)
         Float mint, maxt;
         if (!clip(o, dir, mint, maxt)) return 1.0f;
         mint = std::max(mint, rmint);

@@ -186,3 +186,51 @@ def test_guided_volumetric_path_is_unbiased(pkg, oracle):
     c = slice(12, 28)
     assert abs(g_dist[c, c].mean() - ref[c, c].mean()) < 0.03 * ref[c, c].mean()
     assert abs(g_dir[c, c].mean() - ref[c, c].mean()) < 0.03 * ref[c, c].mean()
+
+
+def test_simpson_quadrature_and_inversion(pkg, oracle):
+    """method = simpson (heterogeneous.cpp:301-376, 420-544): composite Simpson is exact for a density that is linear along
+    the ray, so both the transmittance exp(-int) and the inverted free-flight distance have closed forms."""
+    import b200pg._abi as A
+
+    res = 33
+    z, y, x = np.meshgrid(np.linspace(0, 1, res), np.linspace(0, 1, res), np.linspace(0, 1, res), indexing="ij")
+    dens = (0.2 + 0.6 * x).astype(np.float32)  # linear in world x over [-1, 1]: d(X) = 0.5 + 0.3 X
+    sb = _medium_scene(pkg, dens, scale_=3.0)
+    sb.media[0]["method"] = A.MEDIUM_SIMPSON
+    sc = oracle.scene(sb)
+    n = 100000
+    o = np.repeat(np.array([[-0.9, 0.1, -0.2]], np.float32), n, 0)
+    d = np.repeat(np.array([[1.0, 0, 0]], np.float32), n, 0)
+    length = 1.6  # stays inside the valid cells (the last cell layer of a grid volume is empty)
+    t, tr, wo, pdf = sc.medium_sample(0, _rays(o, d, 0.0, length))
+    sigma = lambda X: 3.0 * (0.5 + 0.3 * X)
+    integral = lambda s: 3.0 * ((0.5 + 0.3 * -0.9) * s + 0.15 * s * s)  # int_0^s sigma(-0.9 + u) du
+    T = np.exp(-integral(length))
+    # transmittance is deterministic with this method
+    np.testing.assert_allclose(tr, T, rtol=2e-4)
+    scattered = np.isfinite(t)
+    assert abs(scattered.mean() - (1 - T)) < 4 * np.sqrt(T * (1 - T) / n)
+    # the sampled distances follow the cdf 1 - exp(-integral(s)), truncated at `length`
+    ks = stats.kstest(t[scattered][:50000], lambda s: (1 - np.exp(-integral(s))) / (1 - T))
+    assert ks.pvalue > 1e-3, ks
+    # the whole volumetric Li agrees between the two methods in expectation (absorbing slab, emitter behind it)
+    from b200pg import api
+
+    S = pkg.scenes
+    means = []
+    for method in (A.MEDIUM_WOODCOCK, A.MEDIUM_SIMPSON):
+        sb2 = S.SceneBuilder(16, 16, spp=1)
+        med = sb2.medium(np.full((6, 6, 6), 0.7, np.float32), (-2, -2, -0.75), (2, 2, 1.0), scale_=1.3, albedo=(0.5, 0.5, 0.5),
+                         phase="isotropic", g=0.0)
+        sb2.media[0]["method"] = method
+        sb2.cube([S.scale(1.5, 1.5, 0.5)], bsdf=-1, interior=med)
+        sb2.rectangle([S.scale(4, 4, 1), S.translate(0, 0, -2)], radiance=(1, 1, 1))
+        sb2.set_camera((0, 0, 6), (0, 0, 0), (0, 1, 0), 5.0)
+        p = api.default_params()
+        p.max_depth, p.volumetric = 6, 1
+        rng = np.random.RandomState(1)
+        m = 60000
+        L = oracle.scene(sb2).radiance(p, rng.randint(0, 256, m).astype(np.uint32), np.arange(m).astype(np.uint32))
+        means.append(L[:, 0].mean())
+    assert abs(means[0] - means[1]) < 0.02 * means[0], means
