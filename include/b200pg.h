@@ -124,6 +124,8 @@ typedef struct B200pgSensor { /* `perspective`, src/sensors/perspective.cpp */
 typedef struct B200pgFilm { /* `hdrfilm` + `gaussian` rfilter */
     int32_t width, height;
     float filter_stddev; /* gaussian stddev, radius = 4*stddev (gaussian.cpp:33-37) */
+    int32_t file_format;      /* hdrfilm `fileFormat`: 0 = openexr (default, hdrfilm.cpp:212-226), 1 = pfm, 2 = rgbe */
+    int32_t component_format; /* hdrfilm `componentFormat`: 0 = float16 (default, :219-220), 1 = float32 */
 } B200pgFilm;
 
 typedef struct B200pgSceneDesc {
@@ -245,7 +247,10 @@ int b200pg_film_clear(void *integ);
 int b200pg_film_device_buffer(void *integ, void **dev_ptr, size_t *n_floats); /* H*W*4: R,G,B,weight */
 int b200pg_film_read(void *integ, float *rgbaw /* H*W*5: R,G,B,alpha,weight (imageblock.h:131-138) */);
 int b200pg_film_develop(void *integ, float *rgb /* H*W*3 = RGB/weight, fmtconv.cpp:978-1005 */);
-int b200pg_film_write(void *integ, const char *path /* .pfm */);
+/* Film::develop to a file (hdrfilm.cpp:487-546), format chosen by the extension: .exr (scanline OpenEXR, uncompressed, channels
+ * B G R as float16 or float32 per the film's componentFormat), .pfm (float32), .rgbe / .hdr (Radiance RGBE, flat).
+ * The reference's banner (`banner=true` draws a logo into the image, :501-511) is never drawn. */
+int b200pg_film_write(void *integ, const char *path);
 int b200pg_stats(void *integ, B200pgStats *out);
 void b200pg_destroy(void *integ);
 

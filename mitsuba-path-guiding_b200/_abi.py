@@ -82,7 +82,8 @@ class Sensor(C.Structure):
 
 
 class Film(C.Structure):
-    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("filter_stddev", C.c_float)]
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("filter_stddev", C.c_float),
+                ("file_format", C.c_int32), ("component_format", C.c_int32)]
 
 
 class SceneDesc(C.Structure):

@@ -10,7 +10,8 @@
 
 static void usage() {
     std::printf("Usage: b200pg-render [options] <scene.xml>\n"
-                "   -o fname     Write the developed image to fname (.pfm). Default: <scene>.pfm\n"
+                "   -o fname     Write the developed image to fname (.exr, .pfm or .rgbe). Default: <scene> + the extension of\n"
+                "                the film's fileFormat (openexr unless the scene says otherwise, hdrfilm.cpp:212-226)\n"
                 "   -D key=val   Define a constant, which can be referenced as \"$key\" in the scene\n"
                 "   -p index     CUDA device to render on (default 0)\n"
                 "   -q           Quiet mode\n");
@@ -48,7 +49,9 @@ int main(int argc, char **argv) {
         out = scenePath;
         size_t dot = out.find_last_of('.');
         if (dot != std::string::npos) out = out.substr(0, dot);
-        out += ".pfm";
+        const B200pgSceneDesc *desc = b200pg_scene_desc(scene);
+        const int ff = desc ? desc->film.file_format : 0;
+        out += ff == 1 ? ".pfm" : (ff == 2 ? ".rgbe" : ".exr");
     }
     if (b200pg_film_write(integ, out.c_str()) != 0) { std::fprintf(stderr, "Error: %s\n", b200pg_last_error()); return 4; }
     B200pgStats st;

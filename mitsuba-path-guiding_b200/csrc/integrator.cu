@@ -604,6 +604,133 @@ int b200pg_film_develop(void *integ, float *rgb) {
     PG_END
 }
 
+// ---- image writers (Bitmap::write, src/libcore/bitmap.cpp: PFM, OpenEXR, RGBE) -----------------------------------------
+static uint16_t floatToHalf(float f) {  // round to nearest even, IEEE binary16
+    uint32_t x;
+    std::memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    x &= 0x7FFFFFFFu;
+    if (x >= 0x7F800000u) return (uint16_t)(sign | 0x7C00u | (x > 0x7F800000u ? 0x200u : 0u));  // inf / nan
+    if (x >= 0x477FF000u) return (uint16_t)(sign | 0x7C00u);                                      // overflow -> inf
+    if (x < 0x33000001u) return (uint16_t)sign;                                                    // underflow -> 0
+    int e = (int)(x >> 23) - 127 + 15;
+    uint32_t m = x & 0x7FFFFFu;
+    if (e <= 0) {  // subnormal half
+        m |= 0x800000u;
+        const int shift = 14 - e;
+        uint32_t h = m >> shift;
+        const uint32_t rem = m & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+        if (rem > halfway || (rem == halfway && (h & 1u))) h++;
+        return (uint16_t)(sign | h);
+    }
+    uint32_t h = ((uint32_t)e << 10) | (m >> 13);
+    const uint32_t rem = m & 0x1FFFu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) h++;
+    return (uint16_t)(sign | h);
+}
+
+static bool writePfm(const char *path, const float *rgb, int W, int H) {
+    FILE *f = std::fopen(path, "wb");
+    if (!f) return false;
+    std::fprintf(f, "PF\n%d %d\n-1.0\n", W, H);  // little endian, bottom-up scanlines (bitmap.cpp writePFM)
+    for (int y = H - 1; y >= 0; --y) std::fwrite(rgb + (size_t)y * W * 3, sizeof(float), (size_t)W * 3, f);
+    return std::fclose(f) == 0;
+}
+
+// Scanline OpenEXR, single part, no compression, channels B, G, R (alphabetical, as the format requires)
+static bool writeExr(const char *path, const float *rgb, int W, int H, bool half) {
+    FILE *f = std::fopen(path, "wb");
+    if (!f) return false;
+    std::vector<unsigned char> hdr;
+    auto put = [&](const void *p, size_t n) { hdr.insert(hdr.end(), (const unsigned char *)p, (const unsigned char *)p + n); };
+    auto putStr = [&](const char *s) { put(s, std::strlen(s) + 1); };
+    auto putI = [&](int32_t v) { put(&v, 4); };
+    auto putF = [&](float v) { put(&v, 4); };
+    auto attr = [&](const char *name, const char *type, int32_t size) { putStr(name); putStr(type); putI(size); };
+    const uint32_t magic = 20000630u;
+    put(&magic, 4);
+    putI(2);  // version 2, scanline, single part
+    attr("channels", "chlist", 3 * 18 + 1);
+    for (const char *c : {"B", "G", "R"}) {
+        putStr(c);
+        putI(half ? 1 : 2);  // HALF / FLOAT
+        const unsigned char lin[4] = {0, 0, 0, 0};
+        put(lin, 4);
+        putI(1);
+        putI(1);
+    }
+    hdr.push_back(0);
+    attr("compression", "compression", 1);
+    hdr.push_back(0);
+    attr("dataWindow", "box2i", 16);
+    putI(0); putI(0); putI(W - 1); putI(H - 1);
+    attr("displayWindow", "box2i", 16);
+    putI(0); putI(0); putI(W - 1); putI(H - 1);
+    attr("lineOrder", "lineOrder", 1);
+    hdr.push_back(0);
+    attr("pixelAspectRatio", "float", 4);
+    putF(1.0f);
+    attr("screenWindowCenter", "v2f", 8);
+    putF(0.0f); putF(0.0f);
+    attr("screenWindowWidth", "float", 4);
+    putF(1.0f);
+    hdr.push_back(0);
+    const size_t bpc = half ? 2 : 4, lineBytes = (size_t)W * 3 * bpc;
+    std::fwrite(hdr.data(), 1, hdr.size(), f);
+    uint64_t offset = hdr.size() + (uint64_t)H * 8;
+    for (int y = 0; y < H; ++y) {
+        std::fwrite(&offset, 8, 1, f);
+        offset += 8 + lineBytes;
+    }
+    std::vector<unsigned char> line(lineBytes);
+    for (int y = 0; y < H; ++y) {
+        const int32_t yy = y, sz = (int32_t)lineBytes;
+        std::fwrite(&yy, 4, 1, f);
+        std::fwrite(&sz, 4, 1, f);
+        for (int c = 0; c < 3; ++c) {  // B, G, R planes of the scanline
+            const int src = 2 - c;
+            for (int x = 0; x < W; ++x) {
+                const float v = rgb[((size_t)y * W + x) * 3 + src];
+                if (half) {
+                    const uint16_t h = floatToHalf(v);
+                    std::memcpy(&line[((size_t)c * W + x) * 2], &h, 2);
+                } else {
+                    std::memcpy(&line[((size_t)c * W + x) * 4], &v, 4);
+                }
+            }
+        }
+        std::fwrite(line.data(), 1, lineBytes, f);
+    }
+    return std::fclose(f) == 0;
+}
+
+// Radiance RGBE, flat (uncompressed) scanlines, top to bottom (bitmap.cpp writeRGBE / rgbe.cpp)
+static bool writeRgbe(const char *path, const float *rgb, int W, int H) {
+    FILE *f = std::fopen(path, "wb");
+    if (!f) return false;
+    std::fprintf(f, "#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n", H, W);
+    std::vector<unsigned char> line((size_t)W * 4);
+    for (int y = 0; y < H; ++y) {
+        for (int x = 0; x < W; ++x) {
+            const float *p = rgb + ((size_t)y * W + x) * 3;
+            const float v = std::max(p[0], std::max(p[1], p[2]));
+            unsigned char *o = &line[(size_t)x * 4];
+            if (!(v > 1e-32f)) {
+                o[0] = o[1] = o[2] = o[3] = 0;
+            } else {
+                int e;
+                const float sc = std::frexp(v, &e) * 256.0f / v;
+                o[0] = (unsigned char)(p[0] * sc);
+                o[1] = (unsigned char)(p[1] * sc);
+                o[2] = (unsigned char)(p[2] * sc);
+                o[3] = (unsigned char)(e + 128);
+            }
+        }
+        std::fwrite(line.data(), 1, line.size(), f);
+    }
+    return std::fclose(f) == 0;
+}
+
 int b200pg_film_write(void *integ, const char *path) {
     if (!integ || !path) return fail("null argument");
     Integrator *self = (Integrator *)integ;
@@ -611,13 +738,16 @@ int b200pg_film_write(void *integ, const char *path) {
     std::vector<float> rgb((size_t)W * H * 3);
     int r = b200pg_film_develop(integ, rgb.data());
     if (r) return r;
-    std::string p(path);
-    if (p.size() < 4 || p.substr(p.size() - 4) != ".pfm") return fail("only .pfm output is supported (hdrfilm fileFormat=pfm)");
-    FILE *f = std::fopen(path, "wb");
-    if (!f) return fail(std::string("cannot open ") + path);
-    std::fprintf(f, "PF\n%d %d\n-1.0\n", W, H);  // little endian, bottom-up scanlines (bitmap.cpp writePFM)
-    for (int y = H - 1; y >= 0; --y) std::fwrite(rgb.data() + (size_t)y * W * 3, sizeof(float), (size_t)W * 3, f);
-    std::fclose(f);
+    std::string p(path), ext;
+    const size_t dot = p.find_last_of('.');
+    if (dot != std::string::npos) ext = p.substr(dot);
+    for (auto &c : ext) c = (char)std::tolower(c);
+    bool ok;
+    if (ext == ".pfm") ok = writePfm(path, rgb.data(), W, H);
+    else if (ext == ".exr") ok = writeExr(path, rgb.data(), W, H, self->scene->film.component_format == 0);
+    else if (ext == ".rgbe" || ext == ".hdr") ok = writeRgbe(path, rgb.data(), W, H);
+    else return fail("unsupported image extension \"" + ext + "\" (hdrfilm writes .exr, .pfm or .rgbe)");
+    if (!ok) return fail(std::string("cannot write ") + path);
     return 0;
 }
 

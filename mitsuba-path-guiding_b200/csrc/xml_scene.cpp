@@ -924,6 +924,21 @@ struct Loader {
                 H.film.width = getInt(*c, "width", 768);
                 H.film.height = getInt(*c, "height", 576);
                 if (prop(*c, "cropWidth") || prop(*c, "cropOffsetX")) fail("hdrfilm: crop windows are not supported");
+                {  // hdrfilm.cpp:212-240
+                    std::string ff = getString(*c, "fileFormat", "openexr"), cf = getString(*c, "componentFormat", "float16"),
+                                pf = getString(*c, "pixelFormat", "rgb");
+                    for (auto &ch : ff) ch = (char)std::tolower(ch);
+                    for (auto &ch : cf) ch = (char)std::tolower(ch);
+                    for (auto &ch : pf) ch = (char)std::tolower(ch);
+                    if (ff == "openexr") H.film.file_format = 0;
+                    else if (ff == "pfm") H.film.file_format = 1;
+                    else if (ff == "rgbe") H.film.file_format = 2;
+                    else fail("The \"fileFormat\" parameter must either be equal to \"openexr\", \"pfm\", or \"rgbe\"!");
+                    if (cf == "float16") H.film.component_format = 0;
+                    else if (cf == "float32") H.film.component_format = 1;
+                    else fail("The \"componentFormat\" parameter must either be equal to \"float16\" or \"float32\" (uint32 is not supported)");
+                    if (pf != "rgb") fail("hdrfilm: pixelFormat \"" + pf + "\" is not supported (need rgb)");
+                }
                 for (auto &f : c->children)
                     if (f->tag == "rfilter") {
                         if (f->get("type") != "gaussian") fail("rfilter plugin \"" + f->get("type") + "\" is not supported (need gaussian)");

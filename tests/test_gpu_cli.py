@@ -78,3 +78,48 @@ def test_cli_errors_are_loud(tmp_path):
     bad.write_text('<scene version="0.6.0"><integrator type="bdpt"/></scene>')
     r = subprocess.run([exe, str(bad)], capture_output=True, text=True)
     assert r.returncode != 0 and "not on the accelerated path" in r.stderr
+
+
+def test_film_writers_exr_pfm_rgbe(pkg, tmp_path):
+    """hdrfilm output formats (hdrfilm.cpp:212-240, 526-546): OpenEXR (the default; float16 / float32 components), PFM, RGBE,
+    read back with OpenCV and compared with b200pg_film_develop."""
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    cv2 = pytest.importorskip("cv2")
+    from b200pg import api
+
+    sb = pkg.scenes.cornell_box(80, 48, spp=8)
+    xml = pkg.scenes.save_scene(sb, str(tmp_path))
+    sc = api.Scene.load_xml(xml)
+    assert sc.desc.film.file_format == 1 and sc.desc.film.component_format == 1  # the scene writer asks for pfm / float32
+    it = api.Integrator(sc, sc.integrator_params())
+    it.render()
+    ref = it.develop()
+    it.film_write(str(tmp_path / "a.exr"))
+    a = cv2.imread(str(tmp_path / "a.exr"), cv2.IMREAD_UNCHANGED)[..., ::-1]
+    assert a.shape == ref.shape and a.dtype == np.float32
+    np.testing.assert_array_equal(a, ref)  # float32 components: lossless
+    it.film_write(str(tmp_path / "a.pfm"))
+    np.testing.assert_array_equal(_read_pfm(str(tmp_path / "a.pfm")), ref)
+    it.film_write(str(tmp_path / "a.hdr"))
+    h = cv2.imread(str(tmp_path / "a.hdr"), cv2.IMREAD_UNCHANGED)[..., ::-1]
+    np.testing.assert_allclose(h, ref, rtol=0.02, atol=ref.max() / 128)  # shared 8-bit mantissas
+    with pytest.raises(api.B200pgError, match="extension"):
+        it.film_write(str(tmp_path / "a.png"))
+    # hdrfilm defaults (no fileFormat / componentFormat in the XML): OpenEXR with float16 components; the CLI's default
+    # output name follows fileFormat
+    text = open(xml).read()
+    text = text.replace('<string name="componentFormat" value="float32"/>', "").replace('<string name="fileFormat" value="pfm"/>', "")
+    pdef = tmp_path / "scene_default.xml"
+    pdef.write_text(text)
+    d = api.Scene.load_xml(str(pdef)).desc.film
+    assert (d.file_format, d.component_format) == (0, 0)
+    exe = os.path.join(PKG_DIR, "b200pg-render")
+    r = subprocess.run([exe, "-q", str(pdef)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    b = cv2.imread(str(tmp_path / "scene_default.exr"), cv2.IMREAD_UNCHANGED)[..., ::-1]
+    np.testing.assert_allclose(b, ref, rtol=3e-3, atol=2e-4)  # same render (atomics order) through 11-bit mantissas
+    bad = text.replace('<film type="hdrfilm">', '<film type="hdrfilm"><string name="fileFormat" value="png"/>')
+    pbad = tmp_path / "bad.xml"
+    pbad.write_text(bad)
+    with pytest.raises(api.B200pgError, match="fileFormat"):
+        api.Scene.load_xml(str(pbad))
