@@ -601,7 +601,7 @@ struct Loader {
         return idx;
     }
 
-    void loadSerialized(const std::string &path, int shapeIndex, const M4 &toWorld, bool flipNormals, B200pgShape &s) {
+    void loadSerialized(const std::string &path, int shapeIndex, const M4 &toWorld, bool flipNormals, bool faceNormals, B200pgShape &s) {
         // trimesh.cpp:175-270: header 0x041C, version 3|4, zlib stream: flags, [name], counts, positions, normals, uvs, colors, indices
         std::ifstream f(path, std::ios::binary | std::ios::ate);
         if (!f) fail("serialized: cannot open \"" + path + "\"");
@@ -684,7 +684,7 @@ struct Loader {
         std::vector<uint32_t> idx(nt * 3);
         need(nt * 12);
         std::memcpy(idx.data(), &out[p], nt * 12);
-        finishMesh(pos, nrm, uv, idx, toWorld, flipNormals, (flags & 0x0010) != 0, s);
+        finishMesh(pos, nrm, uv, idx, toWorld, flipNormals, faceNormals || (flags & 0x0010) != 0, s);
     }
 
     void loadObj(const std::string &path, const M4 &toWorld, bool flipNormals, bool faceNormals, B200pgShape &s) {
@@ -735,8 +735,129 @@ struct Loader {
         finishMesh(pos, nrm, uv, idx, toWorld, flipNormals, faceNormals, s);
     }
 
+    // PLY (src/shapes/ply.cpp): ascii and binary little/big endian; vertex properties x y z [nx ny nz] [u v | s t], faces as
+    // index lists (triangles and convex polygons, fanned like ply.cpp's face callback)
+    void loadPly(const std::string &path, const M4 &toWorld, bool flipNormals, bool faceNormals, B200pgShape &s) {
+        std::ifstream f(path, std::ios::binary);
+        if (!f) fail("ply: cannot open \"" + path + "\"");
+        std::string line;
+        std::getline(f, line);
+        if (line.substr(0, 3) != "ply") fail("ply: \"" + path + "\" is not a PLY file");
+        enum { kAscii, kLE, kBE } fmt = kAscii;
+        struct Prop { std::string name, type, countType, itemType; bool list; };
+        struct Elem { std::string name; size_t count; std::vector<Prop> props; };
+        std::vector<Elem> elems;
+        while (std::getline(f, line)) {
+            if (!line.empty() && line.back() == '\r') line.pop_back();
+            std::istringstream is(line);
+            std::string t;
+            is >> t;
+            if (t == "format") {
+                std::string v;
+                is >> v;
+                fmt = v == "ascii" ? kAscii : (v == "binary_little_endian" ? kLE : kBE);
+            } else if (t == "element") {
+                Elem e;
+                is >> e.name >> e.count;
+                elems.push_back(e);
+            } else if (t == "property") {
+                if (elems.empty()) fail("ply: property before element");
+                Prop p;
+                std::string a;
+                is >> a;
+                p.list = a == "list";
+                if (p.list) is >> p.countType >> p.itemType >> p.name;
+                else { p.type = a; is >> p.name; }
+                elems.back().props.push_back(p);
+            } else if (t == "end_header") break;
+        }
+        auto sizeOf = [&](const std::string &t) -> int {
+            if (t == "char" || t == "uchar" || t == "int8" || t == "uint8") return 1;
+            if (t == "short" || t == "ushort" || t == "int16" || t == "uint16") return 2;
+            if (t == "int" || t == "uint" || t == "float" || t == "int32" || t == "uint32" || t == "float32") return 4;
+            if (t == "double" || t == "float64") return 8;
+            fail("ply: unknown property type \"" + t + "\"");
+            return 0;
+        };
+        auto readNum = [&](const std::string &t) -> double {
+            if (fmt == kAscii) {
+                double v;
+                f >> v;
+                return v;
+            }
+            unsigned char b[8];
+            const int n = sizeOf(t);
+            f.read((char *)b, n);
+            if (fmt == kBE) std::reverse(b, b + n);
+            if (t == "char" || t == "int8") return (double)*(int8_t *)b;
+            if (t == "uchar" || t == "uint8") return (double)*(uint8_t *)b;
+            if (t == "short" || t == "int16") { int16_t v; std::memcpy(&v, b, 2); return v; }
+            if (t == "ushort" || t == "uint16") { uint16_t v; std::memcpy(&v, b, 2); return v; }
+            if (t == "int" || t == "int32") { int32_t v; std::memcpy(&v, b, 4); return v; }
+            if (t == "uint" || t == "uint32") { uint32_t v; std::memcpy(&v, b, 4); return v; }
+            if (t == "float" || t == "float32") { float v; std::memcpy(&v, b, 4); return v; }
+            double v;
+            std::memcpy(&v, b, 8);
+            return v;
+        };
+        std::vector<float> pos, nrm, uv;
+        std::vector<uint32_t> idx;
+        for (auto &e : elems) {
+            if (e.name == "vertex") {
+                bool hasN = false, hasUV = false;
+                for (auto &p : e.props) {
+                    hasN |= p.name == "nx";
+                    hasUV |= p.name == "u" || p.name == "s";
+                }
+                pos.resize(3 * e.count);
+                if (hasN) nrm.resize(3 * e.count);
+                if (hasUV) uv.resize(2 * e.count);
+                for (size_t v = 0; v < e.count; ++v)
+                    for (auto &p : e.props) {
+                        if (p.list) {
+                            const int n = (int)readNum(p.countType);
+                            for (int k = 0; k < n; ++k) readNum(p.itemType);
+                            continue;
+                        }
+                        const float val = (float)readNum(p.type);
+                        if (p.name == "x") pos[3 * v] = val;
+                        else if (p.name == "y") pos[3 * v + 1] = val;
+                        else if (p.name == "z") pos[3 * v + 2] = val;
+                        else if (p.name == "nx") nrm[3 * v] = val;
+                        else if (p.name == "ny") nrm[3 * v + 1] = val;
+                        else if (p.name == "nz") nrm[3 * v + 2] = val;
+                        else if (p.name == "u" || p.name == "s") uv[2 * v] = val;
+                        else if (p.name == "v" || p.name == "t") uv[2 * v + 1] = val;
+                    }
+            } else if (e.name == "face") {
+                for (size_t i = 0; i < e.count; ++i)
+                    for (auto &p : e.props) {
+                        if (!p.list) { readNum(p.type); continue; }
+                        const int n = (int)readNum(p.countType);
+                        std::vector<uint32_t> poly(n);
+                        for (int k = 0; k < n; ++k) poly[k] = (uint32_t)readNum(p.itemType);
+                        if (p.name == "vertex_indices" || p.name == "vertex_index")
+                            for (int k = 2; k < n; ++k) idx.insert(idx.end(), {poly[0], poly[k - 1], poly[k]});
+                    }
+            } else {
+                for (size_t i = 0; i < e.count; ++i)
+                    for (auto &p : e.props) {
+                        if (!p.list) { readNum(p.type); continue; }
+                        const int n = (int)readNum(p.countType);
+                        for (int k = 0; k < n; ++k) readNum(p.itemType);
+                    }
+            }
+        }
+        if (!f && !f.eof()) fail("ply: truncated file \"" + path + "\"");
+        if (idx.empty() || pos.empty()) fail("Unable to load \"" + path + "\" (no triangles or vertices found)!");  // ply.cpp:101-102
+        for (uint32_t i : idx)
+            if ((size_t)i * 3 >= pos.size()) fail("ply: vertex index out of range");
+        finishMesh(pos, nrm, uv, idx, toWorld, flipNormals, faceNormals, s);
+    }
+
     void finishMesh(std::vector<float> &pos, std::vector<float> &nrm, std::vector<float> &uv, std::vector<uint32_t> &idx,
                     const M4 &toWorld, bool flipNormals, bool faceNormals, B200pgShape &s) {
+        const float *computedNormals = nullptr;
         // apply toWorld (serialized.cpp / obj.cpp transform vertices on load); normals with the inverse transpose
         double a[9] = {toWorld.m[0], toWorld.m[1], toWorld.m[2], toWorld.m[4], toWorld.m[5], toWorld.m[6], toWorld.m[8], toWorld.m[9], toWorld.m[10]};
         double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
@@ -750,7 +871,64 @@ struct Loader {
             pos[3 * v + 1] = toWorld.m[4] * x + toWorld.m[5] * y + toWorld.m[6] * z + toWorld.m[7];
             pos[3 * v + 2] = toWorld.m[8] * x + toWorld.m[9] * y + toWorld.m[10] * z + toWorld.m[11];
         }
-        if (faceNormals) nrm.clear();
+        if (faceNormals) {
+            nrm.clear();
+            if (flipNormals)  // TriMesh::computeNormals changes the winding order instead (trimesh.cpp:610-622)
+                for (size_t t = 0; t + 2 < idx.size(); t += 3) std::swap(idx[t], idx[t + 1]);
+        } else if (nrm.empty()) {
+            // TriMesh::configure -> computeNormals (trimesh.cpp:373, 631-668): a mesh without vertex normals gets angle-weighted
+            // smooth normals (Thuermer & Wuethrich, JGT 1998), computed on the transformed positions
+            const size_t nv = pos.size() / 3;
+            std::vector<float> acc(3 * nv, 0.0f);
+            auto P = [&](uint32_t i, int c) { return pos[3 * (size_t)i + c]; };
+            for (size_t t = 0; t + 2 < idx.size(); t += 3) {
+                float n[3] = {0, 0, 0};
+                for (int i = 0; i < 3; ++i) {
+                    const uint32_t i0 = idx[t + i], i1 = idx[t + (i + 1) % 3], i2 = idx[t + (i + 2) % 3];
+                    float a[3], b[3];
+                    for (int c = 0; c < 3; ++c) {
+                        a[c] = P(i1, c) - P(i0, c);
+                        b[c] = P(i2, c) - P(i0, c);
+                    }
+                    if (i == 0) {
+                        n[0] = a[1] * b[2] - a[2] * b[1];
+                        n[1] = a[2] * b[0] - a[0] * b[2];
+                        n[2] = a[0] * b[1] - a[1] * b[0];
+                        const float len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+                        if (len == 0) break;
+                        for (int c = 0; c < 3; ++c) n[c] /= len;
+                    }
+                    const float la = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]), lb = std::sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
+                    float u[3], v[3], d = 0, s2 = 0, m2 = 0;
+                    for (int c = 0; c < 3; ++c) {
+                        u[c] = a[c] / la;
+                        v[c] = b[c] / lb;
+                        d += u[c] * v[c];
+                    }
+                    for (int c = 0; c < 3; ++c) {
+                        s2 += (v[c] + u[c]) * (v[c] + u[c]);
+                        m2 += (v[c] - u[c]) * (v[c] - u[c]);
+                    }
+                    // unitAngle (util.h:325-330)
+                    const float angle = d < 0 ? 3.14159265358979323846f - 2 * std::asin(0.5f * std::sqrt(s2)) : 2 * std::asin(0.5f * std::sqrt(m2));
+                    for (int c = 0; c < 3; ++c) acc[3 * (size_t)i0 + c] += n[c] * angle;
+                }
+            }
+            nrm.resize(3 * nv);
+            for (size_t v = 0; v < nv; ++v) {
+                float len = std::sqrt(acc[3 * v] * acc[3 * v] + acc[3 * v + 1] * acc[3 * v + 1] + acc[3 * v + 2] * acc[3 * v + 2]);
+                if (flipNormals) len *= -1;
+                if (len != 0) {
+                    for (int c = 0; c < 3; ++c) nrm[3 * v + c] = acc[3 * v + c] / len;
+                } else {  // "Choose some bogus value" (trimesh.cpp:660-663)
+                    nrm[3 * v] = 1; nrm[3 * v + 1] = 0; nrm[3 * v + 2] = 0;
+                }
+            }
+            // these normals are already in world space and already flipped: skip the transform below
+            H.ownedF.push_back(std::move(nrm));
+            computedNormals = H.ownedF.back().data();
+            nrm.clear();
+        }
         for (size_t v = 0; v < nrm.size() / 3; ++v) {
             double x = nrm[3 * v], y = nrm[3 * v + 1], z = nrm[3 * v + 2];
             double nx = inv[0] * x + inv[3] * y + inv[6] * z, ny = inv[1] * x + inv[4] * y + inv[7] * z, nz = inv[2] * x + inv[5] * y + inv[8] * z;
@@ -767,6 +945,8 @@ struct Loader {
         if (!nrm.empty()) {
             H.ownedF.push_back(std::move(nrm));
             s.normals = H.ownedF.back().data();
+        } else if (computedNormals) {
+            s.normals = computedNormals;
         }
         if (!uv.empty()) {
             H.ownedF.push_back(std::move(uv));
@@ -809,15 +989,19 @@ struct Loader {
             std::string fn = getString(n, "filename", "");
             if (fn.empty()) fail("serialized: missing filename");
             if (fn[0] != '/') fn = baseDir + "/" + fn;
-            loadSerialized(fn, getInt(n, "shapeIndex", 0), toWorld, flip, s);
-            if (getBool(n, "faceNormals", false)) s.normals = nullptr;
+            loadSerialized(fn, getInt(n, "shapeIndex", 0), toWorld, flip, getBool(n, "faceNormals", false), s);
         } else if (type == "obj") {
             std::string fn = getString(n, "filename", "");
             if (fn.empty()) fail("obj: missing filename");
             if (fn[0] != '/') fn = baseDir + "/" + fn;
             loadObj(fn, toWorld, flip, getBool(n, "faceNormals", false), s);
+        } else if (type == "ply") {
+            std::string fn = getString(n, "filename", "");
+            if (fn.empty()) fail("ply: missing filename");
+            if (fn[0] != '/') fn = baseDir + "/" + fn;
+            loadPly(fn, toWorld, flip, getBool(n, "faceNormals", false), s);
         } else {
-            fail("shape plugin \"" + type + "\" is not on the accelerated path (supported: rectangle, cube, serialized, obj)");
+            fail("shape plugin \"" + type + "\" is not on the accelerated path (supported: rectangle, cube, serialized, obj, ply)");
         }
         for (auto &c : n.children) {
             if (c->tag == "bsdf") {

@@ -139,3 +139,84 @@ def test_missing_file_and_version(api, tmp_path):
     path.write_text(_scene('<shape type="rectangle"/>').replace(' version="0.6.0"', "").replace("$spp", "4"))
     with pytest.raises(api.B200pgError, match="version"):
         api.Scene.load_xml(str(path))
+
+
+def _angle_weighted_normals(P, T):
+    """TriMesh::computeNormals (trimesh.cpp:631-668) in numpy."""
+    N = np.zeros_like(P)
+    for tri in T:
+        n = None
+        for i in range(3):
+            v0, v1, v2 = P[tri[i]], P[tri[(i + 1) % 3]], P[tri[(i + 2) % 3]]
+            a, b = v1 - v0, v2 - v0
+            if i == 0:
+                n = np.cross(a, b)
+                n = n / np.linalg.norm(n)
+            u, v = a / np.linalg.norm(a), b / np.linalg.norm(b)
+            ang = np.pi - 2 * np.arcsin(0.5 * np.linalg.norm(v + u)) if u @ v < 0 else 2 * np.arcsin(0.5 * np.linalg.norm(v - u))
+            N[tri[i]] += n * ang
+    return N / np.linalg.norm(N, axis=1, keepdims=True)
+
+
+def _mesh_xml(tmp_path, shape_xml):
+    path = tmp_path / "m.xml"
+    path.write_text(_scene(shape_xml).replace("$spp", "4"))
+    return str(path)
+
+
+def test_meshes_without_normals_get_smooth_normals_and_ply_loads(api, pkg, tmp_path):
+    """TriMesh::configure always runs computeNormals (trimesh.cpp:373): obj / ply / serialized meshes without vertex normals
+    are shaded with angle-weighted smooth normals unless faceNormals=true. Also covers the ply loader (ascii + binary)."""
+    S = pkg.scenes
+    P, _, T = S.heightfield_mesh(n=6, seed=5, amp=0.3)
+    P = P.astype(np.float32)
+    want = _angle_weighted_normals(P.astype(np.float64), T)
+    # --- obj without vn
+    with open(tmp_path / "m.obj", "w") as f:
+        for p in P:
+            f.write("v %.9g %.9g %.9g\n" % tuple(p))
+        for t in T:
+            f.write("f %d %d %d\n" % tuple(t + 1))
+    # --- ply, ascii and binary little endian, with an extra per-vertex property and quads split by the loader
+    hdr = "ply\nformat %s 1.0\ncomment test\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\nproperty uchar red\n" \
+          "element face %d\nproperty list uchar int vertex_indices\nend_header\n"
+    with open(tmp_path / "a.ply", "w") as f:
+        f.write(hdr % ("ascii", len(P), len(T)))
+        for p in P:
+            f.write("%.9g %.9g %.9g 7\n" % tuple(p))
+        for t in T:
+            f.write("3 %d %d %d\n" % tuple(t))
+    with open(tmp_path / "b.ply", "wb") as f:
+        f.write((hdr % ("binary_little_endian", len(P), len(T))).encode())
+        for p in P:
+            f.write(p.astype("<f4").tobytes() + b"\x07")
+        for t in T:
+            f.write(b"\x03" + t.astype("<i4").tobytes())
+    body = '<shape type="%s"><string name="filename" value="%s"/>%s<bsdf type="diffuse"/></shape>' \
+           '<shape type="rectangle"><emitter type="area"><rgb name="radiance" value="1"/></emitter></shape>'
+    for kind, fn in (("obj", "m.obj"), ("ply", "a.ply"), ("ply", "b.ply")):
+        sc1 = api.Scene.load_xml(_mesh_xml(tmp_path, body % (kind, fn, "")))  # keep the handle alive: desc points into it
+        d = sc1.desc
+        sh = d.shapes[0]
+        assert sh.n_vertices == len(P) and sh.n_triangles == len(T) and bool(sh.normals)
+        got = np.ctypeslib.as_array(sh.normals, (sh.n_vertices * 3,)).reshape(-1, 3)
+        gpos = np.ctypeslib.as_array(sh.positions, (sh.n_vertices * 3,)).reshape(-1, 3)
+        # the obj loader numbers vertices in order of first use: match by position
+        order = [int(np.where((P == q).all(1))[0][0]) for q in gpos]
+        assert sorted(order) == list(range(len(P)))
+        np.testing.assert_allclose(got, want[order], atol=2e-6)
+        # faceNormals=true: no vertex normals; flipNormals then swaps the winding (trimesh.cpp:610-622)
+        sc2 = api.Scene.load_xml(_mesh_xml(tmp_path, body % (kind, fn, '<boolean name="faceNormals" value="true"/>')))
+        d2 = sc2.desc
+        assert not bool(d2.shapes[0].normals)
+        sc3 = api.Scene.load_xml(_mesh_xml(tmp_path, body % (kind, fn, '<boolean name="faceNormals" value="true"/><boolean name="flipNormals" value="true"/>')))
+        d3 = sc3.desc
+        i3 = np.ctypeslib.as_array(d3.shapes[0].indices, (len(T) * 3,)).reshape(-1, 3)
+        p3 = np.ctypeslib.as_array(d3.shapes[0].positions, (len(P) * 3,)).reshape(-1, 3)
+        np.testing.assert_array_equal(p3[i3], P[T[:, [1, 0, 2]]])  # same triangles, first two corners swapped
+        # flipNormals on smooth normals: negated
+        sc4 = api.Scene.load_xml(_mesh_xml(tmp_path, body % (kind, fn, '<boolean name="flipNormals" value="true"/>')))
+        d4 = sc4.desc
+        np.testing.assert_allclose(np.ctypeslib.as_array(d4.shapes[0].normals, (len(P) * 3,)).reshape(-1, 3), -want[order], atol=2e-6)
+    with pytest.raises(api.B200pgError, match="ply"):
+        api.Scene.load_xml(_mesh_xml(tmp_path, body % ("ply", "missing.ply", "")))
