@@ -1,5 +1,5 @@
 """relMSE at equal time (north-star metric): guided (training included in the budget) vs unguided, config C2.
-usage: equal_time.py [size] [budgets_s...]   -> one JSON line per budget on stdout"""
+usage: equal_time.py [size | WxH] [budgets_s...]   -> one JSON line per budget on stdout"""
 import json, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
@@ -7,9 +7,10 @@ import __graft_entry__ as ge
 pkg = ge.load_package()
 from b200pg import api
 
-size = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+size = sys.argv[1] if len(sys.argv) > 1 else "1024"
+W, H = (int(x) for x in size.split("x")) if "x" in size else (int(size), int(size))
 budgets = [float(x) for x in sys.argv[2:]] or [0.25, 0.5, 1.0, 2.0]
-sb = pkg.scenes.cornell_caustic(size, size)
+sb = pkg.scenes.cornell_caustic(W, H)
 scene = api.Scene.from_builder(sb)
 
 
