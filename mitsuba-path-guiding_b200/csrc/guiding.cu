@@ -635,7 +635,7 @@ __global__ void __launch_bounds__(256) k_mstep_allreduce(CommView cv, float4 *__
         do {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
             if ((int)(v - cv.epoch) >= 0) break;
-            if (clock64() - t0 > 4000000000LL) {  // ~2 s: a peer never arrived; fail loudly instead of hanging the GPU
+            if (clock64() - t0 > 20000000000LL) {  // ~10 s: a peer never arrived; fail loudly instead of hanging the GPU
                 atomicExch(cv.error, 1u);
                 break;
             }
