@@ -418,6 +418,7 @@ __global__ void __launch_bounds__(kShadeThreads, 6) k_shade_vol(ShadeArgs A) {
         uint32_t shOnSurface = 0;
         uint64_t shRng = 0;
         uint32_t depth = 0, vcount = 0;
+        float neeDirPdf = 0.0f, neeLightPdf = 0.0f;
 
         if (valid) {
             const float4 ro = A.cur.rayO[i], rd = A.cur.rayD[i], thr4 = A.cur.thr[i], rad4 = A.cur.rad[i];
@@ -499,10 +500,11 @@ __global__ void __launch_bounds__(kShadeThreads, 6) k_shade_vol(ShadeArgs A) {
                                 if (!isZero(value)) {
                                     const float phaseVal = phaseEval(M, -d, dRec.d);
                                     if (phaseVal != 0) {
-                                        float dirPdf = phaseVal;  // phase pdf == phase value
-                                        if (guided) dirPdf = A.G.alpha * guidePdf(A.G, gcell, dRec.d) + (1 - A.G.alpha) * phaseVal;
-                                        const float weight = miWeight(dRec.pdf, dirPdf);
-                                        shC = thr * value * phaseVal * weight;
+                                        // the MIS weight needs the direction pdf (phase pdf == phase value; at a guided vertex
+                                        // mixed with the mixture pdf, evaluated below together with the sampled direction)
+                                        neeDirPdf = phaseVal;
+                                        neeLightPdf = dRec.pdf;
+                                        shC = thr * value * phaseVal;
                                         shO = mRec.p;
                                         shD = dRec.d;
                                         shMaxT = dRec.dist;
@@ -527,12 +529,16 @@ __global__ void __launch_bounds__(kShadeThreads, 6) k_shade_vol(ShadeArgs A) {
                                 } else {
                                     wo = phaseSample(M, -d, u12, pp);
                                 }
-                                phasePdf = A.G.alpha * guidePdf(A.G, gcell, wo) + (1 - A.G.alpha) * pp;
+                                float gNee = 0.0f, gWo = 0.0f;  // one pass over the cell's lobes for both directions
+                                guidePdf2(A.G, gcell, wantShadow ? shD : wo, wo, gNee, gWo);
+                                if (wantShadow) neeDirPdf = A.G.alpha * gNee + (1 - A.G.alpha) * neeDirPdf;
+                                phasePdf = A.G.alpha * gWo + (1 - A.G.alpha) * pp;
                                 dirOk = pp > 0 && phasePdf > 0;
                                 if (dirOk) thr = thr * (pp / phasePdf);
                             } else {
                                 wo = phaseSample(M, -d, rng.next2D(), phasePdf);  // phase weight == 1
                             }
+                            if (wantShadow) shC = shC * miWeight(neeLightPdf, neeDirPdf);
                             if (!dirOk) {
                                 terminate = true;
                             } else {
@@ -577,10 +583,9 @@ __global__ void __launch_bounds__(kShadeThreads, 6) k_shade_vol(ShadeArgs A) {
                                     const float3 woL = its.sh.toLocal(dRec.d);
                                     const float3 bsdfVal = bsdfEval(bsdf, its.wi, woL);
                                     if (!isZero(bsdfVal) && (!cfg.strictNormals || dot(its.geoN, dRec.d) * woL.z > 0)) {
-                                        float bPdf = bsdfPdf(bsdf, its.wi, woL);
-                                        if (guided) bPdf = A.G.alpha * guidePdf(A.G, gcell, dRec.d) + (1 - A.G.alpha) * bPdf;
-                                        const float weight = miWeight(dRec.pdf, bPdf);
-                                        shC = thr * value * bsdfVal * weight;
+                                        neeDirPdf = bsdfPdf(bsdf, its.wi, woL);
+                                        neeLightPdf = dRec.pdf;
+                                        shC = thr * value * bsdfVal;
                                         shO = its.p;
                                         shD = dRec.d;
                                         shMaxT = dRec.dist;
@@ -615,12 +620,16 @@ __global__ void __launch_bounds__(kShadeThreads, 6) k_shade_vol(ShadeArgs A) {
                                     fcos = w * pb;
                                     wo = its.sh.toWorld(woL);
                                 }
-                                bPdf = ok ? A.G.alpha * guidePdf(A.G, gcell, wo) + (1 - A.G.alpha) * pb : 0.0f;
+                                float gNee = 0.0f, gWo = 0.0f;
+                                if (wantShadow || ok) guidePdf2(A.G, gcell, wantShadow ? shD : wo, ok ? wo : shD, gNee, gWo);
+                                if (wantShadow) neeDirPdf = A.G.alpha * gNee + (1 - A.G.alpha) * neeDirPdf;
+                                bPdf = ok ? A.G.alpha * gWo + (1 - A.G.alpha) * pb : 0.0f;
                                 bsdfWeight = (ok && !isZero(fcos) && bPdf > 0) ? fcos / bPdf : f3(0.0f);
                             } else {
                                 bsdfWeight = bsdfSample(bsdf, its.wi, rng.next2D(), woL, bPdf, bEta, sampledType);
                                 wo = its.sh.toWorld(woL);
                             }
+                            if (wantShadow) shC = shC * miWeight(neeLightPdf, neeDirPdf);
                             if (isZero(bsdfWeight) || (cfg.strictNormals && dot(its.geoN, wo) * woL.z <= 0)) {
                                 terminate = true;
                             } else {
