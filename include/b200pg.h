@@ -247,6 +247,11 @@ int b200pg_film_clear(void *integ);
 int b200pg_film_device_buffer(void *integ, void **dev_ptr, size_t *n_floats); /* H*W*4: R,G,B,weight */
 int b200pg_film_read(void *integ, float *rgbaw /* H*W*5: R,G,B,alpha,weight (imageblock.h:131-138) */);
 int b200pg_film_develop(void *integ, float *rgb /* H*W*3 = RGB/weight, fmtconv.cpp:978-1005 */);
+/* Progressive preview (what mtsgui does between progressions, renderproc.cpp:141-148 + the film's develop): snapshot the film as
+ * it is now and copy it to `rgbaw_pinned` (page-locked host memory, H*W*5) on a second stream while rendering continues;
+ * b200pg_film_read_wait blocks until the snapshot has arrived. A new async read first waits for the previous one. */
+int b200pg_film_read_async(void *integ, float *rgbaw_pinned);
+int b200pg_film_read_wait(void *integ);
 /* Film::develop to a file (hdrfilm.cpp:487-546), format chosen by the extension: .exr (scanline OpenEXR, uncompressed, channels
  * B G R as float16 or float32 per the film's componentFormat), .pfm (float32), .rgbe / .hdr (Radiance RGBE, flat).
  * The reference's banner (`banner=true` draws a logo into the image, :501-511) is never drawn. */

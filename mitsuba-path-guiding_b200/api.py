@@ -70,6 +70,8 @@ def lib():
     L.b200pg_k_vmm_pdf_sample.argtypes = [C.c_void_p, fp, fp, fp, C.c_size_t, fp, fp, fp, u32p]
     L.b200pg_k_bin_samples.argtypes = [C.c_void_p, fp, C.c_size_t, u32p, u32p, u32p, u32p]
     L.b200pg_k_em_step.argtypes = [C.c_void_p, fp, fp, fp, fp, fp, C.c_size_t, C.c_int, fp]
+    L.b200pg_film_read_async.argtypes = [C.c_void_p, fp]
+    L.b200pg_film_read_wait.argtypes = [C.c_void_p]
     L.b200pg_train.argtypes = [C.c_void_p, C.c_int, u32p, u32p]
     L.b200pg_comm_local_handle.argtypes = [C.c_void_p, C.c_void_p]
     L.b200pg_comm_connect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -191,6 +193,14 @@ class Integrator:
         assert out.dtype == np.float32 and out.size == self.H * self.W * 5 and out.flags["C_CONTIGUOUS"]
         _check(lib().b200pg_film_read(self.h, _f(out)))
         return out
+
+    def film_async(self, out):
+        """Snapshot the film into the (pinned) array `out` while rendering continues; film_wait() blocks until it is there."""
+        assert out.dtype == np.float32 and out.flags["C_CONTIGUOUS"]
+        _check(lib().b200pg_film_read_async(self.h, _f(out)))
+
+    def film_wait(self):
+        _check(lib().b200pg_film_read_wait(self.h))
 
     def develop(self):
         out = np.zeros((self.H, self.W, 3), np.float32)

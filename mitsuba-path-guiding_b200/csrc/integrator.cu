@@ -77,7 +77,8 @@ struct Integrator {
     HostScene *scene = nullptr;
     B200pgIntegratorParams params;
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copyStream = nullptr;
+    cudaEvent_t evExport = nullptr;
     std::atomic<int> cancel{0};
 
     // device scene
@@ -157,6 +158,8 @@ struct Integrator {
 
     ~Integrator() {
         if (stream) cudaStreamDestroy(stream);
+        if (copyStream) cudaStreamDestroy(copyStream);
+        if (evExport) cudaEventDestroy(evExport);
         for (auto &e : ev)
             if (e) cudaEventDestroy(e);
         for (auto &sp : spans) {
@@ -590,6 +593,29 @@ int b200pg_film_read(void *integ, float *rgbaw) {
     CUDA_OK(cudaMemcpyAsync(rgbaw, self->dFilmOut.p, self->dFilm.n * 5 * sizeof(float), cudaMemcpyDeviceToHost, self->stream));
     CUDA_OK(cudaStreamSynchronize(self->stream));
     self->stats.kernel_launches++;
+    PG_END
+}
+
+// Asynchronous variant for progressive previews: the 5-channel expansion is enqueued on the render stream (so it sees the
+// film exactly as it is now), the device->host copy runs on a second stream and overlaps whatever is rendered next.
+int b200pg_film_read_async(void *integ, float *rgbaw_pinned) {
+    PG_TRY(integ)
+    if (!self->copyStream) {
+        CUDA_OK(cudaStreamCreateWithFlags(&self->copyStream, cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&self->evExport, cudaEventDisableTiming));
+    }
+    CUDA_OK(cudaStreamSynchronize(self->copyStream));  // the previous read must have left the staging buffer
+    self->dFilmOut.alloc(self->dFilm.n * 5);
+    launchFilmExport(self->dFilm.p, self->dFilmOut.p, (uint32_t)self->dFilm.n, 0, self->stream);
+    CUDA_OK(cudaEventRecord(self->evExport, self->stream));
+    CUDA_OK(cudaStreamWaitEvent(self->copyStream, self->evExport, 0));
+    CUDA_OK(cudaMemcpyAsync(rgbaw_pinned, self->dFilmOut.p, self->dFilm.n * 5 * sizeof(float), cudaMemcpyDeviceToHost, self->copyStream));
+    self->stats.kernel_launches++;
+    PG_END
+}
+int b200pg_film_read_wait(void *integ) {
+    PG_TRY(integ)
+    if (self->copyStream) CUDA_OK(cudaStreamSynchronize(self->copyStream));
     PG_END
 }
 

@@ -278,3 +278,21 @@ def test_errors_are_loud(api, pkg):
         api.Integrator(sc, p)
     with pytest.raises(api.B200pgError):
         api.Integrator(sc, _params(api), device=99)
+
+
+def test_async_film_snapshot_equals_blocking_read(api, cornell):
+    """b200pg_film_read_async: the snapshot is of the film at the time of the call, even when rendering continues."""
+    import torch
+
+    sb, osc, it = cornell
+    it.film_clear()
+    it.progression(0, 2)
+    want = it.film()
+    host = torch.empty((sb.height, sb.width, 5), dtype=torch.float32, pin_memory=True).numpy()
+    it.film_async(host)
+    it.progression(2, 2)  # keeps accumulating while the copy is in flight
+    it.film_wait()
+    np.testing.assert_array_equal(host, want)
+    it.film_async(host)
+    it.film_wait()
+    np.testing.assert_array_equal(host, it.film())
