@@ -97,7 +97,15 @@ __global__ void __launch_bounds__(256) k_generate(DeviceScene S, BatchDesc B, Pa
             sample = B.sampleList[i];
         } else {
             sample = B.firstSample + i / nPix;
-            pixel = B.rowBegin * W + i % nPix;
+            uint32_t j = i % nPix;
+            // a warp covers an 8 x 4 pixel tile instead of 32 pixels of one row: its first hits are neighbours in two
+            // dimensions (same material, same guiding cell), and queue compaction keeps that order for later bounces.
+            // Samples are keyed by (pixel, sample index), so the order does not change any result.
+            if ((W & 7u) == 0 && (B.nRows & 3u) == 0) {
+                const uint32_t tile = j >> 5, within = j & 31u, tilesX = W >> 3;
+                j = ((tile / tilesX) * 4 + (within >> 3)) * W + (tile % tilesX) * 8 + (within & 7u);
+            }
+            pixel = B.rowBegin * W + j;
         }
         Rng rng;
         rng.init(S.seed, pixel, sample);

@@ -137,3 +137,70 @@ def test_energy_conservation(scene):
         wi = np.repeat(np.array([[0.3, 0.1, 0.9486833]], np.float32), n, 0)
         s = sc.bsdf(idx[name], wi, wi, rng.rand(n, 2).astype(np.float32))
         assert s["weight"].mean(0).max() <= 1.0 + 5e-3, name
+
+
+# ---- the reference's rough-transmittance test (src/tests/test_rtrans.cpp:135-260): the tabulated transmittance, reduced
+# to one (eta, alpha) like RoughPlastic::configure does (rtrans.h:292-388), against a numerical integration of the rough
+# dielectric BTDF (tolerance 1e-3 there; a few 1e-3 here because the integral is Monte Carlo) ----------------------------
+def _cubic_interp(x, values):  # evalCubicInterp1D on [0, 1] (src/libcore/spline.cpp:23-60)
+    size = len(values)
+    t = x * (size - 1)
+    k = max(0, min(int(t), size - 2))
+    f0, f1 = values[k], values[k + 1]
+    d0 = 0.5 * (values[k + 1] - values[k - 1]) if k > 0 else values[k + 1] - values[k]
+    d1 = 0.5 * (values[k + 2] - values[k]) if k + 2 < size else values[k + 1] - values[k]
+    t -= k
+    t2, t3 = t * t, t * t * t
+    return (2 * t3 - 3 * t2 + 1) * f0 + (-2 * t3 + 3 * t2) * f1 + (t3 - 2 * t2 + t) * d0 + (t3 - t2) * d1
+
+
+def _fresnel_dielectric(c, eta):  # fresnelDielectricExt for cos >= 0, eta > 1 (util.cpp:653-683)
+    st2 = (1 - c * c) / (eta * eta)
+    ct = np.sqrt(np.maximum(1 - st2, 0))
+    rs = (c - eta * ct) / (c + eta * ct)
+    rp = (eta * c - ct) / (eta * c + ct)
+    return 0.5 * (rs * rs + rp * rp), ct
+
+
+def _g1(v, m, alpha, ggx):  # smithG1 (microfacet.h:477-514)
+    ok = (np.einsum("ij,ij->i", v, m) * v[:, 2]) > 0
+    tan = np.sqrt(np.maximum(1 - v[:, 2] ** 2, 0)) / np.abs(v[:, 2])
+    if ggx:
+        g = 2 / (1 + np.sqrt(1 + (alpha * tan) ** 2))
+    else:
+        a = 1 / np.maximum(alpha * tan, 1e-12)
+        g = np.where(a >= 1.6, 1.0, (3.535 * a + 2.181 * a * a) / (1 + 2.276 * a + 2.577 * a * a))
+    return np.where(tan == 0, 1.0, g) * ok
+
+
+@pytest.mark.parametrize("distr,eta,alpha", [("beckmann", 1.5, 0.2), ("ggx", 1.3, 0.4), ("beckmann", 1.49, 0.7)])
+def test_rough_transmittance_table_vs_btdf_integration(pkg, oracle, distr, eta, alpha):
+    from b200pg import rtrans
+
+    ext, ed, idf = oracle.rtrans_reduce(rtrans.load_packed(distr), eta, alpha)
+    rng = np.random.RandomState(4)
+    n = 400000
+    ggx = distr == "ggx"
+    for cos_i in (0.25, 0.5, 0.8, 1.0):
+        # microfacet normals m ~ D(m) cos(theta_m) (sampleAll, microfacet.h:287-395)
+        u1, u2 = rng.rand(n), rng.rand(n)
+        tan2 = alpha * alpha * u1 / (1 - u1) if ggx else -alpha * alpha * np.log(1 - u1)
+        cm = 1 / np.sqrt(1 + tan2)
+        sm = np.sqrt(np.maximum(1 - cm * cm, 0))
+        phi = 2 * np.pi * u2
+        m = np.stack([sm * np.cos(phi), sm * np.sin(phi), cm], 1)
+        wi = np.array([np.sqrt(1 - cos_i * cos_i), 0.0, cos_i])
+        wim = m @ wi
+        F, ct = _fresnel_dielectric(np.maximum(wim, 0), eta)
+        # refracted direction (util.cpp refract): wo = m * (wi.m / eta - cos_t) - wi / eta
+        wo = m * (wim / eta - ct)[:, None] - wi[None] / eta
+        wiv = np.repeat(wi[None], n, 0)
+        # weight of the transmission lobe for pdf D cos_m: |wi.m| G / (cos_i cos_m) * (1 - F)   (Walter et al. 2007, eq. 41)
+        w = np.where(wim > 0, (1 - F) * wim * _g1(wiv, m, alpha, ggx) * _g1(wo, m, alpha, ggx) / (cos_i * cm), 0.0)
+        ref = w.mean()
+        dat = _cubic_interp(cos_i ** 0.25, ext)  # RoughTransmittance::eval warps cos(theta) with pow(., 1/4), rtrans.h:232-240
+        assert abs(ref - dat) < 4e-3 + 4 * w.std() / np.sqrt(n), (distr, eta, alpha, cos_i, ref, dat)
+    # diffuse transmittance = 2 int_0^1 x T(x) dx (test_rtrans.cpp:44-47) of the same table
+    xs = (np.arange(4000) + 0.5) / 4000
+    num = np.mean([2 * x * _cubic_interp(x ** 0.25, ext) for x in xs])
+    assert abs(num - ed) < 3e-3, (num, ed)
