@@ -722,7 +722,23 @@ static Scene *buildScene(const B200pgSceneDesc *desc) {
     }
     if (desc->n_emitters > 0) cdfNormalize(sc->emitterCdf);
 
-    sc->kd.build(sc->primBoxes);
+    // clipping is on by default (m_clip, gkdtree.h:739): triangles through Triangle::getClippedAABB, other shapes through
+    // Shape::getClippedAABB = bounding box clipped to the cell (shape.cpp)
+    Scene *scp = sc.get();
+    sc->kd.build(sc->primBoxes, [scp](uint32_t prim, const AABB &box) {
+        const TriAccel &ta = scp->triAccel[prim];
+        if (ta.k == KNoTriangleFlag) {
+            AABB r = scp->primBoxes[prim];
+            for (int j = 0; j < 3; ++j) {
+                r.min[j] = std::max(r.min[j], box.min[j]);
+                r.max[j] = std::min(r.max[j], box.max[j]);
+            }
+            return r;
+        }
+        const Shape &s = scp->shapes[ta.shapeIndex];
+        return clippedTriangleAABB(s.positions[s.indices[3 * ta.primIndex]], s.positions[s.indices[3 * ta.primIndex + 1]],
+                                   s.positions[s.indices[3 * ta.primIndex + 2]], box);
+    });
 
     // camera, perspective.cpp:126-155 (no crop window)
     const B200pgSensor &sd = desc->sensor;
@@ -971,6 +987,20 @@ int orc_phase(void *s, int medium, const float *wi, const float *wo, const float
         Vec3 w = M.phaseSample(vi, Vec2(u[2 * i], u[2 * i + 1]), pdf);
         out_wo[3 * i] = w.x; out_wo[3 * i + 1] = w.y; out_wo[3 * i + 2] = w.z;
         out_pdf[i] = pdf;
+    }
+    return 0;
+}
+
+// Triangle::getClippedAABB on one triangle (tri = 9 floats, box = min xyz, max xyz; out = min xyz, max xyz, inverted when
+// the triangle is clipped away): the known-answer vectors of src/tests/test_kd.cpp:34-83
+int orc_clipped_aabb(const float *tri, const float *box, float *out) {
+    AABB b;
+    b.min = Vec3(box[0], box[1], box[2]);
+    b.max = Vec3(box[3], box[4], box[5]);
+    AABB r = clippedTriangleAABB(Vec3(tri[0], tri[1], tri[2]), Vec3(tri[3], tri[4], tri[5]), Vec3(tri[6], tri[7], tri[8]), b);
+    for (int j = 0; j < 3; ++j) {
+        out[j] = r.min[j];
+        out[3 + j] = r.max[j];
     }
     return 0;
 }

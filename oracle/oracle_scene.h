@@ -4,6 +4,7 @@
 // (sahkdtree3.h:178-308), TriAccel (triaccel.h:37-158), rectangle (rectangle.cpp:125-168)
 // and intersection records (skdtree.h:343-428).
 #pragma once
+#include <functional>
 #include <cstdio>
 #include <memory>
 #include <vector>
@@ -175,6 +176,62 @@ inline Float cdfNormalize(std::vector<Float> &cdf) {  // pmf.h:98-112
     return sum;
 }
 
+// Triangle::getClippedAABB (src/libcore/triangle.cpp:69-138): Sutherland-Hodgman clipping of the triangle against the six
+// planes of `box`, in double precision ("the kd-tree code will frequently call this function with almost-collapsed
+// AABBs"), bounds rounded outward (castflt_down / castflt_up), then clipped to the box.
+inline int sutherlandHodgman(const double (*in)[3], int inCount, double (*out)[3], int axis, double splitPos, bool isMinimum) {
+    if (inCount < 3) return 0;
+    double cur[3] = {in[0][0], in[0][1], in[0][2]};
+    const double sign = isMinimum ? 1.0 : -1.0;
+    bool curIsInside = sign * (cur[axis] - splitPos) >= 0;
+    int outCount = 0;
+    for (int i = 0; i < inCount; ++i) {
+        const int nextIdx = i + 1 == inCount ? 0 : i + 1;
+        const double next[3] = {in[nextIdx][0], in[nextIdx][1], in[nextIdx][2]};
+        const bool nextIsInside = sign * (next[axis] - splitPos) >= 0;
+        if (curIsInside && nextIsInside) {
+            for (int c = 0; c < 3; ++c) out[outCount][c] = next[c];
+            ++outCount;
+        } else if (curIsInside != nextIsInside) {
+            const double t = (splitPos - cur[axis]) / (next[axis] - cur[axis]);
+            for (int c = 0; c < 3; ++c) out[outCount][c] = cur[c] + (next[c] - cur[c]) * t;
+            out[outCount][axis] = splitPos;  // avoid roundoff errors
+            ++outCount;
+            if (nextIsInside) {
+                for (int c = 0; c < 3; ++c) out[outCount][c] = next[c];
+                ++outCount;
+            }
+        }
+        for (int c = 0; c < 3; ++c) cur[c] = next[c];
+        curIsInside = nextIsInside;
+    }
+    return outCount;
+}
+inline AABB clippedTriangleAABB(const Vec3 &p0, const Vec3 &p1, const Vec3 &p2, const AABB &box) {
+    double v1[10][3] = {{p0.x, p0.y, p0.z}, {p1.x, p1.y, p1.z}, {p2.x, p2.y, p2.z}}, v2[10][3];
+    int n = 3;
+    for (int axis = 0; axis < 3; ++axis) {
+        n = sutherlandHodgman(v1, n, v2, axis, box.min[axis], true);
+        n = sutherlandHodgman(v2, n, v1, axis, box.max[axis], false);
+    }
+    AABB r;
+    r.reset();
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < 3; ++j) {
+            const double pos = v1[i][j];
+            float lo = (float)pos, hi = (float)pos;
+            if ((double)lo > pos) lo = std::nextafter(lo, -std::numeric_limits<float>::infinity());  // castflt_down
+            if ((double)hi < pos) hi = std::nextafter(hi, std::numeric_limits<float>::infinity());   // castflt_up
+            r.min[j] = std::min(r.min[j], lo);
+            r.max[j] = std::max(r.max[j], hi);
+        }
+    for (int j = 0; j < 3; ++j) {  // AABB::clip
+        r.min[j] = std::max(r.min[j], box.min[j]);
+        r.max[j] = std::min(r.max[j], box.max[j]);
+    }
+    return r;
+}
+
 // ---------------------------------------------------------------------------
 // kd-tree: 8-byte nodes (gkdtree.h:452-582): leaf = {start|0x80000000, end};
 // inner = {(leftOffset << 2) | axis, split}; children adjacent (right = left + 1).
@@ -207,8 +264,12 @@ public:
     std::vector<uint32_t> indices;
     AABB aabb, tightAABB;
 
-    void build(const std::vector<AABB> &primBoxes) {
-        boxes = &primBoxes;
+    // clip(prim, box) = bounds of the part of primitive `prim` inside `box` (Triangle::getClippedAABB for triangles,
+    // AABB intersection for other shapes, Shape::getClippedAABB); null = no clipping (m_clip = false)
+    typedef std::function<AABB(uint32_t, const AABB &)> ClipFn;
+
+    void build(const std::vector<AABB> &primBoxes, const ClipFn &clip = nullptr) {
+        clipFn = clip;
         uint32_t n = (uint32_t)primBoxes.size();
         aabb.reset();
         for (uint32_t i = 0; i < n; ++i) aabb.expandBy(primBoxes[i]);
@@ -222,18 +283,24 @@ public:
         nodes.clear();
         indices.clear();
         nodes.push_back(KDNode());
-        std::vector<uint32_t> all(n);
-        for (uint32_t i = 0; i < n; ++i) all[i] = i;
-        buildNode(0, all, aabb, 0, 0);
+        std::vector<Item> all(n);
+        for (uint32_t i = 0; i < n; ++i) all[i] = Item{i, primBoxes[i]};
+        buildNode(0, all, aabb, 0, 0, false);
         // enlarge after the build (gkdtree.h:1214-1219)
         const Float eps = 1e-3f;
         aabb.min = aabb.min - ((aabb.max - aabb.min) * eps + Vec3(eps));
         aabb.max = aabb.max + ((aabb.max - aabb.min) * eps + Vec3(eps));
-        boxes = nullptr;
+        clipFn = nullptr;
     }
 
+    uint64_t prunedPrims = 0;  // references removed by clipping ("perfect splits")
+
 private:
-    const std::vector<AABB> *boxes = nullptr;
+    ClipFn clipFn;
+    struct Item {
+        uint32_t prim;
+        AABB box;  // bounds of the primitive inside the node it currently belongs to
+    };
 
     struct Event {
         Float pos;
@@ -241,11 +308,14 @@ private:
         bool operator<(const Event &o) const { return pos < o.pos || (pos == o.pos && type < o.type); }
     };
 
-    void makeLeaf(uint32_t nodeIdx, const std::vector<uint32_t> &prims) {
+    void makeLeaf(uint32_t nodeIdx, const std::vector<Item> &prims) {
         KDNode &nd = nodes[nodeIdx];
         nd.a = 0x80000000u | (uint32_t)indices.size();
-        indices.insert(indices.end(), prims.begin(), prims.end());
+        for (const Item &it : prims) indices.push_back(it.prim);
         nd.end = (uint32_t)indices.size();
+    }
+    static bool usable(const AABB &b) {  // isValid() && getSurfaceArea() > 0 (gkdtree.h:1563-1564, 2228)
+        return b.min.x <= b.max.x && b.min.y <= b.max.y && b.min.z <= b.max.z && b.surfaceArea() > 0;
     }
 
     inline Float sahCost(const AABB &box, int axis, Float split, uint32_t nL, uint32_t nR) const {
@@ -261,7 +331,7 @@ private:
         return cost;
     }
 
-    void buildNode(uint32_t nodeIdx, std::vector<uint32_t> &prims, const AABB &box, int depth, uint32_t badRefines) {
+    void buildNode(uint32_t nodeIdx, std::vector<Item> &prims, const AABB &box, int depth, uint32_t badRefines, bool exactStage) {
         uint32_t n = (uint32_t)prims.size();
         if (n <= stopPrims || depth >= maxDepth) {  // gkdtree.h:1797-1800
             makeLeaf(nodeIdx, prims);
@@ -270,12 +340,31 @@ private:
         Float bestCost = std::numeric_limits<Float>::infinity(), bestSplit = 0;
         int bestAxis = -1;
         bool bestPlanarLeft = true;
+        const bool exact = n <= exactPrimThreshold;
 
-        if (n > exactPrimThreshold) {
+        if (exact && !exactStage && clipFn) {
+            // passing from min-max binning to the O(n log n) builder: clip every primitive to the node (createEventList,
+            // gkdtree.h:1551-1592); primitives whose clipped bounds are invalid or have no area drop out
+            std::vector<Item> kept;
+            kept.reserve(n);
+            for (const Item &it : prims) {
+                AABB c = clipFn(it.prim, box);
+                if (usable(c)) kept.push_back(Item{it.prim, c});
+                else ++prunedPrims;
+            }
+            prims.swap(kept);
+            n = (uint32_t)prims.size();
+            if (n <= stopPrims) {
+                makeLeaf(nodeIdx, prims);
+                return;
+            }
+        }
+
+        if (!exact) {
             // min-max binning (gkdtree.h:1792-1925): bins over the tight bounds of the node
             AABB tight;
-            for (uint32_t p : prims) {
-                const AABB &b = (*boxes)[p];
+            for (const Item &it : prims) {
+                const AABB &b = it.box;
                 for (int i = 0; i < 3; ++i) {
                     tight.min[i] = std::min(tight.min[i], std::max(b.min[i], box.min[i]));
                     tight.max[i] = std::max(tight.max[i], std::min(b.max[i], box.max[i]));
@@ -288,8 +377,8 @@ private:
                 std::fill(minBins.begin(), minBins.end(), 0u);
                 std::fill(maxBins.begin(), maxBins.end(), 0u);
                 Float invBin = (Float)minMaxBins / (hi - lo);
-                for (uint32_t p : prims) {
-                    const AABB &b = (*boxes)[p];
+                for (const Item &it : prims) {
+                    const AABB &b = it.box;
                     int i0 = std::min((int)minMaxBins - 1, std::max(0, (int)((std::max(b.min[axis], lo) - lo) * invBin)));
                     int i1 = std::min((int)minMaxBins - 1, std::max(0, (int)((std::min(b.max[axis], hi) - lo) * invBin)));
                     minBins[i0]++;
@@ -316,8 +405,8 @@ private:
             ev.reserve(2 * n);
             for (int axis = 0; axis < 3; ++axis) {
                 ev.clear();
-                for (uint32_t p : prims) {
-                    const AABB &b = (*boxes)[p];
+                for (const Item &it : prims) {
+                    const AABB &b = it.box;
                     Float lo = std::max(b.min[axis], box.min[axis]), hi = std::min(b.max[axis], box.max[axis]);
                     if (lo == hi) {
                         ev.push_back({lo, 1});
@@ -364,35 +453,42 @@ private:
             ++badRefines;
         }
 
-        std::vector<uint32_t> left, right;
-        for (uint32_t p : prims) {
-            const AABB &b = (*boxes)[p];
+        AABB lb = box, rb = box;
+        lb.max[bestAxis] = bestSplit;
+        rb.min[bestAxis] = bestSplit;
+        std::vector<Item> left, right;
+        for (const Item &it : prims) {
+            const AABB &b = it.box;
             Float lo = std::max(b.min[bestAxis], box.min[bestAxis]), hi = std::min(b.max[bestAxis], box.max[bestAxis]);
             if (lo == hi && lo == bestSplit) {
-                (bestPlanarLeft ? left : right).push_back(p);
-            } else {
-                if (lo < bestSplit) left.push_back(p);
-                if (hi > bestSplit) right.push_back(p);
-                if (lo >= bestSplit && hi <= bestSplit && !(lo == hi && lo == bestSplit)) {
-                    // degenerate sliver exactly on the plane handled above; nothing else can land here
+                (bestPlanarLeft ? left : right).push_back(it);
+            } else if (lo < bestSplit && hi > bestSplit) {
+                // the primitive overlaps the split plane: re-clip for each side ("perfect splits", gkdtree.h:2218-2265)
+                if (exact && clipFn) {
+                    AABB cl = clipFn(it.prim, lb), cr = clipFn(it.prim, rb);
+                    if (usable(cl)) left.push_back(Item{it.prim, cl}); else ++prunedPrims;
+                    if (usable(cr)) right.push_back(Item{it.prim, cr}); else ++prunedPrims;
+                } else {
+                    left.push_back(it);
+                    right.push_back(it);
                 }
+            } else {
+                if (lo < bestSplit) left.push_back(it);
+                if (hi > bestSplit) right.push_back(it);
             }
         }
         if (left.size() == n && right.size() == n) {  // no progress at all
             makeLeaf(nodeIdx, prims);
             return;
         }
-        std::vector<uint32_t>().swap(prims);
+        std::vector<Item>().swap(prims);
         uint32_t leftIdx = (uint32_t)nodes.size();
         nodes.push_back(KDNode());
         nodes.push_back(KDNode());
         nodes[nodeIdx].a = ((leftIdx - nodeIdx) << 2) | (uint32_t)bestAxis;
         nodes[nodeIdx].split = bestSplit;
-        AABB lb = box, rb = box;
-        lb.max[bestAxis] = bestSplit;
-        rb.min[bestAxis] = bestSplit;
-        buildNode(leftIdx, left, lb, depth + 1, badRefines);
-        buildNode(leftIdx + 1, right, rb, depth + 1, badRefines);
+        buildNode(leftIdx, left, lb, depth + 1, badRefines, exact);
+        buildNode(leftIdx + 1, right, rb, depth + 1, badRefines, exact);
     }
 };
 

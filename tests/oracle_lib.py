@@ -37,6 +37,7 @@ class Oracle:
         L.orc_bsdf.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_size_t, fp, fp, fp, fp, fp, u32p]
         L.orc_radiance.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), u32p, u32p, C.c_size_t, fp, C.c_void_p, C.c_void_p]
         L.orc_film_splat.argtypes = [C.c_void_p, fp, fp, C.c_size_t, fp]
+        L.orc_clipped_aabb.argtypes = [fp, fp, fp]
         L.orc_grid_lookup.argtypes = [C.c_void_p, C.c_int, fp, C.c_size_t, fp]
         L.orc_medium_sample.argtypes = [C.c_void_p, C.c_int, fp, C.c_size_t, fp, fp, fp, fp]
         L.orc_phase.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_size_t, fp, fp, fp]
@@ -68,6 +69,13 @@ class Oracle:
         return self.lib.orc_num_threads()
 
     # ---- rough transmittance tables
+    def clipped_aabb(self, tri, box_min, box_max):
+        t = np.ascontiguousarray(tri, np.float32).ravel()
+        b = np.ascontiguousarray(list(box_min) + list(box_max), np.float32)
+        out = np.zeros(6, np.float32)
+        self.lib.orc_clipped_aabb(_f(t), _f(b), _f(out))
+        return out[:3], out[3:]
+
     def rtrans_reduce(self, table, eta, alpha):
         """table: dict from b200pg.rtrans.load_packed / load_dat (raw floats in file order)."""
         ext = np.zeros(table["thetaN"], np.float32)

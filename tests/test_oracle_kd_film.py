@@ -123,3 +123,19 @@ def test_render_is_deterministic_and_partitionable(pkg, oracle):
     c, _ = sc.render(p, 1, 1, film=c)
     np.testing.assert_allclose(a, c, rtol=1e-5, atol=1e-5)
     assert sa["paths"] == 64 * 64 * 2 and 1.0 <= sa["path_length_sum"] / sa["paths"] <= 5.0
+
+
+def test_triangle_clipping_known_answers(oracle):
+    """test01_sutherlandHodgman of the reference (src/tests/test_kd.cpp:34-83): Triangle::getClippedAABB on the unit
+    triangle -- the vectors the kd-tree's "perfect splits" rely on."""
+    tri = [(0, 0, 0), (1, 0, 0), (1, 1, 0)]
+    lo, hi = oracle.clipped_aabb(tri, (0, .5, -1), (1, 1, 1))          # split the triangle in half
+    assert tuple(lo) == (.5, .5, 0) and tuple(hi) == (1, 1, 0)
+    lo, hi = oracle.clipped_aabb(tri, (2, 2, 2), (3, 3, 3))            # completely clipped away
+    assert not (lo <= hi).all()
+    lo, hi = oracle.clipped_aabb(tri, (-1, -1, -1), (1, 1, 1))         # box contains the triangle: no clipping
+    assert tuple(lo) == (0, 0, 0) and tuple(hi) == (1, 1, 0)
+    lo, hi = oracle.clipped_aabb(tri, (-100, -100, 0), (100, 100, 0))  # triangle within a flat cell is kept
+    assert tuple(lo) == (0, 0, 0) and tuple(hi) == (1, 1, 0)
+    lo, hi = oracle.clipped_aabb(tri, (0, 1, 0), (1, 2, 0))            # just touching: collapsed point AABB
+    assert tuple(lo) == (1, 1, 0) and tuple(hi) == (1, 1, 0)
