@@ -353,6 +353,26 @@ def main():
                                       "and the algorithmic figure may exceed the HBM peak; queue_only_gbs counts the ray/hit "
                                       "records that do stream through HBM"}}
 
+    # ---- extra figure: rendering with the trained field, no recording and no training update (what a long guided render
+    # does once the training progressions are over); same brackets as the main figure
+    render_only = None
+    if guided:
+        integ.guiding_mode(False, True)
+        barrier()
+        r0 = integ.stats()
+        tr0 = time.perf_counter()
+        for k in range(args.steps):
+            integ.progression((20_000_000 + k * world + rank) * spp, spp)
+        barrier()
+        rdt = time.perf_counter() - tr0
+        if world > 1:
+            tt = torch.tensor([rdt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            rdt = float(tt.item())
+        r1 = integ.stats()
+        render_only = {"value": (r1["paths"] - r0["paths"]) * world / rdt / 1e6, "unit": "Mpaths/s", "ms_per_step": 1e3 * rdt / args.steps,
+                       "what": "guided rendering with the trained field, no training"}
+
     # ---- end-to-end through the C-ABI with host buffers: scene H2D + render + film D2H every step
     barrier()
     host_film = torch.empty((sb.height, sb.width, 5), dtype=torch.float32, pin_memory=True).numpy()  # pinned host buffer
@@ -438,7 +458,7 @@ def main():
             "mrays_per_sec": rays / wall / 1e6,
             "gpu_launches": int(launches),
             "clocks": clocks.summary(t_start, t_e2e_end),
-            "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
+            "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "render_only": render_only,
         }
         print(json.dumps(line))
     if world > 1:
