@@ -325,9 +325,29 @@ struct Loader {
         if (!p) return false;
         if (p->tag != "rgb" && p->tag != "spectrum" && p->tag != "srgb")
             fail(std::string("property \"") + name + "\" must be <rgb> or <spectrum>");
-        if (p->tag == "srgb") fail("<srgb> values are not supported, use linear <rgb>");
         if (p->has("filename")) fail("<spectrum filename=...> is not supported");
         std::string v = p->get("value");
+        if (p->tag == "srgb") {  // scenehandler.cpp:505-531, Spectrum::fromSRGB (spectrum.cpp:402-421)
+            auto tk = tokenize(v, ", ");
+            float c[3];
+            if (tk.size() == 1 && tk[0].size() == 7 && tk[0][0] == '#') {
+                char *end = nullptr;
+                const long enc = std::strtol(tk[0].c_str() + 1, &end, 16);
+                if (*end != '\0') fail(std::string("Invalid sRGB value specified (in <") + name + ">)");
+                c[0] = ((enc & 0xFF0000) >> 16) / 255.0f;
+                c[1] = ((enc & 0x00FF00) >> 8) / 255.0f;
+                c[2] = (enc & 0x0000FF) / 255.0f;
+            } else if (tk.size() == 1) {
+                c[0] = c[1] = c[2] = toFloat(*p, tk[0]);
+            } else if (tk.size() == 3) {
+                for (int i = 0; i < 3; ++i) c[i] = toFloat(*p, tk[i]);
+            } else {
+                fail("Invalid sRGB value specified");
+            }
+            for (int i = 0; i < 3; ++i)
+                out[i] = c[i] <= 0.04045f ? c[i] * (float)(1.0 / 12.92) : std::pow((c[i] + 0.055f) * (float)(1.0 / 1.055), 2.4f);
+            return true;
+        }
         if (v.find(':') != std::string::npos) fail("wavelength:value spectra are not supported in RGB mode here");
         auto tok = tokenize(v, ", ");
         if (tok.size() == 1) {
@@ -1138,11 +1158,10 @@ struct Loader {
         }
     }
 
-    void parseScene(const XmlNode &root) {
-        if (root.tag != "scene") fail("the root element must be <scene>");
-        if (!root.has("version")) fail("The scene is missing a version attribute!");  // scenehandler.cpp:228-233
-        b200pg_integrator_params_default(&H.xmlParams);
-        bool haveSensor = false;
+    bool haveSensor = false;
+    int includeDepth = 0;
+
+    void parseChildren(const XmlNode &root) {
         for (auto &c : root.children) {
             if (c->tag == "default") continue;
             if (c->tag == "integrator") parseIntegrator(*c);
@@ -1151,11 +1170,46 @@ struct Loader {
             else if (c->tag == "medium") parseMedium(*c);
             else if (c->tag == "shape") parseShape(*c);
             else if (c->tag == "emitter") fail("emitter plugin \"" + c->get("type") + "\" is not on the accelerated path (area lights attached to shapes only)");
-            else if (c->tag == "include") fail("<include> is not supported");
-            else if (c->tag == "texture" || c->tag == "subsurface" || c->tag == "phase" || c->tag == "volume")
+            else if (c->tag == "include") {
+                // scenehandler.cpp:658-682: the included file is a <scene> of its own; its objects (and ids) join this scene
+                std::string fn = c->get("filename");
+                if (fn.empty()) fail("<include>: missing filename");
+                if (fn[0] != '/') fn = baseDir + "/" + fn;
+                if (++includeDepth > 16) fail("<include>: nesting too deep (cycle?)");
+                std::ifstream f(fn);
+                if (!f) fail("<include>: cannot open \"" + fn + "\"");
+                std::stringstream ss;
+                ss << f.rdbuf();
+                const std::string text = ss.str();
+                XmlParser parser(text);
+                std::unique_ptr<XmlNode> inc = parser.parse();
+                if (inc->tag != "scene") fail("<include>: the root element of \"" + fn + "\" must be <scene>");
+                const std::string saved = baseDir;
+                const size_t slash = fn.find_last_of('/');
+                baseDir = slash == std::string::npos ? "." : fn.substr(0, slash);
+                substAll(*inc);
+                parseChildren(*inc);
+                baseDir = saved;
+                --includeDepth;
+            } else if (c->tag == "alias") {
+                // scenehandler.cpp:646-656
+                const std::string id = c->get("id"), as = c->get("as");
+                if (bsdfIds.count(as) || mediumIds.count(as)) fail("Duplicate ID '" + id + "' used in scene description!");
+                if (bsdfIds.count(id)) bsdfIds[as] = bsdfIds[id];
+                else if (mediumIds.count(id)) mediumIds[as] = mediumIds[id];
+                else fail("Referenced object '" + id + "' not found!");
+            } else if (c->tag == "texture" || c->tag == "subsurface" || c->tag == "phase" || c->tag == "volume")
                 fail("top-level <" + c->tag + "> objects are not supported");
             else fail("unexpected tag <" + c->tag + ">");
         }
+    }
+
+    void parseScene(const XmlNode &root) {
+        if (root.tag != "scene") fail("the root element must be <scene>");
+        if (!root.has("version")) fail("The scene is missing a version attribute!");  // scenehandler.cpp:228-233
+        b200pg_integrator_params_default(&H.xmlParams);
+        haveSensor = false;
+        parseChildren(root);
         if (!haveSensor) fail("the scene needs a perspective <sensor> (the reference's default sensor fallback, scene.cpp:272-312, is not replicated)");
     }
 };

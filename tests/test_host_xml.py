@@ -220,3 +220,33 @@ def test_meshes_without_normals_get_smooth_normals_and_ply_loads(api, pkg, tmp_p
         np.testing.assert_allclose(np.ctypeslib.as_array(d4.shapes[0].normals, (len(P) * 3,)).reshape(-1, 3), -want[order], atol=2e-6)
     with pytest.raises(api.B200pgError, match="ply"):
         api.Scene.load_xml(_mesh_xml(tmp_path, body % ("ply", "missing.ply", "")))
+
+
+def test_include_alias_and_srgb(api, tmp_path):
+    """scenehandler.cpp: <include> (:658-682), <alias> (:646-656), <srgb> (:505-531 + Spectrum::fromSRGB)."""
+    (tmp_path / "sub").mkdir()
+    (tmp_path / "sub" / "materials.xml").write_text(
+        '<scene version="0.6.0"><bsdf type="diffuse" id="red"><srgb name="reflectance" value="#ff8000"/></bsdf>'
+        '<bsdf type="diffuse" id="grey"><srgb name="reflectance" value="0.5"/></bsdf><alias id="red" as="wall"/></scene>')
+    body = '''<include filename="sub/materials.xml"/>
+    <shape type="rectangle"><ref id="wall"/></shape>
+    <shape type="rectangle"><transform name="toWorld"><translate x="3"/></transform><ref id="grey"/></shape>
+    <shape type="rectangle"><transform name="toWorld"><translate y="3"/></transform><emitter type="area"><rgb name="radiance" value="1"/></emitter></shape>'''
+    path = tmp_path / "inc.xml"
+    path.write_text(_scene(body).replace("$spp", "4"))
+    sc = api.Scene.load_xml(str(path))
+    d = sc.desc
+    dec = lambda c: c / 12.92 if c <= 0.04045 else ((c + 0.055) / 1.055) ** 2.4
+    red = d.bsdfs[d.shapes[0].bsdf]
+    np.testing.assert_allclose(list(red.reflectance), [dec(1.0), dec(128 / 255), dec(0.0)], rtol=1e-6)
+    grey = d.bsdfs[d.shapes[1].bsdf]
+    np.testing.assert_allclose(list(grey.reflectance), [dec(0.5)] * 3, rtol=1e-6)
+    assert d.shapes[0].bsdf != d.shapes[1].bsdf
+    bad = tmp_path / "bad_alias.xml"
+    bad.write_text(_scene('<alias id="nope" as="x"/>' + body).replace("$spp", "4"))
+    with pytest.raises(api.B200pgError, match="not found"):
+        api.Scene.load_xml(str(bad))
+    bad2 = tmp_path / "bad_inc.xml"
+    bad2.write_text(_scene('<include filename="missing.xml"/>' + body).replace("$spp", "4"))
+    with pytest.raises(api.B200pgError, match="include"):
+        api.Scene.load_xml(str(bad2))
