@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--no-guiding", action="store_true")
     ap.add_argument("--guided-distance", action="store_true", help="medium workloads: guided free-flight sampling")
     ap.add_argument("--nccl-allreduce", action="store_true", help="sum EM statistics with torch.distributed/NCCL instead of the fused peer-memory kernel")
+    ap.add_argument("--sort-bounces", type=int, default=-1, help="coherence sort of the shade queue by guiding cell on bounces 1..n (0 = off, -1 = library default)")
     ap.add_argument("--ref-seconds", type=float, default=3.0)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU leg (profiling runs)")
@@ -204,6 +205,8 @@ def main():
     p = guided_params(pkg, args)
     guided = bool(p.guiding)
     integ = api.Integrator(scene, p, device=local)
+    if args.sort_bounces >= 0:
+        integ.set_option("sort_bounces", args.sort_bounces)
     spp = args.spp_per_step
     npix = sb.width * sb.height
 

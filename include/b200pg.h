@@ -262,7 +262,10 @@ void b200pg_destroy(void *integ);
 /* Measurement helpers (no reference counterpart; the reference only logs "Progression[i] took t s",
  * progressiveintegrator.cpp:314-317).
  *   options: "count_traversal" (0/1: counting variant of the trace kernels fills bvh_nodes_visited /
- *            prims_tested), "timing" (0/1: per-stage CUDA events).
+ *            prims_tested), "timing" (0/1: per-stage CUDA events), "sort_bounces" (n: guided surface progressions
+ *            shade bounces 1..n through a permutation that groups the queued paths by guiding cell; 0 = queue order;
+ *            default 0, or the value of the environment variable
+ *            B200PG_SORT_BOUNCES; per-path results do not depend on it).
  *   stage times: 5 doubles / 5 launch counts = trace(closest), shade, shadow(any-hit), film, train.
  *   scene_upload: re-sends the compiled scene host->device (bench.py's end-to-end leg). */
 int b200pg_set_option(void *integ, const char *name, int value);
@@ -323,6 +326,14 @@ int b200pg_k_bin_samples(void *integ, const float *pos, size_t n, uint32_t *out_
  * b200pg_stats().guide_cells * (4K+8) floats (pass NULL when they are not needed). */
 int b200pg_k_em_step(void *integ, const float *pos, const float *dir, const float *weight, const float *pdf,
                      const float *dist, size_t n, int n_iter, float *stats_out);
+/* Microbenchmark of the statistics exchange alone (SURVEY.md 8d, config C5 "EM allreduce scaling"): n_iter launches of the
+ * fused cross-GPU sum + M-step kernel over n_cells synthetic cells (K = the integrator's guide_max_components), after 3
+ * warm-up launches; *ms_per_iter = average device time (CUDA events). Every connected rank must make the same call (the
+ * kernel contains the cross-GPU barriers). mode 0: as b200pg_train runs it (form chosen by size); 1: this rank's own
+ * buffer only (the M-step share); 2: all-read form (every rank reads every peer's buffer); 3: reduce-scatter +
+ * all-gather form (every rank sums its slice of the cells and pushes the sums). Requires b200pg_comm_connect (world = 1
+ * is allowed). The guiding field itself is not touched. */
+int b200pg_k_em_exchange(void *integ, uint32_t n_cells, int n_iter, int mode, float *ms_per_iter);
 /* Field snapshot as 32-bit words: header[8] = {'GUID', nNodes, nCells, K, 0...}, nodes[4*nNodes] = {axis (3 = leaf),
  * split, left | cell, 0}, cell headers[8*nCells] = {running sample count, running weight sum, 0...}, lobes[12*nCells*K] =
  * {pi, mu.xyz, kappa, norm, exp(-2 kappa), 0, S, R.xyz}. Pass out = NULL to query the size. */

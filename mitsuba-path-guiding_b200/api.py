@@ -77,6 +77,7 @@ def lib():
     L.b200pg_comm_connect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.b200pg_field_snapshot.argtypes = [C.c_void_p, u32p, C.POINTER(C.c_size_t)]
     L.b200pg_field_load.argtypes = [C.c_void_p, u32p, C.c_size_t]
+    L.b200pg_k_em_exchange.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_float)]
     _lib = L
     return L
 
@@ -286,6 +287,13 @@ class Integrator:
         assert len(handles) == 64 * world
         buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
         _check(lib().b200pg_comm_connect(self.h, rank, world, buf))
+
+    def em_exchange_bench(self, n_cells, n_iter=20, mode=0):
+        """Average ms per fused statistics sum + M-step launch over n_cells synthetic cells (b200pg_k_em_exchange);
+        mode 0 = as trained, 1 = local M-step only, 2 = all-read form, 3 = reduce-scatter + all-gather form."""
+        ms = C.c_float(0)
+        _check(lib().b200pg_k_em_exchange(self.h, n_cells, n_iter, int(mode), C.byref(ms)))
+        return ms.value
 
     def field_snapshot(self):
         n = C.c_size_t(0)

@@ -13,6 +13,7 @@
 // This is the repo's own algorithm (no guiding code exists in the reference snapshot); the CPU
 // statement it is tested against is oracle/oracle_guiding.h.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -602,34 +603,65 @@ __global__ void __launch_bounds__(256) k_mstep(float4 *__restrict__ lobes, float
 // peers' E-step results, read straight from their HBM over NVLink, (4) M-step. The statistics buffers are
 // double-buffered by iteration parity, so no second barrier is needed: a rank can overwrite buffer b only after
 // passing the barrier of the next iteration, which every peer reaches only after it finished reading buffer b.
+//
+// Large fields (cv.twoPhase): every rank reading every peer's whole buffer moves (world-1) x B bytes per rank. Instead,
+// rank r sums only ITS slice of the cells (reads (world-1)/world x B) and pushes the sums into every rank's `sum`
+// region (writes (world-1)/world x B), a second barrier follows, and the M-step reads the local `sum` region: the
+// traffic of a reduce-scatter + all-gather, still one kernel and still bit-identical everywhere (every cell is summed
+// by exactly one rank, in rank order).
+// Exchange block of a rank: {buf0, buf1, sum: bufFloats floats each; 64 flags: [0,16) barrier 1, [16,32) barrier 2,
+// [48] block counter of the intra-GPU grid barrier, [63] spare slot of the local-only microbenchmark}.
 struct CommView {
     float *const *peers;   // world pointers to the ranks' exchange blocks
     int rank, world;
+    int flagSlot;          // arrival slot this rank signals in (= rank; the local-only microbenchmark uses a spare slot)
     uint32_t epoch;        // arrival value of this iteration (monotonic)
     size_t bufFloats;      // floats per statistics buffer
     int buf;               // which of the two buffers this iteration uses
+    int twoPhase;
     uint32_t *error;       // set when the wait timed out (a peer never arrived)
 };
+static constexpr int kExchangeThreads = 1024;  // one block per SM (all blocks must be resident while they wait)
 __device__ __forceinline__ uint32_t *commFlags(float *block, size_t bufFloats) {
-    return reinterpret_cast<uint32_t *>(block + 2 * bufFloats);
+    return reinterpret_cast<uint32_t *>(block + 3 * bufFloats);
 }
-__device__ __forceinline__ float ldPeer(const float *p) {  // system-scope load that bypasses the (non-coherent) L1
-    float v;
-    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+__device__ __forceinline__ float4 ldPeer4(const float *p) {  // system-scope load that bypasses the (non-coherent) L1
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
     return v;
 }
-
-__global__ void __launch_bounds__(256) k_mstep_allreduce(CommView cv, float4 *__restrict__ lobes, float4 *__restrict__ lobeStats,
-                                                         float *__restrict__ stats, uint32_t nCells, int K, int stride, int commit) {
-    // ---- barrier: every block signals/waits on its own (the flag rows are written once per rank and iteration by
-    // block 0; all blocks poll the same local row)
-    if (blockIdx.x == 0 && (int)threadIdx.x < cv.world) {
+__device__ __forceinline__ void stPeer4(float *p, float4 v) {
+    asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// Sum of one float4 of statistics over n source blocks in source order; loads are issued four at a time.
+__device__ __forceinline__ float4 sumSources(float *const *src, int n, size_t ofs) {
+    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    for (int r = 0; r < n; r += 4) {
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (r + j < n) v[j] = ldPeer4(src[r + j] + ofs);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (r + j < n) {
+                acc.x += v[j].x;
+                acc.y += v[j].y;
+                acc.z += v[j].z;
+                acc.w += v[j].w;
+            }
+    }
+    return acc;
+}
+// Cross-GPU barrier: block 0 signals `epoch` in slot (base + flagSlot) of every peer's flag row, every block waits until
+// all `world` slots of the local row have reached it.
+__device__ __forceinline__ void commBarrier(const CommView &cv, int slotBase, bool signal) {
+    if (signal && (int)threadIdx.x < cv.world) {
         __threadfence_system();
-        uint32_t *peerRow = commFlags(cv.peers[threadIdx.x], cv.bufFloats) + cv.rank;
+        uint32_t *peerRow = commFlags(cv.peers[threadIdx.x], cv.bufFloats) + slotBase + cv.flagSlot;
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peerRow), "r"(cv.epoch) : "memory");
     }
     if ((int)threadIdx.x < cv.world) {
-        const uint32_t *mine = commFlags(cv.peers[cv.rank], cv.bufFloats) + threadIdx.x;
+        const uint32_t *mine = commFlags(cv.peers[cv.rank], cv.bufFloats) + slotBase + threadIdx.x;
         const long long t0 = clock64();
         uint32_t v;
         do {
@@ -642,18 +674,53 @@ __global__ void __launch_bounds__(256) k_mstep_allreduce(CommView cv, float4 *__
         } while (true);
     }
     __syncthreads();
+}
+
+__global__ void __launch_bounds__(kExchangeThreads) k_mstep_allreduce(CommView cv, float4 *__restrict__ lobes,
+                                                                       float4 *__restrict__ lobeStats, float *__restrict__ stats,
+                                                                       uint32_t nCells, int K, int stride, int commit) {
+    __shared__ float *sSrc[16];
+    __shared__ int sLast;
+    commBarrier(cv, 0, blockIdx.x == 0);
 
     const uint32_t warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = (gridDim.x * blockDim.x) >> 5;
     const int k = (int)lane();
     const size_t bufOfs = (size_t)cv.buf * cv.bufFloats;
-    for (uint32_t c = warpGlobal; c < nCells; c += nWarps) {
-        // sum over ranks, element e = lane, lane + 32, ... of the cell's `stride` statistics
-        float *own = stats + (size_t)c * stride;
-        for (int e = k; e < stride; e += 32) {
-            float acc = 0.0f;
-            for (int r = 0; r < cv.world; ++r) acc += ldPeer(cv.peers[r] + bufOfs + (size_t)c * stride + e);
-            own[e] = acc;
+    int nSrc = cv.world;
+    if ((int)threadIdx.x < cv.world) sSrc[threadIdx.x] = cv.peers[threadIdx.x] + bufOfs;
+    __syncthreads();
+    if (cv.twoPhase) {
+        // ---- reduce-scatter + all-gather: this rank's slice of the cells, summed once and pushed to every rank
+        const uint32_t per = (nCells + (uint32_t)cv.world - 1u) / (uint32_t)cv.world;
+        const uint32_t c0 = min(nCells, per * (uint32_t)cv.rank), c1 = min(nCells, c0 + per);
+        const size_t sumOfs = 2 * cv.bufFloats;
+        for (uint32_t c = c0 + warpGlobal; c < c1; c += nWarps)
+            for (int e = k; e < (stride >> 2); e += 32) {
+                const size_t o = (size_t)c * stride + 4 * e;
+                const float4 acc = sumSources(sSrc, cv.world, o);
+                for (int r = 0; r < cv.world; ++r) stPeer4(cv.peers[r] + sumOfs + o, acc);
+            }
+        // intra-GPU grid barrier (every block's pushes are out), then the second cross-GPU barrier
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            uint32_t *gridDone = commFlags(cv.peers[cv.rank], cv.bufFloats) + 48;
+            const uint32_t prev = atomicAdd(gridDone, 1u);
+            sLast = prev == gridDim.x - 1;
+            if (sLast) atomicExch(gridDone, 0u);
         }
+        __syncthreads();
+        commBarrier(cv, 16, sLast != 0);
+        if (threadIdx.x == 0) sSrc[0] = cv.peers[cv.rank] + sumOfs;
+        __syncthreads();
+        nSrc = 1;
+    }
+    for (uint32_t c = warpGlobal; c < nCells; c += nWarps) {
+        // sum over the sources, float4 e = lane, lane + 32, ... of the cell's `stride` statistics
+        // (16-byte accesses: stride = 4K + 8 is a multiple of 4 floats and the buffers are 256-byte aligned)
+        float *own = stats + (size_t)c * stride;
+        for (int e = k; e < (stride >> 2); e += 32)
+            reinterpret_cast<float4 *>(own)[e] = sumSources(sSrc, nSrc, (size_t)c * stride + 4 * e);
         __syncwarp();
         const float *st = own;
         float4 a = make_float4(0, 0, 0, 0), b = a, s = a;
@@ -1058,15 +1125,14 @@ void GuidingHost::train(int nIter) {
             cv.peers = dCommPeers.p;
             cv.rank = commRank;
             cv.world = commWorld;
+            cv.flagSlot = commRank;
             cv.epoch = ++commEpoch;
             cv.bufFloats = commFloats;
             cv.buf = buf;
+            cv.twoPhase = exchangeTwoPhase(numCells()) ? 1 : 0;
             cv.error = dCommError.p;
-            int sms = 148;
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-            // every block of the grid must be resident while it waits for the peers: at most one block per SM
-            const int grid = (int)std::max<size_t>(1, std::min<size_t>(((size_t)numCells() * 32 + 255) / 256, (size_t)sms));
-            k_mstep_allreduce<<<grid, 256, 0, stream>>>(cv, dLobes.p, dLobeStats.p, dStats.p, numCells(), K, stride, commit ? 1 : 0);
+            k_mstep_allreduce<<<exchangeGrid(numCells()), kExchangeThreads, 0, stream>>>(cv, dLobes.p, dLobeStats.p, dStats.p, numCells(), K,
+                                                                                       stride, commit ? 1 : 0);
             launches++;
         } else {  // single GPU: the per-cell sum of the partials is folded into the M-step kernel
             estepOnly();
@@ -1084,10 +1150,24 @@ void GuidingHost::train(int nIter) {
     end();
 }
 
+// every block of the exchange grid must be resident while it waits for the peers: at most one block per SM
+int GuidingHost::exchangeGrid(uint32_t cells) const {
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (int)std::max<size_t>(1, std::min<size_t>(((size_t)cells * 32 + kExchangeThreads - 1) / kExchangeThreads, (size_t)sms));
+}
+// reduce-scatter + all-gather form once the all-read form would pull more than 1 MB from the peers (measured cross-over,
+// tools/em_exchange_bench.py); depends only on numbers every rank shares
+bool GuidingHost::exchangeTwoPhase(uint32_t cells) const {
+    if (commForceMode >= 0) return commForceMode != 0 && commWorld > 1;
+    return commWorld > 1 && (size_t)cells * statsStride() * sizeof(float) * (size_t)(commWorld - 1) > ((size_t)1 << 20);
+}
+
 void GuidingHost::commLocalHandle(void *out64) {
     if (!commBlock) {
         commFloats = kCommMaxCells * statsStride();
-        const size_t bytes = 2 * commFloats * sizeof(float) + 64 * sizeof(uint32_t);
+        const size_t bytes = 3 * commFloats * sizeof(float) + 64 * sizeof(uint32_t);  // {buf0, buf1, sum, flags}
         CUDA_OK(cudaMalloc(&commBlock, bytes));
         CUDA_OK(cudaMemset(commBlock, 0, bytes));
     }
@@ -1114,10 +1194,71 @@ void GuidingHost::commConnect(int rank, int world, const void *handles) {
     commRank = rank;
     commWorld = world;
     commEpoch = 0;
+    if (const char *e = std::getenv("B200PG_EXCHANGE_FORM")) commForceMode = std::atoi(e);  // tests: 0 all-read, 1 two-phase
     dCommPeers.upload(commPeers, (size_t)world, stream);
     dCommError.alloc(1);
     CUDA_OK(cudaMemsetAsync(dCommError.p, 0, sizeof(uint32_t), stream));
     CUDA_OK(cudaStreamSynchronize(stream));
+}
+
+// ---- exchange microbenchmark ("EM-allreduce scaling, cells in {1 k, 8 k, 64 k} x K = 32") --------
+// Times k_mstep_allreduce alone: synthetic statistics in both exchange buffers, scratch lobes (the field is not touched).
+// Every connected rank must call it with the same arguments (the kernel contains the cross-GPU barrier).
+// localOnly: the same kernel restricted to this rank's own buffer = the M-step share of the time.
+__global__ void k_fill_stats(float *p, size_t n, uint32_t seed) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t h = (uint32_t)i * 2654435761u + seed * 40503u;
+        h ^= h >> 15;
+        p[i] = 0.25f + (float)(h & 1023u) * (1.0f / 1024.0f);
+    }
+}
+float GuidingHost::exchangeBench(uint32_t cells, int nIter, bool localOnly) {
+    if (!commBlock || commWorld < 1 || !dCommPeers.p) throw std::runtime_error("b200pg_comm_connect must be called first");
+    if (cells == 0 || cells > kCommMaxCells) throw std::runtime_error("cell count outside the exchange buffer");
+    const int stride = (int)statsStride();
+    DevBuf<float4> lobesT, statsT;
+    DevBuf<float> sumT;
+    lobesT.allocExact((size_t)cells * K * 2);
+    statsT.allocExact((size_t)cells * K);
+    sumT.allocExact((size_t)cells * stride);
+    CUDA_OK(cudaMemsetAsync(lobesT.p, 0, (size_t)cells * K * 2 * sizeof(float4), stream));
+    CUDA_OK(cudaMemsetAsync(statsT.p, 0, (size_t)cells * K * sizeof(float4), stream));
+    k_fill_stats<<<592, 256, 0, stream>>>(commBlock, 2 * commFloats, (uint32_t)commRank + 1u);
+    CUDA_OK(cudaStreamSynchronize(stream));
+    const int grid = exchangeGrid(cells);
+    float *selfPeer = commBlock;
+    DevBuf<float *> dSelf;
+    dSelf.upload(&selfPeer, 1, stream);
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0));
+    CUDA_OK(cudaEventCreate(&e1));
+    const int warm = 3;
+    for (int it = 0; it < warm + nIter; ++it) {
+        if (it == warm) CUDA_OK(cudaEventRecord(e0, stream));
+        CommView cv;
+        cv.peers = localOnly ? dSelf.p : dCommPeers.p;
+        cv.rank = localOnly ? 0 : commRank;
+        cv.world = localOnly ? 1 : commWorld;
+        cv.flagSlot = localOnly ? 63 : commRank;
+        cv.buf = (int)(commEpoch & 1u);
+        cv.epoch = localOnly ? 0u : ++commEpoch;  // epoch 0 is always "arrived"
+        cv.bufFloats = commFloats;
+        cv.twoPhase = (!localOnly && exchangeTwoPhase(cells)) ? 1 : 0;
+        cv.error = dCommError.p;
+        k_mstep_allreduce<<<grid, kExchangeThreads, 0, stream>>>(cv, lobesT.p, statsT.p, sumT.p, cells, K, stride, 0);
+        launches++;
+    }
+    CUDA_OK(cudaEventRecord(e1, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    CUDA_OK(cudaGetLastError());
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    uint32_t err = 0;
+    CUDA_OK(cudaMemcpy(&err, dCommError.p, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (err) throw std::runtime_error("multi-GPU statistics exchange timed out: a peer rank never arrived");
+    return ms / (float)nIter;
 }
 
 void GuidingHost::commClose() {

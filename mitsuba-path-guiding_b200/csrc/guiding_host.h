@@ -103,10 +103,10 @@ struct GuidingHost {
 
     // ---- multi-GPU: peer-memory exchange of the per-cell EM statistics (no NCCL call on the data path) -----------
     // Every rank owns one cudaMalloc'ed exchange block {2 x kCommCapacity floats of statistics (double-buffered by EM
-    // iteration parity), 64 arrival flags} that its peers map through CUDA IPC. k_mstep_allreduce signals arrival
+    // iteration parity), kCommCapacity floats of pushed sums (large fields), 64 flags} that its peers map through CUDA IPC. k_mstep_allreduce signals arrival
     // in every peer's flag row, waits for all peers, then sums the cell's statistics over the ranks in rank order
     // (identical result on every rank) and runs the M-step in the same kernel.
-    static constexpr size_t kCommMaxCells = 16384;
+    static constexpr size_t kCommMaxCells = 65536;
     int commRank = 0, commWorld = 1;
     uint32_t commEpoch = 0;
     float *commBlock = nullptr;            // own exchange block (device)
@@ -117,6 +117,11 @@ struct GuidingHost {
     void commLocalHandle(void *out64);
     void commConnect(int rank, int world, const void *handles);
     void commClose();
+    // microbenchmark of the exchange step alone: avg ms per k_mstep_allreduce over `cells` synthetic cells
+    float exchangeBench(uint32_t cells, int nIter, bool localOnly);
+    int commForceMode = -1;  // -1: choose by size; 0: all-read form; 1: reduce-scatter + all-gather form (microbenchmark)
+    int exchangeGrid(uint32_t cells) const;
+    bool exchangeTwoPhase(uint32_t cells) const;
     ~GuidingHost() { commClose(); }
 
     // per-kernel entry points

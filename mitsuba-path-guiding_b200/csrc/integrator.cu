@@ -13,6 +13,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <memory>
@@ -31,7 +32,7 @@ namespace pg {
 // launch wrappers implemented in kernels.cu
 void launchGenerate(const DeviceScene &S, const BatchDesc &B, const PathState &P, Counters *C, cudaStream_t st);
 void launchTrace(const DeviceScene &S, const PathState &P, float4 *hits, const uint32_t *nPtr, uint32_t *work, Counters *C,
-                 bool count, cudaStream_t st);
+                 bool count, const SortArgs *sort, cudaStream_t st);
 void launchShadow(const DeviceScene &S, const ShadowQueue &Q, float4 *rad, const uint32_t *nPtr, uint32_t *work, Counters *C,
                   bool count, cudaStream_t st);
 void launchShade(const ShadeArgs &A, cudaStream_t st);
@@ -105,6 +106,11 @@ struct Integrator {
     DevBuf<float> dFilmOut;
     size_t batchCapacity = 0;
     bool countTraversal = false;
+    // coherence sort of the shade queue by guiding cell: bounces 1..sortBounces of a guided (sampling) progression
+    // (default off: on C2 with ~800 cells the gathered state reads cost more than the coherent lobe loads save --
+    // DESIGN.md, optimisation log 7; B200PG_SORT_BOUNCES / b200pg_set_option("sort_bounces") turn it on)
+    int sortBounces = std::getenv("B200PG_SORT_BOUNCES") ? std::atoi(std::getenv("B200PG_SORT_BOUNCES")) : 0;
+    DevBuf<uint32_t> dSortKey, dSortRank, dSortPerm, dBinCount, dBinOffset;
 
     B200pgStats stats;
     cudaEvent_t ev[8];
@@ -229,6 +235,7 @@ struct Integrator {
             dShAux.alloc(n); dTrkA.alloc(n); dTrkB.alloc(n); dLookL.alloc(n);
         }
         dSplat.alloc(2 * n);
+        dSortKey.alloc(n); dSortRank.alloc(n); dSortPerm.alloc(n);
         batchCapacity = n;
     }
 
@@ -277,14 +284,32 @@ struct Integrator {
         A.radianceOut = radianceOut;
         A.splat = dSplat.p;
         A.trkA = dTrkA.p; A.trkB = dTrkB.p; A.lookL = dLookL.p;
+        A.perm = nullptr;
+        // coherence sort (surface path, sampling from a trained field): bins = 1 + cells
+        const bool sortOn = sortBounces > 0 && !params.volumetric && A.G.enabled;
+        SortArgs sortArgs = {};
+        if (sortOn) {
+            const size_t bins = 1 + (size_t)guide.numCells();
+            if (bins > dBinCount.n) {
+                dBinCount.alloc(bins); dBinOffset.alloc(dBinCount.n);
+                CUDA_OK(cudaMemsetAsync(dBinCount.p, 0, dBinCount.n * sizeof(uint32_t), stream));
+            }
+            sortArgs.guideNodes = guide.dNodes.p;
+            sortArgs.binCount = dBinCount.p; sortArgs.binOffset = dBinOffset.p;
+            sortArgs.key = dSortKey.p; sortArgs.rank = dSortRank.p; sortArgs.perm = dSortPerm.p;
+            sortArgs.nCells = guide.dCounts.p;
+        }
         const int maxBounces = params.max_depth > 0 ? std::min(params.max_depth + 1, 256) : 256;
         Counters *C = dCounters.p;
         int b = 0;
         for (; b < maxBounces; ++b) {
             if (cancel.load()) break;
             cudaEvent_t t = spanBegin();
-            launchTrace(S, cur, dHits.p, &C->queue[b], &C->traceWork[b], C, countTraversal, stream);
+            const bool sorted = sortOn && b >= 1 && b <= sortBounces;
+            launchTrace(S, cur, dHits.p, &C->queue[b], &C->traceWork[b], C, countTraversal, sorted ? &sortArgs : nullptr, stream);
+            if (sorted) stats.kernel_launches += 2;
             spanEnd(kTimeTrace, t);
+            A.perm = sorted ? dSortPerm.p : nullptr;
             A.cur = cur;
             A.next = next;
             A.bounce = b;
@@ -311,6 +336,7 @@ struct Integrator {
         }
         A.cur = cur;
         A.next = next;
+        A.perm = nullptr;
         A.bounce = std::min(b, maxBounces);
         launchFlush(A, stream);
         stats.kernel_launches++;
@@ -794,6 +820,7 @@ int b200pg_set_option(void *integ, const char *name, int value) {
     std::string n(name);
     if (n == "count_traversal") self->countTraversal = value != 0;
     else if (n == "timing") self->timing = value != 0;
+    else if (n == "sort_bounces") self->sortBounces = value;
     else return fail("unknown option " + n);
     return 0;
 }
@@ -1065,6 +1092,21 @@ int b200pg_k_em_step(void *integ, const float *pos, const float *dir, const floa
                                     cudaMemcpyDeviceToHost, self->stream));
         g.end();
     }
+    PG_END
+}
+int b200pg_k_em_exchange(void *integ, uint32_t n_cells, int n_iter, int mode, float *ms_per_iter) {
+    PG_TRY(integ)
+    if (!ms_per_iter || n_iter <= 0 || mode < 0 || mode > 3) return fail("invalid argument");
+    if (!self->guide.active) return fail("guiding is not enabled in the integrator parameters");
+    const int before = self->guide.commForceMode;
+    self->guide.commForceMode = mode == 2 ? 0 : mode == 3 ? 1 : -1;
+    try {
+        *ms_per_iter = self->guide.exchangeBench(n_cells, n_iter, mode == 1);
+    } catch (...) {
+        self->guide.commForceMode = before;
+        throw;
+    }
+    self->guide.commForceMode = before;
     PG_END
 }
 int b200pg_field_snapshot(void *integ, uint32_t *out, size_t *n_words) {

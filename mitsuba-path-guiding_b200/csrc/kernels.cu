@@ -131,10 +131,10 @@ __global__ void __launch_bounds__(256) k_generate(DeviceScene S, BatchDesc B, Pa
 // Traversal. One thread per ray, warps fetch 32 rays at a time from a device work counter
 // (dynamic load balancing: rays of one queue differ a lot in traversal length).
 // ------------------------------------------------------------------------------------------
-template <bool kCount>
+template <bool kCount, bool kKey>
 __global__ void __launch_bounds__(128) k_trace(DeviceScene S, const float4 *__restrict__ rayO, const float4 *__restrict__ rayD,
                                                const uint32_t *__restrict__ flags, float4 *__restrict__ hits,
-                                               const uint32_t *nPtr, uint32_t *work, Counters *C) {
+                                               const uint32_t *nPtr, uint32_t *work, Counters *C, SortArgs Q) {
     const uint32_t n = *nPtr;
     unsigned long long rays = 0;
     uint32_t cn = 0, cp = 0;
@@ -144,20 +144,42 @@ __global__ void __launch_bounds__(128) k_trace(DeviceScene S, const float4 *__re
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n) break;
         const uint32_t i = base + laneId();
+        uint32_t bin = 0xFFFFFFFFu;  // lanes past the end of the queue
         if (i < n) {
             Hit h;
             h.prim = kMiss;
             h.t = kInf;
             h.u = h.v = 0;
+            bin = 0;
             if (!(flags[i] & (kFlagDead | kFlagNoTrace))) {
                 const float4 ro = rayO[i], rd = rayD[i];
                 const float3 o = f3(ro.x, ro.y, ro.z), d = f3(rd.x, rd.y, rd.z);
                 const float mint = adaptiveMinT(o, ro.w, false);
                 traceRay<false, kCount>(S, o, d, mint, rd.w, h, &cn, &cp);
                 if (h.prim == kMiss) h.t = kInf;
+                else if (kKey) {  // guiding cell of the hit point (ordering only: the shade stage looks its cell up itself)
+                    const float3 p = o + d * h.t;
+                    uint32_t nd = 0;
+                    while (true) {
+                        const uint4 g = __ldg(Q.guideNodes + nd);
+                        if (g.x == 3u) { bin = 1u + g.z; break; }
+                        nd = comp(p, (int)g.x) < __uint_as_float(g.y) ? g.z : g.z + 1;
+                    }
+                }
                 rays++;
             }
             hits[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+        }
+        if (kKey) {  // rank inside the bin: one atomic per distinct bin of the warp
+            const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+            const int leader = __ffs(peers) - 1;
+            uint32_t first = 0;
+            if (bin != 0xFFFFFFFFu && (int)laneId() == leader) first = atomicAdd(Q.binCount + bin, (uint32_t)__popc(peers));
+            first = __shfl_sync(peers, first, leader);
+            if (bin != 0xFFFFFFFFu) {
+                Q.key[i] = bin;
+                Q.rank[i] = first + (uint32_t)__popc(peers & ((1u << laneId()) - 1u));
+            }
         }
     }
     warpAddU64(&C->normalRays, rays);
@@ -165,6 +187,50 @@ __global__ void __launch_bounds__(128) k_trace(DeviceScene S, const float4 *__re
         warpAddU64(&C->nodesVisited, cn);
         warpAddU64(&C->primsTested, cp);
     }
+}
+
+// Coherence sort, step 2: exclusive scan of the 1 + cells bin counters (single block; the counters are re-zeroed for the
+// next bounce) and step 3: permutation.
+__global__ void __launch_bounds__(1024) k_bin_scan(SortArgs Q) {
+    __shared__ uint32_t sWarp[32];
+    __shared__ uint32_t sCarry;
+    const uint32_t nBins = 1u + *Q.nCells;
+    if (threadIdx.x == 0) sCarry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nBins; base += 1024u) {
+        const uint32_t b = base + threadIdx.x;
+        const uint32_t v = b < nBins ? Q.binCount[b] : 0u;
+        if (b < nBins) Q.binCount[b] = 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((int)laneId() >= o) x += y;
+        }
+        if (laneId() == 31) sWarp[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = sWarp[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+                if ((int)laneId() >= o) w += y;
+            }
+            sWarp[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const uint32_t warpBase = (threadIdx.x >> 5) ? sWarp[(threadIdx.x >> 5) - 1] : 0u;
+        const uint32_t carry = sCarry;
+        if (b < nBins) Q.binOffset[b] = carry + warpBase + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) sCarry = carry + warpBase + x;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) k_bin_scatter(SortArgs Q, const uint32_t *nPtr) {
+    const uint32_t n = *nPtr;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        Q.perm[__ldg(Q.binOffset + Q.key[i]) + Q.rank[i]] = i;
 }
 
 // Shadow rays: any-hit; an unoccluded ray adds its contribution to the path record it belongs to.
@@ -251,8 +317,9 @@ __global__ void __launch_bounds__(kShadeThreads, 8) k_shade(ShadeArgs A) {
     uint32_t appendParity = 0;
 
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const uint32_t i = base + threadIdx.x;
-        const bool valid = i < n;
+        const uint32_t q = base + threadIdx.x;
+        const bool valid = q < n;
+        const uint32_t i = (valid && A.perm) ? A.perm[q] : q;
 
         bool alive = false;      // continues into the next queue
         bool wantShadow = false;
@@ -551,12 +618,21 @@ void launchGenerate(const DeviceScene &S, const BatchDesc &B, const PathState &P
     k_generate<<<grid, 256, 0, st>>>(S, B, P, C);
 }
 void launchTrace(const DeviceScene &S, const PathState &P, float4 *hits, const uint32_t *nPtr, uint32_t *work, Counters *C,
-                 bool count, cudaStream_t st) {
-    static int grid = persistentGrid(k_trace<false>, 128);
-    if (count)
-        k_trace<true><<<grid, 128, 0, st>>>(S, P.rayO, P.rayD, P.flags, hits, nPtr, work, C);
+                 bool count, const SortArgs *sort, cudaStream_t st) {
+    static int grid = persistentGrid(k_trace<false, false>, 128);
+    static int gridKey = persistentGrid(k_trace<false, true>, 128);
+    const SortArgs none = {};
+    if (sort) {
+        if (count)
+            k_trace<true, true><<<gridKey, 128, 0, st>>>(S, P.rayO, P.rayD, P.flags, hits, nPtr, work, C, *sort);
+        else
+            k_trace<false, true><<<gridKey, 128, 0, st>>>(S, P.rayO, P.rayD, P.flags, hits, nPtr, work, C, *sort);
+        k_bin_scan<<<1, 1024, 0, st>>>(*sort);
+        k_bin_scatter<<<numSMs() * 4, 256, 0, st>>>(*sort, nPtr);
+    } else if (count)
+        k_trace<true, false><<<grid, 128, 0, st>>>(S, P.rayO, P.rayD, P.flags, hits, nPtr, work, C, none);
     else
-        k_trace<false><<<grid, 128, 0, st>>>(S, P.rayO, P.rayD, P.flags, hits, nPtr, work, C);
+        k_trace<false, false><<<grid, 128, 0, st>>>(S, P.rayO, P.rayD, P.flags, hits, nPtr, work, C, none);
 }
 void launchShadow(const DeviceScene &S, const ShadowQueue &Q, float4 *rad, const uint32_t *nPtr, uint32_t *work, Counters *C,
                   bool count, cudaStream_t st) {

@@ -91,6 +91,20 @@ struct ShadeArgs {
     float4 *lookL;       // volumetric: per queued path, MIS-weighted emitter radiance found by k_look_vol
     GuideDevice G;
     int bounce;
+    const uint32_t *perm;  // coherence sort: queue order -> path index (nullptr = shade in queue order)
+};
+
+// Coherence sort of the shade queue by guiding cell (north star, subsystem 2: "sorting by cell to restore coherence").
+// k_trace bins every traced path by the cell of its hit point (bin 0 = nothing to shade: miss / parked) and takes its
+// rank inside the bin with one warp-aggregated atomic; k_bin_scan turns the counts into offsets; k_bin_scatter writes
+// the permutation the shade stage reads its paths through. Keys never leave the device; order inside a bin is arbitrary.
+struct SortArgs {
+    const uint4 *guideNodes;  // spatial tree of the guiding field
+    uint32_t *binCount;       // 1 + cells counters (zeroed by k_bin_scan for the next bounce)
+    uint32_t *binOffset;
+    uint32_t *key, *rank;     // per queued path
+    uint32_t *perm;
+    const uint32_t *nCells;   // device-resident cell count of the field
 };
 
 }  // namespace pg

@@ -60,6 +60,16 @@ def test_two_gpu_fused_statistics_sum(tmp_path, pkg):
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     f0, f1 = np.load(tmp_path / "field_0.npy"), np.load(tmp_path / "field_1.npy")
     assert np.array_equal(f0, f1)  # replicated fields stay bit-identical without a broadcast
+    # the reduce-scatter + all-gather form of the exchange (large fields) adds the same numbers in the same rank order:
+    # forced on through the environment it must reproduce the all-read form's field bit for bit
+    os.environ["B200PG_EXCHANGE_FORM"] = "1"
+    try:
+        mp.spawn(_worker, args=(2, port + 1, str(tmp_path)), nprocs=2, join=True)
+    finally:
+        del os.environ["B200PG_EXCHANGE_FORM"]
+    g0, g1 = np.load(tmp_path / "field_0.npy"), np.load(tmp_path / "field_1.npy")
+    assert np.array_equal(g0, g1)
+    assert g0.shape == f0.shape and np.array_equal(g0[:8], f0[:8])  # same tree size
     # single GPU, union of the samples: the first update sees exactly the same samples (unguided progression), so the
     # spatial tree after it must be identical and the mixtures agree to the statistics' tolerance
     sb = pkg.scenes.cornell_caustic(128, 128, spp=8)
