@@ -244,6 +244,13 @@ int b200pg_comm_local_handle(void *integ, void *handle64);
 int b200pg_comm_connect(void *integ, int rank, int world, const void *handles);
 
 int b200pg_film_clear(void *integ);
+/* Multi-GPU film merge, one process per GPU (every GPU keeps a full-size film of its own sample batches; the
+ * reference merges its workers' ImageBlocks in Film::put, renderproc.cpp:141-148). b200pg_film_ipc_handle returns the
+ * 64-byte CUDA IPC handle of this handle's device film; b200pg_film_add_peers(rank, world, handles = world x 64 bytes)
+ * adds the films of all other ranks into this one, read over NVLink in rank order. The caller makes sure the peers have
+ * finished rendering and keep their handles alive until the call returns. */
+int b200pg_film_ipc_handle(void *integ, void *handle64);
+int b200pg_film_add_peers(void *integ, int rank, int world, const void *handles);
 int b200pg_film_device_buffer(void *integ, void **dev_ptr, size_t *n_floats); /* H*W*4: R,G,B,weight */
 int b200pg_film_read(void *integ, float *rgbaw /* H*W*5: R,G,B,alpha,weight (imageblock.h:131-138) */);
 int b200pg_film_develop(void *integ, float *rgb /* H*W*3 = RGB/weight, fmtconv.cpp:978-1005 */);

@@ -12,7 +12,8 @@ import numpy as np
 from . import _abi as A
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200pg.so")
+# B200PG_LIB: development aid (tools/build_variant.sh builds the library with other compile-time knobs for A/B runs)
+LIB_PATH = os.environ.get("B200PG_LIB") or os.path.join(_HERE, "libb200pg.so")
 
 fp = C.POINTER(C.c_float)
 u32p = C.POINTER(C.c_uint32)
@@ -77,6 +78,8 @@ def lib():
     L.b200pg_comm_connect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.b200pg_field_snapshot.argtypes = [C.c_void_p, u32p, C.POINTER(C.c_size_t)]
     L.b200pg_field_load.argtypes = [C.c_void_p, u32p, C.c_size_t]
+    L.b200pg_film_ipc_handle.argtypes = [C.c_void_p, C.c_void_p]
+    L.b200pg_film_add_peers.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.b200pg_k_em_exchange.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_float)]
     _lib = L
     return L

@@ -9,6 +9,28 @@ namespace pg {
 
 #define PG_DEV __device__ __forceinline__
 
+// Streamed-once data (wavefront state, queues, training records): evict-first loads / stores keep it from displacing the
+// small hot working set (guiding lobes, tree nodes, scene records) in L1 and L2.
+#ifndef PG_STREAM
+#define PG_STREAM 1
+#endif
+template <typename T>
+PG_DEV T ldStream(const T *p) {
+#if PG_STREAM
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+template <typename T>
+PG_DEV void stStream(T *p, T v) {
+#if PG_STREAM
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
 static constexpr float kEpsilon = 1e-4f;        // include/mitsuba/core/constants.h:28
 static constexpr float kShadowEpsilon = 1e-3f;  // constants.h:29
 static constexpr float kPi = 3.14159265358979323846f;

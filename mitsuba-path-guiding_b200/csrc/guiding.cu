@@ -1157,11 +1157,12 @@ int GuidingHost::exchangeGrid(uint32_t cells) const {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     return (int)std::max<size_t>(1, std::min<size_t>(((size_t)cells * 32 + kExchangeThreads - 1) / kExchangeThreads, (size_t)sms));
 }
-// reduce-scatter + all-gather form once the all-read form would pull more than 1 MB from the peers (measured cross-over,
-// tools/em_exchange_bench.py); depends only on numbers every rank shares
+// reduce-scatter + all-gather form once the all-read form would pull more than 8 MB from the peers (measured cross-over on
+// 4 and 8 B200s, profiles/r01_v5_em_exchange.jsonl; with two ranks both forms move the same bytes and the all-read form
+// saves a barrier); depends only on numbers every rank shares
 bool GuidingHost::exchangeTwoPhase(uint32_t cells) const {
     if (commForceMode >= 0) return commForceMode != 0 && commWorld > 1;
-    return commWorld > 1 && (size_t)cells * statsStride() * sizeof(float) * (size_t)(commWorld - 1) > ((size_t)1 << 20);
+    return commWorld > 2 && (size_t)cells * statsStride() * sizeof(float) * (size_t)(commWorld - 1) > ((size_t)8 << 20);
 }
 
 void GuidingHost::commLocalHandle(void *out64) {

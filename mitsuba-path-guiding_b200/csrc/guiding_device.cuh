@@ -76,7 +76,11 @@ PG_DEV float guidePdf(const GuideDevice &G, uint32_t cell, float3 w) {
 PG_DEV void guidePdf2(const GuideDevice &G, uint32_t cell, float3 w1, float3 w2, float &p1, float &p2) {
     const float4 *L = G.lobes + (size_t)cell * G.K * 2;
     float s1 = 0, s2 = 0;
-#pragma unroll 2  // 2 beats 4 and 8 at 64 registers (fewer spills; the loads are L1/L2 hits)
+#ifndef PG_PDF2_UNROLL
+#define PG_PDF2_UNROLL 2  // 2 beats 4 and 8 at 64 registers (fewer spills; the loads are L1/L2 hits)
+#endif
+    constexpr int kUnroll = PG_PDF2_UNROLL;
+#pragma unroll kUnroll
     for (int k = 0; k < G.K; ++k) {
         const float4 a = __ldg(L + 2 * k), b = __ldg(L + 2 * k + 1);
         s1 += guideLobeTerm(a, b, w1);

@@ -37,6 +37,7 @@ void launchShadow(const DeviceScene &S, const ShadowQueue &Q, float4 *rad, const
                   bool count, cudaStream_t st);
 void launchShade(const ShadeArgs &A, cudaStream_t st);
 void launchFlush(const ShadeArgs &A, cudaStream_t st);
+void launchFilmAdd(float4 *film, const float4 *peer, uint32_t n, cudaStream_t st);
 // volpath.cu
 void launchShadeVol(const ShadeArgs &A, cudaStream_t st);
 void launchShadowVol(const DeviceScene &S, const ShadowQueue &Q, float4 *rad, const uint32_t *nPtr, uint32_t *work, Counters *C,
@@ -599,6 +600,35 @@ int b200pg_film_clear(void *integ) {
     PG_TRY(integ)
     CUDA_OK(cudaMemsetAsync(self->dFilm.p, 0, self->dFilm.n * sizeof(float4), self->stream));
     CUDA_OK(cudaStreamSynchronize(self->stream));
+    PG_END
+}
+
+int b200pg_film_ipc_handle(void *integ, void *handle64) {
+    PG_TRY(integ)
+    if (!handle64) return fail("null argument");
+    CUDA_OK(cudaStreamSynchronize(self->stream));
+    cudaIpcMemHandle_t h;
+    CUDA_OK(cudaIpcGetMemHandle(&h, self->dFilm.p));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(handle64, &h, 64);
+    PG_END
+}
+
+int b200pg_film_add_peers(void *integ, int rank, int world, const void *handles) {
+    PG_TRY(integ)
+    if (!handles || world < 1 || rank < 0 || rank >= world) return fail("invalid argument");
+    for (int r = 0; r < world; ++r) {  // fixed peer order
+        if (r == rank) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, (const char *)handles + 64 * (size_t)r, 64);
+        void *ptr = nullptr;
+        CUDA_OK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        launchFilmAdd(self->dFilm.p, (const float4 *)ptr, (uint32_t)self->dFilm.n, self->stream);
+        cudaError_t e = cudaStreamSynchronize(self->stream);
+        cudaIpcCloseMemHandle(ptr);
+        CUDA_OK(e);
+    }
+    CUDA_OK(cudaGetLastError());
     PG_END
 }
 

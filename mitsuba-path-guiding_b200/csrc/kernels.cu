@@ -84,6 +84,16 @@ __global__ void __launch_bounds__(256) k_film_export(const float4 *__restrict__ 
     }
 }
 
+// Multi-GPU film merge (every GPU holds a full-size film): film += a peer's film, read over NVLink
+__global__ void __launch_bounds__(256) k_film_add(float4 *__restrict__ film, const float4 *__restrict__ peer, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 f = film[i];
+        const float4 g = ldStream(peer + i);
+        f.x += g.x; f.y += g.y; f.z += g.z; f.w += g.w;
+        film[i] = f;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Camera rays
 // ------------------------------------------------------------------------------------------
@@ -306,7 +316,10 @@ __global__ void __launch_bounds__(128) k_trace_rays(DeviceScene S, const float4 
 // Shade stage (surface path tracer, ProgressiveMIPathTracer::Li)
 // ------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(kShadeThreads, 8) k_shade(ShadeArgs A) {
+#ifndef PG_SHADE_BLOCKS
+#define PG_SHADE_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(kShadeThreads, PG_SHADE_BLOCKS) k_shade(ShadeArgs A) {
     const DeviceScene &S = A.S;
     const IntegratorConfig &cfg = A.cfg;
     const uint32_t n = A.C->queue[A.bounce];
@@ -339,15 +352,15 @@ __global__ void __launch_bounds__(kShadeThreads, 8) k_shade(ShadeArgs A) {
         uint32_t depth = 0, vcount = 0;
 
         if (valid) {
-            ro = A.cur.rayO[i];
-            rd = A.cur.rayD[i];
-            thr4 = A.cur.thr[i];
-            rad4 = A.cur.rad[i];
-            pos4 = A.cur.pos[i];
-            fl = A.cur.flags[i];
-            slot = A.cur.slot[i];
-            medium = A.cur.medium[i];
-            const float4 h4 = A.hits[i];
+            ro = ldStream(A.cur.rayO + i);
+            rd = ldStream(A.cur.rayD + i);
+            thr4 = ldStream(A.cur.thr + i);
+            rad4 = ldStream(A.cur.rad + i);
+            pos4 = ldStream(A.cur.pos + i);
+            fl = ldStream(A.cur.flags + i);
+            slot = ldStream(A.cur.slot + i);
+            medium = ldStream(A.cur.medium + i);
+            const float4 h4 = ldStream(A.hits + i);
             L = f3(rad4.x, rad4.y, rad4.z);
             thr = f3(thr4.x, thr4.y, thr4.z);
             eta = thr4.w;
@@ -515,20 +528,20 @@ __global__ void __launch_bounds__(kShadeThreads, 8) k_shade(ShadeArgs A) {
         appendParity ^= 1u;
         const uint32_t j = ap.idxA, sidx = ap.idxB;
         if (alive) {
-            A.next.rayO[j] = make_float4(newO.x, newO.y, newO.z, kEpsilon);
-            A.next.rayD[j] = make_float4(newD.x, newD.y, newD.z, kInf);
-            A.next.thr[j] = make_float4(thr.x, thr.y, thr.z, eta);
-            A.next.rad[j] = make_float4(L.x, L.y, L.z, newPdf);
-            A.next.pos[j] = make_float4(pos4.x, pos4.y, __uint_as_float((uint32_t)rng.state),
-                                        __uint_as_float((uint32_t)(rng.state >> 32)));
-            A.next.flags[j] = (fl & ~(kDepthMask | (0xFFu << kVertShift))) | (depth & kDepthMask) | (vcount << kVertShift);
-            A.next.slot[j] = slot;
-            A.next.medium[j] = medium;
+            stStream(A.next.rayO + j, make_float4(newO.x, newO.y, newO.z, kEpsilon));
+            stStream(A.next.rayD + j, make_float4(newD.x, newD.y, newD.z, kInf));
+            stStream(A.next.thr + j, make_float4(thr.x, thr.y, thr.z, eta));
+            stStream(A.next.rad + j, make_float4(L.x, L.y, L.z, newPdf));
+            stStream(A.next.pos + j, make_float4(pos4.x, pos4.y, __uint_as_float((uint32_t)rng.state),
+                                                 __uint_as_float((uint32_t)(rng.state >> 32))));
+            stStream(A.next.flags + j, (fl & ~(kDepthMask | (0xFFu << kVertShift))) | (depth & kDepthMask) | (vcount << kVertShift));
+            stStream(A.next.slot + j, slot);
+            stStream(A.next.medium + j, medium);
         }
         if (wantShadow) {
-            A.shadow.o[sidx] = make_float4(shO.x, shO.y, shO.z, kEpsilon);
-            A.shadow.d[sidx] = make_float4(shD.x, shD.y, shD.z, shMaxT);
-            A.shadow.c[sidx] = make_float4(shC.x, shC.y, shC.z, __uint_as_float(j));
+            stStream(A.shadow.o + sidx, make_float4(shO.x, shO.y, shO.z, kEpsilon));
+            stStream(A.shadow.d + sidx, make_float4(shD.x, shD.y, shD.z, shMaxT));
+            stStream(A.shadow.c + sidx, make_float4(shC.x, shC.y, shC.z, __uint_as_float(j)));
         }
         if (valid && terminate) {
             donePaths++;
@@ -652,6 +665,9 @@ void launchSplat(const FilmRecord &F, float4 *film, const float4 *splat, uint32_
 }
 void launchFilmExport(const float4 *film, float *out, uint32_t n, int develop, cudaStream_t st) {
     k_film_export<<<numSMs() * 4, 256, 0, st>>>(film, out, n, develop);
+}
+void launchFilmAdd(float4 *film, const float4 *peer, uint32_t n, cudaStream_t st) {
+    k_film_add<<<numSMs() * 4, 256, 0, st>>>(film, peer, n);
 }
 void launchFlush(const ShadeArgs &A, cudaStream_t st) {
     static int grid = persistentGrid(k_flush, 256);
