@@ -119,7 +119,7 @@ def guided_params(pkg, args):
     p.max_depth = 8
     p.guiding = 0 if args.no_guiding else 1
     p.guide_max_components = 16
-    p.guide_max_cell_samples = 32768
+    p.guide_max_cell_samples = args.max_cell_samples
     p.volumetric = 1 if args.workload == "medium_1024" else 0
     p.guided_distance = 1 if (p.volumetric and p.guiding and args.guided_distance) else 0
     return p
@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--no-guiding", action="store_true")
     ap.add_argument("--guided-distance", action="store_true", help="medium workloads: guided free-flight sampling")
     ap.add_argument("--nccl-allreduce", action="store_true", help="sum EM statistics with torch.distributed/NCCL instead of the fused peer-memory kernel")
+    ap.add_argument("--max-cell-samples", type=int, default=32768, help="spatial split threshold of the guiding field (experiments: a smaller value grows the larger field of a multi-GPU job on one GPU)")
     ap.add_argument("--sort-bounces", type=int, default=-1, help="coherence sort of the shade queue by guiding cell on bounces 1..n (0 = off, -1 = library default)")
     ap.add_argument("--ref-seconds", type=float, default=3.0)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)

@@ -3,7 +3,7 @@
 args=$1; shift
 for v in "$@"; do
   if [ "$v" = default ]; then unset B200PG_LIB; else export B200PG_LIB=$PWD/mitsuba-path-guiding_b200/_variants/libb200pg_$v.so; fi
-  python bench.py --steps 16 --warmup 3 --no-cpu-baseline $args > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err || tail -3 gpurun_out/ab_$v.err
+  python bench.py --steps 16 --warmup 3 --no-cpu-baseline $args $EXTRA > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err || tail -3 gpurun_out/ab_$v.err
   python - "$v" <<'PY'
 import json,sys
 v=sys.argv[1]
