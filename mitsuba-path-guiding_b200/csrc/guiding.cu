@@ -535,65 +535,106 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const float *__restrict
     }
 }
 
-// ---- M-step: one warp per cell, lane k = lobe k ----------------------------------------------------------
-// With `partials` != nullptr the per-cell sum of the chunk partials (k_reduce_partials' job: fixed order, double
-// accumulation) is done here by the cell's warp first -- one launch and one round trip of the statistics less per EM
-// iteration on the single-GPU path.
+// ---- M-step: lane k = lobe k -----------------------------------------------------------------------------
+// PG_MSTEP_BODY: the refit of one cell by one warp from `st` (the cell's summed statistics) -- shared by both kernels.
+#define PG_MSTEP_BODY(c, st)                                                                      \
+    {                                                                                             \
+        float4 a = make_float4(0, 0, 0, 0), b = a, s = a;                                         \
+        float S = 0, R0 = 0, R1 = 0, R2 = 0;                                                      \
+        if (k < K) {                                                                              \
+            const float4 *L = lobes + ((size_t)(c) * K + k) * 2;                                  \
+            a = L[0];                                                                             \
+            b = L[1];                                                                             \
+            s = lobeStats[(size_t)(c) * K + k];                                                   \
+            S = kGuideDecay * s.x + (st)[4 * k];                                                  \
+            R0 = kGuideDecay * s.y + (st)[4 * k + 1];                                             \
+            R1 = kGuideDecay * s.z + (st)[4 * k + 2];                                             \
+            R2 = kGuideDecay * s.w + (st)[4 * k + 3];                                             \
+        }                                                                                         \
+        float sumS = S;                                                                           \
+        _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) sumS += __shfl_xor_sync(0xffffffffu, sumS, o); \
+        if (k < K) {                                                                              \
+            if (sumS > 0 && isfinite(sumS)) {                                                     \
+                const float prior = kGuidePriorWeight * sumS / (float)K;                          \
+                const float denom = 1.0f / (sumS + (float)K * prior);                             \
+                a.x = (S + prior) * denom;                                                        \
+                const float rl = sqrtf(R0 * R0 + R1 * R1 + R2 * R2);                              \
+                float rbar = (rl + prior * kGuidePriorMeanCos) / (S + prior);                     \
+                rbar = fminf(rbar, 0.9999f);                                                      \
+                const float kappa = rbar * (3.0f - rbar * rbar) / (1.0f - rbar * rbar);           \
+                b.x = fminf(kGuideKappaMax, fmaxf(kGuideKappaMin, kappa));                        \
+                if (rl > 0) {                                                                     \
+                    const float ir = 1.0f / rl;                                                   \
+                    a.y = R0 * ir;                                                                \
+                    a.z = R1 * ir;                                                                \
+                    a.w = R2 * ir;                                                                \
+                }                                                                                 \
+                b.z = expf(-2.0f * b.x);                                                          \
+                b.y = b.x / (2 * kPi * (1.0f - b.z));                                             \
+            }                                                                                     \
+            float4 *L = lobes + ((size_t)(c) * K + k) * 2;                                        \
+            L[0] = a;                                                                             \
+            L[1] = b;                                                                             \
+            if (commit) lobeStats[(size_t)(c) * K + k] = make_float4(S, R0, R1, R2);              \
+        }                                                                                         \
+    }
+
+// One warp per cell; the statistics are already summed per cell (multi-GPU / external-collective path).
 __global__ void __launch_bounds__(256) k_mstep(float4 *__restrict__ lobes, float4 *__restrict__ lobeStats, float *__restrict__ stats,
-                                               uint32_t nCells, int K, int stride, int commit, const float *__restrict__ partials,
-                                               const uint32_t *__restrict__ workOfs) {
+                                               uint32_t nCells, int K, int stride, int commit) {
     const uint32_t warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = (gridDim.x * blockDim.x) >> 5;
     const int k = (int)lane();
     for (uint32_t c = warpGlobal; c < nCells; c += nWarps) {
-        if (partials) {
-            const uint32_t w0 = workOfs[c], w1 = workOfs[c + 1];
+        const float *st = stats + (size_t)c * stride;
+        PG_MSTEP_BODY(c, st)
+    }
+}
+
+// Single-GPU path: the per-cell sum of the chunk partials (k_reduce_partials' job) folded in -- one launch and one round
+// trip of the statistics less per EM iteration. ONE BLOCK PER CELL: a cell owns between one and several hundred chunks
+// (a few cells in front of the light hold most of the samples), and a single warp walking them one dependent load at a
+// time made the whole launch wait for the heaviest cell (ncu launch list r01_v5: 120 us at 788 cells). The block's
+// 8 warps take the chunks round-robin, 4 loads in flight each, in double; warp 0 adds the 8 partial sums in warp order
+// (a fixed order: results do not depend on scheduling) and refits the cell.
+static constexpr int kMstepWarps = 8;
+__global__ void __launch_bounds__(kMstepWarps * 32) k_mstep_partials(float4 *__restrict__ lobes, float4 *__restrict__ lobeStats,
+                                                                     float *__restrict__ stats, uint32_t nCells, int K, int stride,
+                                                                     int commit, const float *__restrict__ partials,
+                                                                     const uint32_t *__restrict__ workOfs) {
+    __shared__ double sAcc[kMstepWarps][4 * kGuideMaxK + 8];
+    const int k = (int)lane(), warp = (int)(threadIdx.x >> 5);
+    for (uint32_t c = blockIdx.x; c < nCells; c += gridDim.x) {
+        const uint32_t w0 = workOfs[c], w1 = workOfs[c + 1];
+        for (int e = k; e < stride; e += 32) {
+            double acc = 0.0;
+            uint32_t w = w0 + (uint32_t)warp;
+            for (; w + 3 * kMstepWarps < w1; w += 4 * kMstepWarps) {
+                const float v0 = __ldcs(partials + (size_t)w * stride + e);
+                const float v1 = __ldcs(partials + (size_t)(w + kMstepWarps) * stride + e);
+                const float v2 = __ldcs(partials + (size_t)(w + 2 * kMstepWarps) * stride + e);
+                const float v3 = __ldcs(partials + (size_t)(w + 3 * kMstepWarps) * stride + e);
+                acc += (double)v0;
+                acc += (double)v1;
+                acc += (double)v2;
+                acc += (double)v3;
+            }
+            for (; w < w1; w += kMstepWarps) acc += (double)__ldcs(partials + (size_t)w * stride + e);
+            sAcc[warp][e] = acc;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            float *own = stats + (size_t)c * stride;
             for (int e = k; e < stride; e += 32) {
                 double acc = 0.0;
-                for (uint32_t w = w0; w < w1; ++w) acc += (double)partials[(size_t)w * stride + e];
-                stats[(size_t)c * stride + e] = (float)acc;
+#pragma unroll
+                for (int j = 0; j < kMstepWarps; ++j) acc += sAcc[j][e];
+                own[e] = (float)acc;
             }
             __syncwarp();
+            const float *st = own;
+            PG_MSTEP_BODY(c, st)
         }
-        const float *st = stats + (size_t)c * stride;
-        float4 a = make_float4(0, 0, 0, 0), b = a, s = a;
-        float S = 0, R0 = 0, R1 = 0, R2 = 0;
-        if (k < K) {
-            const float4 *L = lobes + ((size_t)c * K + k) * 2;
-            a = L[0];
-            b = L[1];
-            s = lobeStats[(size_t)c * K + k];
-            S = kGuideDecay * s.x + st[4 * k];
-            R0 = kGuideDecay * s.y + st[4 * k + 1];
-            R1 = kGuideDecay * s.z + st[4 * k + 2];
-            R2 = kGuideDecay * s.w + st[4 * k + 3];
-        }
-        float sumS = S;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sumS += __shfl_xor_sync(0xffffffffu, sumS, o);
-        if (k < K) {
-            if (sumS > 0 && isfinite(sumS)) {
-                const float prior = kGuidePriorWeight * sumS / (float)K;
-                const float denom = 1.0f / (sumS + (float)K * prior);
-                a.x = (S + prior) * denom;
-                const float rl = sqrtf(R0 * R0 + R1 * R1 + R2 * R2);
-                float rbar = (rl + prior * kGuidePriorMeanCos) / (S + prior);
-                rbar = fminf(rbar, 0.9999f);
-                const float kappa = rbar * (3.0f - rbar * rbar) / (1.0f - rbar * rbar);
-                b.x = fminf(kGuideKappaMax, fmaxf(kGuideKappaMin, kappa));
-                if (rl > 0) {
-                    const float ir = 1.0f / rl;
-                    a.y = R0 * ir;
-                    a.z = R1 * ir;
-                    a.w = R2 * ir;
-                }
-                b.z = expf(-2.0f * b.x);
-                b.y = b.x / (2 * kPi * (1.0f - b.z));
-            }
-            float4 *L = lobes + ((size_t)c * K + k) * 2;
-            L[0] = a;
-            L[1] = b;
-            if (commit) lobeStats[(size_t)c * K + k] = make_float4(S, R0, R1, R2);
-        }
+        __syncthreads();
     }
 }
 
@@ -1084,8 +1125,7 @@ void GuidingHost::estepOnly() {
 
 void GuidingHost::update(bool commit) {
     const int stride = (int)statsStride();
-    k_mstep<<<gridFor((size_t)numCells() * 32, 256), 256, 0, stream>>>(dLobes.p, dLobeStats.p, dStats.p, numCells(), K, stride, commit ? 1 : 0,
-                                                                       nullptr, nullptr);
+    k_mstep<<<gridFor((size_t)numCells() * 32, 256), 256, 0, stream>>>(dLobes.p, dLobeStats.p, dStats.p, numCells(), K, stride, commit ? 1 : 0);
     launches++;
 }
 
@@ -1136,8 +1176,8 @@ void GuidingHost::train(int nIter) {
             launches++;
         } else {  // single GPU: the per-cell sum of the partials is folded into the M-step kernel
             estepOnly();
-            k_mstep<<<gridFor((size_t)numCells() * 32, 256), 256, 0, stream>>>(dLobes.p, dLobeStats.p, dStats.p, numCells(), K, stride,
-                                                                               commit ? 1 : 0, dPartials.p, dWorkOfs.p);
+            k_mstep_partials<<<gridFor((size_t)numCells() * kMstepWarps * 32, kMstepWarps * 32), kMstepWarps * 32, 0, stream>>>(
+                dLobes.p, dLobeStats.p, dStats.p, numCells(), K, stride, commit ? 1 : 0, dPartials.p, dWorkOfs.p);
             launches++;
         }
     }
