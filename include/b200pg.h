@@ -244,6 +244,16 @@ int b200pg_comm_local_handle(void *integ, void *handle64);
 int b200pg_comm_connect(void *integ, int rank, int world, const void *handles);
 
 int b200pg_film_clear(void *integ);
+/* Denoiser feature buffers (src/librender/denoiser.cpp:138-144, Denoiser::add: per-pixel running means of the sample
+ * colour, albedo and normal over the samples that fall into the pixel). Enabled by b200pg_set_option("feature_buffers", 1)
+ * before rendering; cleared by b200pg_film_clear. The reference never fills Sample::albedo / normal (nothing in its tree
+ * calls the denoiser), so: first intersection of the camera ray; albedo = diffuse reflectance (diffuse, roughplastic),
+ * specular reflectance (roughconductor), 1 (dielectric, null); normal = shading normal (world space); both 0 for rays
+ * that leave the scene. b200pg_features_read: out = H*W*10 floats {color.rgb, albedo.rgb, normal.xyz, sample count};
+ * b200pg_features_write: float32 OpenEXR with the layers color / albedo / normal of Denoiser::saveBuffers
+ * (denoiser.cpp:88-112). */
+int b200pg_features_read(void *integ, float *out);
+int b200pg_features_write(void *integ, const char *path);
 /* Multi-GPU film merge, one process per GPU (every GPU keeps a full-size film of its own sample batches; the
  * reference merges its workers' ImageBlocks in Film::put, renderproc.cpp:141-148). b200pg_film_ipc_handle returns the
  * 64-byte CUDA IPC handle of this handle's device film; b200pg_film_add_peers(rank, world, handles = world x 64 bytes)
@@ -272,7 +282,8 @@ void b200pg_destroy(void *integ);
  *            prims_tested), "timing" (0/1: per-stage CUDA events), "sort_bounces" (n: guided surface progressions
  *            shade bounces 1..n through a permutation that groups the queued paths by guiding cell; 0 = queue order;
  *            default 0, or the value of the environment variable
- *            B200PG_SORT_BOUNCES; per-path results do not depend on it).
+ *            B200PG_SORT_BOUNCES; per-path results do not depend on it), "feature_buffers" (0/1: accumulate the denoiser
+ *            feature buffers, see b200pg_features_read).
  *   stage times: 5 doubles / 5 launch counts = trace(closest), shade, shadow(any-hit), film, train.
  *   scene_upload: re-sends the compiled scene host->device (bench.py's end-to-end leg). */
 int b200pg_set_option(void *integ, const char *name, int value);

@@ -78,6 +78,8 @@ def lib():
     L.b200pg_comm_connect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.b200pg_field_snapshot.argtypes = [C.c_void_p, u32p, C.POINTER(C.c_size_t)]
     L.b200pg_field_load.argtypes = [C.c_void_p, u32p, C.c_size_t]
+    L.b200pg_features_read.argtypes = [C.c_void_p, fp]
+    L.b200pg_features_write.argtypes = [C.c_void_p, C.c_char_p]
     L.b200pg_film_ipc_handle.argtypes = [C.c_void_p, C.c_void_p]
     L.b200pg_film_add_peers.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.b200pg_k_em_exchange.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_float)]
@@ -210,6 +212,15 @@ class Integrator:
         out = np.zeros((self.H, self.W, 3), np.float32)
         _check(lib().b200pg_film_develop(self.h, _f(out)))
         return out
+
+    def features(self):
+        """Denoiser feature buffers (H, W, 10) = color.rgb, albedo.rgb, normal.xyz, sample count (set_option("feature_buffers", 1))."""
+        out = np.zeros((self.H, self.W, 10), np.float32)
+        _check(lib().b200pg_features_read(self.h, _f(out)))
+        return out
+
+    def features_write(self, path):
+        _check(lib().b200pg_features_write(self.h, path.encode()))
 
     def film_write(self, path):
         _check(lib().b200pg_film_write(self.h, path.encode()))

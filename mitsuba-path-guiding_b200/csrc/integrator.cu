@@ -38,6 +38,8 @@ void launchShadow(const DeviceScene &S, const ShadowQueue &Q, float4 *rad, const
 void launchShade(const ShadeArgs &A, cudaStream_t st);
 void launchFlush(const ShadeArgs &A, cudaStream_t st);
 void launchFilmAdd(float4 *film, const float4 *peer, uint32_t n, cudaStream_t st);
+void launchFeatures(const DeviceScene &S, const PathState &P, const float4 *hits, const uint32_t *nPtr, float4 *feat, cudaStream_t st);
+void launchFeatureColor(const FilmRecord &F, const float4 *splat, uint32_t n, float maxComponentValue, float4 *feat, cudaStream_t st);
 // volpath.cu
 void launchShadeVol(const ShadeArgs &A, cudaStream_t st);
 void launchShadowVol(const DeviceScene &S, const ShadowQueue &Q, float4 *rad, const uint32_t *nPtr, uint32_t *work, Counters *C,
@@ -112,6 +114,9 @@ struct Integrator {
     // DESIGN.md, optimisation log 7; B200PG_SORT_BOUNCES / b200pg_set_option("sort_bounces") turn it on)
     int sortBounces = std::getenv("B200PG_SORT_BOUNCES") ? std::atoi(std::getenv("B200PG_SORT_BOUNCES")) : 0;
     DevBuf<uint32_t> dSortKey, dSortRank, dSortPerm, dBinCount, dBinOffset;
+    // denoiser feature buffers (denoiser.cpp:138-144): 3 float4 per pixel, allocated by set_option("feature_buffers", 1)
+    bool featureBuffers = false;
+    DevBuf<float4> dFeat;
 
     B200pgStats stats;
     cudaEvent_t ev[8];
@@ -310,6 +315,10 @@ struct Integrator {
             launchTrace(S, cur, dHits.p, &C->queue[b], &C->traceWork[b], C, countTraversal, sorted ? &sortArgs : nullptr, stream);
             if (sorted) stats.kernel_launches += 2;
             spanEnd(kTimeTrace, t);
+            if (b == 0 && featureBuffers && !radianceOut) {
+                launchFeatures(S, cur, dHits.p, &C->queue[0], dFeat.p, stream);
+                stats.kernel_launches++;
+            }
             A.perm = sorted ? dSortPerm.p : nullptr;
             A.cur = cur;
             A.next = next;
@@ -344,8 +353,12 @@ struct Integrator {
         if (!radianceOut && !cancel.load()) {  // every path of the batch has ended exactly once: rasterise them
             cudaEvent_t t = spanBegin();
             launchSplat(S.film, dFilm.p, dSplat.p, B.nPaths, params.max_component_value, stream);
-            spanEnd(kTimeFilm, t);
             stats.kernel_launches++;
+            if (featureBuffers) {
+                launchFeatureColor(S.film, dSplat.p, B.nPaths, params.max_component_value, dFeat.p, stream);
+                stats.kernel_launches++;
+            }
+            spanEnd(kTimeFilm, t);
         }
     }
 
@@ -599,6 +612,7 @@ int b200pg_cancel(void *integ) {
 int b200pg_film_clear(void *integ) {
     PG_TRY(integ)
     CUDA_OK(cudaMemsetAsync(self->dFilm.p, 0, self->dFilm.n * sizeof(float4), self->stream));
+    if (self->dFeat.p) CUDA_OK(cudaMemsetAsync(self->dFeat.p, 0, self->dFeat.n * sizeof(float4), self->stream));
     CUDA_OK(cudaStreamSynchronize(self->stream));
     PG_END
 }
@@ -719,8 +733,16 @@ static bool writePfm(const char *path, const float *rgb, int W, int H) {
     return std::fclose(f) == 0;
 }
 
-// Scanline OpenEXR, single part, no compression, channels B, G, R (alphabetical, as the format requires)
-static bool writeExr(const char *path, const float *rgb, int W, int H, bool half) {
+// Scanline OpenEXR, single part, no compression. Channels must be given in alphabetical order of their names (the
+// format stores them sorted); channel c of pixel i is chans[c].base[i * chans[c].stride].
+struct ExrChannel {
+    std::string name;
+    const float *base;
+    size_t stride;
+};
+static bool writeExrChannels(const char *path, const std::vector<ExrChannel> &chans, int W, int H, bool half) {
+    for (size_t c = 1; c < chans.size(); ++c)
+        if (!(chans[c - 1].name < chans[c].name)) return false;
     FILE *f = std::fopen(path, "wb");
     if (!f) return false;
     std::vector<unsigned char> hdr;
@@ -732,9 +754,11 @@ static bool writeExr(const char *path, const float *rgb, int W, int H, bool half
     const uint32_t magic = 20000630u;
     put(&magic, 4);
     putI(2);  // version 2, scanline, single part
-    attr("channels", "chlist", 3 * 18 + 1);
-    for (const char *c : {"B", "G", "R"}) {
-        putStr(c);
+    int32_t chlist = 1;
+    for (const auto &c : chans) chlist += (int32_t)c.name.size() + 1 + 16;
+    attr("channels", "chlist", chlist);
+    for (const auto &c : chans) {
+        putStr(c.name.c_str());
         putI(half ? 1 : 2);  // HALF / FLOAT
         const unsigned char lin[4] = {0, 0, 0, 0};
         put(lin, 4);
@@ -757,7 +781,7 @@ static bool writeExr(const char *path, const float *rgb, int W, int H, bool half
     attr("screenWindowWidth", "float", 4);
     putF(1.0f);
     hdr.push_back(0);
-    const size_t bpc = half ? 2 : 4, lineBytes = (size_t)W * 3 * bpc;
+    const size_t bpc = half ? 2 : 4, nc = chans.size(), lineBytes = (size_t)W * nc * bpc;
     std::fwrite(hdr.data(), 1, hdr.size(), f);
     uint64_t offset = hdr.size() + (uint64_t)H * 8;
     for (int y = 0; y < H; ++y) {
@@ -769,21 +793,23 @@ static bool writeExr(const char *path, const float *rgb, int W, int H, bool half
         const int32_t yy = y, sz = (int32_t)lineBytes;
         std::fwrite(&yy, 4, 1, f);
         std::fwrite(&sz, 4, 1, f);
-        for (int c = 0; c < 3; ++c) {  // B, G, R planes of the scanline
-            const int src = 2 - c;
+        for (size_t c = 0; c < nc; ++c) {  // one plane per channel inside the scanline
             for (int x = 0; x < W; ++x) {
-                const float v = rgb[((size_t)y * W + x) * 3 + src];
+                const float v = chans[c].base[((size_t)y * W + x) * chans[c].stride];
                 if (half) {
                     const uint16_t h = floatToHalf(v);
-                    std::memcpy(&line[((size_t)c * W + x) * 2], &h, 2);
+                    std::memcpy(&line[(c * W + x) * 2], &h, 2);
                 } else {
-                    std::memcpy(&line[((size_t)c * W + x) * 4], &v, 4);
+                    std::memcpy(&line[(c * W + x) * 4], &v, 4);
                 }
             }
         }
         std::fwrite(line.data(), 1, lineBytes, f);
     }
     return std::fclose(f) == 0;
+}
+static bool writeExr(const char *path, const float *rgb, int W, int H, bool half) {
+    return writeExrChannels(path, {{"B", rgb + 2, 3}, {"G", rgb + 1, 3}, {"R", rgb, 3}}, W, H, half);
 }
 
 // Radiance RGBE, flat (uncompressed) scanlines, top to bottom (bitmap.cpp writeRGBE / rgbe.cpp)
@@ -833,6 +859,45 @@ int b200pg_film_write(void *integ, const char *path) {
     return 0;
 }
 
+// Denoiser feature buffers (denoiser.cpp:138-144): out = H*W*10 floats {color.rgb, albedo.rgb, normal.xyz, sample count}
+int b200pg_features_read(void *integ, float *out) {
+    PG_TRY(integ)
+    if (!out) return fail("null argument");
+    if (!self->dFeat.p) return fail("feature buffers are not enabled (b200pg_set_option(\"feature_buffers\", 1))");
+    const size_t n = self->dFilm.n;
+    std::vector<float4> h(n * 3);
+    CUDA_OK(cudaMemcpyAsync(h.data(), self->dFeat.p, n * 3 * sizeof(float4), cudaMemcpyDeviceToHost, self->stream));
+    CUDA_OK(cudaStreamSynchronize(self->stream));
+    for (size_t i = 0; i < n; ++i) {
+        const float4 c = h[3 * i], a = h[3 * i + 1], nn = h[3 * i + 2];
+        const float ic = c.w > 0 ? 1.0f / c.w : 0.0f, ia = a.w > 0 ? 1.0f / a.w : 0.0f;
+        float *o = out + 10 * i;
+        o[0] = c.x * ic; o[1] = c.y * ic; o[2] = c.z * ic;
+        o[3] = a.x * ia; o[4] = a.y * ia; o[5] = a.z * ia;
+        o[6] = nn.x * ia; o[7] = nn.y * ia; o[8] = nn.z * ia;
+        o[9] = a.w;
+    }
+    PG_END
+}
+
+// Multi-channel OpenEXR (float32) with the layer names Denoiser::saveBuffers uses (denoiser.cpp:88-112): color, albedo,
+// normal (normal.R/G/B = x/y/z)
+int b200pg_features_write(void *integ, const char *path) {
+    if (!integ || !path) return fail("null argument");
+    Integrator *self = (Integrator *)integ;
+    const int W = self->scene->film.width, H = self->scene->film.height;
+    std::vector<float> f((size_t)W * H * 10);
+    int r = b200pg_features_read(integ, f.data());
+    if (r) return r;
+    const float *b = f.data();
+    const std::vector<ExrChannel> chans = {{"albedo.B", b + 5, 10}, {"albedo.G", b + 4, 10}, {"albedo.R", b + 3, 10},
+                                           {"color.B", b + 2, 10},  {"color.G", b + 1, 10},  {"color.R", b + 0, 10},
+                                           {"normal.B", b + 8, 10}, {"normal.G", b + 7, 10}, {"normal.R", b + 6, 10}};
+    if (!writeExrChannels(path, chans, W, H, false)) return fail(std::string("cannot write ") + path);
+    return 0;
+}
+
+
 int b200pg_stats(void *integ, B200pgStats *out) {
     if (!integ || !out) return fail("null argument");
     Integrator *self = (Integrator *)integ;
@@ -851,6 +916,17 @@ int b200pg_set_option(void *integ, const char *name, int value) {
     if (n == "count_traversal") self->countTraversal = value != 0;
     else if (n == "timing") self->timing = value != 0;
     else if (n == "sort_bounces") self->sortBounces = value;
+    else if (n == "feature_buffers") {
+        self->featureBuffers = value != 0;
+        if (self->featureBuffers && !self->dFeat.p) {
+            try {
+                CUDA_OK(cudaSetDevice(self->device));
+                self->dFeat.allocExact(self->dFilm.n * 3);
+                CUDA_OK(cudaMemsetAsync(self->dFeat.p, 0, self->dFeat.n * sizeof(float4), self->stream));
+                CUDA_OK(cudaStreamSynchronize(self->stream));
+            } catch (const std::exception &e) { return fail(e.what()); }
+        }
+    }
     else return fail("unknown option " + n);
     return 0;
 }

@@ -564,6 +564,50 @@ __global__ void __launch_bounds__(256) k_splat(FilmRecord F, float4 *film, const
     }
 }
 
+// Denoiser feature buffers (src/librender/denoiser.cpp:138-144, Denoiser::add keeps per-pixel running means of the sample
+// colour, albedo and normal; here: per-pixel sums + counts, divided on read). feat = 3 float4 per pixel:
+// {colour sum, #colour samples} {albedo sum, #samples} {normal sum, 0}. The reference never fills albedo / normal (nothing
+// calls its denoiser), so the definitions are this repo's: first intersection of the camera ray; albedo =
+// diffuse reflectance (diffuse, roughplastic), specular reflectance (roughconductor), 1 (dielectric, null); normal =
+// shading normal; 0 when the ray leaves the scene. k_features runs once per batch after the first trace.
+__global__ void __launch_bounds__(256) k_features(DeviceScene S, PathState P, const float4 *__restrict__ hits, const uint32_t *nPtr,
+                                                  float4 *feat) {
+    const uint32_t n = *nPtr;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 ro = P.rayO[i], rd = P.rayD[i], pos4 = P.pos[i], h4 = hits[i];
+        const int px = min(max((int)pos4.x, 0), S.film.width - 1), py = min(max((int)pos4.y, 0), S.film.height - 1);
+        const size_t pixel = (size_t)py * S.film.width + px;
+        float3 albedo = f3(0.0f), normal = f3(0.0f);
+        Hit h;
+        h.t = h4.x;
+        h.u = h4.y;
+        h.v = h4.z;
+        h.prim = __float_as_uint(h4.w);
+        if (h.prim != kMiss) {
+            Intersection its;
+            fillIntersection(S, f3(ro.x, ro.y, ro.z), f3(rd.x, rd.y, rd.z), h, its);
+            const BsdfRecord &b = S.bsdfs[its.bsdf];
+            albedo = (b.type == B200PG_BSDF_DIFFUSE || b.type == B200PG_BSDF_ROUGHPLASTIC) ? ld3(b.reflectance)
+                     : (b.type == B200PG_BSDF_ROUGHCONDUCTOR ? ld3(b.specRefl) : f3(1.0f));
+            normal = its.sh.n;
+        }
+        atomicAdd(feat + 3 * pixel + 1, make_float4(albedo.x, albedo.y, albedo.z, 1.0f));
+        atomicAdd(feat + 3 * pixel + 2, make_float4(normal.x, normal.y, normal.z, 0.0f));
+    }
+}
+__global__ void __launch_bounds__(256) k_feature_color(FilmRecord F, const float4 *__restrict__ splat, uint32_t n, float maxComponentValue,
+                                                       float4 *feat) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 a = splat[2 * (size_t)i], b = splat[2 * (size_t)i + 1];
+        float3 spec = f3(a.z, a.w, b.x);
+        const float maxSpec = maxComp(spec);
+        if (maxSpec > maxComponentValue) spec = spec * (maxComponentValue / maxSpec);
+        if (!(isfinite(spec.x) && isfinite(spec.y) && isfinite(spec.z)) || spec.x < 0 || spec.y < 0 || spec.z < 0) continue;
+        const int px = min(max((int)a.x, 0), F.width - 1), py = min(max((int)a.y, 0), F.height - 1);
+        atomicAdd(feat + 3 * ((size_t)py * F.width + px), make_float4(spec.x, spec.y, spec.z, 1.0f));
+    }
+}
+
 // Flush whatever is still queued after the last bounce (only parked/dead records can remain).
 __global__ void __launch_bounds__(256) k_flush(ShadeArgs A) {
     const uint32_t n = A.C->queue[A.bounce];
@@ -665,6 +709,12 @@ void launchSplat(const FilmRecord &F, float4 *film, const float4 *splat, uint32_
 }
 void launchFilmExport(const float4 *film, float *out, uint32_t n, int develop, cudaStream_t st) {
     k_film_export<<<numSMs() * 4, 256, 0, st>>>(film, out, n, develop);
+}
+void launchFeatures(const DeviceScene &S, const PathState &P, const float4 *hits, const uint32_t *nPtr, float4 *feat, cudaStream_t st) {
+    k_features<<<numSMs() * 4, 256, 0, st>>>(S, P, hits, nPtr, feat);
+}
+void launchFeatureColor(const FilmRecord &F, const float4 *splat, uint32_t n, float maxComponentValue, float4 *feat, cudaStream_t st) {
+    k_feature_color<<<numSMs() * 4, 256, 0, st>>>(F, splat, n, maxComponentValue, feat);
 }
 void launchFilmAdd(float4 *film, const float4 *peer, uint32_t n, cudaStream_t st) {
     k_film_add<<<numSMs() * 4, 256, 0, st>>>(film, peer, n);

@@ -943,6 +943,52 @@ int orc_radiance(void *s, const B200pgIntegratorParams *P, const uint32_t *pixel
     return 0;
 }
 
+// Denoiser feature buffers (src/librender/denoiser.cpp:138-144, Denoiser::add): per-pixel RUNNING MEANS of the sample colour,
+// the albedo and the normal over the samples of the pixel (box: every sample counts for the pixel its position falls in).
+// The reference never fills Sample::albedo / normal (nothing in the tree calls the denoiser), so the definitions are
+// this repo's (DESIGN.md "Feature buffers"): first intersection of the camera ray; albedo = diffuse reflectance
+// (diffuse, roughplastic), specular reflectance (roughconductor), 1 (dielectric, null); normal = shading normal
+// (world space); both 0 when the ray leaves the scene. out: H*W*10 = {color.rgb, albedo.rgb, normal.xyz, sample count}.
+static Vec3 featureAlbedo(const Bsdf &b) {
+    switch (b.d.type) {
+        case B200PG_BSDF_DIFFUSE:
+        case B200PG_BSDF_ROUGHPLASTIC: return b.R();
+        case B200PG_BSDF_ROUGHCONDUCTOR: return b.SR();
+        default: return Vec3(1.0f);
+    }
+}
+int orc_features(void *s, const B200pgIntegratorParams *P, int first_sample, int n_samples, float *out) {
+    Scene *sc = (Scene *)s;
+    const int W = sc->film.width, H = sc->film.height;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long long pix = 0; pix < (long long)W * H; ++pix) {
+        float *o = out + 10 * pix;
+        const int x = (int)(pix % W), y = (int)(pix / W);
+        for (int j = 0; j < n_samples; ++j) {
+            Rng rng;
+            rng.init(sc->seed, (uint32_t)pix, (uint32_t)(first_sample + j));
+            Vec2 off = rng.next2D();
+            Vec2 samplePos(x + off.x, y + off.y);
+            Ray ray = sc->sampleRay(samplePos);
+            Stats st;
+            Intersection its;
+            Vec3 albedo(0.0f), normal(0.0f);
+            if (sc->rayIntersect(ray, its, &st) && its.isValid()) {
+                albedo = featureAlbedo(sc->bsdfOf(sc->shapes[its.shape]));
+                normal = its.shFrame.n;
+            }
+            Vec3 L = Li(*sc, *P, ray, rng, st, nullptr);
+            float maxSpec = L.maxc();
+            if (maxSpec > P->max_component_value) L *= P->max_component_value / maxSpec;
+            o[9] += 1.0f;
+            const float a = 1.0f / o[9];  // Denoiser::add
+            const float v[9] = {L.x, L.y, L.z, albedo.x, albedo.y, albedo.z, normal.x, normal.y, normal.z};
+            for (int k = 0; k < 9; ++k) o[k] = (1.0f - a) * o[k] + a * v[k];
+        }
+    }
+    return 0;
+}
+
 // GridDataSource::lookupFloat on a batch of points (gridvolume.cpp:337-388)
 int orc_grid_lookup(void *s, int medium, const float *p, size_t n, float *out) {
     Scene *sc = (Scene *)s;

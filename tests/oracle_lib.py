@@ -43,6 +43,7 @@ class Oracle:
         L.orc_phase.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_size_t, fp, fp, fp]
         L.orc_render.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), C.c_int, C.c_int, C.c_int, C.c_int, fp,
                                  C.c_int, u64p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
+        L.orc_features.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), C.c_int, C.c_int, fp]
         L.orc_field_create.restype = C.c_void_p
         L.orc_field_create.argtypes = [C.c_int, fp, fp]
         L.orc_field_destroy.argtypes = [C.c_void_p]
@@ -285,6 +286,13 @@ class OracleScene:
         film = np.zeros((self.H, self.W, 5), np.float32)
         self.L.orc_film_splat(self.h, _f(pos), _f(rgb), pos.shape[0], _f(film))
         return film
+
+    def features(self, params, first_sample=0, n_samples=1, out=None):
+        """Denoiser feature buffers (denoiser.cpp:138-144): (H, W, 10) running means {color, albedo, normal, count}."""
+        if out is None:
+            out = np.zeros((self.H, self.W, 10), np.float32)
+        assert self.L.orc_features(self.h, C.byref(params), first_sample, n_samples, _f(out)) == 0
+        return out
 
     def render(self, params, first_sample=0, n_samples=1, rows=None, film=None, nthreads=0, field=None, sink=None):
         if film is None:
