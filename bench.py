@@ -9,7 +9,9 @@
 A "step" = one guiding TRAINING ITERATION of the guided path tracer: one progression (``--spp-per-step`` samples per
 pixel, recording path-vertex samples and sampling from the current field) over the whole image, followed by the
 training update (radix-sort binning, ``--em-iters`` weighted-EM iterations, spatial split). With N > 1 GPUs the
-per-cell EM sufficient statistics are summed with one NCCL allreduce per EM iteration (the only data-path collective).
+per-cell EM sufficient statistics are summed over the ranks once per EM iteration -- the only exchange on the data path --
+inside the library's M-step kernel over NVLink peer memory (CUDA IPC; torch.distributed only carries the 64-byte handles
+and the final film reduce); ``--nccl-allreduce`` runs the NCCL allreduce variant for comparison.
 value = camera paths completed per second (whole job, all ranks), device-timed with CUDA events, scene resident in HBM. e2e = same metric through the C-ABI with host buffers: per step the
 compiled scene is re-sent host->device and the film is read back device->host.
 """
