@@ -1158,13 +1158,62 @@ struct Loader {
         }
     }
 
-    bool haveSensor = false;
+    bool haveSensor = false, haveIntegrator = false;
     int includeDepth = 0;
+
+    // Scene::configure (scene.cpp:279-305): "No sensors found! Adding a perspective camera.." -- 45 degree field of view,
+    // placed on the -z side of the shapes' bounding box so that it sees the whole scene; default film and sampler.
+    void defaultSensor() {
+        float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
+        auto grow = [&](const float *p) {
+            for (int a = 0; a < 3; ++a) {
+                mn[a] = std::min(mn[a], p[a]);
+                mx[a] = std::max(mx[a], p[a]);
+            }
+        };
+        for (const B200pgShape &s : H.shapes) {
+            if (s.type == B200PG_SHAPE_RECTANGLE) {
+                for (int c = 0; c < 4; ++c) {
+                    const float x = (c & 1) ? 1.0f : -1.0f, y = (c & 2) ? 1.0f : -1.0f;
+                    const float *m = s.to_world;
+                    const float p[3] = {m[0] * x + m[1] * y + m[3], m[4] * x + m[5] * y + m[7], m[8] * x + m[9] * y + m[11]};
+                    grow(p);
+                }
+            } else {
+                for (uint32_t v = 0; v < s.n_vertices; ++v) grow(s.positions + 3 * (size_t)v);
+            }
+        }
+        B200pgSensor &S = H.sensor;
+        std::memset(&S, 0, sizeof(S));
+        M4 tw = translate(0, 0, 0);
+        S.fov = 45.0f;
+        S.fov_axis = 0;
+        S.near_clip = 1e-2f;
+        S.far_clip = 1e4f;
+        S.medium = -1;
+        if (mn[0] <= mx[0]) {
+            const float ext[3] = {mx[0] - mn[0], mx[1] - mn[1], mx[2] - mn[2]};
+            const float maxXY = std::max(ext[0], ext[1]);
+            const float distance = maxXY / (2.0f * std::tan(45 * 0.5f * 3.14159265358979323846f / 180));
+            const float maxXYZ = std::max(ext[2], maxXY);
+            S.far_clip = maxXYZ * 5 + distance;
+            S.near_clip = distance / 100;
+            tw = translate(0.5f * (mn[0] + mx[0]), 0.5f * (mn[1] + mx[1]), mn[2] - distance);
+        }
+        std::memcpy(S.to_world, tw.m, sizeof(tw.m));
+        H.film.width = 768;  // film.cpp:29-32, hdrfilm.cpp:207-220, independent.cpp:57
+        H.film.height = 576;
+        H.film.filter_stddev = 0.5f;
+        H.film.file_format = 0;
+        H.film.component_format = 0;
+        H.sampleCount = 4;
+        H.seed = 1337;
+    }
 
     void parseChildren(const XmlNode &root) {
         for (auto &c : root.children) {
             if (c->tag == "default") continue;
-            if (c->tag == "integrator") parseIntegrator(*c);
+            if (c->tag == "integrator") { parseIntegrator(*c); haveIntegrator = true; }
             else if (c->tag == "sensor") { parseSensor(*c); haveSensor = true; }
             else if (c->tag == "bsdf") parseBsdf(*c);
             else if (c->tag == "medium") parseMedium(*c);
@@ -1208,9 +1257,13 @@ struct Loader {
         if (root.tag != "scene") fail("the root element must be <scene>");
         if (!root.has("version")) fail("The scene is missing a version attribute!");  // scenehandler.cpp:228-233
         b200pg_integrator_params_default(&H.xmlParams);
-        haveSensor = false;
+        haveSensor = haveIntegrator = false;
         parseChildren(root);
-        if (!haveSensor) fail("the scene needs a perspective <sensor> (the reference's default sensor fallback, scene.cpp:272-312, is not replicated)");
+        if (!haveSensor) defaultSensor();
+        // Scene::configure (scene.cpp:272-277) falls back to the `direct` integrator: emitted radiance + direct illumination.
+        // `direct` itself is not on the accelerated path; the path tracer with maxDepth = 2 computes the same quantity
+        // (same expectation; the reference's default takes one emitter and one BSDF sample per shading point as well)
+        if (!haveIntegrator) H.xmlParams.max_depth = 2;
     }
 };
 

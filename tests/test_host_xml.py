@@ -250,3 +250,33 @@ def test_include_alias_and_srgb(api, tmp_path):
     bad2.write_text(_scene('<include filename="missing.xml"/>' + body).replace("$spp", "4"))
     with pytest.raises(api.B200pgError, match="include"):
         api.Scene.load_xml(str(bad2))
+
+
+def test_default_sensor_and_integrator_fallbacks(api, tmp_path):
+    """Scene::configure (scene.cpp:272-305): a scene without <sensor> gets a 45-degree perspective camera on the -z side of
+    the shapes' bounding box (default film 768x576 and independent sampler, 4 spp); a scene without <integrator> renders
+    direct illumination (`direct` in the reference, maxDepth = 2 here)."""
+    path = tmp_path / "min.xml"
+    path.write_text('''<scene version="0.6.0">
+      <shape type="rectangle"><transform name="toWorld"><scale x="2" y="1"/><translate x="1" y="3" z="5"/></transform></shape>
+      <shape type="cube"><transform name="toWorld"><scale value="0.5"/><translate x="0" y="3" z="8"/></transform>
+        <emitter type="area"><rgb name="radiance" value="2"/></emitter></shape>
+    </scene>''')
+    sc = api.Scene.load_xml(str(path))
+    d = sc.desc
+    assert (d.film.width, d.film.height, d.sample_count) == (768, 576, 4)
+    # bounding box: x in [-1, 3], y in [2, 4], z in [5, 8.5]
+    ext_xy, ext_z = 4.0, 3.5
+    dist = ext_xy / (2 * np.tan(np.radians(22.5)))
+    assert d.sensor.fov == 45.0 and d.sensor.fov_axis == 0
+    np.testing.assert_allclose(d.sensor.near_clip, dist / 100, rtol=1e-6)
+    np.testing.assert_allclose(d.sensor.far_clip, max(ext_z, ext_xy) * 5 + dist, rtol=1e-6)
+    m = np.array(d.sensor.to_world[:]).reshape(4, 4)
+    np.testing.assert_allclose(m[:3, :3], np.eye(3), atol=0)
+    np.testing.assert_allclose(m[:3, 3], [1.0, 3.0, 5.0 - dist], atol=2e-6)   # (5 - 4.83: float cancellation)
+    p = sc.integrator_params()
+    assert p.max_depth == 2 and p.guiding == 0 and p.volumetric == 0
+    # an explicit integrator keeps its own defaults
+    path2 = tmp_path / "min2.xml"
+    path2.write_text(path.read_text().replace("</scene>", '<integrator type="path"/></scene>'))
+    assert api.Scene.load_xml(str(path2)).integrator_params().max_depth == -1
