@@ -888,6 +888,28 @@ int orc_camera_rays(void *s, const float *pos, size_t n, float *rays) {
     return 0;
 }
 
+// MicrofacetDistribution on its own (src/tests/test_microfacet.cpp drives the class directly): for a fixed incident
+// direction wi, out_m[i] = sampleVisible(wi, u[i]) when u != NULL; for every normal m[i] (the sampled ones, or the given
+// ones when u == NULL): pdfVisible(wi, m), D(m) = eval(m) and smithG1(wi, m).
+int orc_microfacet(int type, float alphaU, float alphaV, const float *wi, const float *u, float *m, size_t n, float *out_pdf,
+                   float *out_D, float *out_G1) {
+    MicrofacetDistribution distr(type, alphaU, alphaV);
+    const Vec3 vi(wi[0], wi[1], wi[2]);
+    for (size_t i = 0; i < n; ++i) {
+        Vec3 mm;
+        if (u) {
+            mm = distr.sampleVisible(vi, Vec2(u[2 * i], u[2 * i + 1]));
+            m[3 * i] = mm.x; m[3 * i + 1] = mm.y; m[3 * i + 2] = mm.z;
+        } else {
+            mm = Vec3(m[3 * i], m[3 * i + 1], m[3 * i + 2]);
+        }
+        if (out_pdf) out_pdf[i] = distr.pdfVisible(vi, mm);
+        if (out_D) out_D[i] = distr.eval(mm);
+        if (out_G1) out_G1[i] = distr.smithG1(vi, mm);
+    }
+    return 0;
+}
+
 int orc_bsdf(void *s, int bsdfIndex, const float *wi, const float *wo, const float *u, size_t n, float *out_eval,
              float *out_pdf, float *out_wo, float *out_weight, float *out_spdf, uint32_t *out_flags) {
     Scene *sc = (Scene *)s;

@@ -43,6 +43,7 @@ class Oracle:
         L.orc_phase.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_size_t, fp, fp, fp]
         L.orc_render.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), C.c_int, C.c_int, C.c_int, C.c_int, fp,
                                  C.c_int, u64p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
+        L.orc_microfacet.argtypes = [C.c_int, C.c_float, C.c_float, fp, fp, fp, C.c_size_t, fp, fp, fp]
         L.orc_features.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), C.c_int, C.c_int, fp]
         L.orc_field_create.restype = C.c_void_p
         L.orc_field_create.argtypes = [C.c_int, fp, fp]
@@ -70,6 +71,21 @@ class Oracle:
         return self.lib.orc_num_threads()
 
     # ---- rough transmittance tables
+    def microfacet(self, distr, alpha_u, alpha_v, wi, u=None, m=None):
+        """MicrofacetDistribution (microfacet.h): visible-normal samples for u (n, 2), or the given normals m (n, 3);
+        returns m, pdfVisible(wi, m), D(m), smithG1(wi, m)."""
+        wi = np.ascontiguousarray(wi, np.float32)
+        if u is not None:
+            u = np.ascontiguousarray(u, np.float32)
+            n = u.shape[0]
+            m = np.zeros((n, 3), np.float32)
+        else:
+            m = np.ascontiguousarray(m, np.float32).copy()
+            n = m.shape[0]
+        pdf, D, G1 = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+        self.lib.orc_microfacet(int(distr), alpha_u, alpha_v, _f(wi), _f(u) if u is not None else None, _f(m), n, _f(pdf), _f(D), _f(G1))
+        return m, pdf, D, G1
+
     def clipped_aabb(self, tri, box_min, box_max):
         t = np.ascontiguousarray(tri, np.float32).ravel()
         b = np.ascontiguousarray(list(box_min) + list(box_max), np.float32)

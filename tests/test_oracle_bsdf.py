@@ -204,3 +204,80 @@ def test_rough_transmittance_table_vs_btdf_integration(pkg, oracle, distr, eta, 
     xs = (np.arange(4000) + 0.5) / 4000
     num = np.mean([2 * x * _cubic_interp(x ** 0.25, ext) for x in xs])
     assert abs(num - ed) < 3e-3, (num, ed)
+
+
+# ---- src/tests/test_microfacet.cpp restated (the reference's own test of MicrofacetDistribution) ---------------------------
+def _chi2_visible(oracle, distr, au, av, wi, rng, theta_bins=10, phi_bins=20, sub=24):
+    """ChiSquare(thetaBins = 10, 2 * thetaBins) of sampleVisible(wi, .) against pdfVisible(wi, .) (test_microfacet.cpp:133-170)."""
+    n = theta_bins * phi_bins * 1000
+    m, pdf_s, _, _ = oracle.microfacet(distr, au, av, wi, u=rng.rand(n, 2))
+    # the adapter's assertions (test_microfacet.cpp:72-76): finite, unit length
+    assert np.isfinite(m).all() and np.abs(np.linalg.norm(m, axis=1) - 1).max() < 1e-4
+    assert np.isfinite(pdf_s).all() and (pdf_s >= 0).all()
+    theta = np.arccos(np.clip(m[:, 2], -1, 1))
+    phi = np.arctan2(m[:, 1], m[:, 0])
+    phi[phi < 0] += 2 * np.pi
+    ti = np.minimum((theta / np.pi * theta_bins).astype(int), theta_bins - 1)
+    pi_ = np.minimum((phi / (2 * np.pi) * phi_bins).astype(int), phi_bins - 1)
+    obs = np.bincount(ti * phi_bins + pi_, minlength=theta_bins * phi_bins).astype(np.float64)
+    tt = (np.arange(theta_bins * sub) + 0.5) * (np.pi / (theta_bins * sub))
+    pp = (np.arange(phi_bins * sub) + 0.5) * (2 * np.pi / (phi_bins * sub))
+    T, P = np.meshgrid(tt, pp, indexing="ij")
+    d = np.stack([np.sin(T) * np.cos(P), np.sin(T) * np.sin(P), np.cos(T)], -1).reshape(-1, 3).astype(np.float32)
+    _, pdf, _, _ = oracle.microfacet(distr, au, av, wi, m=d)
+    w = (pdf.astype(np.float64).reshape(T.shape) * np.sin(T)) * (np.pi / (theta_bins * sub)) * (2 * np.pi / (phi_bins * sub))
+    total = w.sum()
+    exp = w.reshape(theta_bins, sub, phi_bins, sub).sum((1, 3)).ravel() * n
+    order = np.argsort(exp)
+    pooled_o = pooled_e = 0.0
+    chsq, dof = 0.0, 0
+    for i in order:  # chisquare.cpp: cells with an expected frequency below 5 are pooled
+        if exp[i] == 0:
+            if obs[i] > n * 1e-5:
+                return 0.0, total
+            continue
+        if exp[i] < 5:
+            pooled_o += obs[i]
+            pooled_e += exp[i]
+            continue
+        chsq += (obs[i] - exp[i]) ** 2 / exp[i]
+        dof += 1
+    if pooled_e > 0:
+        chsq += (pooled_o - pooled_e) ** 2 / pooled_e
+        dof += 1
+    return float(stats.chi2.sf(chsq, max(dof - 1, 1))), total
+
+
+def test_microfacet_visible_normal_sampling(oracle):
+    """test02_MicrofacetVisible (test_microfacet.cpp:133-170): Beckmann 0.3, Beckmann 0.5/0.3, GGX 0.1, GGX 0.2/0.3, each at 10
+    incident directions drawn uniformly from the hemisphere; significance 0.0025 with Sidak correction over the 40 tests."""
+    rng = np.random.RandomState(11)
+    distrs = [(0, 0.3, 0.3), (0, 0.5, 0.3), (1, 0.1, 0.1), (1, 0.2, 0.3)]
+    n_tests = 10 * len(distrs)
+    alpha = 1 - (1 - SIGNIFICANCE) ** (1.0 / n_tests)
+    for k in range(10):
+        u = rng.rand(2)
+        z = u[0]                                                   # warp::squareToUniformHemisphere (warp.cpp:33-39)
+        r = np.sqrt(max(0.0, 1 - z * z))
+        wi = np.array([r * np.cos(2 * np.pi * u[1]), r * np.sin(2 * np.pi * u[1]), z], np.float32)
+        for distr, au, av in distrs:
+            p, total = _chi2_visible(oracle, distr, au, av, wi, rng)
+            assert p > alpha, "chi^2 rejected distr %d alpha (%g, %g) at wi=%s (p=%g)" % (distr, au, av, wi, p)
+            if wi[2] > 0.2:  # the visible-normal density integrates to one (midpoint rule on the test's own grid)
+                assert abs(total - 1) < 2e-2, (distr, au, av, wi, total)
+
+
+@pytest.mark.parametrize("distr,au,av", [(0, 0.5, 0.5), (0, 0.5, 0.3), (1, 0.5, 0.5), (1, 0.5, 0.3)])
+def test_microfacet_projected_area_normalisation(oracle, distr, au, av):
+    """pdfAll(m) = D(m) cos(theta_m) is a density (what test01_Microfacet checks for sampleAll, test_microfacet.cpp:95-131, on
+    the same four Beckmann / GGX parameter sets): the projected microfacet area integrates to one; and Smith's G1 at normal
+    incidence is one."""
+    nt, npi = 2000, 720
+    tt = (np.arange(nt) + 0.5) * (0.5 * np.pi / nt)
+    pp = (np.arange(npi) + 0.5) * (2 * np.pi / npi)
+    T, P = np.meshgrid(tt, pp, indexing="ij")
+    m = np.stack([np.sin(T) * np.cos(P), np.sin(T) * np.sin(P), np.cos(T)], -1).reshape(-1, 3).astype(np.float32)
+    _, _, D, G1 = oracle.microfacet(distr, au, av, np.array([0, 0, 1], np.float32), m=m)
+    integral = (D.astype(np.float64).reshape(T.shape) * np.cos(T) * np.sin(T)).sum() * (0.5 * np.pi / nt) * (2 * np.pi / npi)
+    assert abs(integral - 1) < 2e-3, integral
+    assert np.all(G1[m[:, 2] > 0] == 1.0)
