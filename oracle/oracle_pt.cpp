@@ -888,6 +888,33 @@ int orc_camera_rays(void *s, const float *pos, size_t n, float *rays) {
     return 0;
 }
 
+// Full intersection records (ShapeKDTree::rayIntersect + fillIntersectionRecord, skdtree.h:343-428), the quantities the
+// reference's src/tests/test_dgeom.cpp asserts: out[18 * i] = {t, p.xyz, uv.xy, geoFrame.n, shFrame.n, shFrame.s, dpdu};
+// t = inf for a miss.
+int orc_intersect(void *s, const float *rays, size_t n, float *out) {
+    Scene *sc = (Scene *)s;
+    for (size_t i = 0; i < n; ++i) {
+        const float *r = rays + 8 * i;
+        Ray ray(Vec3(r[0], r[1], r[2]), Vec3(r[4], r[5], r[6]), r[3], r[7]);
+        Intersection its;
+        Stats st;
+        float *o = out + 18 * i;
+        for (int k = 0; k < 18; ++k) o[k] = 0.0f;
+        if (!sc->rayIntersect(ray, its, &st) || !its.isValid()) {
+            o[0] = std::numeric_limits<float>::infinity();
+            continue;
+        }
+        o[0] = its.t;
+        o[1] = its.p.x; o[2] = its.p.y; o[3] = its.p.z;
+        o[4] = its.uv.x; o[5] = its.uv.y;
+        o[6] = its.geoN.x; o[7] = its.geoN.y; o[8] = its.geoN.z;
+        o[9] = its.shFrame.n.x; o[10] = its.shFrame.n.y; o[11] = its.shFrame.n.z;
+        o[12] = its.shFrame.s.x; o[13] = its.shFrame.s.y; o[14] = its.shFrame.s.z;
+        o[15] = its.dpdu.x; o[16] = its.dpdu.y; o[17] = its.dpdu.z;
+    }
+    return 0;
+}
+
 // MicrofacetDistribution on its own (src/tests/test_microfacet.cpp drives the class directly): for a fixed incident
 // direction wi, out_m[i] = sampleVisible(wi, u[i]) when u != NULL; for every normal m[i] (the sampled ones, or the given
 // ones when u == NULL): pdfVisible(wi, m), D(m) = eval(m) and smithG1(wi, m).

@@ -43,6 +43,7 @@ class Oracle:
         L.orc_phase.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_size_t, fp, fp, fp]
         L.orc_render.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), C.c_int, C.c_int, C.c_int, C.c_int, fp,
                                  C.c_int, u64p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
+        L.orc_intersect.argtypes = [C.c_void_p, fp, C.c_size_t, fp]
         L.orc_microfacet.argtypes = [C.c_int, C.c_float, C.c_float, fp, fp, fp, C.c_size_t, fp, fp, fp]
         L.orc_features.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), C.c_int, C.c_int, fp]
         L.orc_field_create.restype = C.c_void_p
@@ -238,6 +239,14 @@ class OracleScene:
         cnt = (C.c_uint64 * 3)()
         self.L.orc_trace(self.h, _f(rays), n, int(shadow), _f(tuv), _u(prim), cnt, nthreads)
         return tuv, prim, dict(nodes=cnt[0], indices=cnt[1], prims=cnt[2])
+
+    def intersect(self, rays):
+        """Full intersection records: dict of t, p, uv, geo_n, sh_n, sh_s, dpdu (skdtree.h:343-428)."""
+        rays = np.ascontiguousarray(rays, np.float32)
+        out = np.zeros((rays.shape[0], 18), np.float32)
+        self.L.orc_intersect(self.h, _f(rays), rays.shape[0], _f(out))
+        return dict(t=out[:, 0], p=out[:, 1:4], uv=out[:, 4:6], geo_n=out[:, 6:9], sh_n=out[:, 9:12], sh_s=out[:, 12:15],
+                    dpdu=out[:, 15:18])
 
     def trace_bruteforce(self, rays):
         rays = np.ascontiguousarray(rays, np.float32)

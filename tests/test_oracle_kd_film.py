@@ -139,3 +139,39 @@ def test_triangle_clipping_known_answers(oracle):
     assert tuple(lo) == (0, 0, 0) and tuple(hi) == (1, 1, 0)
     lo, hi = oracle.clipped_aabb(tri, (0, 1, 0), (1, 2, 0))            # just touching: collapsed point AABB
     assert tuple(lo) == (1, 1, 0) and tuple(hi) == (1, 1, 0)
+
+
+# ---- src/tests/test_dgeom.cpp restated: known answers for ShapeKDTree::rayIntersect + fillIntersectionRecord -------------
+def _one_triangle(pkg, oracle, N=None, UV=None):
+    sb = pkg.scenes.SceneBuilder(8, 8, spp=1)
+    sb.set_camera((0, 0, -4), (0, 0, 0), (0, 1, 0), 40.0)
+    sb.trimesh(P=[[0, 0, 0], [1, 0, 0], [0, 1, 0]], T=[[0, 1, 2]], N=N, UV=UV, bsdf=sb.diffuse((0.5, 0.5, 0.5)))
+    return oracle.scene(sb)
+
+
+def test_dgeom_trimesh_known_answers(pkg, oracle):
+    ray = np.array([[0.1, 0.2, -1.0, 0.0, 0, 0, 1, np.inf]], np.float32)   # Ray(Point(0.1, 0.2, -1), Vector(0, 0, 1))
+    eps = 1e-4                                                             # Epsilon (constants.h:28)
+    # test01_trimesh_1 (test_dgeom.cpp:34-66): no normals, no UV coordinates -- exact answers
+    its = _one_triangle(pkg, oracle).intersect(ray)
+    assert np.array_equal(its["p"][0], np.float32([0.1, 0.2, 0.0]))
+    assert np.array_equal(its["uv"][0], np.float32([0.1, 0.2]))           # barycentric coordinates stand in for UVs
+    assert np.array_equal(its["sh_n"][0], [0, 0, 1]) and np.array_equal(its["geo_n"][0], [0, 0, 1])
+    assert np.array_equal(its["dpdu"][0], [1, 0, 0])
+    assert its["t"][0] == 1.0
+    # test02_trimesh_2 (:68-117): shading normals and UV coordinates, no explicit parameterisation
+    normals = np.float32([[-0.3, 0, 1], [0.3, 0, 1], [0, 0.3, 1]])
+    uv = np.float32([[0.1, 0.1], [1.1, 0.1], [0.1, 0.9]])
+    its = _one_triangle(pkg, oracle, N=normals, UV=uv).intersect(ray)
+    assert np.array_equal(its["p"][0], np.float32([0.1, 0.2, 0.0]))
+    assert np.abs(its["uv"][0] - [0.2, 0.26]).max() <= eps
+    assert np.array_equal(its["geo_n"][0], [0, 0, 1])
+    n = normals[0] * 0.7 + normals[1] * 0.1 + normals[2] * 0.2
+    n /= np.linalg.norm(n)
+    assert np.abs(its["sh_n"][0] - n).max() <= eps
+    assert np.abs(its["dpdu"][0] - [1, 0, 0]).max() <= eps                # vertices[1] - vertices[0]
+    s = its["dpdu"][0] - its["sh_n"][0] * np.dot(its["sh_n"][0], its["dpdu"][0])
+    assert np.abs(its["sh_s"][0] - s / np.linalg.norm(s)).max() <= eps    # computeShadingFrame (util.cpp:605-610)
+    # a ray that misses the triangle
+    miss = oracle_miss = _one_triangle(pkg, oracle).intersect(np.array([[0.8, 0.8, -1.0, 0.0, 0, 0, 1, np.inf]], np.float32))
+    assert np.isinf(miss["t"][0])
