@@ -302,12 +302,19 @@ def test_dgeom_known_answer_through_the_gpu_traversal(pkg, api):
     """The reference's known answer for ShapeKDTree::rayIntersect on a single triangle (src/tests/test_dgeom.cpp:34-66:
     Ray((0.1, 0.2, -1), (0, 0, 1)) hits (0,0,0)-(1,0,0)-(0,1,0) at p = (0.1, 0.2, 0), barycentric uv = (0.1, 0.2)); the oracle
     reproduces it exactly (tests/test_oracle_kd_film.py), the GPU's affine-map triangle test to the parity bars."""
-    sb = pkg.scenes.SceneBuilder(8, 8, spp=1)
+    S = pkg.scenes
+    sb = S.SceneBuilder(8, 8, spp=1)
     sb.set_camera((0, 0, -4), (0, 0, 0), (0, 1, 0), 40.0)
-    sb.trimesh(P=[[0, 0, 0], [1, 0, 0], [0, 1, 0]], T=[[0, 1, 2]], bsdf=sb.diffuse((0.5, 0.5, 0.5)))
+    white = sb.diffuse((0.5, 0.5, 0.5))
+    sb.trimesh(P=[[0, 0, 0], [1, 0, 0], [0, 1, 0]], T=[[0, 1, 2]], bsdf=white)
+    # an emitter and a few more primitives well away from the two test rays (x, y >= 20), so that the scene has a light and
+    # the BVH has inner nodes like every other scene of this suite
+    sb.rectangle([S.translate(20.0, 20.0, 10.0)], bsdf=white, radiance=(1, 1, 1))
+    for i in range(1, 6):
+        sb.rectangle([S.translate(20.0 + 3.0 * i, 20.0, 10.0)], bsdf=white)
     it = api.Integrator(api.Scene.from_builder(sb), _params(api))
     rays = np.array([[0.1, 0.2, -1.0, 0.0, 0, 0, 1, np.inf], [0.8, 0.8, -1.0, 0.0, 0, 0, 1, np.inf]], np.float32)
     tuv, prim = it.k_trace(rays)
-    assert prim[0] == 0 and prim[1] == 0xFFFFFFFF
+    assert prim[0] == 0 and prim[1] == 0xFFFFFFFF          # global primitive ids follow the shape order: the triangle is 0
     assert abs(tuv[0, 0] - 1.0) <= 2e-6 and np.abs(tuv[0, 1:] - [0.1, 0.2]).max() <= 2e-5
     it.close()
