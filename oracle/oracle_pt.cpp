@@ -888,6 +888,48 @@ int orc_camera_rays(void *s, const float *pos, size_t n, float *rays) {
     return 0;
 }
 
+// Next-event estimation on its own, the way src/tests/test_chisquare.cpp test03_EmitterDirect drives an emitter
+// (EmitterAdapter: sampleDirect for the samples, pdfDirect for the density). Reference point ref with normal refN
+// (refN = 0: no facing test, records.inl:160-164).
+//   u != NULL: out_d[i], out_dist[i], out_pdf[i], out_value[i] = Scene::sampleEmitterDirect(u[i]) WITHOUT the visibility test
+//   u == NULL: out_pdf[i] = Scene::pdfEmitterDirect for the given direction d[i]: the ray (ref, d) is traced, and if the
+//              first surface it meets is an emitter the query record is filled from the hit (records.inl:170-178), as
+//              the path tracer does for BSDF-sampled rays (progressive_path.cpp:243-262); 0 otherwise.
+int orc_emitter_direct(void *s, const float *ref, const float *refN, const float *u, float *d, size_t n, float *out_dist,
+                       float *out_pdf, float *out_value) {
+    Scene *sc = (Scene *)s;
+    for (size_t i = 0; i < n; ++i) {
+        Scene::DirectSample dRec;
+        dRec.ref = Vec3(ref[0], ref[1], ref[2]);
+        dRec.refN = Vec3(refN[0], refN[1], refN[2]);
+        if (u) {
+            Vec3 value = sc->sampleEmitterDirectNoVis(dRec, Vec2(u[2 * i], u[2 * i + 1]));
+            d[3 * i] = dRec.d.x; d[3 * i + 1] = dRec.d.y; d[3 * i + 2] = dRec.d.z;
+            if (out_dist) out_dist[i] = dRec.dist;
+            if (out_pdf) out_pdf[i] = dRec.pdf;
+            if (out_value) { out_value[3 * i] = value.x; out_value[3 * i + 1] = value.y; out_value[3 * i + 2] = value.z; }
+        } else {
+            Ray ray(dRec.ref, Vec3(d[3 * i], d[3 * i + 1], d[3 * i + 2]));
+            Intersection its;
+            Stats st;
+            Float pdf = 0.0f;
+            if (sc->rayIntersect(ray, its, &st) && its.isValid() && sc->shapes[its.shape].emitter >= 0) {
+                dRec.p = its.p;
+                dRec.n = its.shFrame.n;
+                dRec.emitter = sc->shapes[its.shape].emitter;
+                dRec.d = ray.d;
+                dRec.dist = its.t;
+                pdf = sc->pdfEmitterDirect(dRec);
+                if (out_dist) out_dist[i] = its.t;
+            } else if (out_dist) {
+                out_dist[i] = std::numeric_limits<float>::infinity();
+            }
+            out_pdf[i] = pdf;
+        }
+    }
+    return 0;
+}
+
 // Full intersection records (ShapeKDTree::rayIntersect + fillIntersectionRecord, skdtree.h:343-428), the quantities the
 // reference's src/tests/test_dgeom.cpp asserts: out[18 * i] = {t, p.xyz, uv.xy, geoFrame.n, shFrame.n, shFrame.s, dpdu};
 // t = inf for a miss.

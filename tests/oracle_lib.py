@@ -43,6 +43,7 @@ class Oracle:
         L.orc_phase.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_size_t, fp, fp, fp]
         L.orc_render.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), C.c_int, C.c_int, C.c_int, C.c_int, fp,
                                  C.c_int, u64p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
+        L.orc_emitter_direct.argtypes = [C.c_void_p, fp, fp, fp, fp, C.c_size_t, fp, fp, fp]
         L.orc_intersect.argtypes = [C.c_void_p, fp, C.c_size_t, fp]
         L.orc_microfacet.argtypes = [C.c_int, C.c_float, C.c_float, fp, fp, fp, C.c_size_t, fp, fp, fp]
         L.orc_features.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), C.c_int, C.c_int, fp]
@@ -247,6 +248,23 @@ class OracleScene:
         self.L.orc_intersect(self.h, _f(rays), rays.shape[0], _f(out))
         return dict(t=out[:, 0], p=out[:, 1:4], uv=out[:, 4:6], geo_n=out[:, 6:9], sh_n=out[:, 9:12], sh_s=out[:, 12:15],
                     dpdu=out[:, 15:18])
+
+    def emitter_sample(self, ref, ref_n, u):
+        """Scene::sampleEmitterDirect without the visibility test: directions, distances, solid-angle pdfs, radiance / pdf."""
+        ref, ref_n, u = (np.ascontiguousarray(a, np.float32) for a in (ref, ref_n, u))
+        n = u.shape[0]
+        d, dist, pdf, val = np.zeros((n, 3), np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros((n, 3), np.float32)
+        self.L.orc_emitter_direct(self.h, _f(ref), _f(ref_n), _f(u), _f(d), n, _f(dist), _f(pdf), _f(val))
+        return d, dist, pdf, val
+
+    def emitter_pdf(self, ref, ref_n, d):
+        """Scene::pdfEmitterDirect for rays (ref, d) whose first hit is an emitter (0 otherwise)."""
+        ref, ref_n = (np.ascontiguousarray(a, np.float32) for a in (ref, ref_n))
+        d = np.ascontiguousarray(d, np.float32).copy()
+        n = d.shape[0]
+        pdf = np.zeros(n, np.float32)
+        self.L.orc_emitter_direct(self.h, _f(ref), _f(ref_n), None, _f(d), n, None, _f(pdf), None)
+        return pdf
 
     def trace_bruteforce(self, rays):
         rays = np.ascontiguousarray(rays, np.float32)

@@ -175,3 +175,76 @@ def test_dgeom_trimesh_known_answers(pkg, oracle):
     # a ray that misses the triangle
     miss = oracle_miss = _one_triangle(pkg, oracle).intersect(np.array([[0.8, 0.8, -1.0, 0.0, 0, 0, 1, np.inf]], np.float32))
     assert np.isinf(miss["t"][0])
+
+
+# ---- next-event estimation, tested the way src/tests/test_chisquare.cpp test03_EmitterDirect tests an emitter ---------------
+def test_emitter_direct_sampling_chi_square(pkg, oracle):
+    """EmitterAdapter (test_chisquare.cpp:344-391): directions from sampleDirect against the solid-angle density pdfDirect on
+    a 10 x 20 (theta, phi) grid, significance 0.0025 (Sidak over the reference points). The reference runs this on its
+    envmap emitter only (data/tests/test_emitter.xml); here the same test drives the path's emitter, the area light
+    (area.cpp:158-183, shape.cpp:102-126, scene.cpp:871-895, 992-995), at three unoccluded reference points of the Cornell box.
+    Also: sampleDirect's value x pdf is the emitted radiance (17, 12, 4), the identity test_chisquare.cpp:34-38 checks for
+    BSDFs."""
+    from scipy import stats
+
+    osc = oracle.scene(pkg.scenes.cornell_box(32, 32, spp=1))
+    rng = np.random.RandomState(3)
+    refs = ([-0.7, 0.2, 0.8], [0.0, 1.0, 0.9], [0.8, 1.5, 0.0])
+    alpha = 1 - (1 - 0.0025) ** (1.0 / len(refs))
+    theta_bins, phi_bins = 10, 20
+    for ref in refs:
+        zero_n = [0, 0, 0]                                  # DirectSamplingRecord(Point, time): no reference normal
+        n = theta_bins * phi_bins * 1000
+        d, dist, pdf_s, val = osc.emitter_sample(ref, zero_n, rng.rand(n, 2))
+        assert (pdf_s > 0).all() and np.abs(np.linalg.norm(d, axis=1) - 1).max() < 1e-5
+        np.testing.assert_allclose(val * pdf_s[:, None], np.tile([17.0, 12.0, 4.0], (n, 1)), rtol=1e-5)
+        assert np.abs(osc.emitter_pdf(ref, zero_n, d[:5000]) - pdf_s[:5000]).max() <= 1e-5 * pdf_s.max()
+        theta = np.arccos(np.clip(d[:, 2], -1, 1))
+        phi = np.arctan2(d[:, 1], d[:, 0])
+        phi[phi < 0] += 2 * np.pi
+        ti = np.minimum((theta / np.pi * theta_bins).astype(int), theta_bins - 1)
+        pi_ = np.minimum((phi / (2 * np.pi) * phi_bins).astype(int), phi_bins - 1)
+        obs = np.bincount(ti * phi_bins + pi_, minlength=theta_bins * phi_bins).astype(np.float64)
+        # expected bin masses: the integral of pdfDirect over each (theta, phi) cell. The density is discontinuous at the light's
+        # silhouette, so instead of a quadrature over the sphere (the reference integrates adaptively, chisquare.cpp) the
+        # integral is taken over the light's own area, where the integrand pdf(w(x)) |cos| / r^2 is smooth: x on a 1200 x 1200
+        # midpoint grid of the 0.47 x 0.38 rectangle at y = 1.98 (scenes.cornell_box); only the cell boundaries cut the grid.
+        m = 1200
+        gx = ((np.arange(m) + 0.5) / m - 0.5) * 0.47
+        gz = ((np.arange(m) + 0.5) / m - 0.5) * 0.38
+        X, Z = np.meshgrid(gx, gz, indexing="ij")
+        x = np.stack([X.ravel(), np.full(m * m, 1.98), Z.ravel()], 1)
+        v = x - np.asarray(ref, np.float64)
+        r2 = (v * v).sum(1)
+        w_dir = (v / np.sqrt(r2)[:, None]).astype(np.float32)
+        pdf = osc.emitter_pdf(ref, zero_n, w_dir).astype(np.float64)
+        mass = pdf * np.abs(w_dir[:, 1]) / r2 * (0.47 * 0.38 / (m * m))       # the light's normal is -y
+        assert abs(mass.sum() - 1) < 2e-3
+        th = np.arccos(np.clip(w_dir[:, 2], -1, 1))
+        ph = np.arctan2(w_dir[:, 1], w_dir[:, 0])
+        ph[ph < 0] += 2 * np.pi
+        cell = np.minimum((th / np.pi * theta_bins).astype(int), theta_bins - 1) * phi_bins + \
+            np.minimum((ph / (2 * np.pi) * phi_bins).astype(int), phi_bins - 1)
+        exp = np.bincount(cell, weights=mass, minlength=theta_bins * phi_bins) * n / mass.sum()
+        chsq, dof, po, pe = 0.0, 0, 0.0, 0.0
+        for i in np.argsort(exp):
+            if exp[i] == 0:
+                assert obs[i] <= n * 1e-3, "samples where the density is zero"
+                continue
+            if exp[i] < 5:
+                po += obs[i]
+                pe += exp[i]
+                continue
+            chsq += (obs[i] - exp[i]) ** 2 / exp[i]
+            dof += 1
+        if pe > 0:
+            chsq += (po - pe) ** 2 / pe
+            dof += 1
+        p = float(stats.chi2.sf(chsq, max(dof - 1, 1)))
+        assert p > alpha, "chi^2 rejected the area light at ref=%s (p=%g, dof=%d)" % (ref, p, dof)
+    # facing tests of Scene::sampleEmitterDirect / AreaLight::sampleDirect: a reference normal pointing away from the light,
+    # or a reference point behind the (one-sided) light, gets no contribution
+    d, dist, pdf_s, val = osc.emitter_sample([0.0, 1.0, 0.9], [0, -1, 0], rng.rand(100, 2))
+    assert (pdf_s == 0).all() and (val == 0).all()
+    d, dist, pdf_s, val = osc.emitter_sample([0.0, 2.5, 0.0], [0, 0, 0], rng.rand(100, 2))
+    assert (pdf_s == 0).all() and (val == 0).all()
