@@ -317,3 +317,65 @@ def test_ply_loader_on_the_reference_bunny(api, tmp_path):
     used[T.ravel()] = True                                   # the file carries a few vertices no face references
     cosang = (acc * N).sum(1)[used]
     assert used.mean() > 0.9 and np.median(cosang) > 0.999 and np.quantile(cosang, 0.01) > 0.9
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/data/tests/test_bsdf.xml"), reason="needs the reference tree (not on the GPU box)")
+def test_reference_bsdf_test_file_parses_to_the_tested_parameterisations(api, pkg, tmp_path):
+    """The BSDF consistency tests (tests/test_oracle_bsdf.py, tests/test_gpu_parity.py) run on hand-written copies of the
+    parameterisations of data/tests/test_bsdf.xml (tests/bsdf_cases.py). Here the <bsdf> elements are taken VERBATIM from the
+    reference's file, pushed through the XML reader, and compared with those copies -- so the two cannot drift apart. Elements
+    of plugins that are off the path are rejected with an error naming the plugin."""
+    import xml.etree.ElementTree as ET
+
+    from bsdf_cases import bsdf_scene, CU_ETA, CU_K
+
+    root = ET.parse("/root/reference/data/tests/test_bsdf.xml").getroot()
+    elems = [e for e in root if e.tag == "bsdf"]
+    want_sb, idx = bsdf_scene()
+    want_scene = api.Scene.from_builder(want_sb)
+    want_desc = want_scene.desc
+
+    def load(elem_xml):
+        p = tmp_path / "b.xml"
+        p.write_text(_scene('<shape type="rectangle">%s</shape>' % elem_xml).replace("$spp", "4"))
+        sc = api.Scene.load_xml(str(p))
+        return sc, sc.desc.bsdfs[sc.desc.shapes[0].bsdf]
+
+    def find(pred):
+        hits = [e for e in elems if pred(e)]
+        assert hits, "element not found in test_bsdf.xml"
+        return hits[0]
+
+    def same(a, b, fields):
+        assert (a.type, a.twosided, a.distribution) == (b.type, b.twosided, b.distribution)
+        for f in fields:
+            va, vb = getattr(a, f), getattr(b, f)
+            np.testing.assert_allclose(np.array(va[:] if hasattr(va, "__len__") else [va]),
+                                       np.array(vb[:] if hasattr(vb, "__len__") else [vb]), rtol=1e-6, atol=1e-7, err_msg=f)
+
+    # <bsdf type="diffuse"/> and the two-sided wrapper around it
+    sc, b = load(ET.tostring(find(lambda e: e.get("type") == "diffuse" and len(e) == 0), encoding="unicode"))
+    same(b, want_desc.bsdfs[idx["diffuse"]], ("reflectance",))
+    sc, b = load(ET.tostring(find(lambda e: e.get("type") == "twosided" and e[0].get("type") == "diffuse"), encoding="unicode"))
+    same(b, want_desc.bsdfs[idx["twosided_diffuse"]], ("reflectance",))
+    # dielectric with named IORs (water / air, ior.h:39-64)
+    sc, b = load(ET.tostring(find(lambda e: e.get("type") == "dielectric" and any(c.get("value") == "water" for c in e)), encoding="unicode"))
+    same(b, want_desc.bsdfs[idx["dielectric_water_air"]], ("int_ior", "ext_ior", "specular_reflectance", "specular_transmittance"))
+    # roughconductor, Beckmann alpha = .3: the file relies on the default material (Cu, an .spd file); the RGB eta / k of
+    # bsdf_cases are injected, everything else is the reference's element
+    e = find(lambda e: e.get("type") == "roughconductor" and any(c.get("value") == "beckmann" for c in e))
+    e = ET.fromstring(ET.tostring(e))
+    for name, v in (("eta", CU_ETA), ("k", CU_K)):
+        ET.SubElement(e, "rgb", name=name, value=" ".join(repr(float(x)) for x in v))
+    sc, b = load(ET.tostring(e, encoding="unicode"))
+    same(b, want_desc.bsdfs[idx["roughconductor_beckmann_0.3"]], ("alpha_u", "alpha_v", "eta", "k", "specular_reflectance"))
+    # roughplastic, Beckmann alpha = .7 (defaults: polypropylene / air, diffuse .5)
+    sc, b = load(ET.tostring(find(lambda e: e.get("type") == "roughplastic"), encoding="unicode"))
+    same(b, want_desc.bsdfs[idx["roughplastic_beckmann_0.7"]], ("alpha_u", "int_ior", "ext_ior", "reflectance", "specular_reflectance", "nonlinear"))
+    # everything else in the file is off the accelerated path and must be refused by name
+    for e in elems:
+        t = e.get("type")
+        if t in ("diffuse", "twosided", "dielectric", "roughconductor", "roughplastic"):
+            continue
+        with pytest.raises(api.B200pgError, match=t):
+            load(ET.tostring(e, encoding="unicode"))
