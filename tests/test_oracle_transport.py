@@ -1,0 +1,83 @@
+"""Analytic pins of the oracle's light transport (ProgressiveMIPathTracer::Li restated, progressive_path.cpp:133-314): the
+reference ships no rendered image or radiance value to compare with, so the whole estimator -- emitter
+sampling, BSDF sampling, the power-heuristic MIS between them, Russian roulette -- is held against closed forms:
+  * direct illumination of a diffuse floor point under a rectangular Lambertian light = rho * L * F, F the form factor of a
+    differential element to a parallel rectangle;
+  * the furnace: inside a closed box whose walls all emit L and reflect rho, the radiance is L / (1 - rho) in every direction.
+The GPU path agrees with the oracle sample by sample (tests/test_gpu_parity.py), so these pins carry over."""
+import numpy as np
+import pytest
+
+
+def _params(pkg, **kw):
+    p = pkg._abi.default_params()
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def _corner_form_factor(a, b, c):
+    """Differential element to a parallel a x b rectangle whose corner lies on the element's normal, distance c."""
+    X, Y = a / c, b / c
+    return (X / np.sqrt(1 + X * X) * np.arctan(Y / np.sqrt(1 + X * X)) + Y / np.sqrt(1 + Y * Y) * np.arctan(X / np.sqrt(1 + Y * Y))) / (2 * np.pi)
+
+
+@pytest.mark.parametrize("use_nee", [1, 0])
+def test_direct_illumination_matches_the_form_factor(pkg, oracle, use_nee):
+    S = pkg.scenes
+    rho, L, h, hx, hz = 0.6, (5.0, 3.0, 1.0), 1.5, 0.8, 0.5
+    sb = S.SceneBuilder(9, 9, spp=1)
+    X = (1, 0, 0)
+    sb.rectangle([S.scale(50, 50, 1), S.rotate(X, -90.0)], bsdf=sb.diffuse((rho, rho, rho)))                      # floor, y = 0, +y
+    sb.rectangle([S.scale(hx, hz, 1), S.rotate(X, 90.0), S.translate(0.3, h, -0.2)], bsdf=-1, radiance=L)         # light, -y
+    # the camera looks at the floor point (0.5, 0, 0.1) through a very narrow pixel, from below the light's plane
+    target = np.array([0.5, 0.0, 0.1])
+    sb.set_camera((3.0, 1.0, 2.5), tuple(target), (0, 1, 0), 0.05)
+    osc = oracle.scene(sb)
+    n = 400000
+    pix = np.full(n, 4 * 9 + 4, np.uint32)                                                                         # centre pixel
+    rad = osc.radiance(_params(pkg, max_depth=2, use_nee=use_nee), pix, np.arange(n, dtype=np.uint32)).astype(np.float64)
+    # form factor by superposition of four corner rectangles around the foot point of the floor point
+    dx0, dx1 = target[0] - (0.3 - hx), (0.3 + hx) - target[0]
+    dz0, dz1 = target[2] - (-0.2 - hz), (-0.2 + hz) - target[2]
+    assert min(dx0, dx1, dz0, dz1) > 0
+    F = sum(_corner_form_factor(a, b, h) for a in (dx0, dx1) for b in (dz0, dz1))
+    want = rho * np.array(L) * F
+    mean, sem = rad.mean(0), rad.std(0) / np.sqrt(n)
+    assert np.all(np.abs(mean - want) <= 4 * sem + 2e-3 * want), (mean, want, sem)
+    assert np.all(sem < 0.01 * want)
+
+
+@pytest.mark.parametrize("kw", [dict(max_depth=-1, rr_depth=5), dict(max_depth=-1, rr_depth=1), dict(max_depth=-1, rr_depth=3, use_nee=0)])
+def test_furnace(pkg, oracle, kw):
+    S = pkg.scenes
+    rho, L = 0.5, 1.0
+    sb = S.SceneBuilder(8, 8, spp=1)
+    mat = sb.diffuse((rho, rho, rho))
+    X, Y = (1, 0, 0), (0, 1, 0)
+    # the six faces of [-1, 1]^3, normals pointing inwards, every face an emitter
+    faces = [[S.translate(0, 0, -1)],                                   # z = -1, normal +z
+             [S.rotate(Y, 180.0), S.translate(0, 0, 1)],                # z = +1, normal -z
+             [S.rotate(Y, 90.0), S.translate(-1, 0, 0)],                # x = -1, normal +x
+             [S.rotate(Y, -90.0), S.translate(1, 0, 0)],                # x = +1, normal -x
+             [S.rotate(X, -90.0), S.translate(0, -1, 0)],               # y = -1, normal +y
+             [S.rotate(X, 90.0), S.translate(0, 1, 0)]]                 # y = +1, normal -y
+    for ops in faces:
+        sb.rectangle(ops, bsdf=mat, radiance=(L, L, L))
+    sb.set_camera((0.1, -0.2, 0.3), (0.9, 0.4, -1.0), (0, 1, 0), 70.0)
+    osc = oracle.scene(sb)
+    # every face really faces inwards: a ray from the centre sees an emitting front side everywhere
+    rng = np.random.RandomState(0)
+    n = 200000
+    pix = rng.randint(0, 64, n).astype(np.uint32)
+    rad = osc.radiance(_params(pkg, **kw), pix, np.arange(n, dtype=np.uint32)).astype(np.float64)
+    want = L / (1 - rho)
+    mean, sem = rad.mean(0), rad.std(0) / np.sqrt(n)
+    assert np.all(np.abs(mean - want) <= 4 * sem + 1e-3 * want), (mean, want, sem)
+    # truncated series: maxDepth = k keeps the first k terms L (1 + rho + ... + rho^(k-1)) -- emitted radiance of the first
+    # hit, then one term per further vertex (progressive_path.cpp:149, 175-184)
+    for k in (1, 2, 4):
+        r = osc.radiance(_params(pkg, max_depth=k, rr_depth=100), pix[:50000], np.arange(50000, dtype=np.uint32)).astype(np.float64)
+        want_k = L * (1 - rho ** k) / (1 - rho)
+        m, s = r.mean(0), r.std(0) / np.sqrt(50000)
+        assert np.all(np.abs(m - want_k) <= 4 * s + 1e-3 * want_k), (k, m, want_k)
