@@ -81,3 +81,34 @@ def test_furnace(pkg, oracle, kw):
         want_k = L * (1 - rho ** k) / (1 - rho)
         m, s = r.mean(0), r.std(0) / np.sqrt(50000)
         assert np.all(np.abs(m - want_k) <= 4 * s + 1e-3 * want_k), (k, m, want_k)
+
+
+def test_guided_furnace(pkg, oracle):
+    """One-sample MIS between the BSDF and a TRAINED guiding field must not bias the estimator: the furnace value L / (1 - rho)
+    again, with directions drawn from the mixtures half of the time (field trained by two updates on this scene)."""
+    S = pkg.scenes
+    rho, L = 0.5, 1.0
+    sb = S.SceneBuilder(16, 16, spp=4)
+    mat = sb.diffuse((rho, rho, rho))
+    X, Y = (1, 0, 0), (0, 1, 0)
+    for ops in ([S.translate(0, 0, -1)], [S.rotate(Y, 180.0), S.translate(0, 0, 1)], [S.rotate(Y, 90.0), S.translate(-1, 0, 0)],
+                [S.rotate(Y, -90.0), S.translate(1, 0, 0)], [S.rotate(X, -90.0), S.translate(0, -1, 0)],
+                [S.rotate(X, 90.0), S.translate(0, 1, 0)]):
+        sb.rectangle(ops, bsdf=mat, radiance=(L, L, L))
+    sb.set_camera((0.1, -0.2, 0.3), (0.9, 0.4, -1.0), (0, 1, 0), 70.0)
+    osc = oracle.scene(sb)
+    p = _params(pkg, max_depth=-1, rr_depth=5, guiding=1, guide_max_components=8, guide_max_cell_samples=2000)
+    fld = oracle.field(8, (0, 0, 0), (1, 1, 1))
+    sink = oracle.samples()
+    for k in range(2):
+        sink.clear()
+        osc.render(p, 8 * k, 8, field=fld if k else None, sink=sink)
+        fld.train_sink(sink, 4, 2000.0)
+    assert fld.info()["cells"] > 1
+    rng = np.random.RandomState(1)
+    n = 200000
+    pix = rng.randint(0, 256, n).astype(np.uint32)
+    rad = osc.radiance(p, pix, 1000 + np.arange(n, dtype=np.uint32), field=fld).astype(np.float64)
+    want = L / (1 - rho)
+    mean, sem = rad.mean(0), rad.std(0) / np.sqrt(n)
+    assert np.all(np.abs(mean - want) <= 4 * sem + 1e-3 * want), (mean, want, sem)
