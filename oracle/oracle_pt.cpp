@@ -930,6 +930,14 @@ int orc_emitter_direct(void *s, const float *ref, const float *refN, const float
     return 0;
 }
 
+// Test hook: 1 = the emitter look-up of the volumetric path uses the total distance from the path vertex (see the REFERENCE
+// QUIRK note in oracle_volpath.h); 0 (default) = the reference's behaviour. Returns the previous value.
+int orc_debug_lookup_total_distance(int on) {
+    const int before = g_lookupTotalDistance;
+    g_lookupTotalDistance = on ? 1 : 0;
+    return before;
+}
+
 // Full intersection records (ShapeKDTree::rayIntersect + fillIntersectionRecord, skdtree.h:343-428), the quantities the
 // reference's src/tests/test_dgeom.cpp asserts: out[18 * i] = {t, p.xyz, uv.xy, geoFrame.n, shFrame.n, shFrame.s, dpdu};
 // t = inf for a miss.

@@ -82,6 +82,16 @@ static Float evalTransmittance(const Scene &scene, const Vec3 &p1, bool p1OnSurf
     return transmittance;
 }
 
+// REFERENCE QUIRK, reproduced on purpose (parity): when the sampled ray reaches an emitter THROUGH index-matched boundaries,
+// dRec.setQuery(ray, *its) (records.inl:170-178) takes dist = its.t of the LAST segment -- the ray origin has been moved to
+// the last boundary (progressive_volpath.cpp:437) -- not the distance from the path vertex. pdfEmitterDirect converts the
+// area density with dist^2 (shape.cpp:117-126), so the emitter pdf that enters the MIS weight is too small, the
+// BSDF/phase-sampled contribution is over-weighted, and the estimator is biased bright wherever a null boundary lies
+// between a vertex and the light (the furnace test measures +7..10 %; without next-event estimation, or with the total
+// distance, it returns the exact value: tests/test_oracle_transport.py). g_lookupTotalDistance = 1 (test hook
+// orc_debug_flag) switches to the total distance to demonstrate this; the default is the reference's behaviour.
+static int g_lookupTotalDistance = 0;
+
 // progressive_volpath.cpp:401-460
 static void rayIntersectAndLookForEmitter(const Scene &scene, Rng &rng, int medium, int maxInteractions, Ray ray, Intersection &_its,
                                           Scene::DirectSample &dRec, Vec3 &value, Stats &st) {
@@ -89,6 +99,7 @@ static void rayIntersectAndLookForEmitter(const Scene &scene, Rng &rng, int medi
     Float transmittance = 1.0f;
     bool surface = false;
     int interactions = 0;
+    Float walked = 0.0f;  // length of the segments before the last one
     while (true) {
         surface = scene.rayIntersect(ray, *its, &st);
         if (medium >= 0) transmittance *= scene.media[medium].evalTransmittance(ray.o, ray.d, 0, its->t, rng);
@@ -99,6 +110,7 @@ static void rayIntersectAndLookForEmitter(const Scene &scene, Rng &rng, int medi
         if (transmittance == 0) return;
         const Shape &s = scene.shapes[its->shape];
         if (s.isMediumTransition()) medium = targetMedium(s, its->geoN, ray.d);
+        walked += its->t;
         ray.o = ray(its->t);
         ray.mint = Epsilon;
         its = &its2;
@@ -109,7 +121,7 @@ static void rayIntersectAndLookForEmitter(const Scene &scene, Rng &rng, int medi
         dRec.n = its->shFrame.n;
         dRec.emitter = scene.shapes[its->shape].emitter;
         dRec.d = ray.d;
-        dRec.dist = its->t;
+        dRec.dist = g_lookupTotalDistance ? walked + its->t : its->t;  // see REFERENCE QUIRK above
         value = scene.emitterEval(*its, -ray.d) * transmittance;
     }
 }
