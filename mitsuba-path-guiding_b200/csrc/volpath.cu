@@ -249,6 +249,9 @@ struct LookJob {
             const float3 value = Le * transmittance;
             const bool prevMedium = (fl & kFlagPrevMedium) != 0;
             if (!isZero(value) && (!prevMedium || fminf(value.x, fminf(value.y, value.z)) > 0.0f)) {  // (:288-303, :330-345)
+                // cur.t is the length of the LAST segment, as in the reference (dRec.setQuery(ray, *its) after the ray origin was
+                // moved to the last index-matched boundary, progressive_volpath.cpp:437-452 / records.inl:170-178) -- not the
+                // distance from the path vertex. Kept for parity; DESIGN.md section 2 ("volumetric Li") has the consequence.
                 const float emitterPdf = (A.cfg.useNee && !(fl & kFlagPrevDelta)) ? pdfEmitterDirect(S, cur.emitter, d, cur.shN, cur.t) : 0.0f;
                 const float weight = A.cfg.useNee ? miWeight(prevPdf, emitterPdf) : 1.0f;
                 contrib = thr * value * weight;
