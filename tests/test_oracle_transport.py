@@ -164,3 +164,32 @@ def test_volumetric_furnace(pkg, oracle, phase, g, method):
     assert np.all(np.abs(mean - want) <= 4 * sem + 2e-3 * want), (mean, want, sem)
     mean, sem = mean_sem()                                           # NEE as the reference does it: biased bright
     assert np.all(mean > 1.05 * want) and np.all(mean < 1.2 * want), (mean, want, sem)
+
+
+@pytest.mark.parametrize("volumetric", [0, 1])
+def test_furnace_with_a_glass_cube(pkg, oracle, volumetric):
+    """A smooth dielectric neither absorbs nor emits: seen from outside, the furnace keeps L / (1 - rho) with a glass cube in
+    it. Exercises SmoothDielectric::sample (dielectric.cpp:300-394): the Fresnel split between the two delta lobes, the
+    radiance scaling factor^2 of transmitted radiance (:311-314) that must cancel over an entry / exit pair, bRec.eta in the
+    Russian-roulette term eta^2 (progressive_path.cpp:296-306), total internal reflection chains inside the cube, and the
+    rule that delta lobes take no next-event estimation and pass emitted radiance with weight one (:276-284). Both
+    integrators (the volumetric one walks the same surfaces without any medium)."""
+    S = pkg.scenes
+    rho, L = 0.5, 1.0
+    sb = S.SceneBuilder(16, 16, spp=4)
+    mat = sb.diffuse((rho, rho, rho))
+    X, Y = (1, 0, 0), (0, 1, 0)
+    for ops in ([S.translate(0, 0, -1)], [S.rotate(Y, 180.0), S.translate(0, 0, 1)], [S.rotate(Y, 90.0), S.translate(-1, 0, 0)],
+                [S.rotate(Y, -90.0), S.translate(1, 0, 0)], [S.rotate(X, -90.0), S.translate(0, -1, 0)],
+                [S.rotate(X, 90.0), S.translate(0, 1, 0)]):
+        sb.rectangle(ops, bsdf=mat, radiance=(L, L, L))
+    sb.cube([S.scale(0.4, 0.3, 0.35), S.rotate(Y, 25.0), S.translate(0.1, -0.1, 0.0)], bsdf=sb.dielectric())
+    sb.set_camera((0.8, 0.7, 0.9), (0.0, 0.0, 0.0), (0, 1, 0), 50.0)          # outside the glass, looking at it
+    osc = oracle.scene(sb)
+    rng = np.random.RandomState(4)
+    n = 200000
+    pix = rng.randint(0, 256, n).astype(np.uint32)
+    rad = osc.radiance(_params(pkg, max_depth=-1, rr_depth=5, volumetric=volumetric), pix, np.arange(n, dtype=np.uint32)).astype(np.float64)
+    want = L / (1 - rho)
+    mean, sem = rad.mean(0), rad.std(0) / np.sqrt(n)
+    assert np.all(np.abs(mean - want) <= 4 * sem + 2e-3 * want), (mean, want, sem)
