@@ -248,3 +248,43 @@ def test_emitter_direct_sampling_chi_square(pkg, oracle):
     assert (pdf_s == 0).all() and (val == 0).all()
     d, dist, pdf_s, val = osc.emitter_sample([0.0, 2.5, 0.0], [0, 0, 0], rng.rand(100, 2))
     assert (pdf_s == 0).all() and (val == 0).all()
+
+
+@pytest.mark.parametrize("fov_axis", [0, 1, 2, 3, 4])
+def test_perspective_camera_geometry(pkg, oracle, fov_axis):
+    """PerspectiveCameraImpl (perspective.cpp:126-180, 271-298) and Transform::lookAt / perspective (transform.cpp:99-123,
+    191-214), pinned to what they must satisfy: the centre ray runs along the viewing direction, the field of view is
+    measured along the chosen axis (x, y, diagonal, smaller, larger: sensor.cpp:240-258), pixels are square, the image is
+    not mirrored (+x to the right, pixel row 0 at the top for a camera on +z looking at the origin with up = +y), and the
+    ray interval is the near / far clip distance measured along the optical axis."""
+    W, H, fov = 64, 40, 50.0
+    sb = pkg.scenes.SceneBuilder(W, H, spp=1)
+    sb.rectangle([pkg.scenes.scale(1, 1, 1)], bsdf=sb.diffuse((0.5, 0.5, 0.5)), radiance=(1, 1, 1))
+    origin, target = np.array([0.5, 0.25, 4.0]), np.array([0.0, 0.0, 0.0])
+    sb.set_camera(tuple(origin), tuple(target), (0, 1, 0), fov, fov_axis=fov_axis)
+    osc = oracle.scene(sb)
+    pos = np.float32([[W / 2, H / 2], [0, H / 2], [W, H / 2], [W / 2, 0], [W / 2, H], [0, 0], [W, H]])
+    r = osc.camera_rays(pos)
+    o, mint, d, maxt = r[:, :3], r[:, 3], r[:, 4:7], r[:, 7]
+    axis = (target - origin) / np.linalg.norm(target - origin)
+    np.testing.assert_allclose(o, np.tile(origin, (len(pos), 1)), atol=1e-6)
+    np.testing.assert_allclose(np.linalg.norm(d, axis=1), 1, atol=1e-6)
+    np.testing.assert_allclose(d[0], axis, atol=1e-6)
+    cosang = d @ axis
+    half = lambda i: np.degrees(np.arccos(cosang[i]))              # angle between ray i and the optical axis
+    np.testing.assert_allclose(half(1), half(2), atol=1e-3)        # symmetric
+    np.testing.assert_allclose(half(3), half(4), atol=1e-3)
+    tx, ty = np.tan(np.radians(half(1))), np.tan(np.radians(half(3)))
+    np.testing.assert_allclose(ty / tx, H / W, rtol=1e-4)          # square pixels
+    tdiag = np.tan(np.radians(half(5)))
+    np.testing.assert_allclose(tdiag, np.hypot(tx, ty), rtol=1e-4)
+    measured = {0: 2 * half(1), 1: 2 * half(3), 2: 2 * half(5), 3: 2 * min(half(1), half(3)), 4: 2 * max(half(1), half(3))}[fov_axis]
+    np.testing.assert_allclose(measured, fov, atol=2e-3)
+    # orientation: pixel column 0 looks to -x, row 0 looks up
+    right = np.cross(axis, [0, 1, 0])
+    right /= np.linalg.norm(right)
+    up = np.cross(right, axis)
+    assert d[1] @ right < 0 < d[2] @ right and d[3] @ up > 0 > d[4] @ up
+    # near / far clip (defaults 1e-2 / 1e4, sensor.cpp:158-160) along the optical axis: mint = near / cos, maxt = far / cos
+    np.testing.assert_allclose(mint * cosang, 1e-2, rtol=1e-4)
+    np.testing.assert_allclose(maxt * cosang, 1e4, rtol=1e-4)
