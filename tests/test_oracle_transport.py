@@ -22,14 +22,19 @@ def _corner_form_factor(a, b, c):
     return (X / np.sqrt(1 + X * X) * np.arctan(Y / np.sqrt(1 + X * X)) + Y / np.sqrt(1 + Y * Y) * np.arctan(X / np.sqrt(1 + Y * Y))) / (2 * np.pi)
 
 
+@pytest.mark.parametrize("light", ["rectangle", "trimesh"])
 @pytest.mark.parametrize("use_nee", [1, 0])
-def test_direct_illumination_matches_the_form_factor(pkg, oracle, use_nee):
+def test_direct_illumination_matches_the_form_factor(pkg, oracle, use_nee, light):
     S = pkg.scenes
     rho, L, h, hx, hz = 0.6, (5.0, 3.0, 1.0), 1.5, 0.8, 0.5
     sb = S.SceneBuilder(9, 9, spp=1)
     X = (1, 0, 0)
     sb.rectangle([S.scale(50, 50, 1), S.rotate(X, -90.0)], bsdf=sb.diffuse((rho, rho, rho)))                      # floor, y = 0, +y
-    sb.rectangle([S.scale(hx, hz, 1), S.rotate(X, 90.0), S.translate(0.3, h, -0.2)], bsdf=-1, radiance=L)         # light, -y
+    if light == "rectangle":   # Rectangle::samplePosition (rectangle.cpp:210-216)
+        sb.rectangle([S.scale(hx, hz, 1), S.rotate(X, 90.0), S.translate(0.3, h, -0.2)], bsdf=-1, radiance=L)     # light, -y
+    else:                      # the same light as two triangles: TriMesh::samplePosition over the area cdf (trimesh.cpp:412-423)
+        P = [[0.3 - hx, h, -0.2 - hz], [0.3 + hx, h, -0.2 - hz], [0.3 + hx, h, -0.2 + hz], [0.3 - hx, h, -0.2 + hz]]
+        sb.trimesh(P=P, T=[[0, 1, 2], [0, 2, 3]], bsdf=-1, radiance=L)                                            # winding: normal -y
     # the camera looks at the floor point (0.5, 0, 0.1) through a very narrow pixel, from below the light's plane
     target = np.array([0.5, 0.0, 0.1])
     sb.set_camera((3.0, 1.0, 2.5), tuple(target), (0, 1, 0), 0.05)
