@@ -198,3 +198,32 @@ def test_furnace_with_a_glass_cube(pkg, oracle, volumetric):
     want = L / (1 - rho)
     mean, sem = rad.mean(0), rad.std(0) / np.sqrt(n)
     assert np.all(np.abs(mean - want) <= 4 * sem + 2e-3 * want), (mean, want, sem)
+
+
+def test_two_lights_share_the_emitter_pmf(pkg, oracle):
+    """Scene::sampleEmitterDirect picks an emitter from the discrete distribution over samplingWeight (scene.cpp:871-895,
+    pmf.h:124-188, reusing the sample) and divides by its probability: two lights of different size and radiance add up to
+    rho * (L1 F1 + L2 F2)."""
+    S = pkg.scenes
+    rho = 0.5
+    sb = S.SceneBuilder(9, 9, spp=1)
+    X = (1, 0, 0)
+    sb.rectangle([S.scale(50, 50, 1), S.rotate(X, -90.0)], bsdf=sb.diffuse((rho, rho, rho)))
+    lights = [((0.4, 0.3), (0.0, 1.2, 0.0), (4.0, 4.0, 4.0)), ((0.2, 0.6), (0.9, 2.0, -0.5), (1.0, 9.0, 2.0))]
+    for (hx, hz), c, L in lights:
+        sb.rectangle([S.scale(hx, hz, 1), S.rotate(X, 90.0), S.translate(*c)], bsdf=-1, radiance=L)
+    target = np.array([0.2, 0.0, 0.1])
+    sb.set_camera((3.0, 1.0, 2.5), tuple(target), (0, 1, 0), 0.05)
+    osc = oracle.scene(sb)
+
+    def signed_ff(x0, x1, z0, z1, h):  # rectangle [x0, x1] x [z0, z1] relative to the foot point, any position (superposition)
+        f = lambda a, b: np.sign(a) * np.sign(b) * _corner_form_factor(abs(a), abs(b), h) if a != 0 and b != 0 else 0.0
+        return f(x1, z1) - f(x0, z1) - f(x1, z0) + f(x0, z0)
+
+    want = np.zeros(3)
+    for (hx, hz), c, L in lights:
+        want += rho * np.array(L) * signed_ff(c[0] - hx - target[0], c[0] + hx - target[0], c[2] - hz - target[2], c[2] + hz - target[2], c[1])
+    n = 400000
+    rad = osc.radiance(_params(pkg, max_depth=2), np.full(n, 40, np.uint32), np.arange(n, dtype=np.uint32)).astype(np.float64)
+    mean, sem = rad.mean(0), rad.std(0) / np.sqrt(n)
+    assert np.all(np.abs(mean - want) <= 4 * sem + 2e-3 * want), (mean, want, sem)
