@@ -8,6 +8,8 @@ The GPU path agrees with the oracle sample by sample (tests/test_gpu_parity.py),
 import numpy as np
 import pytest
 
+from transport_cases import corner_form_factor as _corner_form_factor, form_factor_scene, furnace_scene
+
 
 def _params(pkg, **kw):
     p = pkg._abi.default_params()
@@ -16,38 +18,14 @@ def _params(pkg, **kw):
     return p
 
 
-def _corner_form_factor(a, b, c):
-    """Differential element to a parallel a x b rectangle whose corner lies on the element's normal, distance c."""
-    X, Y = a / c, b / c
-    return (X / np.sqrt(1 + X * X) * np.arctan(Y / np.sqrt(1 + X * X)) + Y / np.sqrt(1 + Y * Y) * np.arctan(X / np.sqrt(1 + Y * Y))) / (2 * np.pi)
-
-
 @pytest.mark.parametrize("light", ["rectangle", "trimesh"])
 @pytest.mark.parametrize("use_nee", [1, 0])
 def test_direct_illumination_matches_the_form_factor(pkg, oracle, use_nee, light):
-    S = pkg.scenes
-    rho, L, h, hx, hz = 0.6, (5.0, 3.0, 1.0), 1.5, 0.8, 0.5
-    sb = S.SceneBuilder(9, 9, spp=1)
-    X = (1, 0, 0)
-    sb.rectangle([S.scale(50, 50, 1), S.rotate(X, -90.0)], bsdf=sb.diffuse((rho, rho, rho)))                      # floor, y = 0, +y
-    if light == "rectangle":   # Rectangle::samplePosition (rectangle.cpp:210-216)
-        sb.rectangle([S.scale(hx, hz, 1), S.rotate(X, 90.0), S.translate(0.3, h, -0.2)], bsdf=-1, radiance=L)     # light, -y
-    else:                      # the same light as two triangles: TriMesh::samplePosition over the area cdf (trimesh.cpp:412-423)
-        P = [[0.3 - hx, h, -0.2 - hz], [0.3 + hx, h, -0.2 - hz], [0.3 + hx, h, -0.2 + hz], [0.3 - hx, h, -0.2 + hz]]
-        sb.trimesh(P=P, T=[[0, 1, 2], [0, 2, 3]], bsdf=-1, radiance=L)                                            # winding: normal -y
-    # the camera looks at the floor point (0.5, 0, 0.1) through a very narrow pixel, from below the light's plane
-    target = np.array([0.5, 0.0, 0.1])
-    sb.set_camera((3.0, 1.0, 2.5), tuple(target), (0, 1, 0), 0.05)
+    sb, centre, want = form_factor_scene(pkg, light)
     osc = oracle.scene(sb)
     n = 400000
-    pix = np.full(n, 4 * 9 + 4, np.uint32)                                                                         # centre pixel
+    pix = np.full(n, centre, np.uint32)
     rad = osc.radiance(_params(pkg, max_depth=2, use_nee=use_nee), pix, np.arange(n, dtype=np.uint32)).astype(np.float64)
-    # form factor by superposition of four corner rectangles around the foot point of the floor point
-    dx0, dx1 = target[0] - (0.3 - hx), (0.3 + hx) - target[0]
-    dz0, dz1 = target[2] - (-0.2 - hz), (-0.2 + hz) - target[2]
-    assert min(dx0, dx1, dz0, dz1) > 0
-    F = sum(_corner_form_factor(a, b, h) for a in (dx0, dx1) for b in (dz0, dz1))
-    want = rho * np.array(L) * F
     mean, sem = rad.mean(0), rad.std(0) / np.sqrt(n)
     assert np.all(np.abs(mean - want) <= 4 * sem + 2e-3 * want), (mean, want, sem)
     assert np.all(sem < 0.01 * want)
@@ -55,28 +33,14 @@ def test_direct_illumination_matches_the_form_factor(pkg, oracle, use_nee, light
 
 @pytest.mark.parametrize("kw", [dict(max_depth=-1, rr_depth=5), dict(max_depth=-1, rr_depth=1), dict(max_depth=-1, rr_depth=3, use_nee=0)])
 def test_furnace(pkg, oracle, kw):
-    S = pkg.scenes
+    sb, want = furnace_scene(pkg, res=8)
     rho, L = 0.5, 1.0
-    sb = S.SceneBuilder(8, 8, spp=1)
-    mat = sb.diffuse((rho, rho, rho))
-    X, Y = (1, 0, 0), (0, 1, 0)
-    # the six faces of [-1, 1]^3, normals pointing inwards, every face an emitter
-    faces = [[S.translate(0, 0, -1)],                                   # z = -1, normal +z
-             [S.rotate(Y, 180.0), S.translate(0, 0, 1)],                # z = +1, normal -z
-             [S.rotate(Y, 90.0), S.translate(-1, 0, 0)],                # x = -1, normal +x
-             [S.rotate(Y, -90.0), S.translate(1, 0, 0)],                # x = +1, normal -x
-             [S.rotate(X, -90.0), S.translate(0, -1, 0)],               # y = -1, normal +y
-             [S.rotate(X, 90.0), S.translate(0, 1, 0)]]                 # y = +1, normal -y
-    for ops in faces:
-        sb.rectangle(ops, bsdf=mat, radiance=(L, L, L))
-    sb.set_camera((0.1, -0.2, 0.3), (0.9, 0.4, -1.0), (0, 1, 0), 70.0)
     osc = oracle.scene(sb)
     # every face really faces inwards: a ray from the centre sees an emitting front side everywhere
     rng = np.random.RandomState(0)
     n = 200000
     pix = rng.randint(0, 64, n).astype(np.uint32)
     rad = osc.radiance(_params(pkg, **kw), pix, np.arange(n, dtype=np.uint32)).astype(np.float64)
-    want = L / (1 - rho)
     mean, sem = rad.mean(0), rad.std(0) / np.sqrt(n)
     assert np.all(np.abs(mean - want) <= 4 * sem + 1e-3 * want), (mean, want, sem)
     # truncated series: maxDepth = k keeps the first k terms L (1 + rho + ... + rho^(k-1)) -- emitted radiance of the first
@@ -91,16 +55,7 @@ def test_furnace(pkg, oracle, kw):
 def test_guided_furnace(pkg, oracle):
     """One-sample MIS between the BSDF and a TRAINED guiding field must not bias the estimator: the furnace value L / (1 - rho)
     again, with directions drawn from the mixtures half of the time (field trained by two updates on this scene)."""
-    S = pkg.scenes
-    rho, L = 0.5, 1.0
-    sb = S.SceneBuilder(16, 16, spp=4)
-    mat = sb.diffuse((rho, rho, rho))
-    X, Y = (1, 0, 0), (0, 1, 0)
-    for ops in ([S.translate(0, 0, -1)], [S.rotate(Y, 180.0), S.translate(0, 0, 1)], [S.rotate(Y, 90.0), S.translate(-1, 0, 0)],
-                [S.rotate(Y, -90.0), S.translate(1, 0, 0)], [S.rotate(X, -90.0), S.translate(0, -1, 0)],
-                [S.rotate(X, 90.0), S.translate(0, 1, 0)]):
-        sb.rectangle(ops, bsdf=mat, radiance=(L, L, L))
-    sb.set_camera((0.1, -0.2, 0.3), (0.9, 0.4, -1.0), (0, 1, 0), 70.0)
+    sb, want = furnace_scene(pkg)
     osc = oracle.scene(sb)
     p = _params(pkg, max_depth=-1, rr_depth=5, guiding=1, guide_max_components=8, guide_max_cell_samples=2000)
     fld = oracle.field(8, (0, 0, 0), (1, 1, 1))
@@ -114,7 +69,6 @@ def test_guided_furnace(pkg, oracle):
     n = 200000
     pix = rng.randint(0, 256, n).astype(np.uint32)
     rad = osc.radiance(p, pix, 1000 + np.arange(n, dtype=np.uint32), field=fld).astype(np.float64)
-    want = L / (1 - rho)
     mean, sem = rad.mean(0), rad.std(0) / np.sqrt(n)
     assert np.all(np.abs(mean - want) <= 4 * sem + 1e-3 * want), (mean, want, sem)
 
@@ -132,28 +86,12 @@ def test_volumetric_furnace(pkg, oracle, phase, g, method):
     without NEE the reference algorithm returns the exact value; with NEE and the total distance (oracle test hook) it does
     too; with NEE as the reference does it, the result is several per cent too bright -- which this test pins, because the
     product reproduces the reference (parity), not the corrected estimator."""
-    S = pkg.scenes
-    rho, L = 0.5, 1.0
-    sb = S.SceneBuilder(16, 16, spp=4)
-    mat = sb.diffuse((rho, rho, rho))
-    X, Y = (1, 0, 0), (0, 1, 0)
-    for ops in ([S.translate(0, 0, -1)], [S.rotate(Y, 180.0), S.translate(0, 0, 1)], [S.rotate(Y, 90.0), S.translate(-1, 0, 0)],
-                [S.rotate(Y, -90.0), S.translate(1, 0, 0)], [S.rotate(X, -90.0), S.translate(0, -1, 0)],
-                [S.rotate(X, 90.0), S.translate(0, 1, 0)]):
-        sb.rectangle(ops, bsdf=mat, radiance=(L, L, L))
-    res = 12
-    t = (np.arange(res) + 0.5) / res - 0.5
-    Z3, Y3, X3 = np.meshgrid(t, t, t, indexing="ij")
-    dens = np.clip(1.0 - 3.0 * (X3 * X3 + Y3 * Y3 + Z3 * Z3), 0.05, 1.0).astype(np.float32)       # densities must stay <= 1
-    med = sb.medium(dens, (-0.5, -0.5, -0.5), (0.5, 0.5, 0.5), scale_=4.0, albedo=(1.0, 1.0, 1.0), phase=phase, g=g, method=method)
-    sb.cube([S.scale(0.5, 0.5, 0.5)], bsdf=-1, interior=med)
-    sb.set_camera((0.8, 0.7, 0.9), (0.0, 0.0, 0.0), (0, 1, 0), 50.0)                                  # looks through the medium
+    sb, want = furnace_scene(pkg, medium=(phase, g, method))
     osc = oracle.scene(sb)
     rng = np.random.RandomState(2)
     n = 120000
     pix = rng.randint(0, 256, n).astype(np.uint32)
     smp = np.arange(n, dtype=np.uint32)
-    want = L / (1 - rho)
 
     def mean_sem(**kw):
         r = osc.radiance(_params(pkg, max_depth=-1, rr_depth=5, volumetric=1, **kw), pix, smp).astype(np.float64)
@@ -179,23 +117,12 @@ def test_furnace_with_a_glass_cube(pkg, oracle, volumetric):
     Russian-roulette term eta^2 (progressive_path.cpp:296-306), total internal reflection chains inside the cube, and the
     rule that delta lobes take no next-event estimation and pass emitted radiance with weight one (:276-284). Both
     integrators (the volumetric one walks the same surfaces without any medium)."""
-    S = pkg.scenes
-    rho, L = 0.5, 1.0
-    sb = S.SceneBuilder(16, 16, spp=4)
-    mat = sb.diffuse((rho, rho, rho))
-    X, Y = (1, 0, 0), (0, 1, 0)
-    for ops in ([S.translate(0, 0, -1)], [S.rotate(Y, 180.0), S.translate(0, 0, 1)], [S.rotate(Y, 90.0), S.translate(-1, 0, 0)],
-                [S.rotate(Y, -90.0), S.translate(1, 0, 0)], [S.rotate(X, -90.0), S.translate(0, -1, 0)],
-                [S.rotate(X, 90.0), S.translate(0, 1, 0)]):
-        sb.rectangle(ops, bsdf=mat, radiance=(L, L, L))
-    sb.cube([S.scale(0.4, 0.3, 0.35), S.rotate(Y, 25.0), S.translate(0.1, -0.1, 0.0)], bsdf=sb.dielectric())
-    sb.set_camera((0.8, 0.7, 0.9), (0.0, 0.0, 0.0), (0, 1, 0), 50.0)          # outside the glass, looking at it
+    sb, want = furnace_scene(pkg, glass=True)
     osc = oracle.scene(sb)
     rng = np.random.RandomState(4)
     n = 200000
     pix = rng.randint(0, 256, n).astype(np.uint32)
     rad = osc.radiance(_params(pkg, max_depth=-1, rr_depth=5, volumetric=volumetric), pix, np.arange(n, dtype=np.uint32)).astype(np.float64)
-    want = L / (1 - rho)
     mean, sem = rad.mean(0), rad.std(0) / np.sqrt(n)
     assert np.all(np.abs(mean - want) <= 4 * sem + 2e-3 * want), (mean, want, sem)
 
