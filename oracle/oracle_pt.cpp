@@ -850,7 +850,7 @@ int orc_trace_bruteforce(void *s, const float *rays, size_t n, float *tuv, uint3
         if (mint == Epsilon)
             mint *= std::max(std::max(std::max(std::abs(ray.o.x), std::abs(ray.o.y)), std::abs(ray.o.z)), Epsilon);
         Float t = std::numeric_limits<Float>::infinity();
-        IntersectionCache cache, best;
+        IntersectionCache cache{}, best{};
         bool found = false;
         for (uint32_t p = 0; p < sc->triAccel.size(); ++p) {
             Float tt;
