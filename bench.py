@@ -97,6 +97,7 @@ class CpuGuidedStep:
         self.sink = self.orc.samples() if guided else None
         self.trained = False
         self.k = 0
+        self.kd = dict(kd_nodes=0, kd_indices=0, prim_tests=0, normal_rays=0, shadow_rays=0)
 
     def load_field(self, words):
         self.field.load(words)
@@ -113,7 +114,24 @@ class CpuGuidedStep:
             self.field.train_sink(self.sink, self.em_iters, float(self.p.guide_max_cell_samples))
             self.trained = True
         self.k += 1
+        for key in ("kd_nodes", "kd_indices", "prim_tests"):
+            self.kd[key] += st[key]
+        self.kd["normal_rays"] += st["normal_rays"]
+        self.kd["shadow_rays"] += st["shadow_rays"]
         return time.perf_counter() - t0, st["paths"], st["normal_rays"] + st["shadow_rays"]
+
+    def kd_bytes_per_ray(self):
+        """B_ray = 32 (ray) + 16 (hit; 4 for a shadow ray) + 8 n_node + 4 n_idx + 48 n_tri, averaged over the
+        exact ray set by the reference's counting traversal (rayIntersectHavranCollectStatistics, sahkdtree3.h:330-429) --
+        here: the oracle's restatement of that traversal over everything this object has rendered."""
+        k = self.kd
+        rays = k["normal_rays"] + k["shadow_rays"]
+        if not rays:
+            return None
+        n_node, n_idx, n_tri = k["kd_nodes"] / rays, k["kd_indices"] / rays, k["prim_tests"] / rays
+        hit = (16 * k["normal_rays"] + 4 * k["shadow_rays"]) / rays
+        return {"nodes": n_node, "indices": n_idx, "prim_tests": n_tri, "B_ray": 32 + hit + 8 * n_node + 4 * n_idx + 48 * n_tri,
+                "structure": "SAH kd-tree of the reference (oracle restatement), counting traversal"}
 
 
 def guided_params(pkg, args):
@@ -161,7 +179,8 @@ def run_reference(args):
         "config": {"workload": desc, "spp_per_step": spp, "rows": rows, "pretrain_iterations": args.pretrain if guided else 0,
                    "guiding": ("training iteration per step: K=16 vMF lobes/cell, %d EM iterations" % args.em_iters) if guided else "off"},
         "mrays_per_sec": rays / t / 1e6,
-        "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": cores, "kind": "port", "sample": sample,
+                         "kd_traversal_per_ray": cpu.kd_bytes_per_ray()},
         "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -451,7 +470,7 @@ def main():
                    "sample": "%d guided training iterations over rows 0..%d of the %dx%d image at %d spp (%.1f s of CPU work)"
                              % (nrep, rows, sb.width, sb.height, spp, t) if guided else
                              "%d unguided progressions over rows 0..%d at %d spp (%.1f s)" % (nrep, rows, spp, t),
-                   "mrays_per_sec": nr2 / t / 1e6}
+                   "mrays_per_sec": nr2 / t / 1e6, "kd_traversal_per_ray": cb.kd_bytes_per_ray()}
         except Exception as ex:  # the oracle is test infrastructure; its absence must not break the product arm
             cpu = {"value": None, "unit": "Mpaths/s", "cores": 0, "kind": "port", "sample": "oracle unavailable: %s" % ex}
         line = {
