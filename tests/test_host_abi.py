@@ -107,3 +107,33 @@ def test_no_cpu_fallback(api, pkg):
     sc = api.Scene.from_builder(pkg.scenes.cornell_box(16, 16))
     with pytest.raises(api.B200pgError, match="CUDA"):
         api.Integrator(sc, api.default_params())
+
+
+def test_header_is_plain_c_and_links_from_c(pkg, tmp_path):
+    """The boundary is a C ABI: include/b200pg.h compiles as strict C99 (no C++ or torch types in any signature) and a C
+    program links against libb200pg.so and calls it (here: the entry points that need no GPU)."""
+    import shutil
+    import subprocess
+
+    from conftest import PKG_DIR, ROOT
+
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include "b200pg.h"\n'
+                   'int main(void) {\n'
+                   '    B200pgIntegratorParams p;\n'
+                   '    b200pg_integrator_params_default(&p);\n'
+                   '    char err[256];\n'
+                   '    void *s = b200pg_scene_load_xml("/nonexistent.xml", NULL, err, sizeof err);\n'
+                   '    printf("%d %d %d %s\\n", b200pg_version(), p.rr_depth, s == NULL, err);\n'
+                   '    return 0;\n}\n')
+    exe = tmp_path / "t_c"
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                        "-L", PKG_DIR, "-lb200pg", "-Wl,-rpath," + PKG_DIR, "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    ver, rr, null, msg = out.stdout.split(" ", 3)
+    assert int(ver) >= 100 and int(rr) == 5 and null == "1" and "cannot open" in msg
