@@ -154,3 +154,22 @@ def test_two_lights_share_the_emitter_pmf(pkg, oracle):
     rad = osc.radiance(_params(pkg, max_depth=2), np.full(n, 40, np.uint32), np.arange(n, dtype=np.uint32)).astype(np.float64)
     mean, sem = rad.mean(0), rad.std(0) / np.sqrt(n)
     assert np.all(np.abs(mean - want) <= 4 * sem + 2e-3 * want), (mean, want, sem)
+
+
+@pytest.mark.parametrize("volumetric", [0, 1])
+def test_furnace_hide_emitters_and_strict_normals(pkg, oracle, volumetric):
+    """hideEmitters drops only the emission of directly visible emitters ((!m_hideEmitters || scattered),
+    progressive_path.cpp:167-169): the furnace loses exactly its first term, L / (1 - rho) - L. strictNormals changes nothing
+    on flat-shaded geometry (geometric and shading normals agree, :175-184)."""
+    sb, want = furnace_scene(pkg)
+    osc = oracle.scene(sb)
+    rng = np.random.RandomState(6)
+    n = 150000
+    pix = rng.randint(0, 256, n).astype(np.uint32)
+    smp = np.arange(n, dtype=np.uint32)
+    r = osc.radiance(_params(pkg, max_depth=-1, rr_depth=5, hide_emitters=1, volumetric=volumetric), pix, smp).astype(np.float64)
+    mean, sem = r.mean(0), r.std(0) / np.sqrt(n)
+    assert np.all(np.abs(mean - (want - 1.0)) <= 4 * sem + 1e-3), (mean, want - 1.0, sem)
+    a = osc.radiance(_params(pkg, max_depth=-1, rr_depth=5, volumetric=volumetric), pix[:20000], smp[:20000])
+    b = osc.radiance(_params(pkg, max_depth=-1, rr_depth=5, strict_normals=1, volumetric=volumetric), pix[:20000], smp[:20000])
+    assert np.array_equal(a, b)
