@@ -173,3 +173,24 @@ def test_furnace_hide_emitters_and_strict_normals(pkg, oracle, volumetric):
     a = osc.radiance(_params(pkg, max_depth=-1, rr_depth=5, volumetric=volumetric), pix[:20000], smp[:20000])
     b = osc.radiance(_params(pkg, max_depth=-1, rr_depth=5, strict_normals=1, volumetric=volumetric), pix[:20000], smp[:20000])
     assert np.array_equal(a, b)
+
+
+def test_furnace_image_is_flat_including_the_border(pkg, oracle):
+    """The whole image pipeline on the furnace: tiles with filter borders merged into the film (imageproc.cpp:27-78,
+    imageblock.h:131-197), Gaussian reconstruction filter, develop = colour / weight (fmtconv.cpp:978-1005). A constant
+    radiance field must come out constant in every pixel -- also in the first and last rows / columns, where part of the
+    filter footprint falls outside the image and only the weight division keeps the level."""
+    from oracle_lib import develop
+
+    sb, want = furnace_scene(pkg, res=40)                       # 40 x 40: two tiles in each direction (32-pixel tiles)
+    osc = oracle.scene(sb)
+    film, st = osc.render(_params(pkg, max_depth=-1, rr_depth=5), 0, 48)
+    img = develop(film)
+    assert img.shape == (40, 40, 3) and np.isfinite(img).all()
+    assert abs(img.mean() - want) < 0.01
+    border = np.concatenate([img[0].ravel(), img[-1].ravel(), img[:, 0].ravel(), img[:, -1].ravel()])
+    inner = img[4:-4, 4:-4].ravel()
+    assert abs(border.mean() - want) < 0.03 and abs(inner.mean() - want) < 0.01
+    assert img.std() < 0.25                                     # per-pixel noise of 48 samples with std ~ 1 each, filtered
+    # the weight channel: interior pixels collect the full normalised footprint of 48 samples per pixel
+    assert abs(film[8:-8, 8:-8, 4].mean() / 48 - 1.0) < 0.02
