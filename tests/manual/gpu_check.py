@@ -1,7 +1,7 @@
 """Ad-hoc GPU-vs-oracle comparison (development aid; the judged tests live in tests/)."""
 import sys, time, os
 import numpy as np
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from conftest import load_package
 b = load_package()
 from b200pg import api

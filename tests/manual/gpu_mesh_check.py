@@ -1,7 +1,7 @@
 """C4: procedural mesh scene. Parity on a 200k-triangle version vs the oracle; performance + counters at ~10M triangles."""
 import sys, time, os
 import numpy as np
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from conftest import load_package
 b = load_package()
 from b200pg import api

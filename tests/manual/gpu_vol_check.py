@@ -1,7 +1,7 @@
 """C3: heterogeneous medium. Sample-by-sample parity of the volumetric path vs the oracle on a small grid, then timing at 256^3 / 1024^2."""
 import sys, time, os
 import numpy as np
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from conftest import load_package
 b = load_package()
 from b200pg import api
