@@ -238,3 +238,29 @@ def test_the_field_learns_where_the_light_is(pkg, oracle):
         mean, sem = r.mean(0), r.std(0) / np.sqrt(n2)
         assert np.all(np.abs(mean - want) <= 4 * sem + 2e-3 * want), (mean, want, sem)
     assert g.var(0).sum() < 0.5 * u.var(0).sum(), (g.var(0), u.var(0))
+
+
+@pytest.mark.parametrize("guided_distance", [0, 1])
+def test_guided_volumetric_furnace(pkg, oracle, guided_distance):
+    """The guided volumetric path (direction guiding at medium and surface vertices; optionally guided free-flight sampling with
+    weighted delta tracking) against the furnace value, with a trained field. Next-event estimation is off so that the
+    reference's look-up quirk (test_volumetric_furnace) does not enter: what is tested is that the guided decisions --
+    mixture / phase one-sample MIS, guided collision probabilities and their weights -- leave the estimator unbiased."""
+    sb, want = furnace_scene(pkg, medium=("hg", 0.5, "woodcock"))
+    osc = oracle.scene(sb)
+    K = 8
+    p = _params(pkg, max_depth=-1, rr_depth=5, volumetric=1, use_nee=0, guiding=1, guide_max_components=K,
+                guide_max_cell_samples=3000, guided_distance=guided_distance)
+    fld = oracle.field(K, (0, 0, 0), (1, 1, 1))
+    sink = oracle.samples()
+    for k in range(2):
+        sink.clear()
+        osc.render(p, 4 * k, 4, field=fld if k else None, sink=sink)
+        fld.train_sink(sink, 4, 3000.0)
+    assert fld.info()["cells"] > 1
+    rng = np.random.RandomState(8)
+    n = 150000
+    pix = rng.randint(0, 256, n).astype(np.uint32)
+    rad = osc.radiance(p, pix, 5000 + np.arange(n, dtype=np.uint32), field=fld).astype(np.float64)
+    mean, sem = rad.mean(0), rad.std(0) / np.sqrt(n)
+    assert np.all(np.abs(mean - want) <= 4 * sem + 2e-3 * want), (mean, want, sem)
