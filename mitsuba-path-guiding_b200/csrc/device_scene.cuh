@@ -34,6 +34,7 @@ struct DeviceScene {
     const float *density;
     const uint32_t *primGlobalId;
     const PrimInfo *primInfo;
+    const float4 *shadeTris;  // 6 x float4 per primitive slot (pg_types.h: ShadeTri)
     uint32_t nEmitters;
     uint32_t nPrims;
     CameraRecord camera;
@@ -57,37 +58,65 @@ PG_DEV float adaptiveMinT(float3 o, float mint, bool shadow) {
     return mint;
 }
 
-// One inner-node step of the BVH2 descent: tests both child boxes (4 x LDG.128), continues with the nearer hit
-// child and pushes the farther one. kDoneNode when the stack runs empty.
+// Packed FP32 pairs (sm_100a: FADD2 / FMUL2 process two floats per instruction). The slab distances of one box axis,
+// (min - o) * idir and (max - o) * idir, are exactly the two lanes of one pair, so the twelve subtract + twelve multiply of a
+// node visit become six + six instructions with bit-identical results.
+#ifndef PG_PACKED_SLABS
+#define PG_PACKED_SLABS 1
+#endif
+PG_DEV float2 slabPair(float lo, float hi, float o, float idir) {
+#if PG_PACKED_SLABS
+    float2 v = make_float2(lo, hi), o2 = make_float2(o, o), i2 = make_float2(idir, idir);
+    unsigned long long d, e;
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(d) : "l"(reinterpret_cast<unsigned long long &>(v)), "l"(reinterpret_cast<unsigned long long &>(o2)));
+    asm("mul.f32x2 %0, %1, %2;" : "=l"(e) : "l"(d), "l"(reinterpret_cast<unsigned long long &>(i2)));
+    return reinterpret_cast<float2 &>(e);
+#else
+    return make_float2((lo - o) * idir, (hi - o) * idir);
+#endif
+}
+
+// Box tests of one inner node (4 x LDG.128): returns how many children the ray interval [mint, tmax] overlaps; c0 = the
+// nearer (or only) hit child, c1 = the farther one.
 static constexpr int kDoneNode = (int)0x80000000;  // ~kDoneNode is not a valid leaf code
-PG_DEV int bvhNodeStep(const DeviceScene &S, int node, float3 o, float3 idir, float mint, float tmax, int *stack, int &sp) {
+PG_DEV int bvhTestNode(const DeviceScene &S, int node, float3 o, float3 idir, float mint, float tmax, int &c0, int &c1) {
     const float4 n0 = __ldg(S.nodes + 4 * node + 0);
     const float4 n1 = __ldg(S.nodes + 4 * node + 1);
     const float4 n2 = __ldg(S.nodes + 4 * node + 2);
     const float4 n3 = __ldg(S.nodes + 4 * node + 3);
     // slabs; fminf/fmaxf drop NaNs from 0*inf
-    const float c0lox = (n0.x - o.x) * idir.x, c0hix = (n0.y - o.x) * idir.x;
-    const float c0loy = (n0.z - o.y) * idir.y, c0hiy = (n0.w - o.y) * idir.y;
-    const float c0loz = (n2.x - o.z) * idir.z, c0hiz = (n2.y - o.z) * idir.z;
-    const float c1lox = (n1.x - o.x) * idir.x, c1hix = (n1.y - o.x) * idir.x;
-    const float c1loy = (n1.z - o.y) * idir.y, c1hiy = (n1.w - o.y) * idir.y;
-    const float c1loz = (n2.z - o.z) * idir.z, c1hiz = (n2.w - o.z) * idir.z;
-    const float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), mint));
-    const float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tmax));
-    const float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), mint));
-    const float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tmax));
+    const float2 x0 = slabPair(n0.x, n0.y, o.x, idir.x), y0 = slabPair(n0.z, n0.w, o.y, idir.y), z0 = slabPair(n2.x, n2.y, o.z, idir.z);
+    const float2 x1 = slabPair(n1.x, n1.y, o.x, idir.x), y1 = slabPair(n1.z, n1.w, o.y, idir.y), z1 = slabPair(n2.z, n2.w, o.z, idir.z);
+    const float t0n = fmaxf(fmaxf(fminf(x0.x, x0.y), fminf(y0.x, y0.y)), fmaxf(fminf(z0.x, z0.y), mint));
+    const float t0f = fminf(fminf(fmaxf(x0.x, x0.y), fmaxf(y0.x, y0.y)), fminf(fmaxf(z0.x, z0.y), tmax));
+    const float t1n = fmaxf(fmaxf(fminf(x1.x, x1.y), fminf(y1.x, y1.y)), fmaxf(fminf(z1.x, z1.y), mint));
+    const float t1f = fminf(fminf(fmaxf(x1.x, x1.y), fmaxf(y1.x, y1.y)), fminf(fmaxf(z1.x, z1.y), tmax));
     // conservative far bound (flat boxes, rounding): 1 + 2*gamma(3)
     const bool h0 = t0n <= t0f * 1.0000004f;
     const bool h1 = t1n <= t1f * 1.0000004f;
-    int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+    c0 = __float_as_int(n3.x);
+    c1 = __float_as_int(n3.y);
     if (h0 && h1) {
         if (t1n < t0n) {
             const int tmp = c0; c0 = c1; c1 = tmp;
         }
+        return 2;
+    }
+    if (h1) c0 = c1;
+    return (h0 | h1) ? 1 : 0;
+}
+
+// One inner-node step of the BVH2 descent: continues with the nearer hit child and pushes the farther one.
+// kDoneNode when the stack runs empty.
+static constexpr int kTraceStack = 64;  // the builder bounds the tree depth (host_scene.cpp: median splits below depth 36)
+PG_DEV int bvhNodeStep(const DeviceScene &S, int node, float3 o, float3 idir, float mint, float tmax, int *stack, int &sp) {
+    int c0, c1;
+    const int nh = bvhTestNode(S, node, o, idir, mint, tmax, c0, c1);
+    if (nh == 2) {
         stack[sp++] = c1;
         return c0;
     }
-    if (h0 | h1) return h0 ? c0 : c1;
+    if (nh == 1) return c0;
     return sp ? stack[--sp] : kDoneNode;
 }
 
@@ -133,7 +162,7 @@ PG_DEV bool traceRay(const DeviceScene &S, float3 o, float3 d, float mint, float
     // "while-while" traversal: every lane first descends to its next leaf, then the warp processes
     // leaves together, so that the (uniform, branch-free) primitive test runs with many lanes active.
     const float3 idir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    int stack[48];
+    int stack[kTraceStack];
     int sp = 0;
     int node = 0;
     hit.prim = kMiss;
@@ -163,29 +192,27 @@ struct Intersection {
 };
 
 PG_DEV void fillIntersection(const DeviceScene &S, float3 o, float3 d, const Hit &h, Intersection &its) {
-    const PrimInfo pi = S.primInfo[h.prim];
-    const uint32_t shapeIdx = pi.shape, primIdx = pi.prim;
-    const ShapeRecord sr = S.shapes[shapeIdx];
-    its.shape = (int)shapeIdx;
-    its.bsdf = sr.bsdf;
-    its.emitter = sr.emitter;
-    its.primIndex = primIdx;
+    const float4 *T = S.shadeTris + 6 * (size_t)h.prim;
+    const float4 r0 = __ldg(T), r1 = __ldg(T + 1), r2 = __ldg(T + 2), r3 = __ldg(T + 3), r4 = __ldg(T + 4);
+    const uint32_t flags = __float_as_uint(r1.w);
+    its.shape = (int)__float_as_uint(r0.w);
+    its.bsdf = (int)__float_as_uint(r3.w);
+    its.emitter = (int)__float_as_uint(r4.w);
+    its.primIndex = __float_as_uint(r2.w);
     its.t = h.t;
     float3 dpdu, shN;
-    if (sr.type == B200PG_SHAPE_TRIMESH) {
-        const MeshRecord mr = S.meshes[sr.meshOffset];
-        const uint32_t *idx = S.indices + 3 * ((size_t)mr.indexOffset + primIdx);
-        const uint32_t i0 = idx[0] + mr.vertexOffset, i1 = idx[1] + mr.vertexOffset, i2 = idx[2] + mr.vertexOffset;
+    if (flags & 1u) {  // triangle (skdtree.h:343-428)
         const float3 b = f3(1 - h.u - h.v, h.u, h.v);
-        const float3 p0 = ld3(S.positions + 3 * (size_t)i0), p1 = ld3(S.positions + 3 * (size_t)i1), p2 = ld3(S.positions + 3 * (size_t)i2);
+        const float3 p0 = f3(r0.x, r0.y, r0.z), p1 = f3(r1.x, r1.y, r1.z), p2 = f3(r2.x, r2.y, r2.z);
         its.p = p0 * b.x + p1 * b.y + p2 * b.z;
         float3 side1 = p1 - p0, side2 = p2 - p0;
         float3 faceNormal = cross(side1, side2);
         float len = length(faceNormal);
         if (!isZero(faceNormal)) faceNormal = faceNormal / len;
         dpdu = side1;
-        if (mr.hasNormals) {
-            const float3 n0 = ld3(S.normals + 3 * (size_t)i0), n1 = ld3(S.normals + 3 * (size_t)i1), n2 = ld3(S.normals + 3 * (size_t)i2);
+        if (flags & 2u) {
+            const float4 r5 = __ldg(T + 5);
+            const float3 n0 = f3(r3.x, r3.y, r3.z), n1 = f3(r4.x, r4.y, r4.z), n2 = f3(r5.x, r5.y, r5.z);
             shN = normalize(n0 * b.x + n1 * b.y + n2 * b.z);
             if (dot(faceNormal, shN) < 0) faceNormal = -faceNormal;
         } else {
@@ -193,11 +220,12 @@ PG_DEV void fillIntersection(const DeviceScene &S, float3 o, float3 d, const Hit
         }
         its.geoN = faceNormal;
         its.uv = make_float2(b.y, b.z);
-    } else {
-        const float4 r3 = __ldg(S.rects + 8 * sr.meshOffset + 3), r4 = __ldg(S.rects + 8 * sr.meshOffset + 4);
-        shN = f3(r3.x, r3.y, r3.z);
+    } else {  // rectangle (rectangle.cpp:155-168)
+        const uint32_t rect = S.shapes[its.shape].meshOffset;
+        const float4 q3 = __ldg(S.rects + 8 * rect + 3), q4 = __ldg(S.rects + 8 * rect + 4);
+        shN = f3(q3.x, q3.y, q3.z);
         its.geoN = shN;
-        dpdu = f3(r4.x, r4.y, r4.z);
+        dpdu = f3(q4.x, q4.y, q4.z);
         its.uv = make_float2(0.5f * (h.u + 1), 0.5f * (h.v + 1));
         its.p = o + d * h.t;
     }

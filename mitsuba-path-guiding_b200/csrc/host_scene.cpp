@@ -130,7 +130,7 @@ struct Builder {
     std::vector<BPrim> &P;
     std::vector<TmpNode> nodes;
     std::atomic<int> next{0};
-    static const int kLeaf = 4, kBins = 16;
+    static const int kLeaf = 4, kBins = 16, kMedianDepth = 36;
     explicit Builder(std::vector<BPrim> &p) : P(p) { nodes.resize(std::max<size_t>(1, p.size())); }
 
     static int32_t leafCode(size_t begin, size_t count) { return ~(int32_t)((begin << 4) | count); }
@@ -190,7 +190,15 @@ struct Builder {
             }
         }
         size_t mid;
-        if (bestAxis < 0) {
+        if (depth >= kMedianDepth) {
+            // depth bound for the traversal stack (device_scene.cuh: kTraceStack = 64): from here on the primitives are halved
+            // along the widest centroid axis, so the subtree adds at most log2(n) <= 24 levels
+            int axis = 0;
+            for (int a = 1; a < 3; ++a)
+                if (cb.mx[a] - cb.mn[a] > cb.mx[axis] - cb.mn[axis]) axis = a;
+            mid = begin + n / 2;
+            std::nth_element(&P[begin], &P[mid], &P[begin] + n, [=](const BPrim &a, const BPrim &b) { return a.c[axis] < b.c[axis]; });
+        } else if (bestAxis < 0) {
             mid = begin + n / 2;  // coincident centroids: split by index
         } else {
             float lo = cb.mn[bestAxis], hi = cb.mx[bestAxis];
@@ -834,10 +842,34 @@ bool HostScene::compile(std::string &err) {
             err = "more than 16M primitives are not supported by the leaf encoding";
             return false;
         }
+        shadeTris.assign(bprims.size() * 24, 0.0f);
+#pragma omp parallel for schedule(static)
         for (size_t i = 0; i < bprims.size(); ++i) {
             prims[i] = flat[bprims[i].id];
             primInfo[i] = flatInfo[bprims[i].id];
             primGlobalId[i] = bprims[i].id;
+            // shading record (pg_types.h: ShadeTri): the hit's vertex data in one place, in BVH order
+            const PrimInfo pi = primInfo[i];
+            const ShapeRecord &sr = shapeRecs[pi.shape];
+            float *q = &shadeTris[i * 24];
+            uint32_t flags = 0;
+            if (pi.prim != kNoTriangle) {
+                const MeshRecord &mr = meshes[sr.meshOffset];
+                const uint32_t *idx = &indices[3 * ((size_t)mr.indexOffset + pi.prim)];
+                flags = 1u | (mr.hasNormals ? 2u : 0u);
+                for (int v = 0; v < 3; ++v) {
+                    const size_t vi = (size_t)idx[v] + mr.vertexOffset;
+                    for (int a = 0; a < 3; ++a) {
+                        q[4 * v + a] = positions[3 * vi + a];
+                        q[12 + 4 * v + a] = mr.hasNormals ? normals[3 * vi + a] : 0.0f;
+                    }
+                }
+            }
+            q[3] = u2f(pi.shape);
+            q[7] = u2f(flags);
+            q[11] = u2f(pi.prim);
+            q[15] = u2f((uint32_t)sr.bsdf);
+            q[19] = u2f((uint32_t)sr.emitter);
         }
     }
 

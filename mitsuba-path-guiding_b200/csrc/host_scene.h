@@ -31,6 +31,7 @@ struct HostScene {
     std::vector<PrimRecord> prims;       // BVH leaf order
     std::vector<uint32_t> primGlobalId;  // BVH order -> global primitive id
     std::vector<PrimInfo> primInfo;      // BVH order -> (shape, primitive index)
+    std::vector<float> shadeTris;        // BVH order -> ShadeTri (24 floats), what the shade stage reads per hit
     std::vector<RectRecord> rects;
     std::vector<ShapeRecord> shapeRecs;
     std::vector<MeshRecord> meshes;

@@ -32,9 +32,9 @@ namespace pg {
 // launch wrappers implemented in kernels.cu
 void launchGenerate(const DeviceScene &S, const BatchDesc &B, const PathState &P, Counters *C, cudaStream_t st);
 void launchTrace(const DeviceScene &S, const PathState &P, float4 *hits, const uint32_t *nPtr, uint32_t *work, Counters *C,
-                 bool count, const SortArgs *sort, cudaStream_t st);
+                 bool count, const SortArgs *sort, bool speculative, cudaStream_t st);
 void launchShadow(const DeviceScene &S, const ShadowQueue &Q, float4 *rad, const uint32_t *nPtr, uint32_t *work, Counters *C,
-                  bool count, cudaStream_t st);
+                  bool count, bool speculative, cudaStream_t st);
 void launchShade(const ShadeArgs &A, cudaStream_t st);
 void launchFlush(const ShadeArgs &A, cudaStream_t st);
 void launchFilmAdd(float4 *film, const float4 *peer, uint32_t n, cudaStream_t st);
@@ -50,7 +50,7 @@ void launchMediumTest(const DeviceScene &S, int medium, const float4 *rays, uint
 void launchFilmExport(const float4 *film, float *out, uint32_t n, int develop, cudaStream_t st);
 void launchSplat(const FilmRecord &F, float4 *film, const float4 *splat, uint32_t n, float maxComponentValue, cudaStream_t st);
 void launchTraceRays(const DeviceScene &S, const float4 *rays, uint32_t n, float4 *hits, uint32_t *work, Counters *C, bool shadow,
-                     bool count, cudaStream_t st);
+                     bool count, bool speculative, cudaStream_t st);
 void launchFilmSplat(const FilmRecord &F, float4 *film, const float2 *pos, const float3 *rgb, uint32_t n, float maxComponentValue,
                      cudaStream_t st);
 void launchBsdfTest(const DeviceScene &S, int bsdfIndex, const float *wi, const float *wo, const float *u, uint32_t n, float *outEval,
@@ -92,6 +92,7 @@ struct Integrator {
     DevBuf<float> dPositions, dNormals, dTexcoords, dAreaCdf, dEmitterCdf, dDensity;
     DevBuf<uint32_t> dIndices, dPrimGlobal;
     DevBuf<PrimInfo> dPrimInfo;
+    DevBuf<float4> dShadeTris;
     DevBuf<BsdfRecord> dBsdfs;
     DevBuf<EmitterRecord> dEmitters;
     DevBuf<MediumRecord> dMedia;
@@ -114,6 +115,9 @@ struct Integrator {
     // DESIGN.md, optimisation log 7; B200PG_SORT_BOUNCES / b200pg_set_option("sort_bounces") turn it on)
     int sortBounces = std::getenv("B200PG_SORT_BOUNCES") ? std::atoi(std::getenv("B200PG_SORT_BOUNCES")) : 0;
     DevBuf<uint32_t> dSortKey, dSortRank, dSortPerm, dBinCount, dBinOffset;
+    // persistent speculative traversal with per-lane refill (kernels.cu: traceQueueSpeculative): bit 0 = closest-hit queues of
+    // bounces >= 1, bit 1 = shadow queues, bit 2 = camera rays too (coherent: the batch kernel is as good there)
+    int traceSpec = std::getenv("B200PG_TRACE_SPEC") ? std::atoi(std::getenv("B200PG_TRACE_SPEC")) : 3;
     // denoiser feature buffers (denoiser.cpp:138-144): 3 float4 per pixel, allocated by set_option("feature_buffers", 1)
     bool featureBuffers = false;
     DevBuf<float4> dFeat;
@@ -212,6 +216,7 @@ struct Integrator {
         dDensity.upload(H.densityPool, stream);
         dPrimGlobal.upload(H.primGlobalId, stream);
         dPrimInfo.upload(H.primInfo, stream);
+        dShadeTris.upload(reinterpret_cast<const float4 *>(H.shadeTris.data()), H.shadeTris.size() / 4, stream);
         S.nodes = dNodes.p; S.prims = dPrims.p; S.rects = dRects.p;
         S.shapes = dShapes.p; S.meshes = dMeshes.p;
         S.positions = dPositions.p; S.normals = dNormals.p; S.texcoords = dTexcoords.p;
@@ -219,6 +224,7 @@ struct Integrator {
         S.bsdfs = dBsdfs.p; S.emitters = dEmitters.p; S.emitterCdf = dEmitterCdf.p;
         S.media = dMedia.p; S.density = dDensity.p; S.primGlobalId = dPrimGlobal.p;
         S.primInfo = dPrimInfo.p;
+        S.shadeTris = dShadeTris.p;
         S.nEmitters = (uint32_t)H.emitters.size();
         S.nPrims = (uint32_t)H.prims.size();
         S.camera = H.camera;
@@ -312,7 +318,8 @@ struct Integrator {
             if (cancel.load()) break;
             cudaEvent_t t = spanBegin();
             const bool sorted = sortOn && b >= 1 && b <= sortBounces;
-            launchTrace(S, cur, dHits.p, &C->queue[b], &C->traceWork[b], C, countTraversal, sorted ? &sortArgs : nullptr, stream);
+            launchTrace(S, cur, dHits.p, &C->queue[b], &C->traceWork[b], C, countTraversal, sorted ? &sortArgs : nullptr,
+                        (traceSpec & (b == 0 ? 4 : 1)) != 0, stream);
             if (sorted) stats.kernel_launches += 2;
             spanEnd(kTimeTrace, t);
             if (b == 0 && featureBuffers && !radianceOut) {
@@ -330,7 +337,7 @@ struct Integrator {
             if (params.volumetric)
                 launchShadowVol(S, A.shadow, next.rad, &C->shadow[b], &C->shadowWork[b], C, stream);
             else
-                launchShadow(S, A.shadow, next.rad, &C->shadow[b], &C->shadowWork[b], C, countTraversal, stream);
+                launchShadow(S, A.shadow, next.rad, &C->shadow[b], &C->shadowWork[b], C, countTraversal, (traceSpec & 2) != 0, stream);
             spanEnd(kTimeShadow, t);
             stats.kernel_launches += 3;
             std::swap(cur, next);
@@ -916,6 +923,7 @@ int b200pg_set_option(void *integ, const char *name, int value) {
     if (n == "count_traversal") self->countTraversal = value != 0;
     else if (n == "timing") self->timing = value != 0;
     else if (n == "sort_bounces") self->sortBounces = value;
+    else if (n == "trace_spec") self->traceSpec = value;
     else if (n == "feature_buffers") {
         self->featureBuffers = value != 0;
         if (self->featureBuffers && !self->dFeat.p) {
@@ -955,6 +963,8 @@ int b200pg_scene_upload(void *integ, size_t *bytes) {
     total += H.nodes.size() * 64 + H.prims.size() * 48 + H.rects.size() * 128;
     up(self->dShapes, H.shapeRecs);
     up(self->dPrimInfo, H.primInfo);
+    self->dShadeTris.upload(reinterpret_cast<const float4 *>(H.shadeTris.data()), H.shadeTris.size() / 4, self->stream);
+    total += H.shadeTris.size() * sizeof(float);
     up(self->dMeshes, H.meshes);
     up(self->dPositions, H.positions);
     up(self->dNormals, H.normals);
@@ -982,7 +992,7 @@ int b200pg_k_trace_device(void *integ, const void *d_rays, size_t n, int shadow,
     }
     CUDA_OK(cudaEventRecord(self->ev[0], self->stream));
     launchTraceRays(self->S, (const float4 *)d_rays, (uint32_t)n, (float4 *)d_hits, &C->misc[0], C, shadow != 0, counts != nullptr,
-                    self->stream);
+                    (self->traceSpec & (shadow ? 2 : 1)) != 0, self->stream);
     CUDA_OK(cudaEventRecord(self->ev[1], self->stream));
     CUDA_OK(cudaStreamSynchronize(self->stream));
     CUDA_OK(cudaGetLastError());

@@ -199,6 +199,201 @@ __global__ void __launch_bounds__(128) k_trace(DeviceScene S, const float4 *__re
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Persistent speculative traversal with per-lane refill (incoherent queues: bounces >= 1 and shadow rays).
+//
+// The batch-of-32 kernel above runs a warp until its slowest ray is done. On the 10 M-triangle mesh the secondary rays
+// need 26 node visits on average but 80 at the 99th percentile, and a ray that has just been fetched needs ~23 visits to
+// its first leaf while its neighbours need 2-3 to their next one: ncu shows 4.7-7.7 of 32 lanes per instruction there
+// (profiles/r01: prof_trace_mesh). tools/bvhsim replays the same traversal on the host under different warp schedules
+// (profiles/r02_bvhsim.txt): lock-step batches issue 93.7 node steps per ray slot on the diffuse-bounce set, refill +
+// speculation 56.6. Hence:
+//   * a lane that finishes its ray fetches the next one from the queue cursor as soon as fewer than kRefillBelow lanes are
+//     busy (one atomic per refill of the warp);
+//   * speculative descent: a lane that reaches a leaf postpones it and keeps descending (its interval is not shortened
+//     yet, which is conservative) until every lane of the warp holds a leaf -- then all leaves are tested together.
+// Results are identical to traceRay(): the same node / primitive tests, and a closest hit does not depend on visit order
+// (ties: the lowest t wins, equal t keeps the first found -- the reference has no rule either, skdtree.cpp:112-142).
+// ------------------------------------------------------------------------------------------
+static constexpr int kRefillBelow = 24;
+
+template <bool kAnyHit, bool kCount, typename Queue>
+PG_DEV void traceQueueSpeculative(const DeviceScene &S, Queue Q, uint32_t n, uint32_t *work, uint32_t &cntNodes, uint32_t &cntPrims,
+                                  unsigned long long &cntRays) {
+    constexpr unsigned kFull = 0xffffffffu;
+    int stack[kTraceStack];
+    int sp = 0, node = kDoneNode, leaf = 0;
+    uint32_t rayIdx = 0xFFFFFFFFu;
+    float3 o = f3(0.0f), d = f3(0.0f), idir = f3(0.0f);
+    float mint = 0.0f, tmax = 0.0f;
+    Hit hit;
+    hit.prim = kMiss;
+    hit.t = hit.u = hit.v = 0.0f;
+    bool exhausted = false;  // warp-uniform: the queue cursor has passed the end
+    while (true) {
+        // ---- refill: lanes without a ray take consecutive queue entries
+        unsigned idle = __ballot_sync(kFull, rayIdx == 0xFFFFFFFFu);
+        while (!exhausted && __popc(idle) > 32 - kRefillBelow) {
+            const uint32_t cnt = (uint32_t)__popc(idle);
+            uint32_t base = 0;
+            if (laneId() == 0) base = atomicAdd(work, cnt);
+            base = __shfl_sync(kFull, base, 0);
+            if (base + cnt >= n) exhausted = true;
+            if (rayIdx == 0xFFFFFFFFu) {
+                const uint32_t i = base + (uint32_t)__popc(idle & ((1u << laneId()) - 1u));
+                if (i < n && Q.fetch(i, o, d, mint, tmax)) {
+                    rayIdx = i;
+                    idir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                    node = 0;
+                    sp = 0;
+                    leaf = 0;
+                    hit.prim = kMiss;
+                    hit.t = tmax;
+                    hit.u = hit.v = 0.0f;
+                    cntRays++;
+                }
+            }
+            idle = __ballot_sync(kFull, rayIdx == 0xFFFFFFFFu);
+        }
+        if (idle == kFull) break;
+        // ---- speculative descent: until every lane with a ray holds a leaf (or has nothing left to visit)
+        while (__any_sync(kFull, node >= 0 && leaf == 0)) {
+            if (node >= 0) {
+                if (kCount) cntNodes++;
+                node = bvhNodeStep(S, node, o, idir, mint, tmax, stack, sp);
+                if (node < 0 && node != kDoneNode && leaf == 0) {  // first leaf: postpone it, continue with the next subtree
+                    leaf = node;
+                    node = sp ? stack[--sp] : kDoneNode;
+                }
+            }
+        }
+        // ---- leaves: the postponed one, then any leaf the lane is standing on
+        while (leaf != 0) {
+            const bool found = bvhLeafStep<kAnyHit, kCount>(S, leaf, o, d, mint, tmax, hit, &cntPrims);
+            leaf = 0;
+            if (kAnyHit && found) {
+                node = kDoneNode;
+            } else if (node < 0 && node != kDoneNode) {
+                leaf = node;
+                node = sp ? stack[--sp] : kDoneNode;
+            }
+        }
+        // ---- finished rays hand in their result and become idle
+        if (rayIdx != 0xFFFFFFFFu && node == kDoneNode) {
+            Q.finish(rayIdx, hit);
+            rayIdx = 0xFFFFFFFFu;
+        }
+    }
+}
+
+struct ClosestQueue {  // the wavefront's ray queue (path state) -> hit records
+    const float4 *rayO, *rayD;
+    const uint32_t *flags;
+    float4 *hits;
+    PG_DEV bool fetch(uint32_t i, float3 &o, float3 &d, float &mint, float &tmax) const {
+        if (flags[i] & (kFlagDead | kFlagNoTrace)) {
+            hits[i] = make_float4(kInf, 0.0f, 0.0f, __uint_as_float(kMiss));
+            return false;
+        }
+        const float4 ro = rayO[i], rd = rayD[i];
+        o = f3(ro.x, ro.y, ro.z);
+        d = f3(rd.x, rd.y, rd.z);
+        mint = adaptiveMinT(o, ro.w, false);
+        tmax = rd.w;
+        return true;
+    }
+    PG_DEV void finish(uint32_t i, const Hit &h) const {
+        hits[i] = h.prim == kMiss ? make_float4(kInf, 0.0f, 0.0f, __uint_as_float(kMiss))
+                                  : make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+    }
+};
+struct ShadowRayQueue {  // shadow queue -> adds the contribution of unoccluded rays to the path record
+    ShadowQueue Q;
+    float4 *rad;
+    PG_DEV bool fetch(uint32_t i, float3 &o, float3 &d, float &mint, float &tmax) const {
+        const float4 ro = Q.o[i], rd = Q.d[i];
+        o = f3(ro.x, ro.y, ro.z);
+        d = f3(rd.x, rd.y, rd.z);
+        mint = adaptiveMinT(o, ro.w, true);
+        tmax = rd.w;
+        if (!(tmax > mint)) {  // empty interval: unoccluded (as k_shadow)
+            Hit none;
+            none.prim = kMiss;
+            finish(i, none);
+            return false;
+        }
+        return true;
+    }
+    PG_DEV void finish(uint32_t i, const Hit &h) const {
+        if (h.prim != kMiss) return;
+        const float4 c = Q.c[i];
+        const uint32_t dst = __float_as_uint(c.w);
+        float4 r = rad[dst];  // exactly one shadow ray per path and bounce: no race
+        r.x += c.x;
+        r.y += c.y;
+        r.z += c.z;
+        rad[dst] = r;
+    }
+};
+
+struct RayListQueue {  // stand-alone ray queries (b200pg_k_trace*): rays as {o, mint}{d, maxt}, hits with global primitive ids
+    const float4 *rays;
+    float4 *hits;
+    const uint32_t *primGlobalId;
+    bool shadow;
+    PG_DEV bool fetch(uint32_t i, float3 &o, float3 &d, float &mint, float &tmax) const {
+        const float4 ro = rays[2 * i], rd = rays[2 * i + 1];
+        o = f3(ro.x, ro.y, ro.z);
+        d = f3(rd.x, rd.y, rd.z);
+        mint = adaptiveMinT(o, ro.w, shadow);
+        tmax = rd.w;
+        if (!(tmax > mint)) {
+            hits[i] = make_float4(kInf, 0.0f, 0.0f, __uint_as_float(kMiss));
+            return false;
+        }
+        return true;
+    }
+    PG_DEV void finish(uint32_t i, const Hit &h) const {
+        // any-hit mode reports the primitive only (as k_trace_rays: t, u, v of an occluder are whatever was found first)
+        hits[i] = h.prim == kMiss ? make_float4(kInf, 0.0f, 0.0f, __uint_as_float(kMiss))
+                                  : make_float4(h.t, h.u, h.v, __uint_as_float(primGlobalId[h.prim]));
+    }
+};
+template <bool kShadow, bool kCount>
+__global__ void __launch_bounds__(128) k_trace_rays_spec(DeviceScene S, RayListQueue Q, uint32_t n, uint32_t *work, Counters *C) {
+    unsigned long long rays = 0;
+    uint32_t cn = 0, cp = 0;
+    traceQueueSpeculative<kShadow, kCount>(S, Q, n, work, cn, cp, rays);
+    if (kCount) {
+        warpAddU64(&C->nodesVisited, cn);
+        warpAddU64(&C->primsTested, cp);
+    }
+}
+template <bool kCount>
+__global__ void __launch_bounds__(128) k_trace_spec(DeviceScene S, ClosestQueue Q, const uint32_t *nPtr, uint32_t *work, Counters *C) {
+    unsigned long long rays = 0;
+    uint32_t cn = 0, cp = 0;
+    traceQueueSpeculative<false, kCount>(S, Q, *nPtr, work, cn, cp, rays);
+    warpAddU64(&C->normalRays, rays);
+    if (kCount) {
+        warpAddU64(&C->nodesVisited, cn);
+        warpAddU64(&C->primsTested, cp);
+    }
+}
+template <bool kCount>
+__global__ void __launch_bounds__(128) k_shadow_spec(DeviceScene S, ShadowRayQueue Q, const uint32_t *nPtr, uint32_t *work, Counters *C) {
+    unsigned long long rays = 0;
+    uint32_t cn = 0, cp = 0;
+    const uint32_t n = *nPtr;
+    traceQueueSpeculative<true, kCount>(S, Q, n, work, cn, cp, rays);
+    // every queued shadow ray counts (the batch kernel counts empty intervals as well)
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&C->shadowRays, (unsigned long long)n);
+    if (kCount) {
+        warpAddU64(&C->nodesVisited, cn);
+        warpAddU64(&C->primsTested, cp);
+    }
+}
+
 // Coherence sort, step 2: exclusive scan of the 1 + cells bin counters (single block; the counters are re-zeroed for the
 // next bounce) and step 3: permutation.
 __global__ void __launch_bounds__(1024) k_bin_scan(SortArgs Q) {
@@ -675,9 +870,10 @@ void launchGenerate(const DeviceScene &S, const BatchDesc &B, const PathState &P
     k_generate<<<grid, 256, 0, st>>>(S, B, P, C);
 }
 void launchTrace(const DeviceScene &S, const PathState &P, float4 *hits, const uint32_t *nPtr, uint32_t *work, Counters *C,
-                 bool count, const SortArgs *sort, cudaStream_t st) {
+                 bool count, const SortArgs *sort, bool speculative, cudaStream_t st) {
     static int grid = persistentGrid(k_trace<false, false>, 128);
     static int gridKey = persistentGrid(k_trace<false, true>, 128);
+    static int gridSpec = persistentGrid(k_trace_spec<false>, 128);
     const SortArgs none = {};
     if (sort) {
         if (count)
@@ -686,15 +882,28 @@ void launchTrace(const DeviceScene &S, const PathState &P, float4 *hits, const u
             k_trace<false, true><<<gridKey, 128, 0, st>>>(S, P.rayO, P.rayD, P.flags, hits, nPtr, work, C, *sort);
         k_bin_scan<<<1, 1024, 0, st>>>(*sort);
         k_bin_scatter<<<numSMs() * 4, 256, 0, st>>>(*sort, nPtr);
+    } else if (speculative) {
+        const ClosestQueue Q = {P.rayO, P.rayD, P.flags, hits};
+        if (count)
+            k_trace_spec<true><<<gridSpec, 128, 0, st>>>(S, Q, nPtr, work, C);
+        else
+            k_trace_spec<false><<<gridSpec, 128, 0, st>>>(S, Q, nPtr, work, C);
     } else if (count)
         k_trace<true, false><<<grid, 128, 0, st>>>(S, P.rayO, P.rayD, P.flags, hits, nPtr, work, C, none);
     else
         k_trace<false, false><<<grid, 128, 0, st>>>(S, P.rayO, P.rayD, P.flags, hits, nPtr, work, C, none);
 }
 void launchShadow(const DeviceScene &S, const ShadowQueue &Q, float4 *rad, const uint32_t *nPtr, uint32_t *work, Counters *C,
-                  bool count, cudaStream_t st) {
+                  bool count, bool speculative, cudaStream_t st) {
     static int grid = persistentGrid(k_shadow<false>, 128);
-    if (count)
+    static int gridSpec = persistentGrid(k_shadow_spec<false>, 128);
+    if (speculative) {
+        const ShadowRayQueue R = {Q, rad};
+        if (count)
+            k_shadow_spec<true><<<gridSpec, 128, 0, st>>>(S, R, nPtr, work, C);
+        else
+            k_shadow_spec<false><<<gridSpec, 128, 0, st>>>(S, R, nPtr, work, C);
+    } else if (count)
         k_shadow<true><<<grid, 128, 0, st>>>(S, Q, rad, nPtr, work, C);
     else
         k_shadow<false><<<grid, 128, 0, st>>>(S, Q, rad, nPtr, work, C);
@@ -724,9 +933,19 @@ void launchFlush(const ShadeArgs &A, cudaStream_t st) {
     k_flush<<<grid, 256, 0, st>>>(A);
 }
 void launchTraceRays(const DeviceScene &S, const float4 *rays, uint32_t n, float4 *hits, uint32_t *work, Counters *C, bool shadow,
-                     bool count, cudaStream_t st) {
+                     bool count, bool speculative, cudaStream_t st) {
     static int grid = persistentGrid(k_trace_rays<false, false>, 128);
-    if (shadow) {
+    static int gridSpec = persistentGrid(k_trace_rays_spec<false, false>, 128);
+    if (speculative) {
+        const RayListQueue Q = {rays, hits, S.primGlobalId, shadow};
+        if (shadow) {
+            if (count) k_trace_rays_spec<true, true><<<gridSpec, 128, 0, st>>>(S, Q, n, work, C);
+            else k_trace_rays_spec<true, false><<<gridSpec, 128, 0, st>>>(S, Q, n, work, C);
+        } else {
+            if (count) k_trace_rays_spec<false, true><<<gridSpec, 128, 0, st>>>(S, Q, n, work, C);
+            else k_trace_rays_spec<false, false><<<gridSpec, 128, 0, st>>>(S, Q, n, work, C);
+        }
+    } else if (shadow) {
         if (count) k_trace_rays<true, true><<<grid, 128, 0, st>>>(S, rays, n, hits, work, C);
         else k_trace_rays<true, false><<<grid, 128, 0, st>>>(S, rays, n, hits, work, C);
     } else {

@@ -33,7 +33,18 @@ struct PrimRecord {
     float q[12];
 };
 
-struct PrimInfo {  // read by the shade stage only
+// Shading record of a primitive, 96 B = 6 x float4 = three whole 32-byte sectors, in BVH leaf order (indexed by the hit's
+// primitive slot). Everything fillIntersection needs about a triangle sits in ONE place: the previous chain
+// PrimInfo -> ShapeRecord -> MeshRecord -> indices -> positions / normals was five dependent, scattered loads deep and
+// touched ~9 sectors per hit on the 10 M-triangle mesh.
+//   r0 = p0.xyz, shape index       r1 = p1.xyz, flags (bit 0: triangle, bit 1: has vertex normals)
+//   r2 = p2.xyz, primitive index   r3 = n0.xyz, bsdf index   r4 = n1.xyz, emitter index   r5 = n2.xyz, 0
+// Rectangles keep only the .w words (their frame lives in RectRecord).
+struct ShadeTri {
+    float q[24];
+};
+
+struct PrimInfo {  // (shape, primitive) of a BVH slot: medium-boundary logic of the volumetric path
     uint32_t shape, prim;  // prim == kNoTriangle for rectangles
 };
 

@@ -1,0 +1,123 @@
+"""Config C4 at test size: the procedural heightfield mesh (vertex normals, roughconductor / roughplastic quadrants, two area
+lights) with n = 317 -> 199 712 triangles, CUDA path against the oracle.
+
+  * hit records on camera rays, bounce rays and shadow rays for BOTH traversal kernels (batches of 32 and the persistent
+    speculative kernel with per-lane refill): identical primitive, t within 2e-6, (u, v) within 2e-5;
+  * a chord set in the pattern of the reference's own kd-tree test/benchmark (src/tests/test_kd.cpp:86-133: uniformly
+    random chords through the bounding sphere of a mesh, closest- and any-hit), checked against the oracle's kd-tree;
+  * per-sample radiance through the mesh materials, sample by sample;
+  * ray / path counters of a whole progression against the oracle's render of the same samples.
+The 10 M-triangle scene itself (BASELINE config 3) runs in bench.py's `workloads` block and tests/test_gpu_fullsize.py.
+"""
+import numpy as np
+import pytest
+
+from test_gpu_parity import _check_hits, _secondary_rays
+
+pytestmark = pytest.mark.gpu
+
+N_MESH = 317
+
+
+@pytest.fixture(scope="module")
+def api(pkg):
+    from b200pg import api as _api
+
+    return _api
+
+
+@pytest.fixture(scope="module")
+def mesh(pkg, api, oracle):
+    sb = pkg.scenes.mesh_scene(256, 256, n=N_MESH)
+    p = api.default_params()
+    p.max_depth = 8
+    return sb, oracle.scene(sb), api.Integrator(api.Scene.from_builder(sb), p), p
+
+
+def _sphere_chords(rng, n, center, radius):
+    """test_kd.cpp:100-112: two uniform points on the bounding sphere, ray through both."""
+    def on_sphere(k):
+        v = rng.randn(k, 3)
+        return center + radius * v / np.linalg.norm(v, axis=1, keepdims=True)
+    a, b = on_sphere(n), on_sphere(n)
+    d = b - a
+    length = np.linalg.norm(d, axis=1, keepdims=True)
+    d /= length
+    return np.concatenate([a, np.zeros((n, 1)), d, length], 1).astype(np.float32)
+
+
+@pytest.mark.parametrize("spec", [0, 3])
+def test_mesh_hits_both_traversal_kernels(mesh, spec):
+    sb, osc, it, _ = mesh
+    it.set_option("trace_spec", spec)
+    try:
+        rng = np.random.RandomState(11)
+        pos = (rng.rand(200000, 2) * [sb.width, sb.height]).astype(np.float32)
+        rays = osc.camera_rays(pos)
+        tuv_o, prim_o, _ = osc.trace(rays)
+        tuv_g, prim_g = it.k_trace(rays)
+        assert (prim_o != 0xFFFFFFFF).mean() > 0.3
+        # a ray through a shared edge / vertex of two triangles may pick either neighbour: 1 in 10^4
+        _check_hits(tuv_o, prim_o, tuv_g, prim_g, max_mismatch=int(1e-4 * len(prim_o)))
+        r2 = _secondary_rays(rays, tuv_o, prim_o, rng, osc)
+        tuv_o2, prim_o2, _ = osc.trace(r2)
+        tuv_g2, prim_g2 = it.k_trace(r2)
+        _check_hits(tuv_o2, prim_o2, tuv_g2, prim_g2, max_mismatch=int(3e-4 * len(prim_o2)))
+        r3 = r2.copy()
+        r3[:, 7] = rng.rand(r3.shape[0]).astype(np.float32) * 2.0
+        _, occ_o, _ = osc.trace(r3, shadow=True)
+        _, occ_g = it.k_trace(r3, shadow=True)
+        assert ((occ_o != 0xFFFFFFFF) != (occ_g != 0xFFFFFFFF)).sum() <= int(3e-4 * len(occ_o))
+    finally:
+        it.set_option("trace_spec", 3)
+
+
+@pytest.mark.parametrize("spec", [0, 3])
+def test_mesh_chord_set_like_test_kd(mesh, spec):
+    sb, osc, it, _ = mesh
+    it.set_option("trace_spec", spec)
+    try:
+        rng = np.random.RandomState(5)
+        chords = _sphere_chords(rng, 300000, np.array([0.0, 0.0, 0.0]), 1.5)
+        tuv_o, prim_o, _ = osc.trace(chords)
+        tuv_g, prim_g = it.k_trace(chords)
+        assert 0.05 < (prim_o != 0xFFFFFFFF).mean() < 0.95
+        _check_hits(tuv_o, prim_o, tuv_g, prim_g, max_mismatch=int(1e-4 * len(prim_o)))
+        _, occ_o, _ = osc.trace(chords, shadow=True)
+        _, occ_g = it.k_trace(chords, shadow=True)
+        assert ((occ_o != 0xFFFFFFFF) != (occ_g != 0xFFFFFFFF)).sum() <= int(1e-4 * len(occ_o))
+    finally:
+        it.set_option("trace_spec", 3)
+
+
+def test_mesh_radiance_sample_by_sample(mesh):
+    sb, osc, it, p = mesh
+    rng = np.random.RandomState(3)
+    pix = rng.randint(0, sb.width * sb.height, 60000).astype(np.uint32)
+    smp = rng.randint(0, 64, 60000).astype(np.uint32)
+    Lo = osc.radiance(p, pix, smp)
+    Lg = it.k_radiance(pix, smp)
+    err = np.abs(Lo - Lg).max(1) / (np.abs(Lo).max(1) + 1e-3)
+    assert (Lo.max(1) > 0).mean() > 0.2
+    # microfacet lobes at grazing angles amplify a 1-ulp difference in the half vector: 0.5 % of the samples
+    assert (err > 1e-3).mean() < 5e-3, "fraction of samples off by > 1e-3 relative: %g" % (err > 1e-3).mean()
+    assert abs(Lg.mean() - Lo.mean()) <= 2e-3 * Lo.mean()
+
+
+def test_mesh_progression_counters_and_image(mesh, api):
+    sb, osc, it, p = mesh
+    it.film_clear()
+    s0 = it.stats()
+    it.progression(0, 2)
+    s1 = it.stats()
+    film_o, st = osc.render(p, 0, 2)
+    from oracle_lib import develop
+
+    paths = s1["paths"] - s0["paths"]
+    assert paths == st["paths"] == sb.width * sb.height * 2
+    for key in ("normal_rays", "shadow_rays"):
+        g, o = s1[key] - s0[key], st[key]
+        assert abs(g - o) <= 2e-3 * o, (key, g, o)
+    img_g, img_o = it.develop(), develop(film_o)
+    num = np.abs(img_g - img_o).sum()
+    assert num / np.abs(img_o).sum() < 5e-3  # same samples on both sides: differences are flipped decisions only
