@@ -205,7 +205,18 @@ int b200pg_scene_integrator_params(void *scene, B200pgIntegratorParams *out);
 void b200pg_scene_destroy(void *scene);
 
 void *b200pg_integrator_create(void *scene, const B200pgIntegratorParams *params, int device);
-int b200pg_render(void *integ); /* blocking: all progressions on this handle's device */
+/* Integrator::render (integrator.h:86-95; ProgressiveMonteCarloIntegrator::render, progressiveintegrator.cpp:170-220): blocking,
+ * runs all progressions -- sample budget (renderSamples, :65-114) or time budget (renderTime, :117-168) -- with the guiding
+ * field trained during the first `training_progressions` passes.
+ *   device_count <= 1 or devices == NULL: on the integrator's own device.
+ *   device_count  > 1: on all listed devices inside this one call, as the reference registers every worker inside one
+ *     render() (mitsuba.cpp:278-327, progressiveintegrator.cpp:84-103). devices[0] must be the integrator's own device; the
+ *     library replicates scene and field on the other devices (one host thread each), device r renders sample block
+ *     g * device_count + r of global pass g, the per-cell EM statistics are summed over NVLink peer memory inside the M-step
+ *     kernel, and the workers' films are added into this integrator's film before the call returns. The sample count is
+ *     rounded up to a multiple of device_count * samples_per_progression. Peer access between the devices is required.
+ * Clears a previous b200pg_cancel. Returns 0, or < 0 with b200pg_last_error(). */
+int b200pg_render(void *integ, int device_count, const int *devices);
 int b200pg_cancel(void *integ); /* async-safe */
 
 /* Progression-granular control (what ProgressiveMonteCarloIntegrator::renderSamples does,

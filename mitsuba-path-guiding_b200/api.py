@@ -45,7 +45,8 @@ def lib():
     L.b200pg_scene_destroy.argtypes = [C.c_void_p]
     L.b200pg_integrator_create.restype = C.c_void_p
     L.b200pg_integrator_create.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), C.c_int]
-    for name in ("b200pg_render", "b200pg_cancel", "b200pg_film_clear", "b200pg_train_accumulate", "b200pg_train_end"):
+    L.b200pg_render.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    for name in ("b200pg_cancel", "b200pg_film_clear", "b200pg_train_accumulate", "b200pg_train_end"):
         getattr(L, name).argtypes = [C.c_void_p]
     L.b200pg_train_update.argtypes = [C.c_void_p, C.c_int]
     L.b200pg_train_begin.argtypes = [C.c_void_p, u32p, u32p]
@@ -179,8 +180,14 @@ class Integrator:
             pass
 
     # ---- rendering
-    def render(self):
-        _check(lib().b200pg_render(self.h))
+    def render(self, devices=None):
+        """Integrator::render. devices = list of CUDA device indices (first = this integrator's own) renders on all of them
+        inside the one call; None = this integrator's device."""
+        if devices:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            _check(lib().b200pg_render(self.h, len(devices), arr))
+        else:
+            _check(lib().b200pg_render(self.h, 0, None))
 
     def cancel(self):
         _check(lib().b200pg_cancel(self.h))

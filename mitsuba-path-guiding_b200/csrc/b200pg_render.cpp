@@ -100,7 +100,7 @@ static int renderSingle(const Options &o) {
     if (o.seconds >= 0) p.max_render_time = o.seconds;
     void *integ = b200pg_integrator_create(scene, &p, o.device);
     if (!integ) { std::fprintf(stderr, "Error: %s\n", b200pg_last_error()); return 2; }
-    if (b200pg_render(integ) != 0) { std::fprintf(stderr, "Error: %s\n", b200pg_last_error()); return 3; }
+    if (b200pg_render(integ, 1, &o.device) != 0) { std::fprintf(stderr, "Error: %s\n", b200pg_last_error()); return 3; }
     const std::string out = outputName(o, scene);
     if (b200pg_film_write(integ, out.c_str()) != 0) { std::fprintf(stderr, "Error: %s\n", b200pg_last_error()); return 4; }
     B200pgStats st;

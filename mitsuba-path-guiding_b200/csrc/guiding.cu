@@ -660,7 +660,8 @@ struct CommView {
     size_t bufFloats;      // floats per statistics buffer
     int buf;               // which of the two buffers this iteration uses
     int twoPhase;
-    uint32_t *error;       // set when the wait timed out (a peer never arrived)
+    uint32_t *error;       // set when the wait timed out (a peer never arrived); sticky until the next connect
+    unsigned long long timeoutNs;  // wall-clock bound of one barrier wait
 };
 static constexpr int kExchangeThreads = 1024;  // one block per SM (all blocks must be resident while they wait)
 __device__ __forceinline__ uint32_t *commFlags(float *block, size_t bufFloats) {
@@ -694,8 +695,15 @@ __device__ __forceinline__ float4 sumSources(float *const *src, int n, size_t of
     return acc;
 }
 // Cross-GPU barrier: block 0 signals `epoch` in slot (base + flagSlot) of every peer's flag row, every block waits until
-// all `world` slots of the local row have reached it.
-__device__ __forceinline__ void commBarrier(const CommView &cv, int slotBase, bool signal) {
+// all `world` slots of the local row have reached it. The wait is bounded in WALL-CLOCK time (%globaltimer, nanoseconds,
+// cv.timeoutNs from the host -- not in SM cycles, whose rate varies); a rank whose peer never arrives raises cv.error.
+// Returns false (for the whole block) when the exchange has failed: the caller must then leave the field alone.
+__device__ __forceinline__ unsigned long long globalTimerNs() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ bool commBarrier(const CommView &cv, int slotBase, bool signal, int *sFail) {
     if (signal && (int)threadIdx.x < cv.world) {
         __threadfence_system();
         uint32_t *peerRow = commFlags(cv.peers[threadIdx.x], cv.bufFloats) + slotBase + cv.flagSlot;
@@ -703,26 +711,32 @@ __device__ __forceinline__ void commBarrier(const CommView &cv, int slotBase, bo
     }
     if ((int)threadIdx.x < cv.world) {
         const uint32_t *mine = commFlags(cv.peers[cv.rank], cv.bufFloats) + slotBase + threadIdx.x;
-        const long long t0 = clock64();
-        uint32_t v;
+        const unsigned long long t0 = globalTimerNs();
+        uint32_t v, spins = 0;
         do {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
             if ((int)(v - cv.epoch) >= 0) break;
-            if (clock64() - t0 > 20000000000LL) {  // ~10 s: a peer never arrived; fail loudly instead of hanging the GPU
+            if ((++spins & 1023u) == 0 && globalTimerNs() - t0 > cv.timeoutNs) {  // a peer never arrived: fail loudly, do not hang
                 atomicExch(cv.error, 1u);
                 break;
             }
         } while (true);
     }
     __syncthreads();
+    if (threadIdx.x == 0) *sFail = *reinterpret_cast<volatile uint32_t *>(cv.error) != 0u;
+    __syncthreads();
+    return *sFail == 0;
 }
 
 __global__ void __launch_bounds__(kExchangeThreads) k_mstep_allreduce(CommView cv, float4 *__restrict__ lobes,
                                                                        float4 *__restrict__ lobeStats, float *__restrict__ stats,
                                                                        uint32_t nCells, int K, int stride, int commit) {
     __shared__ float *sSrc[16];
-    __shared__ int sLast;
-    commBarrier(cv, 0, blockIdx.x == 0);
+    __shared__ int sLast, sFail;
+    // A failed exchange is sticky: once a wait has timed out (this iteration or an earlier one) no block sums, refits or
+    // pushes anything any more, so the field of the surviving ranks stays what it was; the host raises after the loop.
+    if (*reinterpret_cast<volatile uint32_t *>(cv.error) != 0u) return;
+    if (!commBarrier(cv, 0, blockIdx.x == 0, &sFail)) return;
 
     const uint32_t warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = (gridDim.x * blockDim.x) >> 5;
     const int k = (int)lane();
@@ -751,7 +765,7 @@ __global__ void __launch_bounds__(kExchangeThreads) k_mstep_allreduce(CommView c
             if (sLast) atomicExch(gridDone, 0u);
         }
         __syncthreads();
-        commBarrier(cv, 16, sLast != 0);
+        if (!commBarrier(cv, 16, sLast != 0, &sFail)) return;
         if (threadIdx.x == 0) sSrc[0] = cv.peers[cv.rank] + sumOfs;
         __syncthreads();
         nSrc = 1;
@@ -1171,6 +1185,7 @@ void GuidingHost::train(int nIter) {
             cv.buf = buf;
             cv.twoPhase = exchangeTwoPhase(numCells()) ? 1 : 0;
             cv.error = dCommError.p;
+            cv.timeoutNs = commTimeoutNs;
             k_mstep_allreduce<<<exchangeGrid(numCells()), kExchangeThreads, 0, stream>>>(cv, dLobes.p, dLobeStats.p, dStats.p, numCells(), K,
                                                                                        stride, commit ? 1 : 0);
             launches++;
@@ -1234,12 +1249,45 @@ void GuidingHost::commConnect(int rank, int world, const void *handles) {
     }
     commRank = rank;
     commWorld = world;
+    commIpc = true;
+    finishConnect();
+}
+
+// Shared tail of the two connect paths: a (re)connect starts from a clean slate -- error flag cleared, the intra-GPU grid
+// counter of the two-phase form zeroed (a failed exchange can leave it non-zero). The arrival flags are NOT cleared here:
+// a peer that connected first may already have signalled; epochs restart at 0 on every rank and the flags only ever
+// compare as "reached", so stale larger values from a previous session must be wiped by the owner BEFORE anyone connects
+// (commLocalHandle / commLocalBlock zero the block when it is created; reconnecting ranks call commResetFlags first).
+void GuidingHost::finishConnect() {
     commEpoch = 0;
     if (const char *e = std::getenv("B200PG_EXCHANGE_FORM")) commForceMode = std::atoi(e);  // tests: 0 all-read, 1 two-phase
-    dCommPeers.upload(commPeers, (size_t)world, stream);
+    if (const char *e = std::getenv("B200PG_COMM_TIMEOUT_S")) commTimeoutNs = (unsigned long long)(std::atof(e) * 1e9);
+    dCommPeers.upload(commPeers, (size_t)commWorld, stream);
     dCommError.alloc(1);
     CUDA_OK(cudaMemsetAsync(dCommError.p, 0, sizeof(uint32_t), stream));
+    CUDA_OK(cudaMemsetAsync(reinterpret_cast<uint32_t *>(commBlock + 3 * commFloats) + 48, 0, sizeof(uint32_t), stream));
     CUDA_OK(cudaStreamSynchronize(stream));
+}
+
+// In-process variant (b200pg_render with a device list: one worker thread per GPU inside one process, where CUDA IPC handles
+// cannot be opened): the ranks exchange plain device pointers; peer access between the devices must be enabled.
+float *GuidingHost::commLocalBlock() {
+    if (!commBlock) {
+        commFloats = kCommMaxCells * statsStride();
+        const size_t bytes = 3 * commFloats * sizeof(float) + 64 * sizeof(uint32_t);  // {buf0, buf1, sum, flags}
+        CUDA_OK(cudaMalloc(&commBlock, bytes));
+        CUDA_OK(cudaMemset(commBlock, 0, bytes));
+    }
+    return commBlock;
+}
+void GuidingHost::commConnectPointers(int rank, int world, float *const *blocks) {
+    if (world < 1 || world > 16 || rank < 0 || rank >= world) throw std::runtime_error("invalid rank / world size");
+    if (!commBlock || blocks[rank] != commBlock) throw std::runtime_error("commLocalBlock must be called first");
+    for (int r = 0; r < world; ++r) commPeers[r] = blocks[r];
+    commRank = rank;
+    commWorld = world;
+    commIpc = false;
+    finishConnect();
 }
 
 // ---- exchange microbenchmark ("EM-allreduce scaling, cells in {1 k, 8 k, 64 k} x K = 32") --------
@@ -1286,6 +1334,7 @@ float GuidingHost::exchangeBench(uint32_t cells, int nIter, bool localOnly) {
         cv.bufFloats = commFloats;
         cv.twoPhase = (!localOnly && exchangeTwoPhase(cells)) ? 1 : 0;
         cv.error = dCommError.p;
+        cv.timeoutNs = commTimeoutNs;
         k_mstep_allreduce<<<grid, kExchangeThreads, 0, stream>>>(cv, lobesT.p, statsT.p, sumT.p, cells, K, stride, 0);
         launches++;
     }
@@ -1302,9 +1351,20 @@ float GuidingHost::exchangeBench(uint32_t cells, int nIter, bool localOnly) {
     return ms / (float)nIter;
 }
 
+// back to a single rank; the exchange block stays allocated for the next connect
+void GuidingHost::commDisconnect() {
+    for (int r = 0; r < commWorld; ++r)
+        if (commIpc && r != commRank && commPeers[r]) cudaIpcCloseMemHandle(commPeers[r]);
+    for (auto &q : commPeers) q = nullptr;
+    commWorld = 1;
+    commRank = 0;
+    commEpoch = 0;
+    if (commBlock) cudaMemset(reinterpret_cast<uint32_t *>(commBlock + 3 * commFloats), 0, 64 * sizeof(uint32_t));  // arrival flags
+}
+
 void GuidingHost::commClose() {
     for (int r = 0; r < commWorld; ++r)
-        if (r != commRank && commPeers[r]) cudaIpcCloseMemHandle(commPeers[r]);
+        if (commIpc && r != commRank && commPeers[r]) cudaIpcCloseMemHandle(commPeers[r]);
     if (commBlock) cudaFree(commBlock);
     commBlock = nullptr;
     commWorld = 1;

@@ -116,7 +116,13 @@ struct GuidingHost {
     DevBuf<uint32_t> dCommError;
     void commLocalHandle(void *out64);
     void commConnect(int rank, int world, const void *handles);
+    float *commLocalBlock();
+    void commConnectPointers(int rank, int world, float *const *blocks);
+    void finishConnect();
+    bool commIpc = true;                   // peers were mapped through CUDA IPC (closed with cudaIpcCloseMemHandle)
+    unsigned long long commTimeoutNs = 10000000000ULL;  // bound of one cross-GPU barrier wait (B200PG_COMM_TIMEOUT_S)
     void commClose();
+    void commDisconnect();
     // microbenchmark of the exchange step alone: avg ms per k_mstep_allreduce over `cells` synthetic cells
     float exchangeBench(uint32_t cells, int nIter, bool localOnly);
     int commForceMode = -1;  // -1: choose by size; 0: all-read form; 1: reduce-scatter + all-gather form (microbenchmark)

@@ -11,6 +11,9 @@
 
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -123,6 +126,7 @@ struct Integrator {
     DevBuf<float4> dFeat;
 
     B200pgStats stats;
+    uint64_t peerPaths = 0, peerNormalRays = 0, peerShadowRays = 0, peerPathLen = 0;  // workers of multi-device renders
     cudaEvent_t ev[8];
     GuidingHost guide;
 
@@ -373,10 +377,10 @@ struct Integrator {
         Counters h;
         CUDA_OK(cudaMemcpyAsync(&h, dCounters.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
         CUDA_OK(cudaStreamSynchronize(stream));
-        stats.paths = h.paths;
-        stats.normal_rays = h.normalRays;
-        stats.shadow_rays = h.shadowRays;
-        stats.path_length_sum = h.pathLen;
+        stats.paths = h.paths + peerPaths;
+        stats.normal_rays = h.normalRays + peerNormalRays;
+        stats.shadow_rays = h.shadowRays + peerShadowRays;
+        stats.path_length_sum = h.pathLen + peerPathLen;
         stats.bvh_nodes_visited = h.nodesVisited;
         stats.prims_tested = h.primsTested;
         stats.train_samples = guide.samplesTrained;
@@ -568,43 +572,203 @@ int b200pg_progression_render(void *integ, int first_sample, int n_samples, int 
     PG_END
 }
 
-int b200pg_render(void *integ) {
+// ---- the progressive loop (ProgressiveMonteCarloIntegrator::renderSamples / renderTime, progressiveintegrator.cpp:65-168)
+// One pass = preprogression (what this pass records / samples from) -> progression -> postprogression (refit the field from
+// the pass' samples; the last training pass may discard the film). The SAME routine serves the sample budget, the time
+// budget and every worker of a multi-device render, so the estimator does not depend on how the job was launched.
+namespace pg {
+struct PassPlan {
+    int perPass, numPasses, trainPasses;
+    bool timed;
+    double limit;
+    int rank, world;
+};
+static PassPlan makePlan(const Integrator &I, int rank, int world) {
+    PassPlan P;
+    P.perPass = std::max(1, I.params.samples_per_progression);
+    const int passes = std::max(1, I.scene->sampleCount / P.perPass);
+    P.world = std::max(1, world);
+    P.rank = rank;
+    P.numPasses = (passes + P.world - 1) / P.world;  // global passes: `world` sample blocks each, one per device
+    P.timed = I.params.max_render_time > 0;
+    P.limit = (double)I.params.max_render_time;
+    // the sample budget trains at most as long as it renders; a time budget has no pass count to clamp against
+    P.trainPasses = I.guide.active ? std::max(0, I.params.training_progressions) : 0;
+    if (!P.timed) P.trainPasses = std::min(P.trainPasses, passes);
+    return P;
+}
+// global pass g of the plan on this integrator; `record` is the same on every rank (same number of training SAMPLES as a
+// single-device run)
+static void runPass(Integrator &I, const PassPlan &P, int g) {
+    const bool record = g * P.world < P.trainPasses;
+    I.guide.recording = I.guide.active && record;
+    I.guide.sampling = true;
+    I.renderProgression((g * P.world + P.rank) * P.perPass, P.perPass, 0, 0);
+    if (I.guide.recording && !I.cancel.load()) {
+        cudaEvent_t t = I.spanBegin();
+        I.guide.trainLocal();  // with connected peers the statistics are summed over all devices inside the M-step kernel
+        I.spanEnd(Integrator::kTimeTrain, t);
+        CUDA_OK(cudaStreamSynchronize(I.stream));
+        I.drainSpans();
+        if (I.params.guide_train_discard_film && (g + 1) * P.world >= P.trainPasses)
+            CUDA_OK(cudaMemsetAsync(I.dFilm.p, 0, I.dFilm.n * sizeof(float4), I.stream));
+    }
+}
+
+// Host-side rendezvous of the device workers of one render call: rank 0 publishes a verdict (continue / stop) that everybody
+// obeys, so that all workers leave the loop -- and its in-kernel cross-GPU barriers -- together. A worker that fails aborts
+// the rendezvous and thereby the job.
+struct Rendezvous {
+    std::mutex m;
+    std::condition_variable cv;
+    int world, arrived = 0, generation = 0;
+    bool aborted = false, verdict = false;
+    std::string error;
+    explicit Rendezvous(int w) : world(w) {}
+    // returns false when the job was aborted; *stop receives rank 0's verdict
+    bool arrive(int rank, bool myStop, bool *stop) {
+        std::unique_lock<std::mutex> lk(m);
+        if (aborted) return false;
+        if (rank == 0) verdict = myStop;
+        const int gen = generation;
+        if (++arrived == world) {
+            arrived = 0;
+            ++generation;
+            cv.notify_all();
+        } else {
+            cv.wait(lk, [&] { return generation != gen || aborted; });
+            if (aborted && generation == gen) return false;
+        }
+        *stop = verdict;
+        return true;
+    }
+    void abort(const std::string &why) {
+        std::lock_guard<std::mutex> lk(m);
+        if (!aborted) error = why;
+        aborted = true;
+        cv.notify_all();
+    }
+};
+
+static void renderLoop(Integrator &I, const PassPlan &P, Rendezvous *rv, std::atomic<int> &cancel) {
+    CUDA_OK(cudaSetDevice(I.device));
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int g = 0; P.timed || g < P.numPasses; ++g) {
+        if (cancel.load()) I.cancel.store(1);
+        runPass(I, P, g);
+        bool stop = cancel.load() != 0;
+        if (P.timed) stop = stop || std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() >= P.limit;
+        if (rv && !rv->arrive(P.rank, stop, &stop)) return;
+        if (stop) break;
+    }
+    I.pullCounters();
+}
+}  // namespace pg
+
+int b200pg_render(void *integ, int device_count, const int *devices) {
     PG_TRY(integ)
-    // ProgressiveMonteCarloIntegrator::renderSamples (progressiveintegrator.cpp:65-114) /
-    // renderTime (:117-168)
-    const int spp = self->scene->sampleCount;
-    const int perPass = self->params.samples_per_progression;
-    const int numPasses = std::max(1, spp / perPass);
-    auto t0 = std::chrono::steady_clock::now();
-    if (self->params.max_render_time > 0) {
-        int pass = 0;
-        while (!self->cancel.load()) {
-            self->guide.recording = self->guide.active && pass < self->params.training_progressions;
-            self->guide.sampling = true;
-            self->renderProgression(pass * perPass, perPass, 0, 0);
-            if (self->guide.recording) self->guide.trainLocal();
-            ++pass;
-            double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-            if (el >= self->params.max_render_time) break;
+    self->cancel.store(0);  // a cancelled render does not poison the next one (Integrator::cancel is per render job, integrator.h:84-87)
+    if (device_count <= 1 || !devices) {
+        if (devices && device_count == 1 && devices[0] != self->device)
+            return fail("the integrator lives on device " + std::to_string(self->device) + ", not on the requested device");
+        if (self->guide.commWorld > 1)
+            return fail("peers are connected (b200pg_comm_connect): drive the progressions of every rank yourself, or render with a device list");
+        renderLoop(*self, makePlan(*self, 0, 1), nullptr, self->cancel);
+        return 0;
+    }
+    // ---- several devices inside this call (the reference registers all its workers inside one render(): mitsuba.cpp:278-327,
+    // progressiveintegrator.cpp:84-103). Device devices[0] must be the integrator's own; the scene and the field are replicated,
+    // device r renders sample block g * n + r of global pass g, the EM statistics are summed over NVLink peer memory inside
+    // the M-step kernel, and the films are added into this integrator's film at the end.
+    const int world = device_count;
+    if (world > 16) return fail("at most 16 devices");
+    if (devices[0] != self->device) return fail("devices[0] must be the device the integrator was created on");
+    int available = 0;
+    CUDA_OK(cudaGetDeviceCount(&available));
+    for (int r = 0; r < world; ++r) {
+        if (devices[r] < 0 || devices[r] >= available) return fail("invalid CUDA device index in the device list");
+        for (int q = 0; q < r; ++q)
+            if (devices[q] == devices[r]) return fail("a device is listed twice");
+    }
+    if (self->guide.commWorld > 1) return fail("peers are already connected (b200pg_comm_connect)");
+    std::vector<std::unique_ptr<Integrator>> workers;  // ranks 1..world-1
+    std::vector<Integrator *> ranks((size_t)world, nullptr);
+    ranks[0] = self;
+    for (int r = 1; r < world; ++r) {
+        std::unique_ptr<Integrator> W(new Integrator());
+        W->scene = self->scene;
+        W->params = self->params;
+        W->device = devices[r];
+        W->traceSpec = self->traceSpec;
+        W->sortBounces = self->sortBounces;
+        W->timing = self->timing;
+        W->init();
+        if (self->guide.active) {  // a field trained by earlier calls stays the common start
+            CUDA_OK(cudaSetDevice(self->device));
+            const std::vector<uint32_t> words = self->guide.snapshot();
+            CUDA_OK(cudaSetDevice(W->device));
+            if (!W->guide.load(words.data(), words.size())) return fail("cannot replicate the guiding field");
         }
-    } else {
-        const int trainPasses = self->guide.active ? std::min(self->params.training_progressions, numPasses) : 0;
-        for (int pass = 0; pass < numPasses && !self->cancel.load(); ++pass) {
-            // preprogression: choose what this pass records / samples
-            self->guide.recording = pass < trainPasses;
-            self->guide.sampling = true;
-            self->renderProgression(pass * perPass, perPass, 0, 0);
-            // postprogression: refit the field from this pass' samples
-            if (pass < trainPasses) {
-                cudaEvent_t t = self->spanBegin();
-                self->guide.trainLocal();
-                self->spanEnd(Integrator::kTimeTrain, t);
-                CUDA_OK(cudaStreamSynchronize(self->stream));
-                self->drainSpans();
-                if (self->params.guide_train_discard_film && pass == trainPasses - 1)
-                    CUDA_OK(cudaMemsetAsync(self->dFilm.p, 0, self->dFilm.n * sizeof(float4), self->stream));
+        ranks[(size_t)r] = W.get();
+        workers.push_back(std::move(W));
+    }
+    for (int r = 0; r < world; ++r) {  // peer access in both directions (exchange blocks, films)
+        CUDA_OK(cudaSetDevice(devices[r]));
+        for (int q = 0; q < world; ++q) {
+            if (q == r) continue;
+            int can = 0;
+            CUDA_OK(cudaDeviceCanAccessPeer(&can, devices[r], devices[q]));
+            if (!can) return fail("devices " + std::to_string(devices[r]) + " and " + std::to_string(devices[q]) + " cannot access each other's memory");
+            cudaError_t e = cudaDeviceEnablePeerAccess(devices[q], 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else CUDA_OK(e);
+        }
+    }
+    if (self->guide.active) {
+        std::vector<float *> blocks((size_t)world, nullptr);
+        for (int r = 0; r < world; ++r) {
+            CUDA_OK(cudaSetDevice(devices[r]));
+            blocks[(size_t)r] = ranks[(size_t)r]->guide.commLocalBlock();
+        }
+        for (int r = 0; r < world; ++r) {
+            CUDA_OK(cudaSetDevice(devices[r]));
+            ranks[(size_t)r]->guide.commConnectPointers(r, world, blocks.data());
+        }
+    }
+    Rendezvous rv(world);
+    std::vector<std::thread> threads;
+    for (int r = 1; r < world; ++r)
+        threads.emplace_back([&, r] {
+            try {
+                renderLoop(*ranks[(size_t)r], makePlan(*ranks[(size_t)r], r, world), &rv, self->cancel);
+            } catch (const std::exception &e) {
+                rv.abort(std::string("device ") + std::to_string(devices[r]) + ": " + e.what());
             }
+        });
+    try {
+        renderLoop(*self, makePlan(*self, 0, world), &rv, self->cancel);
+    } catch (const std::exception &e) {
+        rv.abort(std::string("device ") + std::to_string(devices[0]) + ": " + e.what());
+    }
+    for (auto &t : threads) t.join();
+    CUDA_OK(cudaSetDevice(self->device));
+    if (self->guide.active) {  // back to a single-device integrator; the (identical) field of rank 0 is the result
+        for (int r = 0; r < world; ++r) {
+            cudaSetDevice(devices[r]);
+            ranks[(size_t)r]->guide.commDisconnect();
         }
+        CUDA_OK(cudaSetDevice(self->device));
+    }
+    if (rv.aborted) return fail("multi-device render failed: " + rv.error);
+    for (int r = 1; r < world; ++r) {  // film += the peers' films over NVLink, statistics summed
+        Integrator &W = *ranks[(size_t)r];
+        launchFilmAdd(self->dFilm.p, W.dFilm.p, (uint32_t)self->dFilm.n, self->stream);
+        CUDA_OK(cudaStreamSynchronize(self->stream));
+        self->stats.kernel_launches += 1 + W.stats.kernel_launches + W.guide.launches;
+        self->peerPaths += W.stats.paths;
+        self->peerNormalRays += W.stats.normal_rays;
+        self->peerShadowRays += W.stats.shadow_rays;
+        self->peerPathLen += W.stats.path_length_sum;
     }
     self->pullCounters();
     PG_END
