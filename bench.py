@@ -30,6 +30,9 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+DEFAULT_LANES = 2  # concurrent wavefront sub-batches per progression (the library's default)
+
+
 def workload(name):
     import __graft_entry__ as ge
 
@@ -176,8 +179,13 @@ def run_reference(args):
         "impl": "reference", "metric": "paths_per_sec", "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "spp_per_step": spp, "rows": rows, "pretrain_iterations": args.pretrain if guided else 0,
-                   "guiding": ("training iteration per step: K=16 vMF lobes/cell, %d EM iterations" % args.em_iters) if guided else "off"},
+        # same keys as the GPU arm's config (the driver compares them); every step renders rows 0..`rows` of the image (see
+        # cpu_baseline.sample), the throughput figure does not depend on the band height
+        "config": {"workload": desc, "spp_per_step": spp, "paths_per_step_per_gpu": sb.width * sb.height * spp,
+                   "pretrain_iterations": args.pretrain if guided else 0,
+                   "l2": "n/a (host CPU); each step is a bounded band of %d rows of the image" % rows,
+                   "guiding": ("training iteration per step: K=16 vMF lobes/cell, %d EM iterations" % args.em_iters) if guided else "off",
+                   "parallelism": "%d host threads, 32x32 tiles (imageproc.cpp:27-78)" % cores},
         "mrays_per_sec": rays / t / 1e6,
         "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": cores, "kind": "port", "sample": sample,
                          "kd_traversal_per_ray": cpu.kd_bytes_per_ray()},
@@ -186,14 +194,14 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def main():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="cornell_caustic_1024")
-    ap.add_argument("--spp-per-step", type=int, default=4)
+    ap.add_argument("--spp-per-step", type=int, default=0, help="0 = the workload's default (4; 1 for the 2048^2 mesh)")
     ap.add_argument("--em-iters", type=int, default=4)
     ap.add_argument("--pretrain", type=int, default=12, help="untimed training iterations before warm-up (steady-state field)")
     ap.add_argument("--no-guiding", action="store_true")
@@ -201,28 +209,78 @@ def main():
     ap.add_argument("--nccl-allreduce", action="store_true", help="sum EM statistics with torch.distributed/NCCL instead of the fused peer-memory kernel")
     ap.add_argument("--max-cell-samples", type=int, default=32768, help="spatial split threshold of the guiding field (experiments: a smaller value grows the larger field of a multi-GPU job on one GPU)")
     ap.add_argument("--sort-bounces", type=int, default=-1, help="coherence sort of the shade queue by guiding cell on bounces 1..n (0 = off, -1 = library default)")
+    ap.add_argument("--lanes", type=int, default=-1, help="concurrent wavefront sub-batches per progression (-1 = library default)")
     ap.add_argument("--ref-seconds", type=float, default=3.0)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU leg (profiling runs)")
-    args = ap.parse_args()
+    ap.add_argument("--no-workloads", action="store_true", help="skip the short C3 / C4 runs of the `workloads` block")
+    ap.add_argument("--workloads", default="medium_1024,mesh_10m", help="extra BASELINE configs measured (briefly) next to the headline, N = 1 only")
+    args = ap.parse_args(argv)
     args.warmup = max(args.warmup, 0)
+    if args.spp_per_step <= 0:
+        args.spp_per_step = 1 if args.workload == "mesh_10m" else 4
+    return args
 
-    if args.impl == "reference":
-        return run_reference(args)
 
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """torch.distributed plumbing shared by all measurements of one process."""
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        # NCCL_DEBUG=VERSION (set in some images) makes NCCL print its version banner to STDOUT, next to the one JSON line
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
 
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world > 1:
+            # NCCL_DEBUG=VERSION (set in some images) makes NCCL print its version banner to STDOUT, next to the one JSON line
+            if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+                os.environ["NCCL_DEBUG"] = "WARN"
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        torch.cuda.set_device(self.local)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def gather_bytes(self, b):
+        """all-gather of a fixed-size byte string -> list over ranks"""
+        torch, dist = self.torch, self.dist
+        mine = torch.frombuffer(bytearray(b), dtype=torch.uint8).cuda()
+        out = [torch.empty(len(b), dtype=torch.uint8, device="cuda") for _ in range(self.world)]
+        dist.all_gather(out, mine)
+        return [bytes(g.cpu().numpy().tobytes()) for g in out]
+
+
+def traffic_table():
+    try:  # per-launch DRAM bytes from the committed ncu --set full captures (profiles/)
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return {}
+
+
+def measure(ctx, args, headline):
+    """One workload: pre-train, warm up, time `steps` guided training iterations (value), the same through the C-ABI with host
+    buffers (e2e), a one-lane profiling pass for the per-kernel roofline figures, and (rank 0, N = 1) the CPU baseline."""
+    import hashlib
+
+    torch, dist, rank, world, local = ctx.torch, ctx.dist, ctx.rank, ctx.world, ctx.local
     pkg, sb, desc = workload(args.workload)
     from b200pg import api
 
@@ -232,8 +290,13 @@ def main():
     integ = api.Integrator(scene, p, device=local)
     if args.sort_bounces >= 0:
         integ.set_option("sort_bounces", args.sort_bounces)
+    lanes = args.lanes if args.lanes > 0 else int(os.environ.get("B200PG_LANES", DEFAULT_LANES))
+    overlap = 0 if os.environ.get("B200PG_OVERLAP_SHADOW") == "0" else 1
+    integ.set_option("lanes", lanes)
+    integ.set_option("overlap_shadow", overlap)
     spp = args.spp_per_step
     npix = sb.width * sb.height
+    barrier = ctx.barrier
 
     def wrap(ptr, n):
         class _W:
@@ -245,24 +308,21 @@ def main():
         dist.all_reduce(wrap(ptr, n), op=dist.ReduceOp.SUM)
         torch.cuda.synchronize()
 
-    # ---- multi-GPU plumbing: torch.distributed only carries the 64-byte CUDA IPC handles of the exchange blocks; the
-    # per-iteration sum of the EM statistics then happens inside the library's M-step kernel over NVLink peer memory
-    if world > 1 and guided and not args.nccl_allreduce:
-        mine = torch.frombuffer(bytearray(integ.comm_local_handle()), dtype=torch.uint8).cuda()
-        gathered = [torch.empty(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
-        dist.all_gather(gathered, mine)
-        integ.comm_connect(rank, world, b"".join(bytes(g.cpu().numpy().tobytes()) for g in gathered))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    # ---- multi-GPU plumbing: torch.distributed only carries the 64-byte CUDA IPC handles (exchange blocks, films); the
+    # per-iteration sum of the EM statistics then happens inside the library's M-step kernel over NVLink peer memory, and
+    # previews of the job's film are merged on rank 0's device
+    if world > 1:
+        if guided and not args.nccl_allreduce:
+            integ.comm_connect(rank, world, b"".join(ctx.gather_bytes(integ.comm_local_handle())))
+        film_handles = b"".join(ctx.gather_bytes(integ.film_ipc_handle()))
+        if rank == 0:
+            integ.film_peers_connect(rank, world, film_handles)
 
     # ---- sample batches are split per GPU: rank r renders sample indices r*spp.. of every step (weak scaling)
-    def step(k):
+    def step(k, rows=None):
         if guided:
             integ.guiding_mode(True, k > 0)
-        integ.progression((k * world + rank) * spp, spp)
+        integ.progression((k * world + rank) * spp, spp, rows=rows)
         if guided:
             if world > 1 and args.nccl_allreduce:  # comparison path: NCCL allreduce between separate E / M kernels
                 integ.train(args.em_iters, allreduce_stats)
@@ -284,10 +344,9 @@ def main():
     base += max(args.warmup, 3)
     barrier()
     s0 = integ.stats()
+    # ---- timed region: wall clock between two barrier + synchronize brackets (everything the step does on the host and
+    # the device); the CUDA-event time of the progressions + training updates is reported next to it as device_total
     t0s = integ.stage_times()
-    # device time of the timed region = seconds_total of the stream (CUDA-event drained) -> use CUDA events via torch on
-    # our own stream is not visible to torch; the library brackets every progression with stream syncs and reports
-    # per-stage CUDA-event times; the step time below is host wall-clock around fully synchronised progressions.
     barrier()
     t_start = time.perf_counter()
     for k in range(args.steps):
@@ -296,31 +355,63 @@ def main():
     wall = time.perf_counter() - t_start
     s1 = integ.stats()
     t1s = integ.stage_times()
-    # device time: CUDA events recorded on the launching stream around every progression (b200pg stats)
-    elapsed = (s1["seconds_total"] - s0["seconds_total"]) + (t1s["train"]["seconds"] - t0s["train"]["seconds"])
-    if world > 1:
-        tt = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        elapsed = float(tt.item())
+    device_total = ctx.max_over_ranks((s1["seconds_total"] - s0["seconds_total"]) + (t1s["train"]["seconds"] - t0s["train"]["seconds"]))
     paths = (s1["paths"] - s0["paths"]) * world
     rays = (s1["normal_rays"] - s0["normal_rays"] + s1["shadow_rays"] - s0["shadow_rays"]) * world
     launches = s1["kernel_launches"] - s0["kernel_launches"]
-    # the step time is the wall clock between two barrier + synchronize brackets (everything the step does on the host
-    # and the device); `elapsed` above (sum of the CUDA-event spans) is reported next to it as device_total
-    if world > 1:
-        tw = torch.tensor([wall], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-        wall = float(tw.item())
+    wall = ctx.max_over_ranks(wall)
     value = paths / wall / 1e6
+    base += args.steps
 
-    # ---- roofline of the dominant kernel (closest-hit traversal): algorithmic bytes from a counting pass
-    tr_sec = t1s["trace"]["seconds"] - t0s["trace"]["seconds"]
-    tr_n = t1s["trace"]["launches"] - t0s["trace"]["launches"]
-    sh_sec = t1s["shade"]["seconds"] - t0s["shade"]["seconds"]
-    sd_sec = t1s["shadow"]["seconds"] - t0s["shadow"]["seconds"]
+    # ---- multi-GPU correctness, visible to whoever reads the line: the replicated fields must be bit-identical after the
+    # timed updates, and the job's merged film must hold exactly the samples all ranks rendered
+    multi = None
+    if world > 1:
+        h = hashlib.sha1(np.ascontiguousarray(integ.field_snapshot()).tobytes()).digest()[:16] if guided else b"\0" * 16
+        hashes = ctx.gather_bytes(h)
+        barrier()
+        own = integ.film()  # (H, W, 5) of this rank
+        w_sum = ctx.sum_over_ranks(float(own[..., 4].astype(np.float64).sum()))
+        rgb_sum = ctx.sum_over_ranks(float(own[..., :3].astype(np.float64).sum()))
+        multi = {"field_identical_on_all_ranks": bool(all(x == hashes[0] for x in hashes)) if guided else None,
+                 "field_sha1_16": hashes[0].hex() if guided else None}
+        if rank == 0:
+            merged = np.empty_like(own)
+            pinned = torch.empty(own.shape, dtype=torch.float32, pin_memory=True).numpy()
+            integ.film_async(pinned)
+            integ.film_wait()
+            merged[:] = pinned
+            mw, mrgb = float(merged[..., 4].astype(np.float64).sum()), float(merged[..., :3].astype(np.float64).sum())
+            multi.update({"merged_film_weight_sum": mw, "sum_of_rank_weight_sums": w_sum,
+                          "merged_film_matches_rank_sum": bool(abs(mw - w_sum) <= 1e-5 * w_sum and abs(mrgb - rgb_sum) <= 1e-4 * abs(rgb_sum)),
+                          "samples_in_merged_film": mw, "camera_samples_rendered": float(integ.stats()["paths"]) * world,
+                          "note": "a sample's filter weights sum to 1 inside the image (less at the border): weight sum / samples "
+                                  "must sit just below 1"})
+            multi["weight_sum_over_samples"] = mw / max(multi["camera_samples_rendered"], 1.0)
+            assert multi["merged_film_matches_rank_sum"], "the merged film is not the sum of the ranks' films"
+            assert 0.97 <= multi["weight_sum_over_samples"] <= 1.0001, "merged film does not hold the samples the ranks rendered"
+        barrier()
+        assert multi["field_identical_on_all_ranks"] in (True, None), "replicated guiding fields diverged across ranks"
+
+    # ---- roofline of the dominant kernels: ONE-LANE profiling pass (no overlapping streams), same steps, so that every
+    # kernel's CUDA-event span is its own; algorithmic bytes from the step's counters
     roof = None
     e2e = None
     cpu = None
+    prof_steps = max(2, min(args.steps, 4))
+    integ.set_option("lanes", 1)
+    integ.set_option("overlap_shadow", 0)
+    barrier()
+    p0s, ps0 = integ.stage_times(), integ.stats()
+    for k in range(prof_steps):
+        step(base + k)
+    barrier()
+    p1s, ps1 = integ.stage_times(), integ.stats()
+    base += prof_steps
+    tr_sec = p1s["trace"]["seconds"] - p0s["trace"]["seconds"]
+    tr_n = p1s["trace"]["launches"] - p0s["trace"]["launches"]
+    sh_sec = p1s["shade"]["seconds"] - p0s["shade"]["seconds"]
+    sd_sec = p1s["shadow"]["seconds"] - p0s["shadow"]["seconds"]
     if rank == 0:
         integ.set_option("count_traversal", 1)
         if guided:
@@ -340,51 +431,61 @@ def main():
         # Shade stage: path-state streaming. Per queued path 92 B state + 16 B hit in, 92 B out per surviving path,
         # 52 B per shadow-queue entry, 20 B splat record per finished path; per recorded training vertex 64 B record +
         # 16 B close, and per emitted training sample 64 B read back + 36 B written (DESIGN.md "Data layout").
-        step_paths = (s1["paths"] - s0["paths"]) / args.steps
-        step_nrays = (s1["normal_rays"] - s0["normal_rays"]) / args.steps
-        step_srays = (s1["shadow_rays"] - s0["shadow_rays"]) / args.steps
-        step_train = (s1["train_samples"] - s0["train_samples"]) / args.steps if guided else 0.0
+        step_paths = (ps1["paths"] - ps0["paths"]) / prof_steps
+        step_nrays = (ps1["normal_rays"] - ps0["normal_rays"]) / prof_steps
+        step_srays = (ps1["shadow_rays"] - ps0["shadow_rays"]) / prof_steps
+        step_train = (ps1["train_samples"] - ps0["train_samples"]) / prof_steps if guided else 0.0
         shade_bytes = 108.0 * step_nrays + 92.0 * max(step_nrays - step_paths, 0.0) + 52.0 * step_srays + 20.0 * step_paths \
             + 180.0 * step_train
-        tn_sec = t1s["train"]["seconds"] - t0s["train"]["seconds"]
+        tn_sec = p1s["train"]["seconds"] - p0s["train"]["seconds"]
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        sh_n = t1s["shade"]["launches"] - t0s["shade"]["launches"]
-        traffic = None
-        try:  # per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture (profiles/)
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        except Exception:
-            pass
-        stage = {"trace": tr_sec, "shade": sh_sec, "shadow": sd_sec, "film": t1s["film"]["seconds"] - t0s["film"]["seconds"],
-                 "train": tn_sec, "device_total": elapsed, "host_wall": wall}
-        ach_shade = shade_bytes * args.steps / max(sh_sec, 1e-9) / 1e9
-        ach_trav = trav_bytes * args.steps / max(trace_all, 1e-9) / 1e9
-        # the kernel with the largest share of the step is the shade stage (profiles/: ncu launch list of this command)
+        sh_n = p1s["shade"]["launches"] - p0s["shade"]["launches"]
+        traffic = traffic_table().get(args.workload, {})
+        one_lane_total = (ps1["seconds_total"] - ps0["seconds_total"]) + tn_sec
+        stage = {"trace": tr_sec / prof_steps, "shade": sh_sec / prof_steps, "shadow": sd_sec / prof_steps,
+                 "film": (p1s["film"]["seconds"] - p0s["film"]["seconds"]) / prof_steps, "train": tn_sec / prof_steps,
+                 "one_lane_step": one_lane_total / prof_steps, "timed_step_device": device_total / args.steps,
+                 "timed_step_host_wall": wall / args.steps,
+                 "what": "seconds per step; the stage figures come from a %d-step pass with ONE lane and no stream overlap (each "
+                         "kernel's CUDA-event span is exclusive), the timed steps run the library default" % prof_steps}
+        ach_shade = shade_bytes * prof_steps / max(sh_sec, 1e-9) / 1e9
+        ach_trav = trav_bytes * prof_steps / max(trace_all, 1e-9) / 1e9
+        n_prims = sum(int(np.asarray(sh["T"]).shape[0]) if isinstance(sh, dict) and sh.get("T") is not None else 1 for sh in sb.shapes)
+        scene_bytes = n_prims * (48 + 96 + 32)  # primitive + shading records + ~half a 64-byte BVH node per primitive
+        scene_in_cache = scene_bytes < (32 << 20)
+        trav_traffic = traffic.get("trace_dram_bytes_per_step")
         roof = {"bound": "hbm", "achieved": ach_shade, "peak": peak, "unit": "GB/s", "frac": ach_shade / peak,
-                "traffic": (traffic or {}).get("k_shade_bytes_per_launch"),
+                "traffic": traffic.get("k_shade_bytes_per_launch"),
                 "kernel": "k_shade (intersection fill, NEE, BSDF / guided sampling, queue compaction, training records)",
-                "share_of_step": sh_sec / max(elapsed, 1e-9),
+                "share_of_step": sh_sec / max(one_lane_total, 1e-9),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                "algorithmic_bytes_per_launch": shade_bytes * args.steps / max(sh_n, 1),
+                "algorithmic_bytes_per_launch": shade_bytes * prof_steps / max(sh_n, 1),
                 "avg_launch_ms": 1e3 * sh_sec / max(sh_n, 1),
                 "stage_seconds": stage,
-                "traversal": {"kernel": "k_trace + k_shadow (BVH traversal)", "achieved": ach_trav, "frac": ach_trav / peak,
+                "traversal": {"kernel": "k_trace / k_trace_spec + k_shadow_spec (BVH traversal)", "achieved": ach_trav, "frac": ach_trav / peak,
                               "algorithmic_bytes_per_step": trav_bytes,
-                              "queue_only_gbs": (48.0 * nrays + 52.0 * srays) * args.steps / max(trace_all, 1e-9) / 1e9,
+                              "traffic": trav_traffic,
+                              "traffic_frac_of_peak": (trav_traffic / max(trace_all / prof_steps, 1e-9) / 1e9 / peak) if trav_traffic else None,
+                              "queue_only_gbs": (48.0 * nrays + 52.0 * srays) * prof_steps / max(trace_all, 1e-9) / 1e9,
                               "per_ray": {"nodes": nodes / max(nrays + srays, 1), "prims": prims / max(nrays + srays, 1)},
                               "avg_launch_ms": 1e3 * tr_sec / max(tr_n, 1),
-                              "note": "the BVH of this 40-primitive scene is L1-resident, so node/primitive bytes never reach HBM "
-                                      "and the algorithmic figure may exceed the HBM peak; queue_only_gbs counts the ray/hit "
-                                      "records that do stream through HBM"}}
+                              "note": ("the BVH of this small scene is L1-resident, so node / primitive bytes never reach HBM and the "
+                                       "algorithmic figure may exceed the HBM peak; queue_only_gbs counts the ray / hit records that do "
+                                       "stream through HBM") if scene_in_cache else
+                                      ("BVH nodes + primitive records exceed the 126 MB L2: `traffic` = ncu dram__bytes (read + write) of "
+                                       "the traversal kernels of one step (profiles/), `achieved` = algorithmic bytes / time")}}
+    integ.set_option("lanes", lanes)
+    integ.set_option("overlap_shadow", overlap)
 
     # ---- extra figure: rendering with the trained field, no recording and no training update (what a long guided render
     # does once the training progressions are over); same brackets as the main figure
     render_only = None
-    if guided:
+    if guided and headline:
         integ.guiding_mode(False, True)
         barrier()
         r0 = integ.stats()
@@ -392,67 +493,102 @@ def main():
         for k in range(args.steps):
             integ.progression((20_000_000 + k * world + rank) * spp, spp)
         barrier()
-        rdt = time.perf_counter() - tr0
-        if world > 1:
-            tt = torch.tensor([rdt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            rdt = float(tt.item())
+        rdt = ctx.max_over_ranks(time.perf_counter() - tr0)
         r1 = integ.stats()
         render_only = {"value": (r1["paths"] - r0["paths"]) * world / rdt / 1e6, "unit": "Mpaths/s", "ms_per_step": 1e3 * rdt / args.steps,
                        "what": "guided rendering with the trained field, no training"}
 
-    # ---- end-to-end through the C-ABI with host buffers: scene H2D + render + film D2H every step
+    # ---- strong scaling extra (N > 1): the SAME step as one GPU renders (spp samples per pixel over the whole image), its rows
+    # split into N bands, one per rank; training statistics still summed over the ranks
+    strong = None
+    if world > 1 and headline:
+        rows_per = (sb.height // world + 3) // 4 * 4
+        r_lo, r_hi = min(sb.height, rank * rows_per), min(sb.height, (rank + 1) * rows_per)
+        if rank == world - 1:
+            r_hi = sb.height
+
+        def strong_step(k):
+            if guided:
+                integ.guiding_mode(True, True)
+            if r_hi > r_lo:
+                integ.progression((30_000_000 + k) * spp, spp, rows=(r_lo, r_hi))
+            if guided:
+                integ.train_fused(args.em_iters)
+        for k in range(3):
+            strong_step(k)
+        barrier()
+        q0 = integ.stats()
+        ts0 = time.perf_counter()
+        for k in range(args.steps):
+            strong_step(3 + k)
+        barrier()
+        sdt = ctx.max_over_ranks(time.perf_counter() - ts0)
+        q1 = integ.stats()
+        sp = ctx.sum_over_ranks(float(q1["paths"] - q0["paths"]))
+        strong = {"value": sp / sdt / 1e6, "unit": "Mpaths/s", "ms_per_step": 1e3 * sdt / args.steps, "scaling": "strong",
+                  "what": "the single-GPU step (%d spp over the whole %dx%d image) with its rows split into %d bands" % (spp, sb.width, sb.height, world)}
+
+    # ---- end-to-end through the C-ABI with host buffers: scene H2D + render + film D2H every step. With N > 1 the job's
+    # film is merged on rank 0's device over NVLink and copied to the host ONCE per step (rank 0), not once per rank.
     barrier()
-    host_film = torch.empty((sb.height, sb.width, 5), dtype=torch.float32, pin_memory=True).numpy()  # pinned host buffer
-    host_films = [host_film, torch.empty((sb.height, sb.width, 5), dtype=torch.float32, pin_memory=True).numpy()]
-    integ.film(out=host_film)
+    host_films = [torch.empty((sb.height, sb.width, 5), dtype=torch.float32, pin_memory=True).numpy() for _ in range(2)]
+    if rank == 0:
+        integ.film_async(host_films[0])
+        integ.film_wait()
+    barrier()
     e0 = integ.stats()
     h2d = d2h = 0
     te = time.perf_counter()
     for k in range(args.steps):
-        _t0 = time.perf_counter()
         h2d = integ.scene_upload()
-        _t1 = time.perf_counter()
-        step(base + args.steps + k)
-        _t2 = time.perf_counter()
-        # the step's result: a snapshot of the film, copied device->host on a second stream while the next step renders
-        # (double-buffered pinned host arrays; the last snapshot is awaited inside the timed region)
-        integ.film_async(host_films[k & 1])
-        d2h = host_film.nbytes
-        if os.environ.get("B200PG_BENCH_DEBUG"):
-            print("e2e step", k, "upload %.2f step %.2f film %.2f ms" % (1e3 * (_t1 - _t0), 1e3 * (_t2 - _t1), 1e3 * (time.perf_counter() - _t2)), file=sys.stderr)
-    integ.film_wait()
-    _tb = time.perf_counter()
+        step(base + k)
+        # the step's result: a snapshot of the (merged) film, copied device->host on a second stream while the next step
+        # renders (double-buffered pinned host arrays; the last snapshot is awaited inside the timed region)
+        if rank == 0:
+            integ.film_async(host_films[k & 1])
+            d2h = host_films[0].nbytes
+    if rank == 0:
+        integ.film_wait()
     barrier()
-    e_elapsed = time.perf_counter() - te
+    e_elapsed = ctx.max_over_ranks(time.perf_counter() - te)
     t_e2e_end = time.perf_counter()
     clocks.stop_flag = True
-    if os.environ.get("B200PG_BENCH_DEBUG"):
-        print("e2e rank", rank, "loop %.2f ms, closing barrier %.2f ms" % (1e3 * (_tb - te), 1e3 * (time.perf_counter() - _tb)), file=sys.stderr)
-    if world > 1:
-        tt = torch.tensor([e_elapsed], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e_elapsed = float(tt.item())
     e1 = integ.stats()
     e2e = {"value": (e1["paths"] - e0["paths"]) * world / e_elapsed / 1e6, "unit": "Mpaths/s",
-           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+           "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h),
+           "what": "scene re-sent host->device on every rank and the job's film read back device->host every step"
+                   + (" (merged over NVLink on rank 0's device, one copy for the whole job)" if world > 1 else "")}
+    base += args.steps
+    if h2d > (64 << 20):  # large scenes: the real API keeps the scene resident across progressions -- report that, too
+        barrier()
+        f0 = integ.stats()
+        tf = time.perf_counter()
+        for k in range(args.steps):
+            step(base + k)
+            if rank == 0:
+                integ.film_async(host_films[k & 1])
+        if rank == 0:
+            integ.film_wait()
+        barrier()
+        f_el = ctx.max_over_ranks(time.perf_counter() - tf)
+        f1 = integ.stats()
+        e2e["scene_resident"] = {"value": (f1["paths"] - f0["paths"]) * world / f_el / 1e6, "unit": "Mpaths/s",
+                                 "what": "same, scene uploaded once (as b200pg_render does): per step only the film travels"}
+        base += args.steps
 
-    # ---- multi-GPU: every rank holds a full-size film; one NCCL reduce at the end
-    if world > 1:
-        ptr, n = integ.film_device_buffer()
-        dist.reduce(wrap(ptr, n), dst=0, op=dist.ReduceOp.SUM)
-        torch.cuda.synchronize()
-
+    line = None
     if rank == 0:
         # ---- CPU baseline: the same guided training iteration with the oracle (port of the reference algorithm) on all
-        # host threads, starting from the field the GPU has trained so far, on a bounded band of rows (~10-30 s in total)
+        # host threads, starting from the field the GPU has trained so far, on a bounded band of rows
         try:
             if world > 1:
                 raise RuntimeError("reported at N=1 only")
             if args.no_cpu_baseline:
                 raise RuntimeError("skipped (--no-cpu-baseline)")
             ncores = len(os.sched_getaffinity(0))  # torchrun sets OMP_NUM_THREADS=1: ask for all host cores explicitly
+            tb = time.perf_counter()
             cb = CpuGuidedStep(pkg, sb, p, guided, args.em_iters, ncores)
+            build_s = time.perf_counter() - tb
             if guided:
                 cb.load_field(integ.field_snapshot())
             sec, np_, nr = cb.step(32, spp)
@@ -467,8 +603,8 @@ def main():
                 nr2 += nr
                 nrep += 1
             cpu = {"value": np2 / t / 1e6, "unit": "Mpaths/s", "cores": ncores, "kind": "port",
-                   "sample": "%d guided training iterations over rows 0..%d of the %dx%d image at %d spp (%.1f s of CPU work)"
-                             % (nrep, rows, sb.width, sb.height, spp, t) if guided else
+                   "sample": "%d guided training iterations over rows 0..%d of the %dx%d image at %d spp (%.1f s of CPU work; kd-tree "
+                             "build %.1f s not counted)" % (nrep, rows, sb.width, sb.height, spp, t, build_s) if guided else
                              "%d unguided progressions over rows 0..%d at %d spp (%.1f s)" % (nrep, rows, spp, t),
                    "mrays_per_sec": nr2 / t / 1e6, "kd_traversal_per_ray": cb.kd_bytes_per_ray()}
         except Exception as ex:  # the oracle is test infrastructure; its absence must not break the product arm
@@ -487,10 +623,49 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks.summary(t_start, t_e2e_end),
             "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "render_only": render_only,
+            "lanes": lanes,
         }
+        if multi is not None:
+            line["multi_gpu_checks"] = multi
+        if strong is not None:
+            line["strong_scaling"] = strong
+        if cpu and cpu.get("value"):
+            line["vs_cpu_baseline"] = {"value_ratio": value / cpu["value"], "e2e_ratio": e2e["value"] / cpu["value"]}
+    integ.close()
+    scene.close()
+    return line
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    ctx = Ctx()
+    line = measure(ctx, args, headline=True)
+    # ---- the other BASELINE configs that fit one GPU, measured briefly next to the headline (N = 1 only; the N > 1 runs of the
+    # driver's scaling sweep stay short): C3 heterogeneous medium with guided distance sampling, C4 10 M-triangle mesh
+    if ctx.world == 1 and not args.no_workloads and args.workload == "cornell_caustic_1024" and line is not None:
+        extra = {}
+        for name in [w for w in args.workloads.split(",") if w]:
+            a = parse_args([])
+            a.workload = name
+            a.steps, a.warmup, a.pretrain = 6, 3, 8
+            a.spp_per_step = 1 if name == "mesh_10m" else 4
+            a.guided_distance = name == "medium_1024"
+            a.cpu_baseline_seconds = 6.0
+            a.no_cpu_baseline = args.no_cpu_baseline
+            a.lanes = args.lanes
+            try:
+                w = measure(ctx, a, headline=False)
+                extra[name] = {k: w[k] for k in ("value", "unit", "ms_per_step", "steps", "config", "mrays_per_sec", "e2e", "roofline",
+                                                 "cpu_baseline", "vs_cpu_baseline", "clocks") if k in w}
+            except Exception as ex:
+                extra[name] = {"error": str(ex)}
+        line["workloads"] = extra
+    if ctx.rank == 0:
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if ctx.world > 1:
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -280,6 +280,11 @@ int b200pg_film_develop(void *integ, float *rgb /* H*W*3 = RGB/weight, fmtconv.c
  * b200pg_film_read_wait blocks until the snapshot has arrived. A new async read first waits for the previous one. */
 int b200pg_film_read_async(void *integ, float *rgbaw_pinned);
 int b200pg_film_read_wait(void *integ);
+/* Multi-GPU previews (the reference merges the workers' image blocks in the master's film, renderproc.cpp:141-148): map the
+ * films of the other ranks (handles of b200pg_film_ipc_handle, `world` x 64 bytes, own slot ignored). From then on
+ * b200pg_film_read_async delivers own film + the peers' films, summed on the device over NVLink in fixed rank order, so a
+ * job needs ONE device->host copy per preview. The films themselves are not modified. world <= 1 or handles == NULL unmaps. */
+int b200pg_film_peers_connect(void *integ, int rank, int world, const void *handles);
 /* Film::develop to a file (hdrfilm.cpp:487-546), format chosen by the extension: .exr (scanline OpenEXR, uncompressed, channels
  * B G R as float16 or float32 per the film's componentFormat), .pfm (float32), .rgbe / .hdr (Radiance RGBE, flat).
  * The reference's banner (`banner=true` draws a logo into the image, :501-511) is never drawn. */

@@ -83,6 +83,7 @@ def lib():
     L.b200pg_features_write.argtypes = [C.c_void_p, C.c_char_p]
     L.b200pg_film_ipc_handle.argtypes = [C.c_void_p, C.c_void_p]
     L.b200pg_film_add_peers.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.b200pg_film_peers_connect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.b200pg_k_em_exchange.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_float)]
     _lib = L
     return L
@@ -214,6 +215,22 @@ class Integrator:
 
     def film_wait(self):
         _check(lib().b200pg_film_read_wait(self.h))
+
+    def film_ipc_handle(self):
+        """64-byte CUDA IPC handle of this integrator's film (for the other ranks' film_peers_connect / film_add_peers)."""
+        buf = C.create_string_buffer(64)
+        _check(lib().b200pg_film_ipc_handle(self.h, buf))
+        return buf.raw
+
+    def film_add_peers(self, rank, world, handles):
+        """film += the other ranks' films, read over NVLink (end of a multi-GPU job)."""
+        buf = C.create_string_buffer(bytes(handles), 64 * world)
+        _check(lib().b200pg_film_add_peers(self.h, rank, world, buf))
+
+    def film_peers_connect(self, rank, world, handles):
+        """Map the other ranks' films (world x 64-byte IPC handles): film_async then delivers the job's merged film."""
+        buf = C.create_string_buffer(bytes(handles), 64 * world) if handles else None
+        _check(lib().b200pg_film_peers_connect(self.h, rank, world, buf))
 
     def develop(self):
         out = np.zeros((self.H, self.W, 3), np.float32)

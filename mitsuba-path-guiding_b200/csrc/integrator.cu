@@ -41,6 +41,7 @@ void launchShadow(const DeviceScene &S, const ShadowQueue &Q, float4 *rad, const
 void launchShade(const ShadeArgs &A, cudaStream_t st);
 void launchFlush(const ShadeArgs &A, cudaStream_t st);
 void launchFilmAdd(float4 *film, const float4 *peer, uint32_t n, cudaStream_t st);
+void launchFilmExportMerged(const float4 *film, const float4 *const *peers, int nPeers, float *out, uint32_t n, cudaStream_t st);
 void launchFeatures(const DeviceScene &S, const PathState &P, const float4 *hits, const uint32_t *nPtr, float4 *feat, cudaStream_t st);
 void launchFeatureColor(const FilmRecord &F, const float4 *splat, uint32_t n, float maxComponentValue, float4 *feat, cudaStream_t st);
 // volpath.cu
@@ -101,23 +102,39 @@ struct Integrator {
     DevBuf<MediumRecord> dMedia;
     DeviceScene S;
 
-    // wavefront state
-    PathBuffers bufA, bufB;
-    DevBuf<float4> dHits, dShO, dShD, dShC;
-    DevBuf<int32_t> dShMedium;
-    DevBuf<uint4> dShAux;
-    DevBuf<float4> dTrkA, dTrkB, dLookL;
+    // wavefront state: `lanes` independent sub-batches in flight, each on its own stream with its own queues and counters.
+    // The persistent kernels of one lane leave the SMs one block at a time as their queue runs dry -- on an open scene the
+    // last rays of a bounce are single dependent-load chains hundreds of node visits long (C4: bounces 2-5 take 260-470 us
+    // each for < 4 % of the rays, profiles/r02_c4_launches.csv) -- and the next lane's kernels move into the freed SMs.
+    // Film, splat records and the guiding buffers are shared (atomics / disjoint slot ranges).
+    struct Lane {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t evDone = nullptr, evShade = nullptr, evShadow = nullptr;
+        cudaStream_t shadowStream = nullptr;
+        PathBuffers bufA, bufB;
+        DevBuf<float4> dHits, dShO, dShD, dShC;
+        DevBuf<int32_t> dShMedium;
+        DevBuf<uint4> dShAux;
+        DevBuf<float4> dTrkA, dTrkB, dLookL;
+        DevBuf<uint32_t> dSortKey, dSortRank, dSortPerm, dBinCount, dBinOffset;
+        DevBuf<Counters> dCounters;
+        size_t capacity = 0;
+    };
+    static constexpr int kMaxLanes = 8;
+    Lane lane[kMaxLanes];
+    bool overlapShadow = !(std::getenv("B200PG_OVERLAP_SHADOW") && std::atoi(std::getenv("B200PG_OVERLAP_SHADOW")) == 0);
+    int lanes = std::getenv("B200PG_LANES") ? std::max(1, std::min(kMaxLanes, std::atoi(std::getenv("B200PG_LANES")))) : 2;
     DevBuf<float4> dSplat;
-    DevBuf<Counters> dCounters;
     DevBuf<float4> dFilm;
-    DevBuf<float> dFilmOut;
-    size_t batchCapacity = 0;
+    DevBuf<float> dFilmOut, dFilmAsync;
+    cudaEvent_t evFork = nullptr;
+    const float4 *filmPeers[16] = {nullptr};  // peers' films mapped through CUDA IPC (b200pg_film_peers_connect)
+    int nFilmPeers = 0;
     bool countTraversal = false;
     // coherence sort of the shade queue by guiding cell: bounces 1..sortBounces of a guided (sampling) progression
     // (default off: on C2 with ~800 cells the gathered state reads cost more than the coherent lobe loads save --
     // DESIGN.md, optimisation log 7; B200PG_SORT_BOUNCES / b200pg_set_option("sort_bounces") turn it on)
     int sortBounces = std::getenv("B200PG_SORT_BOUNCES") ? std::atoi(std::getenv("B200PG_SORT_BOUNCES")) : 0;
-    DevBuf<uint32_t> dSortKey, dSortRank, dSortPerm, dBinCount, dBinOffset;
     // persistent speculative traversal with per-lane refill (kernels.cu: traceQueueSpeculative): bit 0 = closest-hit queues of
     // bounces >= 1, bit 1 = shadow queues, bit 2 = camera rays too (coherent: the batch kernel is as good there)
     int traceSpec = std::getenv("B200PG_TRACE_SPEC") ? std::atoi(std::getenv("B200PG_TRACE_SPEC")) : 3;
@@ -148,16 +165,18 @@ struct Integrator {
         evPool.pop_back();
         return e;
     }
-    cudaEvent_t spanBegin() {
+    // With several lanes in flight the spans of different streams overlap in wall time: the per-stage seconds are then
+    // stream time, not exclusive GPU time (bench.py measures its per-kernel roofline figures with one lane).
+    cudaEvent_t spanBegin(cudaStream_t st = nullptr) {
         if (!timing) return nullptr;
         cudaEvent_t a = getEvent();
-        CUDA_OK(cudaEventRecord(a, stream));
+        CUDA_OK(cudaEventRecord(a, st ? st : stream));
         return a;
     }
-    void spanEnd(int kind, cudaEvent_t a) {
+    void spanEnd(int kind, cudaEvent_t a, cudaStream_t st = nullptr) {
         if (!timing) return;
         cudaEvent_t b = getEvent();
-        CUDA_OK(cudaEventRecord(b, stream));
+        CUDA_OK(cudaEventRecord(b, st ? st : stream));
         spans.push_back(Span{kind, a, b});
     }
     void drainSpans() {  // requires a synchronised stream
@@ -187,6 +206,15 @@ struct Integrator {
             cudaEventDestroy(sp.b);
         }
         for (auto &e : evPool) cudaEventDestroy(e);
+        for (auto &L : lane) {
+            if (L.stream) cudaStreamDestroy(L.stream);
+            if (L.shadowStream) cudaStreamDestroy(L.shadowStream);
+            if (L.evDone) cudaEventDestroy(L.evDone);
+            if (L.evShade) cudaEventDestroy(L.evShade);
+            if (L.evShadow) cudaEventDestroy(L.evShadow);
+        }
+        if (evFork) cudaEventDestroy(evFork);
+        for (int r = 0; r < nFilmPeers; ++r) cudaIpcCloseMemHandle((void *)filmPeers[r]);
     }
 
     void init() {
@@ -234,8 +262,16 @@ struct Integrator {
         S.camera = H.camera;
         S.film = H.filmRec;
         S.seed = H.seed;
-        dCounters.alloc(1);
-        CUDA_OK(cudaMemsetAsync(dCounters.p, 0, sizeof(Counters), stream));
+        CUDA_OK(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming));
+        for (auto &L : lane) {
+            CUDA_OK(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+            CUDA_OK(cudaStreamCreateWithFlags(&L.shadowStream, cudaStreamNonBlocking));
+            CUDA_OK(cudaEventCreateWithFlags(&L.evDone, cudaEventDisableTiming));
+            CUDA_OK(cudaEventCreateWithFlags(&L.evShade, cudaEventDisableTiming));
+            CUDA_OK(cudaEventCreateWithFlags(&L.evShadow, cudaEventDisableTiming));
+            L.dCounters.alloc(1);
+            CUDA_OK(cudaMemsetAsync(L.dCounters.p, 0, sizeof(Counters), stream));
+        }
         dFilm.allocExact((size_t)H.film.width * H.film.height);
         CUDA_OK(cudaMemsetAsync(dFilm.p, 0, dFilm.n * sizeof(float4), stream));
         if (params.use_nee && H.emitters.empty()) params.use_nee = 0;  // nothing to sample
@@ -243,16 +279,15 @@ struct Integrator {
         CUDA_OK(cudaStreamSynchronize(stream));
     }
 
-    void ensureBatch(size_t n) {
-        if (n <= batchCapacity) return;
-        bufA.alloc(n); bufB.alloc(n);
-        dHits.alloc(n); dShO.alloc(n); dShD.alloc(n); dShC.alloc(n); dShMedium.alloc(n);
+    void ensureLane(Lane &L, size_t n) {
+        if (n <= L.capacity) return;
+        L.bufA.alloc(n); L.bufB.alloc(n);
+        L.dHits.alloc(n); L.dShO.alloc(n); L.dShD.alloc(n); L.dShC.alloc(n); L.dShMedium.alloc(n);
         if (params.volumetric) {
-            dShAux.alloc(n); dTrkA.alloc(n); dTrkB.alloc(n); dLookL.alloc(n);
+            L.dShAux.alloc(n); L.dTrkA.alloc(n); L.dTrkB.alloc(n); L.dLookL.alloc(n);
         }
-        dSplat.alloc(2 * n);
-        dSortKey.alloc(n); dSortRank.alloc(n); dSortPerm.alloc(n);
-        batchCapacity = n;
+        L.dSortKey.alloc(n); L.dSortRank.alloc(n); L.dSortPerm.alloc(n);
+        L.capacity = n;
     }
 
     IntegratorConfig config() const {
@@ -271,118 +306,179 @@ struct Integrator {
         return c;
     }
 
-    // Runs one wavefront batch to completion (all bounces). Everything is enqueued on `stream`
-    // without host synchronisation unless maxDepth is infinite.
-    void runBatch(const BatchDesc &B, float *radianceOut) {
-        ensureBatch(B.nPaths);
-        guide.ensureBatch(B.nPaths);
-        if (guide.active && guide.recording) {  // room for this batch's training samples (renderProgression sizes it for a
-            // whole progression beforehand; this covers stand-alone batches such as b200pg_k_radiance)
-            const size_t want = std::min<size_t>((size_t)B.nPaths * guide.maxVerts, (size_t)48 << 20);
+    // Runs up to `lanes` wavefront batches to completion (all bounces), one lane each, their kernels interleaved bounce by
+    // bounce on the lanes' streams. Everything is enqueued without host synchronisation unless maxDepth is infinite. The
+    // batches' slot ranges [slotBase, slotBase + nPaths) must be disjoint (splat records, training-vertex records).
+    // On return the main stream waits for every lane.
+    void runBatches(const BatchDesc *batches, int nBatches, float *radianceOut) {
+        size_t totalSlots = 0;
+        for (int l = 0; l < nBatches; ++l) totalSlots = std::max<size_t>(totalSlots, (size_t)batches[l].slotBase + batches[l].nPaths);
+        dSplat.alloc(2 * totalSlots);
+        guide.ensureBatch(totalSlots);
+        if (guide.active && guide.recording) {  // room for the training samples (renderProgression sizes it for a whole
+            // progression beforehand; this covers stand-alone batches such as b200pg_k_radiance)
+            const size_t want = std::min<size_t>(totalSlots * guide.maxVerts, (size_t)48 << 20);
             if (want > guide.sampleCapacity) {
                 guide.dSPos.alloc(want); guide.dSDir.alloc(want); guide.dSDist.alloc(want);
                 guide.sampleCapacity = want;
             }
         }
+        for (int l = 0; l < nBatches; ++l) ensureLane(lane[l], batches[l].nPaths);
+        const bool single = nBatches == 1;  // one batch: run on the main stream itself (no fork / join events)
+        if (!single) CUDA_OK(cudaEventRecord(evFork, stream));
         const size_t zeroBytes = offsetof(Counters, paths);
-        CUDA_OK(cudaMemsetAsync(dCounters.p, 0, zeroBytes, stream));
-        PathState cur = bufA.view(), next = bufB.view();
-        launchGenerate(S, B, cur, dCounters.p, stream);
-        stats.kernel_launches++;
-        ShadeArgs A;
-        A.S = S;
-        A.cfg = config();
-        guide.configure(A);
-        A.shadow.o = dShO.p; A.shadow.d = dShD.p; A.shadow.c = dShC.p; A.shadow.medium = dShMedium.p; A.shadow.aux = dShAux.p;
-        A.hits = dHits.p;
-        A.C = dCounters.p;
-        A.film = dFilm.p;
-        A.radianceOut = radianceOut;
-        A.splat = dSplat.p;
-        A.trkA = dTrkA.p; A.trkB = dTrkB.p; A.lookL = dLookL.p;
-        A.perm = nullptr;
-        // coherence sort (surface path, sampling from a trained field): bins = 1 + cells
-        const bool sortOn = sortBounces > 0 && !params.volumetric && A.G.enabled;
-        SortArgs sortArgs = {};
-        if (sortOn) {
-            const size_t bins = 1 + (size_t)guide.numCells();
-            if (bins > dBinCount.n) {
-                dBinCount.alloc(bins); dBinOffset.alloc(dBinCount.n);
-                CUDA_OK(cudaMemsetAsync(dBinCount.p, 0, dBinCount.n * sizeof(uint32_t), stream));
+        ShadeArgs A[kMaxLanes];
+        PathState cur[kMaxLanes], next[kMaxLanes];
+        SortArgs sortArgs[kMaxLanes];
+        cudaStream_t st[kMaxLanes];
+        bool live[kMaxLanes];
+        const bool sortOn = sortBounces > 0 && !params.volumetric && guide.active && guide.sampling && guide.trained;
+        for (int l = 0; l < nBatches; ++l) {
+            Lane &L = lane[l];
+            st[l] = single ? stream : L.stream;
+            live[l] = true;
+            if (!single) CUDA_OK(cudaStreamWaitEvent(st[l], evFork, 0));
+            CUDA_OK(cudaMemsetAsync(L.dCounters.p, 0, zeroBytes, st[l]));
+            cur[l] = L.bufA.view();
+            next[l] = L.bufB.view();
+            launchGenerate(S, batches[l], cur[l], L.dCounters.p, st[l]);
+            stats.kernel_launches++;
+            ShadeArgs &a = A[l];
+            a.S = S;
+            a.cfg = config();
+            guide.configure(a);
+            a.shadow.o = L.dShO.p; a.shadow.d = L.dShD.p; a.shadow.c = L.dShC.p; a.shadow.medium = L.dShMedium.p; a.shadow.aux = L.dShAux.p;
+            a.hits = L.dHits.p;
+            a.C = L.dCounters.p;
+            a.film = dFilm.p;
+            a.radianceOut = radianceOut;
+            a.splat = dSplat.p;
+            a.trkA = L.dTrkA.p; a.trkB = L.dTrkB.p; a.lookL = L.dLookL.p;
+            a.perm = nullptr;
+            sortArgs[l] = SortArgs{};
+            if (sortOn) {  // coherence sort (surface path, sampling from a trained field): bins = 1 + cells
+                const size_t bins = 1 + (size_t)guide.numCells();
+                if (bins > L.dBinCount.n) {
+                    L.dBinCount.alloc(bins); L.dBinOffset.alloc(L.dBinCount.n);
+                    CUDA_OK(cudaMemsetAsync(L.dBinCount.p, 0, L.dBinCount.n * sizeof(uint32_t), st[l]));
+                }
+                sortArgs[l].guideNodes = guide.dNodes.p;
+                sortArgs[l].binCount = L.dBinCount.p; sortArgs[l].binOffset = L.dBinOffset.p;
+                sortArgs[l].key = L.dSortKey.p; sortArgs[l].rank = L.dSortRank.p; sortArgs[l].perm = L.dSortPerm.p;
+                sortArgs[l].nCells = guide.dCounts.p;
             }
-            sortArgs.guideNodes = guide.dNodes.p;
-            sortArgs.binCount = dBinCount.p; sortArgs.binOffset = dBinOffset.p;
-            sortArgs.key = dSortKey.p; sortArgs.rank = dSortRank.p; sortArgs.perm = dSortPerm.p;
-            sortArgs.nCells = guide.dCounts.p;
         }
         const int maxBounces = params.max_depth > 0 ? std::min(params.max_depth + 1, 256) : 256;
-        Counters *C = dCounters.p;
-        int b = 0;
-        for (; b < maxBounces; ++b) {
-            if (cancel.load()) break;
-            cudaEvent_t t = spanBegin();
-            const bool sorted = sortOn && b >= 1 && b <= sortBounces;
-            launchTrace(S, cur, dHits.p, &C->queue[b], &C->traceWork[b], C, countTraversal, sorted ? &sortArgs : nullptr,
-                        (traceSpec & (b == 0 ? 4 : 1)) != 0, stream);
-            if (sorted) stats.kernel_launches += 2;
-            spanEnd(kTimeTrace, t);
-            if (b == 0 && featureBuffers && !radianceOut) {
-                launchFeatures(S, cur, dHits.p, &C->queue[0], dFeat.p, stream);
-                stats.kernel_launches++;
+        int lastBounce[kMaxLanes];
+        for (int l = 0; l < nBatches; ++l) lastBounce[l] = maxBounces;
+        for (int b = 0; b < maxBounces; ++b) {
+            if (cancel.load()) {
+                for (int l = 0; l < nBatches; ++l)
+                    if (live[l]) { lastBounce[l] = b; live[l] = false; }
+                break;
             }
-            A.perm = sorted ? dSortPerm.p : nullptr;
-            A.cur = cur;
-            A.next = next;
-            A.bounce = b;
-            t = spanBegin();
-            if (params.volumetric) launchShadeVol(A, stream); else launchShade(A, stream);
-            spanEnd(kTimeShade, t);
-            t = spanBegin();
-            if (params.volumetric)
-                launchShadowVol(S, A.shadow, next.rad, &C->shadow[b], &C->shadowWork[b], C, stream);
-            else
-                launchShadow(S, A.shadow, next.rad, &C->shadow[b], &C->shadowWork[b], C, countTraversal, (traceSpec & 2) != 0, stream);
-            spanEnd(kTimeShadow, t);
-            stats.kernel_launches += 3;
-            std::swap(cur, next);
-            if (params.max_depth <= 0 && (b & 3) == 3) {  // infinite depth: poll the queue size
-                uint32_t nq = 0;
-                CUDA_OK(cudaMemcpyAsync(&nq, &C->queue[b + 1], sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-                CUDA_OK(cudaStreamSynchronize(stream));
-                if (nq == 0) {
-                    ++b;
-                    break;
+            bool any = false;
+            for (int l = 0; l < nBatches; ++l) {
+                if (!live[l]) continue;
+                any = true;
+                Lane &L = lane[l];
+                Counters *C = L.dCounters.p;
+                cudaEvent_t t = spanBegin(st[l]);
+                const bool sorted = sortOn && b >= 1 && b <= sortBounces;
+                launchTrace(S, cur[l], L.dHits.p, &C->queue[b], &C->traceWork[b], C, countTraversal, sorted ? &sortArgs[l] : nullptr,
+                            (traceSpec & (b == 0 ? 4 : 1)) != 0, st[l]);
+                if (sorted) stats.kernel_launches += 2;
+                spanEnd(kTimeTrace, t, st[l]);
+                if (b == 0 && featureBuffers && !radianceOut) {
+                    launchFeatures(S, cur[l], L.dHits.p, &C->queue[0], dFeat.p, st[l]);
+                    stats.kernel_launches++;
+                }
+                ShadeArgs &a = A[l];
+                a.perm = sorted ? L.dSortPerm.p : nullptr;
+                a.cur = cur[l];
+                a.next = next[l];
+                a.bounce = b;
+                // shadow rays of bounce b-1 add into the path records this shade stage reads: they must have landed
+                if (overlapShadow && b > 0) CUDA_OK(cudaStreamWaitEvent(st[l], L.evShadow, 0));
+                t = spanBegin(st[l]);
+                if (params.volumetric) launchShadeVol(a, st[l]); else launchShade(a, st[l]);
+                spanEnd(kTimeShade, t, st[l]);
+                // The shadow stage of bounce b only touches the shadow queue and next.rad; the closest-hit stage of bounce
+                // b + 1 reads rays and flags. With overlapShadow the two run concurrently (second stream): the shadow
+                // kernel's blocks move into the SMs that the trace kernel's tail leaves idle.
+                cudaStream_t ss = overlapShadow ? L.shadowStream : st[l];
+                if (overlapShadow) {
+                    CUDA_OK(cudaEventRecord(L.evShade, st[l]));
+                    CUDA_OK(cudaStreamWaitEvent(ss, L.evShade, 0));
+                }
+                t = spanBegin(ss);
+                if (params.volumetric)
+                    launchShadowVol(S, a.shadow, next[l].rad, &C->shadow[b], &C->shadowWork[b], C, ss);
+                else
+                    launchShadow(S, a.shadow, next[l].rad, &C->shadow[b], &C->shadowWork[b], C, countTraversal, (traceSpec & 2) != 0, ss);
+                spanEnd(kTimeShadow, t, ss);
+                if (overlapShadow) CUDA_OK(cudaEventRecord(L.evShadow, ss));
+                stats.kernel_launches += 3;
+                std::swap(cur[l], next[l]);
+                if (params.max_depth <= 0 && (b & 3) == 3) {  // infinite depth: poll the queue size
+                    uint32_t nq = 0;
+                    CUDA_OK(cudaMemcpyAsync(&nq, &C->queue[b + 1], sizeof(uint32_t), cudaMemcpyDeviceToHost, st[l]));
+                    CUDA_OK(cudaStreamSynchronize(st[l]));
+                    if (nq == 0) {
+                        lastBounce[l] = b + 1;
+                        live[l] = false;
+                    }
                 }
             }
+            if (!any) break;
         }
-        A.cur = cur;
-        A.next = next;
-        A.perm = nullptr;
-        A.bounce = std::min(b, maxBounces);
-        launchFlush(A, stream);
-        stats.kernel_launches++;
-        if (!radianceOut && !cancel.load()) {  // every path of the batch has ended exactly once: rasterise them
-            cudaEvent_t t = spanBegin();
-            launchSplat(S.film, dFilm.p, dSplat.p, B.nPaths, params.max_component_value, stream);
+        for (int l = 0; l < nBatches; ++l) {
+            Lane &L = lane[l];
+            ShadeArgs &a = A[l];
+            a.cur = cur[l];
+            a.next = next[l];
+            a.perm = nullptr;
+            a.bounce = std::min(lastBounce[l], maxBounces);
+            if (overlapShadow && a.bounce > 0) CUDA_OK(cudaStreamWaitEvent(st[l], L.evShadow, 0));
+            launchFlush(a, st[l]);
             stats.kernel_launches++;
-            if (featureBuffers) {
-                launchFeatureColor(S.film, dSplat.p, B.nPaths, params.max_component_value, dFeat.p, stream);
+            if (!radianceOut && !cancel.load()) {  // every path of the batch has ended exactly once: rasterise them
+                cudaEvent_t t = spanBegin(st[l]);
+                const float4 *sp = dSplat.p + 2 * (size_t)batches[l].slotBase;
+                launchSplat(S.film, dFilm.p, sp, batches[l].nPaths, params.max_component_value, st[l]);
                 stats.kernel_launches++;
+                if (featureBuffers) {
+                    launchFeatureColor(S.film, sp, batches[l].nPaths, params.max_component_value, dFeat.p, st[l]);
+                    stats.kernel_launches++;
+                }
+                spanEnd(kTimeFilm, t, st[l]);
             }
-            spanEnd(kTimeFilm, t);
+            if (!single) {
+                CUDA_OK(cudaEventRecord(L.evDone, st[l]));
+                CUDA_OK(cudaStreamWaitEvent(stream, L.evDone, 0));
+            }
         }
     }
+    void runBatch(const BatchDesc &B, float *radianceOut) { runBatches(&B, 1, radianceOut); }
 
     void pullCounters() {
-        Counters h;
-        CUDA_OK(cudaMemcpyAsync(&h, dCounters.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+        struct Tail { unsigned long long paths, normalRays, shadowRays, pathLen, nodesVisited, primsTested, trainSamples; };
+        static_assert(sizeof(Tail) == sizeof(Counters) - offsetof(Counters, paths), "Counters statistics tail");
+        Tail h[kMaxLanes];
+        for (int l = 0; l < kMaxLanes; ++l)
+            CUDA_OK(cudaMemcpyAsync(&h[l], &lane[l].dCounters.p->paths, sizeof(Tail), cudaMemcpyDeviceToHost, stream));
         CUDA_OK(cudaStreamSynchronize(stream));
-        stats.paths = h.paths + peerPaths;
-        stats.normal_rays = h.normalRays + peerNormalRays;
-        stats.shadow_rays = h.shadowRays + peerShadowRays;
-        stats.path_length_sum = h.pathLen + peerPathLen;
-        stats.bvh_nodes_visited = h.nodesVisited;
-        stats.prims_tested = h.primsTested;
+        uint64_t paths = 0, nr = 0, sr = 0, pl = 0, nv = 0, pt = 0;
+        for (int l = 0; l < kMaxLanes; ++l) {
+            paths += h[l].paths; nr += h[l].normalRays; sr += h[l].shadowRays; pl += h[l].pathLen;
+            nv += h[l].nodesVisited; pt += h[l].primsTested;
+        }
+        stats.paths = paths + peerPaths;
+        stats.normal_rays = nr + peerNormalRays;
+        stats.shadow_rays = sr + peerShadowRays;
+        stats.path_length_sum = pl + peerPathLen;
+        stats.bvh_nodes_visited = nv;
+        stats.prims_tested = pt;
         stats.train_samples = guide.samplesTrained;
     }
 
@@ -403,11 +499,15 @@ struct Integrator {
         }
         // device time of the whole progression: CUDA events on the launching stream
         CUDA_OK(cudaEventRecord(ev[2], stream));
-        // split: whole band x k samples if it fits, else row chunks per sample
+        // Split into batches: whole band x k samples where that fits, else row chunks per sample; `lanes` batches run
+        // concurrently, so the batch size aims at total / lanes (not below 256 k paths: smaller kernels do not fill the GPU).
         const size_t bandPaths = rowPaths * (rowEnd - rowBegin);
-        if (bandPaths <= maxBatch) {
-            int spb = (int)std::max<size_t>(1, maxBatch / bandPaths);
-            for (int s = 0; s < nSamples && !cancel.load(); s += spb) {
+        const size_t total = bandPaths * (size_t)nSamples;
+        const size_t target = std::min(maxBatch, std::max<size_t>((total + lanes - 1) / lanes, (size_t)256 << 10));
+        std::vector<BatchDesc> batches;
+        if (bandPaths <= target) {
+            const int spb = (int)std::max<size_t>(1, target / bandPaths);
+            for (int s = 0; s < nSamples; s += spb) {
                 BatchDesc B;
                 std::memset(&B, 0, sizeof(B));
                 B.rowBegin = rowBegin;
@@ -415,12 +515,13 @@ struct Integrator {
                 B.firstSample = firstSample + s;
                 B.nSamples = std::min(spb, nSamples - s);
                 B.nPaths = (uint32_t)(bandPaths * B.nSamples);
-                runBatch(B, nullptr);
+                batches.push_back(B);
             }
         } else {
-            int rowsPer = (int)std::max<size_t>(1, maxBatch / rowPaths);
+            int rowsPer = (int)std::max<size_t>(1, target / rowPaths);
+            if (rowsPer >= 4) rowsPer &= ~3;  // k_generate's 8 x 4 pixel tiles
             for (int s = 0; s < nSamples; ++s)
-                for (int r = rowBegin; r < rowEnd && !cancel.load(); r += rowsPer) {
+                for (int r = rowBegin; r < rowEnd; r += rowsPer) {
                     BatchDesc B;
                     std::memset(&B, 0, sizeof(B));
                     B.rowBegin = r;
@@ -428,8 +529,17 @@ struct Integrator {
                     B.firstSample = firstSample + s;
                     B.nSamples = 1;
                     B.nPaths = (uint32_t)(rowPaths * B.nRows);
-                    runBatch(B, nullptr);
+                    batches.push_back(B);
                 }
+        }
+        for (size_t i = 0; i < batches.size() && !cancel.load(); i += (size_t)lanes) {
+            const int n = (int)std::min<size_t>((size_t)lanes, batches.size() - i);
+            uint32_t base = 0;
+            for (int l = 0; l < n; ++l) {  // disjoint slot ranges inside the group
+                batches[i + l].slotBase = base;
+                base += batches[i + l].nPaths;
+            }
+            runBatches(&batches[i], n, nullptr);
         }
         CUDA_OK(cudaEventRecord(ev[3], stream));
         uint32_t recorded = 0xFFFFFFFFu;
@@ -567,6 +677,7 @@ void *b200pg_integrator_create(void *scene, const B200pgIntegratorParams *params
 
 int b200pg_progression_render(void *integ, int first_sample, int n_samples, int row_begin, int row_end) {
     PG_TRY(integ)
+    self->cancel.store(0);  // a cancel request ends the call it interrupts, not every later one
     self->renderProgression(first_sample, n_samples, row_begin, row_end);
     self->pullCounters();
     PG_END
@@ -846,12 +957,39 @@ int b200pg_film_read_async(void *integ, float *rgbaw_pinned) {
         CUDA_OK(cudaEventCreateWithFlags(&self->evExport, cudaEventDisableTiming));
     }
     CUDA_OK(cudaStreamSynchronize(self->copyStream));  // the previous read must have left the staging buffer
-    self->dFilmOut.alloc(self->dFilm.n * 5);
-    launchFilmExport(self->dFilm.p, self->dFilmOut.p, (uint32_t)self->dFilm.n, 0, self->stream);
+    // the asynchronous path stages through its OWN buffer: b200pg_film_read / _develop / _write re-use dFilmOut on the render
+    // stream and must not tear a preview copy that is still in flight
+    self->dFilmAsync.alloc(self->dFilm.n * 5);
+    if (self->nFilmPeers > 0)
+        launchFilmExportMerged(self->dFilm.p, self->filmPeers, self->nFilmPeers, self->dFilmAsync.p, (uint32_t)self->dFilm.n, self->stream);
+    else
+        launchFilmExport(self->dFilm.p, self->dFilmAsync.p, (uint32_t)self->dFilm.n, 0, self->stream);
     CUDA_OK(cudaEventRecord(self->evExport, self->stream));
     CUDA_OK(cudaStreamWaitEvent(self->copyStream, self->evExport, 0));
-    CUDA_OK(cudaMemcpyAsync(rgbaw_pinned, self->dFilmOut.p, self->dFilm.n * 5 * sizeof(float), cudaMemcpyDeviceToHost, self->copyStream));
+    CUDA_OK(cudaMemcpyAsync(rgbaw_pinned, self->dFilmAsync.p, self->dFilm.n * 5 * sizeof(float), cudaMemcpyDeviceToHost, self->copyStream));
     self->stats.kernel_launches++;
+    PG_END
+}
+// Multi-GPU previews: maps the films of the other ranks (CUDA IPC handles from b200pg_film_ipc_handle, `world` x 64 bytes, own
+// slot ignored). From then on b200pg_film_read_async on this integrator delivers own film + the peers' films, summed on the
+// device over NVLink in fixed rank order -- ONE device->host copy per preview for the whole job instead of one per rank. The
+// films are not modified. world = 1 (or handles = NULL) unmaps.
+int b200pg_film_peers_connect(void *integ, int rank, int world, const void *handles) {
+    PG_TRY(integ)
+    CUDA_OK(cudaStreamSynchronize(self->stream));
+    if (self->copyStream) CUDA_OK(cudaStreamSynchronize(self->copyStream));
+    for (int r = 0; r < self->nFilmPeers; ++r) cudaIpcCloseMemHandle((void *)self->filmPeers[r]);
+    self->nFilmPeers = 0;
+    if (!handles || world <= 1) return 0;
+    if (world > 16 || rank < 0 || rank >= world) return fail("invalid argument");
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, (const char *)handles + 64 * (size_t)r, 64);
+        void *ptr = nullptr;
+        CUDA_OK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        self->filmPeers[self->nFilmPeers++] = (const float4 *)ptr;
+    }
     PG_END
 }
 int b200pg_film_read_wait(void *integ) {
@@ -1088,6 +1226,8 @@ int b200pg_set_option(void *integ, const char *name, int value) {
     else if (n == "timing") self->timing = value != 0;
     else if (n == "sort_bounces") self->sortBounces = value;
     else if (n == "trace_spec") self->traceSpec = value;
+    else if (n == "overlap_shadow") self->overlapShadow = value != 0;
+    else if (n == "lanes") self->lanes = std::max(1, std::min((int)Integrator::kMaxLanes, value));
     else if (n == "feature_buffers") {
         self->featureBuffers = value != 0;
         if (self->featureBuffers && !self->dFeat.p) {
@@ -1149,7 +1289,7 @@ int b200pg_scene_upload(void *integ, size_t *bytes) {
 // ---------------------------------------------------------------------------------------------
 int b200pg_k_trace_device(void *integ, const void *d_rays, size_t n, int shadow, void *d_hits, float *ms, uint64_t *counts) {
     PG_TRY(integ)
-    Counters *C = self->dCounters.p;
+    Counters *C = self->lane[0].dCounters.p;
     CUDA_OK(cudaMemsetAsync(&C->misc[0], 0, sizeof(uint32_t), self->stream));
     if (counts) {
         CUDA_OK(cudaMemsetAsync(&C->nodesVisited, 0, 2 * sizeof(unsigned long long), self->stream));

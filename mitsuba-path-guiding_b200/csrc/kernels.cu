@@ -84,6 +84,28 @@ __global__ void __launch_bounds__(256) k_film_export(const float4 *__restrict__ 
     }
 }
 
+// Merged preview of a multi-GPU job: (own film + the peers' films, read over NVLink) expanded to (R,G,B,alpha,weight) -- the
+// films themselves are left untouched, so it can run after every progression while all ranks keep accumulating.
+struct FilmPeers {
+    const float4 *p[16];
+    int n;
+};
+__global__ void __launch_bounds__(256) k_film_export_merged(const float4 *__restrict__ film, FilmPeers peers, float *__restrict__ out,
+                                                            uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 f = film[i];
+        for (int r = 0; r < peers.n; ++r) {  // fixed peer order
+            const float4 g = ldStream(peers.p[r] + i);
+            f.x += g.x; f.y += g.y; f.z += g.z; f.w += g.w;
+        }
+        out[5 * (size_t)i + 0] = f.x;
+        out[5 * (size_t)i + 1] = f.y;
+        out[5 * (size_t)i + 2] = f.z;
+        out[5 * (size_t)i + 3] = f.w;
+        out[5 * (size_t)i + 4] = f.w;
+    }
+}
+
 // Multi-GPU film merge (every GPU holds a full-size film): film += a peer's film, read over NVLink
 __global__ void __launch_bounds__(256) k_film_add(float4 *__restrict__ film, const float4 *__restrict__ peer, uint32_t n) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -131,7 +153,7 @@ __global__ void __launch_bounds__(256) k_generate(DeviceScene S, BatchDesc B, Pa
         P.pos[i] = make_float4(samplePos.x, samplePos.y, __uint_as_float((uint32_t)rng.state),
                                __uint_as_float((uint32_t)(rng.state >> 32)));
         P.flags[i] = 1u | kFlagFirst;  // rRec.newQuery: depth = 1 (integrator.h:218-225)
-        P.slot[i] = i;
+        P.slot[i] = B.slotBase + i;
         P.medium[i] = S.camera.medium;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) C->queue[0] = B.nPaths;
@@ -924,6 +946,12 @@ void launchFeatures(const DeviceScene &S, const PathState &P, const float4 *hits
 }
 void launchFeatureColor(const FilmRecord &F, const float4 *splat, uint32_t n, float maxComponentValue, float4 *feat, cudaStream_t st) {
     k_feature_color<<<numSMs() * 4, 256, 0, st>>>(F, splat, n, maxComponentValue, feat);
+}
+void launchFilmExportMerged(const float4 *film, const float4 *const *peers, int nPeers, float *out, uint32_t n, cudaStream_t st) {
+    FilmPeers P;
+    P.n = nPeers;
+    for (int r = 0; r < 16; ++r) P.p[r] = r < nPeers ? peers[r] : nullptr;
+    k_film_export_merged<<<numSMs() * 4, 256, 0, st>>>(film, P, out, n);
 }
 void launchFilmAdd(float4 *film, const float4 *peer, uint32_t n, cudaStream_t st) {
     k_film_add<<<numSMs() * 4, 256, 0, st>>>(film, peer, n);

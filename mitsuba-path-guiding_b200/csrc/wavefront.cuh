@@ -73,6 +73,7 @@ struct BatchDesc {
     uint32_t nPaths;
     uint32_t rowBegin, nRows;  // image band
     uint32_t firstSample, nSamples;
+    uint32_t slotBase;           // first slot (splat record / training-vertex record index) of this batch
     const uint32_t *pixelList;   // optional explicit (pixel, sample) pairs
     const uint32_t *sampleList;
 };
