@@ -401,6 +401,8 @@ def measure(ctx, args, headline):
     prof_steps = max(2, min(args.steps, 4))
     integ.set_option("lanes", 1)
     integ.set_option("overlap_shadow", 0)
+    step(base)  # untimed: the first one-lane step re-sizes the lane's queues
+    base += 1
     barrier()
     p0s, ps0 = integ.stage_times(), integ.stats()
     for k in range(prof_steps):

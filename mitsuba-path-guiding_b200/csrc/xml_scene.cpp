@@ -634,21 +634,28 @@ struct Loader {
         if (rd16(0) != 0x041C) fail("Encountered an invalid file format!");
         int version = rd16(2);
         if (version != 3 && version != 4) fail("Encountered an incompatible file version!");
+        // The file -- trailer included -- is untrusted input: every position derived from it is checked against the file size
+        // before it is dereferenced.
         size_t offset = 0;
         if (shapeIndex != 0) {
             uint32_t count;
             std::memcpy(&count, &buf[size - 4], 4);
-            if (shapeIndex < 0 || shapeIndex > (int)count) fail("Unable to unserialize mesh, shape index is out of range!");
-            if (version == 4) {
-                uint64_t o;
-                std::memcpy(&o, &buf[size - 8 * (count - shapeIndex) - 4], 8);
-                offset = (size_t)o;
-            } else {
-                uint32_t o;
-                std::memcpy(&o, &buf[size - 4 * (count - shapeIndex + 1)], 4);
-                offset = o;
-            }
+            if (shapeIndex < 0 || (uint64_t)shapeIndex >= (uint64_t)count) fail("Unable to unserialize mesh, shape index is out of range!");
+            const uint64_t entry = version == 4 ? 8 : 4;
+            // trailer = `count` offsets + the count itself; it cannot be larger than what follows the 4-byte header
+            if ((uint64_t)count * entry + 4 > (uint64_t)size - 4) fail("serialized: corrupt offset dictionary in \"" + path + "\"");
+            const uint64_t at = version == 4 ? (uint64_t)size - 8 * ((uint64_t)count - (uint64_t)shapeIndex) - 4
+                                             : (uint64_t)size - 4 * ((uint64_t)count - (uint64_t)shapeIndex + 1);
+            if (at < 4 || at + entry > (uint64_t)size) fail("serialized: corrupt offset dictionary in \"" + path + "\"");
+            uint64_t o = 0;
+            std::memcpy(&o, &buf[(size_t)at], (size_t)entry);
+            if (o > (uint64_t)size) fail("serialized: shape offset outside the file \"" + path + "\"");
+            offset = (size_t)o;
         }
+        if (offset + 4 > size) fail("serialized: shape offset outside the file \"" + path + "\"");
+        if (offset != 0 && (rd16(offset) != 0x041C || (rd16(offset + 2) != 3 && rd16(offset + 2) != 4)))
+            fail("Encountered an invalid file format!");
+        if (offset != 0) version = rd16(offset + 2);
         offset += 4;  // skip the (per-shape) header
         z_stream zs;
         std::memset(&zs, 0, sizeof(zs));
@@ -670,30 +677,38 @@ struct Loader {
         } while (rc != Z_STREAM_END);
         inflateEnd(&zs);
         size_t p = 0;
-        auto need = [&](size_t n) { if (p + n > out.size()) fail("serialized: truncated stream"); };
+        // counts come from the (untrusted) stream: sizes are checked -- overflow-safe -- BEFORE anything is allocated
+        auto need = [&](uint64_t n) {
+            if (p > out.size() || n > (uint64_t)(out.size() - p)) fail("serialized: truncated stream");
+        };
+        auto needArr = [&](uint64_t count, uint64_t elem) {
+            if (elem != 0 && count > (uint64_t)out.size() / elem) fail("serialized: truncated stream");
+            need(count * elem);
+        };
         uint32_t flags;
         need(4); std::memcpy(&flags, &out[p], 4); p += 4;
         if (version == 4) {
             while (p < out.size() && out[p] != 0) ++p;
+            if (p >= out.size()) fail("serialized: truncated stream");
             ++p;
         }
         uint64_t nv, nt;
         need(16); std::memcpy(&nv, &out[p], 8); std::memcpy(&nt, &out[p + 8], 8); p += 16;
         const bool dbl = flags & 0x2000;
-        auto readArr = [&](size_t count, std::vector<float> &dst) {
-            dst.resize(count);
+        if (nv > 0xFFFFFFFFull || nt > 0xFFFFFFFFull) fail("serialized: vertex / triangle count out of range");
+        auto readArr = [&](uint64_t count, std::vector<float> &dst) {
+            needArr(count, dbl ? 8 : 4);
+            dst.resize((size_t)count);
             if (dbl) {
-                need(count * 8);
-                for (size_t i = 0; i < count; ++i) {
+                for (size_t i = 0; i < (size_t)count; ++i) {
                     double d;
                     std::memcpy(&d, &out[p + 8 * i], 8);
                     dst[i] = (float)d;
                 }
-                p += count * 8;
+                p += (size_t)count * 8;
             } else {
-                need(count * 4);
-                std::memcpy(dst.data(), &out[p], count * 4);
-                p += count * 4;
+                std::memcpy(dst.data(), &out[p], (size_t)count * 4);
+                p += (size_t)count * 4;
             }
         };
         std::vector<float> pos, nrm, uv, col;
@@ -701,9 +716,11 @@ struct Loader {
         if (flags & 0x0001) readArr(nv * 3, nrm);
         if (flags & 0x0002) readArr(nv * 2, uv);
         if (flags & 0x0008) readArr(nv * 3, col);
-        std::vector<uint32_t> idx(nt * 3);
-        need(nt * 12);
-        std::memcpy(idx.data(), &out[p], nt * 12);
+        needArr(nt * 3, 4);
+        std::vector<uint32_t> idx((size_t)nt * 3);
+        std::memcpy(idx.data(), &out[p], (size_t)nt * 12);
+        for (uint32_t v : idx)
+            if (v >= nv) fail("serialized: vertex index out of range");
         finishMesh(pos, nrm, uv, idx, toWorld, flipNormals, faceNormals || (flags & 0x0010) != 0, s);
     }
 

@@ -219,6 +219,18 @@ class OracleScene:
             raise RuntimeError("orc_scene_create failed")
         self.W, self.H = builder.width, builder.height
 
+    @classmethod
+    def from_desc(cls, orc, desc, keep=None):
+        """Oracle scene from a flat description (e.g. api.Scene.load_xml(...).desc: what the product's XML reader produced)."""
+        self = cls.__new__(cls)
+        self.orc, self.L = orc, orc.lib
+        self.desc, self._keep = desc, keep
+        self.h = self.L.orc_scene_create(C.byref(desc))
+        if not self.h:
+            raise RuntimeError("orc_scene_create failed")
+        self.W, self.H = desc.film.width, desc.film.height
+        return self
+
     def __del__(self):
         try:
             if self.h:

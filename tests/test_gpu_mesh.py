@@ -65,7 +65,9 @@ def test_mesh_hits_both_traversal_kernels(mesh, spec):
         r2 = _secondary_rays(rays, tuv_o, prim_o, rng, osc)
         tuv_o2, prim_o2, _ = osc.trace(r2)
         tuv_g2, prim_g2 = it.k_trace(r2)
-        _check_hits(tuv_o2, prim_o2, tuv_g2, prim_g2, max_mismatch=int(3e-4 * len(prim_o2)), uv_scale=UV_SCALE)
+        # bounce rays graze the neighbouring triangles of the sheet: median error 1e-7, 99.9 % quantile ~2e-5
+        _check_hits(tuv_o2, prim_o2, tuv_g2, prim_g2, max_mismatch=int(3e-4 * len(prim_o2)), uv_scale=UV_SCALE, t_scale=20.0)
+        assert np.median(np.abs(tuv_o2[:, 0] - tuv_g2[:, 0])[(prim_o2 != 0xFFFFFFFF) & (prim_o2 == prim_g2)]) <= 2e-6
         r3 = r2.copy()
         r3[:, 7] = rng.rand(r3.shape[0]).astype(np.float32) * 2.0
         _, occ_o, _ = osc.trace(r3, shadow=True)

@@ -53,10 +53,11 @@ def _secondary_rays(rays, tuv, prim, rng, osc):
                            np.full((P.shape[0], 1), np.inf, np.float32)], 1).astype(np.float32)
 
 
-def _check_hits(tuv_o, prim_o, tuv_g, prim_g, max_mismatch=0, uv_scale=1.0):
+def _check_hits(tuv_o, prim_o, tuv_g, prim_g, max_mismatch=0, uv_scale=1.0, t_scale=1.0):
     """uv_scale: (u, v) are computed with plane coefficients ~ 1 / edge length, so their absolute error grows with the
     inverse triangle size; meshes of small triangles pass the factor by which their edges are shorter than the unit-size
-    primitives the default bound (2e-5) is stated for."""
+    primitives the default bound (2e-5) is stated for. t_scale: rays that leave a surface of small triangles meet their
+    neighbours at grazing angles, where t = (offset - n.o) / (n.d) loses digits like 1e-7 / |n.d|."""
     mism = prim_o != prim_g
     assert mism.sum() <= max_mismatch, "%d primitive-id mismatches" % mism.sum()
     m = (prim_o != 0xFFFFFFFF) & ~mism
@@ -65,8 +66,8 @@ def _check_hits(tuv_o, prim_o, tuv_g, prim_g, max_mismatch=0, uv_scale=1.0):
     rel = np.abs(tuv_o[m, 0] - tuv_g[m, 0]) / (1 + np.abs(tuv_o[m, 0]))
     duv = np.abs(tuv_o[m, 1:] - tuv_g[m, 1:]).max(1)
     if m.sum() > 1000:
-        assert np.quantile(rel, 0.999) <= 2e-6 and np.quantile(duv, 0.999) <= 2e-5 * uv_scale
-        assert rel.max() <= 2e-3 and duv.max() <= min(5e-3 * uv_scale, 0.25)
+        assert np.quantile(rel, 0.999) <= 2e-6 * t_scale and np.quantile(duv, 0.999) <= 2e-5 * uv_scale
+        assert rel.max() <= min(2e-3 * t_scale, 2e-2) and duv.max() <= min(5e-3 * uv_scale, 0.25)
     else:
         assert rel.max() <= 2e-6 and duv.max() <= 2e-5 * uv_scale
     assert np.isinf(tuv_g[prim_g == 0xFFFFFFFF, 0]).all()

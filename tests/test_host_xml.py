@@ -379,3 +379,85 @@ def test_reference_bsdf_test_file_parses_to_the_tested_parameterisations(api, pk
             continue
         with pytest.raises(api.B200pgError, match=t):
             load(ET.tostring(e, encoding="unicode"))
+
+
+def _serialized_file(path, meshes, version=4):
+    """Multi-shape .serialized file (trimesh.cpp:175-270 + the offset dictionary of serialized.cpp): per shape
+    {0x041C, version, zlib{flags, [name], nv, nt, positions, [normals], indices}}, then the offsets and the shape count."""
+    import struct
+    import zlib
+
+    blob, offsets = b"", []
+    for P, T, N in meshes:
+        flags = 0x1000 | (0x0001 if N is not None else 0)
+        body = struct.pack("<I", flags) + (b"m\0" if version == 4 else b"") + struct.pack("<QQ", len(P), len(T))
+        body += np.ascontiguousarray(P, "<f4").tobytes() + (np.ascontiguousarray(N, "<f4").tobytes() if N is not None else b"")
+        body += np.ascontiguousarray(T, "<u4").tobytes()
+        offsets.append(len(blob))
+        blob += struct.pack("<HH", 0x041C, version) + zlib.compress(body, 1)
+    for o in offsets:
+        blob += struct.pack("<Q" if version == 4 else "<I", o)
+    blob += struct.pack("<I", len(meshes))
+    with open(path, "wb") as f:
+        f.write(blob)
+    return blob
+
+
+def test_serialized_loader_and_corrupt_files(api, pkg, tmp_path):
+    """The .serialized loader (trimesh.cpp:175-270): shapeIndex into a two-shape file, v3 and v4; and the file is UNTRUSTED input
+    (ADVICE r1): a corrupt offset dictionary, a truncated stream, absurd counts or out-of-range indices are errors that name the
+    problem, never out-of-bounds reads or giant allocations."""
+    S = pkg.scenes
+    P0, N0, T0 = S.heightfield_mesh(n=5, seed=1, amp=0.2)
+    P1, N1, T1 = S.heightfield_mesh(n=4, seed=2, amp=0.1)
+    body = '<shape type="serialized"><string name="filename" value="%s"/><integer name="shapeIndex" value="%d"/>' \
+           '<bsdf type="diffuse"/></shape><shape type="rectangle"><emitter type="area"><rgb name="radiance" value="1"/></emitter></shape>'
+    for version in (3, 4):
+        fn = str(tmp_path / ("two_v%d.serialized" % version))
+        blob = _serialized_file(fn, [(P0, T0, N0), (P1, T1, None)], version)
+        for k, (P, T) in enumerate(((P0, T0), (P1, T1))):
+            sc = api.Scene.load_xml(_mesh_xml(tmp_path, body % (fn, k)))
+            sh = sc.desc.shapes[0]
+            assert sh.n_vertices == len(P) and sh.n_triangles == len(T)
+            np.testing.assert_array_equal(np.ctypeslib.as_array(sh.positions, (len(P) * 3,)).reshape(-1, 3), P.astype(np.float32))
+            np.testing.assert_array_equal(np.ctypeslib.as_array(sh.indices, (len(T) * 3,)).reshape(-1, 3), T)
+        with pytest.raises(api.B200pgError, match="out of range"):
+            api.Scene.load_xml(_mesh_xml(tmp_path, body % (fn, 2)))
+        # --- corrupt trailer: shape count far larger than the file
+        bad = str(tmp_path / "bad_count.serialized")
+        open(bad, "wb").write(blob[:-4] + (0x7FFFFFF0).to_bytes(4, "little"))
+        with pytest.raises(api.B200pgError, match="corrupt offset dictionary|out of range"):
+            api.Scene.load_xml(_mesh_xml(tmp_path, body % (bad, 1)))
+        # --- corrupt trailer: offset of shape 1 points outside the file
+        entry = 8 if version == 4 else 4
+        pos = len(blob) - 4 - entry
+        bad = str(tmp_path / "bad_offset.serialized")
+        open(bad, "wb").write(blob[:pos] + (len(blob) * 16).to_bytes(entry, "little") + blob[pos + entry:])
+        with pytest.raises(api.B200pgError, match="outside the file"):
+            api.Scene.load_xml(_mesh_xml(tmp_path, body % (bad, 1)))
+        # --- offset that lands inside the file but not on a shape header
+        bad = str(tmp_path / "bad_offset2.serialized")
+        open(bad, "wb").write(blob[:pos] + (7).to_bytes(entry, "little") + blob[pos + entry:])
+        with pytest.raises(api.B200pgError, match="invalid file format|incompatible|inflate"):
+            api.Scene.load_xml(_mesh_xml(tmp_path, body % (bad, 1)))
+    # --- streams whose counts do not match their length
+    import struct
+    import zlib
+
+    def one(body_bytes, name):
+        fn = str(tmp_path / name)
+        open(fn, "wb").write(struct.pack("<HH", 0x041C, 4) + zlib.compress(body_bytes, 1) + struct.pack("<QI", 0, 1))
+        return fn
+    head = struct.pack("<I", 0x1000) + b"m\0"
+    huge = one(head + struct.pack("<QQ", 1 << 40, 1 << 40) + b"\0" * 64, "huge.serialized")
+    with pytest.raises(api.B200pgError, match="out of range|truncated"):
+        api.Scene.load_xml(_mesh_xml(tmp_path, body % (huge, 0)))
+    trunc = one(head + struct.pack("<QQ", 1000, 1000) + b"\0" * 64, "trunc.serialized")
+    with pytest.raises(api.B200pgError, match="truncated"):
+        api.Scene.load_xml(_mesh_xml(tmp_path, body % (trunc, 0)))
+    noname = one(struct.pack("<I", 0x1000) + b"mmmmmmmm", "noname.serialized")
+    with pytest.raises(api.B200pgError, match="truncated"):
+        api.Scene.load_xml(_mesh_xml(tmp_path, body % (noname, 0)))
+    badidx = one(head + struct.pack("<QQ", 3, 1) + np.zeros(9, "<f4").tobytes() + np.array([0, 1, 7], "<u4").tobytes(), "badidx.serialized")
+    with pytest.raises(api.B200pgError, match="index out of range"):
+        api.Scene.load_xml(_mesh_xml(tmp_path, body % (badidx, 0)))
