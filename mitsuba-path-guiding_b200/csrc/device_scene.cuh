@@ -18,6 +18,7 @@ namespace pg {
 
 struct DeviceScene {
     const float4 *nodes;
+    const float4 *wideNodes;  // 6 x float4 per node (pg_types.h: WideNode), nullptr when the scene has no wide tree
     const float4 *prims;
     const float4 *rects;
     const ShapeRecord *shapes;
@@ -118,6 +119,79 @@ PG_DEV int bvhNodeStep(const DeviceScene &S, int node, float3 o, float3 idir, fl
     }
     if (nh == 1) return c0;
     return sp ? stack[--sp] : kDoneNode;
+}
+
+// ---- wide (8-ary, quantised) tree -------------------------------------------------------------------------------------
+// Stack entries carry the entry distance of the subtree, so a popped entry whose distance lies behind the current hit is
+// dropped without touching memory.
+static constexpr int kWideStack = 7 * kWideMaxDepth + 16;
+struct WideEntry {
+    int ref;
+    float tn;
+};
+// The wide test forms (origin - o) * idir - 2^23 * 2^e * idir: with an infinite reciprocal (a zero direction component) that is
+// inf - inf. A reciprocal clamped to 1e25 decides every slab exactly as infinity does (any offset of the ray origin from a
+// plane beyond 1e-20 maps to a distance outside every interval) and keeps the arithmetic finite.
+PG_DEV float3 wideClampIdir(float3 idir) {
+    return f3(copysignf(fminf(fabsf(idir.x), 1e25f), idir.x), copysignf(fminf(fabsf(idir.y), 1e25f), idir.y),
+              copysignf(fminf(fabsf(idir.z), 1e25f), idir.z));
+}
+PG_DEV int widePop(const WideEntry *stack, int &sp, float tmax) {
+    while (sp) {
+        const WideEntry e = stack[--sp];
+        if (e.tn <= tmax) return e.ref;
+    }
+    return kDoneNode;
+}
+// ray distance of the quantised plane `byte` of word w: fma(2^23 + q, s, b) with s = 2^e * idir, b = (origin - o) * idir - 2^23 s.
+// __byte_perm builds the float 2^23 + q (0x4B0000qq) in one instruction: no integer -> float conversion on the slow pipe.
+template <int kByte>
+PG_DEV float widePlane(uint32_t w, float s, float b) {
+    return fmaf(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + kByte)), s, b);
+}
+// One node visit: tests the (up to) 8 children, continues with the nearest hit child and pushes the others; kDoneNode when
+// nothing is left. Same conservative far-bound factor as the binary test.
+PG_DEV int wideNodeStep(const DeviceScene &S, int node, float3 o, float3 idir, float mint, float tmax, WideEntry *stack, int &sp) {
+    const float4 *N = S.wideNodes + 6 * (size_t)node;
+    const float4 h = __ldg(N);
+    const int4 r0 = __ldg(reinterpret_cast<const int4 *>(N + 1)), r1 = __ldg(reinterpret_cast<const int4 *>(N + 2));
+    const uint4 qa = __ldg(reinterpret_cast<const uint4 *>(N + 3)), qb = __ldg(reinterpret_cast<const uint4 *>(N + 4)),
+                qc = __ldg(reinterpret_cast<const uint4 *>(N + 5));
+    const uint32_t meta = __float_as_uint(h.w);
+    const float sx = __uint_as_float((meta & 0xFFu) << 23) * idir.x, sy = __uint_as_float(((meta >> 8) & 0xFFu) << 23) * idir.y,
+                sz = __uint_as_float(((meta >> 16) & 0xFFu) << 23) * idir.z;
+    const float bx = fmaf(-8388608.0f, sx, (h.x - o.x) * idir.x), by = fmaf(-8388608.0f, sy, (h.y - o.y) * idir.y),
+                bz = fmaf(-8388608.0f, sz, (h.z - o.z) * idir.z);
+    int best = kDoneNode;
+    float bestT = kInf;
+#define PG_WIDE_CHILD(REF, LOX, LOY, LOZ, HIX, HIY, HIZ, B)                                                         \
+    {                                                                                                                \
+        const float ax = widePlane<B>(LOX, sx, bx), cx = widePlane<B>(HIX, sx, bx);                                  \
+        const float ay = widePlane<B>(LOY, sy, by), cy = widePlane<B>(HIY, sy, by);                                  \
+        const float az = widePlane<B>(LOZ, sz, bz), cz = widePlane<B>(HIZ, sz, bz);                                  \
+        const float tn = fmaxf(fmaxf(fminf(ax, cx), fminf(ay, cy)), fmaxf(fminf(az, cz), mint));                     \
+        const float tf = fminf(fminf(fmaxf(ax, cx), fmaxf(ay, cy)), fminf(fmaxf(az, cz), tmax));                     \
+        const bool hit = (REF) != kWideEmpty && tn <= tf * 1.0000004f;                                               \
+        const bool better = hit && tn < bestT;                                                                       \
+        /* branch-free: the nearer of (this child, best so far) stays in registers, the other one goes to the stack */ \
+        WideEntry out;                                                                                               \
+        out.ref = better ? best : (REF);                                                                             \
+        out.tn = better ? bestT : tn;                                                                                \
+        if (hit && out.ref != kDoneNode) stack[sp++] = out;                                                          \
+        best = better ? (REF) : best;                                                                                \
+        bestT = better ? tn : bestT;                                                                                 \
+    }
+    PG_WIDE_CHILD(r0.x, qa.x, qa.z, qb.x, qb.z, qc.x, qc.z, 0)
+    PG_WIDE_CHILD(r0.y, qa.x, qa.z, qb.x, qb.z, qc.x, qc.z, 1)
+    PG_WIDE_CHILD(r0.z, qa.x, qa.z, qb.x, qb.z, qc.x, qc.z, 2)
+    PG_WIDE_CHILD(r0.w, qa.x, qa.z, qb.x, qb.z, qc.x, qc.z, 3)
+    PG_WIDE_CHILD(r1.x, qa.y, qa.w, qb.y, qb.w, qc.y, qc.w, 0)
+    PG_WIDE_CHILD(r1.y, qa.y, qa.w, qb.y, qb.w, qc.y, qc.w, 1)
+    PG_WIDE_CHILD(r1.z, qa.y, qa.w, qb.y, qb.w, qc.y, qc.w, 2)
+    PG_WIDE_CHILD(r1.w, qa.y, qa.w, qb.y, qb.w, qc.y, qc.w, 3)
+#undef PG_WIDE_CHILD
+    if (best != kDoneNode) return best;
+    return widePop(stack, sp, tmax);
 }
 
 // All primitives of one leaf (<= 4): the branch-free affine test that serves rectangles and triangles alike.

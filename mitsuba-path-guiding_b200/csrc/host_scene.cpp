@@ -835,6 +835,139 @@ bool HostScene::compile(std::string &err) {
             o.q[13] = u2f((uint32_t)c1);
             o.q[14] = o.q[15] = 0;
         }
+        // ---- wide BVH (pg_types.h: WideNode): the binary tree collapsed to up to 8 children per node with the children's
+        // boxes quantised to 8 bits on a per-node power-of-two grid. Large meshes only: three binary levels become one node
+        // visit (one dependent round trip instead of three) and the node array shrinks ~4.5x (10 M triangles: 256 MB ->
+        // 56 MB, inside the 126 MB L2). Small scenes stay on the binary tree, which lives in L1 there.
+        wideNodes.clear();
+        wideDepth = 0;
+        {
+            const char *env = std::getenv("B200PG_WIDE_MIN_PRIMS");
+            const size_t minPrims = env ? (size_t)std::atoll(env) : (size_t)32768;
+            if (bprims.size() >= minPrims && media.empty()) {
+                auto leafRef = [&](int32_t c) {  // same leaf code as the binary nodes
+                    uint32_t code = (uint32_t)(~c);
+                    uint32_t first = code >> 4, count = code & 15u, mask = 0;
+                    for (uint32_t k = 0; k < count; ++k)
+                        if (flatInfo[bprims[first + k].id].prim == kNoTriangle) mask |= 1u << k;
+                    return ~(int32_t)((first << kLeafShift) | (mask << 3) | count);
+                };
+                const float diag = std::sqrt((rootBox.mx[0] - rootBox.mn[0]) * (rootBox.mx[0] - rootBox.mn[0]) +
+                                             (rootBox.mx[1] - rootBox.mn[1]) * (rootBox.mx[1] - rootBox.mn[1]) +
+                                             (rootBox.mx[2] - rootBox.mn[2]) * (rootBox.mx[2] - rootBox.mn[2]));
+                // leaves below every binary node (children have larger indices than their parent is NOT guaranteed: recurse)
+                std::vector<uint32_t> leafCount(bld.nodes.size(), 0);
+                {
+                    std::vector<int32_t> order2, st2;
+                    st2.push_back(root);
+                    while (!st2.empty()) {
+                        const int32_t b = st2.back();
+                        st2.pop_back();
+                        order2.push_back(b);
+                        for (int c = 0; c < 2; ++c)
+                            if (bld.nodes[b].child[c] >= 0) st2.push_back(bld.nodes[b].child[c]);
+                    }
+                    for (size_t i = order2.size(); i-- > 0;) {  // children before parents
+                        const TmpNode &t = bld.nodes[order2[i]];
+                        uint32_t cnt = 0;
+                        for (int c = 0; c < 2; ++c) cnt += t.child[c] >= 0 ? leafCount[t.child[c]] : (((uint32_t)(~t.child[c]) & 15u) ? 1u : 0u);
+                        leafCount[order2[i]] = cnt;
+                    }
+                }
+                struct Item { int32_t bin; int depth; };  // binary node to collapse into wide node #index-in-queue
+                std::vector<Item> queue;
+                queue.push_back(Item{root, 1});
+                std::vector<WideNode> out;
+                for (size_t qi = 0; qi < queue.size(); ++qi) {
+                    const Item it = queue[qi];
+                    wideDepth = std::max(wideDepth, it.depth);
+                    // collapse: open children until 8 remain. Opening greedily by surface area alone leaves the bottom of the
+                    // tree full of 2-3-child nodes (a balanced 16-leaf subtree becomes 8 two-child nodes: 3.4 children per
+                    // node on the heightfield); so a subtree of <= 8 leaves is either inlined COMPLETELY, when all of its
+                    // leaves fit, or kept whole as a child node that will then be (nearly) full.
+                    int32_t ref[8];
+                    Box box[8];
+                    int n = 2;
+                    ref[0] = bld.nodes[it.bin].child[0]; box[0] = bld.nodes[it.bin].box[0];
+                    ref[1] = bld.nodes[it.bin].child[1]; box[1] = bld.nodes[it.bin].box[1];
+                    while (n < 8) {
+                        int best = -1;
+                        float bestArea = -1;
+                        for (int c = 0; c < n; ++c)  // 1. the largest subtree that is too big for one node
+                            if (ref[c] >= 0 && leafCount[ref[c]] > 8 && box[c].area() > bestArea) { bestArea = box[c].area(); best = c; }
+                        if (best < 0)
+                            for (int c = 0; c < n; ++c)  // 2. a small subtree all of whose leaves fit into the free slots
+                                if (ref[c] >= 0 && n - 1 + (int)leafCount[ref[c]] <= 8 && box[c].area() > bestArea) { bestArea = box[c].area(); best = c; }
+                        if (best < 0) break;
+                        const TmpNode &t = bld.nodes[ref[best]];
+                        ref[best] = t.child[0]; box[best] = t.box[0];
+                        ref[n] = t.child[1]; box[n] = t.box[1];
+                        ++n;
+                    }
+                    // drop the empty child a synthesised root may carry
+                    int m = 0;
+                    for (int c = 0; c < n; ++c)
+                        if (!(ref[c] < 0 && ((uint32_t)(~ref[c]) & 15u) == 0)) { ref[m] = ref[c]; box[m] = box[c]; ++m; }
+                    n = m;
+                    Box all;
+                    all.reset();
+                    for (int c = 0; c < n; ++c) all.grow(box[c].mn, box[c].mx);
+                    WideNode W;
+                    std::memset(&W, 0, sizeof(W));
+                    uint32_t expo[3];
+                    float origin[3], scale[3];
+                    for (int a = 0; a < 3; ++a) {
+                        // grid: origin = lo - delta, planes at origin + q * 2^e, q in [0, 255]. The device evaluates a plane's
+                        // ray distance as fma(2^23 + q, 2^e * idir, (origin - o) * idir - 2^23 * 2^e * idir), which is off by at
+                        // most half a grid step plus ~1e-7 |origin - o| in space: every child box is therefore widened by one
+                        // grid step beyond floor / ceil, and delta adds 1e-6 of the scene diagonal.
+                        const float ext = std::max(all.mx[a] - all.mn[a], 0.0f);
+                        int e = (int)std::ceil(std::log2(std::max((ext * 1.02f + 4e-6f * diag) / 250.0f, 1e-30f)));
+                        float sc, delta;
+                        for (;; ++e) {
+                            sc = std::ldexp(1.0f, e);
+                            delta = sc + 1e-6f * diag;
+                            if ((ext + 2 * delta) / sc <= 252.0f) break;
+                        }
+                        scale[a] = sc;
+                        origin[a] = std::nextafter(all.mn[a] - delta, -std::numeric_limits<float>::infinity());
+                        expo[a] = (uint32_t)(e + 127);
+                    }
+                    W.q[0] = origin[0]; W.q[1] = origin[1]; W.q[2] = origin[2];
+                    W.q[3] = u2f(expo[0] | (expo[1] << 8) | (expo[2] << 16) | ((uint32_t)n << 24));
+                    uint8_t *quant = reinterpret_cast<uint8_t *>(&W.q[12]);  // lox[8] loy[8] loz[8] hix[8] hiy[8] hiz[8]
+                    for (int c = 0; c < 8; ++c) {
+                        int32_t r = (int32_t)0x7FFFFFFF;  // empty slot: never a hit (inverted box), never pushed
+                        if (c < n) {
+                            if (ref[c] >= 0) {
+                                r = (int32_t)queue.size();
+                                queue.push_back(Item{ref[c], it.depth + 1});
+                            } else {
+                                r = leafRef(ref[c]);
+                            }
+                            for (int a = 0; a < 3; ++a) {
+                                const double lo = ((double)box[c].mn[a] - origin[a]) / scale[a], hi = ((double)box[c].mx[a] - origin[a]) / scale[a];
+                                const int qlo = std::max(0, (int)std::floor(lo) - 1), qhi = std::min(255, (int)std::ceil(hi) + 1);
+                                quant[8 * a + c] = (uint8_t)qlo;
+                                quant[24 + 8 * a + c] = (uint8_t)qhi;
+                            }
+                        } else {
+                            for (int a = 0; a < 3; ++a) {
+                                quant[8 * a + c] = 255;
+                                quant[24 + 8 * a + c] = 0;
+                            }
+                        }
+                        W.q[4 + c] = u2f((uint32_t)r);
+                    }
+                    out.push_back(W);
+                }
+                if (wideDepth <= kWideMaxDepth) {
+                    wideNodes.swap(out);
+                } else {
+                    wideDepth = 0;  // degenerate tree: the traversal stack could not hold it -- stay on the binary tree
+                }
+            }
+        }
         prims.resize(bprims.size());
         primGlobalId.resize(bprims.size());
         primInfo.resize(bprims.size());

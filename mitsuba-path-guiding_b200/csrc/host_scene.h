@@ -28,6 +28,8 @@ struct HostScene {
 
     // ---- compiled records
     std::vector<BvhNode> nodes;
+    std::vector<WideNode> wideNodes;     // 8-wide quantised tree over the same leaves (large meshes only; empty otherwise)
+    int wideDepth = 0;
     std::vector<PrimRecord> prims;       // BVH leaf order
     std::vector<uint32_t> primGlobalId;  // BVH order -> global primitive id
     std::vector<PrimInfo> primInfo;      // BVH order -> (shape, primitive index)

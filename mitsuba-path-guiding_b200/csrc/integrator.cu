@@ -90,7 +90,7 @@ struct Integrator {
     std::atomic<int> cancel{0};
 
     // device scene
-    DevBuf<float4> dNodes, dPrims, dRects;
+    DevBuf<float4> dNodes, dWideNodes, dPrims, dRects;
     DevBuf<ShapeRecord> dShapes;
     DevBuf<MeshRecord> dMeshes;
     DevBuf<float> dPositions, dNormals, dTexcoords, dAreaCdf, dEmitterCdf, dDensity;
@@ -137,6 +137,8 @@ struct Integrator {
     int sortBounces = std::getenv("B200PG_SORT_BOUNCES") ? std::atoi(std::getenv("B200PG_SORT_BOUNCES")) : 0;
     // persistent speculative traversal with per-lane refill (kernels.cu: traceQueueSpeculative): bit 0 = closest-hit queues of
     // bounces >= 1, bit 1 = shadow queues, bit 2 = camera rays too (coherent: the batch kernel is as good there)
+    // 8-ary quantised tree for large meshes (walked by the speculative kernels; the batch kernels keep the binary tree)
+    bool useWide = !(std::getenv("B200PG_WIDE") && std::atoi(std::getenv("B200PG_WIDE")) == 0);
     int traceSpec = std::getenv("B200PG_TRACE_SPEC") ? std::atoi(std::getenv("B200PG_TRACE_SPEC")) : 3;
     // denoiser feature buffers (denoiser.cpp:138-144): 3 float4 per pixel, allocated by set_option("feature_buffers", 1)
     bool featureBuffers = false;
@@ -233,6 +235,7 @@ struct Integrator {
         HostScene &H = *scene;
         dNodes.upload(reinterpret_cast<const float4 *>(H.nodes.data()), H.nodes.size() * 4, stream);
         dPrims.upload(reinterpret_cast<const float4 *>(H.prims.data()), H.prims.size() * 3, stream);
+        if (!H.wideNodes.empty()) dWideNodes.upload(reinterpret_cast<const float4 *>(H.wideNodes.data()), H.wideNodes.size() * 6, stream);
         dRects.upload(reinterpret_cast<const float4 *>(H.rects.data()), H.rects.size() * 8, stream);
         dShapes.upload(H.shapeRecs, stream);
         dMeshes.upload(H.meshes, stream);
@@ -250,6 +253,7 @@ struct Integrator {
         dPrimInfo.upload(H.primInfo, stream);
         dShadeTris.upload(reinterpret_cast<const float4 *>(H.shadeTris.data()), H.shadeTris.size() / 4, stream);
         S.nodes = dNodes.p; S.prims = dPrims.p; S.rects = dRects.p;
+        S.wideNodes = (H.wideNodes.empty() || !useWide) ? nullptr : dWideNodes.p;
         S.shapes = dShapes.p; S.meshes = dMeshes.p;
         S.positions = dPositions.p; S.normals = dNormals.p; S.texcoords = dTexcoords.p;
         S.indices = dIndices.p; S.areaCdf = dAreaCdf.p;
@@ -1226,6 +1230,10 @@ int b200pg_set_option(void *integ, const char *name, int value) {
     else if (n == "timing") self->timing = value != 0;
     else if (n == "sort_bounces") self->sortBounces = value;
     else if (n == "trace_spec") self->traceSpec = value;
+    else if (n == "wide_bvh") {
+        self->useWide = value != 0;
+        self->S.wideNodes = (self->scene->wideNodes.empty() || !self->useWide) ? nullptr : self->dWideNodes.p;
+    }
     else if (n == "overlap_shadow") self->overlapShadow = value != 0;
     else if (n == "lanes") self->lanes = std::max(1, std::min((int)Integrator::kMaxLanes, value));
     else if (n == "feature_buffers") {
@@ -1263,6 +1271,10 @@ int b200pg_scene_upload(void *integ, size_t *bytes) {
     };
     self->dNodes.upload(reinterpret_cast<const float4 *>(H.nodes.data()), H.nodes.size() * 4, self->stream);
     self->dPrims.upload(reinterpret_cast<const float4 *>(H.prims.data()), H.prims.size() * 3, self->stream);
+    if (!H.wideNodes.empty()) {
+        self->dWideNodes.upload(reinterpret_cast<const float4 *>(H.wideNodes.data()), H.wideNodes.size() * 6, self->stream);
+        total += H.wideNodes.size() * sizeof(WideNode);
+    }
     self->dRects.upload(reinterpret_cast<const float4 *>(H.rects.data()), H.rects.size() * 8, self->stream);
     total += H.nodes.size() * 64 + H.prims.size() * 48 + H.rects.size() * 128;
     up(self->dShapes, H.shapeRecs);

@@ -239,11 +239,31 @@ __global__ void __launch_bounds__(128) k_trace(DeviceScene S, const float4 *__re
 // ------------------------------------------------------------------------------------------
 static constexpr int kRefillBelow = 24;
 
-template <bool kAnyHit, bool kCount, typename Queue>
+// kWide: walk the 8-ary quantised tree (large meshes) instead of the binary one -- same leaves, same primitive tests.
+template <bool kWide>
+struct TraceStack;
+template <>
+struct TraceStack<false> {
+    int e[kTraceStack];
+    PG_DEV int step(const DeviceScene &S, int node, float3 o, float3 idir, float mint, float tmax, int &sp) {
+        return bvhNodeStep(S, node, o, idir, mint, tmax, e, sp);
+    }
+    PG_DEV int pop(int &sp, float) { return sp ? e[--sp] : kDoneNode; }
+};
+template <>
+struct TraceStack<true> {
+    WideEntry e[kWideStack];
+    PG_DEV int step(const DeviceScene &S, int node, float3 o, float3 idir, float mint, float tmax, int &sp) {
+        return wideNodeStep(S, node, o, idir, mint, tmax, e, sp);
+    }
+    PG_DEV int pop(int &sp, float tmax) { return widePop(e, sp, tmax); }
+};
+
+template <bool kAnyHit, bool kCount, bool kWide, typename Queue>
 PG_DEV void traceQueueSpeculative(const DeviceScene &S, Queue Q, uint32_t n, uint32_t *work, uint32_t &cntNodes, uint32_t &cntPrims,
                                   unsigned long long &cntRays) {
     constexpr unsigned kFull = 0xffffffffu;
-    int stack[kTraceStack];
+    TraceStack<kWide> stack;
     int sp = 0, node = kDoneNode, leaf = 0;
     uint32_t rayIdx = 0xFFFFFFFFu;
     float3 o = f3(0.0f), d = f3(0.0f), idir = f3(0.0f);
@@ -266,6 +286,7 @@ PG_DEV void traceQueueSpeculative(const DeviceScene &S, Queue Q, uint32_t n, uin
                 if (i < n && Q.fetch(i, o, d, mint, tmax)) {
                     rayIdx = i;
                     idir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                    if (kWide) idir = wideClampIdir(idir);
                     node = 0;
                     sp = 0;
                     leaf = 0;
@@ -282,10 +303,10 @@ PG_DEV void traceQueueSpeculative(const DeviceScene &S, Queue Q, uint32_t n, uin
         while (__any_sync(kFull, node >= 0 && leaf == 0)) {
             if (node >= 0) {
                 if (kCount) cntNodes++;
-                node = bvhNodeStep(S, node, o, idir, mint, tmax, stack, sp);
+                node = stack.step(S, node, o, idir, mint, tmax, sp);
                 if (node < 0 && node != kDoneNode && leaf == 0) {  // first leaf: postpone it, continue with the next subtree
                     leaf = node;
-                    node = sp ? stack[--sp] : kDoneNode;
+                    node = stack.pop(sp, tmax);
                 }
             }
         }
@@ -297,7 +318,7 @@ PG_DEV void traceQueueSpeculative(const DeviceScene &S, Queue Q, uint32_t n, uin
                 node = kDoneNode;
             } else if (node < 0 && node != kDoneNode) {
                 leaf = node;
-                node = sp ? stack[--sp] : kDoneNode;
+                node = stack.pop(sp, tmax);
             }
         }
         // ---- finished rays hand in their result and become idle
@@ -381,33 +402,33 @@ struct RayListQueue {  // stand-alone ray queries (b200pg_k_trace*): rays as {o,
                                   : make_float4(h.t, h.u, h.v, __uint_as_float(primGlobalId[h.prim]));
     }
 };
-template <bool kShadow, bool kCount>
+template <bool kShadow, bool kCount, bool kWide>
 __global__ void __launch_bounds__(128) k_trace_rays_spec(DeviceScene S, RayListQueue Q, uint32_t n, uint32_t *work, Counters *C) {
     unsigned long long rays = 0;
     uint32_t cn = 0, cp = 0;
-    traceQueueSpeculative<kShadow, kCount>(S, Q, n, work, cn, cp, rays);
+    traceQueueSpeculative<kShadow, kCount, kWide>(S, Q, n, work, cn, cp, rays);
     if (kCount) {
         warpAddU64(&C->nodesVisited, cn);
         warpAddU64(&C->primsTested, cp);
     }
 }
-template <bool kCount>
+template <bool kCount, bool kWide>
 __global__ void __launch_bounds__(128) k_trace_spec(DeviceScene S, ClosestQueue Q, const uint32_t *nPtr, uint32_t *work, Counters *C) {
     unsigned long long rays = 0;
     uint32_t cn = 0, cp = 0;
-    traceQueueSpeculative<false, kCount>(S, Q, *nPtr, work, cn, cp, rays);
+    traceQueueSpeculative<false, kCount, kWide>(S, Q, *nPtr, work, cn, cp, rays);
     warpAddU64(&C->normalRays, rays);
     if (kCount) {
         warpAddU64(&C->nodesVisited, cn);
         warpAddU64(&C->primsTested, cp);
     }
 }
-template <bool kCount>
+template <bool kCount, bool kWide>
 __global__ void __launch_bounds__(128) k_shadow_spec(DeviceScene S, ShadowRayQueue Q, const uint32_t *nPtr, uint32_t *work, Counters *C) {
     unsigned long long rays = 0;
     uint32_t cn = 0, cp = 0;
     const uint32_t n = *nPtr;
-    traceQueueSpeculative<true, kCount>(S, Q, n, work, cn, cp, rays);
+    traceQueueSpeculative<true, kCount, kWide>(S, Q, n, work, cn, cp, rays);
     // every queued shadow ray counts (the batch kernel counts empty intervals as well)
     if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&C->shadowRays, (unsigned long long)n);
     if (kCount) {
@@ -895,7 +916,8 @@ void launchTrace(const DeviceScene &S, const PathState &P, float4 *hits, const u
                  bool count, const SortArgs *sort, bool speculative, cudaStream_t st) {
     static int grid = persistentGrid(k_trace<false, false>, 128);
     static int gridKey = persistentGrid(k_trace<false, true>, 128);
-    static int gridSpec = persistentGrid(k_trace_spec<false>, 128);
+    static int gridSpec = persistentGrid(k_trace_spec<false, false>, 128);
+    static int gridWide = persistentGrid(k_trace_spec<false, true>, 128);
     const SortArgs none = {};
     if (sort) {
         if (count)
@@ -906,10 +928,13 @@ void launchTrace(const DeviceScene &S, const PathState &P, float4 *hits, const u
         k_bin_scatter<<<numSMs() * 4, 256, 0, st>>>(*sort, nPtr);
     } else if (speculative) {
         const ClosestQueue Q = {P.rayO, P.rayD, P.flags, hits};
-        if (count)
-            k_trace_spec<true><<<gridSpec, 128, 0, st>>>(S, Q, nPtr, work, C);
+        if (S.wideNodes) {
+            if (count) k_trace_spec<true, true><<<gridWide, 128, 0, st>>>(S, Q, nPtr, work, C);
+            else k_trace_spec<false, true><<<gridWide, 128, 0, st>>>(S, Q, nPtr, work, C);
+        } else if (count)
+            k_trace_spec<true, false><<<gridSpec, 128, 0, st>>>(S, Q, nPtr, work, C);
         else
-            k_trace_spec<false><<<gridSpec, 128, 0, st>>>(S, Q, nPtr, work, C);
+            k_trace_spec<false, false><<<gridSpec, 128, 0, st>>>(S, Q, nPtr, work, C);
     } else if (count)
         k_trace<true, false><<<grid, 128, 0, st>>>(S, P.rayO, P.rayD, P.flags, hits, nPtr, work, C, none);
     else
@@ -918,13 +943,17 @@ void launchTrace(const DeviceScene &S, const PathState &P, float4 *hits, const u
 void launchShadow(const DeviceScene &S, const ShadowQueue &Q, float4 *rad, const uint32_t *nPtr, uint32_t *work, Counters *C,
                   bool count, bool speculative, cudaStream_t st) {
     static int grid = persistentGrid(k_shadow<false>, 128);
-    static int gridSpec = persistentGrid(k_shadow_spec<false>, 128);
+    static int gridSpec = persistentGrid(k_shadow_spec<false, false>, 128);
+    static int gridWide = persistentGrid(k_shadow_spec<false, true>, 128);
     if (speculative) {
         const ShadowRayQueue R = {Q, rad};
-        if (count)
-            k_shadow_spec<true><<<gridSpec, 128, 0, st>>>(S, R, nPtr, work, C);
+        if (S.wideNodes) {
+            if (count) k_shadow_spec<true, true><<<gridWide, 128, 0, st>>>(S, R, nPtr, work, C);
+            else k_shadow_spec<false, true><<<gridWide, 128, 0, st>>>(S, R, nPtr, work, C);
+        } else if (count)
+            k_shadow_spec<true, false><<<gridSpec, 128, 0, st>>>(S, R, nPtr, work, C);
         else
-            k_shadow_spec<false><<<gridSpec, 128, 0, st>>>(S, R, nPtr, work, C);
+            k_shadow_spec<false, false><<<gridSpec, 128, 0, st>>>(S, R, nPtr, work, C);
     } else if (count)
         k_shadow<true><<<grid, 128, 0, st>>>(S, Q, rad, nPtr, work, C);
     else
@@ -963,15 +992,24 @@ void launchFlush(const ShadeArgs &A, cudaStream_t st) {
 void launchTraceRays(const DeviceScene &S, const float4 *rays, uint32_t n, float4 *hits, uint32_t *work, Counters *C, bool shadow,
                      bool count, bool speculative, cudaStream_t st) {
     static int grid = persistentGrid(k_trace_rays<false, false>, 128);
-    static int gridSpec = persistentGrid(k_trace_rays_spec<false, false>, 128);
+    static int gridSpec = persistentGrid(k_trace_rays_spec<false, false, false>, 128);
+    static int gridWide = persistentGrid(k_trace_rays_spec<false, false, true>, 128);
     if (speculative) {
         const RayListQueue Q = {rays, hits, S.primGlobalId, shadow};
-        if (shadow) {
-            if (count) k_trace_rays_spec<true, true><<<gridSpec, 128, 0, st>>>(S, Q, n, work, C);
-            else k_trace_rays_spec<true, false><<<gridSpec, 128, 0, st>>>(S, Q, n, work, C);
+        if (S.wideNodes) {
+            if (shadow) {
+                if (count) k_trace_rays_spec<true, true, true><<<gridWide, 128, 0, st>>>(S, Q, n, work, C);
+                else k_trace_rays_spec<true, false, true><<<gridWide, 128, 0, st>>>(S, Q, n, work, C);
+            } else {
+                if (count) k_trace_rays_spec<false, true, true><<<gridWide, 128, 0, st>>>(S, Q, n, work, C);
+                else k_trace_rays_spec<false, false, true><<<gridWide, 128, 0, st>>>(S, Q, n, work, C);
+            }
+        } else if (shadow) {
+            if (count) k_trace_rays_spec<true, true, false><<<gridSpec, 128, 0, st>>>(S, Q, n, work, C);
+            else k_trace_rays_spec<true, false, false><<<gridSpec, 128, 0, st>>>(S, Q, n, work, C);
         } else {
-            if (count) k_trace_rays_spec<false, true><<<gridSpec, 128, 0, st>>>(S, Q, n, work, C);
-            else k_trace_rays_spec<false, false><<<gridSpec, 128, 0, st>>>(S, Q, n, work, C);
+            if (count) k_trace_rays_spec<false, true, false><<<gridSpec, 128, 0, st>>>(S, Q, n, work, C);
+            else k_trace_rays_spec<false, false, false><<<gridSpec, 128, 0, st>>>(S, Q, n, work, C);
         }
     } else if (shadow) {
         if (count) k_trace_rays<true, true><<<grid, 128, 0, st>>>(S, rays, n, hits, work, C);

@@ -22,6 +22,17 @@ struct BvhNode {
 };
 static const int kLeafShift = 7;
 
+// Wide BVH node, 96 B = 6 x float4 = three 32-byte sectors: up to 8 children, boxes quantised to 8 bits on the node's own grid.
+//   q0     = origin.xyz (float), meta = ex | ey << 8 | ez << 16 | nChildren << 24   (e*: biased exponent of the grid step 2^e)
+//   q1, q2 = child[8] (int bits): >= 0 wide node index, < 0 leaf code (as in BvhNode), 0x7FFFFFFF empty slot
+//   q3..q5 = bytes lox[8] loy[8] loz[8] hix[8] hiy[8] hiz[8]: plane position = origin + q * 2^e
+// Built by collapsing the binary tree (host_scene.cpp); conservative: every child box is widened by >= 1 grid step.
+struct WideNode {
+    float q[24];
+};
+static const int kWideMaxDepth = 16;   // the traversal stack holds 7 * depth + postponed entries (device_scene.cuh: kWideStack)
+static const int32_t kWideEmpty = 0x7FFFFFFF;
+
 // Primitive record, 48 B = 3 x float4 (rows of a 3x4 affine map), stored in BVH leaf order.
 // One branch-free test serves both primitive kinds: with l(x) = M x + w,
 //     t = -l(o).z / (M d).z,   (u, v) = (l(o) + t M d).xy

@@ -84,6 +84,71 @@ struct RayState {
 };
 }  // namespace
 
+
+// ---- host replay of the device's wide-node visit (device_scene.cuh: wideNodeStep), operation for operation
+struct WideRay {
+    float o[3], d[3], id[3], mint, tmax;
+    int node, sp, maxSp = 0;
+    struct E { int ref; float tn; } stack[256];
+    uint32_t prim; float t;
+    uint32_t nodeSteps = 0, primTests = 0;
+    static float plane(uint32_t w, int byte, float s, float b) {
+        uint32_t q = (w >> (8 * byte)) & 0xFFu, bits = 0x4B000000u | q;
+        float f;
+        std::memcpy(&f, &bits, 4);
+        return std::fmaf(f, s, b);
+    }
+    int pop() {
+        while (sp) { --sp; if (stack[sp].tn <= tmax) return stack[sp].ref; }
+        return kDone;
+    }
+    void step(const pg::WideNode *nodes) {
+        const float *q = nodes[node].q;
+        nodeSteps++;
+        uint32_t meta; std::memcpy(&meta, &q[3], 4);
+        auto p2 = [](uint32_t e) { uint32_t b = e << 23; float f; std::memcpy(&f, &b, 4); return f; };
+        float s[3] = {p2(meta & 0xFF) * id[0], p2((meta >> 8) & 0xFF) * id[1], p2((meta >> 16) & 0xFF) * id[2]};
+        float b[3];
+        for (int a = 0; a < 3; ++a) b[a] = std::fmaf(-8388608.0f, s[a], (q[a] - o[a]) * id[a]);
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(&q[12]);  // 12 words: lox0 lox1 loy0 loy1 loz0 loz1 hix0 hix1 hiy0 hiy1 hiz0 hiz1
+        int best = kDone; float bestT = INFINITY;
+        for (int c = 0; c < 8; ++c) {
+            int ref; std::memcpy(&ref, &q[4 + c], 4);
+            int wi = c >> 2, by = c & 3;
+            float ax = plane(w[0 + wi], by, s[0], b[0]), cx = plane(w[6 + wi], by, s[0], b[0]);
+            float ay = plane(w[2 + wi], by, s[1], b[1]), cy = plane(w[8 + wi], by, s[1], b[1]);
+            float az = plane(w[4 + wi], by, s[2], b[2]), cz = plane(w[10 + wi], by, s[2], b[2]);
+            float tn = std::fmax(std::fmax(std::fmin(ax, cx), std::fmin(ay, cy)), std::fmax(std::fmin(az, cz), mint));
+            float tf = std::fmin(std::fmin(std::fmax(ax, cx), std::fmax(ay, cy)), std::fmin(std::fmax(az, cz), tmax));
+            bool hit = ref != 0x7FFFFFFF && tn <= tf * 1.0000004f;
+            bool better = hit && tn < bestT;
+            int oref = better ? best : ref; float ot = better ? bestT : tn;
+            if (hit && oref != kDone) { stack[sp].ref = oref; stack[sp].tn = ot; ++sp; maxSp = std::max(maxSp, sp); }
+            best = better ? ref : best; bestT = better ? tn : bestT;
+        }
+        node = best != kDone ? best : pop();
+    }
+    void leaf(const pg::PrimRecord *prims) {
+        uint32_t code = (uint32_t)(~node);
+        uint32_t first = code >> pg::kLeafShift, count = code & 7u, rectMask = (code >> 3) & 15u;
+        for (uint32_t i = 0; i < count; ++i) {
+            const float *r = prims[first + i].q;
+            primTests++;
+            float loz = r[8] * o[0] + r[9] * o[1] + r[10] * o[2] + r[11];
+            float ldz = r[8] * d[0] + r[9] * d[1] + r[10] * d[2];
+            float tt = -loz / ldz;
+            if (tt >= mint && tt <= tmax) {
+                float lox = r[0] * o[0] + r[1] * o[1] + r[2] * o[2] + r[3], loy = r[4] * o[0] + r[5] * o[1] + r[6] * o[2] + r[7];
+                float ldx = r[0] * d[0] + r[1] * d[1] + r[2] * d[2], ldy = r[4] * d[0] + r[5] * d[1] + r[6] * d[2];
+                float u = lox + ldx * tt, v = loy + ldy * tt;
+                bool isRect = (rectMask >> i) & 1u;
+                bool ok = isRect ? (std::fabs(u) <= 1 && std::fabs(v) <= 1) : (u >= 0 && v >= 0 && u + v <= 1.0f);
+                if (ok) { prim = first + i; tmax = tt; t = tt; }
+            }
+        }
+        node = pop();
+    }
+};
 extern "C" {
 // Per-ray counters + hit (for generating secondary rays): out arrays may be null.
 void bvhsim_trace(void *h, const float *rays, size_t n, int anyHit, int cull, uint32_t *nodeSteps, uint32_t *primTests,
@@ -347,5 +412,37 @@ void bvhsim_warps(void *h, const float *rays, size_t n, int anyHit, int cull, in
         out[6] = refills;
     }
     out[0] = laneNode; out[1] = warpNode; out[2] = lanePrim; out[3] = warpPrim; out[4] = maxRay; out[5] = rounds;
+}
+
+// closest hit through the wide tree; out: per-ray node visits, primitive tests, hit; returns the largest stack depth seen
+int bvhsim_trace_wide(void *h, const float *rays, size_t n, uint32_t *nodeSteps, uint32_t *primTests, float *tOut, uint32_t *primOut) {
+    const pg::HostScene &H = ((SceneHandle *)h)->host;
+    if (H.wideNodes.empty()) return -1;
+    int maxSp = 0;
+#pragma omp parallel for schedule(dynamic, 1024) reduction(max : maxSp)
+    for (size_t i = 0; i < n; ++i) {
+        WideRay R;
+        const float *r = rays + 8 * i;
+        for (int a = 0; a < 3; ++a) { R.o[a] = r[a]; R.d[a] = r[4 + a]; R.id[a] = 1.0f / R.d[a]; R.id[a] = std::copysign(std::fmin(std::fabs(R.id[a]), 1e25f), R.id[a]); }
+        R.mint = r[3]; R.tmax = r[7]; R.node = 0; R.sp = 0; R.prim = 0xFFFFFFFFu; R.t = R.tmax;
+        while (R.node != kDone) {
+            while (R.node >= 0) R.step(H.wideNodes.data());
+            if (R.node == kDone) break;
+            R.leaf(H.prims.data());
+        }
+        if (nodeSteps) nodeSteps[i] = R.nodeSteps;
+        if (primTests) primTests[i] = R.primTests;
+        if (tOut) tOut[i] = R.prim == 0xFFFFFFFFu ? INFINITY : R.t;
+        if (primOut) primOut[i] = R.prim;
+        maxSp = std::max(maxSp, R.maxSp);
+    }
+    return maxSp;
+}
+void bvhsim_wide_info(void *h, uint64_t *out) {
+    const pg::HostScene &H = ((SceneHandle *)h)->host;
+    out[0] = H.wideNodes.size(); out[1] = (uint64_t)H.wideDepth; out[2] = H.nodes.size();
+    uint64_t kids = 0;
+    for (auto &w : H.wideNodes) { uint32_t m; std::memcpy(&m, &w.q[3], 4); kids += m >> 24; }
+    out[3] = kids;
 }
 }
