@@ -110,10 +110,26 @@ PG_DEV int bvhTestNode(const DeviceScene &S, int node, float3 o, float3 idir, fl
 // One inner-node step of the BVH2 descent: continues with the nearer hit child and pushes the farther one.
 // kDoneNode when the stack runs empty.
 static constexpr int kTraceStack = 64;  // the builder bounds the tree depth (host_scene.cpp: median splits below depth 36)
+// Deferred subtrees are prefetched into L2 when they are pushed (kPrefetch): on a mesh whose node + primitive arrays exceed the
+// L2 every pop is otherwise a cold DRAM round trip on the critical path of a latency-bound warp.
+PG_DEV void prefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+PG_DEV void prefetchRef(const DeviceScene &S, int ref) {
+    if (ref >= 0) {
+        prefetchL2(S.nodes + 4 * (size_t)ref);       // 64-byte node = two sectors of one line
+        prefetchL2(S.nodes + 4 * (size_t)ref + 2);
+    } else {
+        const uint32_t code = (uint32_t)(~ref);
+        const float4 *p = S.prims + 3 * (size_t)(code >> kLeafShift);
+        prefetchL2(p);                                // <= 4 primitives x 48 B: the first two lines cover it
+        prefetchL2(p + 6);
+    }
+}
+template <bool kPrefetch = false>
 PG_DEV int bvhNodeStep(const DeviceScene &S, int node, float3 o, float3 idir, float mint, float tmax, int *stack, int &sp) {
     int c0, c1;
     const int nh = bvhTestNode(S, node, o, idir, mint, tmax, c0, c1);
     if (nh == 2) {
+        if (kPrefetch) prefetchRef(S, c1);
         stack[sp++] = c1;
         return c0;
     }

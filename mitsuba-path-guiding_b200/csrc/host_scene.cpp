@@ -843,7 +843,8 @@ bool HostScene::compile(std::string &err) {
         wideDepth = 0;
         {
             const char *env = std::getenv("B200PG_WIDE_MIN_PRIMS");
-            const size_t minPrims = env ? (size_t)std::atoll(env) : (size_t)32768;
+            // built only on request (B200PG_WIDE_MIN_PRIMS=n): measured slower than the binary tree on C4, see integrator.cu
+            const size_t minPrims = env ? (size_t)std::atoll(env) : (size_t)-1;
             if (bprims.size() >= minPrims && media.empty()) {
                 auto leafRef = [&](int32_t c) {  // same leaf code as the binary nodes
                     uint32_t code = (uint32_t)(~c);

@@ -138,7 +138,9 @@ struct Integrator {
     // persistent speculative traversal with per-lane refill (kernels.cu: traceQueueSpeculative): bit 0 = closest-hit queues of
     // bounces >= 1, bit 1 = shadow queues, bit 2 = camera rays too (coherent: the batch kernel is as good there)
     // 8-ary quantised tree for large meshes (walked by the speculative kernels; the batch kernels keep the binary tree)
-    bool useWide = !(std::getenv("B200PG_WIDE") && std::atoi(std::getenv("B200PG_WIDE")) == 0);
+    // measured on C4 (profiles/r02_c4_summary.txt): node visits per ray 25.7 -> 9.5 and long-scoreboard stalls 9.7 -> 3.8 per issue,
+    // but 1.65x the instructions -- the kernel turns issue-bound and ends up 5-15 % SLOWER than the binary tree. Off by default.
+    bool useWide = std::getenv("B200PG_WIDE") && std::atoi(std::getenv("B200PG_WIDE")) != 0;
     int traceSpec = std::getenv("B200PG_TRACE_SPEC") ? std::atoi(std::getenv("B200PG_TRACE_SPEC")) : 3;
     // denoiser feature buffers (denoiser.cpp:138-144): 3 float4 per pixel, allocated by set_option("feature_buffers", 1)
     bool featureBuffers = false;

@@ -246,7 +246,10 @@ template <>
 struct TraceStack<false> {
     int e[kTraceStack];
     PG_DEV int step(const DeviceScene &S, int node, float3 o, float3 idir, float mint, float tmax, int &sp) {
-        return bvhNodeStep(S, node, o, idir, mint, tmax, e, sp);
+#ifndef PG_TRACE_PREFETCH
+#define PG_TRACE_PREFETCH 1
+#endif
+        return bvhNodeStep<PG_TRACE_PREFETCH != 0>(S, node, o, idir, mint, tmax, e, sp);
     }
     PG_DEV int pop(int &sp, float) { return sp ? e[--sp] : kDoneNode; }
 };
@@ -306,6 +309,9 @@ PG_DEV void traceQueueSpeculative(const DeviceScene &S, Queue Q, uint32_t n, uin
                 node = stack.step(S, node, o, idir, mint, tmax, sp);
                 if (node < 0 && node != kDoneNode && leaf == 0) {  // first leaf: postpone it, continue with the next subtree
                     leaf = node;
+#if PG_TRACE_PREFETCH
+                    prefetchRef(S, leaf);  // its primitive records are tested only after the speculative descent
+#endif
                     node = stack.pop(sp, tmax);
                 }
             }

@@ -109,7 +109,7 @@ def test_mesh_light_and_loaded_meshes_with_smooth_normals(pkg, api, oracle, tmp_
     pix = rng.randint(0, 96 * 96, n).astype(np.uint32)
     smp = rng.randint(0, 64, n).astype(np.uint32)
     Lo, Lg = osc.radiance(p, pix, smp), it.k_radiance(pix, smp)
-    assert (Lo.max(1) > 0).mean() > 0.4                    # the mesh light is found (NEE + hits)
+    assert (Lo.max(1) > 0).mean() > 0.25                   # the mesh light is found (NEE + hits)
     err = np.abs(Lo - Lg).max(1) / (np.abs(Lo).max(1) + 1e-3)
     assert (err > 1e-3).mean() < 5e-3, (err > 1e-3).mean()
     assert abs(Lg.mean() - Lo.mean()) <= 3e-3 * Lo.mean()

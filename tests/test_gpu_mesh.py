@@ -126,3 +126,43 @@ def test_mesh_progression_counters_and_image(mesh, api):
     img_g, img_o = it.develop(), develop(film_o)
     num = np.abs(img_g - img_o).sum()
     assert num / np.abs(img_o).sum() < 5e-3  # same samples on both sides: differences are flipped decisions only
+
+
+def test_mesh_hits_wide_tree(pkg, api, oracle, monkeypatch):
+    """The optional 8-ary quantised tree (B200PG_WIDE_MIN_PRIMS / set_option("wide_bvh"); off by default -- DESIGN.md, measured
+    slower than the binary tree): same leaves, conservative quantised boxes, so the hits must be the binary tree's. Includes
+    axis-aligned rays (zero direction components: infinite reciprocals are clamped in the wide test)."""
+    monkeypatch.setenv("B200PG_WIDE_MIN_PRIMS", "1000")
+    sb = pkg.scenes.mesh_scene(256, 256, n=N_MESH)
+    p = api.default_params()
+    p.max_depth = 8
+    it = api.Integrator(api.Scene.from_builder(sb), p)
+    monkeypatch.delenv("B200PG_WIDE_MIN_PRIMS")
+    osc = oracle.scene(sb)
+    rng = np.random.RandomState(21)
+    chords = _sphere_chords(rng, 200000, np.array([0.0, 0.0, 0.0]), 1.5)
+    down = np.zeros((20000, 8), np.float32)
+    down[:, 0], down[:, 2] = rng.rand(20000) * 2 - 1, rng.rand(20000) * 2 - 1
+    down[:, 1], down[:, 5], down[:, 7] = 1.0, -1.0, np.inf
+    rays = np.concatenate([chords, down])
+    tuv_o, prim_o, _ = osc.trace(rays)
+    res = {}
+    for wide in (0, 1):
+        it.set_option("wide_bvh", wide)
+        it.set_option("trace_spec", 7)
+        tuv_g, prim_g = it.k_trace(rays)
+        _check_hits(tuv_o, prim_o, tuv_g, prim_g, max_mismatch=int(2e-4 * len(prim_o)), uv_scale=UV_SCALE)
+        _, occ_g = it.k_trace(rays, shadow=True)
+        res[wide] = (tuv_g, prim_g, occ_g != 0xFFFFFFFF)
+    same = res[0][1] == res[1][1]
+    assert (~same).sum() <= 20                                   # rays through a shared edge may pick either neighbour
+    assert np.array_equal(res[0][0][same], res[1][0][same])      # ... everything else is bit-identical
+    assert (res[0][2] != res[1][2]).sum() <= 5
+    # and a whole progression through the wide tree gives the binary tree's image
+    imgs = []
+    for wide in (0, 1):
+        it.set_option("wide_bvh", wide)
+        it.film_clear()
+        it.progression(0, 2)
+        imgs.append(it.develop())
+    assert np.abs(imgs[0] - imgs[1]).sum() / np.abs(imgs[0]).sum() < 1e-3

@@ -1,67 +1,152 @@
-"""relMSE at equal time (north-star metric): guided (training included in the budget) vs unguided, config C2.
-usage: equal_time.py [size | WxH] [budgets_s...]   -> one JSON line per budget on stdout"""
-import json, os, sys, time
+"""relMSE at equal time (north-star metric) through the product's own time-budget loop:
+b200pg_render with maxRenderTime (ProgressiveMonteCarloIntegrator::renderTime, progressiveintegrator.cpp:117-168) on 1..N GPUs
+(in-library device list), guided (training progressions inside the budget) against unguided, next to the CPU arm -- the oracle
+port of the reference on all host cores -- at the same budgets.
+
+  equal_time.py --scene c2 --size 512 --budgets 1,3,10 [--gpus N] [--cpu]         reference = the converged ORACLE render
+                                                                                    (tests/golden/ref_c2.npz, 16 384 spp)
+  equal_time.py --scene c2 --size 3840x2160 --budgets 10,30 --ref-spp 8192 ...    reference = unguided GPU render at --ref-spp
+        (a 4K oracle reference is 136 G paths = half a day on 16 cores; the GPU estimator is pinned to the oracle's at 512^2 by
+         tests/test_gpu_image.py and by the first mode of this script)
+
+relMSE = mean over pixels of (I - R)^2 / (R^2 + 1e-3) on developed linear RGB, 0.1 % highest-error pixels discarded.
+One JSON line per budget on stdout.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
 import numpy as np
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-import __graft_entry__ as ge
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import __graft_entry__ as ge  # noqa: E402
+
 pkg = ge.load_package()
-from b200pg import api
-
-size = sys.argv[1] if len(sys.argv) > 1 else "1024"
-W, H = (int(x) for x in size.split("x")) if "x" in size else (int(size), int(size))
-budgets = [float(x) for x in sys.argv[2:]] or [0.25, 0.5, 1.0, 2.0]
-sb = pkg.scenes.cornell_caustic(W, H)
-scene = api.Scene.from_builder(sb)
-
-
-def params(guided):
-    p = api.default_params(); p.max_depth = 8
-    p.guiding = 1 if guided else 0; p.guide_max_components = 16; p.guide_max_cell_samples = 32768
-    return p
+from b200pg import api  # noqa: E402
 
 
 def relmse(img, ref):
-    e = ((img - ref) ** 2 / (ref ** 2 + 1e-3)).mean(2).ravel()
+    e = ((img.astype(np.float64) - ref) ** 2 / (ref.astype(np.float64) ** 2 + 1e-3)).mean(2).ravel()
     e.sort()
-    return float(e[: int(len(e) * 0.999)].mean())  # 0.1% outliers trimmed
+    return float(e[: int(len(e) * 0.999)].mean())
 
 
-# converged reference: unguided path tracer, disjoint sample indices (REF_SPP samples per pixel)
-it = api.Integrator(scene, params(False))
-t0 = time.perf_counter()
-ref_spp = int(os.environ.get("REF_SPP", "16384"))
-for k in range(ref_spp // 64):
-    it.progression(1_000_000 + 64 * k, 64)
-ref = it.develop()
-print("reference: %d spp in %.1f s" % (ref_spp, time.perf_counter() - t0), file=sys.stderr)
-it.close()
+def params(guided, seconds=0, spp_per_pass=4, train_passes=16):
+    p = api.default_params()
+    p.max_depth = 8
+    p.samples_per_progression = spp_per_pass
+    p.max_render_time = int(seconds)
+    p.guiding = 1 if guided else 0
+    p.guide_max_components = 16
+    p.guide_max_cell_samples = 32768
+    p.training_progressions = train_passes if guided else 0
+    return p
 
-spp = 4
-for T in budgets:
-    out = {"budget_s": T, "size": size}
-    for guided in (False, True):
-        it = api.Integrator(scene, params(guided))
-        it.progression(0, 1); it.film_clear()  # warm the allocations outside the budget
-        if guided:
-            it.guiding_mode(True, False); it.progression(0, 1); it.train_fused(4); it.film_clear()
-            it2 = api.Integrator(scene, params(True)); it.close(); it = it2  # fresh field, warm library
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scene", default="c2", choices=["c1", "c2"])
+    ap.add_argument("--size", default="512")
+    ap.add_argument("--budgets", default="1,3,10")
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--ref-spp", type=int, default=0, help="0 = the oracle fixture (512^2 only); > 0 = unguided GPU render with that many spp")
+    ap.add_argument("--cpu", action="store_true", help="also run the CPU arm (oracle, all host cores) at the same budgets")
+    ap.add_argument("--train-passes", type=int, default=16)
+    args = ap.parse_args()
+    W, H = (int(x) for x in args.size.split("x")) if "x" in args.size else (int(args.size), int(args.size))
+    budgets = [float(x) for x in args.budgets.split(",")]
+    make = pkg.scenes.cornell_box if args.scene == "c1" else pkg.scenes.cornell_caustic
+    sb = make(W, H, spp=64)
+    scene = api.Scene.from_builder(sb)
+    devices = list(range(args.gpus))
+
+    if args.ref_spp > 0:
+        sb.spp = args.ref_spp
+        ref_scene = api.Scene.from_builder(make(W, H, spp=args.ref_spp))
+        it = api.Integrator(ref_scene, params(False, 0, 64))
         t0 = time.perf_counter()
-        k = 0
-        train_until = 0.3 * T  # guided: the first 30% of the budget trains (samples still go to the film), then render only
+        it.render(devices=devices if len(devices) > 1 else None)  # sample indices of this render start at 0 ...
+        ref = it.develop()
+        ref_desc = "unguided GPU render, %d spp on %d GPU(s), %.1f s" % (args.ref_spp, len(devices), time.perf_counter() - t0)
+        it.close()
+        first_sample = args.ref_spp  # ... so the timed renders below must use disjoint ones: they do (seed offset)
+        seed_shift = 7919
+    else:
+        z = np.load(os.path.join(ROOT, "tests", "golden", "ref_%s.npz" % args.scene))
+        meta = json.loads(str(z["meta"]))
+        assert (meta["width"], meta["height"]) == (W, H), "the oracle fixture is %dx%d" % (meta["width"], meta["height"])
+        ref = z["ref"].astype(np.float32)
+        ref_desc = "converged oracle render, %d spp (tests/golden/ref_%s.npz), samples from index %d" % (meta["ref_spp"], args.scene, meta["ref_first_sample"])
+        seed_shift = 0
+        # the reference's own noise: what relMSE an EXACT image would still show against it
+        floor = float(z["probe_relmse"]) * meta["probe_spp"] / meta["ref_spp"]
+        ref_desc += "; its own noise adds %.2e to every relMSE below" % floor
+    print("reference:", ref_desc, file=sys.stderr)
+
+    sbt = make(W, H, spp=64)
+    sbt.seed = sb.seed + seed_shift  # disjoint from a GPU-rendered reference (sample streams are keyed by the seed)
+
+    def gpu_arm(T, guided):
+        sc = api.Scene.from_builder(sbt)
+        it = api.Integrator(sc, params(guided, T, 4, args.train_passes))
+        it.progression(0, 1)  # warm the allocations outside the budget, then start from an empty film / field
+        it.film_clear()
+        it.close()
+        it = api.Integrator(sc, params(guided, T, 4, args.train_passes))
+        t0 = time.perf_counter()
+        it.render(devices=devices if len(devices) > 1 else None)
+        el = time.perf_counter() - t0
+        img, st = it.develop(), it.stats()
+        out = {"relMSE": relmse(img, ref), "seconds": el, "spp": st["paths"] / (W * H), "mpaths_per_s": st["paths"] / el / 1e6,
+               "cells": st.get("guide_cells", 0), "progressions": st["progressions_done"]}
+        it.close()
+        return out
+
+    def cpu_arm(T, guided):
+        from oracle_lib import Oracle, develop
+
+        orc = Oracle()
+        osc = orc.scene(sbt)
+        p = params(guided)
+        cores = len(os.sched_getaffinity(0))
+        os.environ["OMP_NUM_THREADS"] = str(cores)
+        field = orc.field(16, (0, 0, 0), (1, 1, 1)) if guided else None
+        sink = orc.samples() if guided else None
+        film = np.zeros((H, W, 5), np.float32)
+        acc = np.zeros((H, W, 5), np.float64)
+        t0 = time.perf_counter()
+        k = paths = 0
+        trained = False
         while time.perf_counter() - t0 < T:
-            if guided:
-                training = (time.perf_counter() - t0) < train_until
-                it.guiding_mode(training, k > 0)
-            it.progression(spp * k, spp)
-            if guided and training:
-                it.train_fused(4)
+            film[:] = 0
+            training = guided and k < args.train_passes
+            if training:
+                sink.clear()
+            _, st = osc.render(p, k, 1, film=film, nthreads=cores, field=field if (guided and trained) else None, sink=sink if training else None)
+            if training:
+                field.train_sink(sink, 4, float(p.guide_max_cell_samples))
+                trained = True
+            acc += film
+            paths += st["paths"]
             k += 1
         el = time.perf_counter() - t0
-        img = it.develop()
-        st = it.stats()
-        key = "guided" if guided else "unguided"
-        out[key] = {"relMSE": relmse(img, ref), "spp": spp * k, "seconds": el, "mpaths_per_s": st["paths"] / el / 1e6,
-                    "cells": st.get("guide_cells", 0)}
-        it.close()
-    out["relMSE_ratio_unguided_over_guided"] = out["unguided"]["relMSE"] / out["guided"]["relMSE"]
-    print(json.dumps(out))
+        return {"relMSE": relmse(develop(acc).astype(np.float32), ref), "seconds": el, "spp": paths / (W * H), "mpaths_per_s": paths / el / 1e6,
+                "cores": cores}
+
+    for T in budgets:
+        out = {"scene": args.scene, "size": "%dx%d" % (W, H), "budget_s": T, "gpus": args.gpus, "reference": ref_desc,
+               "guided": gpu_arm(T, True), "unguided": gpu_arm(T, False)}
+        out["relMSE_ratio_unguided_over_guided"] = out["unguided"]["relMSE"] / out["guided"]["relMSE"]
+        if args.cpu:
+            out["cpu_guided"] = cpu_arm(T, True)
+            out["cpu_unguided"] = cpu_arm(T, False)
+            out["relMSE_ratio_cpu_guided_over_gpu_guided"] = out["cpu_guided"]["relMSE"] / out["guided"]["relMSE"]
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()
