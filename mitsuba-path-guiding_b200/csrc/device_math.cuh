@@ -31,6 +31,52 @@ PG_DEV void stStream(T *p, T v) {
 #endif
 }
 
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256, PTX ld/st.global.v8.f32). A scattered record costs the L1TEX data pipe
+// one wavefront per (instruction, cache line) pair -- a divergent warp's LDG.128 is ~32 of them -- so a 32-byte-aligned 64-byte
+// BVH node read as two 256-bit loads instead of four 128-bit ones halves the pipe time of a node visit (the traversal and the
+// shade stage are bound by that pipe, profiles/r02_*). Addresses must be 32-byte aligned.
+struct __align__(32) F8 {
+    float4 a, b;
+};
+#ifndef PG_LD256
+#define PG_LD256 1  // 0 = two 128-bit loads (A/B runs)
+#endif
+PG_DEV F8 ldg256(const float4 *p) {  // read-only data (scene, guiding field)
+    F8 r;
+#if PG_LD256
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+        : "l"(p));
+#else
+    r.a = __ldg(p);
+    r.b = __ldg(p + 1);
+#endif
+    return r;
+}
+PG_DEV F8 ldStream256(const float4 *p) {  // streamed-once data (evict-first)
+    F8 r;
+#if PG_LD256
+    asm volatile("ld.global.cs.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+                 : "l"(p)
+                 : "memory");
+#else
+    r.a = ldStream(p);
+    r.b = ldStream(p + 1);
+#endif
+    return r;
+}
+PG_DEV void stStream256(float4 *p, float4 a, float4 b) {
+#if PG_LD256
+    asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x),
+                 "f"(b.y), "f"(b.z), "f"(b.w)
+                 : "memory");
+#else
+    stStream(p, a);
+    stStream(p + 1, b);
+#endif
+}
+
 static constexpr float kEpsilon = 1e-4f;        // include/mitsuba/core/constants.h:28
 static constexpr float kShadowEpsilon = 1e-3f;  // constants.h:29
 static constexpr float kPi = 3.14159265358979323846f;

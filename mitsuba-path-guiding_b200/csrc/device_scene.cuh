@@ -19,7 +19,8 @@ namespace pg {
 struct DeviceScene {
     const float4 *nodes;
     const float4 *wideNodes;  // 6 x float4 per node (pg_types.h: WideNode), nullptr when the scene has no wide tree
-    const float4 *prims;
+    const float4 *primPlanes;  // per primitive slot: plane row of the affine map (16 B)
+    const float4 *primRows;    // per primitive slot: the two (u, v) rows (32 B)
     const float4 *rects;
     const ShapeRecord *shapes;
     const MeshRecord *meshes;
@@ -81,10 +82,8 @@ PG_DEV float2 slabPair(float lo, float hi, float o, float idir) {
 // nearer (or only) hit child, c1 = the farther one.
 static constexpr int kDoneNode = (int)0x80000000;  // ~kDoneNode is not a valid leaf code
 PG_DEV int bvhTestNode(const DeviceScene &S, int node, float3 o, float3 idir, float mint, float tmax, int &c0, int &c1) {
-    const float4 n0 = __ldg(S.nodes + 4 * node + 0);
-    const float4 n1 = __ldg(S.nodes + 4 * node + 1);
-    const float4 n2 = __ldg(S.nodes + 4 * node + 2);
-    const float4 n3 = __ldg(S.nodes + 4 * node + 3);
+    const F8 lo = ldg256(S.nodes + 4 * node), hi = ldg256(S.nodes + 4 * node + 2);  // 64-byte node = 2 x LDG.256
+    const float4 n0 = lo.a, n1 = lo.b, n2 = hi.a, n3 = hi.b;
     // slabs; fminf/fmaxf drop NaNs from 0*inf
     const float2 x0 = slabPair(n0.x, n0.y, o.x, idir.x), y0 = slabPair(n0.z, n0.w, o.y, idir.y), z0 = slabPair(n2.x, n2.y, o.z, idir.z);
     const float2 x1 = slabPair(n1.x, n1.y, o.x, idir.x), y1 = slabPair(n1.z, n1.w, o.y, idir.y), z1 = slabPair(n2.z, n2.w, o.z, idir.z);
@@ -119,9 +118,7 @@ PG_DEV void prefetchRef(const DeviceScene &S, int ref) {
         prefetchL2(S.nodes + 4 * (size_t)ref + 2);
     } else {
         const uint32_t code = (uint32_t)(~ref);
-        const float4 *p = S.prims + 3 * (size_t)(code >> kLeafShift);
-        prefetchL2(p);                                // <= 4 primitives x 48 B: the first two lines cover it
-        prefetchL2(p + 6);
+        prefetchL2(S.primPlanes + (code >> kLeafShift));  // <= 4 planes x 16 B, 32-byte aligned: one line
     }
 }
 template <bool kPrefetch = false>
@@ -212,20 +209,29 @@ PG_DEV int wideNodeStep(const DeviceScene &S, int node, float3 o, float3 idir, f
 
 // All primitives of one leaf (<= 4): the branch-free affine test that serves rectangles and triangles alike.
 // Returns true on the first accepted hit in any-hit mode.
+// The record is split (pg_types.h): the plane row {M_z, w_z} of all primitives in `planes` (16 B each; a leaf starts at an even
+// index, so two neighbouring planes are one aligned 256-bit load), the two (u, v) rows in `rows` (32 B, fetched only for a
+// primitive whose plane distance falls inside the ray interval). Same arithmetic as one 48-byte record.
 template <bool kAnyHit, bool kCount>
 PG_DEV bool bvhLeafStep(const DeviceScene &S, int node, float3 o, float3 d, float mint, float &tmax, Hit &hit, uint32_t *cntPrims) {
     const uint32_t code = (uint32_t)(~node);
     const uint32_t first = code >> kLeafShift, count = code & 7u, rectMask = (code >> 3) & 15u;
-    for (uint32_t i = 0; i < count; ++i) {
-        const float4 r0 = __ldg(S.prims + 3 * (first + i));
-        const float4 r1 = __ldg(S.prims + 3 * (first + i) + 1);
-        const float4 r2 = __ldg(S.prims + 3 * (first + i) + 2);
+    F8 pl[2];
+    pl[0] = ldg256(S.primPlanes + first);
+    pl[1] = pl[0];
+    if (count > 2) pl[1] = ldg256(S.primPlanes + first + 2);
+#pragma unroll
+    for (uint32_t i = 0; i < 4; ++i) {
+        if (i >= count) break;
+        const float4 r2 = (i & 1u) ? pl[i >> 1].b : pl[i >> 1].a;
         if (kCount) (*cntPrims)++;
         // local = M o + w, local direction = M d (rectangle.cpp:125-133 for rectangles)
         const float loz = r2.x * o.x + r2.y * o.y + r2.z * o.z + r2.w;
         const float ldz = r2.x * d.x + r2.y * d.y + r2.z * d.z;
         const float t = -loz / ldz;
         if (t >= mint && t <= tmax) {
+            const F8 uv = ldg256(S.primRows + 2 * (size_t)(first + i));
+            const float4 r0 = uv.a, r1 = uv.b;
             const float lox = r0.x * o.x + r0.y * o.y + r0.z * o.z + r0.w;
             const float loy = r1.x * o.x + r1.y * o.y + r1.z * o.z + r1.w;
             const float ldx = r0.x * d.x + r0.y * d.y + r0.z * d.z;
@@ -282,8 +288,9 @@ struct Intersection {
 };
 
 PG_DEV void fillIntersection(const DeviceScene &S, float3 o, float3 d, const Hit &h, Intersection &its) {
-    const float4 *T = S.shadeTris + 6 * (size_t)h.prim;
-    const float4 r0 = __ldg(T), r1 = __ldg(T + 1), r2 = __ldg(T + 2), r3 = __ldg(T + 3), r4 = __ldg(T + 4);
+    const float4 *T = S.shadeTris + 6 * (size_t)h.prim;  // 96-byte record = 3 x LDG.256
+    const F8 t01 = ldg256(T), t23 = ldg256(T + 2), t45 = ldg256(T + 4);
+    const float4 r0 = t01.a, r1 = t01.b, r2 = t23.a, r3 = t23.b, r4 = t45.a;
     const uint32_t flags = __float_as_uint(r1.w);
     its.shape = (int)__float_as_uint(r0.w);
     its.bsdf = (int)__float_as_uint(r3.w);
@@ -301,7 +308,7 @@ PG_DEV void fillIntersection(const DeviceScene &S, float3 o, float3 d, const Hit
         if (!isZero(faceNormal)) faceNormal = faceNormal / len;
         dpdu = side1;
         if (flags & 2u) {
-            const float4 r5 = __ldg(T + 5);
+            const float4 r5 = t45.b;
             const float3 n0 = f3(r3.x, r3.y, r3.z), n1 = f3(r4.x, r4.y, r4.z), n2 = f3(r5.x, r5.y, r5.z);
             shN = normalize(n0 * b.x + n1 * b.y + n2 * b.z);
             if (dot(faceNormal, shN) < 0) faceNormal = -faceNormal;

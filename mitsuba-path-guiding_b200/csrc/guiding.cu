@@ -824,16 +824,34 @@ __global__ void __launch_bounds__(256) k_guide_query(GuideDevice G, const float 
                                                      const float *__restrict__ u, uint32_t n, float *__restrict__ outPdf,
                                                      float *__restrict__ outDir, float *__restrict__ outSpdf,
                                                      uint32_t *__restrict__ outCell) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float3 p = ld3(pos + 3 * (size_t)i), w = ld3(dir + 3 * (size_t)i);
-        const uint32_t c = guideLookup(G, p);
-        outCell[i] = c;
-        outPdf[i] = guidePdf(G, c, w);
-        const float3 d = guideSample(G, c, u[3 * (size_t)i], u[3 * (size_t)i + 1], u[3 * (size_t)i + 2]);
-        outDir[3 * (size_t)i] = d.x;
-        outDir[3 * (size_t)i + 1] = d.y;
-        outDir[3 * (size_t)i + 2] = d.z;
-        outSpdf[i] = guidePdf(G, c, d);
+    // the warp-cooperative routines the shade stage uses (all lanes of a warp stay in the loop together)
+    __shared__ float4 sCoop[8 * kCoopFloat4PerWarp];
+    float4 *sq = sCoop + kCoopFloat4PerWarp * (threadIdx.x >> 5);
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const bool valid = i < n;
+        float3 p = f3(0.0f), w = f3(0.0f, 0.0f, 1.0f);
+        float u0 = 0, u1 = 0, u2 = 0;
+        uint32_t c = 0;
+        if (valid) {
+            p = ld3(pos + 3 * (size_t)i);
+            w = ld3(dir + 3 * (size_t)i);
+            u0 = u[3 * (size_t)i]; u1 = u[3 * (size_t)i + 1]; u2 = u[3 * (size_t)i + 2];
+            c = guideLookup(G, p);
+        }
+        const int k = guideSelectCoop(G, sq, valid, c, u0);
+        float3 d = f3(0.0f, 0.0f, 1.0f);
+        if (valid) d = guideSampleLobe(G, c, k, u1, u2);
+        float pw = 0, pd = 0;
+        guidePdf2Coop(G, sq, valid, c, w, d, pw, pd);
+        if (valid) {
+            outCell[i] = c;
+            outPdf[i] = pw;
+            outDir[3 * (size_t)i] = d.x;
+            outDir[3 * (size_t)i + 1] = d.y;
+            outDir[3 * (size_t)i + 2] = d.z;
+            outSpdf[i] = pd;
+        }
     }
 }
 

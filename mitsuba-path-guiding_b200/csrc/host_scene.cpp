@@ -240,7 +240,15 @@ std::string dataDir() {
     if (dladdr((void *)&dataDir, &info) && info.dli_fname) {
         std::string p = info.dli_fname;
         size_t s = p.find_last_of('/');
-        if (s != std::string::npos) return p.substr(0, s) + "/data";
+        if (s != std::string::npos) {
+            const std::string dir = p.substr(0, s);
+            // A/B variants of the library live one level down (_variants/) and share the package's tables
+            if (FILE *f = std::fopen((dir + "/data/rtrans_beckmann.bin").c_str(), "rb")) {
+                std::fclose(f);
+                return dir + "/data";
+            }
+            return dir + "/../data";
+        }
     }
     return "data";
 }
@@ -800,6 +808,28 @@ bool HostScene::compile(std::string &err) {
             nInner = 1;
             root = 0;
         }
+        // Primitive slots: every leaf starts at an EVEN slot, so that the plane rows of two neighbouring primitives of a leaf are
+        // one aligned 256-bit load (device_scene.cuh: bvhLeafStep); odd-sized leaves leave a hole behind them.
+        std::vector<uint32_t> slotOf(bprims.size() + 1, 0);
+        uint32_t nSlots = 0;
+        {
+            std::vector<std::pair<uint32_t, uint32_t>> leaves;  // (first, count) in the builder's primitive order
+            for (int i = 0; i < nInner; ++i)
+                for (int c = 0; c < 2; ++c) {
+                    const int32_t ch = bld.nodes[i].child[c];
+                    if (ch >= 0) continue;
+                    const uint32_t code = (uint32_t)(~ch);
+                    if ((code & 15u) != 0) leaves.emplace_back(code >> 4, code & 15u);
+                }
+            std::sort(leaves.begin(), leaves.end());
+            uint32_t cursor = 0;
+            for (auto &lf : leaves) {
+                cursor = (cursor + 1u) & ~1u;
+                for (uint32_t k = 0; k < lf.second; ++k) slotOf[lf.first + k] = cursor + k;
+                cursor += lf.second;
+            }
+            nSlots = ((cursor + 1u) & ~1u) + 2u;  // a leaf's second plane pair may be read one slot past its last primitive
+        }
         // relayout in DFS order so that a node's first child follows it
         std::vector<int32_t> remap(nInner, -1), order;
         order.reserve(nInner);
@@ -827,7 +857,7 @@ bool HostScene::compile(std::string &err) {
                 uint32_t first = code >> 4, count = code & 15u, mask = 0;
                 for (uint32_t k = 0; k < count; ++k)
                     if (flatInfo[bprims[first + k].id].prim == kNoTriangle) mask |= 1u << k;
-                return ~(int32_t)((first << kLeafShift) | (mask << 3) | count);
+                return ~(int32_t)((slotOf[first] << kLeafShift) | (mask << 3) | count);
             };
             int32_t c0 = t.child[0] >= 0 ? remap[t.child[0]] : leaf(t.child[0]);
             int32_t c1 = t.child[1] >= 0 ? remap[t.child[1]] : leaf(t.child[1]);
@@ -851,7 +881,7 @@ bool HostScene::compile(std::string &err) {
                     uint32_t first = code >> 4, count = code & 15u, mask = 0;
                     for (uint32_t k = 0; k < count; ++k)
                         if (flatInfo[bprims[first + k].id].prim == kNoTriangle) mask |= 1u << k;
-                    return ~(int32_t)((first << kLeafShift) | (mask << 3) | count);
+                    return ~(int32_t)((slotOf[first] << kLeafShift) | (mask << 3) | count);
                 };
                 const float diag = std::sqrt((rootBox.mx[0] - rootBox.mn[0]) * (rootBox.mx[0] - rootBox.mn[0]) +
                                              (rootBox.mx[1] - rootBox.mn[1]) * (rootBox.mx[1] - rootBox.mn[1]) +
@@ -969,19 +999,24 @@ bool HostScene::compile(std::string &err) {
                 }
             }
         }
-        prims.resize(bprims.size());
-        primGlobalId.resize(bprims.size());
-        primInfo.resize(bprims.size());
-        if (bprims.size() >= (1u << 24)) {
-            err = "more than 16M primitives are not supported by the leaf encoding";
+        if (nSlots >= (1u << 24)) {
+            err = "more than 16M primitive slots are not supported by the leaf encoding";
             return false;
         }
-        shadeTris.assign(bprims.size() * 24, 0.0f);
+        primPlanes.assign((size_t)nSlots * 4, 0.0f);
+        primRows.assign((size_t)nSlots * 8, 0.0f);
+        primGlobalId.assign(nSlots, 0xFFFFFFFFu);
+        primInfo.assign(nSlots, PrimInfo{0u, kNoTriangle});
+        shadeTris.assign((size_t)nSlots * 24, 0.0f);
+        nPrimitives = bprims.size();
 #pragma omp parallel for schedule(static)
-        for (size_t i = 0; i < bprims.size(); ++i) {
-            prims[i] = flat[bprims[i].id];
-            primInfo[i] = flatInfo[bprims[i].id];
-            primGlobalId[i] = bprims[i].id;
+        for (size_t b = 0; b < bprims.size(); ++b) {
+            const size_t i = slotOf[b];
+            const PrimRecord &pr = flat[bprims[b].id];
+            for (int k = 0; k < 8; ++k) primRows[i * 8 + k] = pr.q[k];        // rows 0 / 1: (u, v)
+            for (int k = 0; k < 4; ++k) primPlanes[i * 4 + k] = pr.q[8 + k];  // row 2: the plane
+            primInfo[i] = flatInfo[bprims[b].id];
+            primGlobalId[i] = bprims[b].id;
             // shading record (pg_types.h: ShadeTri): the hit's vertex data in one place, in BVH order
             const PrimInfo pi = primInfo[i];
             const ShapeRecord &sr = shapeRecs[pi.shape];

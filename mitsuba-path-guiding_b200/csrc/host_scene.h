@@ -30,7 +30,10 @@ struct HostScene {
     std::vector<BvhNode> nodes;
     std::vector<WideNode> wideNodes;     // 8-wide quantised tree over the same leaves (large meshes only; empty otherwise)
     int wideDepth = 0;
-    std::vector<PrimRecord> prims;       // BVH leaf order
+    // primitive records in BVH leaf order, one per SLOT (leaves start at even slots; holes are never referenced):
+    std::vector<float> primPlanes;       // 4 floats: row 2 of the affine map (pg_types.h: PrimRecord), the plane distance
+    std::vector<float> primRows;         // 8 floats: rows 0 / 1, the (u, v) coordinates
+    size_t nPrimitives = 0;              // primitives (slots minus holes)
     std::vector<uint32_t> primGlobalId;  // BVH order -> global primitive id
     std::vector<PrimInfo> primInfo;      // BVH order -> (shape, primitive index)
     std::vector<float> shadeTris;        // BVH order -> ShadeTri (24 floats), what the shade stage reads per hit

@@ -90,7 +90,7 @@ struct Integrator {
     std::atomic<int> cancel{0};
 
     // device scene
-    DevBuf<float4> dNodes, dWideNodes, dPrims, dRects;
+    DevBuf<float4> dNodes, dWideNodes, dPrimPlanes, dPrimRows, dRects;
     DevBuf<ShapeRecord> dShapes;
     DevBuf<MeshRecord> dMeshes;
     DevBuf<float> dPositions, dNormals, dTexcoords, dAreaCdf, dEmitterCdf, dDensity;
@@ -236,7 +236,8 @@ struct Integrator {
         std::memset(&stats, 0, sizeof(stats));
         HostScene &H = *scene;
         dNodes.upload(reinterpret_cast<const float4 *>(H.nodes.data()), H.nodes.size() * 4, stream);
-        dPrims.upload(reinterpret_cast<const float4 *>(H.prims.data()), H.prims.size() * 3, stream);
+        dPrimPlanes.upload(reinterpret_cast<const float4 *>(H.primPlanes.data()), H.primPlanes.size() / 4, stream);
+        dPrimRows.upload(reinterpret_cast<const float4 *>(H.primRows.data()), H.primRows.size() / 4, stream);
         if (!H.wideNodes.empty()) dWideNodes.upload(reinterpret_cast<const float4 *>(H.wideNodes.data()), H.wideNodes.size() * 6, stream);
         dRects.upload(reinterpret_cast<const float4 *>(H.rects.data()), H.rects.size() * 8, stream);
         dShapes.upload(H.shapeRecs, stream);
@@ -254,7 +255,7 @@ struct Integrator {
         dPrimGlobal.upload(H.primGlobalId, stream);
         dPrimInfo.upload(H.primInfo, stream);
         dShadeTris.upload(reinterpret_cast<const float4 *>(H.shadeTris.data()), H.shadeTris.size() / 4, stream);
-        S.nodes = dNodes.p; S.prims = dPrims.p; S.rects = dRects.p;
+        S.nodes = dNodes.p; S.primPlanes = dPrimPlanes.p; S.primRows = dPrimRows.p; S.rects = dRects.p;
         S.wideNodes = (H.wideNodes.empty() || !useWide) ? nullptr : dWideNodes.p;
         S.shapes = dShapes.p; S.meshes = dMeshes.p;
         S.positions = dPositions.p; S.normals = dNormals.p; S.texcoords = dTexcoords.p;
@@ -264,7 +265,7 @@ struct Integrator {
         S.primInfo = dPrimInfo.p;
         S.shadeTris = dShadeTris.p;
         S.nEmitters = (uint32_t)H.emitters.size();
-        S.nPrims = (uint32_t)H.prims.size();
+        S.nPrims = (uint32_t)H.primGlobalId.size();
         S.camera = H.camera;
         S.film = H.filmRec;
         S.seed = H.seed;
@@ -1272,13 +1273,14 @@ int b200pg_scene_upload(void *integ, size_t *bytes) {
         total += src.size() * sizeof(src[0]);
     };
     self->dNodes.upload(reinterpret_cast<const float4 *>(H.nodes.data()), H.nodes.size() * 4, self->stream);
-    self->dPrims.upload(reinterpret_cast<const float4 *>(H.prims.data()), H.prims.size() * 3, self->stream);
+    self->dPrimPlanes.upload(reinterpret_cast<const float4 *>(H.primPlanes.data()), H.primPlanes.size() / 4, self->stream);
+    self->dPrimRows.upload(reinterpret_cast<const float4 *>(H.primRows.data()), H.primRows.size() / 4, self->stream);
     if (!H.wideNodes.empty()) {
         self->dWideNodes.upload(reinterpret_cast<const float4 *>(H.wideNodes.data()), H.wideNodes.size() * 6, self->stream);
         total += H.wideNodes.size() * sizeof(WideNode);
     }
     self->dRects.upload(reinterpret_cast<const float4 *>(H.rects.data()), H.rects.size() * 8, self->stream);
-    total += H.nodes.size() * 64 + H.prims.size() * 48 + H.rects.size() * 128;
+    total += H.nodes.size() * 64 + H.primGlobalId.size() * 48 + H.rects.size() * 128;
     up(self->dShapes, H.shapeRecs);
     up(self->dPrimInfo, H.primInfo);
     self->dShadeTris.upload(reinterpret_cast<const float4 *>(H.shadeTris.data()), H.shadeTris.size() / 4, self->stream);

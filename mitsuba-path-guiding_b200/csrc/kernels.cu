@@ -247,7 +247,7 @@ struct TraceStack<false> {
     int e[kTraceStack];
     PG_DEV int step(const DeviceScene &S, int node, float3 o, float3 idir, float mint, float tmax, int &sp) {
 #ifndef PG_TRACE_PREFETCH
-#define PG_TRACE_PREFETCH 1
+#define PG_TRACE_PREFETCH 0  // measured (r2d): no gain on C4 (407.5 vs 407.7 M paths/s), C2 trace stage 1.33 -> 3.80 ms
 #endif
         return bvhNodeStep<PG_TRACE_PREFETCH != 0>(S, node, o, idir, mint, tmax, e, sp);
     }
@@ -563,6 +563,9 @@ __global__ void __launch_bounds__(128) k_trace_rays(DeviceScene S, const float4 
 #ifndef PG_SHADE_BLOCKS
 #define PG_SHADE_BLOCKS 8
 #endif
+#ifndef PG_SHADE_COOP
+#define PG_SHADE_COOP 1  // warp-cooperative guiding queries (0 = per-thread loops over the cell's lobes, for A/B runs)
+#endif
 __global__ void __launch_bounds__(kShadeThreads, PG_SHADE_BLOCKS) k_shade(ShadeArgs A) {
     const DeviceScene &S = A.S;
     const IntegratorConfig &cfg = A.cfg;
@@ -572,6 +575,10 @@ __global__ void __launch_bounds__(kShadeThreads, PG_SHADE_BLOCKS) k_shade(ShadeA
     unsigned long long donePaths = 0, doneLen = 0;
     __shared__ uint32_t sAppend[2 * 3 * (kShadeThreads / 32 + 1)];
     uint32_t appendParity = 0;
+
+    // staging area of the warp-cooperative guiding queries (guiding_device.cuh): 64 float4 per warp
+    __shared__ float4 sCoop[(kShadeThreads / 32) * kCoopFloat4PerWarp];
+    float4 *sq = sCoop + kCoopFloat4PerWarp * (threadIdx.x >> 5);
 
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t q = base + threadIdx.x;
@@ -595,6 +602,16 @@ __global__ void __launch_bounds__(kShadeThreads, PG_SHADE_BLOCKS) k_shade(ShadeA
         float shMaxT = 0.0f;
         uint32_t depth = 0, vcount = 0;
 
+        // The vertex is shaded in three per-lane phases with the two warp-cooperative guiding queries between them (lobe
+        // selection, mixture pdf of the NEE and the sampled direction): every lane of the warp reaches those two calls.
+        bool shadeIt = false;  // a live surface vertex (hit, not stopped by Russian roulette / depth / strict normals)
+        bool guided = false;
+        Intersection its;
+        const BsdfRecord *bsdfP = S.bsdfs;
+        uint32_t btype = 0, gcell = 0;
+        float3 d = f3(0.0f);
+
+        // ---- phase 1: state, emitted radiance, Russian roulette, stops, guiding cell
         if (valid) {
             ro = ldStream(A.cur.rayO + i);
             rd = ldStream(A.cur.rayD + i);
@@ -613,7 +630,8 @@ __global__ void __launch_bounds__(kShadeThreads, PG_SHADE_BLOCKS) k_shade(ShadeA
             const uint32_t pixel = (uint32_t)samplePos.y * (uint32_t)S.film.width + (uint32_t)samplePos.x;
             rng.state = ((uint64_t)__float_as_uint(pos4.w) << 32) | (uint64_t)__float_as_uint(pos4.z);
             rng.inc = ((uint64_t)pixel << 1) | 1ULL;
-            const float3 o = f3(ro.x, ro.y, ro.z), d = f3(rd.x, rd.y, rd.z);
+            const float3 o = f3(ro.x, ro.y, ro.z);
+            d = f3(rd.x, rd.y, rd.z);
             Hit h;
             h.t = h4.x;
             h.u = h4.y;
@@ -632,9 +650,8 @@ __global__ void __launch_bounds__(kShadeThreads, PG_SHADE_BLOCKS) k_shade(ShadeA
             } else if (h.prim == kMiss) {
                 terminate = true;  // no environment emitter on this path (progressive_path.cpp:150-159)
             } else {
-                Intersection its;
                 fillIntersection(S, o, d, h, its);
-                const BsdfRecord &bsdf = S.bsdfs[its.bsdf];
+                bsdfP = S.bsdfs + its.bsdf;
 
                 // ---- emitted radiance: directly visible (first hit) or reached by BSDF sampling (MIS)
                 if (its.emitter >= 0) {
@@ -663,107 +680,130 @@ __global__ void __launch_bounds__(kShadeThreads, PG_SHADE_BLOCKS) k_shade(ShadeA
                 if (!terminate && (((int)depth >= cfg.maxDepth && cfg.maxDepth > 0) ||
                                    (cfg.strictNormals && dot(d, its.geoN) * its.wi.z >= 0)))
                     terminate = true;
-
                 if (!terminate) {
-                    // ---- direct illumination sampling (:191-219)
-                    const uint32_t btype = bsdf.typeFlags;
+                    shadeIt = true;
+                    btype = bsdfP->typeFlags;
                     // guided vertex: smooth BSDF only -- delta lobes are never guided
-                    const bool guided = A.G.enabled && (btype & kSmooth);
-                    const uint32_t gcell = guided ? guideLookup(A.G, its.p) : 0u;
-                    // NEE (:191-219). At a guided vertex the MIS weight needs the mixture pdf of the light direction; it is
-                    // evaluated together with the pdf of the sampled direction in ONE pass over the cell's lobes below.
-                    bool neePending = false;
-                    float neeBsdfPdf = 0.0f, neeLightPdf = 0.0f;
-                    float3 neeContrib = f3(0.0f);
-                    if (cfg.useNee && (btype & kSmooth)) {
-                        const float3 refN = (btype & (kTransmission | kBackSide)) == 0 ? its.sh.n : f3(0.0f);  // records.inl:160-164
-                        DirectSample dRec;
-                        const float2 u = rng.next2D();
-                        const float3 value = sampleEmitterDirect(S, its.p, refN, u, dRec);
-                        if (!isZero(value)) {
-                            const float3 woL = its.sh.toLocal(dRec.d);
-                            const float3 bsdfVal = bsdfEval(bsdf, its.wi, woL);
-                            if (!isZero(bsdfVal) && (!cfg.strictNormals || dot(its.geoN, dRec.d) * woL.z > 0)) {
-                                neeBsdfPdf = bsdfPdf(bsdf, its.wi, woL);
-                                neeLightPdf = dRec.pdf;
-                                neeContrib = thr * value * bsdfVal;
-                                shO = its.p;
-                                shD = dRec.d;
-                                shMaxT = dRec.dist * (1 - kShadowEpsilon);  // scene.cpp:883-884
-                                neePending = true;
-                            }
-                        }
-                    }
-                    // ---- BSDF sampling (:226-238)
-                    float bPdf, bEta;
-                    uint32_t sampledType;
-                    float3 woL, wo, bsdfWeight;
-                    if (guided) {
-                        // one-sample MIS between the guiding mixture (probability alpha) and the BSDF
-                        float u0 = rng.next1D();
-                        const float2 u12 = rng.next2D();
-                        float3 fcos;
-                        float pb;
-                        bool ok = true;
-                        if (u0 < A.G.alpha) {
-                            u0 /= A.G.alpha;
-                            wo = guideSample(A.G, gcell, u0, u12.x, u12.y);
-                            woL = its.sh.toLocal(wo);
-                            fcos = bsdfEval(bsdf, its.wi, woL);
-                            pb = bsdfPdf(bsdf, its.wi, woL);
-                            bEta = 1.0f;
-                            sampledType = kGlossyReflection;
-                        } else {
-                            const float3 w = bsdfSample(bsdf, its.wi, u12, woL, pb, bEta, sampledType);
-                            ok = !isZero(w);
-                            fcos = w * pb;
-                            wo = its.sh.toWorld(woL);
-                        }
-                        // one pass over the cell's lobes for both directions (a single code path keeps the warp converged;
-                        // an unused direction is evaluated on a dummy and discarded)
-                        float gNee = 0.0f, gWo = 0.0f;
-                        if (neePending || ok) guidePdf2(A.G, gcell, neePending ? shD : wo, ok ? wo : shD, gNee, gWo);
-                        if (neePending) neeBsdfPdf = A.G.alpha * gNee + (1 - A.G.alpha) * neeBsdfPdf;
-                        bPdf = ok ? A.G.alpha * gWo + (1 - A.G.alpha) * pb : 0.0f;
-                        bsdfWeight = (ok && !isZero(fcos) && bPdf > 0) ? fcos / bPdf : f3(0.0f);
-                    } else {
-                        bsdfWeight = bsdfSample(bsdf, its.wi, rng.next2D(), woL, bPdf, bEta, sampledType);
-                        wo = its.sh.toWorld(woL);
-                    }
-                    if (neePending) {
-                        shC = neeContrib * miWeight(neeLightPdf, neeBsdfPdf);
-                        wantShadow = true;
-                    }
-                    if (isZero(bsdfWeight)) {
-                        terminate = true;
-                    } else {
-                        if (cfg.strictNormals && dot(its.geoN, wo) * woL.z <= 0) {
-                            terminate = true;
-                        } else {
-                            thr *= bsdfWeight;  // (:271-272; a miss of the new ray terminates next bounce)
-                            eta *= bEta;
-                            newO = its.p;
-                            newD = wo;
-                            newPdf = bPdf;
-                            fl &= ~(kFlagFirst | kFlagPrevDelta);
-                            if (sampledType & kDelta) fl |= kFlagPrevDelta;
-                            if (sampledType != kNull) fl |= kFlagScattered;
-                            alive = true;
-                            if (A.G.record && (btype & kSmooth) && (int)vcount < A.G.maxVerts) {
-                                guideVertexOpen(A.G, slot, vcount, its.p, bPdf, wo);
-                                vcount++;
-                                fl &= ~kFlagVertexClosed;
-                            }
-                        }
+                    guided = A.G.enabled && (btype & kSmooth);
+                    if (guided) gcell = guideLookup(A.G, its.p);
+                }
+            }
+        }
+        // random numbers in the order the reference consumes them: emitter sample, then the direction sample
+        float2 uNee = make_float2(0.0f, 0.0f), u12 = make_float2(0.0f, 0.0f);
+        float u0 = 0.0f;
+        bool fromField = false;  // the direction comes from the guiding mixture (probability alpha)
+        const bool nee = shadeIt && cfg.useNee && (btype & kSmooth);
+        if (nee) uNee = rng.next2D();
+        if (guided) {
+            u0 = rng.next1D();
+            u12 = rng.next2D();
+            fromField = u0 < A.G.alpha;
+            if (fromField) u0 /= A.G.alpha;
+        }
+        int lobe = 0;
+#if PG_SHADE_COOP
+        if (A.G.enabled) lobe = guideSelectCoop(A.G, sq, fromField, gcell, u0);
+#endif
+
+        // ---- phase 2: direct illumination sample (:191-219) and the sampled direction (:226-238)
+        bool neePending = false, ok = true;
+        float neeBsdfPdf = 0.0f, neeLightPdf = 0.0f, pb = 0.0f, bPdf = 0.0f, bEta = 1.0f;
+        float3 neeContrib = f3(0.0f), fcos = f3(0.0f), wo = f3(0.0f), woL = f3(0.0f), bsdfWeight = f3(0.0f);
+        uint32_t sampledType = 0;
+        if (shadeIt) {
+            const BsdfRecord &bsdf = *bsdfP;
+            // At a guided vertex the MIS weight of the emitter sample needs the mixture pdf of the light direction; it is
+            // evaluated together with the pdf of the sampled direction in ONE pass over the cell's lobes below.
+            if (nee) {
+                const float3 refN = (btype & (kTransmission | kBackSide)) == 0 ? its.sh.n : f3(0.0f);  // records.inl:160-164
+                DirectSample dRec;
+                const float3 value = sampleEmitterDirect(S, its.p, refN, uNee, dRec);
+                if (!isZero(value)) {
+                    const float3 woLn = its.sh.toLocal(dRec.d);
+                    const float3 bsdfVal = bsdfEval(bsdf, its.wi, woLn);
+                    if (!isZero(bsdfVal) && (!cfg.strictNormals || dot(its.geoN, dRec.d) * woLn.z > 0)) {
+                        neeBsdfPdf = bsdfPdf(bsdf, its.wi, woLn);
+                        neeLightPdf = dRec.pdf;
+                        neeContrib = thr * value * bsdfVal;
+                        shO = its.p;
+                        shD = dRec.d;
+                        shMaxT = dRec.dist * (1 - kShadowEpsilon);  // scene.cpp:883-884
+                        neePending = true;
                     }
                 }
             }
-            if (terminate && wantShadow) {
-                // park the record for one bounce so that the shadow ray has somewhere to land
-                alive = true;
-                fl |= kFlagDead;
-                terminate = false;
+            if (guided) {
+                // one-sample MIS between the guiding mixture (probability alpha) and the BSDF
+                if (fromField) {
+#if PG_SHADE_COOP
+                    wo = guideSampleLobe(A.G, gcell, lobe, u12.x, u12.y);
+#else
+                    wo = guideSample(A.G, gcell, u0, u12.x, u12.y);
+#endif
+                    woL = its.sh.toLocal(wo);
+                    fcos = bsdfEval(bsdf, its.wi, woL);
+                    pb = bsdfPdf(bsdf, its.wi, woL);
+                    bEta = 1.0f;
+                    sampledType = kGlossyReflection;
+                } else {
+                    const float3 w = bsdfSample(bsdf, its.wi, u12, woL, pb, bEta, sampledType);
+                    ok = !isZero(w);
+                    fcos = w * pb;
+                    wo = its.sh.toWorld(woL);
+                }
+            } else {
+                bsdfWeight = bsdfSample(bsdf, its.wi, rng.next2D(), woL, bPdf, bEta, sampledType);
+                wo = its.sh.toWorld(woL);
             }
+        }
+        // mixture pdf of both directions (an unused direction is evaluated on a dummy and discarded)
+        float gNee = 0.0f, gWo = 0.0f;
+#if PG_SHADE_COOP
+        if (A.G.enabled)
+            guidePdf2Coop(A.G, sq, guided && (neePending || ok), gcell, neePending ? shD : wo, ok ? wo : shD, gNee, gWo);
+#else
+        if (guided && (neePending || ok)) guidePdf2(A.G, gcell, neePending ? shD : wo, ok ? wo : shD, gNee, gWo);
+        (void)sq; (void)lobe;
+#endif
+
+        // ---- phase 3: weights, next ray
+        if (shadeIt) {
+            if (guided) {
+                if (neePending) neeBsdfPdf = A.G.alpha * gNee + (1 - A.G.alpha) * neeBsdfPdf;
+                bPdf = ok ? A.G.alpha * gWo + (1 - A.G.alpha) * pb : 0.0f;
+                bsdfWeight = (ok && !isZero(fcos) && bPdf > 0) ? fcos / bPdf : f3(0.0f);
+            }
+            if (neePending) {
+                shC = neeContrib * miWeight(neeLightPdf, neeBsdfPdf);
+                wantShadow = true;
+            }
+            if (isZero(bsdfWeight)) {
+                terminate = true;
+            } else if (cfg.strictNormals && dot(its.geoN, wo) * woL.z <= 0) {
+                terminate = true;
+            } else {
+                thr *= bsdfWeight;  // (:271-272; a miss of the new ray terminates next bounce)
+                eta *= bEta;
+                newO = its.p;
+                newD = wo;
+                newPdf = bPdf;
+                fl &= ~(kFlagFirst | kFlagPrevDelta);
+                if (sampledType & kDelta) fl |= kFlagPrevDelta;
+                if (sampledType != kNull) fl |= kFlagScattered;
+                alive = true;
+                if (A.G.record && (btype & kSmooth) && (int)vcount < A.G.maxVerts) {
+                    guideVertexOpen(A.G, slot, vcount, its.p, bPdf, wo);
+                    vcount++;
+                    fl &= ~kFlagVertexClosed;
+                }
+            }
+        }
+        if (valid && terminate && wantShadow) {
+            // park the record for one bounce so that the shadow ray has somewhere to land
+            alive = true;
+            fl |= kFlagDead;
+            terminate = false;
         }
 
         // ---- compaction into the next queue / shadow queue (one atomic per block each)
