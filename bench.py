@@ -633,6 +633,8 @@ def measure(ctx, args, headline):
             line["strong_scaling"] = strong
         if cpu and cpu.get("value"):
             line["vs_cpu_baseline"] = {"value_ratio": value / cpu["value"], "e2e_ratio": e2e["value"] / cpu["value"]}
+            if "scene_resident" in e2e:  # the CPU leg does not rebuild its kd-tree per step either (build time reported in `sample`)
+                line["vs_cpu_baseline"]["e2e_scene_resident_ratio"] = e2e["scene_resident"]["value"] / cpu["value"]
     integ.close()
     scene.close()
     return line

@@ -39,6 +39,8 @@ void launchTrace(const DeviceScene &S, const PathState &P, float4 *hits, const u
 void launchShadow(const DeviceScene &S, const ShadowQueue &Q, float4 *rad, const uint32_t *nPtr, uint32_t *work, Counters *C,
                   bool count, bool speculative, cudaStream_t st);
 void launchShade(const ShadeArgs &A, cudaStream_t st);
+void launchHitPartition(const float4 *hits, const uint32_t *flags, const uint32_t *nPtr, uint32_t *perm, uint32_t *cntNeed,
+                        uint32_t *cntRest, cudaStream_t st);
 void launchFlush(const ShadeArgs &A, cudaStream_t st);
 void launchFilmAdd(float4 *film, const float4 *peer, uint32_t n, cudaStream_t st);
 void launchFilmExportMerged(const float4 *film, const float4 *const *peers, int nPeers, float *out, uint32_t n, cudaStream_t st);
@@ -123,6 +125,7 @@ struct Integrator {
     static constexpr int kMaxLanes = 8;
     Lane lane[kMaxLanes];
     bool overlapShadow = !(std::getenv("B200PG_OVERLAP_SHADOW") && std::atoi(std::getenv("B200PG_OVERLAP_SHADOW")) == 0);
+    bool laneMajor = std::getenv("B200PG_LANE_MAJOR") && std::atoi(std::getenv("B200PG_LANE_MAJOR")) != 0;
     int lanes = std::getenv("B200PG_LANES") ? std::max(1, std::min(kMaxLanes, std::atoi(std::getenv("B200PG_LANES")))) : 2;
     DevBuf<float4> dSplat;
     DevBuf<float4> dFilm;
@@ -141,7 +144,22 @@ struct Integrator {
     // measured on C4 (profiles/r02_c4_summary.txt): node visits per ray 25.7 -> 9.5 and long-scoreboard stalls 9.7 -> 3.8 per issue,
     // but 1.65x the instructions -- the kernel turns issue-bound and ends up 5-15 % SLOWER than the binary tree. Off by default.
     bool useWide = std::getenv("B200PG_WIDE") && std::atoi(std::getenv("B200PG_WIDE")) != 0;
+    // the wide tree only from this bounce on (late bounces hold few rays and are bound by the dependent-load chains of single
+    // long rays, where three binary levels per visit pay; the bulk bounces are issue-bound on the wide node test)
+    int wideFrom = std::getenv("B200PG_WIDE_FROM") ? std::atoi(std::getenv("B200PG_WIDE_FROM")) : 0;
     int traceSpec = std::getenv("B200PG_TRACE_SPEC") ? std::atoi(std::getenv("B200PG_TRACE_SPEC")) : 3;
+    // hit / miss partition of the shade queue (kernels.cu: k_hit_partition) on bounces where, in the previous progression, fewer
+    // than half of the queued paths still had a vertex to shade (open scenes: most bounce rays leave). 0 = never, 1 = adaptive
+    // (default), 2 = every bounce >= 1. Affects the order in which paths are shaded, not what they compute.
+    int partitionMode = std::getenv("B200PG_PARTITION") ? std::atoi(std::getenv("B200PG_PARTITION")) : 1;
+    float shadeNeedRatio[260];   // per bounce, from lane 0's counters of the last progression
+    uint32_t hQueue[260], hPartNeed[260];
+    uint64_t partitionSkipUntil[260];  // a bounce the partition kernel itself found dense is left alone for a while
+    bool partitionBounce(int b, bool sorted) const {
+        if (sorted || params.volumetric || b < 1 || b >= 260) return false;
+        return partitionMode == 2 ||
+               (partitionMode == 1 && shadeNeedRatio[b] < 0.5f && stats.progressions_done >= partitionSkipUntil[b]);
+    }
     // denoiser feature buffers (denoiser.cpp:138-144): 3 float4 per pixel, allocated by set_option("feature_buffers", 1)
     bool featureBuffers = false;
     DevBuf<float4> dFeat;
@@ -234,6 +252,8 @@ struct Integrator {
             CUDA_OK(cudaEventCreate(&e2));
         }
         std::memset(&stats, 0, sizeof(stats));
+        for (float &r : shadeNeedRatio) r = 1.0f;
+        for (uint64_t &u : partitionSkipUntil) u = 0;
         HostScene &H = *scene;
         dNodes.upload(reinterpret_cast<const float4 *>(H.nodes.data()), H.nodes.size() * 4, stream);
         dPrimPlanes.upload(reinterpret_cast<const float4 *>(H.primPlanes.data()), H.primPlanes.size() / 4, stream);
@@ -270,9 +290,15 @@ struct Integrator {
         S.film = H.filmRec;
         S.seed = H.seed;
         CUDA_OK(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming));
+        int prioLeast = 0, prioGreatest = 0;
+        CUDA_OK(cudaDeviceGetStreamPriorityRange(&prioLeast, &prioGreatest));
+        int laneIndex = 0;
         for (auto &L : lane) {
-            CUDA_OK(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
-            CUDA_OK(cudaStreamCreateWithFlags(&L.shadowStream, cudaStreamNonBlocking));
+            // earlier lanes get the SMs first (numerically lower = higher priority): with the lane-major enqueue order the lanes
+            // run staggered instead of side by side
+            const int prio = std::min(prioLeast, prioGreatest + laneIndex++);
+            CUDA_OK(cudaStreamCreateWithPriority(&L.stream, cudaStreamNonBlocking, prio));
+            CUDA_OK(cudaStreamCreateWithPriority(&L.shadowStream, cudaStreamNonBlocking, prio));
             CUDA_OK(cudaEventCreateWithFlags(&L.evDone, cudaEventDisableTiming));
             CUDA_OK(cudaEventCreateWithFlags(&L.evShade, cudaEventDisableTiming));
             CUDA_OK(cudaEventCreateWithFlags(&L.evShadow, cudaEventDisableTiming));
@@ -378,21 +404,29 @@ struct Integrator {
         const int maxBounces = params.max_depth > 0 ? std::min(params.max_depth + 1, 256) : 256;
         int lastBounce[kMaxLanes];
         for (int l = 0; l < nBatches; ++l) lastBounce[l] = maxBounces;
-        for (int b = 0; b < maxBounces; ++b) {
+        // Enqueue order. Bounce-major (bounce b of every lane, then bounce b + 1) keeps symmetric lanes in lock step: their bulk
+        // kernels compete and their latency-bound tails coincide. Lane-major (all bounces of lane 0, then lane 1, ...; finite
+        // depth only -- nothing is polled) staggers them: while lane 0 is in its thin late bounces, lane 1's bulk fills the SMs.
+        const bool byLane = laneMajor && params.max_depth > 0 && nBatches > 1;
+        const int outer = byLane ? nBatches : maxBounces, inner = byLane ? maxBounces : nBatches;
+        for (int oi = 0; oi < outer; ++oi) {
             if (cancel.load()) {
                 for (int l = 0; l < nBatches; ++l)
-                    if (live[l]) { lastBounce[l] = b; live[l] = false; }
+                    if (live[l] && !(byLane && l < oi)) { lastBounce[l] = byLane ? 0 : oi; live[l] = false; }
                 break;
             }
             bool any = false;
-            for (int l = 0; l < nBatches; ++l) {
+            for (int ii = 0; ii < inner; ++ii) {
+                const int b = byLane ? ii : oi, l = byLane ? oi : ii;
                 if (!live[l]) continue;
                 any = true;
                 Lane &L = lane[l];
                 Counters *C = L.dCounters.p;
                 cudaEvent_t t = spanBegin(st[l]);
                 const bool sorted = sortOn && b >= 1 && b <= sortBounces;
-                launchTrace(S, cur[l], L.dHits.p, &C->queue[b], &C->traceWork[b], C, countTraversal, sorted ? &sortArgs[l] : nullptr,
+                DeviceScene Sb = S;
+                if (b < wideFrom) Sb.wideNodes = nullptr;
+                launchTrace(Sb, cur[l], L.dHits.p, &C->queue[b], &C->traceWork[b], C, countTraversal, sorted ? &sortArgs[l] : nullptr,
                             (traceSpec & (b == 0 ? 4 : 1)) != 0, st[l]);
                 if (sorted) stats.kernel_launches += 2;
                 spanEnd(kTimeTrace, t, st[l]);
@@ -402,6 +436,11 @@ struct Integrator {
                 }
                 ShadeArgs &a = A[l];
                 a.perm = sorted ? L.dSortPerm.p : nullptr;
+                if (partitionBounce(b, sorted)) {
+                    launchHitPartition(L.dHits.p, cur[l].flags, &C->queue[b], L.dSortPerm.p, &C->partNeed[b], &C->partRest[b], st[l]);
+                    stats.kernel_launches++;
+                    a.perm = L.dSortPerm.p;
+                }
                 a.cur = cur[l];
                 a.next = next[l];
                 a.bounce = b;
@@ -422,7 +461,7 @@ struct Integrator {
                 if (params.volumetric)
                     launchShadowVol(S, a.shadow, next[l].rad, &C->shadow[b], &C->shadowWork[b], C, ss);
                 else
-                    launchShadow(S, a.shadow, next[l].rad, &C->shadow[b], &C->shadowWork[b], C, countTraversal, (traceSpec & 2) != 0, ss);
+                    launchShadow(Sb, a.shadow, next[l].rad, &C->shadow[b], &C->shadowWork[b], C, countTraversal, (traceSpec & 2) != 0, ss);
                 spanEnd(kTimeShadow, t, ss);
                 if (overlapShadow) CUDA_OK(cudaEventRecord(L.evShadow, ss));
                 stats.kernel_launches += 3;
@@ -437,7 +476,7 @@ struct Integrator {
                     }
                 }
             }
-            if (!any) break;
+            if (!any && !byLane) break;
         }
         for (int l = 0; l < nBatches; ++l) {
             Lane &L = lane[l];
@@ -552,8 +591,22 @@ struct Integrator {
         uint32_t recorded = 0xFFFFFFFFu;
         if (guide.active && guide.recording)  // the training update needs the sample count: fetch it with this sync
             CUDA_OK(cudaMemcpyAsync(&recorded, guide.dSCount.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        if (partitionMode == 1 && !params.volumetric) {  // next progression's partition policy: who still had a vertex to shade
+            CUDA_OK(cudaMemcpyAsync(hQueue, lane[0].dCounters.p->queue, sizeof(hQueue), cudaMemcpyDeviceToHost, stream));
+            CUDA_OK(cudaMemcpyAsync(hPartNeed, lane[0].dCounters.p->partNeed, sizeof(hPartNeed), cudaMemcpyDeviceToHost, stream));
+        }
         CUDA_OK(cudaStreamSynchronize(stream));
         CUDA_OK(cudaGetLastError());
+        if (partitionMode == 1 && !params.volumetric && !batches.empty()) {
+            for (int b = 1; b + 1 < 260; ++b) {
+                const bool ran = partitionBounce(b, false);
+                // small queues are not worth a launch; with the partition on, the kernel's own count is exact, otherwise the
+                // survivors of the bounce are the estimate (a path with a vertex to shade mostly lives on)
+                if (hQueue[b] < (64u << 10)) shadeNeedRatio[b] = 1.0f;
+                else shadeNeedRatio[b] = (float)(ran ? hPartNeed[b] : hQueue[b + 1]) / (float)hQueue[b];
+                if (ran && shadeNeedRatio[b] >= 0.5f) partitionSkipUntil[b] = stats.progressions_done + 64;
+            }
+        }
         guide.pendingCount = recorded;
         drainSpans();
         float msTotal = 0;
@@ -1239,6 +1292,8 @@ int b200pg_set_option(void *integ, const char *name, int value) {
     }
     else if (n == "overlap_shadow") self->overlapShadow = value != 0;
     else if (n == "lanes") self->lanes = std::max(1, std::min((int)Integrator::kMaxLanes, value));
+    else if (n == "partition") self->partitionMode = value;
+    else if (n == "lane_major") self->laneMajor = value != 0;
     else if (n == "feature_buffers") {
         self->featureBuffers = value != 0;
         if (self->featureBuffers && !self->dFeat.p) {

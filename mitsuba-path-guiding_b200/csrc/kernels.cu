@@ -487,6 +487,48 @@ __global__ void __launch_bounds__(256) k_bin_scatter(SortArgs Q, const uint32_t 
         Q.perm[__ldg(Q.binOffset + Q.key[i]) + Q.rank[i]] = i;
 }
 
+// Hit / miss partition of a traced queue (open scenes): perm = [entries with a vertex to shade ..., the rest (missed rays, parked
+// records) in reverse]. On the 10 M-triangle terrain 90-95 % of the bounce-1 rays leave the scene; shaded in queue order, 4 of 5 warps
+// still hold one or two live vertices and walk the whole shading code for them (ncu, guided C4 step: k_shade 2.8 ms on bounce 1 for
+// 0.3 M live vertices, 6 lanes per instruction). Through the permutation the live vertices fill whole warps and the misses form
+// warps that only close their path. Order inside each class follows the queue (block-wise), so the gathers stay nearly coalesced.
+__global__ void __launch_bounds__(256) k_hit_partition(const float4 *__restrict__ hits, const uint32_t *__restrict__ flags,
+                                                       const uint32_t *nPtr, uint32_t *__restrict__ perm, uint32_t *cntNeed,
+                                                       uint32_t *cntRest) {
+    __shared__ uint32_t sWarp[2][8];
+    __shared__ uint32_t sBase[2];
+    const uint32_t n = *nPtr;
+    const uint32_t warp = threadIdx.x >> 5;
+    for (uint32_t base = blockIdx.x * 256u; base < n; base += gridDim.x * 256u) {
+        const uint32_t i = base + threadIdx.x;
+        bool need = false, rest = false;
+        if (i < n) {
+            need = __float_as_uint(ldStream(&hits[i].w)) != kMiss && !(ldStream(flags + i) & kFlagDead);
+            rest = !need;
+        }
+        const unsigned mN = __ballot_sync(0xffffffffu, need), mR = __ballot_sync(0xffffffffu, rest);
+        if (laneId() == 0) {
+            sWarp[0][warp] = __popc(mN);
+            sWarp[1][warp] = __popc(mR);
+        }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            uint32_t total = 0;
+            for (int w = 0; w < 8; ++w) {
+                const uint32_t c = sWarp[threadIdx.x][w];
+                sWarp[threadIdx.x][w] = total;
+                total += c;
+            }
+            sBase[threadIdx.x] = total ? atomicAdd(threadIdx.x ? cntRest : cntNeed, total) : 0u;
+        }
+        __syncthreads();
+        const unsigned lt = (1u << laneId()) - 1u;
+        if (need) perm[sBase[0] + sWarp[0][warp] + __popc(mN & lt)] = i;
+        if (rest) perm[n - 1u - (sBase[1] + sWarp[1][warp] + __popc(mR & lt))] = i;
+        __syncthreads();
+    }
+}
+
 // Shadow rays: any-hit; an unoccluded ray adds its contribution to the path record it belongs to.
 template <bool kCount>
 __global__ void __launch_bounds__(128) k_shadow(DeviceScene S, ShadowQueue Q, float4 *__restrict__ rad, const uint32_t *nPtr,
@@ -563,9 +605,6 @@ __global__ void __launch_bounds__(128) k_trace_rays(DeviceScene S, const float4 
 #ifndef PG_SHADE_BLOCKS
 #define PG_SHADE_BLOCKS 8
 #endif
-#ifndef PG_SHADE_COOP
-#define PG_SHADE_COOP 1  // warp-cooperative guiding queries (0 = per-thread loops over the cell's lobes, for A/B runs)
-#endif
 __global__ void __launch_bounds__(kShadeThreads, PG_SHADE_BLOCKS) k_shade(ShadeArgs A) {
     const DeviceScene &S = A.S;
     const IntegratorConfig &cfg = A.cfg;
@@ -575,10 +614,6 @@ __global__ void __launch_bounds__(kShadeThreads, PG_SHADE_BLOCKS) k_shade(ShadeA
     unsigned long long donePaths = 0, doneLen = 0;
     __shared__ uint32_t sAppend[2 * 3 * (kShadeThreads / 32 + 1)];
     uint32_t appendParity = 0;
-
-    // staging area of the warp-cooperative guiding queries (guiding_device.cuh): 64 float4 per warp
-    __shared__ float4 sCoop[(kShadeThreads / 32) * kCoopFloat4PerWarp];
-    float4 *sq = sCoop + kCoopFloat4PerWarp * (threadIdx.x >> 5);
 
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t q = base + threadIdx.x;
@@ -602,16 +637,6 @@ __global__ void __launch_bounds__(kShadeThreads, PG_SHADE_BLOCKS) k_shade(ShadeA
         float shMaxT = 0.0f;
         uint32_t depth = 0, vcount = 0;
 
-        // The vertex is shaded in three per-lane phases with the two warp-cooperative guiding queries between them (lobe
-        // selection, mixture pdf of the NEE and the sampled direction): every lane of the warp reaches those two calls.
-        bool shadeIt = false;  // a live surface vertex (hit, not stopped by Russian roulette / depth / strict normals)
-        bool guided = false;
-        Intersection its;
-        const BsdfRecord *bsdfP = S.bsdfs;
-        uint32_t btype = 0, gcell = 0;
-        float3 d = f3(0.0f);
-
-        // ---- phase 1: state, emitted radiance, Russian roulette, stops, guiding cell
         if (valid) {
             ro = ldStream(A.cur.rayO + i);
             rd = ldStream(A.cur.rayD + i);
@@ -630,8 +655,7 @@ __global__ void __launch_bounds__(kShadeThreads, PG_SHADE_BLOCKS) k_shade(ShadeA
             const uint32_t pixel = (uint32_t)samplePos.y * (uint32_t)S.film.width + (uint32_t)samplePos.x;
             rng.state = ((uint64_t)__float_as_uint(pos4.w) << 32) | (uint64_t)__float_as_uint(pos4.z);
             rng.inc = ((uint64_t)pixel << 1) | 1ULL;
-            const float3 o = f3(ro.x, ro.y, ro.z);
-            d = f3(rd.x, rd.y, rd.z);
+            const float3 o = f3(ro.x, ro.y, ro.z), d = f3(rd.x, rd.y, rd.z);
             Hit h;
             h.t = h4.x;
             h.u = h4.y;
@@ -650,8 +674,9 @@ __global__ void __launch_bounds__(kShadeThreads, PG_SHADE_BLOCKS) k_shade(ShadeA
             } else if (h.prim == kMiss) {
                 terminate = true;  // no environment emitter on this path (progressive_path.cpp:150-159)
             } else {
+                Intersection its;
                 fillIntersection(S, o, d, h, its);
-                bsdfP = S.bsdfs + its.bsdf;
+                const BsdfRecord &bsdf = S.bsdfs[its.bsdf];
 
                 // ---- emitted radiance: directly visible (first hit) or reached by BSDF sampling (MIS)
                 if (its.emitter >= 0) {
@@ -680,130 +705,121 @@ __global__ void __launch_bounds__(kShadeThreads, PG_SHADE_BLOCKS) k_shade(ShadeA
                 if (!terminate && (((int)depth >= cfg.maxDepth && cfg.maxDepth > 0) ||
                                    (cfg.strictNormals && dot(d, its.geoN) * its.wi.z >= 0)))
                     terminate = true;
-                if (!terminate) {
-                    shadeIt = true;
-                    btype = bsdfP->typeFlags;
-                    // guided vertex: smooth BSDF only -- delta lobes are never guided
-                    guided = A.G.enabled && (btype & kSmooth);
-                    if (guided) gcell = guideLookup(A.G, its.p);
-                }
-            }
-        }
-        // random numbers in the order the reference consumes them: emitter sample, then the direction sample
-        float2 uNee = make_float2(0.0f, 0.0f), u12 = make_float2(0.0f, 0.0f);
-        float u0 = 0.0f;
-        bool fromField = false;  // the direction comes from the guiding mixture (probability alpha)
-        const bool nee = shadeIt && cfg.useNee && (btype & kSmooth);
-        if (nee) uNee = rng.next2D();
-        if (guided) {
-            u0 = rng.next1D();
-            u12 = rng.next2D();
-            fromField = u0 < A.G.alpha;
-            if (fromField) u0 /= A.G.alpha;
-        }
-        int lobe = 0;
-#if PG_SHADE_COOP
-        if (A.G.enabled) lobe = guideSelectCoop(A.G, sq, fromField, gcell, u0);
-#endif
 
-        // ---- phase 2: direct illumination sample (:191-219) and the sampled direction (:226-238)
-        bool neePending = false, ok = true;
-        float neeBsdfPdf = 0.0f, neeLightPdf = 0.0f, pb = 0.0f, bPdf = 0.0f, bEta = 1.0f;
-        float3 neeContrib = f3(0.0f), fcos = f3(0.0f), wo = f3(0.0f), woL = f3(0.0f), bsdfWeight = f3(0.0f);
-        uint32_t sampledType = 0;
-        if (shadeIt) {
-            const BsdfRecord &bsdf = *bsdfP;
-            // At a guided vertex the MIS weight of the emitter sample needs the mixture pdf of the light direction; it is
-            // evaluated together with the pdf of the sampled direction in ONE pass over the cell's lobes below.
-            if (nee) {
-                const float3 refN = (btype & (kTransmission | kBackSide)) == 0 ? its.sh.n : f3(0.0f);  // records.inl:160-164
-                DirectSample dRec;
-                const float3 value = sampleEmitterDirect(S, its.p, refN, uNee, dRec);
-                if (!isZero(value)) {
-                    const float3 woLn = its.sh.toLocal(dRec.d);
-                    const float3 bsdfVal = bsdfEval(bsdf, its.wi, woLn);
-                    if (!isZero(bsdfVal) && (!cfg.strictNormals || dot(its.geoN, dRec.d) * woLn.z > 0)) {
-                        neeBsdfPdf = bsdfPdf(bsdf, its.wi, woLn);
-                        neeLightPdf = dRec.pdf;
-                        neeContrib = thr * value * bsdfVal;
-                        shO = its.p;
-                        shD = dRec.d;
-                        shMaxT = dRec.dist * (1 - kShadowEpsilon);  // scene.cpp:883-884
-                        neePending = true;
+                if (!terminate) {
+                    // ---- direct illumination sampling (:191-219)
+                    const uint32_t btype = bsdf.typeFlags;
+                    // guided vertex: smooth BSDF only -- delta lobes are never guided
+                    const bool guided = A.G.enabled && (btype & kSmooth);
+                    const uint32_t gcell = guided ? guideLookup(A.G, its.p) : 0u;
+                    // NEE (:191-219) and BSDF sampling (:226-238). The BSDF code (microfacet models, Fresnel terms, the rough
+                    // transmittance table) is the bulk of this kernel's instructions, and its instruction-cache footprint decides how
+                    // divergent warps fare (ncu, C4: `no_instruction` was the top stall with every call inlined twice). So each of
+                    // bsdfEval / bsdfPdf / bsdfSample has ONE call site: the emitter direction and the direction drawn from the guiding
+                    // mixture go through the same two-trip loop, and guided / unguided vertices share the bsdfSample call.
+                    // Random numbers are drawn in the order the reference consumes them (emitter sample, then the direction sample).
+                    bool neePending = false;
+                    float neeBsdfPdf = 0.0f, neeLightPdf = 0.0f;
+                    float3 neeContrib = f3(0.0f);
+                    float3 neeValue = f3(0.0f), neeWoL = f3(0.0f);
+                    DirectSample dRec;
+                    dRec.d = f3(0.0f);
+                    dRec.dist = dRec.pdf = 0.0f;
+                    bool neeTry = false;
+                    if (cfg.useNee && (btype & kSmooth)) {
+                        const float3 refN = (btype & (kTransmission | kBackSide)) == 0 ? its.sh.n : f3(0.0f);  // records.inl:160-164
+                        const float2 u = rng.next2D();
+                        neeValue = sampleEmitterDirect(S, its.p, refN, u, dRec);
+                        neeTry = !isZero(neeValue);
+                        if (neeTry) neeWoL = its.sh.toLocal(dRec.d);
+                    }
+                    float bPdf = 0.0f, bEta = 1.0f, pb = 0.0f;
+                    uint32_t sampledType = 0;
+                    float3 woL = f3(0.0f), wo = f3(0.0f), bsdfWeight = f3(0.0f), fcos = f3(0.0f);
+                    // one-sample MIS between the guiding mixture (probability alpha) and the BSDF
+                    float u0 = guided ? rng.next1D() : 1.0f;
+                    const float2 u12 = rng.next2D();
+                    const bool fromField = guided && u0 < A.G.alpha;
+                    if (fromField) {
+                        u0 /= A.G.alpha;
+                        wo = guideSample(A.G, gcell, u0, u12.x, u12.y);
+                        woL = its.sh.toLocal(wo);
+                        bEta = 1.0f;
+                        sampledType = kGlossyReflection;
+                    }
+#pragma unroll 1
+                    for (int pass = 0; pass < 2; ++pass) {  // 0: emitter direction, 1: direction from the guiding mixture
+                        if (!(pass ? fromField : neeTry)) continue;
+                        const float3 dl = pass ? woL : neeWoL;
+                        const float3 f = bsdfEval(bsdf, its.wi, dl);
+                        if (pass) {
+                            fcos = f;
+                            pb = bsdfPdf(bsdf, its.wi, dl);
+                        } else if (!isZero(f) && (!cfg.strictNormals || dot(its.geoN, dRec.d) * dl.z > 0)) {
+                            neeBsdfPdf = bsdfPdf(bsdf, its.wi, dl);
+                            neeLightPdf = dRec.pdf;
+                            neeContrib = thr * neeValue * f;
+                            shO = its.p;
+                            shD = dRec.d;
+                            shMaxT = dRec.dist * (1 - kShadowEpsilon);  // scene.cpp:883-884
+                            neePending = true;
+                        }
+                    }
+                    bool ok = true;
+                    if (!fromField) {
+                        const float3 w = bsdfSample(bsdf, its.wi, u12, woL, pb, bEta, sampledType);
+                        wo = its.sh.toWorld(woL);
+                        if (guided) {
+                            ok = !isZero(w);
+                            fcos = w * pb;
+                        } else {
+                            bsdfWeight = w;
+                            bPdf = pb;
+                        }
+                    }
+                    if (guided) {
+                        // one pass over the cell's lobes for both directions (a single code path keeps the warp converged;
+                        // an unused direction is evaluated on a dummy and discarded)
+                        float gNee = 0.0f, gWo = 0.0f;
+                        if (neePending || ok) guidePdf2(A.G, gcell, neePending ? shD : wo, ok ? wo : shD, gNee, gWo);
+                        if (neePending) neeBsdfPdf = A.G.alpha * gNee + (1 - A.G.alpha) * neeBsdfPdf;
+                        bPdf = ok ? A.G.alpha * gWo + (1 - A.G.alpha) * pb : 0.0f;
+                        bsdfWeight = (ok && !isZero(fcos) && bPdf > 0) ? fcos / bPdf : f3(0.0f);
+                    }
+                    if (neePending) {
+                        shC = neeContrib * miWeight(neeLightPdf, neeBsdfPdf);
+                        wantShadow = true;
+                    }
+                    if (isZero(bsdfWeight)) {
+                        terminate = true;
+                    } else {
+                        if (cfg.strictNormals && dot(its.geoN, wo) * woL.z <= 0) {
+                            terminate = true;
+                        } else {
+                            thr *= bsdfWeight;  // (:271-272; a miss of the new ray terminates next bounce)
+                            eta *= bEta;
+                            newO = its.p;
+                            newD = wo;
+                            newPdf = bPdf;
+                            fl &= ~(kFlagFirst | kFlagPrevDelta);
+                            if (sampledType & kDelta) fl |= kFlagPrevDelta;
+                            if (sampledType != kNull) fl |= kFlagScattered;
+                            alive = true;
+                            if (A.G.record && (btype & kSmooth) && (int)vcount < A.G.maxVerts) {
+                                guideVertexOpen(A.G, slot, vcount, its.p, bPdf, wo);
+                                vcount++;
+                                fl &= ~kFlagVertexClosed;
+                            }
+                        }
                     }
                 }
             }
-            if (guided) {
-                // one-sample MIS between the guiding mixture (probability alpha) and the BSDF
-                if (fromField) {
-#if PG_SHADE_COOP
-                    wo = guideSampleLobe(A.G, gcell, lobe, u12.x, u12.y);
-#else
-                    wo = guideSample(A.G, gcell, u0, u12.x, u12.y);
-#endif
-                    woL = its.sh.toLocal(wo);
-                    fcos = bsdfEval(bsdf, its.wi, woL);
-                    pb = bsdfPdf(bsdf, its.wi, woL);
-                    bEta = 1.0f;
-                    sampledType = kGlossyReflection;
-                } else {
-                    const float3 w = bsdfSample(bsdf, its.wi, u12, woL, pb, bEta, sampledType);
-                    ok = !isZero(w);
-                    fcos = w * pb;
-                    wo = its.sh.toWorld(woL);
-                }
-            } else {
-                bsdfWeight = bsdfSample(bsdf, its.wi, rng.next2D(), woL, bPdf, bEta, sampledType);
-                wo = its.sh.toWorld(woL);
-            }
-        }
-        // mixture pdf of both directions (an unused direction is evaluated on a dummy and discarded)
-        float gNee = 0.0f, gWo = 0.0f;
-#if PG_SHADE_COOP
-        if (A.G.enabled)
-            guidePdf2Coop(A.G, sq, guided && (neePending || ok), gcell, neePending ? shD : wo, ok ? wo : shD, gNee, gWo);
-#else
-        if (guided && (neePending || ok)) guidePdf2(A.G, gcell, neePending ? shD : wo, ok ? wo : shD, gNee, gWo);
-        (void)sq; (void)lobe;
-#endif
-
-        // ---- phase 3: weights, next ray
-        if (shadeIt) {
-            if (guided) {
-                if (neePending) neeBsdfPdf = A.G.alpha * gNee + (1 - A.G.alpha) * neeBsdfPdf;
-                bPdf = ok ? A.G.alpha * gWo + (1 - A.G.alpha) * pb : 0.0f;
-                bsdfWeight = (ok && !isZero(fcos) && bPdf > 0) ? fcos / bPdf : f3(0.0f);
-            }
-            if (neePending) {
-                shC = neeContrib * miWeight(neeLightPdf, neeBsdfPdf);
-                wantShadow = true;
-            }
-            if (isZero(bsdfWeight)) {
-                terminate = true;
-            } else if (cfg.strictNormals && dot(its.geoN, wo) * woL.z <= 0) {
-                terminate = true;
-            } else {
-                thr *= bsdfWeight;  // (:271-272; a miss of the new ray terminates next bounce)
-                eta *= bEta;
-                newO = its.p;
-                newD = wo;
-                newPdf = bPdf;
-                fl &= ~(kFlagFirst | kFlagPrevDelta);
-                if (sampledType & kDelta) fl |= kFlagPrevDelta;
-                if (sampledType != kNull) fl |= kFlagScattered;
+            if (terminate && wantShadow) {
+                // park the record for one bounce so that the shadow ray has somewhere to land
                 alive = true;
-                if (A.G.record && (btype & kSmooth) && (int)vcount < A.G.maxVerts) {
-                    guideVertexOpen(A.G, slot, vcount, its.p, bPdf, wo);
-                    vcount++;
-                    fl &= ~kFlagVertexClosed;
-                }
+                fl |= kFlagDead;
+                terminate = false;
             }
-        }
-        if (valid && terminate && wantShadow) {
-            // park the record for one bounce so that the shadow ray has somewhere to land
-            alive = true;
-            fl |= kFlagDead;
-            terminate = false;
         }
 
         // ---- compaction into the next queue / shadow queue (one atomic per block each)
@@ -985,6 +1001,10 @@ void launchTrace(const DeviceScene &S, const PathState &P, float4 *hits, const u
         k_trace<true, false><<<grid, 128, 0, st>>>(S, P.rayO, P.rayD, P.flags, hits, nPtr, work, C, none);
     else
         k_trace<false, false><<<grid, 128, 0, st>>>(S, P.rayO, P.rayD, P.flags, hits, nPtr, work, C, none);
+}
+void launchHitPartition(const float4 *hits, const uint32_t *flags, const uint32_t *nPtr, uint32_t *perm, uint32_t *cntNeed,
+                        uint32_t *cntRest, cudaStream_t st) {
+    k_hit_partition<<<numSMs() * 4, 256, 0, st>>>(hits, flags, nPtr, perm, cntNeed, cntRest);
 }
 void launchShadow(const DeviceScene &S, const ShadowQueue &Q, float4 *rad, const uint32_t *nPtr, uint32_t *work, Counters *C,
                   bool count, bool speculative, cudaStream_t st) {

@@ -65,6 +65,8 @@ struct Counters {
     uint32_t shadowWork[260];
     uint32_t lookWork[260];    // volumetric tracking stages (volpath.cu)
     uint32_t trackWork[260];
+    uint32_t partNeed[260];    // hit / miss partition of the shade queue (k_hit_partition): entries placed at the front / back
+    uint32_t partRest[260];
     uint32_t misc[16];
     unsigned long long paths, normalRays, shadowRays, pathLen, nodesVisited, primsTested, trainSamples;
 };
