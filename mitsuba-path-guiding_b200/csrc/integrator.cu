@@ -35,9 +35,9 @@ namespace pg {
 // launch wrappers implemented in kernels.cu
 void launchGenerate(const DeviceScene &S, const BatchDesc &B, const PathState &P, Counters *C, cudaStream_t st);
 void launchTrace(const DeviceScene &S, const PathState &P, float4 *hits, const uint32_t *nPtr, uint32_t *work, Counters *C,
-                 bool count, const SortArgs *sort, bool speculative, cudaStream_t st);
+                 bool count, const SortArgs *sort, bool speculative, TailList T, uint32_t *tailWork, cudaStream_t st);
 void launchShadow(const DeviceScene &S, const ShadowQueue &Q, float4 *rad, const uint32_t *nPtr, uint32_t *work, Counters *C,
-                  bool count, bool speculative, cudaStream_t st);
+                  bool count, bool speculative, TailList T, uint32_t *tailWork, cudaStream_t st);
 void launchShade(const ShadeArgs &A, cudaStream_t st);
 void launchHitPartition(const float4 *hits, const uint32_t *flags, const uint32_t *nPtr, uint32_t *perm, uint32_t *cntNeed,
                         uint32_t *cntRest, cudaStream_t st);
@@ -56,7 +56,7 @@ void launchMediumTest(const DeviceScene &S, int medium, const float4 *rays, uint
 void launchFilmExport(const float4 *film, float *out, uint32_t n, int develop, cudaStream_t st);
 void launchSplat(const FilmRecord &F, float4 *film, const float4 *splat, uint32_t n, float maxComponentValue, cudaStream_t st);
 void launchTraceRays(const DeviceScene &S, const float4 *rays, uint32_t n, float4 *hits, uint32_t *work, Counters *C, bool shadow,
-                     bool count, bool speculative, cudaStream_t st);
+                     bool count, bool speculative, TailList T, uint32_t *tailWork, cudaStream_t st);
 void launchFilmSplat(const FilmRecord &F, float4 *film, const float2 *pos, const float3 *rgb, uint32_t n, float maxComponentValue,
                      cudaStream_t st);
 void launchBsdfTest(const DeviceScene &S, int bsdfIndex, const float *wi, const float *wo, const float *u, uint32_t n, float *outEval,
@@ -119,6 +119,7 @@ struct Integrator {
         DevBuf<uint4> dShAux;
         DevBuf<float4> dTrkA, dTrkB, dLookL;
         DevBuf<uint32_t> dSortKey, dSortRank, dSortPerm, dBinCount, dBinOffset;
+        DevBuf<uint32_t> dTail, dShTail;  // long rays handed to the cooperative traversal kernel (closest / shadow queues)
         DevBuf<Counters> dCounters;
         size_t capacity = 0;
     };
@@ -147,6 +148,18 @@ struct Integrator {
     // the wide tree only from this bounce on (late bounces hold few rays and are bound by the dependent-load chains of single
     // long rays, where three binary levels per visit pay; the bulk bounces are issue-bound on the wide node test)
     int wideFrom = std::getenv("B200PG_WIDE_FROM") ? std::atoi(std::getenv("B200PG_WIDE_FROM")) : 0;
+    // node-visit budget of a ray before it is handed to the warp-cooperative kernel (kernels.cu: k_trace_tail); 0 = off. Default:
+    // 96 when the BVH has >= 64 k nodes (a ray can only get that long in a deep tree), else off.
+    int tailVisits = std::getenv("B200PG_TAIL_VISITS") ? std::atoi(std::getenv("B200PG_TAIL_VISITS")) : -1;
+    uint32_t tailBudget() const {
+        if (tailVisits >= 0) return (uint32_t)tailVisits;
+        return scene->nodes.size() >= (64u << 10) ? 96u : 0u;
+    }
+    int tailVisitsSmall = std::getenv("B200PG_TAIL_VISITS_SMALL") ? std::atoi(std::getenv("B200PG_TAIL_VISITS_SMALL")) : -1;
+    TailList tailList(uint32_t *list, uint32_t *count) const {
+        const uint32_t v = tailBudget();
+        return TailList{list, count, v, tailVisitsSmall >= 0 ? (uint32_t)tailVisitsSmall : v};
+    }
     int traceSpec = std::getenv("B200PG_TRACE_SPEC") ? std::atoi(std::getenv("B200PG_TRACE_SPEC")) : 3;
     // hit / miss partition of the shade queue (kernels.cu: k_hit_partition) on bounces where, in the previous progression, fewer
     // than half of the queued paths still had a vertex to shade (open scenes: most bounce rays leave). 0 = never, 1 = adaptive
@@ -320,6 +333,7 @@ struct Integrator {
             L.dShAux.alloc(n); L.dTrkA.alloc(n); L.dTrkB.alloc(n); L.dLookL.alloc(n);
         }
         L.dSortKey.alloc(n); L.dSortRank.alloc(n); L.dSortPerm.alloc(n);
+        L.dTail.alloc(n); L.dShTail.alloc(n);
         L.capacity = n;
     }
 
@@ -427,7 +441,8 @@ struct Integrator {
                 DeviceScene Sb = S;
                 if (b < wideFrom) Sb.wideNodes = nullptr;
                 launchTrace(Sb, cur[l], L.dHits.p, &C->queue[b], &C->traceWork[b], C, countTraversal, sorted ? &sortArgs[l] : nullptr,
-                            (traceSpec & (b == 0 ? 4 : 1)) != 0, st[l]);
+                            (traceSpec & (b == 0 ? 4 : 1)) != 0, tailList(L.dTail.p, &C->tailCount[b]), &C->tailWork[b], st[l]);
+                if (tailBudget() && !sorted && !Sb.wideNodes) stats.kernel_launches++;
                 if (sorted) stats.kernel_launches += 2;
                 spanEnd(kTimeTrace, t, st[l]);
                 if (b == 0 && featureBuffers && !radianceOut) {
@@ -436,6 +451,12 @@ struct Integrator {
                 }
                 ShadeArgs &a = A[l];
                 a.perm = sorted ? L.dSortPerm.p : nullptr;
+                a.permRest = nullptr;
+                if (params.volumetric && partitionMode != 0) {  // event partition (volpath.cu), launched inside launchShadeVol
+                    a.perm = L.dSortPerm.p;
+                    a.permRest = L.dSortKey.p;
+                    stats.kernel_launches++;
+                }
                 if (partitionBounce(b, sorted)) {
                     launchHitPartition(L.dHits.p, cur[l].flags, &C->queue[b], L.dSortPerm.p, &C->partNeed[b], &C->partRest[b], st[l]);
                     stats.kernel_launches++;
@@ -461,7 +482,9 @@ struct Integrator {
                 if (params.volumetric)
                     launchShadowVol(S, a.shadow, next[l].rad, &C->shadow[b], &C->shadowWork[b], C, ss);
                 else
-                    launchShadow(Sb, a.shadow, next[l].rad, &C->shadow[b], &C->shadowWork[b], C, countTraversal, (traceSpec & 2) != 0, ss);
+                    launchShadow(Sb, a.shadow, next[l].rad, &C->shadow[b], &C->shadowWork[b], C, countTraversal, (traceSpec & 2) != 0,
+                                 tailList(L.dShTail.p, &C->shTailCount[b]), &C->shTailWork[b], ss);
+                if (!params.volumetric && (traceSpec & 2) && tailBudget() && !Sb.wideNodes) stats.kernel_launches++;
                 spanEnd(kTimeShadow, t, ss);
                 if (overlapShadow) CUDA_OK(cudaEventRecord(L.evShadow, ss));
                 stats.kernel_launches += 3;
@@ -1293,6 +1316,7 @@ int b200pg_set_option(void *integ, const char *name, int value) {
     else if (n == "overlap_shadow") self->overlapShadow = value != 0;
     else if (n == "lanes") self->lanes = std::max(1, std::min((int)Integrator::kMaxLanes, value));
     else if (n == "partition") self->partitionMode = value;
+    else if (n == "tail_visits") self->tailVisits = value;
     else if (n == "lane_major") self->laneMajor = value != 0;
     else if (n == "feature_buffers") {
         self->featureBuffers = value != 0;
@@ -1361,13 +1385,14 @@ int b200pg_scene_upload(void *integ, size_t *bytes) {
 int b200pg_k_trace_device(void *integ, const void *d_rays, size_t n, int shadow, void *d_hits, float *ms, uint64_t *counts) {
     PG_TRY(integ)
     Counters *C = self->lane[0].dCounters.p;
-    CUDA_OK(cudaMemsetAsync(&C->misc[0], 0, sizeof(uint32_t), self->stream));
+    CUDA_OK(cudaMemsetAsync(&C->misc[0], 0, 3 * sizeof(uint32_t), self->stream));  // work cursor, tail count, tail cursor
+    self->lane[0].dTail.alloc(n);
     if (counts) {
         CUDA_OK(cudaMemsetAsync(&C->nodesVisited, 0, 2 * sizeof(unsigned long long), self->stream));
     }
     CUDA_OK(cudaEventRecord(self->ev[0], self->stream));
     launchTraceRays(self->S, (const float4 *)d_rays, (uint32_t)n, (float4 *)d_hits, &C->misc[0], C, shadow != 0, counts != nullptr,
-                    (self->traceSpec & (shadow ? 2 : 1)) != 0, self->stream);
+                    (self->traceSpec & (shadow ? 2 : 1)) != 0, self->tailList(self->lane[0].dTail.p, &C->misc[1]), &C->misc[2], self->stream);
     CUDA_OK(cudaEventRecord(self->ev[1], self->stream));
     CUDA_OK(cudaStreamSynchronize(self->stream));
     CUDA_OK(cudaGetLastError());

@@ -163,10 +163,164 @@ __global__ void __launch_bounds__(256) k_generate(DeviceScene S, BatchDesc B, Pa
 // Traversal. One thread per ray, warps fetch 32 rays at a time from a device work counter
 // (dynamic load balancing: rays of one queue differ a lot in traversal length).
 // ------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------
+// Long rays. On an open scene a few grazing rays need several hundred node visits (bvhsim, 10 M-triangle terrain: 99.9 %
+// quantile 142, maximum 516 against a mean of 26): one dependent L2 / DRAM round trip per visit, ~0.5 us each, while the
+// rest of the GPU idles -- per step of that config bounces 2-5 took 490-820 us each for < 10 % of the rays, ~3 ms of the 4.6 ms
+// traversal time. The traversal kernels therefore give a ray a budget of node visits (TailList::visits); a ray that needs more (and whatever
+// a warp still holds once the queue has run dry and kTailLanes or fewer lanes are busy) goes to a tail list, and
+// k_trace_tail finishes it with a whole WARP: its pending subtrees sit on a shared-memory stack, every lane pops one entry
+// per round, tests that node's two children (or that leaf's primitives) and pushes what the ray enters; the closest hit is
+// a warp-wide minimum per round. A ray that misses everything -- the common case for the long ones -- has no ordering
+// constraint at all, so the dependent chain shrinks from the number of visits to roughly the depth of the tree.
+// Same node and primitive tests as traceRay(); a round prunes with the hit distance of the previous round, so a few more
+// nodes are tested than sequentially. Exact-t ties between two primitives (shared edges) go to the lower primitive slot.
+// ------------------------------------------------------------------------------------------
+// The budget is a launch parameter (TailList::visits, integrator.cu: 96 for scenes whose BVH is deep enough to have such rays, 0 =
+// off for the Cornell-size scenes, where the extra launches cost more than they can save; measured on C4: 64 / 96 / 160 visits ->
+// 546 / 595 / 583 M paths/s, kTailLanes 0 / 4 / 12 -> 572 / 595 / 573).
+#ifndef PG_TAIL_LANES
+#define PG_TAIL_LANES 4
+#endif
+static constexpr int kTailLanes = PG_TAIL_LANES;
+
+// all lanes of a converged warp; lanes with `pred` append rayIdx
+PG_DEV void tailDefer(const TailList &T, bool pred, uint32_t rayIdx) {
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (!m) return;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if ((int)laneId() == leader) base = atomicAdd(T.count, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pred) T.list[base + (uint32_t)__popc(m & ((1u << laneId()) - 1u))] = rayIdx;
+}
+
+// traceRay() with the visit budget: false + aborted = true when the ray needs more than `budget` node visits
+template <bool kCount>
+PG_DEV void traceRayBudget(const DeviceScene &S, float3 o, float3 d, float mint, float maxt, Hit &hit, uint32_t budget, bool &aborted,
+                           uint32_t *cntNodes, uint32_t *cntPrims) {
+    const float3 idir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    int stack[kTraceStack];
+    int sp = 0, node = 0;
+    uint32_t visits = 0;
+    hit.prim = kMiss;
+    hit.t = maxt;
+    float tmax = maxt;
+    aborted = false;
+    while (true) {
+        while (node >= 0) {
+            if (kCount) (*cntNodes)++;
+            if (++visits > budget) {
+                aborted = true;
+                return;
+            }
+            node = bvhNodeStep(S, node, o, idir, mint, tmax, stack, sp);
+        }
+        if (node == kDoneNode) break;
+        bvhLeafStep<false, kCount>(S, node, o, d, mint, tmax, hit, cntPrims);
+        node = sp ? stack[--sp] : kDoneNode;
+        if (node == kDoneNode) break;
+    }
+}
+
+// entries per warp. Up to kCoopWide entries a round takes up to 32 of them (and pushes at most 64: <= kCoopWide + 32 afterwards);
+// above that it takes one -- a depth-first walk, which adds at most the tree depth (<= kTraceStack = 64) on top.
+static constexpr int kCoopStack = 320, kCoopWide = 192;
+
+// One ray, served by all 32 lanes (every lane holds the same ray; `hit` comes back identical in all lanes). cs = the warp's
+// shared-memory stack.
+template <bool kAnyHit, bool kCount>
+PG_DEV void traceRayCooperative(const DeviceScene &S, int *cs, float3 o, float3 d, float mint, float tmax, Hit &best, uint32_t &cntNodes,
+                                uint32_t &cntPrims) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const int lane = (int)laneId();
+    const float3 idir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    best.prim = kMiss;
+    best.t = tmax;
+    best.u = best.v = 0.0f;
+    int top = 1;
+    if (lane == 0) cs[0] = 0;  // the root
+    __syncwarp();
+    bool found = false;
+    while (top > 0 && !found) {
+        const int take = top > kCoopWide ? 1 : min(top, 32);
+        const int entry = lane < take ? cs[top - 1 - lane] : kDoneNode;
+        top -= take;
+        __syncwarp();
+        int c0 = kDoneNode, c1 = kDoneNode, nh = 0;
+        Hit cand;
+        cand.prim = kMiss;
+        cand.t = kInf;
+        cand.u = cand.v = 0.0f;
+        if (entry >= 0) {
+            if (kCount) cntNodes++;
+            nh = bvhTestNode(S, entry, o, idir, mint, tmax, c0, c1);
+        } else if (entry != kDoneNode) {
+            float tm = tmax;
+            if (bvhLeafStep<kAnyHit, kCount>(S, entry, o, d, mint, tm, cand, &cntPrims)) cand.t = 0.0f;  // any-hit: found
+        }
+        // push: the farther children first, the nearer ones on top (lane 0's on the very top)
+        const unsigned mFar = __ballot_sync(kFull, nh == 2), mNear = __ballot_sync(kFull, nh >= 1);
+        if (nh == 2) cs[top + __popc(mFar & ((1u << lane) - 1u))] = c1;
+        if (nh >= 1) cs[top + __popc(mFar) + __popc(mNear >> lane) - 1] = c0;
+        top += __popc(mFar) + __popc(mNear);
+        // closest candidate of the round (non-negative floats order like their bit patterns)
+        const unsigned mHit = __ballot_sync(kFull, cand.prim != kMiss);
+        if (mHit) {
+            if (kAnyHit) {
+                best.prim = __shfl_sync(kFull, cand.prim, __ffs(mHit) - 1);
+                found = true;
+            } else {
+                const uint32_t tb = cand.prim != kMiss ? __float_as_uint(cand.t) : 0x7F800000u;
+                const uint32_t tmin = __reduce_min_sync(kFull, tb);
+                const uint32_t pmin = __reduce_min_sync(kFull, tb == tmin ? cand.prim : 0xFFFFFFFFu);
+                const unsigned mWin = __ballot_sync(kFull, tb == tmin && cand.prim == pmin);
+                const int win = __ffs(mWin) - 1;
+                const float tw = __uint_as_float(tmin);
+                const float wu = __shfl_sync(kFull, cand.u, win), wv = __shfl_sync(kFull, cand.v, win);
+                if (tw < tmax || (tw == tmax && pmin < best.prim)) {
+                    best.prim = pmin;
+                    best.t = tw;
+                    best.u = wu;
+                    best.v = wv;
+                    tmax = tw;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// The tail kernel: one warp per listed ray, from the root.
+template <bool kAnyHit, bool kCount, typename Queue>
+__global__ void __launch_bounds__(128) k_trace_tail(DeviceScene S, Queue Q, TailList T, uint32_t *work, Counters *C) {
+    __shared__ int sStack[4][kCoopStack];
+    int *cs = sStack[threadIdx.x >> 5];
+    const uint32_t n = *T.count;
+    uint32_t cn = 0, cp = 0;
+    while (true) {
+        uint32_t k = 0;
+        if (laneId() == 0) k = atomicAdd(work, 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= n) break;
+        const uint32_t i = T.list[k];
+        float3 o, d;
+        float mint, tmax;
+        Q.refetch(i, o, d, mint, tmax);  // every lane reads the same ray (broadcast)
+        Hit hit;
+        traceRayCooperative<kAnyHit, kCount>(S, cs, o, d, mint, tmax, hit, cn, cp);
+        if (laneId() == 0) Q.finish(i, hit);
+    }
+    if (kCount) {
+        warpAddU64(&C->nodesVisited, cn);
+        warpAddU64(&C->primsTested, cp);
+    }
+}
+
 template <bool kCount, bool kKey>
 __global__ void __launch_bounds__(128) k_trace(DeviceScene S, const float4 *__restrict__ rayO, const float4 *__restrict__ rayD,
                                                const uint32_t *__restrict__ flags, float4 *__restrict__ hits,
-                                               const uint32_t *nPtr, uint32_t *work, Counters *C, SortArgs Q) {
+                                               const uint32_t *nPtr, uint32_t *work, Counters *C, SortArgs Q, TailList T) {
     const uint32_t n = *nPtr;
     unsigned long long rays = 0;
     uint32_t cn = 0, cp = 0;
@@ -177,6 +331,7 @@ __global__ void __launch_bounds__(128) k_trace(DeviceScene S, const float4 *__re
         if (base >= n) break;
         const uint32_t i = base + laneId();
         uint32_t bin = 0xFFFFFFFFu;  // lanes past the end of the queue
+        bool aborted = false;
         if (i < n) {
             Hit h;
             h.prim = kMiss;
@@ -187,7 +342,8 @@ __global__ void __launch_bounds__(128) k_trace(DeviceScene S, const float4 *__re
                 const float4 ro = rayO[i], rd = rayD[i];
                 const float3 o = f3(ro.x, ro.y, ro.z), d = f3(rd.x, rd.y, rd.z);
                 const float mint = adaptiveMinT(o, ro.w, false);
-                traceRay<false, kCount>(S, o, d, mint, rd.w, h, &cn, &cp);
+                if (kKey) traceRay<false, kCount>(S, o, d, mint, rd.w, h, &cn, &cp);
+                else traceRayBudget<kCount>(S, o, d, mint, rd.w, h, T.visits ? T.budget(n) : 0xFFFFFFFFu, aborted, &cn, &cp);
                 if (h.prim == kMiss) h.t = kInf;
                 else if (kKey) {  // guiding cell of the hit point (ordering only: the shade stage looks its cell up itself)
                     const float3 p = o + d * h.t;
@@ -200,8 +356,9 @@ __global__ void __launch_bounds__(128) k_trace(DeviceScene S, const float4 *__re
                 }
                 rays++;
             }
-            hits[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+            if (!aborted) hits[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
         }
+        if (!kKey) tailDefer(T, aborted, i);  // k_trace_tail writes the hit record of a deferred ray
         if (kKey) {  // rank inside the bin: one atomic per distinct bin of the warp
             const uint32_t peers = __match_any_sync(0xffffffffu, bin);
             const int leader = __ffs(peers) - 1;
@@ -264,10 +421,13 @@ struct TraceStack<true> {
 
 template <bool kAnyHit, bool kCount, bool kWide, typename Queue>
 PG_DEV void traceQueueSpeculative(const DeviceScene &S, Queue Q, uint32_t n, uint32_t *work, uint32_t &cntNodes, uint32_t &cntPrims,
-                                  unsigned long long &cntRays) {
+                                  unsigned long long &cntRays, TailList T) {
     constexpr unsigned kFull = 0xffffffffu;
+    const bool kTail = !kWide && T.visits > 0;  // the cooperative kernel walks the binary tree
+    const uint32_t budget = T.budget(n);
     TraceStack<kWide> stack;
     int sp = 0, node = kDoneNode, leaf = 0;
+    uint32_t visits = 0;
     uint32_t rayIdx = 0xFFFFFFFFu;
     float3 o = f3(0.0f), d = f3(0.0f), idir = f3(0.0f);
     float mint = 0.0f, tmax = 0.0f;
@@ -293,6 +453,7 @@ PG_DEV void traceQueueSpeculative(const DeviceScene &S, Queue Q, uint32_t n, uin
                     node = 0;
                     sp = 0;
                     leaf = 0;
+                    visits = 0;
                     hit.prim = kMiss;
                     hit.t = tmax;
                     hit.u = hit.v = 0.0f;
@@ -302,10 +463,20 @@ PG_DEV void traceQueueSpeculative(const DeviceScene &S, Queue Q, uint32_t n, uin
             idle = __ballot_sync(kFull, rayIdx == 0xFFFFFFFFu);
         }
         if (idle == kFull) break;
+        if (kTail) {
+            // over budget, or the last few rays of a drained queue: hand them to the cooperative kernel
+            const bool last = exhausted && __popc(~idle) <= kTailLanes;
+            const bool defer = rayIdx != 0xFFFFFFFFu && (last || visits > budget);
+            tailDefer(T, defer, rayIdx);
+            if (defer) rayIdx = 0xFFFFFFFFu, node = kDoneNode, leaf = 0;
+            if (last) break;
+            if (__ballot_sync(kFull, rayIdx != 0xFFFFFFFFu) == 0u) continue;  // everything deferred: refill
+        }
         // ---- speculative descent: until every lane with a ray holds a leaf (or has nothing left to visit)
         while (__any_sync(kFull, node >= 0 && leaf == 0)) {
             if (node >= 0) {
                 if (kCount) cntNodes++;
+                visits++;
                 node = stack.step(S, node, o, idir, mint, tmax, sp);
                 if (node < 0 && node != kDoneNode && leaf == 0) {  // first leaf: postpone it, continue with the next subtree
                     leaf = node;
@@ -355,6 +526,13 @@ struct ClosestQueue {  // the wavefront's ray queue (path state) -> hit records
         hits[i] = h.prim == kMiss ? make_float4(kInf, 0.0f, 0.0f, __uint_as_float(kMiss))
                                   : make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
     }
+    PG_DEV void refetch(uint32_t i, float3 &o, float3 &d, float &mint, float &tmax) const {  // a ray that passed fetch() before
+        const float4 ro = rayO[i], rd = rayD[i];
+        o = f3(ro.x, ro.y, ro.z);
+        d = f3(rd.x, rd.y, rd.z);
+        mint = adaptiveMinT(o, ro.w, false);
+        tmax = rd.w;
+    }
 };
 struct ShadowRayQueue {  // shadow queue -> adds the contribution of unoccluded rays to the path record
     ShadowQueue Q;
@@ -372,6 +550,13 @@ struct ShadowRayQueue {  // shadow queue -> adds the contribution of unoccluded 
             return false;
         }
         return true;
+    }
+    PG_DEV void refetch(uint32_t i, float3 &o, float3 &d, float &mint, float &tmax) const {
+        const float4 ro = Q.o[i], rd = Q.d[i];
+        o = f3(ro.x, ro.y, ro.z);
+        d = f3(rd.x, rd.y, rd.z);
+        mint = adaptiveMinT(o, ro.w, true);
+        tmax = rd.w;
     }
     PG_DEV void finish(uint32_t i, const Hit &h) const {
         if (h.prim != kMiss) return;
@@ -402,6 +587,13 @@ struct RayListQueue {  // stand-alone ray queries (b200pg_k_trace*): rays as {o,
         }
         return true;
     }
+    PG_DEV void refetch(uint32_t i, float3 &o, float3 &d, float &mint, float &tmax) const {
+        const float4 ro = rays[2 * i], rd = rays[2 * i + 1];
+        o = f3(ro.x, ro.y, ro.z);
+        d = f3(rd.x, rd.y, rd.z);
+        mint = adaptiveMinT(o, ro.w, shadow);
+        tmax = rd.w;
+    }
     PG_DEV void finish(uint32_t i, const Hit &h) const {
         // any-hit mode reports the primitive only (as k_trace_rays: t, u, v of an occluder are whatever was found first)
         hits[i] = h.prim == kMiss ? make_float4(kInf, 0.0f, 0.0f, __uint_as_float(kMiss))
@@ -409,20 +601,22 @@ struct RayListQueue {  // stand-alone ray queries (b200pg_k_trace*): rays as {o,
     }
 };
 template <bool kShadow, bool kCount, bool kWide>
-__global__ void __launch_bounds__(128) k_trace_rays_spec(DeviceScene S, RayListQueue Q, uint32_t n, uint32_t *work, Counters *C) {
+__global__ void __launch_bounds__(128) k_trace_rays_spec(DeviceScene S, RayListQueue Q, uint32_t n, uint32_t *work, Counters *C,
+                                                         TailList T) {
     unsigned long long rays = 0;
     uint32_t cn = 0, cp = 0;
-    traceQueueSpeculative<kShadow, kCount, kWide>(S, Q, n, work, cn, cp, rays);
+    traceQueueSpeculative<kShadow, kCount, kWide>(S, Q, n, work, cn, cp, rays, T);
     if (kCount) {
         warpAddU64(&C->nodesVisited, cn);
         warpAddU64(&C->primsTested, cp);
     }
 }
 template <bool kCount, bool kWide>
-__global__ void __launch_bounds__(128) k_trace_spec(DeviceScene S, ClosestQueue Q, const uint32_t *nPtr, uint32_t *work, Counters *C) {
+__global__ void __launch_bounds__(128) k_trace_spec(DeviceScene S, ClosestQueue Q, const uint32_t *nPtr, uint32_t *work, Counters *C,
+                                                    TailList T) {
     unsigned long long rays = 0;
     uint32_t cn = 0, cp = 0;
-    traceQueueSpeculative<false, kCount, kWide>(S, Q, *nPtr, work, cn, cp, rays);
+    traceQueueSpeculative<false, kCount, kWide>(S, Q, *nPtr, work, cn, cp, rays, T);
     warpAddU64(&C->normalRays, rays);
     if (kCount) {
         warpAddU64(&C->nodesVisited, cn);
@@ -430,11 +624,12 @@ __global__ void __launch_bounds__(128) k_trace_spec(DeviceScene S, ClosestQueue 
     }
 }
 template <bool kCount, bool kWide>
-__global__ void __launch_bounds__(128) k_shadow_spec(DeviceScene S, ShadowRayQueue Q, const uint32_t *nPtr, uint32_t *work, Counters *C) {
+__global__ void __launch_bounds__(128) k_shadow_spec(DeviceScene S, ShadowRayQueue Q, const uint32_t *nPtr, uint32_t *work, Counters *C,
+                                                     TailList T) {
     unsigned long long rays = 0;
     uint32_t cn = 0, cp = 0;
     const uint32_t n = *nPtr;
-    traceQueueSpeculative<true, kCount, kWide>(S, Q, n, work, cn, cp, rays);
+    traceQueueSpeculative<true, kCount, kWide>(S, Q, n, work, cn, cp, rays, T);
     // every queued shadow ray counts (the batch kernel counts empty intervals as well)
     if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&C->shadowRays, (unsigned long long)n);
     if (kCount) {
@@ -712,72 +907,55 @@ __global__ void __launch_bounds__(kShadeThreads, PG_SHADE_BLOCKS) k_shade(ShadeA
                     // guided vertex: smooth BSDF only -- delta lobes are never guided
                     const bool guided = A.G.enabled && (btype & kSmooth);
                     const uint32_t gcell = guided ? guideLookup(A.G, its.p) : 0u;
-                    // NEE (:191-219) and BSDF sampling (:226-238). The BSDF code (microfacet models, Fresnel terms, the rough
-                    // transmittance table) is the bulk of this kernel's instructions, and its instruction-cache footprint decides how
-                    // divergent warps fare (ncu, C4: `no_instruction` was the top stall with every call inlined twice). So each of
-                    // bsdfEval / bsdfPdf / bsdfSample has ONE call site: the emitter direction and the direction drawn from the guiding
-                    // mixture go through the same two-trip loop, and guided / unguided vertices share the bsdfSample call.
-                    // Random numbers are drawn in the order the reference consumes them (emitter sample, then the direction sample).
+                    // NEE (:191-219). At a guided vertex the MIS weight needs the mixture pdf of the light direction; it is
+                    // evaluated together with the pdf of the sampled direction in ONE pass over the cell's lobes below.
                     bool neePending = false;
                     float neeBsdfPdf = 0.0f, neeLightPdf = 0.0f;
                     float3 neeContrib = f3(0.0f);
-                    float3 neeValue = f3(0.0f), neeWoL = f3(0.0f);
-                    DirectSample dRec;
-                    dRec.d = f3(0.0f);
-                    dRec.dist = dRec.pdf = 0.0f;
-                    bool neeTry = false;
                     if (cfg.useNee && (btype & kSmooth)) {
                         const float3 refN = (btype & (kTransmission | kBackSide)) == 0 ? its.sh.n : f3(0.0f);  // records.inl:160-164
+                        DirectSample dRec;
                         const float2 u = rng.next2D();
-                        neeValue = sampleEmitterDirect(S, its.p, refN, u, dRec);
-                        neeTry = !isZero(neeValue);
-                        if (neeTry) neeWoL = its.sh.toLocal(dRec.d);
-                    }
-                    float bPdf = 0.0f, bEta = 1.0f, pb = 0.0f;
-                    uint32_t sampledType = 0;
-                    float3 woL = f3(0.0f), wo = f3(0.0f), bsdfWeight = f3(0.0f), fcos = f3(0.0f);
-                    // one-sample MIS between the guiding mixture (probability alpha) and the BSDF
-                    float u0 = guided ? rng.next1D() : 1.0f;
-                    const float2 u12 = rng.next2D();
-                    const bool fromField = guided && u0 < A.G.alpha;
-                    if (fromField) {
-                        u0 /= A.G.alpha;
-                        wo = guideSample(A.G, gcell, u0, u12.x, u12.y);
-                        woL = its.sh.toLocal(wo);
-                        bEta = 1.0f;
-                        sampledType = kGlossyReflection;
-                    }
-#pragma unroll 1
-                    for (int pass = 0; pass < 2; ++pass) {  // 0: emitter direction, 1: direction from the guiding mixture
-                        if (!(pass ? fromField : neeTry)) continue;
-                        const float3 dl = pass ? woL : neeWoL;
-                        const float3 f = bsdfEval(bsdf, its.wi, dl);
-                        if (pass) {
-                            fcos = f;
-                            pb = bsdfPdf(bsdf, its.wi, dl);
-                        } else if (!isZero(f) && (!cfg.strictNormals || dot(its.geoN, dRec.d) * dl.z > 0)) {
-                            neeBsdfPdf = bsdfPdf(bsdf, its.wi, dl);
-                            neeLightPdf = dRec.pdf;
-                            neeContrib = thr * neeValue * f;
-                            shO = its.p;
-                            shD = dRec.d;
-                            shMaxT = dRec.dist * (1 - kShadowEpsilon);  // scene.cpp:883-884
-                            neePending = true;
+                        const float3 value = sampleEmitterDirect(S, its.p, refN, u, dRec);
+                        if (!isZero(value)) {
+                            const float3 woL = its.sh.toLocal(dRec.d);
+                            const float3 bsdfVal = bsdfEval(bsdf, its.wi, woL);
+                            if (!isZero(bsdfVal) && (!cfg.strictNormals || dot(its.geoN, dRec.d) * woL.z > 0)) {
+                                neeBsdfPdf = bsdfPdf(bsdf, its.wi, woL);
+                                neeLightPdf = dRec.pdf;
+                                neeContrib = thr * value * bsdfVal;
+                                shO = its.p;
+                                shD = dRec.d;
+                                shMaxT = dRec.dist * (1 - kShadowEpsilon);  // scene.cpp:883-884
+                                neePending = true;
+                            }
                         }
                     }
-                    bool ok = true;
-                    if (!fromField) {
-                        const float3 w = bsdfSample(bsdf, its.wi, u12, woL, pb, bEta, sampledType);
-                        wo = its.sh.toWorld(woL);
-                        if (guided) {
+                    // ---- BSDF sampling (:226-238)
+                    float bPdf, bEta;
+                    uint32_t sampledType;
+                    float3 woL, wo, bsdfWeight;
+                    if (guided) {
+                        // one-sample MIS between the guiding mixture (probability alpha) and the BSDF
+                        float u0 = rng.next1D();
+                        const float2 u12 = rng.next2D();
+                        float3 fcos;
+                        float pb;
+                        bool ok = true;
+                        if (u0 < A.G.alpha) {
+                            u0 /= A.G.alpha;
+                            wo = guideSample(A.G, gcell, u0, u12.x, u12.y);
+                            woL = its.sh.toLocal(wo);
+                            fcos = bsdfEval(bsdf, its.wi, woL);
+                            pb = bsdfPdf(bsdf, its.wi, woL);
+                            bEta = 1.0f;
+                            sampledType = kGlossyReflection;
+                        } else {
+                            const float3 w = bsdfSample(bsdf, its.wi, u12, woL, pb, bEta, sampledType);
                             ok = !isZero(w);
                             fcos = w * pb;
-                        } else {
-                            bsdfWeight = w;
-                            bPdf = pb;
+                            wo = its.sh.toWorld(woL);
                         }
-                    }
-                    if (guided) {
                         // one pass over the cell's lobes for both directions (a single code path keeps the warp converged;
                         // an unused direction is evaluated on a dummy and discarded)
                         float gNee = 0.0f, gWo = 0.0f;
@@ -785,6 +963,9 @@ __global__ void __launch_bounds__(kShadeThreads, PG_SHADE_BLOCKS) k_shade(ShadeA
                         if (neePending) neeBsdfPdf = A.G.alpha * gNee + (1 - A.G.alpha) * neeBsdfPdf;
                         bPdf = ok ? A.G.alpha * gWo + (1 - A.G.alpha) * pb : 0.0f;
                         bsdfWeight = (ok && !isZero(fcos) && bPdf > 0) ? fcos / bPdf : f3(0.0f);
+                    } else {
+                        bsdfWeight = bsdfSample(bsdf, its.wi, rng.next2D(), woL, bPdf, bEta, sampledType);
+                        wo = its.sh.toWorld(woL);
                     }
                     if (neePending) {
                         shC = neeContrib * miWeight(neeLightPdf, neeBsdfPdf);
@@ -975,51 +1156,64 @@ void launchGenerate(const DeviceScene &S, const BatchDesc &B, const PathState &P
     k_generate<<<grid, 256, 0, st>>>(S, B, P, C);
 }
 void launchTrace(const DeviceScene &S, const PathState &P, float4 *hits, const uint32_t *nPtr, uint32_t *work, Counters *C,
-                 bool count, const SortArgs *sort, bool speculative, cudaStream_t st) {
+                 bool count, const SortArgs *sort, bool speculative, TailList T, uint32_t *tailWork, cudaStream_t st) {
     static int grid = persistentGrid(k_trace<false, false>, 128);
     static int gridKey = persistentGrid(k_trace<false, true>, 128);
     static int gridSpec = persistentGrid(k_trace_spec<false, false>, 128);
     static int gridWide = persistentGrid(k_trace_spec<false, true>, 128);
+    static int gridTail = persistentGrid(k_trace_tail<false, false, ClosestQueue>, 128);
     const SortArgs none = {};
+    const ClosestQueue Q = {P.rayO, P.rayD, P.flags, hits};
+    bool tail = T.visits > 0;
     if (sort) {
+        tail = false;
         if (count)
-            k_trace<true, true><<<gridKey, 128, 0, st>>>(S, P.rayO, P.rayD, P.flags, hits, nPtr, work, C, *sort);
+            k_trace<true, true><<<gridKey, 128, 0, st>>>(S, P.rayO, P.rayD, P.flags, hits, nPtr, work, C, *sort, T);
         else
-            k_trace<false, true><<<gridKey, 128, 0, st>>>(S, P.rayO, P.rayD, P.flags, hits, nPtr, work, C, *sort);
+            k_trace<false, true><<<gridKey, 128, 0, st>>>(S, P.rayO, P.rayD, P.flags, hits, nPtr, work, C, *sort, T);
         k_bin_scan<<<1, 1024, 0, st>>>(*sort);
         k_bin_scatter<<<numSMs() * 4, 256, 0, st>>>(*sort, nPtr);
     } else if (speculative) {
-        const ClosestQueue Q = {P.rayO, P.rayD, P.flags, hits};
         if (S.wideNodes) {
-            if (count) k_trace_spec<true, true><<<gridWide, 128, 0, st>>>(S, Q, nPtr, work, C);
-            else k_trace_spec<false, true><<<gridWide, 128, 0, st>>>(S, Q, nPtr, work, C);
+            tail = false;
+            if (count) k_trace_spec<true, true><<<gridWide, 128, 0, st>>>(S, Q, nPtr, work, C, T);
+            else k_trace_spec<false, true><<<gridWide, 128, 0, st>>>(S, Q, nPtr, work, C, T);
         } else if (count)
-            k_trace_spec<true, false><<<gridSpec, 128, 0, st>>>(S, Q, nPtr, work, C);
+            k_trace_spec<true, false><<<gridSpec, 128, 0, st>>>(S, Q, nPtr, work, C, T);
         else
-            k_trace_spec<false, false><<<gridSpec, 128, 0, st>>>(S, Q, nPtr, work, C);
+            k_trace_spec<false, false><<<gridSpec, 128, 0, st>>>(S, Q, nPtr, work, C, T);
     } else if (count)
-        k_trace<true, false><<<grid, 128, 0, st>>>(S, P.rayO, P.rayD, P.flags, hits, nPtr, work, C, none);
+        k_trace<true, false><<<grid, 128, 0, st>>>(S, P.rayO, P.rayD, P.flags, hits, nPtr, work, C, none, T);
     else
-        k_trace<false, false><<<grid, 128, 0, st>>>(S, P.rayO, P.rayD, P.flags, hits, nPtr, work, C, none);
+        k_trace<false, false><<<grid, 128, 0, st>>>(S, P.rayO, P.rayD, P.flags, hits, nPtr, work, C, none, T);
+    if (tail) {  // the long rays the kernel above handed over
+        if (count) k_trace_tail<false, true, ClosestQueue><<<gridTail, 128, 0, st>>>(S, Q, T, tailWork, C);
+        else k_trace_tail<false, false, ClosestQueue><<<gridTail, 128, 0, st>>>(S, Q, T, tailWork, C);
+    }
 }
 void launchHitPartition(const float4 *hits, const uint32_t *flags, const uint32_t *nPtr, uint32_t *perm, uint32_t *cntNeed,
                         uint32_t *cntRest, cudaStream_t st) {
     k_hit_partition<<<numSMs() * 4, 256, 0, st>>>(hits, flags, nPtr, perm, cntNeed, cntRest);
 }
 void launchShadow(const DeviceScene &S, const ShadowQueue &Q, float4 *rad, const uint32_t *nPtr, uint32_t *work, Counters *C,
-                  bool count, bool speculative, cudaStream_t st) {
+                  bool count, bool speculative, TailList T, uint32_t *tailWork, cudaStream_t st) {
     static int grid = persistentGrid(k_shadow<false>, 128);
     static int gridSpec = persistentGrid(k_shadow_spec<false, false>, 128);
     static int gridWide = persistentGrid(k_shadow_spec<false, true>, 128);
+    static int gridTail = persistentGrid(k_trace_tail<true, false, ShadowRayQueue>, 128);
     if (speculative) {
         const ShadowRayQueue R = {Q, rad};
         if (S.wideNodes) {
-            if (count) k_shadow_spec<true, true><<<gridWide, 128, 0, st>>>(S, R, nPtr, work, C);
-            else k_shadow_spec<false, true><<<gridWide, 128, 0, st>>>(S, R, nPtr, work, C);
-        } else if (count)
-            k_shadow_spec<true, false><<<gridSpec, 128, 0, st>>>(S, R, nPtr, work, C);
-        else
-            k_shadow_spec<false, false><<<gridSpec, 128, 0, st>>>(S, R, nPtr, work, C);
+            if (count) k_shadow_spec<true, true><<<gridWide, 128, 0, st>>>(S, R, nPtr, work, C, T);
+            else k_shadow_spec<false, true><<<gridWide, 128, 0, st>>>(S, R, nPtr, work, C, T);
+        } else {
+            if (count) k_shadow_spec<true, false><<<gridSpec, 128, 0, st>>>(S, R, nPtr, work, C, T);
+            else k_shadow_spec<false, false><<<gridSpec, 128, 0, st>>>(S, R, nPtr, work, C, T);
+            if (T.visits > 0) {
+                if (count) k_trace_tail<true, true, ShadowRayQueue><<<gridTail, 128, 0, st>>>(S, R, T, tailWork, C);
+                else k_trace_tail<true, false, ShadowRayQueue><<<gridTail, 128, 0, st>>>(S, R, T, tailWork, C);
+            }
+        }
     } else if (count)
         k_shadow<true><<<grid, 128, 0, st>>>(S, Q, rad, nPtr, work, C);
     else
@@ -1056,26 +1250,38 @@ void launchFlush(const ShadeArgs &A, cudaStream_t st) {
     k_flush<<<grid, 256, 0, st>>>(A);
 }
 void launchTraceRays(const DeviceScene &S, const float4 *rays, uint32_t n, float4 *hits, uint32_t *work, Counters *C, bool shadow,
-                     bool count, bool speculative, cudaStream_t st) {
+                     bool count, bool speculative, TailList T, uint32_t *tailWork, cudaStream_t st) {
     static int grid = persistentGrid(k_trace_rays<false, false>, 128);
     static int gridSpec = persistentGrid(k_trace_rays_spec<false, false, false>, 128);
     static int gridWide = persistentGrid(k_trace_rays_spec<false, false, true>, 128);
+    static int gridTail = persistentGrid(k_trace_tail<false, false, RayListQueue>, 128);
     if (speculative) {
         const RayListQueue Q = {rays, hits, S.primGlobalId, shadow};
         if (S.wideNodes) {
             if (shadow) {
-                if (count) k_trace_rays_spec<true, true, true><<<gridWide, 128, 0, st>>>(S, Q, n, work, C);
-                else k_trace_rays_spec<true, false, true><<<gridWide, 128, 0, st>>>(S, Q, n, work, C);
+                if (count) k_trace_rays_spec<true, true, true><<<gridWide, 128, 0, st>>>(S, Q, n, work, C, T);
+                else k_trace_rays_spec<true, false, true><<<gridWide, 128, 0, st>>>(S, Q, n, work, C, T);
             } else {
-                if (count) k_trace_rays_spec<false, true, true><<<gridWide, 128, 0, st>>>(S, Q, n, work, C);
-                else k_trace_rays_spec<false, false, true><<<gridWide, 128, 0, st>>>(S, Q, n, work, C);
+                if (count) k_trace_rays_spec<false, true, true><<<gridWide, 128, 0, st>>>(S, Q, n, work, C, T);
+                else k_trace_rays_spec<false, false, true><<<gridWide, 128, 0, st>>>(S, Q, n, work, C, T);
             }
-        } else if (shadow) {
-            if (count) k_trace_rays_spec<true, true, false><<<gridSpec, 128, 0, st>>>(S, Q, n, work, C);
-            else k_trace_rays_spec<true, false, false><<<gridSpec, 128, 0, st>>>(S, Q, n, work, C);
         } else {
-            if (count) k_trace_rays_spec<false, true, false><<<gridSpec, 128, 0, st>>>(S, Q, n, work, C);
-            else k_trace_rays_spec<false, false, false><<<gridSpec, 128, 0, st>>>(S, Q, n, work, C);
+            if (shadow) {
+                if (count) k_trace_rays_spec<true, true, false><<<gridSpec, 128, 0, st>>>(S, Q, n, work, C, T);
+                else k_trace_rays_spec<true, false, false><<<gridSpec, 128, 0, st>>>(S, Q, n, work, C, T);
+            } else {
+                if (count) k_trace_rays_spec<false, true, false><<<gridSpec, 128, 0, st>>>(S, Q, n, work, C, T);
+                else k_trace_rays_spec<false, false, false><<<gridSpec, 128, 0, st>>>(S, Q, n, work, C, T);
+            }
+            if (T.visits > 0) {
+                if (shadow) {
+                    if (count) k_trace_tail<true, true, RayListQueue><<<gridTail, 128, 0, st>>>(S, Q, T, tailWork, C);
+                    else k_trace_tail<true, false, RayListQueue><<<gridTail, 128, 0, st>>>(S, Q, T, tailWork, C);
+                } else {
+                    if (count) k_trace_tail<false, true, RayListQueue><<<gridTail, 128, 0, st>>>(S, Q, T, tailWork, C);
+                    else k_trace_tail<false, false, RayListQueue><<<gridTail, 128, 0, st>>>(S, Q, T, tailWork, C);
+                }
+            }
         }
     } else if (shadow) {
         if (count) k_trace_rays<true, true><<<grid, 128, 0, st>>>(S, rays, n, hits, work, C);

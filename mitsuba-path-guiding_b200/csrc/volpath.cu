@@ -390,10 +390,59 @@ __global__ void __launch_bounds__(128) k_track_vol(ShadeArgs A) {
     runWithRefill(job, A.C->queue[A.bounce], &A.C->trackWork[A.bounce]);
 }
 
+// Event partition of the queue in front of k_shade_vol: a path arrives either with a medium scattering event (phase function,
+// guided direction at a medium vertex), with a surface event (BSDF code) or with nothing left to shade (parked, ended by Russian
+// roulette, left the scene). In queue order every warp holds all three and walks both long branches with half of its lanes.
+// perm = [medium events ... | ... surface events], rest = the third class; k_shade_vol maps its queue position through them so that
+// (all but two) warps hold one class. The classification mirrors the branch conditions of k_shade_vol.
+__global__ void __launch_bounds__(256) k_event_partition(ShadeArgs A, uint32_t *__restrict__ perm, uint32_t *__restrict__ rest) {
+    __shared__ uint32_t sWarp[3][8];
+    __shared__ uint32_t sBase[3];
+    const uint32_t n = A.C->queue[A.bounce];
+    uint32_t *cnt[3] = {&A.C->partNeed[A.bounce], &A.C->partSurf[A.bounce], &A.C->partRest[A.bounce]};
+    const uint32_t warp = threadIdx.x >> 5;
+    for (uint32_t base = blockIdx.x * 256u; base < n; base += gridDim.x * 256u) {
+        const uint32_t i = base + threadIdx.x;
+        int cls = -1;
+        if (i < n) {
+            const uint32_t fl = A.cur.flags[i];
+            const float4 tA = A.trkA[i];
+            if ((fl & kFlagDead) || (__float_as_uint(tA.w) & 1u)) cls = 2;
+            else if (tA.x < kInf) cls = 0;
+            else cls = __float_as_uint(A.hits[i].w) != kMiss ? 1 : 2;
+        }
+        unsigned m[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            m[c] = __ballot_sync(0xffffffffu, cls == c);
+            if (laneId() == 0) sWarp[c][warp] = __popc(m[c]);
+        }
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            uint32_t total = 0;
+            for (int w = 0; w < 8; ++w) {
+                const uint32_t c = sWarp[threadIdx.x][w];
+                sWarp[threadIdx.x][w] = total;
+                total += c;
+            }
+            sBase[threadIdx.x] = total ? atomicAdd(cnt[threadIdx.x], total) : 0u;
+        }
+        __syncthreads();
+        if (cls >= 0) {
+            const uint32_t r = sBase[cls] + sWarp[cls][warp] + __popc(m[cls] & ((1u << laneId()) - 1u));
+            if (cls == 0) perm[r] = i;
+            else if (cls == 1) perm[n - 1u - r] = i;
+            else rest[r] = i;
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(kShadeThreads, 6) k_shade_vol(ShadeArgs A) {
     const DeviceScene &S = A.S;
     const IntegratorConfig &cfg = A.cfg;
     const uint32_t n = A.C->queue[A.bounce];
+    const uint32_t nMed = A.perm ? A.C->partNeed[A.bounce] : 0u, nSurf = A.perm ? A.C->partSurf[A.bounce] : 0u;
     uint32_t *nextCount = &A.C->queue[A.bounce + 1];
     uint32_t *shadowCount = &A.C->shadow[A.bounce];
     unsigned long long donePaths = 0, doneLen = 0;
@@ -401,8 +450,11 @@ __global__ void __launch_bounds__(kShadeThreads, 6) k_shade_vol(ShadeArgs A) {
     uint32_t appendParity = 0;
 
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const uint32_t i = base + threadIdx.x;
-        const bool valid = i < n;
+        const uint32_t q = base + threadIdx.x;
+        const bool valid = q < n;
+        uint32_t i = q;
+        if (valid && A.perm)  // event partition: medium events, then surface events, then the paths with nothing to shade
+            i = q < nMed ? A.perm[q] : (q < nMed + nSurf ? A.perm[n - 1u - (q - nMed)] : A.permRest[q - nMed - nSurf]);
 
         bool alive = false, wantShadow = false, terminate = false;
         float4 pos4 = make_float4(0, 0, 0, 0);
@@ -860,6 +912,7 @@ void launchShadeVol(const ShadeArgs &A, cudaStream_t st) {
     static int gridLook = volGrid(k_look_vol, 128), gridTrack = volGrid(k_track_vol, 128), grid = volGrid(k_shade_vol, kShadeThreads);
     k_look_vol<<<gridLook, 128, 0, st>>>(A);
     k_track_vol<<<gridTrack, 128, 0, st>>>(A);
+    if (A.perm) k_event_partition<<<gridLook, 256, 0, st>>>(A, const_cast<uint32_t *>(A.perm), const_cast<uint32_t *>(A.permRest));
     k_shade_vol<<<grid, kShadeThreads, 0, st>>>(A);
 }
 void launchShadowVol(const DeviceScene &S, const ShadowQueue &Q, float4 *rad, const uint32_t *nPtr, uint32_t *work, Counters *C,

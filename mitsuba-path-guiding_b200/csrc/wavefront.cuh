@@ -47,6 +47,15 @@ struct ShadowQueue {
     uint4 *aux;  // volumetric: forked rng state lo/hi, pixel, interactions left
 };
 
+// Rays handed from the traversal kernels to the cooperative one: queue indices, appended with one atomic per warp
+struct TailList {
+    uint32_t *list;
+    uint32_t *count;
+    uint32_t visits;  // node-visit budget of a ray in the first kernel; 0 = no budget, no cooperative kernel (small scenes)
+    uint32_t visitsSmall;  // budget when the queue holds fewer than kTailSmallQueue rays (the thin late bounces)
+    __host__ __device__ uint32_t budget(uint32_t n) const { return n < (512u << 10) ? visitsSmall : visits; }
+};
+
 struct IntegratorConfig {
     int maxDepth, rrDepth, strictNormals, hideEmitters, useNee, volumetric;
     float maxComponentValue;
@@ -65,8 +74,11 @@ struct Counters {
     uint32_t shadowWork[260];
     uint32_t lookWork[260];    // volumetric tracking stages (volpath.cu)
     uint32_t trackWork[260];
+    uint32_t tailCount[260], tailWork[260];      // long rays handed to the cooperative kernel (k_trace_tail): list size, cursor
+    uint32_t shTailCount[260], shTailWork[260];  // same for the shadow queues
     uint32_t partNeed[260];    // hit / miss partition of the shade queue (k_hit_partition): entries placed at the front / back
-    uint32_t partRest[260];
+    uint32_t partRest[260];    // (volumetric path, k_event_partition: medium events / rest, and the surface events below)
+    uint32_t partSurf[260];
     uint32_t misc[16];
     unsigned long long paths, normalRays, shadowRays, pathLen, nodesVisited, primsTested, trainSamples;
 };
@@ -94,7 +106,8 @@ struct ShadeArgs {
     float4 *lookL;       // volumetric: per queued path, MIS-weighted emitter radiance found by k_look_vol
     GuideDevice G;
     int bounce;
-    const uint32_t *perm;  // coherence sort: queue order -> path index (nullptr = shade in queue order)
+    const uint32_t *perm;  // coherence sort / hit partition / event partition: queue position -> path index (nullptr = queue order)
+    const uint32_t *permRest;  // volumetric event partition: the third class
 };
 
 // Coherence sort of the shade queue by guiding cell (north star, subsystem 2: "sorting by cell to restore coherence").

@@ -95,6 +95,35 @@ def test_mesh_chord_set_like_test_kd(mesh, spec):
         it.set_option("trace_spec", 3)
 
 
+def test_mesh_grazing_rays_cooperative_tail(mesh, api):
+    """Rays that skim the terrain need hundreds of node visits: the traversal kernels hand them to the warp-cooperative kernel
+    (kernels.cu: k_trace_tail) after their visit budget. Closest and any-hit results must still be the oracle's."""
+    import torch
+
+    sb, osc, it, _ = mesh
+    rng = np.random.RandomState(17)
+    n = 60000
+    # start on a circle outside the sheet, a little above / below its height range (+-0.05), aim across it almost horizontally
+    phi = rng.rand(n) * 2 * np.pi
+    o = np.stack([1.6 * np.cos(phi), rng.uniform(-0.04, 0.06, n), 1.6 * np.sin(phi)], 1)
+    tgt = np.stack([rng.uniform(-0.9, 0.9, n), rng.uniform(-0.05, 0.05, n), rng.uniform(-0.9, 0.9, n)], 1)
+    d = tgt - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, np.zeros((n, 1)), d, np.full((n, 1), 10.0)], 1).astype(np.float32)
+    tuv_o, prim_o, _ = osc.trace(rays)
+    tuv_g, prim_g = it.k_trace(rays)
+    assert 0.2 < (prim_o != 0xFFFFFFFF).mean() < 0.98
+    _check_hits(tuv_o, prim_o, tuv_g, prim_g, max_mismatch=int(3e-4 * n), uv_scale=UV_SCALE, t_scale=20.0)
+    _, occ_o, _ = osc.trace(rays, shadow=True)
+    _, occ_g = it.k_trace(rays, shadow=True)
+    assert ((occ_o != 0xFFFFFFFF) != (occ_g != 0xFFFFFFFF)).sum() <= int(3e-4 * n)
+    # the set really is long: more node visits per ray than the budget of the first kernel on a good part of the rays
+    d_rays = torch.from_numpy(rays).cuda()
+    d_hits = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    _, (nodes, prims) = it.k_trace_device(d_rays.data_ptr(), n, d_hits.data_ptr(), count=True)
+    assert nodes / n > 60, nodes / n
+
+
 def test_mesh_radiance_sample_by_sample(mesh):
     sb, osc, it, p = mesh
     rng = np.random.RandomState(3)
