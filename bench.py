@@ -191,7 +191,7 @@ def run_reference(args):
                          "kd_traversal_per_ray": cpu.kd_bytes_per_ray()},
         "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def parse_args(argv=None):
@@ -640,7 +640,21 @@ def measure(ctx, args, headline):
     return line
 
 
+def emit(line):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    # Library chatter (NCCL prints its version banner to STDOUT at NCCL_DEBUG >= VERSION, which some images set) must not sit
+    # next to the JSON line: file descriptor 1 is pointed at stderr for the whole run, the line goes to a saved duplicate.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -667,7 +681,7 @@ def main():
                 extra[name] = {"error": str(ex)}
         line["workloads"] = extra
     if ctx.rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if ctx.world > 1:
         ctx.dist.destroy_process_group()
 

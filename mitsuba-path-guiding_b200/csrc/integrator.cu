@@ -90,6 +90,8 @@ struct Integrator {
     cudaStream_t stream = nullptr, copyStream = nullptr;
     cudaEvent_t evExport = nullptr;
     std::atomic<int> cancel{0};
+    bool scenePinned = false;        // b200pg_scene_upload page-locks the scene's large host arrays on first use
+    std::vector<void *> pinnedHost;
 
     // device scene
     DevBuf<float4> dNodes, dWideNodes, dPrimPlanes, dPrimRows, dRects;
@@ -231,6 +233,7 @@ struct Integrator {
     }
 
     ~Integrator() {
+        for (void *h : pinnedHost) cudaHostUnregister(h);
         if (stream) cudaStreamDestroy(stream);
         if (copyStream) cudaStreamDestroy(copyStream);
         if (evExport) cudaEventDestroy(evExport);
@@ -1347,6 +1350,25 @@ int b200pg_scene_upload(void *integ, size_t *bytes) {
     PG_TRY(integ)
     HostScene &H = *self->scene;
     size_t total = 0;
+    if (!self->scenePinned) {  // page-lock the large host arrays once: repeated uploads then run at the PCIe rate
+        auto pin = [&](const void *ptr, size_t nbytes) {
+            if (nbytes < (1u << 20)) return;
+            if (cudaHostRegister(const_cast<void *>(ptr), nbytes, cudaHostRegisterDefault) == cudaSuccess)
+                self->pinnedHost.push_back(const_cast<void *>(ptr));
+            else
+                cudaGetLastError();  // already registered by another integrator of the same scene, or not pinnable: pageable copy
+        };
+        pin(H.nodes.data(), H.nodes.size() * sizeof(H.nodes[0]));
+        pin(H.primPlanes.data(), H.primPlanes.size() * sizeof(float));
+        pin(H.primRows.data(), H.primRows.size() * sizeof(float));
+        pin(H.shadeTris.data(), H.shadeTris.size() * sizeof(float));
+        pin(H.primInfo.data(), H.primInfo.size() * sizeof(H.primInfo[0]));
+        pin(H.positions.data(), H.positions.size() * sizeof(float));
+        pin(H.normals.data(), H.normals.size() * sizeof(float));
+        pin(H.indices.data(), H.indices.size() * sizeof(uint32_t));
+        pin(H.densityPool.data(), H.densityPool.size() * sizeof(float));
+        self->scenePinned = true;
+    }
     auto up = [&](auto &dst, const auto &src) {
         dst.upload(src, self->stream);
         total += src.size() * sizeof(src[0]);

@@ -1,10 +1,14 @@
-// kernels.cu -- the wavefront stages as hand-written sm_100a CUDA kernels:
-//   k_generate   camera-ray generation        (progressiveintegrator.cpp:246-271, perspective.cpp:271-298)
-//   k_trace      closest-hit / any-hit BVH traversal over a compacted ray queue
-//   k_shade      intersection fill, emitted radiance + MIS, Russian roulette, NEE, BSDF sampling,
-//                queue compaction, film splat at termination (progressive_path.cpp:133-314)
-//   k_shadow     shadow-ray resolve: adds the NEE contribution to the (moved) path record
-//   k_film_splat standalone splat kernel (imageblock.h:151-197) used by the parity tests
+// kernels.cu -- the wavefront stages of the surface path as hand-written sm_100a CUDA kernels:
+//   k_generate       camera-ray generation        (progressiveintegrator.cpp:246-271, perspective.cpp:271-298)
+//   k_trace          closest-hit BVH traversal, warps take 32 rays at a time (coherent queues: camera rays)
+//   k_trace_spec / k_shadow_spec   persistent speculative traversal with per-lane refill (bounce and shadow queues)
+//   k_trace_tail     warp-cooperative traversal of the rays that outlive their node-visit budget in the two above
+//   k_hit_partition  hit / miss partition of a sparse shade queue (open scenes)
+//   k_shade          intersection fill, emitted radiance + MIS, Russian roulette, NEE, BSDF / guided sampling, queue
+//                    compaction, training-vertex records; a finished path leaves a splat record (progressive_path.cpp:133-314)
+//   k_shadow         batch any-hit kernel (B200PG_TRACE_SPEC without bit 1); unoccluded rays add their NEE term to the path record
+//   k_splat          film accumulation of a finished batch in pixel order (imageblock.h:151-197)
+//   k_film_*, k_features, k_feature_color, k_flush, test kernels (k_film_splat, k_trace_rays*, k_bsdf_test)
 // All kernels are persistent (grid = k * #SMs) and read their work size from device counters so
 // that a whole batch (all bounces) is enqueued without a host round trip.
 #include <cooperative_groups.h>

@@ -96,10 +96,10 @@ def test_mesh_chord_set_like_test_kd(mesh, spec):
 
 
 def test_mesh_grazing_rays_cooperative_tail(mesh, api):
-    """Rays that skim the terrain need hundreds of node visits: the traversal kernels hand them to the warp-cooperative kernel
-    (kernels.cu: k_trace_tail) after their visit budget. Closest and any-hit results must still be the oracle's."""
-    import torch
-
+    """Rays that skim the terrain need many node visits: the traversal kernels hand a ray to the warp-cooperative kernel
+    (kernels.cu: k_trace_tail) once it has used up its visit budget. Closest- and any-hit results must be the oracle's with the
+    default budget (96 visits: a few per cent of this set), with a budget of 4 (practically every ray is finished by a warp) and
+    with the mechanism off."""
     sb, osc, it, _ = mesh
     rng = np.random.RandomState(17)
     n = 60000
@@ -111,17 +111,17 @@ def test_mesh_grazing_rays_cooperative_tail(mesh, api):
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     rays = np.concatenate([o, np.zeros((n, 1)), d, np.full((n, 1), 10.0)], 1).astype(np.float32)
     tuv_o, prim_o, _ = osc.trace(rays)
-    tuv_g, prim_g = it.k_trace(rays)
-    assert 0.2 < (prim_o != 0xFFFFFFFF).mean() < 0.98
-    _check_hits(tuv_o, prim_o, tuv_g, prim_g, max_mismatch=int(3e-4 * n), uv_scale=UV_SCALE, t_scale=20.0)
     _, occ_o, _ = osc.trace(rays, shadow=True)
-    _, occ_g = it.k_trace(rays, shadow=True)
-    assert ((occ_o != 0xFFFFFFFF) != (occ_g != 0xFFFFFFFF)).sum() <= int(3e-4 * n)
-    # the set really is long: more node visits per ray than the budget of the first kernel on a good part of the rays
-    d_rays = torch.from_numpy(rays).cuda()
-    d_hits = torch.empty((n, 4), dtype=torch.float32, device="cuda")
-    _, (nodes, prims) = it.k_trace_device(d_rays.data_ptr(), n, d_hits.data_ptr(), count=True)
-    assert nodes / n > 60, nodes / n
+    assert 0.2 < (prim_o != 0xFFFFFFFF).mean() < 0.98
+    try:
+        for budget in (-1, 4, 0):  # library default, nearly everything cooperative, off
+            it.set_option("tail_visits", budget)
+            tuv_g, prim_g = it.k_trace(rays)
+            _check_hits(tuv_o, prim_o, tuv_g, prim_g, max_mismatch=int(3e-4 * n), uv_scale=UV_SCALE, t_scale=20.0)
+            _, occ_g = it.k_trace(rays, shadow=True)
+            assert ((occ_o != 0xFFFFFFFF) != (occ_g != 0xFFFFFFFF)).sum() <= int(3e-4 * n), budget
+    finally:
+        it.set_option("tail_visits", -1)
 
 
 def test_mesh_radiance_sample_by_sample(mesh):

@@ -64,16 +64,26 @@ def main():
     scene = api.Scene.from_builder(sb)
     devices = list(range(args.gpus))
 
+    floor = 0.0
     if args.ref_spp > 0:
-        sb.spp = args.ref_spp
-        ref_scene = api.Scene.from_builder(make(W, H, spp=args.ref_spp))
-        it = api.Integrator(ref_scene, params(False, 0, 64))
+        # two independent halves (different seeds): their mean is the reference, their difference measures the reference's OWN
+        # noise -- E[(A - B)^2] / 4 = var(reference) -- which every relMSE below contains and `relMSE_debiased` subtracts
+        half = max(1, args.ref_spp // 2)
         t0 = time.perf_counter()
-        it.render(devices=devices if len(devices) > 1 else None)  # sample indices of this render start at 0 ...
-        ref = it.develop()
-        ref_desc = "unguided GPU render, %d spp on %d GPU(s), %.1f s" % (args.ref_spp, len(devices), time.perf_counter() - t0)
-        it.close()
-        first_sample = args.ref_spp  # ... so the timed renders below must use disjoint ones: they do (seed offset)
+        halves = []
+        for k in range(2):
+            sbr = make(W, H, spp=half)
+            sbr.seed = sb.seed + 104729 * (k + 1)
+            it = api.Integrator(api.Scene.from_builder(sbr), params(False, 0, 64))
+            it.render(devices=devices if len(devices) > 1 else None)
+            halves.append(it.develop().astype(np.float64))
+            it.close()
+        ref = (0.5 * (halves[0] + halves[1])).astype(np.float32)
+        e = (((halves[0] - halves[1]) ** 2) / (ref.astype(np.float64) ** 2 + 1e-3)).mean(2).ravel()
+        e.sort()
+        floor = float(e[: int(len(e) * 0.999)].mean()) / 4.0
+        ref_desc = "unguided GPU render, 2 x %d spp on %d GPU(s), %.1f s; its own noise (from the two halves) adds %.2e to every relMSE" % (
+            half, len(devices), time.perf_counter() - t0, floor)
         seed_shift = 7919
     else:
         z = np.load(os.path.join(ROOT, "tests", "golden", "ref_%s.npz" % args.scene))
@@ -84,7 +94,7 @@ def main():
         seed_shift = 0
         # the reference's own noise: what relMSE an EXACT image would still show against it
         floor = float(z["probe_relmse"]) * meta["probe_spp"] / meta["ref_spp"]
-        ref_desc += "; its own noise adds %.2e to every relMSE below" % floor
+        ref_desc += "; its own noise adds %.2e to every relMSE" % floor
     print("reference:", ref_desc, file=sys.stderr)
 
     sbt = make(W, H, spp=64)
@@ -101,7 +111,8 @@ def main():
         it.render(devices=devices if len(devices) > 1 else None)
         el = time.perf_counter() - t0
         img, st = it.develop(), it.stats()
-        out = {"relMSE": relmse(img, ref), "seconds": el, "spp": st["paths"] / (W * H), "mpaths_per_s": st["paths"] / el / 1e6,
+        r = relmse(img, ref)
+        out = {"relMSE": r, "relMSE_debiased": max(r - floor, 0.0), "seconds": el, "spp": st["paths"] / (W * H), "mpaths_per_s": st["paths"] / el / 1e6,
                "cells": st.get("guide_cells", 0), "progressions": st["progressions_done"]}
         it.close()
         return out
@@ -134,13 +145,17 @@ def main():
             paths += st["paths"]
             k += 1
         el = time.perf_counter() - t0
-        return {"relMSE": relmse(develop(acc).astype(np.float32), ref), "seconds": el, "spp": paths / (W * H), "mpaths_per_s": paths / el / 1e6,
+        r = relmse(develop(acc).astype(np.float32), ref)
+        return {"relMSE": r, "relMSE_debiased": max(r - floor, 0.0), "seconds": el, "spp": paths / (W * H), "mpaths_per_s": paths / el / 1e6,
                 "cores": cores}
 
     for T in budgets:
         out = {"scene": args.scene, "size": "%dx%d" % (W, H), "budget_s": T, "gpus": args.gpus, "reference": ref_desc,
                "guided": gpu_arm(T, True), "unguided": gpu_arm(T, False)}
+        out["reference_noise"] = floor
         out["relMSE_ratio_unguided_over_guided"] = out["unguided"]["relMSE"] / out["guided"]["relMSE"]
+        if out["guided"]["relMSE_debiased"] > 0:
+            out["relMSE_debiased_ratio_unguided_over_guided"] = out["unguided"]["relMSE_debiased"] / out["guided"]["relMSE_debiased"]
         if args.cpu:
             out["cpu_guided"] = cpu_arm(T, True)
             out["cpu_unguided"] = cpu_arm(T, False)
