@@ -146,18 +146,19 @@ static int worker(const Options &o, int rank, int world, int up, int down) {
     const int perPass = p.samples_per_progression > 0 ? p.samples_per_progression : 1;
     const int numPasses = std::max(1, (desc ? desc->sample_count : 4) / perPass);
     const int globalPasses = (numPasses + world - 1) / world;  // the sample count is rounded up to a multiple of world * perPass
-    const int trainPasses = p.guiding ? p.training_progressions : 0;
     const bool timed = p.max_render_time > 0;
+    int trainPasses = p.guiding ? p.training_progressions : 0;
+    if (!timed) trainPasses = std::min(trainPasses, globalPasses);
     const auto t0 = std::chrono::steady_clock::now();
     for (int g = 0; timed || g < globalPasses; ++g) {
-        const bool record = g * world < trainPasses;  // the same number of training SAMPLES as a single-GPU run
+        const bool record = g < trainPasses;  // training_progressions = field updates (global passes), as b200pg_render counts them
         if (p.guiding) PG_CHECK(b200pg_guiding_mode(integ, record ? 1 : 0, 1), 3);
         PG_CHECK(b200pg_progression_render(integ, (g * world + rank) * perPass, perPass, 0, 0), 3);
         if (record) {
             uint32_t ns = 0, nc = 0;
             PG_CHECK(b200pg_train(integ, 0, &ns, &nc), 3);  // statistics summed over all workers inside the M-step kernel
             if (o.verbose && rank == 0) std::printf("Progression[%d]: %u local training samples, %u cells\n", g, ns, nc);
-            if (p.guide_train_discard_film && (g + 1) * world >= trainPasses) PG_CHECK(b200pg_film_clear(integ), 3);
+            if (p.guide_train_discard_film && g + 1 >= trainPasses) PG_CHECK(b200pg_film_clear(integ), 3);
         } else if (o.verbose && rank == 0) {
             std::printf("Progression[%d] took %.3f s so far\n", g, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
         }

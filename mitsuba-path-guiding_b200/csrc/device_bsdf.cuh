@@ -110,12 +110,20 @@ PG_DEV float hypot2(float a, float b) {  // math.cpp:74-88
 }
 
 // ---- microfacet distribution (src/bsdfs/microfacet.h), Beckmann + GGX
+#ifndef PG_MF_NOINLINE
+#define PG_MF_NOINLINE 0
+#endif
+#if PG_MF_NOINLINE
+#define PG_MF __device__ __noinline__
+#else
+#define PG_MF PG_DEV
+#endif
 struct Microfacet {
     int type;
     float au, av;
     PG_DEV Microfacet(int t, float a, float b) : type(t), au(fmaxf(a, 1e-4f)), av(fmaxf(b, 1e-4f)) {}
 
-    PG_DEV float eval(float3 m) const {  // microfacet.h:191-234
+    PG_MF float eval(float3 m) const {  // microfacet.h:191-234
         if (m.z <= 0) return 0.0f;
         float cosTheta2 = m.z * m.z;
         float beckmannExponent = ((m.x * m.x) / (au * au) + (m.y * m.y) / (av * av)) / cosTheta2;
@@ -136,7 +144,7 @@ struct Microfacet {
         float sinPhi2 = v.y * v.y * invSinTheta2;
         return sqrtf(cosPhi2 * au * au + sinPhi2 * av * av);
     }
-    PG_DEV float smithG1(float3 v, float3 m) const {  // microfacet.h:477-514
+    PG_MF float smithG1(float3 v, float3 m) const {  // microfacet.h:477-514
         if (dot(v, m) * v.z <= 0) return 0.0f;
         float temp = 1 - v.z * v.z;  // Frame::tanTheta
         float tanTheta = temp <= 0.0f ? 0.0f : fabsf(sqrtf(temp) / v.z);
@@ -154,7 +162,7 @@ struct Microfacet {
     }
     PG_DEV float G(float3 wi, float3 wo, float3 m) const { return smithG1(wi, m) * smithG1(wo, m); }
 
-    PG_DEV float2 sampleVisible11(float thetaI, float2 sample) const {  // microfacet.h:573-697
+    PG_MF float2 sampleVisible11(float thetaI, float2 sample) const {  // microfacet.h:573-697
         const float SQRT_PI_INV = 1 / sqrtf(kPi);
         float2 slope;
         if (type == 0) {

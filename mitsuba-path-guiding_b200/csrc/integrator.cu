@@ -790,14 +790,16 @@ static PassPlan makePlan(const Integrator &I, int rank, int world) {
     P.timed = I.params.max_render_time > 0;
     P.limit = (double)I.params.max_render_time;
     // the sample budget trains at most as long as it renders; a time budget has no pass count to clamp against
+    // training_progressions counts field UPDATES = global passes: on N devices every update refits from N sample blocks. (Counting
+    // device passes instead -- the same number of training samples as a single-device run -- left an 8-GPU job with two updates
+    // of its 16, and the spatial tree, which splits one level per update, with 4 cells: guided == unguided at 4K, r2p.)
     P.trainPasses = I.guide.active ? std::max(0, I.params.training_progressions) : 0;
-    if (!P.timed) P.trainPasses = std::min(P.trainPasses, passes);
+    if (!P.timed) P.trainPasses = std::min(P.trainPasses, P.numPasses);
     return P;
 }
-// global pass g of the plan on this integrator; `record` is the same on every rank (same number of training SAMPLES as a
-// single-device run)
+// global pass g of the plan on this integrator; `record` is the same on every rank
 static void runPass(Integrator &I, const PassPlan &P, int g) {
-    const bool record = g * P.world < P.trainPasses;
+    const bool record = g < P.trainPasses;
     I.guide.recording = I.guide.active && record;
     I.guide.sampling = true;
     I.renderProgression((g * P.world + P.rank) * P.perPass, P.perPass, 0, 0);
@@ -807,7 +809,7 @@ static void runPass(Integrator &I, const PassPlan &P, int g) {
         I.spanEnd(Integrator::kTimeTrain, t);
         CUDA_OK(cudaStreamSynchronize(I.stream));
         I.drainSpans();
-        if (I.params.guide_train_discard_film && (g + 1) * P.world >= P.trainPasses)
+        if (I.params.guide_train_discard_film && g + 1 >= P.trainPasses)
             CUDA_OK(cudaMemsetAsync(I.dFilm.p, 0, I.dFilm.n * sizeof(float4), I.stream));
     }
 }

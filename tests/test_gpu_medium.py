@@ -79,6 +79,23 @@ def test_vol_radiance_sample_by_sample(api, medium_scene):
     assert abs(got.mean() - want.mean()) < 3e-3 * want.mean()
 
 
+def test_vol_radiance_does_not_depend_on_the_event_partition(api, medium_scene):
+    """k_event_partition orders the queue of k_shade_vol by event class (medium / surface / nothing to shade): the order in which
+    paths are shaded changes, a sample's value must not -- bit for bit."""
+    sb, osc, it = medium_scene
+    rng = np.random.RandomState(29)
+    n = 60000
+    pix = rng.randint(0, sb.width * sb.height, n).astype(np.uint32)
+    smp = rng.randint(0, 1000, n).astype(np.uint32)
+    try:
+        it.set_option("partition", 0)
+        base = it.k_radiance(pix, smp)
+        it.set_option("partition", 1)
+        assert np.array_equal(base, it.k_radiance(pix, smp))
+    finally:
+        it.set_option("partition", 1)
+
+
 def test_vol_parameter_variants(api, pkg, oracle):
     sb = pkg.scenes.cornell_medium(64, 64, spp=4, res=24)
     osc = oracle.scene(sb)

@@ -138,6 +138,30 @@ def test_mesh_radiance_sample_by_sample(mesh):
     assert abs(Lg.mean() - Lo.mean()) <= 2e-3 * Lo.mean()
 
 
+def test_mesh_radiance_does_not_depend_on_the_schedule(mesh):
+    """The hit / miss partition of the shade queue (off / forced on every bounce >= 1) and the visit budget (off / 4 = nearly every
+    ray through the warp-cooperative kernel) change the ORDER in which paths are shaded and rays are traversed, never a sample's
+    value: radiance per (pixel, sample) must be bit-identical under the partition and equal up to exact-t ties under the budget."""
+    sb, osc, it, p = mesh
+    rng = np.random.RandomState(23)
+    pix = rng.randint(0, sb.width * sb.height, 80000).astype(np.uint32)
+    smp = rng.randint(0, 64, 80000).astype(np.uint32)
+    try:
+        it.set_option("partition", 0)
+        base = it.k_radiance(pix, smp)
+        it.set_option("partition", 2)
+        assert np.array_equal(base, it.k_radiance(pix, smp))
+        it.set_option("tail_visits", 4)
+        got = it.k_radiance(pix, smp)
+        assert (np.abs(got - base).max(1) > 1e-6 * (1 + np.abs(base).max(1))).mean() < 1e-3
+        it.set_option("tail_visits", 0)
+        got = it.k_radiance(pix, smp)
+        assert (np.abs(got - base).max(1) > 1e-6 * (1 + np.abs(base).max(1))).mean() < 1e-3
+    finally:
+        it.set_option("partition", 1)
+        it.set_option("tail_visits", -1)
+
+
 def test_mesh_progression_counters_and_image(mesh, api):
     sb, osc, it, p = mesh
     it.film_clear()

@@ -1,6 +1,6 @@
 """One steady-state guided training step of a bench workload between cudaProfilerStart / Stop, one wavefront lane and no stream
 overlap, for `ncu --profile-from-start off` (launch list or --set full of exactly that step).
-usage: profile_step.py [workload] [pretrain] [spp]   (workload as bench.py --workload)"""
+usage: profile_step.py [workload] [pretrain] [spp] [max_cell_samples]   (workload as bench.py --workload)"""
 import os, sys
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
@@ -12,6 +12,8 @@ args = bench.parse_args([])
 args.workload = name
 args.spp_per_step = int(sys.argv[3]) if len(sys.argv) > 3 else (1 if name == "mesh_10m" else 4)
 args.guided_distance = name == "medium_1024"
+if len(sys.argv) > 4:
+    args.max_cell_samples = int(sys.argv[4])  # a smaller split threshold grows the larger field of a multi-GPU job on one GPU
 pkg, sb, desc = bench.workload(name)
 from b200pg import api
 p = bench.guided_params(pkg, args)

@@ -1,0 +1,34 @@
+#!/bin/bash
+# round 2, GPU call Q: parity suite (schedule-independence tests), training kernels at an 8-GPU-size field on one GPU (launch list),
+# noinline microfacet helpers A/B, final ncu --set full of k_shade on C2 (traffic), 4K equal-time with the CPU arm
+mkdir -p gpurun_out
+(time timeout 1200 python -m pytest tests -m gpu -q --maxfail=8) > gpurun_out/r2q_pytest.log 2>&1
+tail -4 gpurun_out/r2q_pytest.log
+V=$PWD/mitsuba-path-guiding_b200/_variants
+run() { # name workload env...
+  n=$1; w=$2; shift 2
+  env "$@" timeout 400 python bench.py --workload $w --steps 8 --warmup 3 --no-cpu-baseline --no-workloads $EXTRA > gpurun_out/r2q_$n.json 2> gpurun_out/r2q_$n.err
+}
+run c4_main mesh_10m A=0
+run c4_mfnoinline mesh_10m B200PG_LIB=$V/libb200pg_mfnoinline.so
+run c2_main cornell_caustic_1024 A=0
+run c2_mfnoinline cornell_caustic_1024 B200PG_LIB=$V/libb200pg_mfnoinline.so
+EXTRA="--max-cell-samples 4096"
+run c2_bigfield cornell_caustic_1024 A=0
+EXTRA=
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob("gpurun_out/r2q_c*.json")):
+    try:
+        d=json.load(open(f)); s=d["roofline"]["stage_seconds"]
+        print("%-26s value %7.1f e2e %7.1f ms/step %6.3f | one-lane %6.3f: trace %5.2f shade %5.2f shadow %4.2f film %4.2f train %5.2f | %s" % (f[15:], d["value"], d["e2e"]["value"], d["ms_per_step"], s["one_lane_step"]*1e3, s["trace"]*1e3, s["shade"]*1e3, s["shadow"]*1e3, s["film"]*1e3, s["train"]*1e3, d["config"]["guiding"][-22:]))
+    except Exception as e: print(f, "failed", e)
+PY
+timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/r2q_launches_c2_bigfield.csv python tools/profile_step.py cornell_caustic_1024 16 4 4096 > gpurun_out/r2q_ncu_c2_bigfield.log 2>&1
+tail -1 gpurun_out/r2q_ncu_c2_bigfield.log
+timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/r2q_launches_c2.csv python tools/profile_step.py cornell_caustic_1024 12 4 > gpurun_out/r2q_ncu_c2.log 2>&1
+tail -1 gpurun_out/r2q_ncu_c2.log
+timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:'k_shade' -c 9 -o gpurun_out/r2q_prof_shade_c2 python tools/profile_step.py cornell_caustic_1024 12 4 > gpurun_out/r2q_ncu_shade.log 2>&1
+tail -1 gpurun_out/r2q_ncu_shade.log
+timeout 900 python tools/equal_time.py --scene c2 --size 3840x2160 --budgets 10,30 --ref-spp 8192 --cpu > gpurun_out/r2q_equal_time_c5_4k_1gpu_cpu.jsonl 2> gpurun_out/r2q_equal_time_c5_4k_1gpu_cpu.err
+tail -1 gpurun_out/r2q_equal_time_c5_4k_1gpu_cpu.err
