@@ -372,7 +372,7 @@ static constexpr int kETile = 64;     // samples per stage (1 KB of positions + 
 // barrier's phase), so 16 KB per warp are in flight ahead of the arithmetic instead of one sample per lane in registers.
 template <int KMAX>
 __global__ void __launch_bounds__(128) k_estep(GuideDevice G, const float4 *__restrict__ sPos, const float4 *__restrict__ sDir,
-                                               const uint4 *__restrict__ work, const uint32_t *__restrict__ counts,
+                                               const uint4 *__restrict__ work, uint32_t *__restrict__ counts,
                                                float *__restrict__ partials, int stride) {
     __shared__ float4 sLobe[4][KMAX * 2];
     __shared__ __align__(128) float4 sTile[4][kEStages][2][kETile];
@@ -387,7 +387,13 @@ __global__ void __launch_bounds__(128) k_estep(GuideDevice G, const float4 *__re
     }
     __syncwarp();
     uint32_t parity = 0;  // bit s = phase the next wait on stage s expects
-    for (uint32_t w = blockIdx.x * 4 + warp; w < nWork; w += gridDim.x * 4) {
+    // dynamic work fetch (counts[3], zeroed before the launch): chunks differ in size once cells hold fewer samples than a chunk
+    // (large fields), and a static round-robin leaves the kernel waiting for the warps that drew the full ones
+    while (true) {
+        uint32_t w = 0;
+        if (ln == 0) w = atomicAdd(&counts[3], 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= nWork) break;
         const uint4 item = work[w];
         __syncwarp();
         for (int k = (int)ln; k < 2 * K; k += 32) myLobes[k] = __ldg(G.lobes + (size_t)item.x * K * 2 + k);
@@ -1145,7 +1151,8 @@ void GuidingHost::estepOnly() {
     const int stride = (int)statsStride();
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    const uint32_t grid = std::max(1u, std::min<uint32_t>((workBound + 3) / 4, (uint32_t)sms * 8));
+    const uint32_t grid = std::max(1u, std::min<uint32_t>((workBound + 3) / 4, (uint32_t)sms * 4));  // one resident wave (128 registers)
+    CUDA_OK(cudaMemsetAsync(dCounts.p + 3, 0, sizeof(uint32_t), stream));
     if (K <= 8)
         k_estep<8><<<grid, 128, 0, stream>>>(G, dSortPos.p, dSortDir.p, dWork.p, dCounts.p, dPartials.p, stride);
     else if (K <= 16)

@@ -262,6 +262,11 @@ struct Integrator {
             throw std::runtime_error("no CUDA device available (this library has no CPU path)");
         if (device < 0 || device >= count) throw std::runtime_error("invalid CUDA device index");
         CUDA_OK(cudaSetDevice(device));
+        // L2 fetch granularity (bytes pulled from DRAM per missing sector; the driver's default is 64): the scattered records of
+        // this path are 16-32 B (training samples in the gather, lobes, tree nodes), so half of every default fetch is wasted
+        // DRAM bandwidth. A/B knob, device-wide: B200PG_L2_FETCH=32|64|128.
+        if (const char *g = std::getenv("B200PG_L2_FETCH"))
+            if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(g)) != cudaSuccess) cudaGetLastError();
         CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         for (auto &e2 : ev) {
             e2 = nullptr;
