@@ -301,6 +301,14 @@ void b200pg_destroy(void *integ);
  *            default 0, or the value of the environment variable
  *            B200PG_SORT_BOUNCES; per-path results do not depend on it), "feature_buffers" (0/1: accumulate the denoiser
  *            feature buffers, see b200pg_features_read).
+ *            Scheduling knobs -- they change the order in which paths are shaded and rays are traversed, never a sample's
+ *            value (tests/test_gpu_mesh.py::test_mesh_radiance_does_not_depend_on_the_schedule): "lanes" (1..8 concurrent
+ *            wavefront sub-batches per progression, default 2), "overlap_shadow" (0/1: shadow stage of bounce b next to the
+ *            closest-hit stage of bounce b + 1, default 1), "lane_major" (0/1 enqueue order, default 0), "trace_spec" (bit 0:
+ *            persistent speculative traversal for bounce queues, bit 1: for shadow queues, bit 2: for camera rays; default 3),
+ *            "partition" (0 = never, 1 = adaptive hit / miss partition of sparse shade queues and the event partition of the
+ *            volumetric path, 2 = every bounce >= 1; default 1), "tail_visits" (node-visit budget of a ray before the
+ *            warp-cooperative kernel finishes it; 0 = off, -1 = library default: 96 on scenes with >= 64 k BVH nodes).
  *   stage times: 5 doubles / 5 launch counts = trace(closest), shade, shadow(any-hit), film, train.
  *   scene_upload: re-sends the compiled scene host->device (bench.py's end-to-end leg). */
 int b200pg_set_option(void *integ, const char *name, int value);

@@ -29,10 +29,10 @@ static constexpr int kChunk = 2048;  // samples per E-step work item (one warp)
 
 __device__ __forceinline__ uint32_t lane() { return threadIdx.x & 31u; }
 
-__global__ void __launch_bounds__(256) k_guide_cells(GuideDevice G, const float4 *__restrict__ sPos, uint32_t n,
+__global__ void __launch_bounds__(256) k_guide_cells(GuideDevice G, const float4 *__restrict__ sRec, uint32_t n,
                                                      uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 p = sPos[i];
+        const float4 p = sRec[2 * (size_t)i];
         keys[i] = guideLookup(G, f3(p.x, p.y, p.z));
         vals[i] = i;
     }
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(128) k_estep(GuideDevice G, const float4 *__re
 // is positive and finite go to the front (count -> work[w].w), the others to the back in reverse order. Zero-weight
 // samples (paths that found no light) only matter for the cell's sample count and position moments, so the E-step
 // iterates over the dense front part with all lanes busy.
-__global__ void __launch_bounds__(128) k_gather_partition(const float4 *__restrict__ sPos, const float4 *__restrict__ sDir,
+__global__ void __launch_bounds__(128) k_gather_partition(const float4 *__restrict__ sRec,
                                                           const uint32_t *__restrict__ perm, uint4 *__restrict__ work,
                                                           const uint32_t *__restrict__ counts, float4 *__restrict__ oPos,
                                                           float4 *__restrict__ oDir, float *__restrict__ partials, int stride, int K) {
@@ -494,8 +494,9 @@ __global__ void __launch_bounds__(128) k_gather_partition(const float4 *__restri
             float4 p = make_float4(0, 0, 0, 0), d = p;
             if (valid) {
                 const uint32_t i = perm[j];
-                p = sPos[i];
-                d = sDir[i];
+                const F8 r = ldStream256(sRec + 2 * (size_t)i);  // one 32-byte record per gathered sample
+                p = r.a;
+                d = r.b;
                 m[0] += p.x; m[1] += p.y; m[2] += p.z;
                 m[3] += p.x * p.x; m[4] += p.y * p.y; m[5] += p.z * p.z;
             }
@@ -862,10 +863,10 @@ __global__ void __launch_bounds__(256) k_guide_query(GuideDevice G, const float 
 }
 
 __global__ void __launch_bounds__(256) k_pack_samples(const float *pos, const float *dir, const float *weight, const float *pdf,
-                                                      const float *dist, uint32_t n, float4 *sPos, float4 *sDir, float *sDist) {
+                                                      const float *dist, uint32_t n, float4 *sRec, float *sDist) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        sPos[i] = make_float4(pos[3 * (size_t)i], pos[3 * (size_t)i + 1], pos[3 * (size_t)i + 2], weight ? weight[i] : 0.0f);
-        sDir[i] = make_float4(dir ? dir[3 * (size_t)i] : 0.0f, dir ? dir[3 * (size_t)i + 1] : 0.0f, dir ? dir[3 * (size_t)i + 2] : 1.0f,
+        sRec[2 * (size_t)i] = make_float4(pos[3 * (size_t)i], pos[3 * (size_t)i + 1], pos[3 * (size_t)i + 2], weight ? weight[i] : 0.0f);
+        sRec[2 * (size_t)i + 1] = make_float4(dir ? dir[3 * (size_t)i] : 0.0f, dir ? dir[3 * (size_t)i + 1] : 0.0f, dir ? dir[3 * (size_t)i + 2] : 1.0f,
                               pdf ? pdf[i] : 1.0f);
         sDist[i] = dist ? dist[i] : 0.0f;
     }
@@ -1028,7 +1029,7 @@ void GuidingHost::configure(ShadeArgs &A) {
     G.record = active && recording;
     G.vRec = dVRec.p;
     G.maxVerts = maxVerts;
-    G.sPos = dSPos.p; G.sDir = dSDir.p; G.sDist = dSDist.p;
+    G.sRec = dSRec.p; G.sDist = dSDist.p;
     G.sCount = dSCount.p;
     G.sCapacity = (uint32_t)sampleCapacity;
 }
@@ -1044,7 +1045,7 @@ void GuidingHost::sortByCell(uint32_t n) {
     G.lobeStats = dLobeStats.p;
     G.K = K;
     if (n) {
-        k_guide_cells<<<gridFor(n, 256), 256, 0, stream>>>(G, dSPos.p, n, dKeysA.p, dValsA.p);
+        k_guide_cells<<<gridFor(n, 256), 256, 0, stream>>>(G, dSRec.p, n, dKeysA.p, dValsA.p);
         launches++;
     }
     uint32_t *kin = dKeysA.p, *vin = dValsA.p, *kout = dKeysB.p, *vout = dValsB.p;
@@ -1092,7 +1093,7 @@ void GuidingHost::buildWork() {
     int smCount = 148;
     cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, 0);
     const uint32_t grid = std::max(1u, std::min<uint32_t>((workBound + 3) / 4, (uint32_t)smCount * 16));
-    k_gather_partition<<<grid, 128, 0, stream>>>(dSPos.p, dSDir.p, sortedPerm, dWork.p, dCounts.p, dSortPos.p, dSortDir.p, dPartials.p,
+    k_gather_partition<<<grid, 128, 0, stream>>>(dSRec.p, sortedPerm, dWork.p, dCounts.p, dSortPos.p, dSortDir.p, dPartials.p,
                                                  (int)statsStride(), K);
     launches++;
 }
@@ -1114,7 +1115,7 @@ void GuidingHost::begin() {
 void GuidingHost::beginExternal(const float *pos, const float *dir, const float *weight, const float *pdf, const float *dist,
                                 size_t n) {
     if (n > sampleCapacity) {
-        dSPos.alloc(n); dSDir.alloc(n); dSDist.alloc(n);
+        dSRec.alloc(2 * n); dSDist.alloc(n);
         sampleCapacity = n;
     }
     DevBuf<float> a, b, c, d, e;
@@ -1125,7 +1126,7 @@ void GuidingHost::beginExternal(const float *pos, const float *dir, const float 
     if (dist) e.upload(dist, n, stream);
     if (n) {
         k_pack_samples<<<gridFor(n, 256), 256, 0, stream>>>(a.p, dir ? b.p : nullptr, weight ? c.p : nullptr, pdf ? d.p : nullptr,
-                                                            dist ? e.p : nullptr, (uint32_t)n, dSPos.p, dSDir.p, dSDist.p);
+                                                            dist ? e.p : nullptr, (uint32_t)n, dSRec.p, dSDist.p);
         launches++;
     }
     CUDA_OK(cudaStreamSynchronize(stream));
@@ -1430,7 +1431,7 @@ void GuidingHost::bin(const float *pos, size_t n, uint32_t *outCell, uint32_t *o
         G.nodes = dNodes.p;
         DevBuf<uint32_t> k, v;
         k.alloc(n); v.alloc(n);
-        k_guide_cells<<<gridFor(n, 256), 256, 0, stream>>>(G, dSPos.p, (uint32_t)n, k.p, v.p);
+        k_guide_cells<<<gridFor(n, 256), 256, 0, stream>>>(G, dSRec.p, (uint32_t)n, k.p, v.p);
         launches++;
         CUDA_OK(cudaMemcpyAsync(outCell, k.p, n * 4, cudaMemcpyDeviceToHost, stream));
         CUDA_OK(cudaStreamSynchronize(stream));

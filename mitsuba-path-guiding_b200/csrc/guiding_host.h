@@ -66,7 +66,7 @@ struct GuidingHost {
 
     // training-vertex records and samples
     DevBuf<float4> dVRec;  // 4 x float4 per training vertex
-    DevBuf<float4> dSPos, dSDir, dSortPos, dSortDir;
+    DevBuf<float4> dSRec, dSortPos, dSortDir;  // samples as recorded (32-byte records) / sorted by cell (two arrays for the E-step's bulk copies)
     DevBuf<float> dSDist;
     DevBuf<uint32_t> dSCount;
     size_t vertCapacity = 0, sampleCapacity = 0;

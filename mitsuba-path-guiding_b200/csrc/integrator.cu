@@ -262,11 +262,6 @@ struct Integrator {
             throw std::runtime_error("no CUDA device available (this library has no CPU path)");
         if (device < 0 || device >= count) throw std::runtime_error("invalid CUDA device index");
         CUDA_OK(cudaSetDevice(device));
-        // L2 fetch granularity (bytes pulled from DRAM per missing sector; the driver's default is 64): the scattered records of
-        // this path are 16-32 B (training samples in the gather, lobes, tree nodes), so half of every default fetch is wasted
-        // DRAM bandwidth. A/B knob, device-wide: B200PG_L2_FETCH=32|64|128.
-        if (const char *g = std::getenv("B200PG_L2_FETCH"))
-            if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(g)) != cudaSuccess) cudaGetLastError();
         CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         for (auto &e2 : ev) {
             e2 = nullptr;
@@ -374,7 +369,7 @@ struct Integrator {
             // progression beforehand; this covers stand-alone batches such as b200pg_k_radiance)
             const size_t want = std::min<size_t>(totalSlots * guide.maxVerts, (size_t)48 << 20);
             if (want > guide.sampleCapacity) {
-                guide.dSPos.alloc(want); guide.dSDir.alloc(want); guide.dSDist.alloc(want);
+                guide.dSRec.alloc(2 * want); guide.dSDist.alloc(want);
                 guide.sampleCapacity = want;
             }
         }
@@ -570,7 +565,7 @@ struct Integrator {
         if (guide.active && guide.recording) {
             size_t want = std::min<size_t>((size_t)W * (rowEnd - rowBegin) * nSamples * guide.maxVerts, (size_t)48 << 20);
             if (want > guide.sampleCapacity) {
-                guide.dSPos.alloc(want); guide.dSDir.alloc(want); guide.dSDist.alloc(want);
+                guide.dSRec.alloc(2 * want); guide.dSDist.alloc(want);
                 guide.sampleCapacity = want;
             }
         }

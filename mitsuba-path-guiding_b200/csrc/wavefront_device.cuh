@@ -107,8 +107,7 @@ PG_DEV void emitTrainingSamples(const GuideDevice &G, uint32_t nMine, uint32_t i
         const float ex = T.x > 0 ? diff.x / T.x : 0.0f, ey = T.y > 0 ? diff.y / T.y : 0.0f, ez = T.z > 0 ? diff.z / T.z : 0.0f;
         float w = ((ex + ey + ez) * (1.0f / 3.0f)) / p.w;
         if (!isfinite(w) || w < 0) w = 0.0f;
-        stStream(G.sPos + dst, make_float4(p.x, p.y, p.z, w));
-        stStream(G.sDir + dst, make_float4(d.x, d.y, d.z, p.w));
+        stStream256(G.sRec + 2 * (size_t)dst, make_float4(p.x, p.y, p.z, w), make_float4(d.x, d.y, d.z, p.w));
         stStream(G.sDist + dst, d.w);
     }
 }
