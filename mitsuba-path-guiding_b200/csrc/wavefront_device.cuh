@@ -101,7 +101,8 @@ PG_DEV void emitTrainingSamples(const GuideDevice &G, uint32_t nMine, uint32_t i
         const uint32_t v = t - (oIncl - oN);
         const size_t vi = (size_t)oSlot * G.maxVerts + v;
         const float4 *rec = G.vRec + 4 * vi;
-        const float4 p = ldStream(rec), d4 = ldStream(rec + 1), T = ldStream(rec + 2), Lk = ldStream(rec + 3);
+        const F8 ra = ldStream256(rec), rb = ldStream256(rec + 2);  // the two 32-byte sectors of the vertex record
+        const float4 p = ra.a, d4 = ra.b, T = rb.a, Lk = rb.b;
         const float4 d = make_float4(d4.x, d4.y, d4.z, T.w);  // direction, distance to the next hit
         const float3 diff = f3(Lx, Ly, Lz) - f3(Lk.x, Lk.y, Lk.z);
         const float ex = T.x > 0 ? diff.x / T.x : 0.0f, ey = T.y > 0 ? diff.y / T.y : 0.0f, ez = T.z > 0 ? diff.z / T.z : 0.0f;
@@ -114,15 +115,13 @@ PG_DEV void emitTrainingSamples(const GuideDevice &G, uint32_t nMine, uint32_t i
 
 PG_DEV void guideVertexOpen(const GuideDevice &G, uint32_t slot, uint32_t v, float3 p, float pdf, float3 wo) {
     float4 *rec = G.vRec + 4 * ((size_t)slot * G.maxVerts + v);
-    stStream(rec, make_float4(p.x, p.y, p.z, pdf));
-    stStream(rec + 1, make_float4(wo.x, wo.y, wo.z, 0.0f));
+    stStream256(rec, make_float4(p.x, p.y, p.z, pdf), make_float4(wo.x, wo.y, wo.z, 0.0f));
 }
 // thr = the throughput the path record carried into this bounce (before Russian roulette rescales it) = the
 // throughput right after the vertex; L = radiance gathered so far (the vertex' NEE has landed by now)
 PG_DEV void guideVertexClose(const GuideDevice &G, uint32_t slot, uint32_t v, float3 thr, float dist, float3 L) {
     float4 *rec = G.vRec + 4 * ((size_t)slot * G.maxVerts + v);
-    stStream(rec + 2, make_float4(thr.x, thr.y, thr.z, dist));
-    stStream(rec + 3, make_float4(L.x, L.y, L.z, 0.0f));
+    stStream256(rec + 2, make_float4(thr.x, thr.y, thr.z, dist), make_float4(L.x, L.y, L.z, 0.0f));
 }
 
 // A terminated path leaves its final sample value in the splat buffer (indexed by the path's slot, i.e.
@@ -133,8 +132,8 @@ PG_DEV void finishPath(const ShadeArgs &A, uint32_t slot, float4 pos4, float3 L)
         A.radianceOut[3 * (size_t)slot + 1] = L.y;
         A.radianceOut[3 * (size_t)slot + 2] = L.z;
     } else {
-        stStream(A.splat + 2 * (size_t)slot, make_float4(pos4.x, pos4.y, L.x, L.y));  // one whole 32-byte sector per sample
-        stStream(A.splat + 2 * (size_t)slot + 1, make_float4(L.z, 0.0f, 0.0f, 0.0f));
+        // one whole 32-byte sector per sample, one 256-bit store
+        stStream256(A.splat + 2 * (size_t)slot, make_float4(pos4.x, pos4.y, L.x, L.y), make_float4(L.z, 0.0f, 0.0f, 0.0f));
     }
 }
 

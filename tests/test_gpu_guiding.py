@@ -68,7 +68,12 @@ def test_query_pdf_and_sample(trained):
     assert np.array_equal(qo["cell"], qg["cell"])                              # indexing: bit-exact
     assert np.all(np.abs(qo["pdf"] - qg["pdf"]) <= 1e-5 * np.maximum(qo["pdf"], 1e-3))
     assert np.abs(qo["dir"] - qg["dir"]).max() <= 1e-5
-    assert np.all(np.abs(qo["spdf"] - qg["spdf"]) <= 1e-5 * np.maximum(qo["spdf"], 1e-2))
+    # pdf of the sampled direction: a sharp lobe (kappa up to 5000) turns the 1e-5 the two directions may differ by into
+    # kappa * 1e-5 relative in the pdf, so the 1e-5 bar is stated where it is meaningful -- the oracle's mixture pdf evaluated
+    # at the direction the GPU drew -- and the two sides' own values only have to agree to that conditioning
+    at_gpu_dir = fld.pdf_sample(pos, qg["dir"], u)["pdf"]
+    assert np.all(np.abs(at_gpu_dir - qg["spdf"]) <= 1e-5 * np.maximum(at_gpu_dir, 1e-2))
+    assert np.quantile(np.abs(qo["spdf"] - qg["spdf"]) / np.maximum(qo["spdf"], 1e-2), 0.999) <= 1e-4
     tuv = it.k_vmm_pdf_sample(pos[:0], d[:0], u[:0])                           # empty input
     assert tuv["pdf"].shape == (0,)
 
