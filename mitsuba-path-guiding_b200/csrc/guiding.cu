@@ -193,7 +193,7 @@ __device__ __forceinline__ uint32_t blockExclusiveScan1024(uint32_t v, uint32_t 
 //   offsets[c]  = first sorted sample of cell c (suffix minimum of the cell starts; empty cells inherit the next start)
 //   workOfs[c]  = first work item of cell c, items = chunks of <= kChunk consecutive samples of ONE cell
 //   counts[2]   = number of work items
-// One block of 1024 threads; nCells <= 16 * 1024.
+// One block of 1024 threads (each walks ceil(nCells / 1024) consecutive cells); nCells <= kCommMaxCells = 65536.
 __global__ void __launch_bounds__(1024) k_build_work(const uint32_t *__restrict__ cellStart, uint32_t nCells, uint32_t n, uint32_t chunk,
                                                      uint32_t *__restrict__ offsets, uint32_t *__restrict__ workOfs,
                                                      uint32_t *__restrict__ counts) {
@@ -1077,7 +1077,7 @@ void GuidingHost::sortByCell(uint32_t n) {
 // Work items, gather + partition, position moments: all enqueued without a host round trip; kernels read the number
 // of work items from dCounts[2] and run on persistent grids.
 void GuidingHost::buildWork() {
-    if (numCells() > 16 * 1024) throw std::runtime_error("guiding field exceeds 16384 cells");
+    if (numCells() > kCommMaxCells) throw std::runtime_error("guiding field exceeds its capacity of 65536 cells");
     const uint32_t nc = numCells();
     workBound = nSamples / kChunk + nc + 1;
     dOffsets.alloc(nc + 1);
@@ -1173,7 +1173,7 @@ void GuidingHost::update(bool commit) {
 // only learns the new cell / node counts (8 bytes).
 void GuidingHost::end() {
     k_split<<<1, 1024, 0, stream>>>(dNodes.p, dLobes.p, dLobeStats.p, dCells.p, dCellLeaf.p, dStats.p, dCounts.p,
-                                   K, (int)statsStride(), maxCellSamples, (uint32_t)std::min<size_t>(dCells.n, 16 * 1024));
+                                   K, (int)statsStride(), maxCellSamples, (uint32_t)std::min<size_t>(dCells.n, kCommMaxCells));
     launches++;
     uint32_t counts[2] = {0, 0};
     CUDA_OK(cudaMemcpyAsync(counts, dCounts.p, sizeof(counts), cudaMemcpyDeviceToHost, stream));
