@@ -32,11 +32,15 @@ def demangle(name):
 
 
 WANT = [
-    ("guiding.o", "k_estep", r"UBLKCP|SYNCS|ARRIVE|MUFU\.EX2", "bulk async copy (UBLKCP) + mbarrier (SYNCS) sample ring, ex2-path exponential"),
-    ("kernels.o", "k_trace_specILb0ELb0E", r"LDG\.E\.128|FADD2|FMUL2|VOTE|CCTL|PREFETCH|LDL|STL", "binary tree: 4 x LDG.128 per node, packed slab arithmetic (FADD2 / FMUL2), warp vote of the speculative descent, L2 prefetch of deferred subtrees, local-memory stack"),
-    ("kernels.o", "k_trace_specILb0ELb1E", r"LDG\.E\.128|PRMT|FFMA|STL\.64|LDL", "8-ary quantised tree: 6 x LDG.128 per node, PRMT builds 2^23 + q, one FFMA per plane, 8-byte (ref, distance) stack entries"),
+    ("guiding.o", "k_estep", r"UBLKCP|SYNCS|ARRIVE|MUFU\.EX2|ATOMG|ATOM\.", "bulk async copy (UBLKCP) + mbarrier (SYNCS) sample ring, ex2-path exponential, dynamic chunk fetch (one atomic per chunk)"),
+    ("kernels.o", "k_trace_specILb0ELb0E", r"LDG\.E.*256|LDG\.E\.128|FADD2|FMUL2|VOTE|LDL|STL|ATOMG|RED", "binary tree: 2 x LDG.256 per node, LDG.256 plane pairs / (u, v) rows, packed slab arithmetic (FADD2 / FMUL2), warp vote of the speculative descent, local-memory stack, tail-list append"),
+    ("kernels.o", "k_trace_tailILb0ELb0ENS_12ClosestQueue", r"LDG\.E.*256|REDUX|VOTE|LDS|STS|SHFL", "warp-cooperative tail kernel: shared-memory stack (LDS / STS), warp-wide minimum of the candidate hit (REDUX.MIN), ballots for the pushes"),
+    ("kernels.o", "k_trace_specILb0ELb1E", r"LDG\.E\.128|PRMT|FFMA|STL\.64|LDL", "8-ary quantised tree (optional): 6 x LDG.128 per node, PRMT builds 2^23 + q, one FFMA per plane, 8-byte (ref, distance) stack entries"),
     ("kernels.o", "k_splatE", r"RED|ATOM", "film accumulation: vector float4 reductions (RED.E.ADD.F32x4 / .128)"),
-    ("kernels.o", "k_shadeENS", r"LDG\.E\.128\.CONSTANT|STG\.E\.EF|LDG\.E\.EF|BAR|RED", "shade stage: 128-bit lobe / record loads, evict-first streaming loads and stores, one barrier pair per compaction"),
+    ("kernels.o", "k_shadeENS", r"LDG\.E.*256|STG\.E.*256|STG\.E\.EF|LDG\.E\.EF|BAR|RED", "shade stage: 256-bit lobe / shading-record loads, 256-bit evict-first stores of the training-vertex and splat records, evict-first streaming of the path state, one barrier pair per compaction"),
+    ("kernels.o", "k_hit_partition", r"VOTE|ATOMG|BAR|LDG|STG", "hit / miss partition: ballots, one atomic per block and class"),
+    ("guiding.o", "k_gather_partition", r"LDG\.E.*256|STG|VOTE", "gather: one 256-bit evict-first load per 32-byte sample record"),
+    ("guiding.o", "k_guide_query", r"SHFL|LDG\.E.*256|LDS|STS|VOTE", "warp-cooperative guiding queries (b200pg_k_vmm_pdf_sample): shared-memory staging of the queries, 256-bit lobe loads, transposed butterfly (SHFL.BFLY), half-warp prefix scan (SHFL.UP)"),
     ("guiding.o", "k_mstep_allreduce", r"LD\.E.*SYS|ST\.E.*SYS|LDG\.E\.128\.STRONG\.SYS|STG\.E\.128\.STRONG\.SYS|STRONG\.SYS|MEMBAR|globaltimer|S2UR.*TIMER|CS2R", "cross-GPU exchange: system-scope 128-bit loads / stores, release / acquire flags, wall-clock timeout (globaltimer)"),
 ]
 
