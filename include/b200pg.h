@@ -308,7 +308,8 @@ void b200pg_destroy(void *integ);
  *            persistent speculative traversal for bounce queues, bit 1: for shadow queues, bit 2: for camera rays; default 3),
  *            "partition" (0 = never, 1 = adaptive hit / miss partition of sparse shade queues and the event partition of the
  *            volumetric path, 2 = every bounce >= 1; default 1), "tail_visits" (node-visit budget of a ray before the
- *            warp-cooperative kernel finishes it; 0 = off, -1 = library default: 96 on scenes with >= 64 k BVH nodes).
+ *            warp-cooperative kernel finishes it; 0 = off, -1 = library default: 96 on scenes with >= 64 k BVH nodes),
+ *            "splat_tile" (0/1: film accumulation through a per-warp shared-memory tile, default 1).
  *   stage times: 5 doubles / 5 launch counts = trace(closest), shade, shadow(any-hit), film, train.
  *   scene_upload: re-sends the compiled scene host->device (bench.py's end-to-end leg). */
 int b200pg_set_option(void *integ, const char *name, int value);

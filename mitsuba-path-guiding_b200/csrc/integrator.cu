@@ -54,7 +54,7 @@ void launchGridLookup(const DeviceScene &S, int medium, const float *p, uint32_t
 void launchMediumTest(const DeviceScene &S, int medium, const float4 *rays, uint32_t n, float *outT, float *outTr, float *outWo,
                       float *outPdf, cudaStream_t st);
 void launchFilmExport(const float4 *film, float *out, uint32_t n, int develop, cudaStream_t st);
-void launchSplat(const FilmRecord &F, float4 *film, const float4 *splat, uint32_t n, float maxComponentValue, cudaStream_t st);
+void launchSplat(const FilmRecord &F, float4 *film, const float4 *splat, uint32_t n, float maxComponentValue, bool tile, cudaStream_t st);
 void launchTraceRays(const DeviceScene &S, const float4 *rays, uint32_t n, float4 *hits, uint32_t *work, Counters *C, bool shadow,
                      bool count, bool speculative, TailList T, uint32_t *tailWork, cudaStream_t st);
 void launchFilmSplat(const FilmRecord &F, float4 *film, const float2 *pos, const float3 *rgb, uint32_t n, float maxComponentValue,
@@ -128,6 +128,7 @@ struct Integrator {
     static constexpr int kMaxLanes = 8;
     Lane lane[kMaxLanes];
     bool overlapShadow = !(std::getenv("B200PG_OVERLAP_SHADOW") && std::atoi(std::getenv("B200PG_OVERLAP_SHADOW")) == 0);
+    bool splatTile = true;  // k_splat accumulates a warp's 8 x 4 pixel tile in shared memory first (set_option "splat_tile")
     bool laneMajor = std::getenv("B200PG_LANE_MAJOR") && std::atoi(std::getenv("B200PG_LANE_MAJOR")) != 0;
     int lanes = std::getenv("B200PG_LANES") ? std::max(1, std::min(kMaxLanes, std::atoi(std::getenv("B200PG_LANES")))) : 2;
     DevBuf<float4> dSplat;
@@ -517,7 +518,7 @@ struct Integrator {
             if (!radianceOut && !cancel.load()) {  // every path of the batch has ended exactly once: rasterise them
                 cudaEvent_t t = spanBegin(st[l]);
                 const float4 *sp = dSplat.p + 2 * (size_t)batches[l].slotBase;
-                launchSplat(S.film, dFilm.p, sp, batches[l].nPaths, params.max_component_value, st[l]);
+                launchSplat(S.film, dFilm.p, sp, batches[l].nPaths, params.max_component_value, splatTile, st[l]);
                 stats.kernel_launches++;
                 if (featureBuffers) {
                     launchFeatureColor(S.film, sp, batches[l].nPaths, params.max_component_value, dFeat.p, st[l]);
@@ -1321,6 +1322,7 @@ int b200pg_set_option(void *integ, const char *name, int value) {
     else if (n == "overlap_shadow") self->overlapShadow = value != 0;
     else if (n == "lanes") self->lanes = std::max(1, std::min((int)Integrator::kMaxLanes, value));
     else if (n == "partition") self->partitionMode = value;
+    else if (n == "splat_tile") self->splatTile = value != 0;
     else if (n == "tail_visits") self->tailVisits = value;
     else if (n == "lane_major") self->laneMajor = value != 0;
     else if (n == "feature_buffers") {

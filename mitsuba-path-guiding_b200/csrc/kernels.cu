@@ -398,7 +398,18 @@ __global__ void __launch_bounds__(128) k_trace(DeviceScene S, const float4 *__re
 // Results are identical to traceRay(): the same node / primitive tests, and a closest hit does not depend on visit order
 // (ties: the lowest t wins, equal t keeps the first found -- the reference has no rule either, skdtree.cpp:112-142).
 // ------------------------------------------------------------------------------------------
-static constexpr int kRefillBelow = 24;
+#ifndef PG_REFILL_BELOW
+#define PG_REFILL_BELOW 24
+#endif
+#ifndef PG_TRACE_MIN_BLOCKS
+#define PG_TRACE_MIN_BLOCKS 0  // resident CTAs per SM the speculative kernels are compiled for (0 = compiler's choice: 56 registers, 9 CTAs; A/B: 10 = 48 registers, 12 = 40)
+#endif
+#if PG_TRACE_MIN_BLOCKS > 0
+#define PG_TRACE_BOUNDS __launch_bounds__(128, PG_TRACE_MIN_BLOCKS)
+#else
+#define PG_TRACE_BOUNDS __launch_bounds__(128)
+#endif
+static constexpr int kRefillBelow = PG_REFILL_BELOW;
 
 // kWide: walk the 8-ary quantised tree (large meshes) instead of the binary one -- same leaves, same primitive tests.
 template <bool kWide>
@@ -616,7 +627,7 @@ __global__ void __launch_bounds__(128) k_trace_rays_spec(DeviceScene S, RayListQ
     }
 }
 template <bool kCount, bool kWide>
-__global__ void __launch_bounds__(128) k_trace_spec(DeviceScene S, ClosestQueue Q, const uint32_t *nPtr, uint32_t *work, Counters *C,
+__global__ void PG_TRACE_BOUNDS k_trace_spec(DeviceScene S, ClosestQueue Q, const uint32_t *nPtr, uint32_t *work, Counters *C,
                                                     TailList T) {
     unsigned long long rays = 0;
     uint32_t cn = 0, cp = 0;
@@ -628,7 +639,7 @@ __global__ void __launch_bounds__(128) k_trace_spec(DeviceScene S, ClosestQueue 
     }
 }
 template <bool kCount, bool kWide>
-__global__ void __launch_bounds__(128) k_shadow_spec(DeviceScene S, ShadowRayQueue Q, const uint32_t *nPtr, uint32_t *work, Counters *C,
+__global__ void PG_TRACE_BOUNDS k_shadow_spec(DeviceScene S, ShadowRayQueue Q, const uint32_t *nPtr, uint32_t *work, Counters *C,
                                                      TailList T) {
     unsigned long long rays = 0;
     uint32_t cn = 0, cp = 0;
@@ -1039,13 +1050,81 @@ __global__ void __launch_bounds__(kShadeThreads, PG_SHADE_BLOCKS) k_shade(ShadeA
     warpAddU64(&A.C->pathLen, doneLen);
 }
 
-// Film accumulation for a finished batch: one thread per camera sample, in slot (= pixel) order, so the
-// 32 float4 atomics of a warp instruction fall on neighbouring texels.
+// Film accumulation for a finished batch: one thread per camera sample, in slot (= pixel) order.
+//
+// A sample's Gaussian footprint covers up to 5 x 5 texels, so a direct scatter issues 25 float4 reductions per sample -- 105 M
+// of them per C2 step, 0.29 ms, bound by the L2's atomic throughput. k_generate lays 32 consecutive slots out as an 8 x 4 pixel
+// tile, so the footprints of one warp's samples overlap heavily: 800 contributions land on 12 x 8 texels. The warp therefore
+// accumulates them in a shared-memory tile first -- 25 steps; in step (dx, dy) every lane adds to the texel at that offset from
+// ITS pixel, which is a different texel for every lane, so plain read-modify-writes need no atomics -- and issues three
+// reductions per lane for the 96 texels afterwards: 8 x fewer atomics. The weights are those of filmSplat (same table bins,
+// same 32 x 32-tile + border coordinates, same rejection rules); only the order of the float additions differs. Warps whose 32
+// slots are not such a tile (pixel lists, odd image sizes, the end of a batch) and filters wider than the tile's 2-texel apron take
+// the scatter path.
+#ifndef PG_SPLAT_TILE
+#define PG_SPLAT_TILE 1
+#endif
 __global__ void __launch_bounds__(256) k_splat(FilmRecord F, float4 *film, const float4 *__restrict__ splat, uint32_t n,
-                                               float maxComponentValue) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 a = splat[2 * (size_t)i], b = splat[2 * (size_t)i + 1];
-        filmSplat(F, film, make_float2(a.x, a.y), f3(a.z, a.w, b.x), maxComponentValue);
+                                               float maxComponentValue, int useTile) {
+    __shared__ float4 sTile[8][96];
+    float4 *tile = sTile[threadIdx.x >> 5];
+    const uint32_t lane = laneId();
+    const int border = (int)ceilf(F.radius - 0.5f);
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + lane;
+        const bool valid = i < n;
+        float4 a = make_float4(0, 0, 0, 0), b = a;
+        if (valid) {
+            a = splat[2 * (size_t)i];
+            b = splat[2 * (size_t)i + 1];
+        }
+        const float2 pos = make_float2(a.x, a.y);
+        float3 spec = f3(a.z, a.w, b.x);
+        const int pxI = min(max((int)pos.x, 0), F.width - 1), pyI = min(max((int)pos.y, 0), F.height - 1);
+        const int x0 = __shfl_sync(0xffffffffu, pxI, 0), y0 = __shfl_sync(0xffffffffu, pyI, 0);
+        const bool inTile = valid && pxI == x0 + (int)(lane & 7u) && pyI == y0 + (int)(lane >> 3);
+        if (!PG_SPLAT_TILE || !useTile || !(F.radius <= 2.0f) || __ballot_sync(0xffffffffu, inTile) != 0xffffffffu) {
+            if (valid) filmSplat(F, film, pos, spec, maxComponentValue);
+            continue;
+        }
+        // ---- the sample's value and per-axis weights, exactly as filmSplat forms them
+        const float maxSpec = maxComp(spec);
+        if (maxSpec > maxComponentValue) spec = spec * (maxComponentValue / maxSpec);
+        const bool ok = isfinite(spec.x) && isfinite(spec.y) && isfinite(spec.z) && spec.x >= 0 && spec.y >= 0 && spec.z >= 0;
+        const int ox = (pxI >> 5) << 5, oy = (pyI >> 5) << 5;
+        const int bw = min(32, F.width - ox) + 2 * border, bh = min(32, F.height - oy) + 2 * border;
+        const float px = pos.x - 0.5f - (float)(ox - border), py = pos.y - 0.5f - (float)(oy - border);
+        const int minx = max((int)ceilf(px - F.radius), 0), miny = max((int)ceilf(py - F.radius), 0);
+        const int maxx = min((int)floorf(px + F.radius), bw - 1), maxy = min((int)floorf(py + F.radius), bh - 1);
+        float wx[5], wy[5];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) {
+            const int x = pxI + d - 2 - ox + border, y = pyI + d - 2 - oy + border;  // block-local texel coordinates
+            wx[d] = (ok && x >= minx && x <= maxx) ? F.values[min((int)fabsf((x - px) * F.scaleFactor), 31)] : 0.0f;
+            wy[d] = (ok && y >= miny && y <= maxy) ? F.values[min((int)fabsf((y - py) * F.scaleFactor), 31)] : 0.0f;
+        }
+        tile[lane] = tile[lane + 32] = tile[lane + 64] = make_float4(0, 0, 0, 0);
+        __syncwarp();
+        const int tx = (int)(lane & 7u), ty = (int)(lane >> 3);
+#pragma unroll
+        for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 5; ++dx) {
+                const float w = wx[dx] * wy[dy];
+                float4 *t = tile + (ty + dy) * 12 + tx + dx;  // a different texel for every lane
+                float4 v = *t;
+                v.x += w * spec.x; v.y += w * spec.y; v.z += w * spec.z; v.w += w;
+                *t = v;
+                __syncwarp();
+            }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int t = (int)lane + 32 * k;
+            const int fx = x0 - 2 + t % 12, fy = y0 - 2 + t / 12;
+            const float4 v = tile[t];
+            if (fx >= 0 && fx < F.width && fy >= 0 && fy < F.height && v.w != 0.0f) atomicAdd(film + (size_t)fy * F.width + fx, v);
+        }
+        __syncwarp();
     }
 }
 
@@ -1227,9 +1306,9 @@ void launchShade(const ShadeArgs &A, cudaStream_t st) {
     static int grid = persistentGrid(k_shade, kShadeThreads);
     k_shade<<<grid, kShadeThreads, 0, st>>>(A);
 }
-void launchSplat(const FilmRecord &F, float4 *film, const float4 *splat, uint32_t n, float maxComponentValue, cudaStream_t st) {
+void launchSplat(const FilmRecord &F, float4 *film, const float4 *splat, uint32_t n, float maxComponentValue, bool tile, cudaStream_t st) {
     static int grid = persistentGrid(k_splat, 256);
-    k_splat<<<grid, 256, 0, st>>>(F, film, splat, n, maxComponentValue);
+    k_splat<<<grid, 256, 0, st>>>(F, film, splat, n, maxComponentValue, tile ? 1 : 0);
 }
 void launchFilmExport(const float4 *film, float *out, uint32_t n, int develop, cudaStream_t st) {
     k_film_export<<<numSMs() * 4, 256, 0, st>>>(film, out, n, develop);

@@ -231,6 +231,25 @@ def test_render_matches_oracle_image_and_counters(api, cornell):
         assert abs(a - b) <= 2e-3 * b + 2, (k_g, a, b)
 
 
+def test_tile_splat_equals_scatter_splat(api, cornell):
+    """k_splat accumulates the 8 x 4 pixel tile of a warp in shared memory before it touches the film (one eighth of the atomics);
+    same weights, different order of the float additions: the two films agree to rounding."""
+    sb, osc, it = cornell
+    try:
+        it.set_option("splat_tile", 0)
+        it.film_clear()
+        it.progression(0, 4)
+        scatter = it.film()
+        it.set_option("splat_tile", 1)
+        it.film_clear()
+        it.progression(0, 4)
+        tiled = it.film()
+    finally:
+        it.set_option("splat_tile", 1)
+    assert scatter[..., 4].sum() > 0
+    np.testing.assert_allclose(tiled, scatter, rtol=2e-5, atol=2e-5 * float(scatter.max()))
+
+
 def test_progression_partition_is_additive(api, cornell):
     """Sample batches / image bands rendered separately accumulate to the same film (multi-GPU split)."""
     sb, osc, it = cornell
