@@ -365,6 +365,9 @@ __device__ __forceinline__ void mbarWait(uint64_t *bar, uint32_t parity) {
 
 static constexpr int kEStages = 4;    // ring depth per warp
 static constexpr int kETile = 64;     // samples per stage (1 KB of positions + 1 KB of directions)
+#ifndef PG_ESTEP_PAIR
+#define PG_ESTEP_PAIR 1
+#endif
 
 // E-step. One warp per work item (<= kChunk consecutive samples of ONE cell, usable weights first); lane = sample.
 // The warp streams its samples through a private ring of kEStages shared-memory tiles filled by 1-D bulk async copies
@@ -417,6 +420,52 @@ __global__ void __launch_bounds__(128) k_estep(GuideDevice G, const float4 *__re
             const int st = (int)(t % kEStages);
             mbarWait(&sBar[warp][st], (parity >> st) & 1u);
             parity ^= 1u << st;
+#if PG_ESTEP_PAIR
+            // the lane's two samples of the tile share every lobe fetch from shared memory (the kernel issued one LDS.128 + one
+            // LDS.64 per lobe and SAMPLE; the shared-memory pipe, not the FP32 pipe, was the busier one). Same terms, same order of
+            // the additions into every accumulator (sample 0 before sample 1) as the one-sample-at-a-time loop.
+            static_assert(kETile == 64, "two samples per lane and tile");
+            float3 dd[2];
+            float sw[2], total[2] = {0.0f, 0.0f};
+            bool live[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const uint32_t local = r * 32 + ln;
+                live[r] = t * kETile + local < nGood;
+                const float4 p = sTile[warp][st][0][local], d = sTile[warp][st][1][local];
+                sw[r] = p.w;
+                dd[r] = f3(d.x, d.y, d.z);
+            }
+            float pk[2][KMAX];
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                pk[0][k] = pk[1][k] = 0.0f;
+                if (k < K) {
+                    const float4 la = myLobes[2 * k], lb = myLobes[2 * k + 1];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        pk[r][k] = guideLobeTerm(la, lb, dd[r]);
+                        total[r] += pk[r][k];
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (!live[r] || !(total[r] > 0) || !isfinite(total[r])) continue;
+                cW += sw[r];
+                const float inv = 1.0f / total[r];
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) {
+                    if (k < K) {
+                        const float g = sw[r] * (pk[r][k] * inv);
+                        S[k] += g;
+                        Rx[k] += g * dd[r].x;
+                        Ry[k] += g * dd[r].y;
+                        Rz[k] += g * dd[r].z;
+                    }
+                }
+            }
+#else
 #pragma unroll
             for (int r = 0; r < kETile / 32; ++r) {
                 const uint32_t local = r * 32 + ln;
@@ -448,6 +497,7 @@ __global__ void __launch_bounds__(128) k_estep(GuideDevice G, const float4 *__re
                     }
                 }
             }
+#endif
             __syncwarp();  // every lane has read the stage: it can be refilled
             if (ln == 0 && t + kEStages < nTiles) issue(t + kEStages);
         }

@@ -476,12 +476,14 @@ __global__ void __launch_bounds__(kShadeThreads, 6) k_shade_vol(ShadeArgs A) {
         float neeDirPdf = 0.0f, neeLightPdf = 0.0f;
 
         if (valid) {
-            const float4 ro = A.cur.rayO[i], rd = A.cur.rayD[i], thr4 = A.cur.thr[i], rad4 = A.cur.rad[i];
-            pos4 = A.cur.pos[i];
-            fl = A.cur.flags[i];
-            slot = A.cur.slot[i];
-            medium = A.cur.medium[i];
-            const float4 h4 = A.hits[i];
+            // streamed-once state: evict-first, as in k_shade
+            const float4 ro = ldStream(A.cur.rayO + i), rd = ldStream(A.cur.rayD + i), thr4 = ldStream(A.cur.thr + i),
+                         rad4 = ldStream(A.cur.rad + i);
+            pos4 = ldStream(A.cur.pos + i);
+            fl = ldStream(A.cur.flags + i);
+            slot = ldStream(A.cur.slot + i);
+            medium = ldStream(A.cur.medium + i);
+            const float4 h4 = ldStream(A.hits + i);
             L = f3(rad4.x, rad4.y, rad4.z);
             thr = f3(thr4.x, thr4.y, thr4.z);
             eta = thr4.w;
@@ -727,14 +729,14 @@ __global__ void __launch_bounds__(kShadeThreads, 6) k_shade_vol(ShadeArgs A) {
         appendParity ^= 1u;
         const uint32_t j = ap.idxA, sidx = ap.idxB;
         if (alive) {
-            A.next.rayO[j] = make_float4(newO.x, newO.y, newO.z, newMint);
-            A.next.rayD[j] = make_float4(newD.x, newD.y, newD.z, kInf);
-            A.next.thr[j] = make_float4(thr.x, thr.y, thr.z, eta);
-            A.next.rad[j] = make_float4(L.x, L.y, L.z, newPdf);
-            A.next.pos[j] = make_float4(pos4.x, pos4.y, __uint_as_float((uint32_t)rng.state), __uint_as_float((uint32_t)(rng.state >> 32)));
-            A.next.flags[j] = (fl & ~(kDepthMask | (0xFFu << kVertShift))) | (depth & kDepthMask) | (vcount << kVertShift);
-            A.next.slot[j] = slot;
-            A.next.medium[j] = medium;
+            stStream(A.next.rayO + j, make_float4(newO.x, newO.y, newO.z, newMint));
+            stStream(A.next.rayD + j, make_float4(newD.x, newD.y, newD.z, kInf));
+            stStream(A.next.thr + j, make_float4(thr.x, thr.y, thr.z, eta));
+            stStream(A.next.rad + j, make_float4(L.x, L.y, L.z, newPdf));
+            stStream(A.next.pos + j, make_float4(pos4.x, pos4.y, __uint_as_float((uint32_t)rng.state), __uint_as_float((uint32_t)(rng.state >> 32))));
+            stStream(A.next.flags + j, (fl & ~(kDepthMask | (0xFFu << kVertShift))) | (depth & kDepthMask) | (vcount << kVertShift));
+            stStream(A.next.slot + j, slot);
+            stStream(A.next.medium + j, medium);
         }
         if (wantShadow) {
             A.shadow.o[sidx] = make_float4(shO.x, shO.y, shO.z, shOnSurface ? kEpsilon : 0.0f);
