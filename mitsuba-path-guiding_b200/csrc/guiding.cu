@@ -38,6 +38,15 @@ __global__ void __launch_bounds__(256) k_guide_cells(GuideDevice G, const float4
     }
 }
 
+// binning keys straight from the recorded samples (see GuidingHost::keysValid): the tree walk already happened in the shade stage
+__global__ void __launch_bounds__(256) k_keys_from_samples(const uint32_t *__restrict__ sKey, uint32_t n, uint32_t *__restrict__ keys,
+                                                           uint32_t *__restrict__ vals) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        keys[i] = sKey[i];
+        vals[i] = i;
+    }
+}
+
 // ---- radix sort pass: per-block digit histogram, laid out digit-major (hist[digit * nBlocks + block])
 __global__ void __launch_bounds__(kSortThreads) k_radix_hist(const uint32_t *__restrict__ keys, uint32_t n, int shift,
                                                              uint32_t *__restrict__ hist, uint32_t nBlocks) {
@@ -988,6 +997,7 @@ void GuidingHost::resetField(const float *, const float *) {
 
 // host mirror -> device (initial field, loaded snapshots)
 void GuidingHost::uploadField() {
+    keysValid = false;  // a different tree: cells stored with recorded samples no longer apply
     nCells = (uint32_t)cells.size();
     nNodes = (uint32_t)nodes.size();
     mirrorValid = true;
@@ -1079,12 +1089,13 @@ void GuidingHost::configure(ShadeArgs &A) {
     G.record = active && recording;
     G.vRec = dVRec.p;
     G.maxVerts = maxVerts;
-    G.sRec = dSRec.p; G.sDist = dSDist.p;
+    G.sRec = dSRec.p; G.sDist = dSDist.p; G.sKey = dSKey.p;
+    if (G.record && !G.enabled) keysValid = false;  // vertices recorded without a cell look-up
     G.sCount = dSCount.p;
     G.sCapacity = (uint32_t)sampleCapacity;
 }
 
-void GuidingHost::sortByCell(uint32_t n) {
+void GuidingHost::sortByCell(uint32_t n, bool storedKeys) {
     const uint32_t nBlocks = (n + kSortTile - 1) / kSortTile;
     dKeysA.alloc(n); dKeysB.alloc(n); dValsA.alloc(n); dValsB.alloc(n);
     dBlockHist.alloc((size_t)256 * std::max(nBlocks, 1u));
@@ -1095,7 +1106,10 @@ void GuidingHost::sortByCell(uint32_t n) {
     G.lobeStats = dLobeStats.p;
     G.K = K;
     if (n) {
-        k_guide_cells<<<gridFor(n, 256), 256, 0, stream>>>(G, dSRec.p, n, dKeysA.p, dValsA.p);
+        if (storedKeys)
+            k_keys_from_samples<<<gridFor(n, 256), 256, 0, stream>>>(dSKey.p, n, dKeysA.p, dValsA.p);
+        else
+            k_guide_cells<<<gridFor(n, 256), 256, 0, stream>>>(G, dSRec.p, n, dKeysA.p, dValsA.p);
         launches++;
     }
     uint32_t *kin = dKeysA.p, *vin = dValsA.p, *kout = dKeysB.p, *vout = dValsB.p;
@@ -1158,14 +1172,14 @@ void GuidingHost::begin() {
     nSamples = (uint32_t)std::min<size_t>(pendingCount, sampleCapacity);
     pendingCount = 0xFFFFFFFFu;
     samplesTrained += nSamples;
-    sortByCell(nSamples);
+    sortByCell(nSamples, keysValid);
     buildWork();
 }
 
 void GuidingHost::beginExternal(const float *pos, const float *dir, const float *weight, const float *pdf, const float *dist,
                                 size_t n) {
     if (n > sampleCapacity) {
-        dSRec.alloc(2 * n); dSDist.alloc(n);
+        dSRec.alloc(2 * n); dSDist.alloc(n); dSKey.alloc(n);
         sampleCapacity = n;
     }
     DevBuf<float> a, b, c, d, e;
@@ -1181,7 +1195,8 @@ void GuidingHost::beginExternal(const float *pos, const float *dir, const float 
     }
     CUDA_OK(cudaStreamSynchronize(stream));
     nSamples = (uint32_t)n;
-    sortByCell(nSamples);
+    keysValid = false;  // these samples came from the host
+    sortByCell(nSamples, false);
     buildWork();
 }
 
@@ -1228,6 +1243,7 @@ void GuidingHost::end() {
     uint32_t counts[2] = {0, 0};
     CUDA_OK(cudaMemcpyAsync(counts, dCounts.p, sizeof(counts), cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaMemsetAsync(dSCount.p, 0, sizeof(uint32_t), stream));
+    keysValid = true;  // the sample buffer is empty: what is recorded from now on is looked up in the tree as it is now
     CUDA_OK(cudaStreamSynchronize(stream));
     CUDA_OK(cudaGetLastError());
     nCells = counts[0];

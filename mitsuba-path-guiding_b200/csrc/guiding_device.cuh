@@ -40,6 +40,7 @@ struct GuideDevice {
                            // training update gathers samples in random order and every gathered 16-byte piece costs a 64-byte
                            // DRAM fetch (ncu: k_gather_partition moved 2.85 GB for 0.9 GB of samples with two separate arrays)
     float *sDist;
+    uint32_t *sKey;        // guiding cell of the sample's vertex, as the shade stage looked it up (the binning key: no second tree walk)
     uint32_t *sCount;
     uint32_t sCapacity;
 };

@@ -68,6 +68,10 @@ struct GuidingHost {
     DevBuf<float4> dVRec;  // 4 x float4 per training vertex
     DevBuf<float4> dSRec, dSortPos, dSortDir;  // samples as recorded (32-byte records) / sorted by cell (two arrays for the E-step's bulk copies)
     DevBuf<float> dSDist;
+    DevBuf<uint32_t> dSKey;      // per recorded sample: the guiding cell the shade stage found for its vertex
+    // the stored keys are the binning keys as long as every sample in the buffer was recorded while sampling from the CURRENT tree
+    // (false after a recording progression without sampling, a field load / reset; true again when the buffer is emptied)
+    bool keysValid = false;
     DevBuf<uint32_t> dSCount;
     size_t vertCapacity = 0, sampleCapacity = 0;
 
@@ -140,7 +144,7 @@ struct GuidingHost {
     bool load(const uint32_t *w, size_t n);
 
 private:
-    void sortByCell(uint32_t n);
+    void sortByCell(uint32_t n, bool storedKeys);
     void buildWork();
 };
 

@@ -370,7 +370,7 @@ struct Integrator {
             // progression beforehand; this covers stand-alone batches such as b200pg_k_radiance)
             const size_t want = std::min<size_t>(totalSlots * guide.maxVerts, (size_t)48 << 20);
             if (want > guide.sampleCapacity) {
-                guide.dSRec.alloc(2 * want); guide.dSDist.alloc(want);
+                guide.dSRec.alloc(2 * want); guide.dSDist.alloc(want); guide.dSKey.alloc(want);
                 guide.sampleCapacity = want;
             }
         }
@@ -566,7 +566,7 @@ struct Integrator {
         if (guide.active && guide.recording) {
             size_t want = std::min<size_t>((size_t)W * (rowEnd - rowBegin) * nSamples * guide.maxVerts, (size_t)48 << 20);
             if (want > guide.sampleCapacity) {
-                guide.dSRec.alloc(2 * want); guide.dSDist.alloc(want);
+                guide.dSRec.alloc(2 * want); guide.dSDist.alloc(want); guide.dSKey.alloc(want);
                 guide.sampleCapacity = want;
             }
         }

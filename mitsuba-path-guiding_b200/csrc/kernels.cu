@@ -1002,7 +1002,7 @@ __global__ void __launch_bounds__(kShadeThreads, PG_SHADE_BLOCKS) k_shade(ShadeA
                             if (sampledType != kNull) fl |= kFlagScattered;
                             alive = true;
                             if (A.G.record && (btype & kSmooth) && (int)vcount < A.G.maxVerts) {
-                                guideVertexOpen(A.G, slot, vcount, its.p, bPdf, wo);
+                                guideVertexOpen(A.G, slot, vcount, its.p, bPdf, wo, gcell);
                                 vcount++;
                                 fl &= ~kFlagVertexClosed;
                             }

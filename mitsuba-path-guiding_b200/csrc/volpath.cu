@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(kShadeThreads, 6) k_shade_vol(ShadeArgs A) {
                                 terminate = true;
                             } else {
                             if (A.G.record && (int)vcount < A.G.maxVerts) {
-                                guideVertexOpen(A.G, slot, vcount, mRec.p, phasePdf, wo);
+                                guideVertexOpen(A.G, slot, vcount, mRec.p, phasePdf, wo, gcell);
                                 vcount++;
                                 fl &= ~kFlagVertexClosed;
                             }
@@ -697,7 +697,7 @@ __global__ void __launch_bounds__(kShadeThreads, 6) k_shade_vol(ShadeArgs A) {
                                 newMint = kEpsilon;
                                 newPdf = bPdf;
                                 if (A.G.record && (btype & kSmooth) && (int)vcount < A.G.maxVerts) {
-                                    guideVertexOpen(A.G, slot, vcount, its.p, bPdf, wo);
+                                    guideVertexOpen(A.G, slot, vcount, its.p, bPdf, wo, gcell);
                                     vcount++;
                                     fl &= ~kFlagVertexClosed;
                                 }

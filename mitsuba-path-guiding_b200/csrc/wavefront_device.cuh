@@ -110,12 +110,13 @@ PG_DEV void emitTrainingSamples(const GuideDevice &G, uint32_t nMine, uint32_t i
         if (!isfinite(w) || w < 0) w = 0.0f;
         stStream256(G.sRec + 2 * (size_t)dst, make_float4(p.x, p.y, p.z, w), make_float4(d.x, d.y, d.z, p.w));
         stStream(G.sDist + dst, d.w);
+        stStream(G.sKey + dst, __float_as_uint(d4.w));  // the vertex' guiding cell rides in the record's spare word
     }
 }
 
-PG_DEV void guideVertexOpen(const GuideDevice &G, uint32_t slot, uint32_t v, float3 p, float pdf, float3 wo) {
+PG_DEV void guideVertexOpen(const GuideDevice &G, uint32_t slot, uint32_t v, float3 p, float pdf, float3 wo, uint32_t cell) {
     float4 *rec = G.vRec + 4 * ((size_t)slot * G.maxVerts + v);
-    stStream256(rec, make_float4(p.x, p.y, p.z, pdf), make_float4(wo.x, wo.y, wo.z, 0.0f));
+    stStream256(rec, make_float4(p.x, p.y, p.z, pdf), make_float4(wo.x, wo.y, wo.z, __uint_as_float(cell)));
 }
 // thr = the throughput the path record carried into this bounce (before Russian roulette rescales it) = the
 // throughput right after the vertex; L = radiance gathered so far (the vertex' NEE has landed by now)
