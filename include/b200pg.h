@@ -157,8 +157,9 @@ typedef struct B200pgIntegratorParams {
     int32_t volumetric;              /* 0 = progressivepath, 1 = progressivevolpath */
     /* guiding */
     int32_t guiding;                 /* 0 = off */
-    int32_t training_progressions;   /* number of passes that train the field (= field updates; on N devices a pass renders N
-                                      * sample blocks, one per device, and the update refits from all of them) */
+    int32_t training_progressions;   /* number of progressions that train the field. On N devices a pass renders N sample blocks
+                                      * and one update refits from all of them: under a sample budget ceil(n / N) passes train (the
+                                      * single-device number of training samples), under a time budget n passes (n updates) */
     float guiding_probability;       /* one-sample MIS selection probability (default .5) */
     int32_t guide_max_components;    /* K <= 32 */
     int32_t guide_max_cell_samples;  /* spatial split threshold */

@@ -147,11 +147,13 @@ static int worker(const Options &o, int rank, int world, int up, int down) {
     const int numPasses = std::max(1, (desc ? desc->sample_count : 4) / perPass);
     const int globalPasses = (numPasses + world - 1) / world;  // the sample count is rounded up to a multiple of world * perPass
     const bool timed = p.max_render_time > 0;
-    int trainPasses = p.guiding ? p.training_progressions : 0;
-    if (!timed) trainPasses = std::min(trainPasses, globalPasses);
+    // global passes that train the field: as b200pg_render counts them (integrator.cu: makePlan) -- the single-device number of
+    // training SAMPLES under a sample budget, training_progressions UPDATES under a time budget
+    const int T = p.guiding ? std::max(0, p.training_progressions) : 0;
+    const int trainPasses = timed ? T : std::min((T + world - 1) / world, globalPasses);
     const auto t0 = std::chrono::steady_clock::now();
     for (int g = 0; timed || g < globalPasses; ++g) {
-        const bool record = g < trainPasses;  // training_progressions = field updates (global passes), as b200pg_render counts them
+        const bool record = g < trainPasses;
         if (p.guiding) PG_CHECK(b200pg_guiding_mode(integ, record ? 1 : 0, 1), 3);
         PG_CHECK(b200pg_progression_render(integ, (g * world + rank) * perPass, perPass, 0, 0), 3);
         if (record) {

@@ -791,11 +791,15 @@ static PassPlan makePlan(const Integrator &I, int rank, int world) {
     P.timed = I.params.max_render_time > 0;
     P.limit = (double)I.params.max_render_time;
     // the sample budget trains at most as long as it renders; a time budget has no pass count to clamp against
-    // training_progressions counts field UPDATES = global passes: on N devices every update refits from N sample blocks. (Counting
-    // device passes instead -- the same number of training samples as a single-device run -- left an 8-GPU job with two updates
-    // of its 16, and the spatial tree, which splits one level per update, with 4 cells: guided == unguided at 4K, r2p.)
-    P.trainPasses = I.guide.active ? std::max(0, I.params.training_progressions) : 0;
-    if (!P.timed) P.trainPasses = std::min(P.trainPasses, P.numPasses);
+    // How many GLOBAL passes train the field (a global pass = `world` sample blocks, one per device).
+    //  * sample budget: ceil(training_progressions / world) -- the same number of training SAMPLES as a single-device run, so the
+    //    split of the budget between training and rendering (and with guide_train_discard_film the film's sample count) does not
+    //    depend on the device count;
+    //  * time budget: training_progressions -- there is no such split to preserve, and the field needs its UPDATES: the spatial
+    //    tree splits one level per update, and counting device passes here left an 8-GPU 4K job with two updates of its sixteen
+    //    and a 4-cell field (guided == unguided, gpurun_out/r2p_equal_time_c5_4k_8gpu.jsonl).
+    const int T = I.guide.active ? std::max(0, I.params.training_progressions) : 0;
+    P.trainPasses = P.timed ? T : std::min((T + P.world - 1) / P.world, P.numPasses);
     return P;
 }
 // global pass g of the plan on this integrator; `record` is the same on every rank
