@@ -311,6 +311,8 @@ void b200pg_destroy(void *integ);
  *            volumetric path, 2 = every bounce >= 1; default 1), "tail_visits" (node-visit budget of a ray before the
  *            warp-cooperative kernel finishes it; 0 = off, -1 = library default: 96 on scenes with >= 64 k BVH nodes),
  *            "splat_tile" (0/1: film accumulation through a per-warp shared-memory tile, default 1).
+ *            "split_levels" (1..16, default 1): spatial split levels per training update of the guiding field (one device);
+ *            this one changes the trained field, as the oracle's guideTrain(..., splitLevels) does.
  *   stage times: 5 doubles / 5 launch counts = trace(closest), shade, shadow(any-hit), film, train.
  *   scene_upload: re-sends the compiled scene host->device (bench.py's end-to-end leg). */
 int b200pg_set_option(void *integ, const char *name, int value);

@@ -264,6 +264,21 @@ __global__ void __launch_bounds__(256) k_fill_work(const uint32_t *__restrict__ 
     }
 }
 
+// Per-cell sums of the chunks' cell statistics (count, first / second position moments) into the cell slots of the stats buffer, for
+// a further split level: one warp per cell, lanes 0..7 = the eight slots, chunks in index order, double accumulators.
+__global__ void __launch_bounds__(256) k_cell_moments(const float *__restrict__ partials, const uint32_t *__restrict__ workOfs,
+                                                      uint32_t nCells, int K, int stride, float *__restrict__ stats) {
+    const uint32_t warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = (gridDim.x * blockDim.x) >> 5;
+    const int e = (int)lane();
+    for (uint32_t c = warpGlobal; c < nCells; c += nWarps) {
+        if (e >= 8) continue;
+        double acc = 0.0;
+        if (e != 1)  // slot 1 (sum of weights) belongs to the E-step, which does not run for a split level
+            for (uint32_t w = workOfs[c]; w < workOfs[c + 1]; ++w) acc += (double)partials[(size_t)w * stride + 4 * K + e];
+        stats[(size_t)c * stride + 4 * K + e] = (float)acc;
+    }
+}
+
 // Spatial refinement on the device (same rule and arithmetic as oracle_guiding.h guideSplit / the former host code):
 // fold this update's cell statistics into the running headers, split every cell whose running sample count exceeds the
 // threshold at the mean sample position along the axis of largest variance; cells are visited in index order, the
@@ -271,7 +286,10 @@ __global__ void __launch_bounds__(256) k_fill_work(const uint32_t *__restrict__ 
 // One block of 1024 threads. counts = {nCells, nNodes, nWork, -}.
 __global__ void __launch_bounds__(1024) k_split(uint4 *__restrict__ nodes, float4 *__restrict__ lobes, float4 *__restrict__ lobeStats,
                                                 float2 *__restrict__ cells, uint32_t *__restrict__ cellLeaf, const float *__restrict__ stats,
-                                                uint32_t *__restrict__ counts, int K, int stride, float maxCellSamples, uint32_t maxCells) {
+                                                uint32_t *__restrict__ counts, int K, int stride, float maxCellSamples, uint32_t maxCells,
+                                                int fold) {
+    // fold = 0: a further split level of the same update (GuidingHost::end): the headers already hold this update's samples, and
+    // `stats` carries only the cell slots (count, position moments) of the samples binned into the tree as it is now
     __shared__ uint32_t sm[33];
     const uint32_t nc0 = counts[0], nn0 = counts[1];
     const uint32_t per = (nc0 + 1023) / 1024;
@@ -280,9 +298,11 @@ __global__ void __launch_bounds__(1024) k_split(uint4 *__restrict__ nodes, float
     for (uint32_t c = c0; c < c1; ++c) {
         const float *cs = stats + (size_t)stride * c + (size_t)K * 4;
         float2 h = cells[c];
-        h.x = kGuideDecay * h.x + cs[0];
-        h.y = kGuideDecay * h.y + cs[1];
-        cells[c] = h;
+        if (fold) {
+            h.x = kGuideDecay * h.x + cs[0];
+            h.y = kGuideDecay * h.y + cs[1];
+            cells[c] = h;
+        }
         bool split = false;
         if (h.x > maxCellSamples && cs[0] >= 2) {
             double best = 0.0;
@@ -1237,11 +1257,30 @@ void GuidingHost::update(bool commit) {
 // Fold the update's cell statistics into the running headers and split over-full cells -- on the device; the host
 // only learns the new cell / node counts (8 bytes).
 void GuidingHost::end() {
+    const uint32_t cap = (uint32_t)std::min<size_t>(dCells.n, kCommMaxCells);
+    uint32_t before = nCells;
     k_split<<<1, 1024, 0, stream>>>(dNodes.p, dLobes.p, dLobeStats.p, dCells.p, dCellLeaf.p, dStats.p, dCounts.p,
-                                   K, (int)statsStride(), maxCellSamples, (uint32_t)std::min<size_t>(dCells.n, kCommMaxCells));
+                                   K, (int)statsStride(), maxCellSamples, cap, 1);
     launches++;
     uint32_t counts[2] = {0, 0};
     CUDA_OK(cudaMemcpyAsync(counts, dCounts.p, sizeof(counts), cudaMemcpyDeviceToHost, stream));
+    // Further split levels of the same update (oracle_guiding.h: guideTrain, splitLevels): bin the samples into the tree as it is
+    // now, and split every cell whose halved running count still exceeds the threshold at the mean of ITS samples. One device only:
+    // with connected peers every level would need its own cross-GPU sum of the cell moments.
+    for (int level = 1; level < splitLevels && commWorld <= 1 && nSamples > 0; ++level) {
+        CUDA_OK(cudaStreamSynchronize(stream));
+        if (counts[0] == before) break;  // nothing split at the previous level
+        before = nCells = counts[0];
+        nNodes = counts[1];
+        sortByCell(nSamples, false);
+        buildWork();  // chunk list + gather: leaves the chunks' position moments in the partials buffer
+        CUDA_OK(cudaMemsetAsync(dStats.p, 0, (size_t)nCells * statsStride() * sizeof(float), stream));
+        k_cell_moments<<<gridFor((size_t)nCells * 32, 256), 256, 0, stream>>>(dPartials.p, dWorkOfs.p, nCells, K, (int)statsStride(), dStats.p);
+        k_split<<<1, 1024, 0, stream>>>(dNodes.p, dLobes.p, dLobeStats.p, dCells.p, dCellLeaf.p, dStats.p, dCounts.p,
+                                       K, (int)statsStride(), maxCellSamples, cap, 0);
+        launches += 2;
+        CUDA_OK(cudaMemcpyAsync(counts, dCounts.p, sizeof(counts), cudaMemcpyDeviceToHost, stream));
+    }
     CUDA_OK(cudaMemsetAsync(dSCount.p, 0, sizeof(uint32_t), stream));
     keysValid = true;  // the sample buffer is empty: what is recorded from now on is looked up in the tree as it is now
     CUDA_OK(cudaStreamSynchronize(stream));

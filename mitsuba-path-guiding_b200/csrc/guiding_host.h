@@ -72,6 +72,7 @@ struct GuidingHost {
     // the stored keys are the binning keys as long as every sample in the buffer was recorded while sampling from the CURRENT tree
     // (false after a recording progression without sampling, a field load / reset; true again when the buffer is emptied)
     bool keysValid = false;
+    int splitLevels = 1;         // spatial split levels per training update (set_option "split_levels"; > 1 on one device only)
     DevBuf<uint32_t> dSCount;
     size_t vertCapacity = 0, sampleCapacity = 0;
 

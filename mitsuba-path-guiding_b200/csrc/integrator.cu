@@ -1326,6 +1326,7 @@ int b200pg_set_option(void *integ, const char *name, int value) {
     else if (n == "overlap_shadow") self->overlapShadow = value != 0;
     else if (n == "lanes") self->lanes = std::max(1, std::min((int)Integrator::kMaxLanes, value));
     else if (n == "partition") self->partitionMode = value;
+    else if (n == "split_levels") self->guide.splitLevels = std::max(1, std::min(16, value));
     else if (n == "splat_tile") self->splatTile = value != 0;
     else if (n == "tail_visits") self->tailVisits = value;
     else if (n == "lane_major") self->laneMajor = value != 0;

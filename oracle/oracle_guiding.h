@@ -332,8 +332,31 @@ inline void guideSplit(GuideField &F, const std::vector<float> &stats, Float max
     }
 }
 
+// Position statistics of this update's samples per cell of the CURRENT tree (the cell-statistics slots of a stats buffer: count and
+// the first / second position moments; the lobe slots stay zero): what a further split level needs after the tree has changed.
+inline void guideCellMoments(const GuideField &F, const GuideSamples &smp, std::vector<float> &stats) {
+    const size_t stride = (size_t)F.K * 4 + 8;
+    std::vector<uint32_t> cell, perm, offsets;
+    guideBin(F, smp.pos.data(), smp.size(), cell, perm, offsets);
+    std::vector<double> st(stride * F.numCells(), 0.0);
+    for (uint32_t c = 0; c < F.numCells(); ++c) {
+        double *cs = &st[stride * c + (size_t)F.K * 4];
+        for (uint32_t j = offsets[c]; j < offsets[c + 1]; ++j) {  // sorted order, as the E-step sums them
+            const Vec3 &p = smp.pos[perm[j]];
+            cs[0] += 1.0;
+            cs[2] += p.x; cs[3] += p.y; cs[4] += p.z;
+            cs[5] += (double)p.x * p.x; cs[6] += (double)p.y * p.y; cs[7] += (double)p.z * p.z;
+        }
+    }
+    stats.assign(st.begin(), st.end());
+}
+
 // One complete training update: bin, nIter x (E-step, M-step), commit, split.
-inline void guideTrain(GuideField &F, const GuideSamples &smp, int nIter, Float maxCellSamples) {
+// splitLevels > 1: after the regular split the samples are binned into the new tree and every cell whose (halved) running sample
+// count still exceeds the threshold splits again, at the mean of ITS samples -- up to splitLevels levels per update, so a field
+// that starts from one cell reaches its size in a few updates instead of one level per update. Children keep inheriting the parent's
+// mixture with half of its statistics; the mixtures themselves are refined by the next update.
+inline void guideTrain(GuideField &F, const GuideSamples &smp, int nIter, Float maxCellSamples, int splitLevels = 1) {
     std::vector<uint32_t> cell, perm, offsets;
     guideBin(F, smp.pos.data(), smp.size(), cell, perm, offsets);
     std::vector<double> statsD;
@@ -343,7 +366,13 @@ inline void guideTrain(GuideField &F, const GuideSamples &smp, int nIter, Float 
         stats.assign(statsD.begin(), statsD.end());
         guideMStep(F, stats, it == nIter - 1);
     }
+    uint32_t before = F.numCells();
     guideSplit(F, stats, maxCellSamples);
+    for (int level = 1; level < splitLevels && F.numCells() != before; ++level) {
+        before = F.numCells();
+        guideCellMoments(F, smp, stats);
+        guideSplit(F, stats, maxCellSamples);
+    }
 }
 
 }  // namespace orc

@@ -1406,6 +1406,15 @@ int orc_train_sink(void *f, void *sink, int nIter, float maxCellSamples) {
     guideTrain(*(GuideField *)f, *(GuideSamples *)sink, nIter, maxCellSamples);
     return 0;
 }
+// the same update with several split levels (oracle_guiding.h: guideTrain, splitLevels)
+int orc_train_levels(void *f, const float *pos, const float *dir, const float *weight, const float *pdf, const float *dist, size_t n,
+                     int nIter, float maxCellSamples, int splitLevels) {
+    GuideField *F = (GuideField *)f;
+    GuideSamples S;
+    fillSamples(S, pos, dir, weight, pdf, dist, n);
+    guideTrain(*F, S, nIter, maxCellSamples, splitLevels);
+    return 0;
+}
 void *orc_samples_create(void) { return new GuideSamples(); }
 void orc_samples_destroy(void *h) { delete (GuideSamples *)h; }
 size_t orc_samples_size(void *h) { return ((GuideSamples *)h)->size(); }

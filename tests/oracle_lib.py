@@ -59,6 +59,7 @@ class Oracle:
         L.orc_estep.argtypes = [C.c_void_p, fp, fp, fp, fp, fp, C.c_size_t, fp]
         L.orc_train.argtypes = [C.c_void_p, fp, fp, fp, fp, fp, C.c_size_t, C.c_int, C.c_float]
         L.orc_train_sink.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float]
+        L.orc_train_levels.argtypes = [C.c_void_p, fp, fp, fp, fp, fp, C.c_size_t, C.c_int, C.c_float, C.c_int]
         L.orc_samples_create.restype = C.c_void_p
         L.orc_samples_destroy.argtypes = [C.c_void_p]
         L.orc_samples_size.restype = C.c_size_t
@@ -199,9 +200,12 @@ class OracleField:
     def train_sink(self, sink, n_iter=4, max_cell_samples=32768):
         self.L.orc_train_sink(self.h, sink.h, n_iter, max_cell_samples)
 
-    def train(self, s, n_iter=4, max_cell_samples=32768):
+    def train(self, s, n_iter=4, max_cell_samples=32768, split_levels=1):
         a, n = self._args(s)
-        self.L.orc_train(self.h, *[_f(x) for x in a], n, n_iter, max_cell_samples)
+        if split_levels > 1:
+            self.L.orc_train_levels(self.h, *[_f(x) for x in a], n, n_iter, max_cell_samples, split_levels)
+        else:
+            self.L.orc_train(self.h, *[_f(x) for x in a], n, n_iter, max_cell_samples)
 
 
 class OracleScene:

@@ -393,3 +393,41 @@ def test_large_field_beyond_16k_cells(pkg, api, oracle):
     it.guiding_mode(False, False)
     plain = it.k_radiance(pix, smp)
     assert np.isfinite(got).all() and abs(got.mean() - plain.mean()) < 0.05 * plain.mean()
+
+
+def test_multi_level_split_matches_oracle(pkg, api, oracle):
+    """set_option("split_levels", n): one training update splits a cell level by level until its halved running sample count is
+    below the threshold (oracle_guiding.h: guideTrain, splitLevels). Same starting field and samples on both sides: identical tree
+    topology, split planes within 1e-5, headers halved alike -- and the tree reaches in ONE update what takes six otherwise."""
+    sb = pkg.scenes.cornell_caustic(64, 64, spp=4)
+    p = api.default_params()
+    p.max_depth, p.guiding, p.guide_max_components, p.guide_max_cell_samples = 8, 1, 8, 1000
+    it = api.Integrator(api.Scene.from_builder(sb), p)
+    fld = oracle.field(8, (0, 0, 0), (1, 1, 1))
+    it.field_load(fld.snapshot())
+    rng = np.random.RandomState(41)
+    n = 50000
+    s = dict(pos=(rng.rand(n, 3) * [2.0, 1.0, 0.5] - [1.0, 0.0, 0.25]).astype(np.float32), dir=random_dirs(rng, n),
+             weight=rng.rand(n).astype(np.float32) + 0.1, pdf=np.ones(n, np.float32), dist=np.ones(n, np.float32))
+    fld.train(s, 2, 1000.0, split_levels=8)
+    it.set_option("split_levels", 8)
+    it.k_em_step(s, 2, 1, 8)
+    a, g = fld.snapshot(), it.field_snapshot()
+    assert np.array_equal(a[:8], g[:8])
+    nn, nc = int(a[1]), int(a[2])
+    assert nc == 64 and nn == 127
+    na, ng = a[8:8 + 4 * nn].reshape(nn, 4), g[8:8 + 4 * nn].reshape(nn, 4)
+    assert np.array_equal(na[:, [0, 2, 3]], ng[:, [0, 2, 3]])                               # topology: bit-exact
+    np.testing.assert_allclose(na[:, 1].view(np.float32), ng[:, 1].view(np.float32), rtol=1e-5, atol=1e-6)
+    ha = a[8 + 4 * nn: 8 + 4 * nn + 8 * nc].view(np.float32).reshape(nc, 8)
+    hg = g[8 + 4 * nn: 8 + 4 * nn + 8 * nc].view(np.float32).reshape(nc, 8)
+    np.testing.assert_allclose(ha[:, :2], hg[:, :2], rtol=1e-5)
+    # binning in the grown tree agrees (a sample within an ulp of a plane may fall on the other side)
+    co, po, oo = fld.bin(s["pos"])
+    cg, pg_, og = it.k_bin_samples(s["pos"], nc)
+    assert (co != cg).sum() <= 5
+    # one level per update (the default) needs six updates for the same size
+    it1 = api.Integrator(api.Scene.from_builder(sb), p)
+    it1.field_load(oracle.field(8, (0, 0, 0), (1, 1, 1)).snapshot())
+    it1.k_em_step(s, 2, 1, 8)
+    assert int(it1.field_snapshot()[2]) == 2

@@ -112,6 +112,34 @@ def test_binning_is_stable_and_split_rule(oracle):
     assert np.array_equal(before[8 + 4 * fld.info()["nodes"] + 8 * nc:].view(np.float32)[0::12], after[8 + 4 * fld.info()["nodes"] + 8 * nc:].view(np.float32)[0::12])
 
 
+def test_multi_level_split_reaches_the_size_in_one_update(oracle):
+    """splitLevels > 1: one update splits a cell as often as its (halved) running sample count exceeds the threshold, each level at
+    the mean of the samples that fall into the cell being split. 50 000 samples against a threshold of 1000: one level gives 2 cells,
+    six levels give 64 cells of ~780 samples; with one level per update the same tree needs six updates' worth of splits."""
+    rng = np.random.RandomState(5)
+    s = _planted(rng, 50000)
+    s["pos"] = rng.rand(50000, 3).astype(np.float32)
+    one = oracle.field(4, (0, 0, 0), (1, 1, 1))
+    one.train(s, n_iter=2, max_cell_samples=1000)
+    assert one.info()["cells"] == 2
+    many = oracle.field(4, (0, 0, 0), (1, 1, 1))
+    many.train(s, n_iter=2, max_cell_samples=1000, split_levels=8)
+    info = many.info()
+    assert info["cells"] == 64 and info["nodes"] == 127       # 50 000 / 2^6 = 781 <= 1000 < 50 000 / 2^5
+    cell, perm, off = many.bin(s["pos"])
+    counts = np.diff(off)
+    assert counts.min() > 500 and counts.max() < 1100          # splits at the sample mean: balanced cells
+    # the first level is the one-level split: same root plane
+    assert np.array_equal(one.snapshot()[8:12][:2], many.snapshot()[8:12][:2])
+    # every cell still holds the (inherited) normalised mixture, and the headers were halved level by level
+    nc = info["cells"]
+    words = many.snapshot()
+    hdr = words[8 + 4 * info["nodes"]: 8 + 4 * info["nodes"] + 8 * nc].view(np.float32).reshape(nc, 8)
+    lob = words[8 + 4 * info["nodes"] + 8 * nc:].view(np.float32).reshape(nc, 4, 12)
+    assert np.allclose(lob[:, :, 0].sum(1), 1, atol=1e-5)
+    assert np.allclose(hdr[:, 0], 50000 / 64, rtol=1e-5)
+
+
 def test_estep_is_linear_in_sample_shards(oracle):
     """The sufficient statistics of disjoint sample shards add up (what the NCCL allreduce relies on)."""
     rng = np.random.RandomState(2)

@@ -56,6 +56,8 @@ def main():
     ap.add_argument("--ref-spp", type=int, default=0, help="0 = the oracle fixture (512^2 only); > 0 = unguided GPU render with that many spp")
     ap.add_argument("--cpu", action="store_true", help="also run the CPU arm (oracle, all host cores) at the same budgets")
     ap.add_argument("--train-passes", type=int, default=16)
+    ap.add_argument("--split-levels", default="1", help="comma list: spatial split levels per training update (set_option split_levels); "
+                                                        "the first entry is the `guided` arm, further ones are reported as guided_levels<n>")
     args = ap.parse_args()
     W, H = (int(x) for x in args.size.split("x")) if "x" in args.size else (int(args.size), int(args.size))
     budgets = [float(x) for x in args.budgets.split(",")]
@@ -100,13 +102,15 @@ def main():
     sbt = make(W, H, spp=64)
     sbt.seed = sb.seed + seed_shift  # disjoint from a GPU-rendered reference (sample streams are keyed by the seed)
 
-    def gpu_arm(T, guided):
+    def gpu_arm(T, guided, levels=1):
         sc = api.Scene.from_builder(sbt)
         it = api.Integrator(sc, params(guided, T, 4, args.train_passes))
         it.progression(0, 1)  # warm the allocations outside the budget, then start from an empty film / field
         it.film_clear()
         it.close()
         it = api.Integrator(sc, params(guided, T, 4, args.train_passes))
+        if guided and levels > 1:
+            it.set_option("split_levels", levels)
         t0 = time.perf_counter()
         it.render(devices=devices if len(devices) > 1 else None)
         el = time.perf_counter() - t0
@@ -150,8 +154,12 @@ def main():
                 "cores": cores}
 
     for T in budgets:
+        levels = [int(x) for x in args.split_levels.split(",")]
         out = {"scene": args.scene, "size": "%dx%d" % (W, H), "budget_s": T, "gpus": args.gpus, "reference": ref_desc,
-               "guided": gpu_arm(T, True), "unguided": gpu_arm(T, False)}
+               "guided": gpu_arm(T, True, levels[0]), "unguided": gpu_arm(T, False)}
+        out["guided"]["split_levels"] = levels[0]
+        for lv in levels[1:]:
+            out["guided_levels%d" % lv] = gpu_arm(T, True, lv)
         out["reference_noise"] = floor
         out["relMSE_ratio_unguided_over_guided"] = out["unguided"]["relMSE"] / out["guided"]["relMSE"]
         if out["guided"]["relMSE_debiased"] > 0:
