@@ -119,7 +119,7 @@ PG_DEV float3 guideSample(const GuideDevice &G, uint32_t cell, float u0, float u
 // A per-thread loop over the K lobes of the lane's own cell issues 2K scattered 16-byte loads per lane, and every such
 // warp instruction touches up to 32 different cache lines: the L1TEX data pipe takes about one line per cycle, and ncu showed
 // it 72-77 % busy on the guided bounces of k_shade with ~60 % of its wavefronts coming from these loads
-// (gpurun_out/prof_shade_v5: l1tex__data_pipe_lsu_wavefronts; the kernel was L1-wavefront-bound, not DRAM-bound).
+// (profiles/r02_shade_coop_summary.txt, r02_shade_final_summary.txt: l1tex__data_pipe_lsu_wavefronts; L1-wavefront-bound, not DRAM-bound).
 // Here the warp serves its lanes one path at a time: lane k fetches lobe k of THAT path's cell, so a load instruction covers
 // 16 lanes x 32 B = 4 lines; K <= 16 uses the two half-warps for the two directions of a pdf query (or for two paths of a
 // lobe selection), K <= 32 one lobe per lane. Idle lanes of a divergent warp (finished, parked or unguided paths) help.

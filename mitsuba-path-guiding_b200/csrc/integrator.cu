@@ -797,7 +797,7 @@ static PassPlan makePlan(const Integrator &I, int rank, int world) {
     //    depend on the device count;
     //  * time budget: training_progressions -- there is no such split to preserve, and the field needs its UPDATES: the spatial
     //    tree splits one level per update, and counting device passes here left an 8-GPU 4K job with two updates of its sixteen
-    //    and a 4-cell field (guided == unguided, gpurun_out/r2p_equal_time_c5_4k_8gpu.jsonl).
+    //    and a 4-cell field (guided == unguided, profiles/r02_equal_time_c5_4k_8gpu_before_schedule_fix.jsonl).
     const int T = I.guide.active ? std::max(0, I.params.training_progressions) : 0;
     P.trainPasses = P.timed ? T : std::min((T + P.world - 1) / P.world, P.numPasses);
     return P;
