@@ -7,7 +7,8 @@ lights) with n = 317 -> 199 712 triangles, CUDA path against the oracle.
     random chords through the bounding sphere of a mesh, closest- and any-hit), checked against the oracle's kd-tree;
   * per-sample radiance through the mesh materials, sample by sample;
   * ray / path counters of a whole progression against the oracle's render of the same samples.
-The 10 M-triangle scene itself (BASELINE config 3) runs in bench.py's `workloads` block and tests/test_gpu_fullsize.py.
+The 10 M-triangle scene itself (BASELINE config 3) runs in bench.py's `workloads` block and, through size-independent properties, in
+test_full_size_c4_properties below.
 """
 import numpy as np
 import pytest
@@ -219,3 +220,82 @@ def test_mesh_hits_wide_tree(pkg, api, oracle, monkeypatch):
         it.progression(0, 2)
         imgs.append(it.develop())
     assert np.abs(imgs[0] - imgs[1]).sum() / np.abs(imgs[0]).sum() < 1e-3
+
+
+def _terrain_height(x, z, seed=1337, amp=0.05):
+    """The analytic surface scenes.heightfield_mesh samples (same seeded sum of six sines), in float64."""
+    rng = np.random.RandomState(seed)
+    y = np.zeros_like(x, dtype=np.float64)
+    for _ in range(6):
+        fx, fz = rng.uniform(2, 14, 2)
+        ph = rng.uniform(0, 2 * np.pi)
+        a = rng.uniform(0.3, 1.0)
+        y += a * np.sin(fx * x + fz * z + ph)
+    return y * amp / 3.0
+
+
+def test_full_size_c4_properties(pkg, api):
+    """BASELINE config C4 at full size -- 10.0 M triangles, 2048 x 2048 -- through properties that do not need the oracle (its kd-tree
+    build alone takes 46 s): closest hits lie on the ANALYTIC terrain the mesh samples (within the linear-interpolation error of a
+    0.9 mm grid), any-hit and closest-hit queries agree on which chords are blocked, a sample's radiance does not depend on the
+    traversal / shading schedule (hit / miss partition bit for bit, visit budget + warp-cooperative kernel up to exact-t ties), and
+    a progression deposits every camera sample in the film."""
+    sb = pkg.scenes.mesh_scene(2048, 2048)
+    p = api.default_params()
+    p.max_depth = 8
+    it = api.Integrator(api.Scene.from_builder(sb), p)
+    rng = np.random.RandomState(43)
+    n = 300000
+    chords = _sphere_chords(rng, n, np.array([0.0, 0.0, 0.0]), 1.5)
+    # a third of the set skims the sheet: long traversals, the visit budget and the cooperative kernel at work
+    k = n // 3
+    phi = rng.rand(k) * 2 * np.pi
+    o = np.stack([1.6 * np.cos(phi), rng.uniform(-0.04, 0.06, k), 1.6 * np.sin(phi)], 1)
+    tgt = np.stack([rng.uniform(-0.9, 0.9, k), rng.uniform(-0.05, 0.05, k), rng.uniform(-0.9, 0.9, k)], 1)
+    d = tgt - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    chords[:k] = np.concatenate([o, np.zeros((k, 1)), d, np.full((k, 1), 10.0)], 1).astype(np.float32)
+    tuv, prim = it.k_trace(chords)
+    hit = prim != 0xFFFFFFFF
+    assert 0.1 < hit.mean() < 0.95
+    pt = chords[:, 0:3].astype(np.float64) + tuv[:, 0:1].astype(np.float64) * chords[:, 4:7].astype(np.float64)
+    on_sheet = hit & (np.abs(pt[:, 1]) < 0.2)          # the two lights hang at y = 0.9
+    assert on_sheet.sum() > 0.9 * hit.sum()
+    dy = np.abs(pt[on_sheet, 1] - _terrain_height(pt[on_sheet, 0], pt[on_sheet, 2]))
+    # vertical distance to the analytic surface: facet interpolation error <= ~1e-6 plus the ray parameter's rounding, which a
+    # grazing ray turns into height error ~ 1e-6 * slope of approach -- bound the bulk tightly and the grazing tail loosely
+    assert np.quantile(dy, 0.99) <= 1e-5 and dy.max() <= 2e-4, (np.quantile(dy, 0.99), dy.max())
+    assert np.abs(pt[on_sheet][:, [0, 2]]).max() <= 1.0 + 1e-5
+    _, occ = it.k_trace(chords, shadow=True)
+    assert ((occ != 0xFFFFFFFF) != hit).sum() <= int(2e-4 * n)
+    # the same queries with the visit budget off: identical up to exact-t ties on shared edges
+    try:
+        it.set_option("tail_visits", 0)
+        tuv0, prim0 = it.k_trace(chords)
+    finally:
+        it.set_option("tail_visits", -1)
+    assert (prim0 != prim).sum() <= int(2e-4 * n)
+    same = (prim0 == prim) & hit
+    assert np.abs(tuv0[same, 0] - tuv[same, 0]).max() <= 1e-5
+    # radiance per sample under different schedules
+    pix = rng.randint(0, sb.width * sb.height, 100000).astype(np.uint32)
+    smp = rng.randint(0, 16, 100000).astype(np.uint32)
+    try:
+        it.set_option("partition", 0)
+        base = it.k_radiance(pix, smp)
+        it.set_option("partition", 2)
+        assert np.array_equal(base, it.k_radiance(pix, smp))
+    finally:
+        it.set_option("partition", 1)
+    assert np.isfinite(base).all() and (base >= 0).all() and (base.max(1) > 0).mean() > 0.1
+    # two progressions (the second one takes the adaptive partition): every camera sample ends up in the film
+    it.film_clear()
+    s0 = it.stats()
+    it.progression(0, 1)
+    it.progression(1, 1)
+    s1 = it.stats()
+    f = it.film()
+    assert s1["paths"] - s0["paths"] == 2 * 2048 * 2048
+    assert np.isfinite(f).all() and (f >= 0).all()
+    assert 0.97 <= f[..., 4].sum() / (2 * 2048 * 2048) <= 1.0001
+    it.close()
