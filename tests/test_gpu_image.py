@@ -1,7 +1,7 @@
 """Image-level parity at a BASELINE size (north star: "the converged render must match the reference's converged render within a
 stated relMSE tolerance"): config C1, Cornell box 512 x 512, maxDepth 8.
 
-Reference = the ORACLE's converged render, 16 384 spp (tests/golden/ref_c1.npz, written once by tools/make_reference.py; the
+Reference = the ORACLE's converged render, 16 384 spp (tests/golden/ref_c1.npz, written once by tests/golden/make_reference.py; the
 reference binary cannot be built). relMSE = mean over pixels of (I - R)^2 / (R^2 + 1e-3) on developed linear RGB
 with the 0.1 % highest-error pixels discarded.
 
