@@ -12,6 +12,21 @@
 
 namespace {
 struct SceneHandle { pg::HostScene host; };
+// the library keeps the primitive record split (plane row / (u, v) rows, one per slot: host_scene.h); the replay below walks the
+// 48-byte form
+static const pg::PrimRecord *primRecords(const pg::HostScene &H) {
+    static std::vector<pg::PrimRecord> recs;
+    static const pg::HostScene *built = nullptr;
+    if (built != &H) {
+        recs.resize(H.primGlobalId.size());
+        for (size_t i = 0; i < recs.size(); ++i) {
+            for (int k = 0; k < 8; ++k) recs[i].q[k] = H.primRows[i * 8 + k];
+            for (int k = 0; k < 4; ++k) recs[i].q[8 + k] = H.primPlanes[i * 4 + k];
+        }
+        built = &H;
+    }
+    return recs.data();
+}
 const int kDone = (int)0x80000000;
 
 struct RayState {
@@ -161,7 +176,7 @@ void bvhsim_trace(void *h, const float *rays, size_t n, int anyHit, int cull, ui
         while (!R.done()) {
             while (R.node >= 0) R.step(H.nodes.data());
             if (R.done()) break;
-            R.leaf(H.prims.data());
+            R.leaf(primRecords(H));
         }
         if (nodeSteps) nodeSteps[i] = R.nodeSteps;
         if (primTests) primTests[i] = R.primTests;
@@ -195,7 +210,7 @@ void bvhsim_warps(void *h, const float *rays, size_t n, int anyHit, int cull, in
                     while (R[l].node >= 0) { R[l].step(H.nodes.data()); s++; }
                     laneNode += s;
                     maxSteps = std::max(maxSteps, s);
-                    if (!R[l].done()) { int p = R[l].leaf(H.prims.data()); lanePrim += p; maxPrims = std::max(maxPrims, p); }
+                    if (!R[l].done()) { int p = R[l].leaf(primRecords(H)); lanePrim += p; maxPrims = std::max(maxPrims, p); }
                 }
                 if (!active) break;
                 warpNode += maxSteps; warpPrim += maxPrims; rounds++;
@@ -229,7 +244,7 @@ void bvhsim_warps(void *h, const float *rays, size_t n, int anyHit, int cull, in
                         int s = 0;
                         while (L[l].node >= 0) { L[l].step(H.nodes.data()); s++; }
                         laneNode += s; maxSteps = std::max(maxSteps, s);
-                        if (!L[l].done()) { int p = L[l].leaf(H.prims.data()); lanePrim += p; maxPrims = std::max(maxPrims, p); }
+                        if (!L[l].done()) { int p = L[l].leaf(primRecords(H)); lanePrim += p; maxPrims = std::max(maxPrims, p); }
                         if (L[l].done()) { hs[l] = 0; maxRay = std::max<double>(maxRay, L[l].nodeSteps); }
                     }
                 } else {
@@ -263,7 +278,7 @@ void bvhsim_warps(void *h, const float *rays, size_t n, int anyHit, int cull, in
                             int save = L[l].node; L[l].node = lf;
                             // leaf() pops on its own: emulate by pushing back the saved continuation
                             if (save != kDone) { L[l].stack[L[l].sp] = save; L[l].stackT[L[l].sp] = -1e30f; L[l].sp++; }
-                            int p = L[l].leaf(H.prims.data());
+                            int p = L[l].leaf(primRecords(H));
                             lanePrim += p; mp = std::max(mp, p);
                         }
                         maxPrims += mp;
@@ -324,7 +339,7 @@ void bvhsim_warps(void *h, const float *rays, size_t n, int anyHit, int cull, in
                         qn[l]--;
                         int save = L[l].node; L[l].node = lf;
                         if (save != kDone) { L[l].stack[L[l].sp] = save; L[l].stackT[L[l].sp] = -1e30f; L[l].sp++; }
-                        int p = L[l].leaf(H.prims.data());
+                        int p = L[l].leaf(primRecords(H));
                         if (anyHit && L[l].prim != 0xFFFFFFFFu) { L[l].node = kDone; qn[l] = 0; }
                         lanePrim += p; mp = std::max(mp, p);
                         // a leaf the lane was stalled on
@@ -383,7 +398,7 @@ void bvhsim_warps(void *h, const float *rays, size_t n, int anyHit, int cull, in
                         qn[l]--;
                         int save = L[l].node; L[l].node = lf;
                         if (save != kDone) { L[l].stack[L[l].sp] = save; L[l].stackT[L[l].sp] = -1e30f; L[l].sp++; }
-                        int p = L[l].leaf(H.prims.data());
+                        int p = L[l].leaf(primRecords(H));
                         if (anyHit && L[l].prim != 0xFFFFFFFFu) { L[l].node = kDone; qn[l] = 0; }
                         lanePrim += p; mp = std::max(mp, p);
                         while (L[l].node < 0 && L[l].node != kDone && qn[l] < cap) { q[l * cap + qn[l]++] = L[l].node; L[l].node = L[l].pop(); }
@@ -428,7 +443,7 @@ int bvhsim_trace_wide(void *h, const float *rays, size_t n, uint32_t *nodeSteps,
         while (R.node != kDone) {
             while (R.node >= 0) R.step(H.wideNodes.data());
             if (R.node == kDone) break;
-            R.leaf(H.prims.data());
+            R.leaf(primRecords(H));
         }
         if (nodeSteps) nodeSteps[i] = R.nodeSteps;
         if (primTests) primTests[i] = R.primTests;
