@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "../../mitsuba-path-guiding_b200/csrc/host_scene.h"
@@ -17,6 +18,8 @@ struct SceneHandle { pg::HostScene host; };
 static const pg::PrimRecord *primRecords(const pg::HostScene &H) {
     static std::vector<pg::PrimRecord> recs;
     static const pg::HostScene *built = nullptr;
+    static std::mutex lock;  // called from inside OpenMP loops
+    std::lock_guard<std::mutex> guard(lock);
     if (built != &H) {
         recs.resize(H.primGlobalId.size());
         for (size_t i = 0; i < recs.size(); ++i) {
@@ -183,6 +186,66 @@ void bvhsim_trace(void *h, const float *rays, size_t n, int anyHit, int cull, ui
         if (leaves) leaves[i] = R.leaves;
         if (tOut) tOut[i] = R.prim == 0xFFFFFFFFu ? INFINITY : R.t;
         if (primOut) primOut[i] = R.prim;
+    }
+}
+
+// Model of the warp-cooperative kernel (kernels.cu: k_trace_tail): ONE ray served by 32 lanes from the root. Per round every lane
+// pops one pending entry (up to 32; one above `wide` entries, the depth-first fallback), tests that node's two children or that
+// leaf's primitives against the hit distance of the PREVIOUS round, and pushes what the ray enters. Reports per ray the number of
+// rounds (= dependent memory round trips, against nodeSteps + leaves of the sequential walk), the node tests (work, against
+// nodeSteps) and the largest stack. The hit must equal the sequential one (asserted by the caller on tOut / primOut).
+void bvhsim_coop(void *h, const float *rays, size_t n, int anyHit, int wide, uint32_t *rounds, uint32_t *nodeTests, uint32_t *maxStack,
+                 float *tOut, uint32_t *primOut) {
+    const pg::HostScene &H = ((SceneHandle *)h)->host;
+    const pg::PrimRecord *prims = primRecords(H);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (size_t i = 0; i < n; ++i) {
+        RayState R;  // used for its node / leaf arithmetic only
+        R.init(rays + 8 * i, anyHit != 0, false);
+        std::vector<int> st;
+        st.push_back(0);
+        uint32_t nr = 0, nt = 0, ms = 1;
+        float tmax = R.tmax, bestT = R.tmax;
+        uint32_t bestPrim = 0xFFFFFFFFu;
+        bool found = false;
+        while (!st.empty() && !found) {
+            const int take = (int)st.size() > wide ? 1 : std::min<int>((int)st.size(), 32);
+            int entry[32];
+            for (int l = 0; l < take; ++l) { entry[l] = st.back(); st.pop_back(); }
+            std::vector<int> farC, nearC;
+            float roundT = tmax;
+            uint32_t roundPrim = bestPrim;
+            for (int l = 0; l < take; ++l) {
+                RayState L = R;
+                L.tmax = tmax;  // every lane of the round prunes with the previous round's distance
+                L.sp = 0;
+                if (entry[l] >= 0) {
+                    nt++;
+                    L.node = entry[l];
+                    L.step(H.nodes.data());  // leaves: node = nearer child, stack[0] = farther one (if both are entered)
+                    if (L.sp == 1) farC.push_back(L.stack[0]);
+                    if (L.node != kDone) nearC.push_back(L.node);
+                } else {
+                    L.node = entry[l];
+                    L.prim = 0xFFFFFFFFu;
+                    L.leaf(prims);
+                    if (L.prim != 0xFFFFFFFFu) {
+                        if (anyHit) { found = true; roundPrim = L.prim; }
+                        else if (L.t < roundT || (L.t == roundT && L.prim < roundPrim)) { roundT = L.t; roundPrim = L.prim; }
+                    }
+                }
+            }
+            for (int c : farC) st.push_back(c);
+            for (size_t k = nearC.size(); k-- > 0;) st.push_back(nearC[k]);
+            if (roundPrim != bestPrim) { bestPrim = roundPrim; bestT = roundT; tmax = roundT; }
+            ms = std::max<uint32_t>(ms, (uint32_t)st.size());
+            nr++;
+        }
+        if (rounds) rounds[i] = nr;
+        if (nodeTests) nodeTests[i] = nt;
+        if (maxStack) maxStack[i] = ms;
+        if (tOut) tOut[i] = bestPrim == 0xFFFFFFFFu ? INFINITY : bestT;
+        if (primOut) primOut[i] = bestPrim;
     }
 }
 
