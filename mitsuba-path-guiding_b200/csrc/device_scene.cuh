@@ -294,7 +294,7 @@ PG_DEV void fillIntersection(const DeviceScene &S, float3 o, float3 d, const Hit
     const uint32_t flags = __float_as_uint(r1.w);
     its.shape = (int)__float_as_uint(r0.w);
     its.bsdf = (int)__float_as_uint(r3.w);
-    its.emitter = (int)__float_as_uint(r4.w);
+    its.emitter = (int)(flags >> 8) - 1;
     its.primIndex = __float_as_uint(r2.w);
     its.t = h.t;
     float3 dpdu, shN;
@@ -306,7 +306,8 @@ PG_DEV void fillIntersection(const DeviceScene &S, float3 o, float3 d, const Hit
         float3 faceNormal = cross(side1, side2);
         float len = length(faceNormal);
         if (!isZero(faceNormal)) faceNormal = faceNormal / len;
-        dpdu = side1;
+        // the UV tangent of meshes with texture coordinates (trimesh.cpp:683-735), else the first edge (skdtree.h:374-381)
+        dpdu = (flags & 4u) ? side1 * r4.w + side2 * t45.b.w : side1;
         if (flags & 2u) {
             const float4 r5 = t45.b;
             const float3 n0 = f3(r3.x, r3.y, r3.z), n1 = f3(r4.x, r4.y, r4.z), n2 = f3(r5.x, r5.y, r5.z);

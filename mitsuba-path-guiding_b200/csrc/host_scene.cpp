@@ -672,6 +672,7 @@ bool HostScene::compile(std::string &err) {
             mr.cdfOffset = (uint32_t)areaCdf.size();
             mr.nTriangles = s.n_triangles;
             mr.hasNormals = s.normals ? 1 : 0;
+            mr.hasTexcoords = s.texcoords ? 1 : 0;
             positions.insert(positions.end(), s.positions, s.positions + 3 * (size_t)s.n_vertices);
             if (s.normals)
                 normals.insert(normals.end(), s.normals, s.normals + 3 * (size_t)s.n_vertices);
@@ -1033,13 +1034,56 @@ bool HostScene::compile(std::string &err) {
                         q[12 + 4 * v + a] = mr.hasNormals ? normals[3 * vi + a] : 0.0f;
                     }
                 }
+                q[19] = 1.0f;  // dpdu = first edge (skdtree.h:378-380) ...
+                q[23] = 0.0f;
+                if (mr.hasTexcoords) {  // ... or the UV tangent, TriMesh::computeUVTangents (trimesh.cpp:701-735)
+                    const float *uv0 = &texcoords[2 * ((size_t)idx[0] + mr.vertexOffset)], *uv1 = &texcoords[2 * ((size_t)idx[1] + mr.vertexOffset)],
+                                *uv2 = &texcoords[2 * ((size_t)idx[2] + mr.vertexOffset)];
+                    const V3 dP1 = v3(q[4] - q[0], q[5] - q[1], q[6] - q[2]), dP2 = v3(q[8] - q[0], q[9] - q[1], q[10] - q[2]);
+                    const float dU1x = uv1[0] - uv0[0], dU1y = uv1[1] - uv0[1], dU2x = uv2[0] - uv0[0], dU2y = uv2[1] - uv0[1];
+                    const V3 n = cross(dP1, dP2);
+                    const float nl = len(n);
+                    if (nl != 0) {  // degenerate triangles are never hit
+                        const float determinant = dU1x * dU2y - dU1y * dU2x;
+                        if (determinant == 0) {
+                            // degenerate parameterisation: coordinateSystem(n / |n|) picks the tangent (util.cpp); it lies in the
+                            // triangle's plane, so it has coefficients in the (dP1, dP2) basis (normal equations, in double)
+                            const V3 nn = v3(n.x / nl, n.y / nl, n.z / nl);
+                            V3 tg;
+                            if (std::fabs(nn.x) > std::fabs(nn.y)) {
+                                const float invLen = 1.0f / std::sqrt(nn.x * nn.x + nn.z * nn.z);
+                                tg = v3(nn.z * invLen, 0.0f, -nn.x * invLen);  // c, then b = cross(c, a)
+                            } else {
+                                const float invLen = 1.0f / std::sqrt(nn.y * nn.y + nn.z * nn.z);
+                                tg = v3(0.0f, nn.z * invLen, -nn.y * invLen);
+                            }
+                            tg = cross(tg, nn);
+                            const double g11 = dot(dP1, dP1), g12 = dot(dP1, dP2), g22 = dot(dP2, dP2), r1 = dot(tg, dP1), r2 = dot(tg, dP2);
+                            const double det = g11 * g22 - g12 * g12;
+                            if (det != 0) {
+                                q[19] = (float)((r1 * g22 - r2 * g12) / det);
+                                q[23] = (float)((r2 * g11 - r1 * g12) / det);
+                            }
+                        } else {
+                            const float invDet = 1.0f / determinant;
+                            q[19] = dU2y * invDet;
+                            q[23] = -dU1y * invDet;
+                        }
+                        flags |= 4u;
+                    }
+                }
             }
+            if (sr.emitter >= (1 << 24) - 1) {
+#pragma omp critical
+                err = "more than 16M emitters are not supported by the shading record";
+            }
+            flags |= (uint32_t)(sr.emitter + 1) << 8;
             q[3] = u2f(pi.shape);
             q[7] = u2f(flags);
             q[11] = u2f(pi.prim);
             q[15] = u2f((uint32_t)sr.bsdf);
-            q[19] = u2f((uint32_t)sr.emitter);
         }
+        if (!err.empty()) return false;
     }
 
     // ---- camera (perspective.cpp:126-155, no crop window)

@@ -48,9 +48,12 @@ struct PrimRecord {
 // primitive slot). Everything fillIntersection needs about a triangle sits in ONE place: the previous chain
 // PrimInfo -> ShapeRecord -> MeshRecord -> indices -> positions / normals was five dependent, scattered loads deep and
 // touched ~9 sectors per hit on the 10 M-triangle mesh.
-//   r0 = p0.xyz, shape index       r1 = p1.xyz, flags (bit 0: triangle, bit 1: has vertex normals)
-//   r2 = p2.xyz, primitive index   r3 = n0.xyz, bsdf index   r4 = n1.xyz, emitter index   r5 = n2.xyz, 0
-// Rectangles keep only the .w words (their frame lives in RectRecord).
+//   r0 = p0.xyz, shape index       r1 = p1.xyz, flags (bit 0: triangle, bit 1: has vertex normals, bit 2: has a UV tangent,
+//                                                      bits 8..31: emitter index + 1, 0 = none)
+//   r2 = p2.xyz, primitive index   r3 = n0.xyz, bsdf index   r4 = n1.xyz, a   r5 = n2.xyz, b
+// (a, b): the triangle's UV tangent dpdu = a (p1 - p0) + b (p2 - p0) of TriMesh::computeUVTangents (trimesh.cpp:683-735), which
+// fillIntersectionRecord uses instead of the first edge whenever the mesh has texture coordinates (skdtree.h:374-381).
+// Rectangles keep only the .w words of r0..r3 (their frame lives in RectRecord).
 struct ShadeTri {
     float q[24];
 };
@@ -83,7 +86,8 @@ struct MeshRecord {  // offsets into the concatenated vertex/index pools
     uint32_t nTriangles;
     float invSurfaceArea;
     uint32_t hasNormals;
-    uint32_t pad0, pad1;
+    uint32_t hasTexcoords;
+    uint32_t pad1;
 };
 
 struct BsdfRecord {  // mirrors B200pgBsdf + derived constants

@@ -255,7 +255,9 @@ struct Scene {
             Vec3 faceNormal(cross(side1, side2));
             Float len = length(faceNormal);
             if (!faceNormal.isZero()) faceNormal /= len;
-            its.dpdu = side1;
+            // skdtree.h:374-381: the per-triangle UV tangent when the mesh has one (TriMesh::configure computes them for every
+            // mesh with texture coordinates, trimesh.cpp:383-385), the first edge otherwise
+            its.dpdu = shape.uvTangents.empty() ? side1 : shape.uvTangents[cache.primIndex];
             if (!shape.normals.empty()) {
                 const Vec3 &n0 = shape.normals[idx0], &n1 = shape.normals[idx1], &n2 = shape.normals[idx2];
                 its.shFrame.n = normalize(n0 * b.x + n1 * b.y + n2 * b.z);
@@ -707,6 +709,27 @@ static Scene *buildScene(const B200pgSceneDesc *desc) {
             }
             Float total = cdfNormalize(s.areaCdf);
             s.invSurfaceArea = 1.0f / total;
+            if (!s.texcoords.empty()) {  // TriMesh::computeUVTangents, trimesh.cpp:683-735
+                s.uvTangents.assign(d.n_triangles, Vec3(0.0f));
+                for (uint32_t t = 0; t < d.n_triangles; ++t) {
+                    const uint32_t i0 = s.indices[3 * t], i1 = s.indices[3 * t + 1], i2 = s.indices[3 * t + 2];
+                    const Vec3 dP1 = s.positions[i1] - s.positions[i0], dP2 = s.positions[i2] - s.positions[i0];
+                    const Vec2 dUV1(s.texcoords[i1].x - s.texcoords[i0].x, s.texcoords[i1].y - s.texcoords[i0].y);
+                    const Vec2 dUV2(s.texcoords[i2].x - s.texcoords[i0].x, s.texcoords[i2].y - s.texcoords[i0].y);
+                    const Vec3 n = cross(dP1, dP2);
+                    const Float len = length(n);
+                    if (len == 0) continue;  // degenerate triangle: the zero tangent stays (never hit)
+                    const Float determinant = dUV1.x * dUV2.y - dUV1.y * dUV2.x;
+                    if (determinant == 0) {  // degenerate parameterisation: any tangent perpendicular to the face normal
+                        Vec3 a, b;
+                        coordinateSystem(n / len, a, b);
+                        s.uvTangents[t] = a;
+                    } else {
+                        const Float invDet = 1.0f / determinant;
+                        s.uvTangents[t] = (dP1 * dUV2.y - dP2 * dUV1.y) * invDet;
+                    }
+                }
+            }
             primCount += d.n_triangles;
         }
         sc->shapes.push_back(std::move(s));

@@ -133,6 +133,7 @@ struct Shape {
     std::vector<Vec3> positions, normals;
     std::vector<Vec2> texcoords;
     std::vector<uint32_t> indices;
+    std::vector<Vec3> uvTangents;  // per-triangle dpdu of TriMesh::computeUVTangents (trimesh.cpp:683-735); empty without texcoords
     std::vector<Float> areaCdf;  // DiscreteDistribution m_cdf (pmf.h)
     uint32_t primOffset;         // first global primitive id
     bool isMediumTransition() const { return interiorMedium >= 0 || exteriorMedium >= 0; }

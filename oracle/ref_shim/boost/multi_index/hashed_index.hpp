@@ -1,0 +1,2 @@
+#pragma once
+#include <boost/multi_index_container.hpp>

@@ -1,0 +1,180 @@
+"""ctypes wrapper around oracle/_ref/libref_harness.so (TEST INFRASTRUCTURE): the REFERENCE's own classes, compiled by
+oracle/Makefile.ref from the sources under /root/reference, behind the C-ABI of oracle/ref_harness/ref_harness.cpp.
+
+The method names and array layouts follow tests/oracle_lib.py's OracleScene so that a test reads
+`ref.intersect(rays)` next to `orc.intersect(rays)`. `available()` is False when the library has not been built (no
+/root/reference at build time and no prebuilt oracle/_ref shipped): tests that need it skip, the committed fixtures under
+tests/golden/upstream_*.npz (tests/golden/make_upstream.py) keep the pin without it."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from conftest import ROOT, load_package
+
+b200pg = load_package()
+A = b200pg._abi
+
+fp = C.POINTER(C.c_float)
+u32p = C.POINTER(C.c_uint32)
+
+SO = os.path.join(ROOT, "oracle", "_ref", "libref_harness.so")
+
+
+def available():
+    return os.path.exists(SO)
+
+
+def _f(a):
+    return a.ctypes.data_as(fp)
+
+
+def _u(a):
+    return a.ctypes.data_as(u32p)
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = L = C.CDLL(SO, mode=C.RTLD_GLOBAL)
+        L.ref_last_error.restype = C.c_char_p
+        L.ref_scene_create.restype = C.c_void_p
+        L.ref_scene_create.argtypes = [C.POINTER(A.SceneDesc)]
+        L.ref_scene_destroy.argtypes = [C.c_void_p]
+        L.ref_kd_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.ref_intersect.argtypes = [C.c_void_p, fp, C.c_size_t, C.c_int, fp, u32p, C.c_int]
+        L.ref_camera_rays.argtypes = [C.c_void_p, fp, C.c_size_t, fp]
+        L.ref_bsdf.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_size_t, fp, fp, fp, fp, fp, u32p]
+        L.ref_emitter_direct.argtypes = [C.c_void_p, fp, fp, fp, fp, C.c_size_t, fp, fp, fp]
+        L.ref_radiance.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), u32p, u32p, C.c_size_t, fp, fp]
+        L.ref_film_splat.argtypes = [C.c_void_p, fp, fp, C.c_size_t, fp]
+        L.ref_render.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), C.c_int, C.c_int, fp, C.c_int, C.c_int,
+                                 C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.ref_grid_lookup.argtypes = [C.c_void_p, C.c_int, fp, C.c_size_t, fp]
+        L.ref_medium_sample.argtypes = [C.c_void_p, C.c_int, fp, C.c_size_t, fp, fp, fp]
+        L.ref_phase.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_size_t, fp, fp, fp]
+        L.ref_num_threads.restype = C.c_int
+    return _LIB
+
+
+class RefScene:
+    """A scene instantiated from reference objects (PluginManager + Properties) out of the same flat description the product
+    and the oracle port consume."""
+
+    def __init__(self, builder=None, desc=None, keep=None, rtrans_reduce=None):
+        self.L = lib()
+        if desc is None:
+            desc, keep = builder.desc(rtrans_reduce=rtrans_reduce)  # the reduced tables are not read by the reference
+        self.desc, self._keep = desc, keep
+        self.h = self.L.ref_scene_create(C.byref(desc))
+        if not self.h:
+            raise RuntimeError("ref_scene_create failed: %s" % self.L.ref_last_error().decode())
+        self.W, self.H = desc.film.width, desc.film.height
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.ref_scene_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def _ok(self, r):
+        if r != 0:
+            raise RuntimeError("ref_harness: %s" % self.L.ref_last_error().decode())
+
+    def kd_info(self):
+        out = (C.c_uint64 * 2)()
+        self._ok(self.L.ref_kd_info(self.h, out))
+        return dict(shapes=out[0], prims=out[1])
+
+    def intersect(self, rays, nthreads=0):
+        """Scene::rayIntersect(ray, its): dict of t, p, uv, geo_n, sh_n, sh_s, dpdu, prim (global id, 0xFFFFFFFF = miss)."""
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = rays.shape[0]
+        out = np.zeros((n, 18), np.float32)
+        prim = np.zeros(n, np.uint32)
+        self._ok(self.L.ref_intersect(self.h, _f(rays), n, 0, _f(out), _u(prim), nthreads))
+        return dict(t=out[:, 0], p=out[:, 1:4], uv=out[:, 4:6], geo_n=out[:, 6:9], sh_n=out[:, 9:12], sh_s=out[:, 12:15],
+                    dpdu=out[:, 15:18], prim=prim)
+
+    def occluded(self, rays, nthreads=0):
+        """Scene::rayIntersect(ray) (shadow rays): bool per ray."""
+        rays = np.ascontiguousarray(rays, np.float32)
+        prim = np.zeros(rays.shape[0], np.uint32)
+        self._ok(self.L.ref_intersect(self.h, _f(rays), rays.shape[0], 1, None, _u(prim), nthreads))
+        return prim == 0
+
+    def camera_rays(self, pos):
+        pos = np.ascontiguousarray(pos, np.float32)
+        rays = np.zeros((pos.shape[0], 8), np.float32)
+        self._ok(self.L.ref_camera_rays(self.h, _f(pos), pos.shape[0], _f(rays)))
+        return rays
+
+    def bsdf(self, index, wi, wo, u):
+        wi, wo, u = (np.ascontiguousarray(a, np.float32) for a in (wi, wo, u))
+        n = wi.shape[0]
+        ev, pdf, swo = np.zeros((n, 3), np.float32), np.zeros(n, np.float32), np.zeros((n, 3), np.float32)
+        w, spdf, fl = np.zeros((n, 3), np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint32)
+        self._ok(self.L.ref_bsdf(self.h, index, _f(wi), _f(wo), _f(u), n, _f(ev), _f(pdf), _f(swo), _f(w), _f(spdf), _u(fl)))
+        return dict(eval=ev, pdf=pdf, wo=swo, weight=w, spdf=spdf, flags=fl)
+
+    def emitter_sample(self, ref, ref_n, u):
+        ref, ref_n, u = (np.ascontiguousarray(a, np.float32) for a in (ref, ref_n, u))
+        n = u.shape[0]
+        d, dist, pdf, val = np.zeros((n, 3), np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros((n, 3), np.float32)
+        self._ok(self.L.ref_emitter_direct(self.h, _f(ref), _f(ref_n), _f(u), _f(d), n, _f(dist), _f(pdf), _f(val)))
+        return d, dist, pdf, val
+
+    def emitter_pdf(self, ref, ref_n, d):
+        ref, ref_n = (np.ascontiguousarray(a, np.float32) for a in (ref, ref_n))
+        d = np.ascontiguousarray(d, np.float32).copy()
+        pdf = np.zeros(d.shape[0], np.float32)
+        self._ok(self.L.ref_emitter_direct(self.h, _f(ref), _f(ref_n), None, _f(d), d.shape[0], None, _f(pdf), None))
+        return pdf
+
+    def radiance(self, params, pixel, sample):
+        """The integrator's Li for camera samples (pixel, sample index) drawn from the shared counter stream."""
+        pixel = np.ascontiguousarray(pixel, np.uint32)
+        sample = np.ascontiguousarray(sample, np.uint32)
+        out = np.zeros((pixel.shape[0], 3), np.float32)
+        pos = np.zeros((pixel.shape[0], 2), np.float32)
+        self._ok(self.L.ref_radiance(self.h, C.byref(params), _u(pixel), _u(sample), pixel.shape[0], _f(out), _f(pos)))
+        return out, pos
+
+    def film_splat(self, pos, rgb):
+        pos, rgb = np.ascontiguousarray(pos, np.float32), np.ascontiguousarray(rgb, np.float32)
+        film = np.zeros((self.H, self.W, 5), np.float32)
+        self._ok(self.L.ref_film_splat(self.h, _f(pos), _f(rgb), pos.shape[0], _f(film)))
+        return film
+
+    def render(self, params, first_sample=0, n_samples=1, nthreads=0, independent=False, want_film=True):
+        """Scene::preprocess + Scene::render of the reference (every stage but Film::develop). Returns (film H*W*5, seconds)."""
+        film = np.zeros((self.H, self.W, 5), np.float32) if want_film else None
+        sec, spp = C.c_double(), C.c_int()
+        self._ok(self.L.ref_render(self.h, C.byref(params), first_sample, n_samples, _f(film) if want_film else None, nthreads,
+                                   int(independent), C.byref(sec), C.byref(spp)))
+        return film, sec.value
+
+    def grid_lookup(self, medium, p):
+        p = np.ascontiguousarray(p, np.float32)
+        out = np.zeros(p.shape[0], np.float32)
+        self._ok(self.L.ref_grid_lookup(self.h, medium, _f(p), p.shape[0], _f(out)))
+        return out
+
+    def medium_sample(self, medium, rays):
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = rays.shape[0]
+        t, ps, tr = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+        self._ok(self.L.ref_medium_sample(self.h, medium, _f(rays), n, _f(t), _f(ps), _f(tr)))
+        return t, ps, tr
+
+    def phase(self, medium, wi, wo, u):
+        wi, wo, u = (np.ascontiguousarray(a, np.float32) for a in (wi, wo, u))
+        n = wi.shape[0]
+        ev, swo, pdf = np.zeros(n, np.float32), np.zeros((n, 3), np.float32), np.zeros(n, np.float32)
+        self._ok(self.L.ref_phase(self.h, medium, _f(wi), _f(wo), _f(u), n, _f(ev), _f(swo), _f(pdf)))
+        return ev, swo, pdf
