@@ -732,9 +732,8 @@ int ref_grid_lookup(void *s, int medium, const float *p, size_t n, float *out) {
     REF_CATCH(-1)
 }
 
-// HeterogeneousMedium::sampleDistance / evalTransmittance (heterogeneous.cpp) with the replay stream (seed, pixel = i, 0):
-// the distance draws first, then a FRESH stream (seed, i, 1) for the transmittance estimate (the two calls are independent
-// estimators; the split keeps their consumption separate on both sides of the comparison).
+// HeterogeneousMedium::sampleDistance, then evalTransmittance (heterogeneous.cpp), both drawing from the replay stream
+// (seed, pixel = i, sample 0) one after the other -- the order orc_medium_sample uses.
 int ref_medium_sample(void *s, int medium, const float *rays, size_t n, float *out_t, float *out_success, float *out_tr) {
     REF_TRY
     RefScene *rs = (RefScene *)s;
@@ -749,7 +748,6 @@ int ref_medium_sample(void *s, int medium, const float *rays, size_t n, float *o
         bool ok = M->sampleDistance(ray, mRec, sampler);
         out_t[i] = ok ? mRec.t : std::numeric_limits<float>::infinity();
         if (out_success) out_success[i] = ok ? mRec.pdfSuccess : mRec.pdfFailure;
-        sampler->setStream((uint32_t)i, 1);
         Spectrum tr = M->evalTransmittance(ray, sampler);
         out_tr[i] = tr[0];
     }

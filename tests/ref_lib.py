@@ -67,7 +67,9 @@ class RefScene:
     def __init__(self, builder=None, desc=None, keep=None, rtrans_reduce=None):
         self.L = lib()
         if desc is None:
-            desc, keep = builder.desc(rtrans_reduce=rtrans_reduce)  # the reduced tables are not read by the reference
+            # the reduced rough-transmittance tables of the description are not read here: the reference's roughplastic loads
+            # data/microfacet/*.dat itself (rtrans.h), so zeros do
+            desc, keep = builder.desc(rtrans_reduce=rtrans_reduce or (lambda distr, eta, alpha: (np.zeros(100), 0.0, 0.0)))
         self.desc, self._keep = desc, keep
         self.h = self.L.ref_scene_create(C.byref(desc))
         if not self.h:

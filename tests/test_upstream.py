@@ -1,0 +1,271 @@
+"""The pin of the oracle port -- and of the CUDA path -- to the REFERENCE ITSELF.
+
+tests/golden/upstream.npz holds what the reference's own classes (compiled from /root/reference by oracle/Makefile.ref, driven
+through oracle/ref_harness) return for the inputs of the golden fixtures: ShapeKDTree::rayIntersect hit records,
+PerspectiveCamera rays, BSDF::eval / pdf / sample for the test_bsdf.xml parameterisations, Scene::sampleEmitterDirect /
+pdfEmitterDirect, ProgressiveMIPathTracer::Li per camera sample (the replay sampler hands the reference the same counter-based
+stream the product uses), ImageBlock::put, the film of ProgressiveMonteCarloIntegrator::render (also with a finite
+maxComponentValue), GridDataSource::lookupFloat, HeterogeneousMedium::sampleDistance / evalTransmittance, the phase functions.
+
+CPU (`-m "not gpu"`):
+  * the oracle port's committed fixtures (tests/golden/*.npz, same inputs) against the reference's outputs -- pure array
+    comparisons, so the pin holds on any machine;
+  * where oracle/_ref is present (the build container; the GPU box gets the prebuilt files), the reference regenerates
+    upstream.npz and must reproduce it, and the oracle is run live against it on the mesh case.
+GPU (`-m gpu`): the CUDA path through the C-ABI against the same reference outputs.
+
+Tolerances: indices / hit-or-miss / sampled-lobe flags exact up to a stated number of knife-edge rays; floats to 1e-5 relative
+unless a line says otherwise (single-precision transport on two compilers: -O2 without FMA for the reference, FMA contraction
+for the oracle and the GPU)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+import make_golden as mg  # noqa: E402
+import make_upstream as mu  # noqa: E402
+
+MISS = 0xFFFFFFFF
+
+
+@pytest.fixture(scope="module")
+def up():
+    return dict(np.load(os.path.join(HERE, "golden", "upstream.npz")))
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return mu.load_gold()
+
+
+def rel_err(a, b, floor=1e-3):
+    return np.abs(a - b) / np.maximum(np.abs(b), floor)
+
+
+def check_hits(t, prim, want_t, want_prim, max_mismatch):
+    mism = prim != want_prim
+    assert mism.sum() <= max_mismatch, mism.sum()
+    m = (want_prim != MISS) & ~mism
+    rel = np.abs(t[m] - want_t[m]) / (1 + np.abs(want_t[m]))
+    assert np.quantile(rel, 0.999) <= 2e-6 and rel.max() <= 2e-3
+
+
+def check_radiance(got, want, frac):
+    """Per-sample radiance: a path whose float rounding flips one discrete decision (a Russian-roulette or lobe choice, a
+    knife-edge hit) lands somewhere else entirely, so the bar is the FRACTION of samples that differ, plus the mean."""
+    err = np.abs(got - want).max(1) / (np.abs(want).max(1) + 1e-3)
+    assert (err > 1e-3).mean() < frac, (err > 1e-3).mean()
+    assert abs(got.mean() - want.mean()) <= 2e-3 * want.mean()
+
+
+def check_bsdf(r, want, name, flag_frac=0.998):
+    for key in ("eval", "pdf"):
+        assert np.all(np.abs(want[key] - r[key]) <= 1e-5 * np.maximum(np.abs(want[key]), 1e-3)), (name, key)
+    good = want["spdf"] > 0  # a failed sample (zero weight) carries no lobe flag in the reference's record
+    assert ((r["spdf"] > 0) == good).mean() > flag_frac, name
+    same = (want["flags"] == r["flags"]) & (r["spdf"] > 0) & good
+    assert same.sum() > flag_frac * good.sum(), name
+    ok = same
+    assert np.abs(want["wo"][ok] - r["wo"][ok]).max() <= 2e-3, name
+    w = rel_err(r["weight"][ok], want["weight"][ok]).max(1)
+    assert np.quantile(w, 0.99) <= 1e-4 and (w > 1e-2).mean() < 5e-3, name  # grazing wo amplifies rounding in G / (cos pdf)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+#  CPU: the oracle port against the reference
+# ---------------------------------------------------------------------------------------------------------------------
+def test_fixture_is_committed_and_small():
+    assert os.path.getsize(os.path.join(HERE, "golden", "upstream.npz")) < 2 << 20
+
+
+@pytest.mark.parametrize("name", ["cornell", "caustic"])
+def test_oracle_traversal_and_radiance_match_the_reference(name, up, gold):
+    g = gold[name]
+    np.testing.assert_allclose(g["rays"], up[name + "/camera_rays"], rtol=1e-6, atol=2e-6)
+    check_hits(g["tuv"][:, 0], g["prim"], up[name + "/t"], up[name + "/prim"], 0)
+    check_hits(g["tuv2"][:, 0], g["prim2"], up[name + "/t2"], up[name + "/prim2"], 0)
+    assert np.array_equal(g["occluded"], up[name + "/occluded"])
+    check_radiance(g["radiance"], up[name + "/radiance"], 1e-3)
+
+
+def test_oracle_film_matches_the_reference(up, gold):
+    g = gold["cornell"]
+    assert np.array_equal(g["film"], up["cornell/film"])  # ImageBlock::put with the Gaussian filter table: bit for bit
+    f, r = g["render_film"], up["cornell/render_film"]
+    np.testing.assert_allclose(f[..., 4], r[..., 4], rtol=1e-6)  # same filter weights, summed in another (tile-merge) order
+    np.testing.assert_allclose(f[..., :3], r[..., :3], rtol=1e-4, atol=2e-4)
+    assert abs(f[..., :3].sum() - r[..., :3].sum()) <= 1e-5 * r[..., :3].sum()
+
+
+def test_oracle_bsdfs_match_the_reference(up, gold):
+    from bsdf_cases import bsdf_scene
+
+    _, idx = bsdf_scene()
+    for name in idx:
+        o = {k: gold["bsdf"]["%s/%s" % (name, k)] for k in mu.BSDF_KEYS}
+        r = {k: up["bsdf/%s/%s" % (name, k)] for k in mu.BSDF_KEYS}
+        check_bsdf(o, r, name, flag_frac=0.9999)
+        assert np.array_equal(o["spdf"] > 0, r["spdf"] > 0), name  # the same samples fail on both sides
+
+
+def test_oracle_medium_matches_the_reference(up, gold):
+    g = gold["medium"]
+    np.testing.assert_allclose(g["density"], up["medium/density"], rtol=1e-5, atol=1e-6)
+    to, tr = g["t"], up["medium/t"]
+    assert np.array_equal(np.isfinite(to), np.isfinite(tr))
+    m = np.isfinite(tr)
+    assert m.mean() > 0.1 and rel_err(to[m], tr[m]).max() <= 1e-5
+    assert np.array_equal(g["transmittance"], up["medium/transmittance"])  # ratio tracking ends in 0 or 1 decisions
+
+
+def _have_ref():
+    import ref_lib
+
+    return ref_lib.available()
+
+
+needs_ref = pytest.mark.skipif(not _have_ref(), reason="oracle/_ref not built (no /root/reference here)")
+
+
+@needs_ref
+def test_reference_reproduces_the_fixture(pkg, up, gold):
+    import ref_lib
+
+    out = mu.generate(pkg, ref_lib, gold)
+    assert sorted(out) == sorted(up)
+    for k, v in out.items():
+        if v.dtype.kind in "ub":
+            assert np.array_equal(v, up[k]), k
+        else:
+            np.testing.assert_allclose(v, up[k], rtol=1e-5, atol=1e-5, err_msg=k)  # the threaded film merge order is free
+
+
+@needs_ref
+def test_oracle_mesh_case_and_emitters_match_the_reference(pkg, oracle, up):
+    """The cases whose inputs live in upstream.npz itself: the 7 k-triangle mesh with vertex normals and rough BSDFs (SAH
+    kd-tree of the reference against the oracle's restatement of it), emitter sampling, the phase functions."""
+    osc = oracle.scene(mu.mesh_case(pkg))
+    g = {k[len("mesh/in_"):]: v for k, v in up.items() if k.startswith("mesh/in_")}
+    np.testing.assert_allclose(osc.camera_rays(g["pos"]), up["mesh/camera_rays"], rtol=1e-6, atol=2e-6)
+    for tag in ("", "2"):
+        rays = g["rays" + tag]
+        tuv, prim, _ = osc.trace(rays)
+        check_hits(tuv[:, 0], prim, up["mesh/t" + tag], up["mesh/prim" + tag], 1)
+        its = osc.intersect(rays)
+        m = (prim != MISS) & (prim == up["mesh/prim" + tag])
+        assert np.abs(its["sh_n"][m] - up["mesh/sh_n" + tag][m]).max() <= 2e-5
+        assert np.abs(its["geo_n"][m] - up["mesh/geo_n" + tag][m]).max() <= 2e-5
+        assert np.abs(its["p"][m] - up["mesh/p" + tag][m]).max() <= 2e-5
+    _, occ, _ = osc.trace(g["rays3"], shadow=True)
+    assert ((occ != MISS) != up["mesh/occluded"]).sum() <= 1
+    check_radiance(osc.radiance(mg.params(pkg), g["pixel"], g["sample"]), up["mesh/radiance"], 2e-3)
+
+    osc = oracle.scene(mg.cases(pkg)["cornell"]())
+    d, dist, pdf, val = osc.emitter_sample(up["cornell/em_ref"], up["cornell/em_refn"], up["cornell/em_u"])
+    np.testing.assert_allclose(d, up["cornell/em_d"], atol=2e-6)
+    np.testing.assert_allclose(dist, up["cornell/em_dist"], rtol=2e-6)
+    np.testing.assert_allclose(pdf, up["cornell/em_pdf"], rtol=1e-5)
+    np.testing.assert_allclose(val, up["cornell/em_value"], rtol=1e-5, atol=1e-6)
+    q = osc.emitter_pdf(up["cornell/em_ref"], up["cornell/em_refn"], up["cornell/em_d"])
+    assert (up["cornell/em_pdf_query"] > 0).mean() > 0.9
+    np.testing.assert_allclose(q, up["cornell/em_pdf_query"], rtol=1e-5)
+    film, _ = osc.render(mg.params(pkg, max_component_value=0.75), 0, 2)  # the clamp of renderBlock (progressiveintegrator.cpp:277-280)
+    np.testing.assert_allclose(film[..., :3], up["cornell/render_film_clamped"][..., :3], rtol=1e-4, atol=2e-4)
+    assert np.abs(film[..., :3] - up["cornell/render_film"][..., :3]).max() > 0.1  # ... which does change this film
+
+    osc = oracle.scene(mg.cases(pkg)["medium"]())
+    ev, wo, pdf = osc.phase(0, up["medium/ph_wi"], up["medium/ph_wo_in"], up["medium/ph_u"])
+    np.testing.assert_allclose(ev, up["medium/ph_eval"], rtol=2e-5)
+    np.testing.assert_allclose(wo, up["medium/ph_wo"], atol=1e-5)
+    np.testing.assert_allclose(pdf, up["medium/ph_pdf"], rtol=2e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+#  GPU: the CUDA path against the reference
+# ---------------------------------------------------------------------------------------------------------------------
+gpu = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api(pkg):
+    from b200pg import api as _api
+
+    return _api
+
+
+@gpu
+@pytest.mark.parametrize("name", ["cornell", "caustic", "mesh"])
+def test_gpu_traversal_and_radiance_match_the_reference(name, pkg, api, up, gold):
+    if name == "mesh":
+        g = {k[len("mesh/in_"):]: v for k, v in up.items() if k.startswith("mesh/in_")}
+        sb = mu.mesh_case(pkg)
+    else:
+        g, sb = gold[name], mg.cases(pkg)[name]()
+    it = api.Integrator(api.Scene.from_builder(sb), mg.params(pkg))
+    tuv, prim = it.k_trace(g["rays"])
+    check_hits(tuv[:, 0], prim, up[name + "/t"], up[name + "/prim"], 1)
+    tuv2, prim2 = it.k_trace(g["rays2"])
+    check_hits(tuv2[:, 0], prim2, up[name + "/t2"], up[name + "/prim2"], 3)
+    _, occ = it.k_trace(g["rays3"], shadow=True)
+    assert ((occ != MISS) != up[name + "/occluded"]).sum() <= 3
+    check_radiance(it.k_radiance(g["pixel"], g["sample"]), up[name + "/radiance"], 5e-3)
+    it.close()
+
+
+@gpu
+def test_gpu_film_matches_the_reference(pkg, api, up, gold):
+    g = gold["cornell"]
+    it = api.Integrator(api.Scene.from_builder(mg.cases(pkg)["cornell"]()), mg.params(pkg))
+    it.film_clear()
+    it.k_film_splat(g["splat_pos"], g["splat_rgb"])
+    film = it.film()
+    np.testing.assert_allclose(film[..., 4], up["cornell/film"][..., 4], rtol=2e-5, atol=1e-5)
+    np.testing.assert_allclose(film[..., :3], up["cornell/film"][..., :3], rtol=2e-5, atol=1e-4)
+    it.film_clear()
+    it.progression(0, 2)  # samples 0, 1 of every pixel: what the reference's render loop produced with the replay sampler
+    f, r = it.film(), up["cornell/render_film"]
+    np.testing.assert_allclose(f[..., 4], r[..., 4], rtol=1e-4, atol=1e-4)
+    dev_g = f[..., :3] / np.maximum(f[..., 4:5], 1e-20)
+    dev_r = r[..., :3] / np.maximum(r[..., 4:5], 1e-20)
+    assert np.abs(dev_g - dev_r).mean() / dev_r.mean() < 5e-3
+    it.close()
+    it = api.Integrator(api.Scene.from_builder(mg.cases(pkg)["cornell"]()), mg.params(pkg, max_component_value=0.75))
+    it.film_clear()
+    it.progression(0, 2)
+    f, r = it.film(), up["cornell/render_film_clamped"]
+    dev_g = f[..., :3] / np.maximum(f[..., 4:5], 1e-20)
+    dev_r = r[..., :3] / np.maximum(r[..., 4:5], 1e-20)
+    assert np.abs(dev_g - dev_r).mean() / dev_r.mean() < 5e-3
+    it.close()
+
+
+@gpu
+def test_gpu_bsdfs_match_the_reference(pkg, api, up, gold):
+    from bsdf_cases import bsdf_scene
+
+    sb, idx = bsdf_scene()
+    it = api.Integrator(api.Scene.from_builder(sb), mg.params(pkg))
+    for name, i in idx.items():
+        g = {k: gold["bsdf"]["%s/%s" % (name, k)] for k in ("wi", "wo_in", "u")}
+        r = it.k_bsdf(i, g["wi"], g["wo_in"], g["u"])
+        check_bsdf(r, {k: up["bsdf/%s/%s" % (name, k)] for k in mu.BSDF_KEYS}, name)
+    it.close()
+
+
+@gpu
+def test_gpu_medium_matches_the_reference(pkg, api, up, gold):
+    g = gold["medium"]
+    it = api.Integrator(api.Scene.from_builder(mg.cases(pkg)["medium"]()), mg.params(pkg, volumetric=1))
+    np.testing.assert_allclose(it.k_grid_lookup(0, g["points"]), up["medium/density"], rtol=1e-5, atol=1e-6)
+    t, tr, wo, pdf = it.k_medium_sample(0, g["rays"])
+    to, tro = up["medium/t"], up["medium/transmittance"]
+    same = np.isfinite(to) == np.isfinite(t)
+    assert same.mean() > 0.998
+    m = same & np.isfinite(to)
+    assert (rel_err(t[m], to[m]) > 1e-5).mean() < 2e-3
+    assert (tro != tr).mean() < 2e-3
+    it.close()
