@@ -155,6 +155,67 @@ class CpuGuidedStep:
                 "structure": "SAH kd-tree of the reference (oracle restatement), counting traversal"}
 
 
+def _reference_unguided_here(pkg, sb, cores, budget_s=8.0):
+    """The REFERENCE ITSELF (its libraries and plugins compiled from /root/reference into oracle/_ref by oracle/Makefile.ref,
+    driven through oracle/ref_harness: test infrastructure) rendering the workload with its stock configuration --
+    `progressivepath` + `independent` sampler, Scene::preprocess + Scene::render on `cores` LocalWorker threads -- next to the
+    oracle port rendering the same thing unguided. The reference snapshot has no guided integrator (the guiding
+    library is an external dependency that is not in the tree), so the guided CPU baseline stays the port; this leg calibrates
+    the port against the real thing on the part both can run. Returns None when oracle/_ref is not there."""
+    try:
+        import ref_lib
+
+        if not ref_lib.available():
+            return {"value": None, "why": "oracle/_ref not built (needs /root/reference at build time)"}
+        if sum(s.get("T").shape[0] for s in sb.shapes if s.get("T") is not None) > 2_000_000:
+            return {"value": None, "why": "skipped: the reference's SAH kd-tree build over this mesh takes minutes"}
+        from oracle_lib import Oracle
+
+        p = pkg._abi.default_params()
+        p.max_depth = 8
+        p.volumetric = 1 if sb.media else 0
+        spp = 1
+        rs = ref_lib.RefScene(sb)
+        # one untimed warm-up progression (the kd-tree build and the per-pixel sampler allocation are not timed either), then
+        # progressions until the budget is spent
+        _, t = rs.render(p, 0, spp, nthreads=cores, independent=True, want_film=False, repeat=-int(1e3 * budget_s))
+        reps = rs.spp_done // spp
+        n = float(sb.width * sb.height * spp * reps)
+        osc = Oracle().scene(sb)
+        osc.render(p, 0, spp, nthreads=cores)
+        to = no = 0.0
+        oreps = 0
+        while oreps < 2 or (to < budget_s / 2 and oreps < 32):
+            _, st = osc.render(p, oreps * spp, spp, nthreads=cores)
+            to += st["seconds"]
+            no += st["paths"]
+            oreps += 1
+        return {"value": n / t / 1e6, "unit": "Mpaths/s", "cores": cores, "kind": "reference",
+                "sample": "%d unguided progressions of the whole %dx%d image at %d spp through Scene::render (%.1f s); g++ -O2 build "
+                          "without the reference's -march=native -funsafe-math-optimizations" % (reps, sb.width, sb.height, spp, t),
+                "port_unguided": {"value": no / to / 1e6, "unit": "Mpaths/s", "kind": "port",
+                                  "sample": "%d progressions, same scene and parameters (%.1f s)" % (oreps, to)}}
+    except Exception as ex:
+        return {"value": None, "why": "failed: %s" % ex}
+
+
+def reference_unguided(workload_name, cores, budget_s=8.0):
+    """Runs _reference_unguided_here in a child process (`bench.py --impl reference-unguided`): the reference libraries bring
+    their own thread / scheduler / logger singletons, and nothing they do may take the measuring process down."""
+    try:
+        env = dict(os.environ, OMP_NUM_THREADS=str(cores))
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference-unguided", "--workload", workload_name,
+                            "--ref-seconds", str(budget_s)], capture_output=True, text=True, timeout=60 + 20 * budget_s, env=env)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"value": None, "why": "child exited %d: %s" % (r.returncode, (r.stderr or "").strip()[-200:])}
+    except Exception as ex:
+        return {"value": None, "why": "failed: %s" % ex}
+
+
 def guided_params(pkg, args):
     p = pkg._abi.default_params()
     p.max_depth = 8
@@ -208,6 +269,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": cores, "kind": "port", "sample": sample,
                          "kd_traversal_per_ray": cpu.kd_bytes_per_ray()},
         "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reference_unguided": reference_unguided(args.workload, cores, args.ref_seconds),
     }
     emit(line)
 
@@ -627,6 +689,8 @@ def measure(ctx, args, headline):
                              "build %.1f s not counted)" % (nrep, rows, sb.width, sb.height, spp, t, build_s) if guided else
                              "%d unguided progressions over rows 0..%d at %d spp (%.1f s)" % (nrep, rows, spp, t),
                    "mrays_per_sec": nr2 / t / 1e6, "kd_traversal_per_ray": cb.kd_bytes_per_ray()}
+            if headline:
+                cpu["reference_unguided"] = reference_unguided(args.workload, ncores, args.cpu_baseline_seconds / 2)
         except Exception as ex:  # the oracle is test infrastructure; its absence must not break the product arm
             cpu = {"value": None, "unit": "Mpaths/s", "cores": 0, "kind": "port", "sample": "oracle unavailable: %s" % ex}
         line = {
@@ -676,6 +740,9 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "reference-unguided":  # child of reference_unguided()
+        pkg, sb, _ = workload(args.workload)
+        return emit(_reference_unguided_here(pkg, sb, len(os.sched_getaffinity(0)), args.ref_seconds))
     ctx = Ctx()
     line = measure(ctx, args, headline=True)
     # ---- the other BASELINE configs that fit one GPU, measured briefly next to the headline (N = 1 only; the N > 1 runs of the

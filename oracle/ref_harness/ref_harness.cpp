@@ -667,9 +667,9 @@ int ref_film_splat(void *s, const float *pos, const float *rgbv, size_t n, float
 // renderSamples / renderTime -> BlockedRenderProcess on `nthreads` LocalWorkers -> renderBlock -> Film::put), everything but
 // Film::develop. Renders samples [first_sample, first_sample + n_samples) of every pixel with the replay sampler
 // (independent = 0) or the reference's own `independent` sampler (independent = 1: the stock configuration; timing runs).
-// film: H*W*5 (the HDRFilm storage without its border, overwritten). seconds: wall time of Scene::render alone.
+// film: H*W*5 (the HDRFilm storage without its border, overwritten). seconds: wall time of the Scene::render calls alone.
 int ref_render(void *s, const B200pgIntegratorParams *P, int first_sample, int n_samples, float *film, int nthreads, int independent,
-               double *seconds, int *spp_done) {
+               double *seconds, int *spp_done, int repeat) {
     REF_TRY
     RefScene *rs = (RefScene *)s;
     B200pgIntegratorParams Q = *P;
@@ -700,11 +700,21 @@ int ref_render(void *s, const B200pgIntegratorParams *P, int first_sample, int n
     ref<RenderJob> job = new RenderJob("ref", rs->scene, queue, sceneID, sensorID, samplerID, false);
     // RenderJob::run (renderjob.cpp:84-112) without the develop step
     if (!rs->scene->preprocess(queue, job, sceneID, sensorID, samplerID)) throw std::runtime_error("preprocess failed");
+    // `repeat` > 1 (timing runs): Scene::render again on the same per-pixel samplers (preprocess allocates one sampler per pixel,
+    // progressiveintegrator.cpp:43-51 -- seconds for a 1024^2 film -- and is not part of the timed region)
+    // repeat < 0: one untimed warm-up render, then renders until -repeat milliseconds have passed (at least two)
+    int done = 0;
+    if (repeat < 0 && !rs->scene->render(queue, job, sceneID, sensorID, samplerID)) throw std::runtime_error("render failed");
     auto t0 = std::chrono::steady_clock::now();
-    if (!rs->scene->render(queue, job, sceneID, sensorID, samplerID)) throw std::runtime_error("render failed");
-    auto t1 = std::chrono::steady_clock::now();
-    if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
-    if (spp_done) *spp_done = n_samples;
+    double elapsed = 0;
+    while (true) {
+        if (!rs->scene->render(queue, job, sceneID, sensorID, samplerID)) throw std::runtime_error("render failed");
+        ++done;
+        elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (repeat >= 0 ? done >= std::max(repeat, 1) : (done >= 2 && elapsed * 1e3 >= -repeat)) break;
+    }
+    if (seconds) *seconds = elapsed;
+    if (spp_done) *spp_done = n_samples * done;
     queue->removeJob(job, false);
     sched->unregisterResource(sceneID);
     sched->unregisterResource(sensorID);

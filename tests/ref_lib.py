@@ -52,7 +52,7 @@ def lib():
         L.ref_radiance.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), u32p, u32p, C.c_size_t, fp, fp]
         L.ref_film_splat.argtypes = [C.c_void_p, fp, fp, C.c_size_t, fp]
         L.ref_render.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), C.c_int, C.c_int, fp, C.c_int, C.c_int,
-                                 C.POINTER(C.c_double), C.POINTER(C.c_int)]
+                                 C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]
         L.ref_grid_lookup.argtypes = [C.c_void_p, C.c_int, fp, C.c_size_t, fp]
         L.ref_medium_sample.argtypes = [C.c_void_p, C.c_int, fp, C.c_size_t, fp, fp, fp]
         L.ref_phase.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_size_t, fp, fp, fp]
@@ -153,12 +153,14 @@ class RefScene:
         self._ok(self.L.ref_film_splat(self.h, _f(pos), _f(rgb), pos.shape[0], _f(film)))
         return film
 
-    def render(self, params, first_sample=0, n_samples=1, nthreads=0, independent=False, want_film=True):
-        """Scene::preprocess + Scene::render of the reference (every stage but Film::develop). Returns (film H*W*5, seconds)."""
+    def render(self, params, first_sample=0, n_samples=1, nthreads=0, independent=False, want_film=True, repeat=1):
+        """Scene::preprocess + Scene::render of the reference (every stage but Film::develop). Returns (film H*W*5, seconds of
+        the `repeat` Scene::render calls; the film is the last one's)."""
         film = np.zeros((self.H, self.W, 5), np.float32) if want_film else None
         sec, spp = C.c_double(), C.c_int()
         self._ok(self.L.ref_render(self.h, C.byref(params), first_sample, n_samples, _f(film) if want_film else None, nthreads,
-                                   int(independent), C.byref(sec), C.byref(spp)))
+                                   int(independent), C.byref(sec), C.byref(spp), repeat))
+        self.spp_done = spp.value
         return film, sec.value
 
     def grid_lookup(self, medium, p):
