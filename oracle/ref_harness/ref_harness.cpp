@@ -181,7 +181,7 @@ struct RefScene {
     uint64_t seed = 0;
     int width = 0, height = 0, sampleCount = 1;
     B200pgIntegratorParams lastParams{};
-    bool haveInteg = false;
+    bool haveInteg = false, pluginInteg = false;
     ~RefScene() {
         for (auto &f : tmpFiles) remove(f.c_str());
     }
@@ -391,9 +391,20 @@ static RefScene *buildScene(const B200pgSceneDesc *d) {
     return rs.release();
 }
 
-static void setIntegrator(RefScene *rs, const B200pgIntegratorParams *P) {
-    if (rs->haveInteg && memcmp(&rs->lastParams, P, sizeof(*P)) == 0) return;
-    Properties p(P->volumetric ? "progressivevolpath" : "progressivepath");
+static void setIntegrator(RefScene *rs, const B200pgIntegratorParams *P, const char *plugin = nullptr, int deviceCount = 1) {
+    if (!plugin && rs->haveInteg && !rs->pluginInteg && memcmp(&rs->lastParams, P, sizeof(*P)) == 0) return;
+    Properties p(plugin ? plugin : (P->volumetric ? "progressivevolpath" : "progressivepath"));
+    if (plugin) {  // the reference-side binding of libb200pg.so (integration/b200guidedpath.cpp): its own parameters
+        p.setBoolean("guiding", P->guiding != 0);
+        p.setInteger("trainingProgressions", P->training_progressions);
+        p.setFloat("guidingProbability", P->guiding_probability);
+        p.setInteger("maxComponents", P->guide_max_components);
+        p.setInteger("maxSamplesPerCell", P->guide_max_cell_samples);
+        p.setBoolean("discardTrainingSamples", P->guide_train_discard_film != 0);
+        p.setBoolean("guidedDistance", P->guided_distance != 0);
+        p.setBoolean("volumetric", P->volumetric != 0);
+        p.setInteger("deviceCount", deviceCount);
+    }
     p.setInteger("maxDepth", P->max_depth);
     p.setInteger("rrDepth", P->rr_depth);
     p.setBoolean("strictNormals", P->strict_normals != 0);
@@ -402,6 +413,7 @@ static void setIntegrator(RefScene *rs, const B200pgIntegratorParams *P) {
     p.setInteger("maxRenderTime", P->max_render_time);
     if (std::isfinite(P->max_component_value)) p.setFloat("maxComponentValue", P->max_component_value);
     if (!P->volumetric) p.setBoolean("useNee", P->use_nee != 0);
+    rs->pluginInteg = plugin != nullptr;
     // progressive_path.cpp:340 registers the class under MonteCarloIntegrator, so that is the type to ask the plugin manager for
     ref<SamplingIntegrator> integ = static_cast<SamplingIntegrator *>(create<MonteCarloIntegrator>(p).get());
     integ->configure();
@@ -445,6 +457,66 @@ static uint32_t globalPrim(const RefScene *rs, const Intersection &its) {
     const bool mesh = its.shape->getClass()->derivesFrom(MTS_CLASS(TriMesh));
     return rs->primOffset[it->second] + (mesh ? its.primIndex : 0u);
 }
+
+static int renderCore(RefScene *rs, int first_sample, int n_samples, float *film, int nthreads, int independent, double *seconds,
+                      int *spp_done, int repeat) {
+    ensureWorkers(nthreads);
+    Scheduler *sched = Scheduler::getInstance();
+    ref<Sampler> sampler;
+    if (independent) {
+        Properties ps("independent");
+        ps.setInteger("sampleCount", n_samples);
+        sampler = create<Sampler>(ps);
+        sampler->configure();
+    } else {
+        sampler = new ReplaySampler(rs->seed, rs->width, (size_t)n_samples, (size_t)first_sample);
+    }
+    rs->scene->setSampler(sampler);
+    ref<RenderQueue> queue = new RenderQueue();
+    // the registrations RenderJob's constructor would make (renderjob.cpp:38-72), made here so that the ids are known
+    const int sceneID = sched->registerResource(rs->scene), sensorID = sched->registerResource(rs->sensor);
+    std::vector<SerializableObject *> samplers(sched->getCoreCount());
+    for (size_t i = 0; i < samplers.size(); ++i) {
+        ref<Sampler> c = sampler->clone();
+        c->incRef();
+        samplers[i] = c.get();
+    }
+    const int samplerID = sched->registerMultiResource(samplers);
+    for (size_t i = 0; i < samplers.size(); ++i) samplers[i]->decRef();
+    ref<RenderJob> job = new RenderJob("ref", rs->scene, queue, sceneID, sensorID, samplerID, false);
+    // RenderJob::run (renderjob.cpp:84-112) without the develop step
+    if (!rs->scene->preprocess(queue, job, sceneID, sensorID, samplerID)) throw std::runtime_error("preprocess failed");
+    // `repeat` > 1 (timing runs): Scene::render again on the same per-pixel samplers (preprocess allocates one sampler per pixel,
+    // progressiveintegrator.cpp:43-51 -- seconds for a 1024^2 film -- and is not part of the timed region)
+    // repeat < 0: one untimed warm-up render, then renders until -repeat milliseconds have passed (at least two)
+    int done = 0;
+    if (repeat < 0 && !rs->scene->render(queue, job, sceneID, sensorID, samplerID)) throw std::runtime_error("render failed");
+    auto t0 = std::chrono::steady_clock::now();
+    double elapsed = 0;
+    while (true) {
+        if (!rs->scene->render(queue, job, sceneID, sensorID, samplerID)) throw std::runtime_error("render failed");
+        ++done;
+        elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (repeat >= 0 ? done >= std::max(repeat, 1) : (done >= 2 && elapsed * 1e3 >= -repeat)) break;
+    }
+    if (seconds) *seconds = elapsed;
+    if (spp_done) *spp_done = n_samples * done;
+    queue->removeJob(job, false);
+    sched->unregisterResource(sceneID);
+    sched->unregisterResource(sensorID);
+    sched->unregisterResource(samplerID);
+    if (film) {
+        ImageBlock *st = rs->film->getStorage();
+        if (!st) throw std::runtime_error("film has no storage");
+        const int b = st->getBorderSize(), sx = rs->width + 2 * b;
+        const Float *data = st->getBitmap()->getFloatData();
+        for (int y = 0; y < rs->height; ++y)
+            for (int x = 0; x < rs->width; ++x)
+                for (int k = 0; k < 5; ++k) film[((size_t)y * rs->width + x) * 5 + k] = data[((size_t)(y + b) * sx + (x + b)) * 5 + k];
+    }
+    return 0;
+}
+
 
 extern "C" {
 
@@ -672,66 +744,26 @@ int ref_render(void *s, const B200pgIntegratorParams *P, int first_sample, int n
                double *seconds, int *spp_done, int repeat) {
     REF_TRY
     RefScene *rs = (RefScene *)s;
-    B200pgIntegratorParams Q = *P;
-    setIntegrator(rs, &Q);
-    ensureWorkers(nthreads);
-    Scheduler *sched = Scheduler::getInstance();
-    ref<Sampler> sampler;
-    if (independent) {
-        Properties ps("independent");
-        ps.setInteger("sampleCount", n_samples);
-        sampler = create<Sampler>(ps);
-        sampler->configure();
-    } else {
-        sampler = new ReplaySampler(rs->seed, rs->width, (size_t)n_samples, (size_t)first_sample);
-    }
-    rs->scene->setSampler(sampler);
-    ref<RenderQueue> queue = new RenderQueue();
-    // the registrations RenderJob's constructor would make (renderjob.cpp:38-72), made here so that the ids are known
-    const int sceneID = sched->registerResource(rs->scene), sensorID = sched->registerResource(rs->sensor);
-    std::vector<SerializableObject *> samplers(sched->getCoreCount());
-    for (size_t i = 0; i < samplers.size(); ++i) {
-        ref<Sampler> c = sampler->clone();
-        c->incRef();
-        samplers[i] = c.get();
-    }
-    const int samplerID = sched->registerMultiResource(samplers);
-    for (size_t i = 0; i < samplers.size(); ++i) samplers[i]->decRef();
-    ref<RenderJob> job = new RenderJob("ref", rs->scene, queue, sceneID, sensorID, samplerID, false);
-    // RenderJob::run (renderjob.cpp:84-112) without the develop step
-    if (!rs->scene->preprocess(queue, job, sceneID, sensorID, samplerID)) throw std::runtime_error("preprocess failed");
-    // `repeat` > 1 (timing runs): Scene::render again on the same per-pixel samplers (preprocess allocates one sampler per pixel,
-    // progressiveintegrator.cpp:43-51 -- seconds for a 1024^2 film -- and is not part of the timed region)
-    // repeat < 0: one untimed warm-up render, then renders until -repeat milliseconds have passed (at least two)
-    int done = 0;
-    if (repeat < 0 && !rs->scene->render(queue, job, sceneID, sensorID, samplerID)) throw std::runtime_error("render failed");
-    auto t0 = std::chrono::steady_clock::now();
-    double elapsed = 0;
-    while (true) {
-        if (!rs->scene->render(queue, job, sceneID, sensorID, samplerID)) throw std::runtime_error("render failed");
-        ++done;
-        elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        if (repeat >= 0 ? done >= std::max(repeat, 1) : (done >= 2 && elapsed * 1e3 >= -repeat)) break;
-    }
-    if (seconds) *seconds = elapsed;
-    if (spp_done) *spp_done = n_samples * done;
-    queue->removeJob(job, false);
-    sched->unregisterResource(sceneID);
-    sched->unregisterResource(sensorID);
-    sched->unregisterResource(samplerID);
-    if (film) {
-        ImageBlock *st = rs->film->getStorage();
-        if (!st) throw std::runtime_error("film has no storage");
-        const int b = st->getBorderSize(), sx = rs->width + 2 * b;
-        const Float *data = st->getBitmap()->getFloatData();
-        for (int y = 0; y < rs->height; ++y)
-            for (int x = 0; x < rs->width; ++x)
-                for (int k = 0; k < 5; ++k) film[((size_t)y * rs->width + x) * 5 + k] = data[((size_t)(y + b) * sx + (x + b)) * 5 + k];
-    }
-    return 0;
+    setIntegrator(rs, P);
+    return renderCore(rs, first_sample, n_samples, film, nthreads, independent, seconds, spp_done, repeat);
     REF_CATCH(-1)
 }
 
+// Scene::preprocess + Scene::render + Integrator::postprocess with the integrator the reference's PluginManager creates from
+// plugins/<plugin>.so -- integration/b200guidedpath.cpp, the reference-side binding of libb200pg.so -- on a scene whose source
+// file is `xml_path` (the binding hands that file to the GPU library). film: the reference's HDRFilm storage afterwards.
+int ref_render_plugin(void *s, const B200pgIntegratorParams *P, const char *plugin, const char *xml_path, int device_count,
+                      float *film, double *seconds) {
+    REF_TRY
+    RefScene *rs = (RefScene *)s;
+    setIntegrator(rs, P, plugin, device_count);
+    rs->scene->setSourceFile(fs::path(xml_path ? xml_path : ""));
+    int spp = 0;
+    const int rc = renderCore(rs, 0, rs->sampleCount, film, 1, 0, seconds, &spp, 1);
+    rs->scene->getIntegrator()->postprocess(rs->scene, nullptr, nullptr, -1, -1, -1);
+    return rc;
+    REF_CATCH(-1)
+}
 // GridDataSource::lookupFloat (gridvolume.cpp:337-388)
 int ref_grid_lookup(void *s, int medium, const float *p, size_t n, float *out) {
     REF_TRY

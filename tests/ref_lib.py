@@ -53,6 +53,8 @@ def lib():
         L.ref_film_splat.argtypes = [C.c_void_p, fp, fp, C.c_size_t, fp]
         L.ref_render.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), C.c_int, C.c_int, fp, C.c_int, C.c_int,
                                  C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]
+        L.ref_render_plugin.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), C.c_char_p, C.c_char_p, C.c_int, fp,
+                                        C.POINTER(C.c_double)]
         L.ref_grid_lookup.argtypes = [C.c_void_p, C.c_int, fp, C.c_size_t, fp]
         L.ref_medium_sample.argtypes = [C.c_void_p, C.c_int, fp, C.c_size_t, fp, fp, fp]
         L.ref_phase.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_size_t, fp, fp, fp]
@@ -161,6 +163,16 @@ class RefScene:
         self._ok(self.L.ref_render(self.h, C.byref(params), first_sample, n_samples, _f(film) if want_film else None, nthreads,
                                    int(independent), C.byref(sec), C.byref(spp), repeat))
         self.spp_done = spp.value
+        return film, sec.value
+
+    def render_plugin(self, params, plugin, xml_path, device_count=1):
+        """The reference's Scene::preprocess / render / postprocess with the integrator its PluginManager loads from
+        plugins/<plugin>.so (integration/b200guidedpath.cpp: the reference-side binding of libb200pg.so). Returns the film the
+        binding put into the reference's HDRFilm (H*W*5) and the seconds Scene::render took."""
+        film = np.zeros((self.H, self.W, 5), np.float32)
+        sec = C.c_double()
+        self._ok(self.L.ref_render_plugin(self.h, C.byref(params), plugin.encode(), (xml_path or "").encode(), device_count, _f(film),
+                                          C.byref(sec)))
         return film, sec.value
 
     def grid_lookup(self, medium, p):

@@ -1,0 +1,86 @@
+"""The drop-in boundary from the reference's side: integration/b200guidedpath.cpp, a Mitsuba integrator plugin written against
+the reference's own plugin interface (MTS_EXPORT_PLUGIN, Integrator::preprocess / render / cancel / postprocess) that forwards
+to libb200pg.so's C-ABI. It is compiled against the reference build of oracle/_ref (integration/Makefile) and exercised here
+through the reference itself: PluginManager::createObject loads plugins/b200guidedpath.so, Scene::render calls it, and the film
+is read back from the reference's HDRFilm storage.
+
+CPU: the plugin loads, parses the reference's parameter names, reads the scene XML -- and fails loudly at the device
+(no CPU fallback). GPU: the film it puts into the reference's HDRFilm equals the film of a direct C-ABI render and, with
+guiding off, the film the reference's own progressivepath renders from the same sample indices."""
+import os
+
+import numpy as np
+import pytest
+
+import ref_lib
+from conftest import ROOT
+
+PLUGIN = os.path.join(ROOT, "oracle", "_ref", "plugins", "b200guidedpath.so")
+pytestmark = pytest.mark.skipif(not (ref_lib.available() and os.path.exists(PLUGIN)),
+                                reason="oracle/_ref or the plugin not built (needs /root/reference at build time)")
+
+
+def _scene(pkg, tmp_path, spp=4):
+    sb = pkg.scenes.cornell_box(64, 64, spp=spp)
+    xml = pkg.scenes.save_scene(sb, str(tmp_path))
+    return sb, xml
+
+
+def _have_gpu():
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_plugin_loads_in_the_reference_and_fails_loudly_without_a_device(pkg, tmp_path):
+    sb, xml = _scene(pkg, tmp_path)
+    rs = ref_lib.RefScene(sb)
+    p = pkg._abi.default_params()
+    p.max_depth, p.guiding = 8, 0
+    if _have_gpu():
+        film, _ = rs.render_plugin(p, "b200guidedpath", xml)
+        assert film[..., 4].sum() > 0
+        return
+    with pytest.raises(RuntimeError) as e:
+        rs.render_plugin(p, "b200guidedpath", xml)
+    assert "no CUDA device" in str(e.value) and "b200guidedpath" in str(e.value)  # the library's own message, through Log(EError)
+    with pytest.raises(RuntimeError) as e:
+        rs.render_plugin(p, "b200guidedpath", "")
+    assert "no source file" in str(e.value)
+    with pytest.raises(RuntimeError) as e:
+        rs.render_plugin(p, "b200guidedpath", os.path.join(str(tmp_path), "missing.xml"))
+    assert "b200guidedpath" in str(e.value)
+    # the reference's own integrator still renders the same scene object afterwards
+    film, _ = rs.render(p, 0, 1)
+    assert film[..., 4].sum() > 0
+
+
+@pytest.mark.gpu
+def test_reference_render_loop_with_the_gpu_integrator(pkg, tmp_path):
+    from b200pg import api
+
+    sb, xml = _scene(pkg, tmp_path)
+    rs = ref_lib.RefScene(sb)
+    p = pkg._abi.default_params()
+    p.max_depth, p.guiding = 8, 0
+    film, sec = rs.render_plugin(p, "b200guidedpath", xml)        # Scene::render -> plugin -> b200pg_render -> Film::put
+    sc = api.Scene.load_xml(xml)
+    it = api.Integrator(sc, p)
+    it.render()
+    direct = it.film()
+    it.close()
+    np.testing.assert_allclose(film[..., 4], direct[..., 4], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(film[..., :3], direct[..., :3], rtol=1e-4, atol=1e-3)
+    own, _ = rs.render(p, 0, 4)                                    # the reference's progressivepath, same sample indices
+    np.testing.assert_allclose(film[..., 4], own[..., 4], rtol=1e-4, atol=1e-4)
+    dev_g = film[..., :3] / np.maximum(film[..., 4:5], 1e-20)
+    dev_r = own[..., :3] / np.maximum(own[..., 4:5], 1e-20)
+    assert np.abs(dev_g - dev_r).mean() / dev_r.mean() < 5e-3
+    pg = pkg._abi.default_params()
+    pg.max_depth, pg.guiding, pg.training_progressions = 8, 1, 2
+    gfilm, _ = rs.render_plugin(pg, "b200guidedpath", xml)        # the guided integrator through the same door
+    dev = gfilm[..., :3] / np.maximum(gfilm[..., 4:5], 1e-20)
+    assert np.isfinite(dev).all() and abs(dev.mean() - dev_r.mean()) < 0.1 * dev_r.mean()
