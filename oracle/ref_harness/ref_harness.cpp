@@ -412,7 +412,7 @@ static void setIntegrator(RefScene *rs, const B200pgIntegratorParams *P, const c
     p.setInteger("samplesPerProgression", P->samples_per_progression > 0 ? P->samples_per_progression : 1);
     p.setInteger("maxRenderTime", P->max_render_time);
     if (std::isfinite(P->max_component_value)) p.setFloat("maxComponentValue", P->max_component_value);
-    if (!P->volumetric) p.setBoolean("useNee", P->use_nee != 0);
+    p.setBoolean("useNee", P->use_nee != 0);  // progressive_path.cpp:117, progressive_volpath.cpp:82
     rs->pluginInteg = plugin != nullptr;
     // progressive_path.cpp:340 registers the class under MonteCarloIntegrator, so that is the type to ask the plugin manager for
     ref<SamplingIntegrator> integ = static_cast<SamplingIntegrator *>(create<MonteCarloIntegrator>(p).get());
