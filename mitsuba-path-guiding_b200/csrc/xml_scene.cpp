@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <array>
 #include <map>
 #include <memory>
 #include <sstream>
@@ -724,13 +725,13 @@ struct Loader {
         finishMesh(pos, nrm, uv, idx, toWorld, flipNormals, faceNormals || (flags & 0x0010) != 0, s);
     }
 
-    void loadObj(const std::string &path, const M4 &toWorld, bool flipNormals, bool faceNormals, B200pgShape &s) {
+    void loadObj(const std::string &path, const M4 &toWorld, bool flipNormals, bool faceNormals, bool flipTexCoords, B200pgShape &s) {
         std::ifstream f(path);
         if (!f) fail("obj: cannot open \"" + path + "\"");
         std::vector<float> P, N, T;
         std::vector<float> pos, nrm, uv;
         std::vector<uint32_t> idx;
-        std::map<std::string, uint32_t> remap;
+        std::map<std::array<int, 3>, uint32_t> remap;  // resolved (position, texcoord, normal) index triple -> vertex (obj.cpp:437-470)
         std::string line;
         bool anyN = false;
         while (std::getline(f, line)) {
@@ -739,28 +740,31 @@ struct Loader {
             is >> t;
             if (t == "v") { float a, b, c; is >> a >> b >> c; P.insert(P.end(), {a, b, c}); }
             else if (t == "vn") { float a, b, c; is >> a >> b >> c; N.insert(N.end(), {a, b, c}); }
-            else if (t == "vt") { float a, b; is >> a >> b; T.insert(T.end(), {a, b}); }
+            else if (t == "vt") { float a, b; is >> a >> b; T.insert(T.end(), {a, flipTexCoords ? 1 - b : b}); }  // obj.cpp:303-308
             else if (t == "f") {
                 std::vector<uint32_t> poly;
                 std::string v;
                 while (is >> v) {
-                    auto it = remap.find(v);
+                    int pi = 0, ti = 0, ni = 0;
+                    if (std::sscanf(v.c_str(), "%d/%d/%d", &pi, &ti, &ni) != 3 && std::sscanf(v.c_str(), "%d//%d", &pi, &ni) != 2 &&
+                        std::sscanf(v.c_str(), "%d/%d", &pi, &ti) != 2)
+                        std::sscanf(v.c_str(), "%d", &pi);
+                    // negative = relative to the elements read so far: resolve BEFORE the look-up ("-1" names a different vertex
+                    // on every line, and "-5" and "2" may name the same one)
+                    if (pi < 0) pi = (int)(P.size() / 3) + pi + 1;
+                    if (ni < 0) ni = (int)(N.size() / 3) + ni + 1;
+                    if (ti < 0) ti = (int)(T.size() / 2) + ti + 1;
+                    if (pi <= 0 || (size_t)pi * 3 > P.size()) fail("obj: vertex index out of range");
+                    const std::array<int, 3> key = {pi, ti, ni};
+                    auto it = remap.find(key);
                     if (it == remap.end()) {
-                        int pi = 0, ti = 0, ni = 0;
-                        if (std::sscanf(v.c_str(), "%d/%d/%d", &pi, &ti, &ni) != 3 && std::sscanf(v.c_str(), "%d//%d", &pi, &ni) != 2 &&
-                            std::sscanf(v.c_str(), "%d/%d", &pi, &ti) != 2)
-                            std::sscanf(v.c_str(), "%d", &pi);
-                        if (pi < 0) pi = (int)(P.size() / 3) + pi + 1;
-                        if (ni < 0) ni = (int)(N.size() / 3) + ni + 1;
-                        if (ti < 0) ti = (int)(T.size() / 2) + ti + 1;
-                        if (pi <= 0 || (size_t)pi * 3 > P.size()) fail("obj: vertex index out of range");
                         uint32_t id = (uint32_t)(pos.size() / 3);
                         pos.insert(pos.end(), &P[3 * (pi - 1)], &P[3 * (pi - 1)] + 3);
                         if (ni > 0 && (size_t)ni * 3 <= N.size()) { nrm.insert(nrm.end(), &N[3 * (ni - 1)], &N[3 * (ni - 1)] + 3); anyN = true; }
                         else nrm.insert(nrm.end(), {0.0f, 0.0f, 0.0f});
                         if (ti > 0 && (size_t)ti * 2 <= T.size()) uv.insert(uv.end(), &T[2 * (ti - 1)], &T[2 * (ti - 1)] + 2);
                         else uv.insert(uv.end(), {0.0f, 0.0f});
-                        it = remap.emplace(v, id).first;
+                        it = remap.emplace(key, id).first;
                     }
                     poly.push_back(it->second);
                 }
@@ -1031,7 +1035,7 @@ struct Loader {
             std::string fn = getString(n, "filename", "");
             if (fn.empty()) fail("obj: missing filename");
             if (fn[0] != '/') fn = baseDir + "/" + fn;
-            loadObj(fn, toWorld, flip, getBool(n, "faceNormals", false), s);
+            loadObj(fn, toWorld, flip, getBool(n, "faceNormals", false), getBool(n, "flipTexCoords", true) /* obj.cpp:211 */, s);
         } else if (type == "ply") {
             std::string fn = getString(n, "filename", "");
             if (fn.empty()) fail("ply: missing filename");

@@ -827,6 +827,76 @@ int ref_phase(void *s, int medium, const float *wi, const float *wo, const float
     REF_CATCH(-1)
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Mesh ingestion: the reference's own loaders -- the `obj` plugin (src/shapes/obj.cpp) and
+// TriMesh(Stream *, int) for `.serialized` files (trimesh.cpp:79-270; the `serialized` plugin adds only an offset cache on top
+// of it) -- followed by TriMesh::configure (normals: trimesh.cpp:608-681). Returned as plain arrays.
+// ---------------------------------------------------------------------------------------------------------------------------
+struct RefMeshes {
+    ref<Shape> owner;
+    std::vector<ref<TriMesh>> meshes;
+};
+
+void *ref_mesh_load(const char *kind, const char *path, int shape_index, int face_normals, int flip_normals, const float *to_world) {
+    REF_TRY
+    ensureInit();
+    std::unique_ptr<RefMeshes> rm(new RefMeshes());
+    if (std::string(kind) == "obj") {
+        Properties p("obj");
+        p.setString("filename", path);
+        p.setBoolean("faceNormals", face_normals != 0);
+        p.setBoolean("flipNormals", flip_normals != 0);
+        if (to_world) p.setTransform("toWorld", xform(to_world));
+        ref<Shape> shape = create<Shape>(p);
+        shape->configure();
+        rm->owner = shape;
+        for (int i = 0;; ++i) {
+            Shape *e = shape->getElement(i);
+            if (!e) break;
+            TriMesh *m = static_cast<TriMesh *>(e);
+            m->configure();
+            rm->meshes.push_back(m);
+        }
+    } else {
+        ref<FileStream> fs = new FileStream(path, FileStream::EReadOnly);
+        // the serialized plugin seeks to the shape's offset from the dictionary at the end of the file (serialized.cpp) before
+        // handing the stream to TriMesh; with idx > 0 TriMesh::TriMesh(Stream *, int) does the same through readOffset
+        ref<TriMesh> m = new TriMesh(fs, shape_index);
+        m->configure();
+        rm->meshes.push_back(m);
+    }
+    return rm.release();
+    REF_CATCH(nullptr)
+}
+void ref_mesh_destroy(void *h) { delete (RefMeshes *)h; }
+int ref_mesh_count(void *h) { return (int)((RefMeshes *)h)->meshes.size(); }
+int ref_mesh_info(void *h, int i, uint64_t *out /* vertices, triangles, has normals, has texcoords */) {
+    const TriMesh *m = ((RefMeshes *)h)->meshes[i];
+    out[0] = m->getVertexCount();
+    out[1] = m->getTriangleCount();
+    out[2] = m->getVertexNormals() != NULL;
+    out[3] = m->getVertexTexcoords() != NULL;
+    return 0;
+}
+int ref_mesh_get(void *h, int i, float *pos, float *nrm, float *uv, uint32_t *idx) {
+    const TriMesh *m = ((RefMeshes *)h)->meshes[i];
+    for (size_t v = 0; v < m->getVertexCount(); ++v) {
+        const Point &p = m->getVertexPositions()[v];
+        pos[3 * v] = p.x; pos[3 * v + 1] = p.y; pos[3 * v + 2] = p.z;
+        if (nrm && m->getVertexNormals()) {
+            const Normal &n = m->getVertexNormals()[v];
+            nrm[3 * v] = n.x; nrm[3 * v + 1] = n.y; nrm[3 * v + 2] = n.z;
+        }
+        if (uv && m->getVertexTexcoords()) {
+            const Point2 &t = m->getVertexTexcoords()[v];
+            uv[2 * v] = t.x; uv[2 * v + 1] = t.y;
+        }
+    }
+    for (size_t t = 0; t < m->getTriangleCount(); ++t)
+        for (int k = 0; k < 3; ++k) idx[3 * t + k] = m->getTriangles()[t].idx[k];
+    return 0;
+}
+
 int ref_num_threads() { return omp_get_max_threads(); }
 
 }  // extern "C"

@@ -59,6 +59,12 @@ def lib():
         L.ref_medium_sample.argtypes = [C.c_void_p, C.c_int, fp, C.c_size_t, fp, fp, fp]
         L.ref_phase.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_size_t, fp, fp, fp]
         L.ref_num_threads.restype = C.c_int
+        L.ref_mesh_load.restype = C.c_void_p
+        L.ref_mesh_load.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, fp]
+        L.ref_mesh_destroy.argtypes = [C.c_void_p]
+        L.ref_mesh_count.argtypes = [C.c_void_p]
+        L.ref_mesh_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
+        L.ref_mesh_get.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, u32p]
     return _LIB
 
 
@@ -194,3 +200,26 @@ class RefScene:
         ev, swo, pdf = np.zeros(n, np.float32), np.zeros((n, 3), np.float32), np.zeros(n, np.float32)
         self._ok(self.L.ref_phase(self.h, medium, _f(wi), _f(wo), _f(u), n, _f(ev), _f(swo), _f(pdf)))
         return ev, swo, pdf
+
+
+def load_meshes(kind, path, shape_index=0, face_normals=False, flip_normals=False, to_world=None):
+    """The reference's own mesh loaders + TriMesh::configure: kind = "obj" (src/shapes/obj.cpp, every sub-mesh) or "serialized"
+    (TriMesh(Stream *, shapeIndex), trimesh.cpp:79-270). Returns a list of dicts P (n, 3), N (n, 3) or None, UV (n, 2) or None,
+    T (m, 3)."""
+    L = lib()
+    m = None if to_world is None else np.ascontiguousarray(to_world, np.float32).ravel()
+    h = L.ref_mesh_load(kind.encode(), str(path).encode(), shape_index, int(face_normals), int(flip_normals), _f(m) if m is not None else None)
+    if not h:
+        raise RuntimeError("ref_mesh_load: %s" % L.ref_last_error().decode())
+    out = []
+    try:
+        for i in range(L.ref_mesh_count(h)):
+            info = (C.c_uint64 * 4)()
+            L.ref_mesh_info(h, i, info)
+            nv, nt = int(info[0]), int(info[1])
+            P, N, UV, T = np.zeros((nv, 3), np.float32), np.zeros((nv, 3), np.float32), np.zeros((nv, 2), np.float32), np.zeros((nt, 3), np.uint32)
+            L.ref_mesh_get(h, i, _f(P), _f(N), _f(UV), _u(T))
+            out.append(dict(P=P, N=N if info[2] else None, UV=UV if info[3] else None, T=T))
+    finally:
+        L.ref_mesh_destroy(h)
+    return out
