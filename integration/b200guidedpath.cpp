@@ -24,6 +24,21 @@
 
 MTS_NAMESPACE_BEGIN
 
+/// The GPU film (R, G, B, alpha, weight per pixel, row-major, crop-sized: ImageBlock's ESpectrumAlphaWeight layout,
+/// imageblock.h:131-138) goes into the reference's film the way a worker's image block does (hdrfilm.cpp:391-393).
+/// extern "C" so that the test harness can drive this one step without a device.
+extern "C" void b200guidedpath_put_film(Film *film, const float *rgbaw) {
+    const Vector2i size = film->getCropSize();
+    ref<ImageBlock> block = new ImageBlock(Bitmap::ESpectrumAlphaWeight, size, film->getReconstructionFilter());
+    block->setOffset(film->getCropOffset());
+    block->clear();
+    const int border = block->getBorderSize(), stride = size.x + 2 * border;
+    Float *dst = block->getBitmap()->getFloatData();
+    for (int y = 0; y < size.y; ++y)
+        memcpy(dst + ((size_t) (y + border) * stride + border) * 5, rgbaw + (size_t) y * size.x * 5, sizeof(float) * 5 * size.x);
+    film->put(block);
+}
+
 class B200GuidedPathTracer : public ProgressiveMonteCarloIntegrator {
 public:
     B200GuidedPathTracer(const Properties &props) : ProgressiveMonteCarloIntegrator(props), m_handle(NULL) {
@@ -89,19 +104,10 @@ public:
         const int rc = b200pg_render(h, (int) devices.size(), devices.data());  // blocking, like Integrator::render
         std::string why = rc ? b200pg_last_error() : "";
         if (rc == 0) {
-            // the GPU film is R, G, B, alpha, weight per pixel -- ImageBlock's ESpectrumAlphaWeight layout
-            // (imageblock.h:131-138) -- and goes into the reference's film the way a worker's block does (hdrfilm.cpp:391-393)
             const Vector2i size = film->getCropSize();
             std::vector<float> rgbaw((size_t) size.x * size.y * 5);
             b200pg_film_read(h, rgbaw.data());
-            ref<ImageBlock> block = new ImageBlock(Bitmap::ESpectrumAlphaWeight, size, film->getReconstructionFilter());
-            block->setOffset(film->getCropOffset());
-            block->clear();
-            const int border = block->getBorderSize(), stride = size.x + 2 * border;
-            Float *dst = block->getBitmap()->getFloatData();
-            for (int y = 0; y < size.y; ++y)
-                memcpy(dst + ((size_t) (y + border) * stride + border) * 5, &rgbaw[(size_t) y * size.x * 5], sizeof(float) * 5 * size.x);
-            film->put(block);
+            b200guidedpath_put_film(film, rgbaw.data());
             b200pg_stats(h, &m_stats);
             m_spp = (int) (m_stats.paths / std::max((uint64_t) 1, (uint64_t) size.x * size.y));
         }

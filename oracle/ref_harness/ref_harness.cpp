@@ -29,6 +29,7 @@
 #include <mitsuba/render/progressiveintegrator.h>
 #include <omp.h>
 #include <execinfo.h>
+#include <dlfcn.h>
 #include <signal.h>
 #include <chrono>
 #include <cstdio>
@@ -764,6 +765,30 @@ int ref_render_plugin(void *s, const B200pgIntegratorParams *P, const char *plug
     return rc;
     REF_CATCH(-1)
 }
+// The film hand-off of the reference-side plugin on its own (integration/b200guidedpath.cpp: b200guidedpath_put_film), so that it
+// can be checked without a device: clears the scene's film, lets the plugin put `rgbaw` (H*W*5) into it, reads the storage back.
+int ref_plugin_put_film(void *s, const float *rgbaw, float *film) {
+    REF_TRY
+    RefScene *rs = (RefScene *)s;
+    const FileResolver *resolver = Thread::getThread()->getFileResolver();
+    fs::path path = resolver->resolve(fs::path("plugins") / "b200guidedpath.so");
+    void *h = dlopen(path.string().c_str(), RTLD_LAZY | RTLD_LOCAL);
+    if (!h) throw std::runtime_error(std::string("dlopen: ") + dlerror());
+    typedef void (*PutFilm)(Film *, const float *);
+    PutFilm put = (PutFilm)dlsym(h, "b200guidedpath_put_film");
+    if (!put) throw std::runtime_error("b200guidedpath_put_film not exported");
+    rs->film->clear();
+    put(rs->film, rgbaw);
+    ImageBlock *st = rs->film->getStorage();
+    const int b = st->getBorderSize(), sx = rs->width + 2 * b;
+    const Float *data = st->getBitmap()->getFloatData();
+    for (int y = 0; y < rs->height; ++y)
+        for (int x = 0; x < rs->width; ++x)
+            for (int k = 0; k < 5; ++k) film[((size_t)y * rs->width + x) * 5 + k] = data[((size_t)(y + b) * sx + (x + b)) * 5 + k];
+    return 0;
+    REF_CATCH(-1)
+}
+
 // GridDataSource::lookupFloat (gridvolume.cpp:337-388)
 int ref_grid_lookup(void *s, int medium, const float *p, size_t n, float *out) {
     REF_TRY

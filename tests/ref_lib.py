@@ -55,6 +55,7 @@ def lib():
                                  C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]
         L.ref_render_plugin.argtypes = [C.c_void_p, C.POINTER(A.IntegratorParams), C.c_char_p, C.c_char_p, C.c_int, fp,
                                         C.POINTER(C.c_double)]
+        L.ref_plugin_put_film.argtypes = [C.c_void_p, fp, fp]
         L.ref_grid_lookup.argtypes = [C.c_void_p, C.c_int, fp, C.c_size_t, fp]
         L.ref_medium_sample.argtypes = [C.c_void_p, C.c_int, fp, C.c_size_t, fp, fp, fp]
         L.ref_phase.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_size_t, fp, fp, fp]
@@ -180,6 +181,13 @@ class RefScene:
         self._ok(self.L.ref_render_plugin(self.h, C.byref(params), plugin.encode(), (xml_path or "").encode(), device_count, _f(film),
                                           C.byref(sec)))
         return film, sec.value
+
+    def plugin_put_film(self, rgbaw):
+        """integration/b200guidedpath.cpp's film hand-off alone: rgbaw (H, W, 5) -> the reference's HDRFilm -> its storage."""
+        rgbaw = np.ascontiguousarray(rgbaw, np.float32)
+        film = np.zeros((self.H, self.W, 5), np.float32)
+        self._ok(self.L.ref_plugin_put_film(self.h, _f(rgbaw), _f(film)))
+        return film
 
     def grid_lookup(self, medium, p):
         p = np.ascontiguousarray(p, np.float32)

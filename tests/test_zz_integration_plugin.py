@@ -58,6 +58,16 @@ def test_plugin_loads_in_the_reference_and_fails_loudly_without_a_device(pkg, tm
     assert film[..., 4].sum() > 0
 
 
+def test_plugin_film_handoff_into_the_reference_film(pkg):
+    """The one step of the plugin's render() that neither side of the device failure above reaches on a CPU-only machine: the
+    GPU film (H x W x 5) becomes an ImageBlock with the film's filter border and goes through Film::put (hdrfilm.cpp:391-393);
+    the reference's film storage must then hold exactly those numbers."""
+    sb = pkg.scenes.cornell_box(48, 32, spp=1)
+    rs = ref_lib.RefScene(sb)
+    rgbaw = np.random.RandomState(1).rand(32, 48, 5).astype(np.float32)
+    assert np.array_equal(rs.plugin_put_film(rgbaw), rgbaw)
+
+
 @pytest.mark.gpu
 def test_reference_render_loop_with_the_gpu_integrator(pkg, tmp_path):
     from b200pg import api
