@@ -922,6 +922,44 @@ int ref_mesh_get(void *h, int i, float *pos, float *nrm, float *uv, uint32_t *id
     return 0;
 }
 
+// A BSDF created the way the scene loader would from XML -- plugin name + named properties, nothing filled in by this file --
+// so that the product's XML reader can be held to the reference's own defaults and property semantics (named IORs, alpha vs
+// alphaU / alphaV, distribution names, ...). props: "name|kind|value;..." with kind f (float), i (integer), b (boolean:
+// true / false), s (string), c (r,g,b colour). twosided != 0 wraps the result in the `twosided` plugin. Evaluated like ref_bsdf.
+int ref_bsdf_from_props(const char *type, const char *props, int twosided, const float *wi, const float *wo, const float *u, size_t n,
+                        float *out_eval, float *out_pdf, float *out_wo, float *out_weight, float *out_spdf, uint32_t *out_flags) {
+    REF_TRY
+    ensureInit();
+    Properties p(type);
+    std::vector<std::string> items = tokenize(props ? props : "", ";");
+    for (const std::string &item : items) {
+        std::vector<std::string> f = tokenize(item, "|");
+        if (f.size() != 3) throw std::runtime_error("bad property \"" + item + "\"");
+        const std::string &name = f[0], &kind = f[1], &value = f[2];
+        if (kind == "f") p.setFloat(name, (Float)atof(value.c_str()));
+        else if (kind == "i") p.setInteger(name, atoi(value.c_str()));
+        else if (kind == "b") p.setBoolean(name, value == "true");
+        else if (kind == "s") p.setString(name, value);
+        else if (kind == "c") {
+            float c[3];
+            if (sscanf(value.c_str(), "%f,%f,%f", &c[0], &c[1], &c[2]) != 3) throw std::runtime_error("bad colour");
+            p.setSpectrum(name, rgb(c));
+        } else throw std::runtime_error("bad property kind");
+    }
+    ref<BSDF> bsdf = create<BSDF>(p);
+    bsdf->configure();
+    if (twosided) {
+        ref<BSDF> outer = create<BSDF>(Properties("twosided"));
+        outer->addChild(bsdf);
+        outer->configure();
+        bsdf = outer;
+    }
+    RefScene tmp;
+    tmp.bsdfs.push_back(bsdf);
+    return ref_bsdf(&tmp, 0, wi, wo, u, n, out_eval, out_pdf, out_wo, out_weight, out_spdf, out_flags);
+    REF_CATCH(-1)
+}
+
 int ref_num_threads() { return omp_get_max_threads(); }
 
 }  // extern "C"

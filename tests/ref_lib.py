@@ -60,6 +60,7 @@ def lib():
         L.ref_medium_sample.argtypes = [C.c_void_p, C.c_int, fp, C.c_size_t, fp, fp, fp]
         L.ref_phase.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_size_t, fp, fp, fp]
         L.ref_num_threads.restype = C.c_int
+        L.ref_bsdf_from_props.argtypes = [C.c_char_p, C.c_char_p, C.c_int, fp, fp, fp, C.c_size_t, fp, fp, fp, fp, fp, u32p]
         L.ref_mesh_load.restype = C.c_void_p
         L.ref_mesh_load.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, fp]
         L.ref_mesh_destroy.argtypes = [C.c_void_p]
@@ -231,3 +232,18 @@ def load_meshes(kind, path, shape_index=0, face_normals=False, flip_normals=Fals
     finally:
         L.ref_mesh_destroy(h)
     return out
+
+
+def bsdf_from_props(plugin, props, wi, wo, u, twosided=False):
+    """A reference BSDF created from a plugin name and named properties only -- [(name, kind, value)] with kind f / i / b / s / c
+    as in an XML scene -- and evaluated like RefScene.bsdf: the reference's own defaults and property semantics."""
+    L = lib()
+    wi, wo, u = (np.ascontiguousarray(a, np.float32) for a in (wi, wo, u))
+    n = wi.shape[0]
+    ev, pdf, swo = np.zeros((n, 3), np.float32), np.zeros(n, np.float32), np.zeros((n, 3), np.float32)
+    w, spdf, fl = np.zeros((n, 3), np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint32)
+    text = ";".join("%s|%s|%s" % t for t in props)
+    if L.ref_bsdf_from_props(plugin.encode(), text.encode(), int(twosided), _f(wi), _f(wo), _f(u), n, _f(ev), _f(pdf), _f(swo), _f(w),
+                             _f(spdf), _u(fl)) != 0:
+        raise RuntimeError("ref_bsdf_from_props: %s" % L.ref_last_error().decode())
+    return dict(eval=ev, pdf=pdf, wo=swo, weight=w, spdf=spdf, flags=fl)
