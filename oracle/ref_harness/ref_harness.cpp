@@ -20,6 +20,7 @@
 #include <mitsuba/core/appender.h>
 #include <mitsuba/render/scene.h>
 #include <mitsuba/render/trimesh.h>
+#include <mitsuba/render/skdtree.h>
 #include <mitsuba/render/renderjob.h>
 #include <mitsuba/render/renderqueue.h>
 #include <mitsuba/render/imageblock.h>
@@ -519,6 +520,60 @@ static int renderCore(RefScene *rs, int first_sample, int n_samples, float *film
 }
 
 
+// "name|kind|value;..." -> Properties, the way SceneHandler::endElement fills them from XML attributes (scenehandler.cpp:296-470).
+// kinds: f float, i integer, b boolean, s string, c "r,g,b" colour, x transform = '/'-separated ops applied in order with the
+// handler's rule m_transform = op * m_transform (:348-440) and the reference's own Transform factories:
+//   t:x,y,z   r:x,y,z,angle(degrees)   s:x,y,z   l:ox,oy,oz,tx,ty,tz[,ux,uy,uz] (lookat; no up -> coordinateSystem, :391-396)   m:16 values
+static Properties parseProps(const char *type, const char *props) {
+    Properties p(type);
+    for (const std::string &item : tokenize(props ? props : "", ";")) {
+        std::vector<std::string> f = tokenize(item, "|");
+        if (f.size() != 3) throw std::runtime_error("bad property \"" + item + "\"");
+        const std::string &name = f[0], &kind = f[1], &value = f[2];
+        if (kind == "f") p.setFloat(name, (Float)atof(value.c_str()));
+        else if (kind == "i") p.setInteger(name, atoi(value.c_str()));
+        else if (kind == "b") p.setBoolean(name, value == "true");
+        else if (kind == "s") p.setString(name, value);
+        else if (kind == "c") {
+            float c[3];
+            if (sscanf(value.c_str(), "%f,%f,%f", &c[0], &c[1], &c[2]) != 3) throw std::runtime_error("bad colour");
+            p.setSpectrum(name, rgb(c));
+        } else if (kind == "x") {
+            Transform trafo;
+            for (const std::string &op : tokenize(value, "/")) {
+                std::vector<Float> v;
+                for (const std::string &t : tokenize(op.substr(2), ",")) v.push_back((Float)atof(t.c_str()));
+                switch (op[0]) {
+                    case 't': trafo = Transform::translate(Vector(v.at(0), v.at(1), v.at(2))) * trafo; break;
+                    case 'r': trafo = Transform::rotate(Vector(v.at(0), v.at(1), v.at(2)), v.at(3)) * trafo; break;
+                    case 's': trafo = Transform::scale(Vector(v.at(0), v.at(1), v.at(2))) * trafo; break;
+                    case 'l': {
+                        Point o(v.at(0), v.at(1), v.at(2)), t(v.at(3), v.at(4), v.at(5));
+                        Vector up(0.0f);
+                        if (v.size() >= 9) up = Vector(v[6], v[7], v[8]);
+                        if (up.lengthSquared() == 0) {
+                            Vector unused;
+                            coordinateSystem(normalize(t - o), up, unused);
+                        }
+                        trafo = Transform::lookAt(o, t, up) * trafo;
+                        break;
+                    }
+                    case 'm': {
+                        Matrix4x4 m;
+                        for (int i = 0; i < 16; ++i) m.m[i / 4][i % 4] = v.at(i);
+                        trafo = Transform(m) * trafo;
+                        break;
+                    }
+                    default: throw std::runtime_error("bad transform op");
+                }
+            }
+            p.setTransform(name, trafo);
+        } else throw std::runtime_error("bad property kind");
+    }
+    return p;
+}
+
+
 extern "C" {
 
 const char *ref_last_error() { return g_err.c_str(); }
@@ -930,22 +985,7 @@ int ref_bsdf_from_props(const char *type, const char *props, int twosided, const
                         float *out_eval, float *out_pdf, float *out_wo, float *out_weight, float *out_spdf, uint32_t *out_flags) {
     REF_TRY
     ensureInit();
-    Properties p(type);
-    std::vector<std::string> items = tokenize(props ? props : "", ";");
-    for (const std::string &item : items) {
-        std::vector<std::string> f = tokenize(item, "|");
-        if (f.size() != 3) throw std::runtime_error("bad property \"" + item + "\"");
-        const std::string &name = f[0], &kind = f[1], &value = f[2];
-        if (kind == "f") p.setFloat(name, (Float)atof(value.c_str()));
-        else if (kind == "i") p.setInteger(name, atoi(value.c_str()));
-        else if (kind == "b") p.setBoolean(name, value == "true");
-        else if (kind == "s") p.setString(name, value);
-        else if (kind == "c") {
-            float c[3];
-            if (sscanf(value.c_str(), "%f,%f,%f", &c[0], &c[1], &c[2]) != 3) throw std::runtime_error("bad colour");
-            p.setSpectrum(name, rgb(c));
-        } else throw std::runtime_error("bad property kind");
-    }
+    Properties p = parseProps(type, props);
     ref<BSDF> bsdf = create<BSDF>(p);
     bsdf->configure();
     if (twosided) {
@@ -957,6 +997,94 @@ int ref_bsdf_from_props(const char *type, const char *props, int twosided, const
     RefScene tmp;
     tmp.bsdfs.push_back(bsdf);
     return ref_bsdf(&tmp, 0, wi, wo, u, n, out_eval, out_pdf, out_wo, out_weight, out_spdf, out_flags);
+    REF_CATCH(-1)
+}
+
+// A `perspective` sensor from named properties (+ an hdrfilm of the given size): rays for film positions pos (pixel units)
+int ref_sensor_rays_from_props(const char *props, int width, int height, const float *pos, size_t n, float *rays) {
+    REF_TRY
+    ensureInit();
+    Properties pf("hdrfilm");
+    pf.setInteger("width", width);
+    pf.setInteger("height", height);
+    pf.setBoolean("banner", false);
+    ref<Film> film = create<Film>(pf);
+    film->configure();
+    ref<Sensor> sensor = create<Sensor>(parseProps("perspective", props));
+    sensor->addChild(film);
+    sensor->configure();
+    for (size_t i = 0; i < n; ++i) {
+        Ray r;
+        sensor->sampleRay(r, Point2(pos[2 * i], pos[2 * i + 1]), Point2(0.5f), 0.5f);
+        float *o = rays + 8 * i;
+        o[0] = r.o.x; o[1] = r.o.y; o[2] = r.o.z; o[3] = r.mint;
+        o[4] = r.d.x; o[5] = r.d.y; o[6] = r.d.z; o[7] = r.maxt;
+    }
+    return 0;
+    REF_CATCH(-1)
+}
+
+// One shape plugin (rectangle, cube, obj) from named properties in a ShapeKDTree of its own: hit records as ref_intersect
+int ref_shape_from_props(const char *plugin, const char *props, const float *rays, size_t n, float *out) {
+    REF_TRY
+    ensureInit();
+    ref<Shape> shape = create<Shape>(parseProps(plugin, props));
+    ref<BSDF> bsdf = create<BSDF>(Properties("diffuse"));
+    bsdf->configure();
+    shape->addChild(bsdf);
+    shape->configure();
+    ref<ShapeKDTree> tree = new ShapeKDTree();
+    if (shape->getClass()->getName() == "WavefrontOBJ") {
+        for (int i = 0;; ++i) {
+            Shape *e = shape->getElement(i);
+            if (!e) break;
+            e->configure();
+            tree->addShape(e);
+        }
+    } else {
+        tree->addShape(shape);
+    }
+    tree->build();
+    for (size_t i = 0; i < n; ++i) {
+        const float *r = rays + 8 * i;
+        Ray ray(Point(r[0], r[1], r[2]), Vector(r[4], r[5], r[6]), r[3], r[7], 0.0f);
+        Intersection its;
+        float *o = out + 18 * i;
+        for (int k = 0; k < 18; ++k) o[k] = 0.0f;
+        if (!tree->rayIntersect(ray, its)) {
+            o[0] = std::numeric_limits<float>::infinity();
+            continue;
+        }
+        o[0] = its.t;
+        o[1] = its.p.x; o[2] = its.p.y; o[3] = its.p.z;
+        o[4] = its.uv.x; o[5] = its.uv.y;
+        o[6] = its.geoFrame.n.x; o[7] = its.geoFrame.n.y; o[8] = its.geoFrame.n.z;
+        o[9] = its.shFrame.n.x; o[10] = its.shFrame.n.y; o[11] = its.shFrame.n.z;
+        o[12] = its.shFrame.s.x; o[13] = its.shFrame.s.y; o[14] = its.shFrame.s.z;
+        o[15] = its.dpdu.x; o[16] = its.dpdu.y; o[17] = its.dpdu.z;
+    }
+    return 0;
+    REF_CATCH(-1)
+}
+
+// Defaults of the reference's objects created without any property: out = {film width, film height, reconstruction filter
+// radius, sampler sampleCount, area light samplingWeight}
+int ref_defaults(float *out) {
+    REF_TRY
+    ensureInit();
+    ref<Film> film = create<Film>(Properties("hdrfilm"));
+    film->configure();
+    ref<Sampler> sampler = create<Sampler>(Properties("independent"));
+    sampler->configure();
+    Properties pe("area");
+    pe.setSpectrum("radiance", Spectrum(1.0f));
+    ref<Emitter> em = create<Emitter>(pe);
+    out[0] = (float)film->getSize().x;
+    out[1] = (float)film->getSize().y;
+    out[2] = film->getReconstructionFilter()->getRadius();
+    out[3] = (float)sampler->getSampleCount();
+    out[4] = em->getSamplingWeight();
+    return 0;
     REF_CATCH(-1)
 }
 

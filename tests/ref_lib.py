@@ -60,6 +60,9 @@ def lib():
         L.ref_medium_sample.argtypes = [C.c_void_p, C.c_int, fp, C.c_size_t, fp, fp, fp]
         L.ref_phase.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_size_t, fp, fp, fp]
         L.ref_num_threads.restype = C.c_int
+        L.ref_sensor_rays_from_props.argtypes = [C.c_char_p, C.c_int, C.c_int, fp, C.c_size_t, fp]
+        L.ref_shape_from_props.argtypes = [C.c_char_p, C.c_char_p, fp, C.c_size_t, fp]
+        L.ref_defaults.argtypes = [fp]
         L.ref_bsdf_from_props.argtypes = [C.c_char_p, C.c_char_p, C.c_int, fp, fp, fp, C.c_size_t, fp, fp, fp, fp, fp, u32p]
         L.ref_mesh_load.restype = C.c_void_p
         L.ref_mesh_load.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, fp]
@@ -247,3 +250,35 @@ def bsdf_from_props(plugin, props, wi, wo, u, twosided=False):
                              _f(spdf), _u(fl)) != 0:
         raise RuntimeError("ref_bsdf_from_props: %s" % L.ref_last_error().decode())
     return dict(eval=ev, pdf=pdf, wo=swo, weight=w, spdf=spdf, flags=fl)
+
+
+def _props_text(props):
+    return ";".join("%s|%s|%s" % t for t in props).encode()
+
+
+def sensor_rays_from_props(props, width, height, pos):
+    """A reference `perspective` sensor from named properties only (kind x = transform ops, see ref_harness.cpp parseProps)."""
+    L = lib()
+    pos = np.ascontiguousarray(pos, np.float32)
+    rays = np.zeros((pos.shape[0], 8), np.float32)
+    if L.ref_sensor_rays_from_props(_props_text(props), width, height, _f(pos), pos.shape[0], _f(rays)) != 0:
+        raise RuntimeError("ref_sensor_rays_from_props: %s" % L.ref_last_error().decode())
+    return rays
+
+
+def shape_hits_from_props(plugin, props, rays):
+    """One reference shape plugin from named properties in a ShapeKDTree of its own: hit records like RefScene.intersect."""
+    L = lib()
+    rays = np.ascontiguousarray(rays, np.float32)
+    out = np.zeros((rays.shape[0], 18), np.float32)
+    if L.ref_shape_from_props(plugin.encode(), _props_text(props), _f(rays), rays.shape[0], _f(out)) != 0:
+        raise RuntimeError("ref_shape_from_props: %s" % L.ref_last_error().decode())
+    return dict(t=out[:, 0], p=out[:, 1:4], uv=out[:, 4:6], geo_n=out[:, 6:9], sh_n=out[:, 9:12], sh_s=out[:, 12:15], dpdu=out[:, 15:18])
+
+
+def defaults():
+    out = np.zeros(8, np.float32)
+    if lib().ref_defaults(_f(out)) != 0:
+        raise RuntimeError("ref_defaults: %s" % lib().ref_last_error().decode())
+    return dict(film_width=int(out[0]), film_height=int(out[1]), filter_radius=float(out[2]), sample_count=int(out[3]),
+                sampling_weight=float(out[4]))

@@ -71,3 +71,121 @@ def test_bsdf_properties_mean_what_the_reference_plugins_say(pkg, oracle, tmp_pa
     w = (np.abs(o["weight"][good] - r["weight"][good]) / np.maximum(np.abs(r["weight"][good]), 1e-3)).max(1)
     assert np.quantile(w, 0.99) <= 2e-4 and (w > 2e-2).mean() < 5e-3
     assert good.mean() > 0.3
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+#  transforms, sensor, shapes, object defaults
+# ---------------------------------------------------------------------------------------------------------------------
+def xf_xml(ops):
+    """'/'-separated ops of ref_harness.cpp's parseProps -> the <transform> children the scene handler reads"""
+    out = ""
+    for op in ops.split("/"):
+        v = op[2:].split(",")
+        if op[0] == "t":
+            out += '<translate x="%s" y="%s" z="%s"/>' % tuple(v)
+        elif op[0] == "r":
+            out += '<rotate x="%s" y="%s" z="%s" angle="%s"/>' % tuple(v)
+        elif op[0] == "s":
+            out += '<scale x="%s" y="%s" z="%s"/>' % tuple(v)
+        elif op[0] == "l":
+            out += '<lookat origin="%s" target="%s"%s/>' % (", ".join(v[:3]), ", ".join(v[3:6]), (' up="%s"' % ", ".join(v[6:9])) if len(v) >= 9 else "")
+        elif op[0] == "m":
+            out += '<matrix value="%s"/>' % " ".join(v)
+    return out
+
+
+def props_xml(props):
+    out = ""
+    for name, kind, value in props:
+        if kind == "x":
+            out += '<transform name="%s">%s</transform>' % (name, xf_xml(value))
+        elif kind == "c":
+            out += '<rgb name="%s" value="%s"/>' % (name, value)
+        else:
+            out += '<%s name="%s" value="%s"/>' % (XML_TAG[kind], name, value)
+    return out
+
+
+SENSORS = {
+    "defaults": [],
+    "lookat_fov": [("toWorld", "x", "l:0,1,3.9,0,1,0,0,1,0"), ("fov", "f", "39.3")],
+    "lookat_no_up": [("toWorld", "x", "l:1,2,3,0,0.5,-1"), ("fov", "f", "55"), ("fovAxis", "s", "y")],
+    "ops_in_order": [("toWorld", "x", "r:0,1,0,35/t:1,2,3/r:1,0,0,-10/s:1,1,1"), ("fov", "f", "70"), ("fovAxis", "s", "diagonal")],
+    "matrix_and_clip": [("toWorld", "x", "m:0,0,1,2,0,1,0,1,-1,0,0,3,0,0,0,1"), ("fov", "f", "30"), ("fovAxis", "s", "smaller"),
+                        ("nearClip", "f", "0.5"), ("farClip", "f", "50")],
+    "focal_length": [("focalLength", "s", "35mm"), ("fovAxis", "s", "larger")],
+}
+
+
+@pytest.mark.parametrize("case", sorted(SENSORS))
+def test_sensor_properties_and_transform_composition(pkg, oracle, tmp_path, case):
+    from b200pg import api
+
+    props = SENSORS[case]
+    W, H = 96, 40
+    xml = ('<scene version="0.6.0"><integrator type="progressivepath"/><sensor type="perspective">%s<sampler type="independent"/>'
+           '<film type="hdrfilm"><integer name="width" value="%d"/><integer name="height" value="%d"/></film></sensor>'
+           '<shape type="rectangle"><emitter type="area"><rgb name="radiance" value="1"/></emitter></shape></scene>') % (props_xml(props), W, H)
+    path = tmp_path / "s.xml"
+    path.write_text(xml)
+    sc = api.Scene.load_xml(str(path))
+    osc = OracleScene.from_desc(oracle, sc.desc, keep=sc)
+    pos = (np.random.RandomState(3).rand(1500, 2) * [W, H]).astype(np.float32)
+    np.testing.assert_allclose(osc.camera_rays(pos), ref_lib.sensor_rays_from_props(props, W, H, pos), rtol=2e-6, atol=3e-6)
+
+
+SHAPES = {
+    "rectangle_default": ("rectangle", []),
+    "rectangle_ops": ("rectangle", [("toWorld", "x", "s:2,0.5,1/r:1,0,0,-90/r:0,1,0,30/t:0.5,-1,1")]),
+    "rectangle_flipped": ("rectangle", [("toWorld", "x", "r:0,1,0,120/t:0,0.3,0"), ("flipNormals", "b", "true")]),
+    "cube_default": ("cube", []),
+    "cube_ops": ("cube", [("toWorld", "x", "s:0.3,0.6,0.2/r:0,1,0,17/r:1,0,0,5/t:-0.4,0.55,-0.35")]),
+    "cube_flipped": ("cube", [("toWorld", "x", "s:0.5,0.5,0.5"), ("flipNormals", "b", "true")]),
+}
+
+
+@pytest.mark.parametrize("case", sorted(SHAPES))
+def test_shape_plugins_and_their_transforms(pkg, oracle, tmp_path, case):
+    """rectangle.cpp / cube.cpp with toWorld built from XML ops and flipNormals: hit distance, position, geometric and shading
+    normal, the shading frame's tangent (per-triangle UV tangents on the cube) of chords through the shape."""
+    from b200pg import api
+
+    plugin, props = SHAPES[case]
+    xml = ('<scene version="0.6.0"><integrator type="progressivepath"/><sensor type="perspective"><sampler type="independent"/>'
+           '<film type="hdrfilm"><integer name="width" value="8"/><integer name="height" value="8"/></film></sensor>'
+           '<shape type="%s">%s<bsdf type="diffuse"/></shape>'
+           '<shape type="rectangle"><transform name="toWorld"><translate x="50" y="50" z="50"/></transform>'
+           '<emitter type="area"><rgb name="radiance" value="1"/></emitter></shape></scene>') % (plugin, props_xml(props))
+    path = tmp_path / "s.xml"
+    path.write_text(xml)
+    sc = api.Scene.load_xml(str(path))
+    osc = OracleScene.from_desc(oracle, sc.desc, keep=sc)
+    rng = np.random.RandomState(8)
+    a, b = rng.randn(6000, 3), rng.randn(6000, 3) * 0.4
+    a = 4.0 * a / np.linalg.norm(a, axis=1, keepdims=True)
+    d = b - a
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([a, np.zeros((6000, 1)), d, np.full((6000, 1), np.inf)], 1).astype(np.float32)
+    o, r = osc.intersect(rays), ref_lib.shape_hits_from_props(plugin, props, rays)
+    hit = np.isfinite(r["t"])
+    assert np.array_equal(np.isfinite(o["t"]), hit) and hit.mean() > 0.03
+    np.testing.assert_allclose(o["t"][hit], r["t"][hit], rtol=1e-5, atol=1e-5)
+    for k in ("p", "geo_n", "sh_n", "sh_s"):
+        assert np.abs(o[k][hit] - r[k][hit]).max() <= 3e-5, k
+
+
+def test_object_defaults(pkg, tmp_path):
+    """film.cpp:29-32 (768 x 576), the gaussian filter's radius (gaussian.cpp:33-37), independent.cpp's sampleCount, the area
+    light's samplingWeight -- as the reference's constructors set them without any property, against the reader's."""
+    from b200pg import api
+
+    path = tmp_path / "s.xml"
+    path.write_text('<scene version="0.6.0"><integrator type="progressivepath"/><sensor type="perspective"><sampler type="independent"/>'
+                    '<film type="hdrfilm"/></sensor><shape type="rectangle"><emitter type="area"><rgb name="radiance" value="1"/>'
+                    '</emitter></shape></scene>')
+    sc = api.Scene.load_xml(str(path))
+    d, r = sc.desc, ref_lib.defaults()
+    assert (d.film.width, d.film.height) == (r["film_width"], r["film_height"])
+    assert abs(4 * d.film.filter_stddev - r["filter_radius"]) < 1e-6
+    assert d.sample_count == r["sample_count"]
+    assert d.emitters[0].sampling_weight == r["sampling_weight"]
