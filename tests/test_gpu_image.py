@@ -1,7 +1,10 @@
 """Image-level parity at a BASELINE size (north star: "the converged render must match the reference's converged render within a
 stated relMSE tolerance"): config C1, Cornell box 512 x 512, maxDepth 8.
 
-Converged image `ref` = the oracle port's render, 16 384 spp (tests/golden/ref_c1.npz, tests/golden/make_reference.py).
+Converged image `ref` = 16 384 spp rendered by THE REFERENCE ITSELF (tests/golden/ref_c1.npz, written by
+`tests/golden/make_reference.py c1 16384 1024 6 reference`: ProgressiveMonteCarloIntegrator::render of the libraries compiled
+from /root/reference into oracle/_ref; 34 min on 6 cores. The oracle port's own 16 k-spp render of the same sample indices, the
+fixture before -- made before the port learnt the per-triangle UV tangents of the two boxes -- sits at relMSE 2.1e-6 from it).
 relMSE = mean over pixels of (I - R)^2 / (R^2 + 1e-3) on developed linear RGB with the 0.1 % highest-error pixels discarded
 (SURVEY.md 8(d)).
 
