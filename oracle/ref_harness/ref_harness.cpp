@@ -298,6 +298,7 @@ static ref<Medium> makeMedium(RefScene &rs, const B200pgMedium &m) {
     return med;
 }
 
+static bool g_noSensor = false;  // ref_scene_create_without_sensor: leave the camera to Scene::configure's fallback
 static RefScene *buildScene(const B200pgSceneDesc *d) {
     ensureInit();
     std::unique_ptr<RefScene> rs(new RefScene());
@@ -338,7 +339,7 @@ static RefScene *buildScene(const B200pgSceneDesc *d) {
     sensor->configure();
     rs->sensor = sensor;
     rs->film = film;
-    rs->scene->addChild(sensor);
+    if (!g_noSensor) rs->scene->addChild(sensor);
 
     uint32_t primOffset = 0;
     std::vector<int> emitterOfShape(d->n_shapes, -1);
@@ -584,6 +585,31 @@ void *ref_scene_create(const B200pgSceneDesc *desc) {
     REF_CATCH(nullptr)
 }
 void ref_scene_destroy(void *s) { delete (RefScene *)s; }
+
+// The shapes of the description WITHOUT its sensor: Scene::configure then adds its fallback camera (scene.cpp:272-305: 45 degree
+// perspective on the -z side of the shapes' bounding box, clip planes from its extents) with the default film. The handle's
+// sensor / film are that camera's afterwards; wh = film size.
+void *ref_scene_create_without_sensor(const B200pgSceneDesc *desc, int *wh) {
+    REF_TRY
+    g_noSensor = true;
+    RefScene *rs = nullptr;
+    try {
+        rs = buildScene(desc);
+    } catch (...) {
+        g_noSensor = false;
+        throw;
+    }
+    g_noSensor = false;
+    ensureBuilt(rs);
+    rs->sensor = rs->scene->getSensor();
+    rs->film = rs->sensor->getFilm();
+    rs->width = rs->film->getSize().x;
+    rs->height = rs->film->getSize().y;
+    wh[0] = rs->width;
+    wh[1] = rs->height;
+    return rs;
+    REF_CATCH(nullptr)
+}
 
 // ShapeKDTree statistics of the reference's own SAH build: out = {node count is not exported by the class; shapes, primitives}
 int ref_kd_info(void *s, uint64_t *out) {

@@ -60,6 +60,8 @@ def lib():
         L.ref_medium_sample.argtypes = [C.c_void_p, C.c_int, fp, C.c_size_t, fp, fp, fp]
         L.ref_phase.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_size_t, fp, fp, fp]
         L.ref_num_threads.restype = C.c_int
+        L.ref_scene_create_without_sensor.restype = C.c_void_p
+        L.ref_scene_create_without_sensor.argtypes = [C.POINTER(A.SceneDesc), C.POINTER(C.c_int)]
         L.ref_sensor_rays_from_props.argtypes = [C.c_char_p, C.c_int, C.c_int, fp, C.c_size_t, fp]
         L.ref_shape_from_props.argtypes = [C.c_char_p, C.c_char_p, fp, C.c_size_t, fp]
         L.ref_defaults.argtypes = [fp]
@@ -77,17 +79,21 @@ class RefScene:
     """A scene instantiated from reference objects (PluginManager + Properties) out of the same flat description the product
     and the oracle port consume."""
 
-    def __init__(self, builder=None, desc=None, keep=None, rtrans_reduce=None):
+    def __init__(self, builder=None, desc=None, keep=None, rtrans_reduce=None, without_sensor=False):
         self.L = lib()
         if desc is None:
             # the reduced rough-transmittance tables of the description are not read here: the reference's roughplastic loads
             # data/microfacet/*.dat itself (rtrans.h), so zeros do
             desc, keep = builder.desc(rtrans_reduce=rtrans_reduce or (lambda distr, eta, alpha: (np.zeros(100), 0.0, 0.0)))
         self.desc, self._keep = desc, keep
-        self.h = self.L.ref_scene_create(C.byref(desc))
+        if without_sensor:  # the camera is Scene::configure's fallback, the film its default
+            wh = (C.c_int * 2)()
+            self.h = self.L.ref_scene_create_without_sensor(C.byref(desc), wh)
+        else:
+            self.h = self.L.ref_scene_create(C.byref(desc))
         if not self.h:
             raise RuntimeError("ref_scene_create failed: %s" % self.L.ref_last_error().decode())
-        self.W, self.H = desc.film.width, desc.film.height
+        self.W, self.H = (wh[0], wh[1]) if without_sensor else (desc.film.width, desc.film.height)
 
     def __del__(self):
         try:

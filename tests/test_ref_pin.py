@@ -114,3 +114,24 @@ def test_kd_tree_hits_on_random_chords_of_a_mesh(pkg, oracle):
     assert np.abs(tuv[m, 0] - hit["t"][m]).max() <= 2e-5
     _, occ, _ = osc.trace(rays, shadow=True)
     assert ((occ != 0xFFFFFFFF) != rs.occluded(rays)).sum() <= 2
+
+
+def test_two_lights_with_different_sampling_weights(pkg, oracle):
+    """Scene::sampleEmitterDirect / pdfEmitterDirect over the discrete emitter distribution (scene.cpp:871-895, pmf.h:124-188: the
+    sample is re-used after the choice) with unequal samplingWeight."""
+    S = pkg.scenes
+    sb = S.SceneBuilder(24, 24, spp=1)
+    X = (1, 0, 0)
+    sb.rectangle([S.scale(50, 50, 1), S.rotate(X, -90.0)], bsdf=sb.diffuse((0.5, 0.5, 0.5)))
+    for (hx, hz), c, L, w in [((0.4, 0.3), (0.0, 1.2, 0.0), (4.0, 4.0, 4.0), 1.0), ((0.2, 0.6), (0.9, 2.0, -0.5), (1.0, 9.0, 2.0), 3.5)]:
+        sb.rectangle([S.scale(hx, hz, 1), S.rotate(X, 90.0), S.translate(*c)], bsdf=-1, radiance=L)
+        sb.emitters[-1]["weight"] = w
+    sb.set_camera((3.0, 1.0, 2.5), (0.2, 0.0, 0.1), (0, 1, 0), 30.0)
+    osc, rs = both(pkg, oracle, sb)
+    compare_li(pkg, osc, rs, params(pkg, max_depth=3), sb.width, sb.height, spp=32)
+    u = np.random.RandomState(6).rand(4000, 2).astype(np.float32)
+    refp, refn = np.array([0.2, 0.0, 0.1], np.float32), np.array([0, 1, 0], np.float32)
+    a, b = osc.emitter_sample(refp, refn, u), rs.emitter_sample(refp, refn, u)
+    np.testing.assert_allclose(a[0], b[0], atol=3e-6)            # directions: the same light was chosen for every sample
+    np.testing.assert_allclose(a[2], b[2], rtol=2e-5)            # pdf includes the choice probability
+    np.testing.assert_allclose(a[3], b[3], rtol=2e-5, atol=1e-6)

@@ -189,3 +189,22 @@ def test_object_defaults(pkg, tmp_path):
     assert abs(4 * d.film.filter_stddev - r["filter_radius"]) < 1e-6
     assert d.sample_count == r["sample_count"]
     assert d.emitters[0].sampling_weight == r["sampling_weight"]
+
+
+def test_fallback_camera_of_a_scene_without_a_sensor(pkg, oracle, tmp_path):
+    """Scene::configure (scene.cpp:272-305) run by the reference on the same shapes: the reader's fallback camera must produce
+    the rays of the camera the reference adds, on the film the reference defaults to."""
+    from b200pg import api
+
+    path = tmp_path / "min.xml"
+    path.write_text("""<scene version="0.6.0">
+      <shape type="rectangle"><transform name="toWorld"><scale x="2" y="1"/><translate x="1" y="3" z="5"/></transform></shape>
+      <shape type="cube"><transform name="toWorld"><scale value="0.5"/><translate x="0" y="3" z="8"/></transform>
+        <emitter type="area"><rgb name="radiance" value="2"/></emitter></shape>
+    </scene>""")
+    sc = api.Scene.load_xml(str(path))
+    osc = OracleScene.from_desc(oracle, sc.desc, keep=sc)
+    rs = ref_lib.RefScene(desc=sc.desc, keep=sc, without_sensor=True)
+    assert (rs.W, rs.H) == (sc.desc.film.width, sc.desc.film.height) == (768, 576)
+    pos = (np.random.RandomState(2).rand(2000, 2) * [768, 576]).astype(np.float32)
+    np.testing.assert_allclose(osc.camera_rays(pos), rs.camera_rays(pos), rtol=3e-6, atol=3e-6)
