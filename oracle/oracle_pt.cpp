@@ -219,6 +219,7 @@ struct Scene {
                 stack[exPt].p[axis] = splitVal;
             }
             if (cnt) cnt->nodes++;
+            if (cnt) cnt->leaves++;
             for (uint32_t entry = currNode->primStart(), last = currNode->primEnd(); entry != last; entry++) {
                 const uint32_t primIdx = kd.indices[entry];
                 if (cnt) cnt->indices++;
@@ -812,6 +813,30 @@ extern "C" {
 void *orc_scene_create(const B200pgSceneDesc *desc) { return buildScene(desc); }
 void orc_scene_destroy(void *s) { delete (Scene *)s; }
 
+// Depth-first dump of the kd-tree (test hook, same layout as the reference harness' ref_kd_dump): per node
+// {axis or -1 for a leaf, split or primitive count, depth}
+int orc_kd_dump(void *s, float *out, int max_nodes) {
+    Scene *sc = (Scene *)s;
+    std::vector<std::pair<const KDNode *, int>> stack;
+    stack.push_back(std::make_pair(sc->kd.nodes.data(), 0));
+    int n = 0;
+    while (!stack.empty() && n < max_nodes) {
+        const KDNode *node = stack.back().first;
+        int depth = stack.back().second;
+        stack.pop_back();
+        if (node->isLeaf()) {
+            out[3 * n] = -1; out[3 * n + 1] = (float)(node->primEnd() - node->primStart()); out[3 * n + 2] = (float)depth;
+        } else {
+            const KDNode *left = node + node->leftOffset();
+            out[3 * n] = (float)node->axis(); out[3 * n + 1] = node->split; out[3 * n + 2] = (float)depth;
+            stack.push_back(std::make_pair(left + 1, depth + 1));
+            stack.push_back(std::make_pair(left, depth + 1));
+        }
+        ++n;
+    }
+    return n;
+}
+
 int orc_kd_info(void *s, uint64_t *out /* nodes, indices, prims */) {
     Scene *sc = (Scene *)s;
     out[0] = sc->kd.nodes.size();
@@ -820,13 +845,13 @@ int orc_kd_info(void *s, uint64_t *out /* nodes, indices, prims */) {
     return 0;
 }
 
-// rays n*8 (o, mint, d, maxt); out tuv n*3, prim n (global prim id), counters[3] summed (may be NULL)
+// rays n*8 (o, mint, d, maxt); out tuv n*3, prim n (global prim id), counters[4] summed (may be NULL)
 int orc_trace(void *s, const float *rays, size_t n, int shadow, float *tuv, uint32_t *prim, uint64_t *counters,
               int nthreads) {
     Scene *sc = (Scene *)s;
     if (nthreads <= 0) nthreads = omp_get_max_threads();
-    uint64_t c0 = 0, c1 = 0, c2 = 0;
-#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 4096) reduction(+ : c0, c1, c2)
+    uint64_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 4096) reduction(+ : c0, c1, c2, c3)
     for (long long i = 0; i < (long long)n; ++i) {
         const float *r = rays + 8 * i;
         Ray ray(Vec3(r[0], r[1], r[2]), Vec3(r[4], r[5], r[6]), r[3], r[7]);
@@ -853,11 +878,13 @@ int orc_trace(void *s, const float *rays, size_t n, int shadow, float *tuv, uint
         c0 += st.trav.nodes;
         c1 += st.trav.indices;
         c2 += st.trav.prims;
+        c3 += st.trav.leaves;
     }
-    if (counters) {
+    if (counters) {  // 4 words: nodes visited (inner + leaf), index entries read, primitive tests, leaf visits
         counters[0] = c0;
         counters[1] = c1;
         counters[2] = c2;
+        counters[3] = c3;
     }
     return 0;
 }

@@ -252,6 +252,7 @@ struct KDNode {
 
 struct TraversalCounters {
     uint64_t nodes = 0, indices = 0, prims = 0;
+    uint64_t leaves = 0;  // leaf visits among `nodes` (the reference's numTraversals counts the inner ones only, sahkdtree3.h:357)
 };
 
 class KDTree {

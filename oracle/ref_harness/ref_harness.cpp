@@ -1114,6 +1114,67 @@ int ref_defaults(float *out) {
     REF_CATCH(-1)
 }
 
+// The reference's COUNTING traversal (rayIntersectHavranCollectStatistics, sahkdtree3.h:330-429: the variant it uses to report
+// kd-tree cost, without mailboxing) on the scene's kd-tree, with the ray interval set up as ShapeKDTree::rayIntersect does
+// (skdtree.cpp:112-142). The method is protected in SAHKDTree3D, hence the accessor subclass. Sums over the n rays:
+// counters = {inner nodes traversed (numTraversals), leaf index entries visited (numIntersections), rays that hit}.
+struct KDProbe : public ShapeKDTree {
+    void count(const Ray &ray, uint64_t *c) const {
+        uint8_t temp[MTS_KD_INTERSECTION_TEMP];
+        Float mint, maxt, t = std::numeric_limits<Float>::infinity();
+        if (!m_aabb.rayIntersect(ray, mint, maxt)) return;
+        Float rayMinT = ray.mint;
+        if (rayMinT == Epsilon) rayMinT *= std::max(std::max(std::max(std::abs(ray.o.x), std::abs(ray.o.y)), std::abs(ray.o.z)), Epsilon);
+        if (rayMinT > mint) mint = rayMinT;
+        if (ray.maxt < maxt) maxt = ray.maxt;
+        if (!(maxt > mint)) return;
+        RayStatistics st = rayIntersectHavranCollectStatistics(ray, mint, maxt, t, temp);
+        c[0] += st.numTraversals;
+        c[1] += st.numIntersections;
+        c[2] += st.foundIntersection ? 1 : 0;
+    }
+};
+int ref_kd_count(void *s, const float *rays, size_t n, uint64_t *counters) {
+    REF_TRY
+    RefScene *rs = (RefScene *)s;
+    ensureBuilt(rs);
+    const KDProbe *probe = static_cast<const KDProbe *>(rs->scene->getKDTree());
+    counters[0] = counters[1] = counters[2] = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const float *r = rays + 8 * i;
+        probe->count(Ray(Point(r[0], r[1], r[2]), Vector(r[4], r[5], r[6]), r[3], r[7], 0.0f), counters);
+    }
+    return 0;
+    REF_CATCH(-1)
+}
+
+// Depth-first dump of the reference's kd-tree: per node 3 floats {axis (or -1 for a leaf), split (or primitive count), depth}
+int ref_kd_dump(void *s, float *out, int max_nodes) {
+    REF_TRY
+    RefScene *rs = (RefScene *)s;
+    ensureBuilt(rs);
+    const ShapeKDTree *tree = rs->scene->getKDTree();
+    typedef ShapeKDTree::KDNode Node;
+    std::vector<std::pair<const Node *, int>> stack;
+    stack.push_back(std::make_pair(tree->getRoot(), 0));
+    int n = 0;
+    while (!stack.empty() && n < max_nodes) {
+        const Node *node = stack.back().first;
+        int depth = stack.back().second;
+        stack.pop_back();
+        if (node->isLeaf()) {
+            out[3 * n] = -1; out[3 * n + 1] = (float)(node->getPrimEnd() - node->getPrimStart()); out[3 * n + 2] = (float)depth;
+        } else {
+            out[3 * n] = (float)node->getAxis(); out[3 * n + 1] = node->getSplit(); out[3 * n + 2] = (float)depth;
+            stack.push_back(std::make_pair(node->getRight(), depth + 1));
+            stack.push_back(std::make_pair(node->getLeft(), depth + 1));
+        }
+        ++n;
+    }
+    return n;
+    REF_CATCH(-1)
+}
+
 int ref_num_threads() { return omp_get_max_threads(); }
 
 }  // extern "C"

@@ -253,9 +253,9 @@ class OracleScene:
         n = rays.shape[0]
         tuv = np.zeros((n, 3), np.float32)
         prim = np.zeros(n, np.uint32)
-        cnt = (C.c_uint64 * 3)()
+        cnt = (C.c_uint64 * 4)()
         self.L.orc_trace(self.h, _f(rays), n, int(shadow), _f(tuv), _u(prim), cnt, nthreads)
-        return tuv, prim, dict(nodes=cnt[0], indices=cnt[1], prims=cnt[2])
+        return tuv, prim, dict(nodes=cnt[0], indices=cnt[1], prims=cnt[2], leaves=cnt[3])
 
     def intersect(self, rays):
         """Full intersection records: dict of t, p, uv, geo_n, sh_n, sh_s, dpdu (skdtree.h:343-428)."""

@@ -60,6 +60,7 @@ def lib():
         L.ref_medium_sample.argtypes = [C.c_void_p, C.c_int, fp, C.c_size_t, fp, fp, fp]
         L.ref_phase.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_size_t, fp, fp, fp]
         L.ref_num_threads.restype = C.c_int
+        L.ref_kd_count.argtypes = [C.c_void_p, fp, C.c_size_t, C.POINTER(C.c_uint64)]
         L.ref_scene_create_without_sensor.restype = C.c_void_p
         L.ref_scene_create_without_sensor.argtypes = [C.POINTER(A.SceneDesc), C.POINTER(C.c_int)]
         L.ref_sensor_rays_from_props.argtypes = [C.c_char_p, C.c_int, C.c_int, fp, C.c_size_t, fp]
@@ -128,6 +129,14 @@ class RefScene:
         prim = np.zeros(rays.shape[0], np.uint32)
         self._ok(self.L.ref_intersect(self.h, _f(rays), rays.shape[0], 1, None, _u(prim), nthreads))
         return prim == 0
+
+    def kd_count(self, rays):
+        """The reference's counting traversal (rayIntersectHavranCollectStatistics) summed over the rays: inner nodes
+        traversed, leaf index entries visited, rays that hit."""
+        rays = np.ascontiguousarray(rays, np.float32)
+        c = (C.c_uint64 * 3)()
+        self._ok(self.L.ref_kd_count(self.h, _f(rays), rays.shape[0], c))
+        return dict(inner=c[0], indices=c[1], hits=c[2])
 
     def camera_rays(self, pos):
         pos = np.ascontiguousarray(pos, np.float32)
