@@ -1157,6 +1157,11 @@ bool HostScene::compile(std::string &err) {
     mediumRecs.clear();
     densityPool.clear();
     for (auto &m : media) {
+        for (int i = 0; i < 16; ++i)
+            if (m.to_world[i] != ((i % 5 == 0) ? 1.0f : 0.0f)) {  // b200pg.h: B200pgMedium::to_world, identity supported
+                err = "medium: a non-identity volume toWorld is not supported";
+                return false;
+            }
         MediumRecord r;
         std::memset(&r, 0, sizeof(r));
         r.method = m.method;

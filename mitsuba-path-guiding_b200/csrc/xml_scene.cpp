@@ -596,6 +596,17 @@ struct Loader {
                     if (fn.empty()) fail("gridvolume: missing filename");
                     if (fn[0] != '/') fn = baseDir + "/" + fn;
                     readVol(fn, m);
+                    // gridvolume.cpp:110-117: `toWorld` places the grid, `min` / `max` override the file's box. The device keeps an
+                    // axis-aligned worldToGrid (scale + offset), so anything else is refused rather than silently dropped.
+                    const M4 vw = getTransform(*c, "toWorld");
+                    const M4 id = identity();
+                    for (int i = 0; i < 16; ++i) {
+                        m.to_world[i] = vw.m[i];
+                        if (vw.m[i] != id.m[i])
+                            fail("gridvolume: a non-identity \"toWorld\" is not supported on this path (move the density box with the "
+                                 "file's bounding box instead)");
+                    }
+                    if (prop(*c, "min") || prop(*c, "max")) fail("gridvolume: \"min\" / \"max\" overrides are not supported on this path");
                     haveDensity = true;
                 } else if (role == "albedo") {
                     if (vt != "constvolume") fail("albedo volume plugin \"" + vt + "\" is not supported (need constvolume)");

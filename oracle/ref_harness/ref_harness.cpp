@@ -1175,6 +1175,36 @@ int ref_kd_dump(void *s, float *out, int max_nodes) {
     REF_CATCH(-1)
 }
 
+// A `heterogeneous` medium the way the scene loader would assemble it from XML: plugin + named properties for the medium, its
+// `density` gridvolume (reads the .vol FILE named in its properties -- the reference's own reader, gridvolume.cpp:218-290), its
+// `albedo` constvolume and its phase function. Returns a scene handle whose medium 0 is that medium (for ref_grid_lookup,
+// ref_medium_sample, ref_phase); seed for the replay stream.
+void *ref_medium_from_props(const char *medium_props, const char *density_props, const char *albedo_props, const char *phase_plugin,
+                            const char *phase_props, uint64_t seed) {
+    REF_TRY
+    ensureInit();
+    std::unique_ptr<RefScene> rs(new RefScene());
+    rs->seed = seed;
+    rs->width = 1 << 20;
+    ref<Medium> med = create<Medium>(parseProps("heterogeneous", medium_props));
+    ref<VolumeDataSource> dens = create<VolumeDataSource>(parseProps("gridvolume", density_props));
+    dens->configure();
+    ref<VolumeDataSource> alb = create<VolumeDataSource>(parseProps("constvolume", albedo_props));
+    alb->configure();
+    med->addChild("density", dens);
+    med->addChild("albedo", alb);
+    if (phase_plugin && *phase_plugin) {
+        ref<PhaseFunction> phase = create<PhaseFunction>(parseProps(phase_plugin, phase_props));
+        phase->configure();
+        med->addChild(phase);
+    }
+    med->configure();
+    rs->media.push_back(med);
+    rs->densities.push_back(dens);
+    return rs.release();
+    REF_CATCH(nullptr)
+}
+
 int ref_num_threads() { return omp_get_max_threads(); }
 
 }  // extern "C"

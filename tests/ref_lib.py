@@ -60,6 +60,8 @@ def lib():
         L.ref_medium_sample.argtypes = [C.c_void_p, C.c_int, fp, C.c_size_t, fp, fp, fp]
         L.ref_phase.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_size_t, fp, fp, fp]
         L.ref_num_threads.restype = C.c_int
+        L.ref_medium_from_props.restype = C.c_void_p
+        L.ref_medium_from_props.argtypes = [C.c_char_p] * 5 + [C.c_uint64]
         L.ref_kd_count.argtypes = [C.c_void_p, fp, C.c_size_t, C.POINTER(C.c_uint64)]
         L.ref_scene_create_without_sensor.restype = C.c_void_p
         L.ref_scene_create_without_sensor.argtypes = [C.POINTER(A.SceneDesc), C.POINTER(C.c_int)]
@@ -297,3 +299,17 @@ def defaults():
         raise RuntimeError("ref_defaults: %s" % lib().ref_last_error().decode())
     return dict(film_width=int(out[0]), film_height=int(out[1]), filter_radius=float(out[2]), sample_count=int(out[3]),
                 sampling_weight=float(out[4]))
+
+
+def medium_from_props(medium, density, albedo, phase_plugin, phase, seed):
+    """A reference `heterogeneous` medium assembled from plugin names + named properties (the density gridvolume reads the .vol
+    file itself). Returns a RefScene-like handle with grid_lookup / medium_sample / phase on medium 0."""
+    L = lib()
+    self = RefScene.__new__(RefScene)
+    self.L, self.desc, self._keep = L, None, None
+    self.h = L.ref_medium_from_props(_props_text(medium), _props_text(density), _props_text(albedo), (phase_plugin or "").encode(),
+                                     _props_text(phase), seed)
+    if not self.h:
+        raise RuntimeError("ref_medium_from_props: %s" % L.ref_last_error().decode())
+    self.W = self.H = 0
+    return self

@@ -208,3 +208,86 @@ def test_fallback_camera_of_a_scene_without_a_sensor(pkg, oracle, tmp_path):
     assert (rs.W, rs.H) == (sc.desc.film.width, sc.desc.film.height) == (768, 576)
     pos = (np.random.RandomState(2).rand(2000, 2) * [768, 576]).astype(np.float32)
     np.testing.assert_allclose(osc.camera_rays(pos), rs.camera_rays(pos), rtol=3e-6, atol=3e-6)
+
+
+MEDIA = {
+    # (medium properties, extra gridvolume properties, phase plugin, phase properties)
+    "defaults": ([], [], "", []),                                                     # woodcock, scale 1, isotropic phase
+    "woodcock_hg": ([("method", "s", "woodcock"), ("scale", "f", "20")], [], "hg", [("g", "f", "0.7")]),
+    "hg_default_g": ([("scale", "f", "8")], [], "hg", []),
+    "simpson_stepsize": ([("method", "s", "simpson"), ("scale", "f", "12"), ("stepSize", "f", "0.02")], [], "isotropic", []),
+}
+
+
+@pytest.mark.parametrize("case", sorted(MEDIA))
+def test_heterogeneous_medium_from_xml_and_the_vol_file(pkg, oracle, tmp_path, case):
+    """<medium type="heterogeneous"> with a gridvolume read from a .vol file (gridvolume.cpp:218-290), through the product's
+    XML reader and through the reference's own plugins: density look-ups, free-flight distances (same stream), transmittance,
+    phase function -- defaults, both tracking methods, an explicit stepSize, a volume-to-world transform."""
+    from b200pg import api
+
+    mprops, dprops, phase_plugin, pprops = MEDIA[case]
+    S = pkg.scenes
+    dens = S.fbm_density(res=24, seed=7)
+    vol = tmp_path / "d.vol"
+    S.write_vol(str(vol), dens, (-0.5, 0.0, -0.5), (0.5, 1.0, 0.5))
+    phase_xml = ('<phase type="%s">%s</phase>' % (phase_plugin, props_xml(pprops))) if phase_plugin else ""
+    xml = ('<scene version="0.6.0"><integrator type="progressivevolpath"/>'
+           '<medium type="heterogeneous" id="m">%s<volume name="density" type="gridvolume"><string name="filename" value="%s"/>%s</volume>'
+           '<volume name="albedo" type="constvolume"><spectrum name="value" value="0.9"/></volume>%s</medium>'
+           '<sensor type="perspective"><sampler type="independent"/><film type="hdrfilm"><integer name="width" value="8"/>'
+           '<integer name="height" value="8"/></film></sensor>'
+           '<shape type="cube"><transform name="toWorld"><scale value="3"/></transform><ref name="interior" id="m"/></shape>'
+           '<shape type="rectangle"><transform name="toWorld"><translate x="0" y="0" z="9"/></transform>'
+           '<emitter type="area"><rgb name="radiance" value="1"/></emitter></shape></scene>') % (
+               props_xml(mprops), vol, props_xml(dprops), phase_xml)
+    path = tmp_path / "s.xml"
+    path.write_text(xml)
+    sc = api.Scene.load_xml(str(path))
+    osc = OracleScene.from_desc(oracle, sc.desc, keep=sc)
+    rm = ref_lib.medium_from_props(mprops, [("filename", "s", str(vol))] + dprops, [("value", "c", "0.9,0.9,0.9")], phase_plugin, pprops,
+                                   sc.desc.seed)
+    rng = np.random.RandomState(4)
+    pts = (rng.rand(4000, 3) * [2.0, 1.6, 2.0] - [1.0, 0.3, 1.0]).astype(np.float32)
+    np.testing.assert_allclose(osc.grid_lookup(0, pts), rm.grid_lookup(0, pts), rtol=1e-5, atol=2e-6)
+    # segments strictly inside the grid's box (a start ON the boundary is a knife edge in the reference itself, DESIGN.md 2)
+    lo, hi = np.array(sc.desc.media[0].aabb_min[:]), np.array(sc.desc.media[0].aabb_max[:])
+    a = lo + (hi - lo) * (0.05 + 0.9 * rng.rand(2000, 3))
+    b = lo + (hi - lo) * (0.05 + 0.9 * rng.rand(2000, 3))
+    d = b - a
+    L = np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([a, np.zeros((2000, 1)), d / L, L * (0.3 + rng.rand(2000, 1))], 1).astype(np.float32)
+    rays[:, 7] = np.minimum(rays[:, 7], (L[:, 0] * 0.999).astype(np.float32))
+    to, tro, _, _ = osc.medium_sample(0, rays)
+    tr, _, trr = rm.medium_sample(0, rays)
+    assert np.array_equal(np.isfinite(to), np.isfinite(tr)) and 0.05 < np.isfinite(tr).mean() < 0.98
+    m = np.isfinite(tr)
+    np.testing.assert_allclose(to[m], tr[m], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(tro, trr, rtol=2e-5, atol=2e-6)
+    wi, wo, u = random_dirs(rng, 1000), random_dirs(rng, 1000), rng.rand(1000, 2).astype(np.float32)
+    eo, er = osc.phase(0, wi, wo, u), rm.phase(0, wi, wo, u)
+    np.testing.assert_allclose(eo[0], er[0], rtol=3e-5)
+    np.testing.assert_allclose(eo[1], er[1], atol=1e-4)  # strongly forward hg: the inversion amplifies rounding
+
+
+def test_volume_transforms_are_refused_not_dropped(pkg, tmp_path):
+    """gridvolume.cpp:110-117 lets `toWorld` / `min` / `max` place the grid. The device keeps an axis-aligned worldToGrid, so the
+    reader refuses them by name (a silently ignored transform renders a different scene -- which this comparison showed it did)."""
+    from b200pg import api
+
+    S = pkg.scenes
+    vol = tmp_path / "d.vol"
+    S.write_vol(str(vol), S.fbm_density(res=8, seed=7), (-0.5, 0.0, -0.5), (0.5, 1.0, 0.5))
+    xml = ('<scene version="0.6.0"><integrator type="progressivevolpath"/><medium type="heterogeneous" id="m">'
+           '<volume name="density" type="gridvolume"><string name="filename" value="%s"/>%s</volume>'
+           '<volume name="albedo" type="constvolume"><spectrum name="value" value="0.9"/></volume></medium>'
+           '<shape type="cube"><ref name="interior" id="m"/></shape>'
+           '<shape type="rectangle"><emitter type="area"><rgb name="radiance" value="1"/></emitter></shape></scene>')
+    for extra, word in (('<transform name="toWorld"><scale x="1.5" y="0.8" z="1.2"/></transform>', "toWorld"),
+                        ('<point name="min" x="0" y="0" z="0"/>', "min")):
+        path = tmp_path / "s.xml"
+        path.write_text(xml % (vol, extra))
+        with pytest.raises(api.B200pgError, match=word):
+            api.Scene.load_xml(str(path))
+    path.write_text(xml % (vol, '<transform name="toWorld"><translate x="0" y="0" z="0"/></transform>'))  # identity is fine
+    api.Scene.load_xml(str(path)).close()
