@@ -2,9 +2,11 @@
 """bench.py -- headline benchmark of the B200-native path tracer (driver contract in the task prompt).
 
   python bench.py --gpus N --steps K --warmup W            this repo's CUDA path
-  python bench.py --impl reference --steps K --warmup W    the reference algorithm on the host cores
-                                                           (oracle restatement; the reference binary cannot
-                                                           be built here)
+  python bench.py --impl reference --steps K --warmup W    the reference algorithm on the host cores: the guided training
+                                                           iteration with the oracle port (the snapshot has no guided
+                                                           integrator to run), plus `reference_unguided`: the reference
+                                                           ITSELF (oracle/_ref, compiled from its sources) rendering the
+                                                           scene with its stock progressivepath next to the port
 
 A "step" = one guiding TRAINING ITERATION of the guided path tracer: one progression (``--spp-per-step`` samples per
 pixel, recording path-vertex samples and sampling from the current field) over the whole image, followed by the
@@ -105,7 +107,7 @@ class ClockSampler(threading.Thread):
 
 class CpuGuidedStep:
     """The same training iteration as the GPU arm, on the host cores, with the oracle (a CPU restatement of the reference
-    algorithm; the reference binary cannot be built here): one progression over a band of rows that records
+    algorithm, pinned sample by sample to the compiled reference; the reference itself has no guided integrator): one progression over a band of rows that records
     path-vertex samples and samples from the current field, then the training update (binning, EM iterations, split)."""
 
     def __init__(self, pkg, sb, p, guided, em_iters, cores):

@@ -6,10 +6,14 @@
 // perspective camera, Gaussian-splat film and ProgressiveMIPathTracer::Li, restated from the
 // reference files cited at each function (paths relative to the reference root).
 //
-// PARITY PINNING: the reference cannot be built here and ships no golden
-// vectors for hit records / film values; the restatement is pinned through the properties the
-// reference's own tests check (test_chisquare: sample<->pdf<->eval consistency, see
-// tests/test_oracle_bsdf.py) and through brute-force cross-checks (tests/test_oracle_kd.py).
+// PARITY PINNING: the restatement is pinned SAMPLE BY SAMPLE to the reference's own code -- its libraries and the plugins
+// of this path compiled from /root/reference into oracle/_ref by oracle/Makefile.ref and driven through
+// oracle/ref_harness/ref_harness.cpp with a replay sampler (tests/test_upstream.py + tests/golden/upstream.npz,
+// tests/test_ref_pin.py, tests/test_ref_xml_semantics.py, tests/test_ref_meshes.py; DESIGN.md "Reference build status") --
+// and, as before, through the properties the reference's own tests check (test_chisquare: sample<->pdf<->eval consistency,
+// tests/test_oracle_bsdf.py; test_kd / test_dgeom known answers, tests/test_oracle_kd_film.py) and closed forms
+// (tests/test_oracle_transport.py). The guiding part (oracle_guiding.h) has no reference counterpart in the snapshot:
+// parity unpinned there, and it says so.
 #include <omp.h>
 
 #include <atomic>

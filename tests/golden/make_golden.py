@@ -4,10 +4,11 @@ What they are: REGRESSION vectors of this repo's CPU oracle (oracle/, the restat
 seeded inputs -- inputs and outputs side by side -- so that (i) a change of the oracle shows up as a diff against committed
 numbers (tests/test_golden.py, CPU) and (ii) the CUDA path can be checked on the GPU box against numbers that were fixed
 when the oracle was pinned (tests/test_golden.py, -m gpu).
-What they are NOT: outputs of the reference binary. The reference cannot be built in this image (DESIGN.md "Reference build
-status"); the reference's own known answers that exist for this path are restated in tests/test_oracle_kd_film.py
-(test_kd.cpp:34-83 clipping vectors), tests/test_oracle_bsdf.py (test_chisquare / test_bsdf.xml) and
-tests/test_oracle_medium.py.
+What they are NOT: outputs of the reference. Those -- for the very same inputs -- are tests/golden/upstream.npz, written by
+make_upstream.py from the reference's own code compiled into oracle/_ref (DESIGN.md "Reference build status"), and
+tests/test_upstream.py holds these fixtures and the CUDA path to them. The reference's own known answers for this path are
+restated in tests/test_oracle_kd_film.py (test_kd.cpp:34-83 clipping vectors, test_dgeom.cpp), tests/test_oracle_bsdf.py
+(test_chisquare / test_bsdf.xml) and tests/test_oracle_medium.py.
 
 usage: python tests/golden/make_golden.py        (needs only the oracle: no GPU, no /root/reference)
 """
