@@ -68,8 +68,11 @@ def test_plugin_film_handoff_into_the_reference_film(pkg):
     assert np.array_equal(rs.plugin_put_film(rgbaw), rgbaw)
 
 
-@pytest.mark.gpu
-def test_reference_render_loop_with_the_gpu_integrator(pkg, tmp_path):
+def _gpu_body(tmp_path):
+    """Runs in a child process (see the test below): Scene::render of the reference with the GPU integrator plugged in."""
+    from conftest import load_package
+
+    pkg = load_package()
     from b200pg import api
 
     sb, xml = _scene(pkg, tmp_path)
@@ -94,3 +97,23 @@ def test_reference_render_loop_with_the_gpu_integrator(pkg, tmp_path):
     gfilm, _ = rs.render_plugin(pg, "b200guidedpath", xml)        # the guided integrator through the same door
     dev = gfilm[..., :3] / np.maximum(gfilm[..., 4:5], 1e-20)
     assert np.isfinite(dev).all() and abs(dev.mean() - dev_r.mean()) < 0.2 * dev_r.mean()  # 2 - 4 spp at 64 x 64: noise
+    print("plugin ok: film through the reference's render loop == direct render; mean %.4f vs the reference's own %.4f; guided %.4f"
+          % (dev_g.mean(), dev_r.mean(), dev.mean()))
+
+
+@pytest.mark.gpu
+def test_reference_render_loop_with_the_gpu_integrator(tmp_path):
+    """In a child process: the reference's thread / scheduler singletons and the CUDA runtime share it, and whatever happens
+    there must show up as one failed test, not as the end of the test run."""
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "plugin ok" in r.stdout, (r.returncode, r.stdout[-2000:], r.stderr[-4000:])
+
+
+if __name__ == "__main__":
+    import pathlib
+    import sys
+
+    _gpu_body(pathlib.Path(sys.argv[1]))
