@@ -12,6 +12,9 @@
 #include "../include/b200pg.h"
 #include "oracle_math.h"
 
+// GCC: keep a function free of fused multiply-add contraction (the translation unit is built with -march=x86-64-v3)
+#define ORC_NO_CONTRACT __attribute__((optimize("fp-contract=off")))
+
 namespace orc {
 
 struct Ray {
@@ -285,9 +288,14 @@ public:
         nodes.clear();
         indices.clear();
         nodes.push_back(KDNode());
-        std::vector<Item> all(n);
-        for (uint32_t i = 0; i < n; ++i) all[i] = Item{i, primBoxes[i]};
-        buildNode(0, all, aabb, 0, 0, false);
+        primBoxesPtr = &primBoxes;
+        // more primitives than the exact method takes: the reference builds in parallel on a multi-core host (gkdtree.h:980-981,
+        // 1036-1037), and a subtree handed to a worker is never torn down again by its min-max ancestors (:1751-1752)
+        parallelBuild = n > exactPrimThreshold;
+        std::vector<uint32_t> all(n);
+        for (uint32_t i = 0; i < n; ++i) all[i] = i;
+        buildMinMax(0, all, aabb, aabb, 1, 0);  // depth 1 = root (gkdtree.h:1050)
+        primBoxesPtr = nullptr;
         // enlarge after the build (gkdtree.h:1214-1219)
         const Float eps = 1e-3f;
         aabb.min = aabb.min - ((aabb.max - aabb.min) * eps + Vec3(eps));
@@ -296,9 +304,12 @@ public:
     }
 
     uint64_t prunedPrims = 0;  // references removed by clipping ("perfect splits")
+    uint64_t retractedSplits = 0;  // splits torn up again because the subtree did not beat the leaf cost
 
 private:
     ClipFn clipFn;
+    const std::vector<AABB> *primBoxesPtr = nullptr;
+    bool parallelBuild = false;
     struct Item {
         uint32_t prim;
         AABB box;  // bounds of the primitive inside the node it currently belongs to
@@ -320,31 +331,197 @@ private:
         return b.min.x <= b.max.x && b.min.y <= b.max.y && b.min.z <= b.max.z && b.surfaceArea() > 0;
     }
 
-    inline Float sahCost(const AABB &box, int axis, Float split, uint32_t nL, uint32_t nR) const {
-        // SurfaceAreaHeuristic3 (sahkdtree3.h:39-84): probabilities = SA(child)/SA(node)
+    // SurfaceAreaHeuristic3 (sahkdtree3.h:39-84): probabilities = SA(child) / SA(node), in the reference's order of operations
+    // (m_temp0 = (e1 e2) temp, m_temp1 = (e1 + e2) temp, p = m_temp0 + m_temp1 * width) and without contraction into fused
+    // multiply-adds (the reference build has none): on a regular mesh whole families of candidate planes have the same cost in
+    // exact arithmetic, and which one wins the strict `<` below is decided by the last bit. With this the port's tree IS the
+    // reference's tree on every scene compared (tests/test_ref_pin.py::test_kd_tree_build_and_traversal_counters).
+    ORC_NO_CONTRACT inline Float sahCost(const AABB &box, int axis, Float split, uint32_t nL, uint32_t nR) const {
         Vec3 d = box.max - box.min;
         int a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
-        Float invSA = 1.0f / (d[0] * d[1] + d[1] * d[2] + d[0] * d[2]);
-        Float cross = d[a1] * d[a2], perim = d[a1] + d[a2];
-        Float pL = (cross + (split - box.min[axis]) * perim) * invSA;
-        Float pR = (cross + (box.max[axis] - split) * perim) * invSA;
-        Float cost = traversalCost + queryCost * (pL * nL + pR * nR);
+        const Float temp = 1.0f / (d[0] * d[1] + d[1] * d[2] + d[0] * d[2]);
+        const Float temp0 = (d[a1] * d[a2]) * temp, temp1 = (d[a1] + d[a2]) * temp;
+        const Float pL = temp0 + temp1 * (split - box.min[axis]);
+        const Float pR = temp0 + temp1 * (box.max[axis] - split);
+        Float cost = traversalCost + queryCost * (pL * (Float)nL + pR * (Float)nR);
         if (nL == 0 || nR == 0) cost *= emptySpaceBonus;  // gkdtree.h:2039-2041
         return cost;
     }
 
-    void buildNode(uint32_t nodeIdx, std::vector<Item> &prims, const AABB &box, int depth, uint32_t badRefines, bool exactStage) {
+    void makeLeafIds(uint32_t nodeIdx, const std::vector<uint32_t> &ids) {
+        KDNode &nd = nodes[nodeIdx];
+        nd.a = 0x80000000u | (uint32_t)indices.size();
+        indices.insert(indices.end(), ids.begin(), ids.end());
+        nd.end = (uint32_t)indices.size();
+    }
+
+    // transitionToNLogN (gkdtree.h:1729-1761): clip the primitives to the node, continue with the exact builder
+    Float transition(uint32_t nodeIdx, std::vector<uint32_t> &ids, const AABB &nodeBox, int depth, uint32_t badRefines) {
+        std::vector<Item> items(ids.size());
+        for (size_t i = 0; i < ids.size(); ++i) items[i] = Item{ids[i], (*primBoxesPtr)[ids[i]]};
+        std::vector<uint32_t>().swap(ids);
+        const Float cost = buildNode(nodeIdx, items, nodeBox, depth, badRefines, false);
+        return parallelBuild ? -std::numeric_limits<Float>::infinity() : cost;
+    }
+
+    // buildTreeMinMax (gkdtree.h:1792-1925) with MinMaxBins (:2412-2600): min-max binning over the TIGHT bounds of the node on the
+    // primitives' full boxes; the partition goes by bin index, the children's tight bounds are the unions of their primitives'
+    // boxes cut at the split plane. Arithmetic in the reference's order and without contraction (see sahCost).
+    ORC_NO_CONTRACT Float buildMinMax(uint32_t nodeIdx, std::vector<uint32_t> &ids, const AABB &nodeBox, const AABB &tightBox, int depth,
+                                      uint32_t badRefines) {
+        const uint32_t n = (uint32_t)ids.size();
+        const Float leafCost = n * queryCost;
+        if (n <= stopPrims || depth >= maxDepth) {
+            makeLeafIds(nodeIdx, ids);
+            return leafCost;
+        }
+        if (n <= exactPrimThreshold) return transition(nodeIdx, ids, nodeBox, depth, badRefines);
+        const std::vector<AABB> &pb = *primBoxesPtr;
+        const int B = (int)minMaxBins;
+        float mn[3], binSize[3], invBinSize[3];
+        for (int a = 0; a < 3; ++a) {  // MinMaxBins::setAABB
+            mn[a] = tightBox.min[a];
+            binSize[a] = (tightBox.max[a] - tightBox.min[a]) / B;
+            invBinSize[a] = 1 / binSize[a];
+        }
+        auto computeIndex = [&](float pos, int a) {
+            return (uint32_t)std::min((float)(B - 1), std::max(0.0f, (pos - mn[a]) * invBinSize[a]));
+        };
+        std::vector<uint32_t> minBins(3 * (size_t)B, 0u), maxBins(3 * (size_t)B, 0u);
+        for (uint32_t id : ids)
+            for (int a = 0; a < 3; ++a) {
+                minBins[a * B + computeIndex(pb[id].min[a], a)]++;
+                maxBins[a * B + computeIndex(pb[id].max[a], a)]++;
+            }
+        // minimizeCost: no empty-space bonus
+        Float bestCost = std::numeric_limits<Float>::infinity();
+        int bestAxis = -1, leftBin = -1;
+        uint32_t bestLeft = 0, bestRight = 0;
+        {
+            Vec3 d = tightBox.max - tightBox.min;
+            const Float temp = 1.0f / (d[0] * d[1] + d[1] * d[2] + d[0] * d[2]);
+            int binIdx = 0;
+            for (int a = 0; a < 3; ++a) {
+                const int a1 = (a + 1) % 3, a2 = (a + 2) % 3;
+                const Float temp0 = (d[a1] * d[a2]) * temp, temp1 = (d[a1] + d[a2]) * temp;
+                uint32_t numLeft = 0, numRight = n;
+                Float leftWidth = 0, rightWidth = tightBox.max[a] - tightBox.min[a];
+                for (int i = 0; i < B - 1; ++i) {
+                    numLeft += minBins[binIdx];
+                    numRight -= maxBins[binIdx];
+                    leftWidth += binSize[a];
+                    rightWidth -= binSize[a];
+                    const Float pL = temp0 + temp1 * leftWidth, pR = temp0 + temp1 * rightWidth;
+                    const Float cost = traversalCost + queryCost * (pL * numLeft + pR * numRight);
+                    if (cost < bestCost) {
+                        bestCost = cost;
+                        bestAxis = a;
+                        bestLeft = numLeft;
+                        bestRight = numRight;
+                        leftBin = i;
+                    }
+                    binIdx++;
+                }
+                binIdx++;
+            }
+        }
+        if (bestCost == std::numeric_limits<Float>::infinity())  // collapsed bounds: the exact method takes over (:1817-1832)
+            return transition(nodeIdx, ids, nodeBox, depth, badRefines);
+        if (bestCost >= leafCost) {
+            if ((bestCost > 4 * leafCost && n < 16) || badRefines >= maxBadRefines) {
+                makeLeafIds(nodeIdx, ids);
+                return leafCost;
+            }
+            ++badRefines;
+        }
+        // MinMaxBins::partition
+        std::vector<uint32_t> left, right;
+        left.reserve(bestLeft);
+        right.reserve(bestRight);
+        AABB lb, rb;
+        lb.reset();
+        rb.reset();
+        for (uint32_t id : ids) {
+            const AABB &b = pb[id];
+            const int startIdx = (int)computeIndex(b.min[bestAxis], bestAxis), endIdx = (int)computeIndex(b.max[bestAxis], bestAxis);
+            if (endIdx <= leftBin) {
+                lb.expandBy(b);
+                left.push_back(id);
+            } else if (startIdx > leftBin) {
+                rb.expandBy(b);
+                right.push_back(id);
+            } else {
+                lb.expandBy(b);
+                rb.expandBy(b);
+                left.push_back(id);
+                right.push_back(id);
+            }
+        }
+        for (int a = 0; a < 3; ++a) {  // AABB::clip(m_aabb)
+            lb.min[a] = std::max(lb.min[a], tightBox.min[a]);
+            lb.max[a] = std::min(lb.max[a], tightBox.max[a]);
+            rb.min[a] = std::max(rb.min[a], tightBox.min[a]);
+            rb.max[a] = std::min(rb.max[a], tightBox.max[a]);
+        }
+        const Float pos = mn[bestAxis] + binSize[bestAxis] * (leftBin + 1);
+        lb.max[bestAxis] = std::min(lb.max[bestAxis], pos);
+        rb.min[bestAxis] = std::max(rb.min[bestAxis], pos);
+        std::vector<uint32_t>().swap(ids);
+        const size_t nodePosBeforeSplit = nodes.size() + 2, indexPosBeforeSplit = indices.size();
+        const uint32_t leftIdx = (uint32_t)nodes.size();
+        nodes.push_back(KDNode());
+        nodes.push_back(KDNode());
+        nodes[nodeIdx].a = ((leftIdx - nodeIdx) << 2) | (uint32_t)bestAxis;
+        nodes[nodeIdx].split = pos;
+        AABB child = nodeBox;
+        child.max[bestAxis] = pos;
+        const Float leftCost = buildMinMax(leftIdx, left, child, lb, depth + 1, badRefines);
+        child.min[bestAxis] = pos;
+        child.max[bestAxis] = nodeBox.max[bestAxis];
+        const Float rightCost = buildMinMax(leftIdx + 1, right, child, rb, depth + 1, badRefines);
+        const Float finalCost = innerCost(nodeBox, bestAxis, pos, leftCost, rightCost);
+        if (finalCost < leafCost) return finalCost;
+        retract(nodeIdx, nodePosBeforeSplit - 2, indexPosBeforeSplit);
+        return leafCost;
+    }
+
+    // Retraction (m_retract, gkdtree.h:1910-1921 / 2385-2394): in the end splitting did not reduce the cost. Tear up everything below
+    // the node and make it a leaf over the primitives its subtree's leaves reference (createLeafAfterRetraction, :1665-1699: the
+    // index entries written since the split, sorted, without duplicates).
+    void retract(uint32_t nodeIdx, size_t nodePos, size_t indexPos) {
+        nodes.resize(nodePos);
+        std::sort(indices.begin() + indexPos, indices.end());
+        indices.erase(std::unique(indices.begin() + indexPos, indices.end()), indices.end());
+        nodes[nodeIdx].a = 0x80000000u | (uint32_t)indexPos;
+        nodes[nodeIdx].end = (uint32_t)indices.size();
+        ++retractedSplits;
+    }
+
+    // the final cost of an inner node from its children's (gkdtree.h:2363-2370), same arithmetic as sahCost
+    ORC_NO_CONTRACT Float innerCost(const AABB &box, int axis, Float split, Float leftCost, Float rightCost) const {
+        Vec3 d = box.max - box.min;
+        int a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
+        const Float temp = 1.0f / (d[0] * d[1] + d[1] * d[2] + d[0] * d[2]);
+        const Float temp0 = (d[a1] * d[a2]) * temp, temp1 = (d[a1] + d[a2]) * temp;
+        const Float pL = temp0 + temp1 * (split - box.min[axis]);
+        const Float pR = temp0 + temp1 * (box.max[axis] - split);
+        return traversalCost + (pL * leftCost + pR * rightCost);
+    }
+
+    // returns the node's cost, as buildTreeMinMax / buildTreeSAH do (the parent's retraction decision needs it)
+    Float buildNode(uint32_t nodeIdx, std::vector<Item> &prims, const AABB &box, int depth, uint32_t badRefines, bool exactStage) {
         uint32_t n = (uint32_t)prims.size();
+        Float leafCost = n * queryCost;
         if (n <= stopPrims || depth >= maxDepth) {  // gkdtree.h:1797-1800
             makeLeaf(nodeIdx, prims);
-            return;
+            return leafCost;
         }
         Float bestCost = std::numeric_limits<Float>::infinity(), bestSplit = 0;
         int bestAxis = -1;
         bool bestPlanarLeft = true;
-        const bool exact = n <= exactPrimThreshold;
+        const bool exact = true;  // buildTreeSAH and its recursion; the min-max stage is buildMinMax below
 
-        if (exact && !exactStage && clipFn) {
+        if (!exactStage && clipFn) {
             // passing from min-max binning to the O(n log n) builder: clip every primitive to the node (createEventList,
             // gkdtree.h:1551-1592); primitives whose clipped bounds are invalid or have no area drop out
             std::vector<Item> kept;
@@ -356,52 +533,14 @@ private:
             }
             prims.swap(kept);
             n = (uint32_t)prims.size();
+            leafCost = n * queryCost;  // buildTreeSAH starts over with the clipped primitive count (gkdtree.h:1958)
             if (n <= stopPrims) {
                 makeLeaf(nodeIdx, prims);
-                return;
+                return leafCost;
             }
         }
 
-        if (!exact) {
-            // min-max binning (gkdtree.h:1792-1925): bins over the tight bounds of the node
-            AABB tight;
-            for (const Item &it : prims) {
-                const AABB &b = it.box;
-                for (int i = 0; i < 3; ++i) {
-                    tight.min[i] = std::min(tight.min[i], std::max(b.min[i], box.min[i]));
-                    tight.max[i] = std::max(tight.max[i], std::min(b.max[i], box.max[i]));
-                }
-            }
-            std::vector<uint32_t> minBins(minMaxBins), maxBins(minMaxBins);
-            for (int axis = 0; axis < 3; ++axis) {
-                Float lo = tight.min[axis], hi = tight.max[axis];
-                if (!(hi > lo)) continue;
-                std::fill(minBins.begin(), minBins.end(), 0u);
-                std::fill(maxBins.begin(), maxBins.end(), 0u);
-                Float invBin = (Float)minMaxBins / (hi - lo);
-                for (const Item &it : prims) {
-                    const AABB &b = it.box;
-                    int i0 = std::min((int)minMaxBins - 1, std::max(0, (int)((std::max(b.min[axis], lo) - lo) * invBin)));
-                    int i1 = std::min((int)minMaxBins - 1, std::max(0, (int)((std::min(b.max[axis], hi) - lo) * invBin)));
-                    minBins[i0]++;
-                    maxBins[i1]++;
-                }
-                uint32_t nL = 0, nR = n;
-                for (uint32_t i = 0; i + 1 < minMaxBins; ++i) {
-                    nL += minBins[i];
-                    nR -= maxBins[i];
-                    Float split = lo + (Float)(i + 1) * (hi - lo) / (Float)minMaxBins;
-                    if (!(split > box.min[axis] && split < box.max[axis])) continue;
-                    Float c = sahCost(box, axis, split, nL, nR);
-                    if (c < bestCost) {
-                        bestCost = c;
-                        bestAxis = axis;
-                        bestSplit = split;
-                        bestPlanarLeft = true;
-                    }
-                }
-            }
-        } else {
+        {
             // exact sweep over sorted edge events (gkdtree.h:1954-2405)
             std::vector<Event> ev;
             ev.reserve(2 * n);
@@ -431,7 +570,7 @@ private:
                         Float cL = sahCost(box, axis, pos, nL + pPlanar, nR);
                         Float cR = sahCost(box, axis, pos, nL, nR + pPlanar);
                         if (cL < bestCost || cR < bestCost) {  // planar prims to the cheaper side (:2050-2078)
-                            bestPlanarLeft = cL <= cR;
+                            bestPlanarLeft = cL < cR;  // a tie goes to the right (gkdtree.h:2064-2074)
                             bestCost = std::min(cL, cR);
                             bestAxis = axis;
                             bestSplit = pos;
@@ -442,15 +581,14 @@ private:
             }
         }
 
-        Float leafCost = n * queryCost;
         if (bestAxis < 0) {
             makeLeaf(nodeIdx, prims);
-            return;
+            return leafCost;
         }
         if (bestCost >= leafCost) {  // "bad refines", gkdtree.h:1835-1843 / 2105-2112
             if ((bestCost > 4 * leafCost && n < 16) || badRefines >= maxBadRefines) {
                 makeLeaf(nodeIdx, prims);
-                return;
+                return leafCost;
             }
             ++badRefines;
         }
@@ -481,16 +619,21 @@ private:
         }
         if (left.size() == n && right.size() == n) {  // no progress at all
             makeLeaf(nodeIdx, prims);
-            return;
+            return leafCost;
         }
         std::vector<Item>().swap(prims);
+        const size_t nodePosBeforeSplit = nodes.size(), indexPosBeforeSplit = indices.size();
         uint32_t leftIdx = (uint32_t)nodes.size();
         nodes.push_back(KDNode());
         nodes.push_back(KDNode());
         nodes[nodeIdx].a = ((leftIdx - nodeIdx) << 2) | (uint32_t)bestAxis;
         nodes[nodeIdx].split = bestSplit;
-        buildNode(leftIdx, left, lb, depth + 1, badRefines, exact);
-        buildNode(leftIdx + 1, right, rb, depth + 1, badRefines, exact);
+        const Float leftCost = buildNode(leftIdx, left, lb, depth + 1, badRefines, exact);
+        const Float rightCost = buildNode(leftIdx + 1, right, rb, depth + 1, badRefines, exact);
+        const Float finalCost = innerCost(box, bestAxis, bestSplit, leftCost, rightCost);
+        if (finalCost < leafCost) return finalCost;
+        retract(nodeIdx, nodePosBeforeSplit, indexPosBeforeSplit);
+        return leafCost;
     }
 };
 
