@@ -269,7 +269,10 @@ def run_reference(args):
                    "parallelism": "%d host threads, 32x32 tiles (imageproc.cpp:27-78)" % cores},
         "mrays_per_sec": rays / t / 1e6,
         "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": cores, "kind": "port", "sample": sample,
-                         "kd_traversal_per_ray": cpu.kd_bytes_per_ray()},
+                         "kd_traversal_per_ray": cpu.kd_bytes_per_ray(),
+                         "note": "kind = port because the step is a GUIDED training iteration and the reference snapshot contains no guided "
+                                 "integrator (SURVEY.md F1); the reference itself, compiled from its sources into oracle/_ref, renders the "
+                                 "same scene unguided in `reference_unguided`, next to the port doing the same"},
         "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "reference_unguided": reference_unguided(args.workload, cores, args.ref_seconds),
     }
