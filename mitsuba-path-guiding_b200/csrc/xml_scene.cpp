@@ -1285,9 +1285,32 @@ struct Loader {
         }
     }
 
+    // The tag set of the reference's scene handler (scenehandler.cpp:70-107). A tag outside it is the reference's "Unhandled tag"
+    // error (:263-266); a tag inside it that this path has no use for -- textures, subsurface models, animated transforms, blackbody
+    // spectra -- is refused by name: an element that is skipped would silently render a different scene (a <texture> child of a
+    // BSDF used to leave the default reflectance in place).
+    void checkTags(const XmlNode &n) {
+        static const char *handled[] = {"scene", "shape", "sampler", "film", "integrator", "sensor", "emitter", "medium", "volume", "phase",
+                                        "bsdf", "rfilter", "ref", "integer", "float", "boolean", "string", "translate", "rotate", "lookat",
+                                        "scale", "matrix", "point", "vector", "rgb", "srgb", "spectrum", "transform", "include", "alias",
+                                        "default"};
+        static const char *refused[] = {"texture", "subsurface", "animation", "blackbody", "null"};
+        bool ok = false;
+        for (const char *t : handled) ok = ok || n.tag == t;
+        if (!ok) {
+            for (const char *t : refused)
+                if (n.tag == t)
+                    fail("<" + n.tag + (n.has("name") ? " name=\"" + n.get("name") + "\"" : "") + (n.has("type") ? " type=\"" + n.get("type") + "\"" : "") +
+                         ">: this element is not supported on the accelerated path");
+            fail("Unhandled tag \"" + n.tag + "\" encountered!");
+        }
+        for (auto &c : n.children) checkTags(*c);
+    }
+
     void parseScene(const XmlNode &root) {
         if (root.tag != "scene") fail("the root element must be <scene>");
         if (!root.has("version")) fail("The scene is missing a version attribute!");  // scenehandler.cpp:228-233
+        checkTags(root);
         b200pg_integrator_params_default(&H.xmlParams);
         haveSensor = haveIntegrator = false;
         parseChildren(root);

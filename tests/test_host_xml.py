@@ -461,3 +461,19 @@ def test_serialized_loader_and_corrupt_files(api, pkg, tmp_path):
     badidx = one(head + struct.pack("<QQ", 3, 1) + np.zeros(9, "<f4").tobytes() + np.array([0, 1, 7], "<u4").tobytes(), "badidx.serialized")
     with pytest.raises(api.B200pgError, match="index out of range"):
         api.Scene.load_xml(_mesh_xml(tmp_path, body % (badidx, 0)))
+
+
+def test_unsupported_and_unknown_elements_are_refused(api, tmp_path):
+    """scenehandler.cpp:70-107 is the tag set; a tag outside it is the reference's "Unhandled tag" error, one inside it that
+    this path cannot honour (a texture, a subsurface model, an animated transform, a blackbody spectrum) is refused by name --
+    never skipped: a <texture name="reflectance"> that is skipped leaves the default reflectance and renders another scene."""
+    body = '<shape type="rectangle">%s<emitter type="area"><rgb name="radiance" value="1"/></emitter></shape>'
+    for inner, word in (('<bsdf type="diffuse"><texture name="reflectance" type="checkerboard"/></bsdf>', 'texture name="reflectance"'),
+                        ('<subsurface type="dipole"/>', "subsurface"),
+                        ('<bsdf type="diffuse"><blackbody name="reflectance" temperature="5000K"/></bsdf>', "blackbody"),
+                        ('<animation name="toWorld"><transform time="0"><translate x="1"/></transform></animation>', "animation"),
+                        ('<bsdf type="diffuse"><colour name="reflectance" value="1"/></bsdf>', "Unhandled tag")):
+        path = tmp_path / "s.xml"
+        path.write_text(_scene(body % inner).replace("$spp", "4"))
+        with pytest.raises(api.B200pgError, match=word):
+            api.Scene.load_xml(str(path))
