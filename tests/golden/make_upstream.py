@@ -48,6 +48,32 @@ def mesh_inputs(pkg, rs):
     return dict(pos=pos, rays=rays, rays2=r2, rays3=r3, pixel=pix, sample=smp)
 
 
+def light_cases(pkg):
+    """Scenes that exercise the emitter code paths: a rectangle light and the same light as a two-triangle mesh over a diffuse
+    floor (shapes without a BSDF of their own), two lights with unequal sampling weights, the furnace with a glass cube."""
+    from transport_cases import form_factor_scene, furnace_scene
+
+    S = pkg.scenes
+
+    def two_lights():
+        sb = S.SceneBuilder(24, 24, spp=1)
+        X = (1, 0, 0)
+        sb.rectangle([S.scale(50, 50, 1), S.rotate(X, -90.0)], bsdf=sb.diffuse((0.5, 0.5, 0.5)))
+        for (hx, hz), c, L, w in [((0.4, 0.3), (0.0, 1.2, 0.0), (4.0, 4.0, 4.0), 1.0), ((0.2, 0.6), (0.9, 2.0, -0.5), (1.0, 9.0, 2.0), 3.5)]:
+            sb.rectangle([S.scale(hx, hz, 1), S.rotate(X, 90.0), S.translate(*c)], bsdf=-1, radiance=L)
+            sb.emitters[-1]["weight"] = w
+        sb.set_camera((3.0, 1.0, 2.5), (0.2, 0.0, 0.1), (0, 1, 0), 30.0)
+        return sb
+
+    return dict(light_rect=lambda: form_factor_scene(pkg, "rectangle")[0], light_mesh=lambda: form_factor_scene(pkg, "trimesh")[0],
+                two_lights=two_lights, furnace_glass=lambda: furnace_scene(pkg, glass=True)[0])
+
+
+def light_samples(sb, n=3000):
+    rng = np.random.RandomState(77)
+    return rng.randint(0, sb.width * sb.height, n).astype(np.uint32), rng.randint(0, 1000, n).astype(np.uint32)
+
+
 def generate(pkg, ref_lib, gold):
     """{key: array}: the reference's outputs, keys '<case>/<name>'."""
     out = {}
@@ -77,6 +103,10 @@ def generate(pkg, ref_lib, gold):
             d, dist, pdf, val = rs.emitter_sample(refp, refn, u)
             out.update({name + "/em_u": u, name + "/em_ref": refp, name + "/em_refn": refn, name + "/em_d": d, name + "/em_dist": dist,
                         name + "/em_pdf": pdf, name + "/em_value": val, name + "/em_pdf_query": rs.emitter_pdf(refp, refn, d)})
+    for name, make in light_cases(pkg).items():
+        sb = make()
+        pix, smp = light_samples(sb)
+        out[name + "/radiance"] = ref_lib.RefScene(sb).radiance(mg.params(pkg, max_depth=-1 if name == "furnace_glass" else 3), pix, smp)[0]
     sb, idx = bsdf_scene()
     rs = ref_lib.RefScene(sb)
     for bname, i in idx.items():
