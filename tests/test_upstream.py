@@ -278,20 +278,6 @@ def test_gpu_traversal_and_radiance_match_the_reference(name, pkg, api, up, gold
 
 
 @gpu
-def test_gpu_emitter_paths_match_the_reference(pkg, api, up):
-    """Rectangle and mesh area lights over shapes with default BSDFs, two lights with unequal sampling weights, the furnace with a
-    glass cube (unbounded depth, Russian roulette, delta lobes): Li per camera sample against the reference's."""
-    for name, make in mu.light_cases(pkg).items():
-        sb = make()
-        pix, smp = mu.light_samples(sb)
-        it = api.Integrator(api.Scene.from_builder(sb), mg.params(pkg, max_depth=-1 if name == "furnace_glass" else 3))
-        # 3000 samples: a handful of flipped decisions (a light hit instead of the floor) moves the mean by a per cent
-        # (the glass furnace runs unbounded depth through total-internal-reflection chains: more decisions per path to flip)
-        check_radiance(it.k_radiance(pix, smp), up[name + "/radiance"], 1.5e-2 if name == "furnace_glass" else 6e-3, mean_tol=3e-2)
-        it.close()
-
-
-@gpu
 def test_gpu_film_matches_the_reference(pkg, api, up, gold):
     g = gold["cornell"]
     it = api.Integrator(api.Scene.from_builder(mg.cases(pkg)["cornell"]()), mg.params(pkg))
@@ -344,3 +330,17 @@ def test_gpu_medium_matches_the_reference(pkg, api, up, gold):
     assert (rel_err(t[m], to[m]) > 1e-5).mean() < 2e-3
     assert (tro != tr).mean() < 2e-3
     it.close()
+
+
+@gpu
+def test_gpu_emitter_paths_match_the_reference(pkg, api, up):
+    """Rectangle and mesh area lights over shapes with default BSDFs, two lights with unequal sampling weights, the furnace with a
+    glass cube (unbounded depth, Russian roulette, delta lobes): Li per camera sample against the reference's."""
+    for name, make in mu.light_cases(pkg).items():
+        sb = make()
+        pix, smp = mu.light_samples(sb)
+        it = api.Integrator(api.Scene.from_builder(sb), mg.params(pkg, max_depth=-1 if name == "furnace_glass" else 3))
+        # 3000 samples: a handful of flipped decisions (a light hit instead of the floor) moves the mean by a per cent
+        # (the glass furnace runs unbounded depth through total-internal-reflection chains: more decisions per path to flip)
+        check_radiance(it.k_radiance(pix, smp), up[name + "/radiance"], 1.5e-2 if name == "furnace_glass" else 6e-3, mean_tol=3e-2)
+        it.close()
