@@ -84,6 +84,31 @@ def test_oracle_image_equals_the_reference_probe(fixture, pkg, oracle):
     assert relmse(img, probe[r0 + 3:r1 - 3]) <= 1e-3 * probe_relmse  # measured 2e-8 on the whole image (float16 probe: 1e-10 floor)
 
 
+def test_oracle_image_equals_the_reference_probe_on_the_caustic_scene(pkg, oracle):
+    """The same check on C2 (tests/golden/ref_c2.npz, the converged image the equal-time sweeps measure against): glass cube, small
+    shielded light, mostly indirect and caustic transport -- a band through the glass cube, 1024 samples per pixel, the oracle
+    port against the image the reference itself rendered from the same sample indices."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "ref_c2.npz"))
+    meta = json.loads(str(z["meta"]))
+    if meta.get("probe_rendered_by") != "reference":
+        pytest.skip("ref_c2.npz predates the reference build")
+    probe, probe_relmse = z["probe"].astype(np.float32), float(z["probe_relmse"])
+    from b200pg import api
+    from oracle_lib import develop
+
+    sb = pkg.scenes.cornell_caustic(512, 512, spp=64)
+    p = api.default_params()
+    p.max_depth = 8
+    r0, r1 = 320, 384
+    acc = np.zeros((512, 512, 5), np.float64)
+    sc = oracle.scene(sb)
+    for s in range(0, 1024, 128):
+        acc += sc.render(p, s, 128, rows=(r0, r1))[0]
+    img = develop(acc)[r0 + 3:r1 - 3]
+    # a caustic sample carries a thousand times the mean: one flipped decision in 60 M paths is visible at this level
+    assert relmse(img, probe[r0 + 3:r1 - 3]) <= 2e-2 * probe_relmse
+
+
 @pytest.mark.gpu
 def test_gpu_image_matches_converged_oracle_render(fixture, pkg):
     from b200pg import api
