@@ -2,7 +2,7 @@
 at C1). Run once in the build container (CPU only, ~30 min on 8 cores); the result is committed as a fixture under
 tests/golden/ because the GPU box has neither the time nor the reason to re-render it.
 
-usage: make_reference.py [c1|c2] [ref_spp] [probe_spp] [threads] [oracle|reference] [keep-ref]
+usage: make_reference.py [c1|c2|c3] [ref_spp] [probe_spp] [threads] [oracle|reference] [keep-ref]
   oracle     the images are rendered by the oracle port (oracle/oracle_pt.cpp)
   reference  the images are rendered by the REFERENCE ITSELF: ProgressiveMonteCarloIntegrator::render of the libraries that
              oracle/Makefile.ref compiles from /root/reference, with the replay sampler of oracle/ref_harness handing it the
@@ -55,10 +55,13 @@ def main():
         sb = pkg.scenes.cornell_box(512, 512, spp=64)
     elif name == "c2":
         sb = pkg.scenes.cornell_caustic(512, 512, spp=64)
+    elif name == "c3":  # the medium scene at a quarter of the bench size, 64^3 grid (ProgressiveVolumetricPathTracer)
+        sb = pkg.scenes.cornell_medium(256, 256, spp=64, res=64)
     else:
         raise SystemExit("unknown scene")
     p = api.default_params()
     p.max_depth = 8
+    p.volumetric = 1 if name == "c3" else 0
     if impl == "reference":
         import ref_lib
 
